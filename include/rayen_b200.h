@@ -1,0 +1,142 @@
+/*
+ * rayen_b200.h -- C ABI of the B200-native RAYEN feasibility layer (librayen_b200.so).
+ *
+ * The reference (leggedrobotics/rayen @ 2f007f7c) is pure Python/PyTorch and has no FFI layer of
+ * its own; the boundary it exposes is the Python class API (rayen/constraint_module.py:17-533).
+ * This header is the thin C boundary that the Python drop-in (rayen_b200/constraint_module.py)
+ * binds with ctypes.  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every tensor, the library owns only the plan;
+ *   - device pointers unless the name says "host"; dense row-major; float32 compute ("f32");
+ *   - every call returns 0 on success, a negative RAYEN_ERR_* code, or a positive cudaError_t;
+ *     nothing throws, exits or synchronises (launch-and-return on the given stream), except the
+ *     *_host_* entry points, which synchronise the stream before returning;
+ *   - a plan is immutable after creation => re-entrant across host threads and streams;
+ *   - rayen_last_error() returns a thread-local message for the last failing call.
+ */
+#ifndef RAYEN_B200_H
+#define RAYEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAYEN_ABI_VERSION 3
+
+/* error codes (negative); positive return values are cudaError_t */
+#define RAYEN_OK 0
+#define RAYEN_ERR_BAD_ARGUMENT (-1)
+#define RAYEN_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels cover (n > 32, LMI size > 32) */
+#define RAYEN_ERR_ABI (-3)
+#define RAYEN_ERR_NO_DEVICE (-4)
+
+/* which scale step follows kappa: reference constraint_module.py:468-474 (RAYEN), :460-466 (RAYEN_old) */
+#define RAYEN_MODE_RAYEN 0     /* alpha = min(1/kappa, ||v||);       v has n columns            */
+#define RAYEN_MODE_RAYEN_OLD 1 /* alpha = 1/(exp(beta)+kappa);       v has n+1 columns (beta last) */
+
+/* family tags stored in the upper 8 bits of the `active` output; low 24 bits = constraint index */
+#define RAYEN_FAM_NONE 0
+#define RAYEN_FAM_LINEAR 1
+#define RAYEN_FAM_QUAD 2
+#define RAYEN_FAM_SOC 3
+#define RAYEN_FAM_LMI 4
+
+/*
+ * Packed, z-space constant block of one feasible set ("plan"), built once on the host by
+ * rayen_b200/plan.py from the buffers the reference registers in ConstraintModule.__init__
+ * (constraint_module.py:38 D, :43-52 H/L, :59-74 buffers, :99-122 phi/delta).  All offsets are in
+ * float32 words from `blob` and are multiples of 4 (16-byte aligned sections).
+ *
+ *   np      n rounded up to 4, 8, 16 or 32: the register row length of a direction u
+ *   LIN     m_pad/4 chunks of 4 rows; chunk c at off_lin + c*lin_chunk_stride;
+ *           word [kk*16 + i*4 + e] = D[4c+i][4kk+e]           (D = A_p / (b_p - A_p z0), zero padded)
+ *   QUAD    item q at off_quad + q*quad_stride: phi_z[np], then the upper-triangular factor G
+ *           (G'G = N' Delta N) row by row, row i holding columns 4*floor(i/4) .. np-1
+ *   SOC     item j at off_soc + j*soc_stride: c_z[np], h[np] (h = M_z' beta - tau c_z), the
+ *           triangular factor R (R'R = M_z' M_z) packed like G, then {A = tau^2 - beta'beta, 0,0,0}
+ *   NMAT    k rows of N (= NA_E), row stride np+4 (absent when N is the identity)
+ *   Y0      y0 = N z0 + yp, k_pad words
+ *   LMI     F~z_a = sum_i N[i][a] * (-L' F_i L), a < n, each rp x rp (rp = r rounded up to 4, 8, 16
+ *           or 32, zero padded), stored [a][row i][lane q][slot t] with column j = q + (rp/4)*t
+ */
+typedef struct RayenPlanDesc {
+  int32_t abi_version; /* must be RAYEN_ABI_VERSION */
+  int32_t n;           /* dimension of the subspace (columns of v)  */
+  int32_t k;           /* dimension of the ambient space (columns of y) */
+  int32_t np;
+  int32_t k_pad;
+  int32_t m;     /* rows of D (before padding) */
+  int32_t m_pad; /* multiple of 4 */
+  int32_t n_quad;
+  int32_t n_soc;
+  int32_t lmi_r;  /* 0 = no LMI */
+  int32_t lmi_rp; /* 4, 8, 16 or 32 */
+  int32_t n_is_identity;
+  int32_t lin_chunk_stride;
+  int32_t quad_stride;
+  int32_t soc_stride;
+  int32_t reserved0;
+  int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_lmi;
+  int64_t blob_words;
+  const float* blob; /* host pointer, blob_words floats */
+} RayenPlanDesc;
+
+typedef struct rayen_plan rayen_plan_t;
+
+int rayen_abi_version(void);
+const char* rayen_last_error(void);
+
+/* Copies the constant block to `device` (one cudaMalloc + cudaMemcpy) and selects the kernels.
+ * Replaces the .to(device) of the reference's registered buffers. */
+int rayen_plan_create(const RayenPlanDesc* desc, int device, rayen_plan_t** out);
+void rayen_plan_destroy(rayen_plan_t* plan);
+
+/* Optional launch tuning for sweeps: samples per thread (1, 2 or 4; 0 = auto) and lanes per sample
+ * (power of two <= 32; 0 = auto) of the linear/quadratic/SOC kernel. */
+int rayen_plan_set_tuning(rayen_plan_t* plan, int samples_per_thread, int lanes_per_sample);
+
+/*
+ * Forward: replaces forwardForRAYEN / forwardForRAYENOld + computeKappa + getyFromz
+ * (constraint_module.py:351-474, :512-514).
+ *   v      [B, ldv]  (ldv >= n, or >= n+1 for RAYEN_OLD), y [B, k]
+ *   kappa  [B] and active [B] receive kappa and (family << 24 | index) of the binding constraint;
+ *          they are what backward needs.  They may be NULL only for plans without an LMI.
+ */
+int rayen_forward_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, float* y, float* kappa,
+                      int32_t* active, int64_t B, int mode, void* cuda_stream);
+
+/*
+ * Backward: the closed form of what autograd derives from the reference forward.
+ *   gy [B, k], kappa/active from the forward call on the same v, gv [B, ldv_g] (ldv_g = n or n+1).
+ */
+int rayen_backward_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, const float* gy,
+                       const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
+                       int mode, void* cuda_stream);
+
+/* Host-buffer variants (the end-to-end path): host->device copies, the kernels, device->host
+ * copies, all on `cuda_stream`, which is synchronised before returning.  Host buffers should be
+ * pinned.  `workspace` is a device buffer of rayen_host_workspace_bytes(plan, B) bytes. */
+int64_t rayen_host_workspace_bytes(const rayen_plan_t* plan, int64_t B);
+int rayen_forward_backward_host_f32(const rayen_plan_t* plan, const float* v_host, const float* gy_host,
+                                    float* y_host, float* gv_host, int64_t B, void* workspace,
+                                    void* cuda_stream);
+
+/* Number of kernels this library has launched in the calling process (all plans, all threads). */
+int64_t rayen_launch_count(void);
+
+/* Introspection for tests / bench: static shared memory, registers, and chosen launch geometry. */
+typedef struct RayenKernelInfo {
+  int32_t regs_lqs_fwd, regs_lqs_bwd, regs_lmi_fwd, regs_lmi_bwd;
+  int32_t smem_lqs_bytes, smem_lmi_bytes;
+  int32_t sm_count;
+  int32_t reserved;
+} RayenKernelInfo;
+int rayen_plan_kernel_info(const rayen_plan_t* plan, RayenKernelInfo* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYEN_B200_H */

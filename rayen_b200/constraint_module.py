@@ -1,0 +1,212 @@
+"""``ConstraintModule``: drop-in for the reference layer, running on hand-written sm_100a kernels.
+
+Mirrors ``rayen/constraint_module.py`` of leggedrobotics/rayen @ 2f007f7c for the methods on the
+ray-shooting path:
+
+* constructor signature, attributes (``cs k n method mapper dim_after_map``) and the registered buffer
+  names / shapes / dtypes of reference constraint_module.py:18-74 and :99-122, so reference
+  ``state_dict``s load;
+* ``forward(x)``: flatten -> ``mapper`` -> ray shooting -> ``[B, k, 1]`` (reference :520-533);
+* ``getDimAfterMap gety0 getyFromz getzFromy`` (reference :506-518);
+* ``method='RAYEN'`` (reference :468-474) and ``method='RAYEN_old'`` (reference :460-466).
+
+What is different underneath: the chain of torch ops in ``computeKappa`` (reference :351-458) and the
+autograd graph it records are replaced by ``rayen_forward_f32`` / ``rayen_backward_f32`` of
+``librayen_b200.so`` (include/rayen_b200.h), called through ctypes on the current CUDA stream with a
+``torch.autograd.Function`` that saves only ``(v, kappa, active)``.  The other methods of the reference
+(UU, Bar, PP, UP, DC3) are comparison baselines outside this package's scope and raise
+``NotImplementedError``.  There is no CPU path: a CPU input raises ``RuntimeError``.
+"""
+import ctypes
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi, plan as plan_mod, utils
+
+_SUPPORTED = ("RAYEN", "RAYEN_old")
+_BASELINES = ("UU", "Bar", "PP", "UP", "DC3")
+
+
+def _as_buffer(array_like):
+    """Same conversion as the reference's ``torch.Tensor(np_array)``: the default dtype at ctor time."""
+    arr = np.asarray(array_like, dtype=np.float64)
+    return torch.tensor(arr, dtype=torch.get_default_dtype())
+
+
+class _RayShoot(torch.autograd.Function):
+    """q:[B, n(+1)] -> y:[B, k] through the C ABI; backward is the closed form."""
+
+    @staticmethod
+    def forward(ctx, q, module):
+        if not q.is_cuda:
+            raise RuntimeError("rayen_b200.ConstraintModule runs on CUDA (sm_100a) only; move the model and its "
+                               "inputs to a B200 device. There is no CPU path.")
+        lib = _cabi.lib()
+        v = q.detach()
+        if v.dtype != torch.float32:
+            v = v.float()
+        if v.stride(1) != 1 or v.stride(0) < v.shape[1]:
+            v = v.contiguous()
+        B, cols = v.shape
+        k, mode = module.k, module._mode
+        dev_plan = module._device_plan(v.device)
+        y = torch.empty((B, k), dtype=torch.float32, device=v.device)
+        kappa = torch.empty((B,), dtype=torch.float32, device=v.device)
+        active = torch.empty((B,), dtype=torch.int32, device=v.device)
+        with torch.cuda.device(v.device):
+            stream = torch.cuda.current_stream(v.device).cuda_stream
+            rc = lib.rayen_forward_f32(dev_plan.handle, v.data_ptr(), v.stride(0) if B > 0 else cols, y.data_ptr(),
+                                       kappa.data_ptr(), active.data_ptr(), B, mode, ctypes.c_void_p(stream))
+        _cabi.check(rc, "rayen_forward_f32")
+        ctx.module = module
+        ctx.in_dtype = q.dtype
+        ctx.save_for_backward(v, kappa, active)
+        module._last = (kappa, active)
+        return y if q.dtype == torch.float32 else y.to(q.dtype)
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _cabi.lib()
+        v, kappa, active = ctx.saved_tensors
+        module = ctx.module
+        gy = gy.detach()
+        if gy.dtype != torch.float32:
+            gy = gy.float()
+        gy = gy.contiguous()
+        B, cols = v.shape
+        gv = torch.empty((B, cols), dtype=torch.float32, device=v.device)
+        dev_plan = module._device_plan(v.device)
+        with torch.cuda.device(v.device):
+            stream = torch.cuda.current_stream(v.device).cuda_stream
+            rc = lib.rayen_backward_f32(dev_plan.handle, v.data_ptr(), v.stride(0) if B > 0 else cols, gy.data_ptr(),
+                                        kappa.data_ptr(), active.data_ptr(), gv.data_ptr(), cols, B, module._mode,
+                                        ctypes.c_void_p(stream))
+        _cabi.check(rc, "rayen_backward_f32")
+        return (gv if ctx.in_dtype == torch.float32 else gv.to(ctx.in_dtype)), None
+
+
+class ConstraintModule(nn.Module):
+    def __init__(self, cs, input_dim=None, method="RAYEN", create_map=True, args_DC3=None):
+        super().__init__()
+        self.method = method
+        if method in _BASELINES:
+            raise NotImplementedError(
+                f"method='{method}' is one of the reference's comparison baselines (UU/Bar/PP/UP/DC3); "
+                "rayen_b200 implements the ray-shooting methods 'RAYEN' and 'RAYEN_old' only")
+        if method not in _SUPPORTED:
+            raise NotImplementedError
+        self.cs = cs
+        self.k = cs.k  # dimension of the ambient space
+        self.n = cs.n  # dimension of the embedded space
+        self._mode = _cabi.MODE_RAYEN if method == "RAYEN" else _cabi.MODE_RAYEN_OLD
+
+        # ---- buffers, same names / shapes as the reference (constraint_module.py:38-74)
+        D = cs.A_p / ((cs.b_p - cs.A_p @ cs.z0) @ np.ones((1, cs.n)))
+        all_P, all_q, all_r = utils.getAllPqrFromQcs(cs.qcs)
+        all_M, all_s, all_c, all_d = utils.getAllMscdFromSocs(cs.socs)
+        if cs.has_lmi_constraints:
+            all_F = [np.array(F, dtype=np.float64) for F in cs.lmic.all_F]
+            H = all_F[-1] + sum(cs.y0[i, 0] * all_F[i] for i in range(cs.lmic.dim()))
+            Hinv = np.linalg.inv(H)
+            self.register_buffer("mHinv", _as_buffer(-Hinv))
+            self.register_buffer("L", _as_buffer(np.linalg.cholesky(Hinv)))
+            # the reference accumulates H in place into its copy of all_F[-1] before registering it
+            all_F = all_F[:-1] + [H]
+        else:
+            all_F = []
+        self.register_buffer("D", _as_buffer(D))
+        for name, seq in (("all_P", all_P), ("all_q", all_q), ("all_r", all_r), ("all_M", all_M),
+                          ("all_s", all_s), ("all_c", all_c), ("all_d", all_d), ("all_F", all_F)):
+            self.register_buffer(name, _as_buffer(np.array(seq)) if len(seq) else torch.zeros(0))
+        for name in ("A_p", "b_p", "yp", "NA_E", "z0", "y0"):
+            self.register_buffer(name, _as_buffer(getattr(cs, name)))
+        if cs.has_quadratic_constraints:  # reference constraint_module.py:99-122
+            y0 = np.asarray(cs.y0, dtype=np.float64)
+            all_delta, all_phi = [], []
+            for P, q, r in zip(all_P, all_q, all_r):
+                w = y0.T @ P + q.T
+                level = float(0.5 * y0.T @ P @ y0 + q.T @ y0 + r)
+                sigma = 2.0 * level
+                all_phi.append(-w / sigma)
+                all_delta.append((w.T @ w - 2.0 * level * P) / sigma ** 2)
+            self.register_buffer("all_delta", _as_buffer(np.array(all_delta)))
+            self.register_buffer("all_phi", _as_buffer(np.array(all_phi)))
+
+        self.dim_after_map = self.n if method == "RAYEN" else self.n + 1
+        if create_map:
+            utils.verify(input_dim is not None, "input_dim needs to be provided")
+            self.mapper = nn.Linear(input_dim, self.dim_after_map)
+        else:
+            self.mapper = nn.Sequential()  # mapper does nothing
+
+        # host-side packed plan (float64 math, float32 block) and its per-GPU uploads
+        self._packed = plan_mod.build_plan_from_constraints(cs)
+        self._plans = {}
+        self._last = None
+
+    # ------------------------------------------------------------------ plan management
+    def _device_plan(self, device):
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        dev_plan = self._plans.get(index)
+        if dev_plan is None:
+            dev_plan = _cabi.DevicePlan(self._packed, index)
+            self._plans[index] = dev_plan
+        return dev_plan
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        self._repack_from_buffers()
+
+    def _repack_from_buffers(self):
+        """Rebuild the device plan from the registered buffers (after ``load_state_dict``)."""
+        g = lambda name: getattr(self, name).detach().cpu().double().numpy()
+        qcs = [(P, q, r) for P, q, r in zip(g("all_P"), g("all_q"), g("all_r"))] if self.all_P.numel() else []
+        socs = [(M, s, c, d) for M, s, c, d in zip(g("all_M"), g("all_s"), g("all_c"), g("all_d"))] \
+            if self.all_M.numel() else []
+        lmi = None
+        if self.all_F.numel():
+            allF = g("all_F")
+            y0 = g("y0")
+            constant = allF[-1] - np.einsum("a,aij->ij", y0[:, 0], allF[:-1])  # undo the H accumulation
+            lmi = [F for F in allF[:-1]] + [constant]
+        self._packed = plan_mod.build_plan(g("A_p"), g("b_p"), g("NA_E"), g("yp"), g("z0"), qcs, socs, lmi)
+        for dev_plan in self._plans.values():
+            dev_plan.close()
+        self._plans = {}
+
+    def set_tuning(self, samples_per_thread=0, lanes_per_sample=0, device=None):
+        """Override the launch geometry of the linear/quadratic/SOC kernel (0 = automatic)."""
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._device_plan(device).set_tuning(samples_per_thread, lanes_per_sample)
+
+    def last_kappa_and_active(self):
+        """(kappa[B], active[B]) of the most recent forward: active = family << 24 | constraint index."""
+        return self._last
+
+    # ------------------------------------------------------------------ reference helper methods
+    def getDimAfterMap(self):
+        return self.dim_after_map
+
+    def gety0(self):
+        return self.getyFromz(self.z0)
+
+    def getyFromz(self, z):
+        return self.NA_E @ z + self.yp
+
+    def getzFromy(self, y):
+        return self.NA_E.T @ (y - self.yp)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x):
+        # x: [B, numel_input_mapper, 1] (anything that views to [B, -1]), as in the reference
+        q = self.mapper(x.view(x.size(0), -1))
+        utils.verify(q.shape[1] == self.dim_after_map,
+                     f"the layer expects {self.dim_after_map} values per sample, got {q.shape[1]}")
+        if q.dtype == torch.float64 and not getattr(self, "_warned_f64", False):
+            warnings.warn("rayen_b200 computes in float32; float64 inputs are cast down and the result cast back")
+            self._warned_f64 = True
+        y = _RayShoot.apply(q, self)
+        return y.unsqueeze(2)

@@ -1,0 +1,629 @@
+// LMI family: kappa = relu(lambda_max(sum_a u_a F~z_a)), fused with the shift-and-scale step.
+//
+// The reference materialises S = einsum(F, rho), L'(-S)L and calls eigvalsh on [B,r,r]
+// (constraint_module.py:401-449).  Here the congruence is folded into the constants on the host and
+// one kernel does, per sample and without touching HBM in between:
+//   1. the contraction S~ = sum_a u_a F~z_a straight into registers,
+//   2. a Householder tridiagonalisation of S~ in registers,
+//   3. lambda_max of the tridiagonal matrix by parallel multisection on Sturm counts,
+//   4. (backward only) the eigenvector: twisted factorisation + back-transform through the
+//      reflectors, then d kappa/du_a = q' F~z_a q,
+//   5. the merge with the kappa of the other families and the scale step / the closed-form g_v.
+//
+// Layout: a matrix of padded size RP (4, 8, 16, 32) is owned by LPM = RP/4 consecutive lanes; lane q
+// keeps columns q, q+LPM, q+2LPM, q+3LPM (all RP rows) in registers: 4*RP floats.  Owning 4 columns
+// instead of 1 cuts the broadcast traffic of the two rank-1 vectors per Householder step (the LSU
+// bound of a column-per-lane layout) by 4x and gives every lane 4 independent FMA chains; the
+// interleaved ownership lets whole column slots drop out at compile time as the reduction proceeds.
+// A warp carries 32/LPM matrices.  Vectors that every lane of a matrix needs go through a small
+// per-matrix shared-memory scratch; sums go through width-LPM shuffles.
+#pragma once
+#include "common.cuh"
+
+namespace rayen {
+
+constexpr int kLmiThreads = 256;
+constexpr int kLmiMaxN = 32;
+
+template <int RP>
+struct LmiCfg {
+  static constexpr int LPM = RP / 4;             // lanes per matrix
+  static constexpr int MPW = 32 / LPM;           // matrices per warp
+  static constexpr int PPL = (LPM >= 8) ? 1 : 8 / LPM;  // Sturm points per lane: 8 points per round
+  static constexpr int ROUNDS = 8;               // 9^8 = 4.3e7 > 2^25
+  // scratch floats per matrix; the pad makes consecutive matrices start LPM (>= 4) banks apart so that
+  // neither the float4 broadcasts nor the scalar stores of the matrices of one warp collide
+  static constexpr int SCR = kLmiMaxN + 6 * RP + (LPM >= 4 ? LPM : 4);
+  static constexpr int NPL = kLmiMaxN / LPM;     // entries of an n-vector per lane
+};
+
+template <int LPM>
+__device__ __forceinline__ int group_or(int x) {
+#pragma unroll
+  for (int off = LPM >> 1; off > 0; off >>= 1) x |= __shfl_xor_sync(0xffffffffu, x, off);
+  return x;
+}
+
+// scratch layout (floats): [0,32) u | v | w | d | e | aux0 | aux1   (each RP long after u)
+template <int RP, bool WANT_GRAD, bool F_SMEM>
+struct LmiSolver {
+  using C = LmiCfg<RP>;
+  static constexpr int LPM = C::LPM;
+
+  float A[RP][4];
+  float* scr;
+  int q;         // lane within the matrix group
+  int grp_base;  // first lane of the group
+
+  __device__ __forceinline__ float* su() { return scr; }
+  __device__ __forceinline__ float* sv() { return scr + kLmiMaxN; }
+  __device__ __forceinline__ float* sw() { return scr + kLmiMaxN + RP; }
+  __device__ __forceinline__ float* sd() { return scr + kLmiMaxN + 2 * RP; }
+  __device__ __forceinline__ float* se() { return scr + kLmiMaxN + 3 * RP; }
+  __device__ __forceinline__ float* sx0() { return scr + kLmiMaxN + 4 * RP; }
+  __device__ __forceinline__ float* sx1() { return scr + kLmiMaxN + 5 * RP; }
+
+  // ---- 0. u = v / max(|v|, eps) into the scratch; returns |v|
+  __device__ __forceinline__ float load_direction(const float* __restrict__ vrow, int n, bool valid) {
+    float ss = 0.f;
+    float* u = su();
+    for (int a = q; a < kLmiMaxN; a += LPM) {
+      const float x = (valid && a < n) ? __ldg(vrow + a) : 0.f;
+      u[a] = x;
+      ss = fmaf(x, x, ss);
+    }
+    ss = group_sum<LPM>(ss);
+    const float s = sqrtf(ss);
+    const float inv = 1.0f / fmaxf(s, kNormEps);
+    for (int a = q; a < kLmiMaxN; a += LPM) u[a] *= inv;
+    __syncwarp();
+    return s;
+  }
+
+  // ---- 1. S~ = sum_a u_a F~z_a; F is [a][row][lane q][slot t], so a lane reads one float4 per row
+  __device__ __forceinline__ void contract(const float* __restrict__ F, int n) {
+#pragma unroll
+    for (int i = 0; i < RP; ++i)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) A[i][t] = 0.f;
+    const float* u = su();
+    const float* Fq = F + 4 * q;
+    for (int a = 0; a < n; ++a) {
+      const float ua = u[a];
+      const float* Fa = Fq + a * (RP * RP);
+#pragma unroll
+      for (int i = 0; i < RP; ++i) {
+        float4 f;
+        if constexpr (F_SMEM)
+          f = ld4(Fa + i * RP);
+        else
+          f = __ldg(reinterpret_cast<const float4*>(Fa + i * RP));
+        A[i][0] = fmaf(ua, f.x, A[i][0]);
+        A[i][1] = fmaf(ua, f.y, A[i][1]);
+        A[i][2] = fmaf(ua, f.z, A[i][2]);
+        A[i][3] = fmaf(ua, f.w, A[i][3]);
+      }
+    }
+  }
+
+  // ---- 2. Householder tridiagonalisation.  Afterwards sd()/se() hold the diagonal / sub-diagonal and,
+  //         if WANT_GRAD, row k of A holds this lane's part of reflector k.
+  template <int K>
+  __device__ __forceinline__ void householder_step(float (&dd)[4], float (&ee)[4]) {
+    constexpr int q1 = (K + 1) % LPM, t1 = (K + 1) / LPM;
+    float xo[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) xo[t] = (q + LPM * t > K) ? A[K][t] : 0.f;
+    const float xk1 = __shfl_sync(0xffffffffu, A[K][t1], grp_base + q1);
+    float loc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (q + LPM * t > K + 1) loc = fmaf(xo[t], xo[t], loc);
+    const float tail2 = group_sum<LPM>(loc);
+    const float sigma = fmaf(xk1, xk1, tail2);
+    const float rt = sqrtf(sigma);
+    const float alpha = (xk1 >= 0.f) ? -rt : rt;
+    const bool skip = !(tail2 > 0.f);  // column already tridiagonal (also covers zero padding)
+    const float tau = skip ? 0.f : 1.0f / fmaf(fabsf(xk1), rt, sigma);
+    const float ek = skip ? xk1 : alpha;
+    if (q == K % LPM) {
+      dd[K / LPM] = A[K][K / LPM];
+      ee[K / LPM] = ek;
+    }
+    float vo[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      vo[t] = xo[t];
+      if (q + LPM * t == K + 1) vo[t] = xk1 - alpha;
+      if (skip) vo[t] = 0.f;
+      sv()[q + LPM * t] = vo[t];
+    }
+    __syncwarp();
+    // p = tau * A v over the live rows (> K); slot t is live while it still has a column > K
+    constexpr int I4 = (K + 1) / 4;
+    float vr[RP];
+#pragma unroll
+    for (int i4 = I4; i4 < RP / 4; ++i4) {
+      const float4 x = ld4(sv() + 4 * i4);
+      vr[4 * i4 + 0] = x.x;
+      vr[4 * i4 + 1] = x.y;
+      vr[4 * i4 + 2] = x.z;
+      vr[4 * i4 + 3] = x.w;
+    }
+    float p[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = K + 1; i < RP; ++i)
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (LPM * t + LPM - 1 > K) p[t] = fmaf(A[i][t], vr[i], p[t]);
+    loc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      p[t] *= tau;
+      loc = fmaf(vo[t], p[t], loc);
+    }
+    const float Kc = 0.5f * tau * group_sum<LPM>(loc);
+    float wo[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      wo[t] = (q + LPM * t > K) ? fmaf(-Kc, vo[t], p[t]) : 0.f;
+      sw()[q + LPM * t] = wo[t];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i4 = I4; i4 < RP / 4; ++i4) {
+      const float4 x = ld4(sw() + 4 * i4);
+      const float wr[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        const int i = 4 * i4 + ii;
+        if (i > K) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (LPM * t + LPM - 1 > K) A[i][t] = fmaf(-vr[i], wo[t], fmaf(-wr[ii], vo[t], A[i][t]));
+        }
+      }
+    }
+    if constexpr (WANT_GRAD) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) A[K][t] = vo[t];
+    }
+    __syncwarp();  // scratch v/w are rewritten by the next step
+  }
+
+  template <int K>
+  __device__ __forceinline__ void householder_all(float (&dd)[4], float (&ee)[4]) {
+    if constexpr (K < RP - 2) {
+      householder_step<K>(dd, ee);
+      householder_all<K + 1>(dd, ee);
+    }
+  }
+
+  __device__ __forceinline__ void tridiagonalize() {
+    float dd[4] = {0.f, 0.f, 0.f, 0.f}, ee[4] = {0.f, 0.f, 0.f, 0.f};
+    householder_all<0>(dd, ee);
+    // trailing 2x2 block
+    constexpr int K2 = RP - 2, K1 = RP - 1;
+    if (q == K2 % LPM) {
+      dd[K2 / LPM] = A[K2][K2 / LPM];
+      ee[K2 / LPM] = A[K1][K2 / LPM];
+    }
+    if (q == K1 % LPM) {
+      dd[K1 / LPM] = A[K1][K1 / LPM];
+      ee[K1 / LPM] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      sd()[q + LPM * t] = dd[t];
+      se()[q + LPM * t] = ee[t];
+    }
+    __syncwarp();
+  }
+
+  // ---- 3. largest eigenvalue of the tridiagonal matrix, clipped at 0 (kappa = relu(lambda_max)).
+  // count(x) = #negative pivots of the LDL' of T - xI = #eigenvalues below x (quotient-form Sturm
+  // sequence with the usual pivmin guard); x is above the spectrum iff count == RP.
+  __device__ __forceinline__ float lambda_max_relu() {
+    float d[WANT_GRAD ? 1 : RP], e2[WANT_GRAD ? 1 : RP];
+    float dmax = -3.0e38f, hi = -3.0e38f, lo_g = 3.0e38f;
+    {
+      float eprev = 0.f;
+#pragma unroll
+      for (int i4 = 0; i4 < RP / 4; ++i4) {
+        const float4 dv = ld4(sd() + 4 * i4), ev = ld4(se() + 4 * i4);
+        const float da[4] = {dv.x, dv.y, dv.z, dv.w}, ea[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const float rad = fabsf(eprev) + fabsf(ea[ii]);
+          dmax = fmaxf(dmax, da[ii]);
+          hi = fmaxf(hi, da[ii] + rad);
+          lo_g = fminf(lo_g, da[ii] - rad);
+          if constexpr (!WANT_GRAD) {
+            d[4 * i4 + ii] = da[ii];
+            e2[4 * i4 + ii] = eprev * eprev;  // e2[i] couples rows i-1 and i
+          }
+          eprev = ea[ii];
+        }
+      }
+    }
+    const float scale = fmaxf(fmaxf(fabsf(hi), fabsf(lo_g)), 1e-30f);
+    const float pivmin = 1e-25f * scale;
+    float lo = fmaxf(dmax, 0.f);
+    hi = fmaf(1e-6f, scale, hi);
+    hi = fmaxf(hi, lo);  // whole spectrum <= 0: degenerate interval, the rounds below return lo = 0 (no early
+                         // exit: the shuffles below need every lane of the warp)
+    for (int round = 0; round < C::ROUNDS; ++round) {
+      const float h = (hi - lo) * (1.0f / 9.0f);
+      int bits = 0;
+#pragma unroll
+      for (int pp = 0; pp < C::PPL; ++pp) {
+        const int pt = q * C::PPL + pp;
+        const float x = fmaf(h, static_cast<float>(pt + 1), lo);
+        int neg = 0;
+        float piv = 1.f;
+        if constexpr (!WANT_GRAD) {
+#pragma unroll
+          for (int i = 0; i < RP; ++i) {
+            piv = (d[i] - x) - (i == 0 ? 0.f : e2[i] * __frcp_rn(piv));
+            if (fabsf(piv) < pivmin) piv = -pivmin;
+            neg += (piv < 0.f) ? 1 : 0;
+          }
+        } else {
+          float eprev = 0.f;
+          for (int i = 0; i < RP; ++i) {
+            const float di = sd()[i];
+            piv = (di - x) - (i == 0 ? 0.f : eprev * eprev * __frcp_rn(piv));
+            if (fabsf(piv) < pivmin) piv = -pivmin;
+            neg += (piv < 0.f) ? 1 : 0;
+            eprev = se()[i];
+          }
+        }
+        bits |= (neg == RP) ? (1 << pt) : 0;
+      }
+      const int mask = group_or<LPM>(bits) & 0xff;
+      const int first = mask ? (__ffs(mask) - 1) : 8;
+      const float new_lo = (first == 0) ? lo : fmaf(h, static_cast<float>(first), lo);
+      const float new_hi = (first == 8) ? hi : fmaf(h, static_cast<float>(first + 1), lo);
+      lo = new_lo;
+      hi = new_hi;
+    }
+    return 0.5f * (lo + hi);
+  }
+
+  // ---- 4. unit eigenvector of lambda (backward only): twisted factorisation of T - lambda I on one
+  // lane per matrix, then q = H_0 ... H_{RP-3} z with the reflectors kept in the dead rows of A.
+  __device__ __forceinline__ void eigenvector(float lam, float (&qo)[4]) {
+    static_assert(WANT_GRAD, "eigenvector needs the reflectors");
+    float* dp = sx0();
+    float* dm = sx1();
+    float* z = sv();
+    if (q == 0) {
+      const float* d = sd();
+      const float* e = se();
+      float scale = 0.f;
+      for (int i = 0; i < RP; ++i) scale = fmaxf(scale, fabsf(d[i]) + fabsf(e[i]));
+      const float tiny = fmaxf(1e-12f * scale, 1e-30f);
+      float piv = d[0] - lam;
+      for (int i = 0; i < RP; ++i) {
+        if (i > 0) piv = (d[i] - lam) - e[i - 1] * e[i - 1] / piv;
+        if (fabsf(piv) < tiny) piv = -tiny;
+        dp[i] = piv;
+      }
+      piv = d[RP - 1] - lam;
+      for (int i = RP - 1; i >= 0; --i) {
+        if (i < RP - 1) piv = (d[i] - lam) - e[i] * e[i] / piv;
+        if (fabsf(piv) < tiny) piv = -tiny;
+        dm[i] = piv;
+      }
+      int kt = 0;
+      float best = 3.0e38f;
+      for (int i = 0; i < RP; ++i) {
+        const float gam = fabsf(dp[i] + dm[i] - (d[i] - lam));
+        if (gam < best) {
+          best = gam;
+          kt = i;
+        }
+      }
+      z[kt] = 1.f;
+      float zi = 1.f, nrm = 1.f;
+      for (int i = kt; i > 0; --i) {
+        zi = -e[i - 1] * zi / dp[i - 1];
+        z[i - 1] = zi;
+        nrm = fmaf(zi, zi, nrm);
+      }
+      zi = 1.f;
+      for (int i = kt; i < RP - 1; ++i) {
+        zi = -e[i] * zi / dm[i + 1];
+        z[i + 1] = zi;
+        nrm = fmaf(zi, zi, nrm);
+      }
+      const float inv = rsqrtf(nrm);
+      for (int i = 0; i < RP; ++i) z[i] *= inv;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) qo[t] = z[q + LPM * t];
+    __syncwarp();
+    back_transform<RP - 3>(qo);
+  }
+
+  template <int K>
+  __device__ __forceinline__ void back_transform(float (&qo)[4]) {
+    if constexpr (K >= 0) {
+      float dot = 0.f, vv = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        dot = fmaf(A[K][t], qo[t], dot);
+        vv = fmaf(A[K][t], A[K][t], vv);
+      }
+      dot = group_sum<LPM>(dot);
+      vv = group_sum<LPM>(vv);
+      const float c = vv > 0.f ? 2.0f * dot / vv : 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) qo[t] = fmaf(-c, A[K][t], qo[t]);
+      back_transform<K - 1>(qo);
+    }
+  }
+
+  // d kappa/du_a = q' F~z_a q for the entries a = q + LPM*slot owned by this lane
+  __device__ __forceinline__ void eig_gradient(const float* __restrict__ F, int n, const float (&qo)[4],
+                                               float (&dk)[C::NPL]) {
+    float* qs = sw();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) qs[q + LPM * t] = qo[t];
+    __syncwarp();
+    float qa[RP];
+#pragma unroll
+    for (int i4 = 0; i4 < RP / 4; ++i4) {
+      const float4 x = ld4(qs + 4 * i4);
+      qa[4 * i4 + 0] = x.x;
+      qa[4 * i4 + 1] = x.y;
+      qa[4 * i4 + 2] = x.z;
+      qa[4 * i4 + 3] = x.w;
+    }
+#pragma unroll
+    for (int sl = 0; sl < C::NPL; ++sl) dk[sl] = 0.f;
+    const float* Fq = F + 4 * q;
+    for (int a = 0; a < n; ++a) {
+      const float* Fa = Fq + a * (RP * RP);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < RP; ++i) {
+        float4 f;
+        if constexpr (F_SMEM)
+          f = ld4(Fa + i * RP);
+        else
+          f = __ldg(reinterpret_cast<const float4*>(Fa + i * RP));
+        acc[0] = fmaf(qa[i], f.x, acc[0]);
+        acc[1] = fmaf(qa[i], f.y, acc[1]);
+        acc[2] = fmaf(qa[i], f.z, acc[2]);
+        acc[3] = fmaf(qa[i], f.w, acc[3]);
+      }
+      float part = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) part = fmaf(acc[t], qo[t], part);
+      part = group_sum<LPM>(part);
+#pragma unroll
+      for (int sl = 0; sl < C::NPL; ++sl)
+        if (a == q + LPM * sl) dk[sl] = part;
+    }
+    __syncwarp();
+  }
+};
+
+// dynamic smem: 64 B barriers | F (if F_SMEM) | per-warp scratch
+template <int RP, bool F_SMEM>
+__host__ __device__ constexpr size_t lmi_smem_bytes(int n, int threads) {
+  return 64 + (F_SMEM ? static_cast<size_t>(n) * RP * RP * 4 : 0) +
+         static_cast<size_t>(threads / 32) * LmiCfg<RP>::MPW * LmiCfg<RP>::SCR * 4;
+}
+
+template <int RP, bool F_SMEM>
+__device__ __forceinline__ const float* lmi_stage(const PlanDev& P, unsigned char* smem_raw, uint64_t* bars,
+                                                  float** scratch_base) {
+  const float* F;
+  if constexpr (F_SMEM) {
+    float* fs = reinterpret_cast<float*>(smem_raw + 64);
+    if (threadIdx.x == 0) {
+      mbar_init(&bars[0], 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) stage_bulk(fs, P.blob + P.off_lmi, P.lmi_words, &bars[0]);
+    F = fs;
+    *scratch_base = fs + P.lmi_words;
+  } else {
+    F = P.blob + P.off_lmi;
+    *scratch_base = reinterpret_cast<float*>(smem_raw + 64);
+  }
+  return F;
+}
+
+// ----------------------------------------------------------------------------- forward
+// prior kappa/tag (from lqs_forward_kernel) are merged when has_prior != 0; y, kappa, active are written.
+template <int RP, bool F_SMEM>
+__global__ void __launch_bounds__(kLmiThreads, 1)
+    lmi_forward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, float* __restrict__ y,
+                       float* __restrict__ kappa_io, int* __restrict__ active_io, long long B, int mode,
+                       int has_prior) {
+  using C = LmiCfg<RP>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* scratch_base;
+  const float* F = lmi_stage<RP, F_SMEM>(P, smem_raw, bars, &scratch_base);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  LmiSolver<RP, false, F_SMEM> S;
+  S.q = lane % C::LPM;
+  S.grp_base = lane - S.q;
+  const int grp = lane / C::LPM;
+  S.scr = scratch_base + (warp * C::MPW + grp) * C::SCR;
+  const int n = P.n, k = P.k;
+  const float* y0 = P.blob + P.off_y0;
+  const float* nmat = P.blob + P.off_nmat;
+  const long long warp_id = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  bool staged = !F_SMEM;
+
+  for (long long base = warp_id * C::MPW; base < B; base += n_warps * C::MPW) {
+    const long long b = base + grp;
+    const bool valid = b < B;
+    const float s = S.load_direction(v + b * ldv, n, valid);
+    if (!staged) {
+      mbar_wait(&bars[0], 0);
+      staged = true;
+    }
+    S.contract(F, n);
+    S.tridiagonalize();
+    const float lam = S.lambda_max_relu();
+    float kap = fmaxf(lam, 0.f);
+    int tag = kap > 0.f ? make_tag(RAYEN_FAM_LMI, 0) : make_tag(RAYEN_FAM_NONE, 0);
+    if (has_prior && valid) {
+      const float k0 = kappa_io[b];
+      const int t0 = active_io[b];
+      if (!(kap > k0)) {
+        kap = k0;
+        tag = t0;
+      }
+    }
+    __syncwarp();  // every lane of the matrix has read the prior before lane 0 overwrites it
+    if (valid) {
+      if (S.q == 0) {
+        kappa_io[b] = kap;
+        active_io[b] = tag;
+      }
+      float alpha;
+      if (mode == RAYEN_MODE_RAYEN_OLD)
+        alpha = 1.0f / (expf(__ldg(v + b * ldv + n)) + kap);
+      else
+        alpha = fminf(1.0f / kap, s);
+      const float* u = S.su();
+      float* yrow = y + b * k;
+      if (P.n_is_identity) {
+        for (int a = S.q; a < k; a += C::LPM) yrow[a] = fmaf(alpha, u[a], __ldg(y0 + a));
+      } else {
+        for (int i = S.q; i < k; i += C::LPM) {
+          const float* nrow = nmat + i * (P.np + 4);
+          float acc = 0.f;
+          for (int a = 0; a < n; ++a) acc = fmaf(__ldg(nrow + a), u[a], acc);
+          yrow[i] = fmaf(alpha, acc, __ldg(y0 + i));
+        }
+      }
+    }
+    __syncwarp();  // the scratch (u) is rewritten by the next sample
+  }
+  if constexpr (F_SMEM) {
+    if (!staged) mbar_wait(&bars[0], 0);
+  }
+}
+
+// ----------------------------------------------------------------------------- backward
+// Only the samples whose binding constraint is the LMI and whose gradient needs d kappa/du are
+// processed; everything else was written by lqs_backward_kernel.  The work list is the batch itself:
+// a matrix group whose sample is not one of those skips to the next (warp-uniform when none is).
+template <int RP, bool F_SMEM>
+__global__ void __launch_bounds__(kLmiThreads, 1)
+    lmi_backward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, const float* __restrict__ gy,
+                        const float* __restrict__ kappa, const int* __restrict__ active, float* __restrict__ gv,
+                        long long ldgv, long long B, int mode) {
+  using C = LmiCfg<RP>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* scratch_base;
+  const float* F = lmi_stage<RP, F_SMEM>(P, smem_raw, bars, &scratch_base);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  LmiSolver<RP, true, F_SMEM> S;
+  S.q = lane % C::LPM;
+  S.grp_base = lane - S.q;
+  const int grp = lane / C::LPM;
+  S.scr = scratch_base + (warp * C::MPW + grp) * C::SCR;
+  const int n = P.n, k = P.k;
+  const float* nmat = P.blob + P.off_nmat;
+  const long long warp_id = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  bool staged = !F_SMEM;
+
+  for (long long base = warp_id * C::MPW; base < B; base += n_warps * C::MPW) {
+    const long long b = base + grp;
+    bool mine = false;
+    float kap = 0.f;
+    if (b < B) {
+      kap = __ldg(kappa + b);
+      mine = tag_family(__ldg(active + b)) == RAYEN_FAM_LMI && kap > 0.f;
+    }
+    const float s = S.load_direction(v + b * ldv, n, mine);
+    if (mine && mode == RAYEN_MODE_RAYEN) mine = (1.0f / kap < s);
+    if (__ballot_sync(0xffffffffu, mine) == 0u) continue;  // warp-uniform
+    if (!staged) {
+      mbar_wait(&bars[0], 0);
+      staged = true;
+    }
+    // groups that are not `mine` run on u = 0 (a zero matrix) and write nothing
+    if (!mine) {
+      for (int a = S.q; a < kLmiMaxN; a += C::LPM) S.su()[a] = 0.f;
+    }
+    __syncwarp();
+    S.contract(F, n);
+    S.tridiagonalize();
+    const float lam = S.lambda_max_relu();
+    float qo[4];
+    S.eigenvector(lam, qo);
+    float dk[C::NPL];
+    S.eig_gradient(F, n, qo, dk);
+
+    // closed-form tail with the n-vector spread over the lanes of the matrix (a = q + LPM*slot)
+    const float* u = S.su();
+    float uo[C::NPL], gz[C::NPL];
+    float gzu = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < C::NPL; ++sl) {
+      const int a = S.q + C::LPM * sl;
+      uo[sl] = u[a];
+      float g = 0.f;
+      if (mine && a < n) {
+        if (P.n_is_identity) {
+          g = __ldg(gy + b * k + a);
+        } else {
+          for (int i = 0; i < k; ++i) g = fmaf(__ldg(gy + b * k + i), __ldg(nmat + i * (P.np + 4) + a), g);
+        }
+      }
+      gz[sl] = g;
+      gzu = fmaf(g, uo[sl], gzu);
+    }
+    gzu = group_sum<C::LPM>(gzu);
+    float gu[C::NPL], guu = 0.f, gbeta = 0.f;
+    if (mode == RAYEN_MODE_RAYEN_OLD) {
+      const float eb = mine ? expf(__ldg(v + b * ldv + n)) : 1.f;
+      const float alpha = 1.0f / (eb + kap);
+      const float c = gzu * alpha * alpha;
+#pragma unroll
+      for (int sl = 0; sl < C::NPL; ++sl) gu[sl] = fmaf(alpha, gz[sl], -c * dk[sl]);
+      gbeta = -c * eb;
+    } else {
+      const float ik = mine ? 1.0f / kap : 0.f;
+      const float c = gzu * ik * ik;
+#pragma unroll
+      for (int sl = 0; sl < C::NPL; ++sl) gu[sl] = fmaf(ik, gz[sl], -c * dk[sl]);
+    }
+#pragma unroll
+    for (int sl = 0; sl < C::NPL; ++sl) guu = fmaf(gu[sl], uo[sl], guu);
+    guu = group_sum<C::LPM>(guu);
+    if (s < kNormEps) guu = 0.f;
+    const float inv_s = 1.0f / fmaxf(s, kNormEps);
+    if (mine) {
+#pragma unroll
+      for (int sl = 0; sl < C::NPL; ++sl) {
+        const int a = S.q + C::LPM * sl;
+        if (a < n) gv[b * ldgv + a] = (gu[sl] - guu * uo[sl]) * inv_s;
+      }
+      if (mode == RAYEN_MODE_RAYEN_OLD && S.q == 0) gv[b * ldgv + n] = gbeta;
+    }
+    __syncwarp();
+  }
+  if constexpr (F_SMEM) {
+    if (!staged) mbar_wait(&bars[0], 0);
+  }
+}
+
+}  // namespace rayen

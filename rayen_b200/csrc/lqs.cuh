@@ -1,0 +1,514 @@
+// Linear / quadratic / SOC families: fused kappa + shift-and-scale forward, closed-form backward.
+//
+// Thread mapping (forward): a "tile" is TM consecutive samples whose unit directions u live in
+// registers (TM x NP floats); L consecutive lanes (L = 1..32, power of two, chosen at launch from the
+// batch size) share one tile and split the constraints between them -- 4-row chunks of D, whole
+// quadratics, whole cones -- then merge their (kappa, tag) with log2(L) shuffles.  The constants
+// are staged once per CTA into shared memory with 1-D TMA bulk copies and read as LDS.128; every
+// LDS.128 feeds 4*TM FMAs, which is what keeps the kernel on the FP32 pipe instead of the LSU.
+#pragma once
+#include "common.cuh"
+
+namespace rayen {
+
+__host__ __device__ constexpr int lqs_max_threads(int np, int tm) {
+  return (np * tm >= 128) ? 384 : ((np * tm >= 64) ? 512 : 768);
+}
+
+// ----------------------------------------------------------------------------- loading directions
+template <int NP>
+__device__ __forceinline__ void load_row(const float* __restrict__ row, int n, bool vec_ok, bool valid,
+                                         float (&x)[NP]) {
+  if (!valid) {
+#pragma unroll
+    for (int a = 0; a < NP; ++a) x[a] = 0.f;
+    return;
+  }
+  if (vec_ok) {
+#pragma unroll
+    for (int kk = 0; kk < NP / 4; ++kk) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * kk < n) t = __ldg(reinterpret_cast<const float4*>(row) + kk);
+      x[4 * kk + 0] = t.x;
+      x[4 * kk + 1] = t.y;
+      x[4 * kk + 2] = t.z;
+      x[4 * kk + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < NP; ++a) x[a] = (a < n) ? __ldg(row + a) : 0.f;
+  }
+}
+
+template <int NP>
+__device__ __forceinline__ float normalize_row(float (&x)[NP]) {
+  float ss = 0.f;
+#pragma unroll
+  for (int a = 0; a < NP; ++a) ss = fmaf(x[a], x[a], ss);
+  const float s = sqrtf(ss);
+  const float inv = 1.0f / fmaxf(s, kNormEps);
+#pragma unroll
+  for (int a = 0; a < NP; ++a) x[a] *= inv;
+  return s;
+}
+
+// dot of a 4-float constant group with u[t][4*kk .. 4*kk+3]
+#define RAYEN_FMA4(acc, c4, uu, kk)            \
+  acc = fmaf((c4).x, (uu)[4 * (kk) + 0], acc); \
+  acc = fmaf((c4).y, (uu)[4 * (kk) + 1], acc); \
+  acc = fmaf((c4).z, (uu)[4 * (kk) + 2], acc); \
+  acc = fmaf((c4).w, (uu)[4 * (kk) + 3], acc);
+
+// ----------------------------------------------------------------------------- kappa of the three families
+// ||T u||^2 for a packed upper-triangular T (row i keeps columns 4*floor(i/4)..NP-1).
+template <int NP, int TM>
+__device__ __forceinline__ void tri_norm2(const float* __restrict__ tri, const float (&u)[TM][NP],
+                                          float (&out)[TM]) {
+#pragma unroll
+  for (int t = 0; t < TM; ++t) out[t] = 0.f;
+  int pos = 0;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float r[TM];
+#pragma unroll
+    for (int t = 0; t < TM; ++t) r[t] = 0.f;
+#pragma unroll
+    for (int kk = i / 4; kk < NP / 4; ++kk) {
+      const float4 g = ld4(tri + pos);
+      pos += 4;
+#pragma unroll
+      for (int t = 0; t < TM; ++t) { RAYEN_FMA4(r[t], g, u[t], kk) }
+    }
+#pragma unroll
+    for (int t = 0; t < TM; ++t) out[t] = fmaf(r[t], r[t], out[t]);
+  }
+}
+
+template <int NP, int TM>
+__device__ __forceinline__ void dot_np(const float* __restrict__ c, const float (&u)[TM][NP], float (&out)[TM]) {
+#pragma unroll
+  for (int t = 0; t < TM; ++t) out[t] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < NP / 4; ++kk) {
+    const float4 g = ld4(c + 4 * kk);
+#pragma unroll
+    for (int t = 0; t < TM; ++t) { RAYEN_FMA4(out[t], g, u[t], kk) }
+  }
+}
+
+// Largest root of -A kappa^2 + 2 hb kappa + cq = 0 (A > 0), i.e. the reference's
+// solveSecondOrderEq (constraint_module.py:339-348) with a' = -A, b' = 2 hb, c' = cq, written in the
+// cancellation-free form.  A non-positive result means the ray never leaves the cone.
+__device__ __forceinline__ float soc_root(float A, float hb, float cq, float* root_out) {
+  const float disc = fmaxf(fmaf(hb, hb, A * cq), 0.f);
+  const float root = sqrtf(disc);
+  if (root_out) *root_out = root;
+  if (hb >= 0.f) return (hb + root) / A;
+  const float den = root - hb;  // > 0
+  return cq / den;
+}
+
+template <int NP, int TM>
+__device__ __forceinline__ void kappa_lqs(const PlanDev& P, const float* __restrict__ cst,
+                                          const float (&u)[TM][NP], int lane_l, int L, float (&best)[TM],
+                                          int (&tag)[TM]) {
+  // ---- linear rows: kappa_j = D_j . u                        (reference constraint_module.py:353)
+  {
+    const float* lin = cst;
+    const int nchunks = P.m_pad >> 2;
+    for (int c = lane_l; c < nchunks; c += L) {
+      const float* p = lin + c * P.lin_stride;
+      float acc[4][TM];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int t = 0; t < TM; ++t) acc[i][t] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < NP / 4; ++kk) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 d = ld4(p + kk * 16 + i * 4);
+#pragma unroll
+          for (int t = 0; t < TM; ++t) { RAYEN_FMA4(acc[i][t], d, u[t], kk) }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int t = 0; t < TM; ++t)
+          if (acc[i][t] > best[t]) {
+            best[t] = acc[i][t];
+            tag[t] = make_tag(RAYEN_FAM_LINEAR, 4 * c + i);
+          }
+    }
+  }
+  // ---- quadratics: kappa_i = phi_z . u + ||G u||             (reference constraint_module.py:360-381)
+  {
+    const float* quad = cst + (P.off_quad - P.off_lin);
+    for (int q = lane_l; q < P.n_quad; q += L) {
+      const float* base = quad + q * P.quad_stride;
+      float lin_part[TM], nrm2[TM];
+      dot_np<NP, TM>(base, u, lin_part);
+      tri_norm2<NP, TM>(base + NP, u, nrm2);
+#pragma unroll
+      for (int t = 0; t < TM; ++t) {
+        const float kap = lin_part[t] + sqrtf(nrm2[t]);
+        if (kap > best[t]) {
+          best[t] = kap;
+          tag[t] = make_tag(RAYEN_FAM_QUAD, q);
+        }
+      }
+    }
+  }
+  // ---- second-order cones                                      (reference constraint_module.py:383-399)
+  {
+    const float* soc = cst + (P.off_soc - P.off_lin);
+    constexpr int TRI = (NP / 4) * (NP / 4 + 1) * 8;  // packed triangular words
+    for (int j = lane_l; j < P.n_soc; j += L) {
+      const float* base = soc + j * P.soc_stride;
+      float cu[TM], hb[TM], nrm2[TM];
+      dot_np<NP, TM>(base, u, cu);
+      dot_np<NP, TM>(base + NP, u, hb);
+      tri_norm2<NP, TM>(base + 2 * NP, u, nrm2);
+      const float A = base[2 * NP + TRI];
+#pragma unroll
+      for (int t = 0; t < TM; ++t) {
+        const float cq = fmaf(-cu[t], cu[t], nrm2[t]);
+        const float kap = soc_root(A, hb[t], cq, nullptr);
+        if (kap > best[t]) {
+          best[t] = kap;
+          tag[t] = make_tag(RAYEN_FAM_SOC, j);
+        }
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- forward kernel
+// grid: persistent CTAs; dynamic smem = 64 B of mbarriers + the LQS constant region (SMEM == true).
+template <int NP, int TM, bool SMEM>
+__global__ void __launch_bounds__(lqs_max_threads(NP, TM), 1)
+    lqs_forward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, float* __restrict__ y,
+                       float* __restrict__ kappa_out, int* __restrict__ active_out, long long B, int mode,
+                       int L, int write_y) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  const float* cst;
+  if constexpr (SMEM) {
+    float* cs = reinterpret_cast<float*>(smem_raw + 64);
+    if (threadIdx.x == 0) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // linear rows first so that their FMAs start while the rest is still in flight
+      const int lin_words = P.off_quad - P.off_lin;
+      stage_bulk(cs, P.blob + P.off_lin, lin_words, &bars[0]);
+      stage_bulk(cs + lin_words, P.blob + P.off_quad, P.lqs_words - lin_words, &bars[1]);
+    }
+    cst = cs;
+  } else {
+    cst = P.blob + P.off_lin;
+  }
+
+  const int lane = threadIdx.x & 31;
+  const int lane_l = lane & (L - 1);
+  const int tiles_per_warp = 32 / L;
+  const long long warp_id = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long n_tiles = (B + TM - 1) / TM;
+  const int n = P.n, k = P.k;
+  const bool vec_in = ((n & 3) == 0) && ((ldv & 3) == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
+  const bool vec_out = ((k & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  bool staged = !SMEM;
+
+  for (long long tile_base = warp_id * tiles_per_warp; tile_base < n_tiles; tile_base += n_warps * tiles_per_warp) {
+    const long long tile = tile_base + lane / L;
+    float u[TM][NP];
+    float s[TM], beta[TM];
+#pragma unroll
+    for (int t = 0; t < TM; ++t) {
+      const long long b = tile * TM + t;
+      const bool valid = (tile < n_tiles) && (b < B);
+      load_row<NP>(v + b * ldv, n, vec_in, valid, u[t]);
+      beta[t] = (mode == RAYEN_MODE_RAYEN_OLD && valid) ? __ldg(v + b * ldv + n) : 0.f;
+      s[t] = normalize_row<NP>(u[t]);
+    }
+    if (!staged) {
+      mbar_wait(&bars[0], 0);
+    }
+    float best[TM];
+    int tag[TM];
+#pragma unroll
+    for (int t = 0; t < TM; ++t) {
+      best[t] = 0.f;
+      tag[t] = make_tag(RAYEN_FAM_NONE, 0);
+    }
+    if (!staged) {
+      // the linear chunk loop only touches the first section; the rest must have landed before the
+      // quadratic loop starts, so wait for both here (the second wait is almost always free).
+      mbar_wait(&bars[1], 0);
+      staged = true;
+    }
+    kappa_lqs<NP, TM>(P, cst, u, lane_l, L, best, tag);
+#pragma unroll
+    for (int t = 0; t < TM; ++t) group_argmax(best[t], tag[t], L);
+
+    const float* y0 = cst + (P.off_y0 - P.off_lin);
+    const float* nmat = cst + (P.off_nmat - P.off_lin);
+#pragma unroll
+    for (int t = 0; t < TM; ++t) {
+      const long long b = tile * TM + t;
+      const bool valid = (tile < n_tiles) && (b < B);
+      if (!valid) continue;
+      const float kap = best[t];
+      if (lane_l == 0) {
+        if (kappa_out) kappa_out[b] = kap;
+        if (active_out) active_out[b] = tag[t];
+      }
+      if (!write_y) continue;
+      // shift-and-scale (reference constraint_module.py:472-474 / :464-465, :512-514)
+      float alpha;
+      if (mode == RAYEN_MODE_RAYEN_OLD)
+        alpha = 1.0f / (expf(beta[t]) + kap);
+      else
+        alpha = fminf(1.0f / kap, s[t]);
+      float* yrow = y + b * k;
+      if (P.n_is_identity) {
+#pragma unroll
+        for (int kk = 0; kk < NP / 4; ++kk) {
+          if (4 * kk < k && (kk & (L - 1)) == lane_l) {
+            const float4 c = ld4(y0 + 4 * kk);
+            float4 o;
+            o.x = fmaf(alpha, u[t][4 * kk + 0], c.x);
+            o.y = fmaf(alpha, u[t][4 * kk + 1], c.y);
+            o.z = fmaf(alpha, u[t][4 * kk + 2], c.z);
+            o.w = fmaf(alpha, u[t][4 * kk + 3], c.w);
+            if (vec_out) {
+              *reinterpret_cast<float4*>(yrow + 4 * kk) = o;
+            } else {
+              if (4 * kk + 0 < k) yrow[4 * kk + 0] = o.x;
+              if (4 * kk + 1 < k) yrow[4 * kk + 1] = o.y;
+              if (4 * kk + 2 < k) yrow[4 * kk + 2] = o.z;
+              if (4 * kk + 3 < k) yrow[4 * kk + 3] = o.w;
+            }
+          }
+        }
+      } else {
+        for (int i = lane_l; i < k; i += L) {
+          const float* nrow = nmat + i * (NP + 4);
+          float acc = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < NP / 4; ++kk) {
+            const float4 g = ld4(nrow + 4 * kk);
+            RAYEN_FMA4(acc, g, u[t], kk)
+          }
+          yrow[i] = fmaf(alpha, acc, y0[i]);
+        }
+      }
+    }
+  }
+  if constexpr (SMEM) {
+    // a CTA that got no tile must still not exit while its bulk copies are in flight
+    if (!staged) {
+      mbar_wait(&bars[0], 0);
+      mbar_wait(&bars[1], 0);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- backward
+// d kappa / d u of the binding constraint, z-space, constants read through L1/L2.
+template <int NP>
+__device__ __forceinline__ void tri_grad(const float* __restrict__ tri, const float (&u)[NP], float (&g)[NP],
+                                         float* norm2) {
+  // g = T'(T u), norm2 = |T u|^2
+  float ss = 0.f;
+#pragma unroll
+  for (int a = 0; a < NP; ++a) g[a] = 0.f;
+  int pos = 0;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float4 row[NP / 4];
+    float r = 0.f;
+#pragma unroll
+    for (int kk = i / 4; kk < NP / 4; ++kk) {
+      row[kk] = __ldg(reinterpret_cast<const float4*>(tri + pos));
+      pos += 4;
+      RAYEN_FMA4(r, row[kk], u, kk)
+    }
+    ss = fmaf(r, r, ss);
+#pragma unroll
+    for (int kk = i / 4; kk < NP / 4; ++kk) {
+      g[4 * kk + 0] = fmaf(row[kk].x, r, g[4 * kk + 0]);
+      g[4 * kk + 1] = fmaf(row[kk].y, r, g[4 * kk + 1]);
+      g[4 * kk + 2] = fmaf(row[kk].z, r, g[4 * kk + 2]);
+      g[4 * kk + 3] = fmaf(row[kk].w, r, g[4 * kk + 3]);
+    }
+  }
+  *norm2 = ss;
+}
+
+template <int NP>
+__device__ __forceinline__ void dkappa_lqs(const PlanDev& P, int tag, float kap, const float (&u)[NP],
+                                           float (&dk)[NP]) {
+  const int fam = tag_family(tag), idx = tag_index(tag);
+  const float* blob = P.blob;
+#pragma unroll
+  for (int a = 0; a < NP; ++a) dk[a] = 0.f;
+  if (fam == RAYEN_FAM_LINEAR) {
+    const float* p = blob + P.off_lin + (idx >> 2) * P.lin_stride + (idx & 3) * 4;
+#pragma unroll
+    for (int kk = 0; kk < NP / 4; ++kk) {
+      const float4 d = __ldg(reinterpret_cast<const float4*>(p + kk * 16));
+      dk[4 * kk + 0] = d.x;
+      dk[4 * kk + 1] = d.y;
+      dk[4 * kk + 2] = d.z;
+      dk[4 * kk + 3] = d.w;
+    }
+  } else if (fam == RAYEN_FAM_QUAD) {
+    const float* base = blob + P.off_quad + idx * P.quad_stride;
+    float g[NP], nrm2;
+    tri_grad<NP>(base + NP, u, g, &nrm2);
+    const float root = sqrtf(nrm2);
+    const float inv = root > 0.f ? 1.0f / root : 0.f;
+#pragma unroll
+    for (int a = 0; a < NP; ++a) dk[a] = fmaf(g[a], inv, __ldg(base + a));
+  } else if (fam == RAYEN_FAM_SOC) {
+    constexpr int TRI = (NP / 4) * (NP / 4 + 1) * 8;
+    const float* base = blob + P.off_soc + idx * P.soc_stride;
+    float g[NP], nrm2, cu = 0.f, hb = 0.f;
+#pragma unroll
+    for (int a = 0; a < NP; ++a) {
+      cu = fmaf(__ldg(base + a), u[a], cu);
+      hb = fmaf(__ldg(base + NP + a), u[a], hb);
+    }
+    tri_grad<NP>(base + 2 * NP, u, g, &nrm2);
+    const float A = __ldg(base + 2 * NP + TRI);
+    const float cq = fmaf(-cu, cu, nrm2);
+    float root;
+    (void)soc_root(A, hb, cq, &root);
+    // d kappa/du = (kappa h + R'R u - (c.u) c) / sqrt(disc);  the reference's autograd is NaN at
+    // disc == 0 (tangent ray, measure zero) -- emit 0 there.
+    const float inv = root > 0.f ? 1.0f / root : 0.f;
+#pragma unroll
+    for (int a = 0; a < NP; ++a)
+      dk[a] = (fmaf(kap, __ldg(base + NP + a), g[a]) - cu * __ldg(base + a)) * inv;
+  }
+}
+
+// Shared tail of both backward kernels: from g_z, u, s, kappa and d kappa/du to g_v.
+template <int NP>
+__device__ __forceinline__ void backward_tail(int mode, float s, float kap, float beta, const float (&u)[NP],
+                                              const float (&gz)[NP], const float (&dk)[NP], bool boundary,
+                                              float (&gv)[NP], float* gbeta) {
+  float gzu = 0.f;
+#pragma unroll
+  for (int a = 0; a < NP; ++a) gzu = fmaf(gz[a], u[a], gzu);
+  float gu[NP];
+  if (mode == RAYEN_MODE_RAYEN_OLD) {
+    const float eb = expf(beta);
+    const float alpha = 1.0f / (eb + kap);
+    const float c = gzu * alpha * alpha;
+#pragma unroll
+    for (int a = 0; a < NP; ++a) gu[a] = fmaf(alpha, gz[a], -c * dk[a]);
+    *gbeta = -c * eb;
+  } else {
+    if (!boundary) {
+      // z = z0 + v: identity Jacobian (and 0 at v == 0, the norm's subgradient)
+#pragma unroll
+      for (int a = 0; a < NP; ++a) gv[a] = (s > 0.f) ? gz[a] : 0.f;
+      return;
+    }
+    const float ik = 1.0f / kap;
+    const float c = gzu * ik * ik;
+#pragma unroll
+    for (int a = 0; a < NP; ++a) gu[a] = fmaf(ik, gz[a], -c * dk[a]);
+  }
+  float guu = 0.f;
+#pragma unroll
+  for (int a = 0; a < NP; ++a) guu = fmaf(gu[a], u[a], guu);
+  const float inv_s = 1.0f / fmaxf(s, kNormEps);
+  if (s < kNormEps) guu = 0.f;  // normalize() divides by the constant eps there
+#pragma unroll
+  for (int a = 0; a < NP; ++a) gv[a] = (gu[a] - guu * u[a]) * inv_s;
+}
+
+// g_z = N' g_y
+template <int NP>
+__device__ __forceinline__ void load_gz(const PlanDev& P, const float* __restrict__ gyrow, bool vec_ok,
+                                        float (&gz)[NP]) {
+  if (P.n_is_identity) {
+    load_row<NP>(gyrow, P.n, vec_ok, true, gz);
+  } else {
+#pragma unroll
+    for (int a = 0; a < NP; ++a) gz[a] = 0.f;
+    const float* nmat = P.blob + P.off_nmat;
+    for (int i = 0; i < P.k; ++i) {
+      const float gi = __ldg(gyrow + i);
+      const float* nrow = nmat + i * (NP + 4);
+#pragma unroll
+      for (int kk = 0; kk < NP / 4; ++kk) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(nrow + 4 * kk));
+        gz[4 * kk + 0] = fmaf(gi, c.x, gz[4 * kk + 0]);
+        gz[4 * kk + 1] = fmaf(gi, c.y, gz[4 * kk + 1]);
+        gz[4 * kk + 2] = fmaf(gi, c.z, gz[4 * kk + 2]);
+        gz[4 * kk + 3] = fmaf(gi, c.w, gz[4 * kk + 3]);
+      }
+    }
+  }
+}
+
+template <int NP>
+__device__ __forceinline__ void store_row(float* __restrict__ row, int n, bool vec_ok, const float (&x)[NP]) {
+  if (vec_ok) {
+#pragma unroll
+    for (int kk = 0; kk < NP / 4; ++kk)
+      if (4 * kk < n)
+        *reinterpret_cast<float4*>(row + 4 * kk) = make_float4(x[4 * kk], x[4 * kk + 1], x[4 * kk + 2], x[4 * kk + 3]);
+  } else {
+#pragma unroll
+    for (int a = 0; a < NP; ++a)
+      if (a < n) row[a] = x[a];
+  }
+}
+
+// One thread per sample.  Samples whose binding constraint is the LMI (and that need d kappa/du) are
+// left to lmi_backward_kernel.
+template <int NP>
+__global__ void __launch_bounds__(256)
+    lqs_backward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, const float* __restrict__ gy,
+                        const float* __restrict__ kappa, const int* __restrict__ active, float* __restrict__ gv,
+                        long long ldgv, long long B, int mode) {
+  const int n = P.n;
+  const bool vec_v = ((n & 3) == 0) && ((ldv & 3) == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
+  const bool vec_gy = ((P.k & 3) == 0) && ((reinterpret_cast<uintptr_t>(gy) & 15) == 0);
+  const bool vec_gv = ((n & 3) == 0) && ((ldgv & 3) == 0) && ((reinterpret_cast<uintptr_t>(gv) & 15) == 0);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; b < B; b += stride) {
+    const float kap = __ldg(kappa + b);
+    const int tag = __ldg(active + b);
+    float u[NP];
+    load_row<NP>(v + b * ldv, n, vec_v, true, u);
+    const float s = normalize_row<NP>(u);
+    const float beta = (mode == RAYEN_MODE_RAYEN_OLD) ? __ldg(v + b * ldv + n) : 0.f;
+    const bool boundary = (mode == RAYEN_MODE_RAYEN_OLD) ? (kap > 0.f) : (1.0f / kap < s);
+    if (boundary && tag_family(tag) == RAYEN_FAM_LMI) continue;
+    float gz[NP], dk[NP], g[NP];
+    load_gz<NP>(P, gy + b * P.k, vec_gy, gz);
+    if (boundary) {
+      dkappa_lqs<NP>(P, tag, kap, u, dk);
+    } else {
+#pragma unroll
+      for (int a = 0; a < NP; ++a) dk[a] = 0.f;
+    }
+    float gbeta = 0.f;
+    backward_tail<NP>(mode, s, kap, beta, u, gz, dk, boundary, g, &gbeta);
+    store_row<NP>(gv + b * ldgv, n, vec_gv, g);
+    if (mode == RAYEN_MODE_RAYEN_OLD) gv[b * ldgv + n] = gbeta;
+  }
+}
+
+}  // namespace rayen

@@ -1,0 +1,459 @@
+// librayen_b200.so -- C ABI (include/rayen_b200.h) over the sm_100a kernels in lqs.cuh / lmi.cuh.
+// Host side only: plan upload, kernel selection, launch geometry.  No torch types, no exceptions
+// across the boundary, no synchronisation except in the *_host_* entry points.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "lmi.cuh"
+#include "lqs.cuh"
+
+using namespace rayen;
+
+// ----------------------------------------------------------------------------- plan object
+struct rayen_plan {
+  PlanDev dev;
+  int device;
+  int sm_count;
+  int max_smem_optin;
+  int tune_tm, tune_lanes;
+  float* d_blob;
+  bool lqs_smem;  // LQS constants fit in shared memory
+  bool lmi_smem;  // LMI matrices fit in shared memory
+  size_t lqs_smem_bytes, lmi_smem_bytes;
+  bool has_lqs;   // any linear row / quadratic / cone (the linear section always has >= 1 row)
+};
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return static_cast<int>(e);
+}
+#define RAYEN_CUDA(call)                                  \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+extern "C" int rayen_abi_version(void) { return RAYEN_ABI_VERSION; }
+extern "C" const char* rayen_last_error(void) { return g_err; }
+extern "C" int64_t rayen_launch_count(void) { return g_launches.load(); }
+
+// ----------------------------------------------------------------------------- kernel tables
+typedef void (*LqsFwdFn)(const PlanDev, const float*, long long, float*, float*, int*, long long, int, int, int);
+typedef void (*LqsBwdFn)(const PlanDev, const float*, long long, const float*, const float*, const int*, float*,
+                         long long, long long, int);
+typedef void (*LmiFwdFn)(const PlanDev, const float*, long long, float*, float*, int*, long long, int, int);
+typedef void (*LmiBwdFn)(const PlanDev, const float*, long long, const float*, const float*, const int*, float*,
+                         long long, long long, int);
+
+static int np_index(int np) { return np == 4 ? 0 : np == 8 ? 1 : np == 16 ? 2 : np == 32 ? 3 : -1; }
+static int tm_index(int tm) { return tm == 1 ? 0 : tm == 2 ? 1 : tm == 4 ? 2 : -1; }
+
+template <int NP, int TM>
+static LqsFwdFn lqs_fwd_pick(bool smem) {
+  return smem ? lqs_forward_kernel<NP, TM, true> : lqs_forward_kernel<NP, TM, false>;
+}
+template <int NP>
+static LqsFwdFn lqs_fwd_pick_tm(int tm, bool smem) {
+  switch (tm) {
+    case 1: return lqs_fwd_pick<NP, 1>(smem);
+    case 2: return lqs_fwd_pick<NP, 2>(smem);
+    default: return lqs_fwd_pick<NP, 4>(smem);
+  }
+}
+static LqsFwdFn lqs_fwd_fn(int np, int tm, bool smem) {
+  switch (np) {
+    case 4: return lqs_fwd_pick_tm<4>(tm, smem);
+    case 8: return lqs_fwd_pick_tm<8>(tm, smem);
+    case 16: return lqs_fwd_pick_tm<16>(tm, smem);
+    default: return lqs_fwd_pick_tm<32>(tm, smem);
+  }
+}
+static LqsBwdFn lqs_bwd_fn(int np) {
+  switch (np) {
+    case 4: return lqs_backward_kernel<4>;
+    case 8: return lqs_backward_kernel<8>;
+    case 16: return lqs_backward_kernel<16>;
+    default: return lqs_backward_kernel<32>;
+  }
+}
+static LmiFwdFn lmi_fwd_fn(int rp, bool smem) {
+  switch (rp) {
+    case 4: return smem ? lmi_forward_kernel<4, true> : lmi_forward_kernel<4, false>;
+    case 8: return smem ? lmi_forward_kernel<8, true> : lmi_forward_kernel<8, false>;
+    case 16: return smem ? lmi_forward_kernel<16, true> : lmi_forward_kernel<16, false>;
+    default: return smem ? lmi_forward_kernel<32, true> : lmi_forward_kernel<32, false>;
+  }
+}
+static LmiBwdFn lmi_bwd_fn(int rp, bool smem) {
+  switch (rp) {
+    case 4: return smem ? lmi_backward_kernel<4, true> : lmi_backward_kernel<4, false>;
+    case 8: return smem ? lmi_backward_kernel<8, true> : lmi_backward_kernel<8, false>;
+    case 16: return smem ? lmi_backward_kernel<16, true> : lmi_backward_kernel<16, false>;
+    default: return smem ? lmi_backward_kernel<32, true> : lmi_backward_kernel<32, false>;
+  }
+}
+static size_t lmi_smem(int rp, bool smem, int n, int threads) {
+  switch (rp) {
+    case 4: return smem ? lmi_smem_bytes<4, true>(n, threads) : lmi_smem_bytes<4, false>(n, threads);
+    case 8: return smem ? lmi_smem_bytes<8, true>(n, threads) : lmi_smem_bytes<8, false>(n, threads);
+    case 16: return smem ? lmi_smem_bytes<16, true>(n, threads) : lmi_smem_bytes<16, false>(n, threads);
+    default: return smem ? lmi_smem_bytes<32, true>(n, threads) : lmi_smem_bytes<32, false>(n, threads);
+  }
+}
+
+static int allow_smem(const void* fn, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  }
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- plan create / destroy
+extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_t** out) {
+  if (!d || !out) return fail(RAYEN_ERR_BAD_ARGUMENT, "rayen_plan_create: null argument");
+  *out = nullptr;
+  if (d->abi_version != RAYEN_ABI_VERSION)
+    return fail(RAYEN_ERR_ABI, "plan descriptor has ABI %d, library has %d", d->abi_version, RAYEN_ABI_VERSION);
+  if (d->n < 1 || d->k < d->n) return fail(RAYEN_ERR_BAD_ARGUMENT, "bad dimensions n=%d k=%d", d->n, d->k);
+  if (np_index(d->np) < 0 || d->np < d->n)
+    return fail(RAYEN_ERR_UNSUPPORTED, "n=%d (np=%d): only n <= 32 is covered", d->n, d->np);
+  if (d->lmi_r > 0 && (np_index(d->lmi_rp) < 0 || d->lmi_rp < d->lmi_r))
+    return fail(RAYEN_ERR_UNSUPPORTED, "LMI size %d (padded %d): only r <= 32 is covered", d->lmi_r, d->lmi_rp);
+  if (d->m_pad % 4 || d->m_pad < d->m || d->m_pad < 4 || d->k_pad % 4 || d->k_pad < d->k)
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "bad padding m=%d m_pad=%d k=%d k_pad=%d", d->m, d->m_pad, d->k, d->k_pad);
+  if (!d->blob || d->blob_words <= 0 || d->blob_words % 4)
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "bad constant block (%lld words)", static_cast<long long>(d->blob_words));
+  const int64_t offs[6] = {d->off_lin, d->off_quad, d->off_soc, d->off_nmat, d->off_y0, d->off_lmi};
+  for (int i = 0; i < 6; ++i) {
+    if (offs[i] < 0 || offs[i] % 4 || offs[i] >= d->blob_words ||
+        (i > 0 && offs[i] < offs[i - 1]))
+      return fail(RAYEN_ERR_BAD_ARGUMENT, "section offset %d = %lld is invalid", i, static_cast<long long>(offs[i]));
+  }
+  const int tri = (d->np / 4) * (d->np / 4 + 1) * 8;
+  if (d->lin_chunk_stride < 4 * d->np || d->lin_chunk_stride % 4 ||
+      d->off_lin + static_cast<int64_t>(d->m_pad / 4) * d->lin_chunk_stride > d->off_quad)
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "linear section does not fit its slot");
+  if (d->n_quad < 0 || (d->n_quad > 0 && (d->quad_stride < d->np + tri || d->quad_stride % 4 ||
+                                           d->off_quad + static_cast<int64_t>(d->n_quad) * d->quad_stride > d->off_soc)))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "quadratic section does not fit its slot");
+  if (d->n_soc < 0 || (d->n_soc > 0 && (d->soc_stride < 2 * d->np + tri + 4 || d->soc_stride % 4 ||
+                                         d->off_soc + static_cast<int64_t>(d->n_soc) * d->soc_stride > d->off_nmat)))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "SOC section does not fit its slot");
+  if (!d->n_is_identity && d->off_nmat + static_cast<int64_t>(d->k) * (d->np + 4) > d->off_y0)
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "N section does not fit its slot");
+  if (d->off_y0 + d->k_pad > d->off_lmi) return fail(RAYEN_ERR_BAD_ARGUMENT, "y0 section does not fit its slot");
+  if (d->lmi_r > 0 && d->off_lmi + static_cast<int64_t>(d->n) * d->lmi_rp * d->lmi_rp > d->blob_words)
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "LMI section does not fit the block");
+  if (d->blob_words > (1ll << 30)) return fail(RAYEN_ERR_UNSUPPORTED, "constant block too large");
+
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+    return fail(RAYEN_ERR_NO_DEVICE, "CUDA device %d is not available (%d devices visible)", device, count);
+  int prev = 0;
+  RAYEN_CUDA(cudaGetDevice(&prev));
+  RAYEN_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  RAYEN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    cudaSetDevice(prev);
+    return fail(RAYEN_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  }
+
+  rayen_plan* p = new (std::nothrow) rayen_plan();
+  if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "out of host memory");
+  memset(p, 0, sizeof(*p));
+  p->device = device;
+  p->sm_count = prop.multiProcessorCount;
+  p->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+  cudaError_t e = cudaMalloc(&p->d_blob, d->blob_words * sizeof(float));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(p->d_blob, d->blob, d->blob_words * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (p->d_blob) cudaFree(p->d_blob);
+    delete p;
+    cudaSetDevice(prev);
+    return cuda_fail(e, "uploading the constant block");
+  }
+  PlanDev& v = p->dev;
+  v.blob = p->d_blob;
+  v.n = d->n; v.k = d->k; v.np = d->np; v.k_pad = d->k_pad;
+  v.m = d->m; v.m_pad = d->m_pad; v.n_quad = d->n_quad; v.n_soc = d->n_soc;
+  v.lmi_r = d->lmi_r; v.lmi_rp = d->lmi_rp; v.n_is_identity = d->n_is_identity;
+  v.lin_stride = d->lin_chunk_stride; v.quad_stride = d->quad_stride; v.soc_stride = d->soc_stride;
+  v.off_lin = static_cast<int>(d->off_lin); v.off_quad = static_cast<int>(d->off_quad);
+  v.off_soc = static_cast<int>(d->off_soc); v.off_nmat = static_cast<int>(d->off_nmat);
+  v.off_y0 = static_cast<int>(d->off_y0); v.off_lmi = static_cast<int>(d->off_lmi);
+  v.lqs_words = static_cast<int>(d->off_lmi - d->off_lin);
+  v.lmi_words = d->lmi_r > 0 ? d->n * d->lmi_rp * d->lmi_rp : 0;
+
+  p->has_lqs = true;
+  p->lqs_smem_bytes = 64 + static_cast<size_t>(v.lqs_words) * 4;
+  p->lqs_smem = p->lqs_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
+  if (!p->lqs_smem) p->lqs_smem_bytes = 64;
+  int rc = 0;
+  for (int tm = 1; tm <= 4 && rc == 0; tm *= 2)
+    rc = allow_smem(reinterpret_cast<const void*>(lqs_fwd_fn(v.np, tm, p->lqs_smem)), p->lqs_smem_bytes);
+  if (rc == 0 && v.lmi_r > 0) {
+    p->lmi_smem_bytes = lmi_smem(v.lmi_rp, true, v.n, kLmiThreads);
+    p->lmi_smem = p->lmi_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
+    if (!p->lmi_smem) p->lmi_smem_bytes = lmi_smem(v.lmi_rp, false, v.n, kLmiThreads);
+    rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_fn(v.lmi_rp, p->lmi_smem)), p->lmi_smem_bytes);
+    if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_bwd_fn(v.lmi_rp, p->lmi_smem)), p->lmi_smem_bytes);
+  }
+  cudaSetDevice(prev);
+  if (rc != 0) {
+    cudaFree(p->d_blob);
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return RAYEN_OK;
+}
+
+extern "C" void rayen_plan_destroy(rayen_plan_t* p) {
+  if (!p) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(p->device);
+  cudaFree(p->d_blob);
+  cudaSetDevice(prev);
+  delete p;
+}
+
+extern "C" int rayen_plan_set_tuning(rayen_plan_t* p, int tm, int lanes) {
+  if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "null plan");
+  if (tm != 0 && tm_index(tm) < 0) return fail(RAYEN_ERR_BAD_ARGUMENT, "samples_per_thread must be 0, 1, 2 or 4");
+  if (lanes != 0 && (lanes < 1 || lanes > 32 || (lanes & (lanes - 1))))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "lanes_per_sample must be 0 or a power of two <= 32");
+  p->tune_tm = tm;
+  p->tune_lanes = lanes;
+  return RAYEN_OK;
+}
+
+extern "C" int rayen_plan_kernel_info(const rayen_plan_t* p, RayenKernelInfo* out) {
+  if (!p || !out) return fail(RAYEN_ERR_BAD_ARGUMENT, "null argument");
+  memset(out, 0, sizeof(*out));
+  cudaFuncAttributes a;
+  RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lqs_fwd_fn(p->dev.np, 4, p->lqs_smem))));
+  out->regs_lqs_fwd = a.numRegs;
+  RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lqs_bwd_fn(p->dev.np))));
+  out->regs_lqs_bwd = a.numRegs;
+  if (p->dev.lmi_r > 0) {
+    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_fwd_fn(p->dev.lmi_rp, p->lmi_smem))));
+    out->regs_lmi_fwd = a.numRegs;
+    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_bwd_fn(p->dev.lmi_rp, p->lmi_smem))));
+    out->regs_lmi_bwd = a.numRegs;
+  }
+  out->smem_lqs_bytes = static_cast<int>(p->lqs_smem_bytes);
+  out->smem_lmi_bytes = static_cast<int>(p->lmi_smem_bytes);
+  out->sm_count = p->sm_count;
+  return RAYEN_OK;
+}
+
+// ----------------------------------------------------------------------------- launch geometry
+static int floor_pow2(long long x) {
+  int p = 1;
+  while (2ll * p <= x) p *= 2;
+  return p;
+}
+static int ceil_pow2(long long x) {
+  int p = 1;
+  while (p < x) p *= 2;
+  return p;
+}
+
+struct LqsGeom {
+  int tm, lanes, block, grid;
+};
+
+// One wave of persistent CTAs: pick the samples-per-thread tile TM (register reuse of every LDS) and
+// the lanes-per-sample split L (parallelism when the batch alone cannot fill 148 SMs).
+static LqsGeom lqs_geometry(const rayen_plan* p, long long B) {
+  const PlanDev& v = p->dev;
+  int items = v.m_pad / 4;
+  if (v.n_quad > items) items = v.n_quad;
+  if (v.n_soc > items) items = v.n_soc;
+  const int max_lanes = ceil_pow2(items) > 32 ? 32 : ceil_pow2(items);
+  LqsGeom g{};
+  int tm = p->tune_tm;
+  if (tm == 0) {
+    tm = 1;
+    for (int cand = 4; cand >= 1; cand /= 2) {
+      const long long cap = static_cast<long long>(p->sm_count) * lqs_max_threads(v.np, cand);
+      const long long tiles = (B + cand - 1) / cand;
+      long long lanes = cap / (tiles > 0 ? tiles : 1);
+      if (lanes > max_lanes) lanes = max_lanes;
+      if (lanes < 1) lanes = 1;
+      if (tiles * floor_pow2(lanes) * 2 >= cap || cand == 1) {
+        tm = cand;
+        break;
+      }
+    }
+  }
+  const long long cap = static_cast<long long>(p->sm_count) * lqs_max_threads(v.np, tm);
+  const long long tiles = (B + tm - 1) / tm;
+  int lanes = p->tune_lanes;
+  if (lanes == 0) {
+    long long l = cap / (tiles > 0 ? tiles : 1);
+    if (l < 1) l = 1;
+    lanes = floor_pow2(l);
+    if (lanes > max_lanes) lanes = max_lanes;
+  }
+  const long long threads = tiles * lanes;
+  int block = lqs_max_threads(v.np, tm);
+  if (threads <= cap) {
+    long long per_sm = (threads + p->sm_count - 1) / p->sm_count;
+    per_sm = (per_sm + 31) / 32 * 32;
+    if (per_sm < 64) per_sm = 64;
+    if (per_sm < block) block = static_cast<int>(per_sm);
+  }
+  long long grid = (threads + block - 1) / block;
+  if (grid > p->sm_count) grid = p->sm_count;
+  if (grid < 1) grid = 1;
+  g.tm = tm;
+  g.lanes = lanes;
+  g.block = block;
+  g.grid = static_cast<int>(grid);
+  return g;
+}
+
+static int check_io(const rayen_plan* p, const void* a, const void* b, long long B, int mode) {
+  if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "null plan");
+  if (B < 0) return fail(RAYEN_ERR_BAD_ARGUMENT, "negative batch");
+  if (B > 0 && (!a || !b)) return fail(RAYEN_ERR_BAD_ARGUMENT, "null tensor");
+  if (mode != RAYEN_MODE_RAYEN && mode != RAYEN_MODE_RAYEN_OLD) return fail(RAYEN_ERR_BAD_ARGUMENT, "bad mode %d", mode);
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- forward / backward
+extern "C" int rayen_forward_f32(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa,
+                                 int32_t* active, int64_t B, int mode, void* stream_) {
+  int rc = check_io(p, v, y, B, mode);
+  if (rc) return rc;
+  if (B == 0) return RAYEN_OK;
+  const PlanDev& d = p->dev;
+  const int need = d.n + (mode == RAYEN_MODE_RAYEN_OLD ? 1 : 0);
+  if (ldv < need) return fail(RAYEN_ERR_BAD_ARGUMENT, "ldv=%lld < %d", static_cast<long long>(ldv), need);
+  const bool has_lmi = d.lmi_r > 0;
+  if (has_lmi && (!kappa || !active))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the kappa and active outputs");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int prev = 0;
+  RAYEN_CUDA(cudaGetDevice(&prev));
+  if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
+
+  const LqsGeom g = lqs_geometry(p, B);
+  LqsFwdFn f = lqs_fwd_fn(d.np, g.tm, p->lqs_smem);
+  f<<<g.grid, g.block, p->lqs_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode, g.lanes, has_lmi ? 0 : 1);
+  g_launches.fetch_add(1);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && has_lmi) {
+    const int mpw = 32 / (d.lmi_rp / 4);
+    long long blocks = (B + static_cast<long long>(mpw) * (kLmiThreads / 32) - 1) / (static_cast<long long>(mpw) * (kLmiThreads / 32));
+    if (blocks > p->sm_count) blocks = p->sm_count;
+    LmiFwdFn lf = lmi_fwd_fn(d.lmi_rp, p->lmi_smem);
+    lf<<<static_cast<int>(blocks), kLmiThreads, p->lmi_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode, 1);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+  }
+  if (prev != p->device) cudaSetDevice(prev);
+  if (e != cudaSuccess) return cuda_fail(e, "forward launch");
+  return RAYEN_OK;
+}
+
+extern "C" int rayen_backward_f32(const rayen_plan_t* p, const float* v, int64_t ldv, const float* gy,
+                                  const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
+                                  int mode, void* stream_) {
+  int rc = check_io(p, v, gy, B, mode);
+  if (rc) return rc;
+  if (B == 0) return RAYEN_OK;
+  if (!kappa || !active || !gv) return fail(RAYEN_ERR_BAD_ARGUMENT, "backward needs kappa, active and gv");
+  const PlanDev& d = p->dev;
+  const int need = d.n + (mode == RAYEN_MODE_RAYEN_OLD ? 1 : 0);
+  if (ldv < need || ldgv < need)
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "ldv=%lld / ldgv=%lld < %d", static_cast<long long>(ldv),
+                static_cast<long long>(ldgv), need);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int prev = 0;
+  RAYEN_CUDA(cudaGetDevice(&prev));
+  if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
+
+  const int block = 128;
+  long long grid = (B + block - 1) / block;
+  const long long cap = static_cast<long long>(p->sm_count) * 16;
+  if (grid > cap) grid = cap;
+  LqsBwdFn f = lqs_bwd_fn(d.np);
+  f<<<static_cast<int>(grid), block, 0, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
+  g_launches.fetch_add(1);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && d.lmi_r > 0) {
+    const int mpw = 32 / (d.lmi_rp / 4);
+    long long blocks = (B + static_cast<long long>(mpw) * (kLmiThreads / 32) - 1) / (static_cast<long long>(mpw) * (kLmiThreads / 32));
+    if (blocks > p->sm_count) blocks = p->sm_count;
+    LmiBwdFn lf = lmi_bwd_fn(d.lmi_rp, p->lmi_smem);
+    lf<<<static_cast<int>(blocks), kLmiThreads, p->lmi_smem_bytes, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+  }
+  if (prev != p->device) cudaSetDevice(prev);
+  if (e != cudaSuccess) return cuda_fail(e, "backward launch");
+  return RAYEN_OK;
+}
+
+// ----------------------------------------------------------------------------- host-buffer path
+extern "C" int64_t rayen_host_workspace_bytes(const rayen_plan_t* p, int64_t B) {
+  if (!p || B < 0) return -1;
+  const int64_t n = p->dev.n, k = p->dev.k;
+  // v | gy | y | gv | kappa | active, each rounded up to 256 B
+  auto r = [](int64_t x) { return (x + 255) / 256 * 256; };
+  return r(B * n * 4) * 2 + r(B * k * 4) * 2 + r(B * 4) * 2;
+}
+
+extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* p, const float* v_host, const float* gy_host,
+                                               float* y_host, float* gv_host, int64_t B, void* workspace,
+                                               void* stream_) {
+  if (!p || !v_host || !gy_host || !y_host || !gv_host || (!workspace && B > 0))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "null argument");
+  if (B == 0) return RAYEN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t n = p->dev.n, k = p->dev.k;
+  auto r = [](int64_t x) { return (x + 255) / 256 * 256; };
+  char* w = static_cast<char*>(workspace);
+  float* v = reinterpret_cast<float*>(w); w += r(B * n * 4);
+  float* gy = reinterpret_cast<float*>(w); w += r(B * k * 4);
+  float* y = reinterpret_cast<float*>(w); w += r(B * k * 4);
+  float* gv = reinterpret_cast<float*>(w); w += r(B * n * 4);
+  float* kappa = reinterpret_cast<float*>(w); w += r(B * 4);
+  int32_t* active = reinterpret_cast<int32_t*>(w);
+  int prev = 0;
+  RAYEN_CUDA(cudaGetDevice(&prev));
+  if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
+  int rc = 0;
+  cudaError_t e = cudaMemcpyAsync(v, v_host, B * n * 4, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(gy, gy_host, B * k * 4, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) rc = rayen_forward_f32(p, v, n, y, kappa, active, B, RAYEN_MODE_RAYEN, stream);
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(y_host, y, B * k * 4, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess && rc == 0)
+    rc = rayen_backward_f32(p, v, n, gy, kappa, active, gv, n, B, RAYEN_MODE_RAYEN, stream);
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(gv_host, gv, B * n * 4, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(stream);
+  if (prev != p->device) cudaSetDevice(prev);
+  if (e != cudaSuccess) return cuda_fail(e, "host-buffer forward+backward");
+  return rc;
+}

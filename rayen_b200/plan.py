@@ -1,0 +1,305 @@
+"""Host-side plan packer: constraint set -> the z-space constant block the sm_100a kernels read.
+
+One-time work, float64 numpy, then a single float32 blob laid out exactly as
+``include/rayen_b200.h`` (struct ``RayenPlanDesc``) describes.  It restates, in the subspace
+coordinates z (y = N z + yp), the per-constraint constants that the reference precomputes in
+``ConstraintModule.__init__`` (rayen/constraint_module.py:38 D; :43-52 H, L; :99-122 sigma, phi,
+delta) or recomputes on every forward call (:383-399: beta, tau and a' of each cone):
+
+    linear     D = A_p / (b_p - A_p z0)                                       kappa_j = D_j . u
+    quadratic  phi_z = N' phi,  G'G = N' Delta N   (G upper triangular)        kappa = phi_z.u + ||G u||
+    SOC        c_z = N'c, h = (M N)'beta - tau c_z, R'R = (M N)'(M N), A = tau^2 - |beta|^2
+               kappa = largest root of  -A kappa^2 + 2 (h.u) kappa + |R u|^2 - (c_z.u)^2
+    LMI        F~z_a = sum_i N[i,a] (-L' F_i L),  L = chol(H^-1), H = F(y0)   kappa = lambda_max(sum_a u_a F~z_a)
+
+so the ambient direction rho = N u is never formed on the device and every family costs O(n^2)
+per constraint and sample (the triangular factors halve the reference's dense forms).
+"""
+import ctypes
+
+import numpy as np
+
+ABI_VERSION = 3
+MAX_NP = 32
+MAX_LMI = 32
+
+
+class PlanError(RuntimeError):
+    pass
+
+
+def _round_up_pow2(x, choices=(4, 8, 16, 32)):
+    for c in choices:
+        if x <= c:
+            return c
+    return None
+
+
+def _bank_stride(words):
+    """Smallest stride >= words that is a multiple of 4 and = 4 (mod 32): consecutive items start 16 B
+    apart modulo the 128-B bank window, so 8 lanes reading 8 different items do not conflict."""
+    s = (words + 3) // 4 * 4
+    while s % 32 != 4:
+        s += 4
+    return s
+
+
+def _triangular_factor(S, np_):
+    """Upper-triangular T (np_ x np_, zero padded) with T'T = S for a symmetric PSD S (may be singular)."""
+    n = S.shape[0]
+    S = 0.5 * (S + S.T)
+    lam, Q = np.linalg.eigh(S)
+    G0 = np.sqrt(np.clip(lam, 0.0, None))[:, None] * Q.T
+    R = np.linalg.qr(G0, mode="r")
+    T = np.zeros((np_, np_))
+    T[: R.shape[0], :n] = np.triu(R)
+    return T
+
+
+def _pack_triangular(T):
+    """Row i keeps columns 4*floor(i/4) .. np-1."""
+    np_ = T.shape[0]
+    out = []
+    for i in range(np_):
+        out.append(T[i, (i // 4) * 4:])
+    return np.concatenate(out)
+
+
+def packed_triangular_words(np_):
+    return sum(np_ - (i // 4) * 4 for i in range(np_))
+
+
+class PackedPlan:
+    """Float32 blob + the integers of ``RayenPlanDesc``; also keeps the float64 pieces for tests."""
+
+    def __init__(self):
+        self.blob = None
+        self.fields = {}
+        self.f64 = {}
+
+    def desc(self):
+        from ._cabi import RayenPlanDesc
+        d = RayenPlanDesc()
+        for key, val in self.fields.items():
+            setattr(d, key, val)
+        d.abi_version = ABI_VERSION
+        d.blob_words = int(self.blob.size)
+        d.blob = self.blob.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        return d
+
+
+def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None):
+    """Pack a preprocessed feasible set.
+
+    ``A_p, b_p, NA_E, yp, z0`` are the fields of ``ConvexConstraints`` (reference constraints.py:366-436),
+    ``qcs`` = [(P,q,r)], ``socs`` = [(M,s,c,d)], ``lmi`` = [F_0..F_k] or None, all in the ambient space.
+    """
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    A_p, N = f64(A_p), f64(NA_E)
+    b_p, yp, z0 = f64(b_p).reshape(-1, 1), f64(yp).reshape(-1, 1), f64(z0).reshape(-1, 1)
+    k, n = N.shape
+    y0 = N @ z0 + yp
+    np_ = _round_up_pow2(n)
+    if np_ is None:
+        raise PlanError(f"subspace dimension n={n} > {MAX_NP} is not covered by the sm_100a kernels yet")
+    k_pad = (k + 3) // 4 * 4
+    plan = PackedPlan()
+    sections = []
+    cursor = 0
+
+    def add(arr):
+        nonlocal cursor
+        arr = np.asarray(arr, dtype=np.float64).reshape(-1)
+        pad = (-arr.size) % 4
+        if pad:
+            arr = np.concatenate((arr, np.zeros(pad)))
+        off = cursor
+        sections.append(arr)
+        cursor += arr.size
+        return off
+
+    # ---- linear rows (reference constraint_module.py:38)
+    slack = b_p - A_p @ z0
+    if np.any(slack <= 0):
+        raise PlanError("z0 is not strictly inside the linear constraints (b_p - A_p z0 must be > 0)")
+    D = A_p / slack
+    m = D.shape[0]
+    m_pad = (m + 3) // 4 * 4
+    Dp = np.zeros((m_pad, np_))
+    Dp[:m, :n] = D
+    lin_stride = 4 * np_ + 4
+    lin = np.zeros((m_pad // 4, lin_stride))
+    for c in range(m_pad // 4):
+        # [kk][i][e] = D[4c+i][4kk+e]
+        blockv = Dp[4 * c:4 * c + 4, :].reshape(4, np_ // 4, 4).transpose(1, 0, 2)
+        lin[c, :4 * np_] = blockv.reshape(-1)
+    off_lin = add(lin)
+
+    # ---- quadratic constraints (reference constraint_module.py:99-122)
+    tri_words = packed_triangular_words(np_)
+    quad_stride = _bank_stride(np_ + tri_words)
+    quad = np.zeros((max(len(qcs), 1), quad_stride))
+    quad_f64 = []
+    for i, (P, q, r) in enumerate(qcs):
+        P, q, r = f64(P), f64(q).reshape(-1, 1), float(np.asarray(r).reshape(-1)[0])
+        level = float(0.5 * y0.T @ P @ y0 + q.T @ y0 + r)
+        if level >= 0:
+            raise PlanError(f"y0 is not strictly inside quadratic constraint {i} (g(y0)={level})")
+        sigma = 2.0 * level
+        w = P @ y0 + q
+        phi = -w / sigma
+        Delta = (w @ w.T - 2.0 * level * P) / sigma ** 2
+        phi_z = (N.T @ phi)[:, 0]
+        Delta_z = N.T @ Delta @ N
+        G = _triangular_factor(Delta_z, np_)
+        quad[i, :n] = phi_z
+        quad[i, np_:np_ + tri_words] = _pack_triangular(G)
+        quad_f64.append((phi_z, Delta_z, G))
+    off_quad = add(quad) if len(qcs) else add(np.zeros(4))
+
+    # ---- second-order cones (reference constraint_module.py:383-399)
+    soc_stride = _bank_stride(2 * np_ + tri_words + 4)
+    soc = np.zeros((max(len(socs), 1), soc_stride))
+    soc_f64 = []
+    for j, (M, s, c, d) in enumerate(socs):
+        M, s, c, d = f64(M), f64(s).reshape(-1, 1), f64(c).reshape(-1, 1), float(np.asarray(d).reshape(-1)[0])
+        beta = M @ y0 + s
+        tau = float(c.T @ y0 + d)
+        A = tau * tau - float(beta.T @ beta)
+        if not (A > 0 and tau > 0):
+            raise PlanError(f"y0 is not strictly inside SOC constraint {j}")
+        Mz = M @ N
+        cz = (N.T @ c)[:, 0]
+        h = (Mz.T @ beta)[:, 0] - tau * cz
+        R = _triangular_factor(Mz.T @ Mz, np_)
+        soc[j, :n] = cz
+        soc[j, np_:np_ + n] = h
+        soc[j, 2 * np_:2 * np_ + tri_words] = _pack_triangular(R)
+        soc[j, 2 * np_ + tri_words] = A
+        soc_f64.append((cz, h, Mz, A, R))
+    off_soc = add(soc) if len(socs) else add(np.zeros(4))
+
+    # ---- N and y0
+    n_is_identity = int(k == n and np.array_equal(N, np.eye(k)))
+    nm = np.zeros((k, np_ + 4))
+    nm[:, :n] = N
+    off_nmat = add(nm) if not n_is_identity else add(np.zeros(4))
+    y0p = np.zeros(k_pad)
+    y0p[:k] = y0[:, 0]
+    off_y0 = add(y0p)
+
+    # ---- LMI (reference constraint_module.py:43-52 and :412-421, congruence folded into the constants)
+    lmi_r = lmi_rp = 0
+    off_lmi = add(np.zeros(4))
+    Fz = None
+    if lmi is not None:
+        allF = np.asarray([f64(F) for F in lmi])
+        lmi_r = allF.shape[1]
+        lmi_rp = _round_up_pow2(lmi_r)
+        if lmi_rp is None:
+            raise PlanError(f"LMI size r={lmi_r} > {MAX_LMI} is not covered by the sm_100a kernels yet")
+        H = allF[-1] + np.einsum("a,aij->ij", y0[:, 0], allF[:-1])
+        try:
+            L = np.linalg.cholesky(np.linalg.inv(H))
+        except np.linalg.LinAlgError:
+            raise PlanError("y0 is not strictly inside the LMI constraint (F(y0) must be positive definite)")
+        Ft = -np.einsum("ji,ajk,kl->ail", L, allF[:-1], L)
+        Fz = np.einsum("ia,ijk->ajk", N, Ft)
+        Fz = 0.5 * (Fz + Fz.transpose(0, 2, 1))
+        lpm = lmi_rp // 4
+        Fpad = np.zeros((n, lmi_rp, lmi_rp))
+        Fpad[:, :lmi_r, :lmi_r] = Fz
+        # [a][i][q][t] with column j = q + lpm*t
+        Fperm = Fpad.reshape(n, lmi_rp, 4, lpm).transpose(0, 1, 3, 2)
+        off_lmi = add(Fperm)
+
+    blob = np.concatenate(sections).astype(np.float32)
+    assert blob.size == cursor and cursor % 4 == 0
+    plan.blob = np.ascontiguousarray(blob)
+    plan.fields = dict(n=n, k=k, np=np_, k_pad=k_pad, m=m, m_pad=m_pad, n_quad=len(qcs), n_soc=len(socs),
+                       lmi_r=lmi_r, lmi_rp=lmi_rp, n_is_identity=n_is_identity,
+                       lin_chunk_stride=lin_stride, quad_stride=quad_stride, soc_stride=soc_stride,
+                       off_lin=off_lin, off_quad=off_quad, off_soc=off_soc, off_nmat=off_nmat,
+                       off_y0=off_y0, off_lmi=off_lmi)
+    plan.f64 = dict(D=D, N=N, y0=y0, z0=z0, yp=yp, quads=quad_f64, socs=soc_f64, Fz=Fz)
+    return plan
+
+
+def build_plan_from_constraints(cs):
+    """Pack a ``ConvexConstraints``-like object (this package's or the reference's)."""
+    qcs = [(qc.P, qc.q, qc.r) for qc in cs.qcs]
+    socs = [(sc.M, sc.s, sc.c, sc.d) for sc in cs.socs]
+    lmi = list(cs.lmic.all_F) if cs.lmic is not None else None
+    return build_plan(cs.A_p, cs.b_p, cs.NA_E, cs.yp, cs.z0, qcs, socs, lmi)
+
+
+# --------------------------------------------------------------------------- numpy model of the kernels
+def evaluate_plan_numpy(plan, v):
+    """Float64 evaluation of kappa and y straight from the PACKED blob (not from the original matrices).
+
+    Host-side self-check of the packer: it decodes the same words the kernels decode, so a layout bug
+    shows up on the CPU.  Not a fallback -- nothing in the product path calls it.
+    """
+    f = plan.fields
+    blob = plan.blob.astype(np.float64)
+    n, k, np_ = f["n"], f["k"], f["np"]
+    v = np.asarray(v, dtype=np.float64).reshape(-1, n)
+    B = v.shape[0]
+    s = np.linalg.norm(v, axis=1)
+    u = np.zeros((B, np_))
+    u[:, :n] = v / np.maximum(s, 1e-12)[:, None]
+    best = np.zeros(B)
+    act = np.zeros(B, dtype=np.int64)
+
+    def consider(val, tag):
+        nonlocal best, act
+        better = val > best
+        best = np.where(better, val, best)
+        act = np.where(better, tag, act)
+
+    for c in range(f["m_pad"] // 4):
+        base = f["off_lin"] + c * f["lin_chunk_stride"]
+        blk = blob[base:base + 4 * np_].reshape(np_ // 4, 4, 4).transpose(1, 0, 2).reshape(4, np_)
+        for i in range(4):
+            consider(u @ blk[i], (1 << 24) | (4 * c + i))
+
+    def unpack_tri(words):
+        T = np.zeros((np_, np_))
+        pos = 0
+        for i in range(np_):
+            c0 = (i // 4) * 4
+            T[i, c0:] = words[pos:pos + np_ - c0]
+            pos += np_ - c0
+        return T
+
+    tri_words = packed_triangular_words(np_)
+    for i in range(f["n_quad"]):
+        base = f["off_quad"] + i * f["quad_stride"]
+        phi = blob[base:base + np_]
+        G = unpack_tri(blob[base + np_:base + np_ + tri_words])
+        consider(u @ phi + np.linalg.norm(u @ G.T, axis=1), (2 << 24) | i)
+    for j in range(f["n_soc"]):
+        base = f["off_soc"] + j * f["soc_stride"]
+        cz, h = blob[base:base + np_], blob[base + np_:base + 2 * np_]
+        R = unpack_tri(blob[base + 2 * np_:base + 2 * np_ + tri_words])
+        A = blob[base + 2 * np_ + tri_words]
+        hb, cu = u @ h, u @ cz
+        cq = np.sum((u @ R.T) ** 2, axis=1) - cu ** 2
+        root = np.sqrt(np.maximum(hb * hb + A * cq, 0.0))
+        consider((hb + root) / A, (3 << 24) | j)
+    if f["lmi_r"]:
+        rp = f["lmi_rp"]
+        lpm = rp // 4
+        Fperm = blob[f["off_lmi"]:f["off_lmi"] + n * rp * rp].reshape(n, rp, lpm, 4)
+        Fz = Fperm.transpose(0, 1, 3, 2).reshape(n, rp, rp)
+        S = np.einsum("ba,aij->bij", u[:, :n], Fz)
+        consider(np.linalg.eigvalsh(S)[:, -1], 4 << 24)
+    with np.errstate(divide="ignore"):
+        alpha = np.minimum(np.where(best > 0, 1.0 / np.where(best > 0, best, 1.0), np.inf), s)
+    y0 = blob[f["off_y0"]:f["off_y0"] + k]
+    if f["n_is_identity"]:
+        rho = u[:, :n]
+    else:
+        Nm = blob[f["off_nmat"]:f["off_nmat"] + k * (np_ + 4)].reshape(k, np_ + 4)[:, :np_]
+        rho = u @ Nm.T
+    return y0[None, :] + alpha[:, None] * rho, best, act
