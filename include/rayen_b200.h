@@ -116,6 +116,15 @@ int rayen_backward_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, co
                        const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
                        int mode, void* cuda_stream);
 
+/* Per-kernel launches for profiling and the roofline measurement in bench.py: stage_mask bit 0 = the
+ * linear/quadratic/SOC kernel, bit 1 = the LMI kernel (3 = what rayen_forward_f32 / rayen_backward_f32
+ * launch).  With stage_mask == 2 the kappa/active buffers must already hold the first stage's result. */
+int rayen_forward_stage_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, float* y, float* kappa,
+                            int32_t* active, int64_t B, int mode, int stage_mask, void* cuda_stream);
+int rayen_backward_stage_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, const float* gy,
+                             const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
+                             int mode, int stage_mask, void* cuda_stream);
+
 /* Host-buffer variants (the end-to-end path): host->device copies, the kernels, device->host
  * copies, all on `cuda_stream`, which is synchronised before returning.  Host buffers should be
  * pinned.  `workspace` is a device buffer of rayen_host_workspace_bytes(plan, B) bytes. */

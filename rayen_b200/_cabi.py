@@ -47,6 +47,10 @@ SYMBOLS = {
     "rayen_forward_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, ctypes.c_int64, ctypes.c_int, _P]),
     "rayen_backward_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_int64,
                                           ctypes.c_int, _P]),
+    "rayen_forward_stage_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, ctypes.c_int64, ctypes.c_int,
+                                               ctypes.c_int, _P]),
+    "rayen_backward_stage_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, _P, ctypes.c_int64,
+                                                ctypes.c_int64, ctypes.c_int, ctypes.c_int, _P]),
     "rayen_host_workspace_bytes": (ctypes.c_int64, [_P, ctypes.c_int64]),
     "rayen_forward_backward_host_f32": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int64, _P, _P]),
     "rayen_launch_count": (ctypes.c_int64, []),

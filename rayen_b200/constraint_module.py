@@ -182,6 +182,35 @@ class ConstraintModule(nn.Module):
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._device_plan(device).set_tuning(samples_per_thread, lanes_per_sample)
 
+    def forward_backward_host(self, v_host, gy_host, y_host=None, gv_host=None, device=None):
+        """End-to-end step on HOST buffers through ``rayen_forward_backward_host_f32``: copies ``v_host`` [B,n]
+        and ``gy_host`` [B,k] (float32, ideally pinned) to the GPU, runs forward + backward, copies ``y`` [B,k]
+        and ``g_v`` [B,n] back and synchronises.  method='RAYEN' only.  Returns (y_host, gv_host)."""
+        utils.verify(self._mode == _cabi.MODE_RAYEN, "forward_backward_host supports method='RAYEN'")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        for t in (v_host, gy_host):
+            utils.verify(t.dtype == torch.float32 and t.is_contiguous() and not t.is_cuda, "host float32 contiguous tensors expected")
+        B = v_host.shape[0]
+        utils.verify(tuple(v_host.shape) == (B, self.n) and tuple(gy_host.shape) == (B, self.k), "bad shapes")
+        if y_host is None:
+            y_host = torch.empty((B, self.k), dtype=torch.float32).pin_memory()
+        if gv_host is None:
+            gv_host = torch.empty((B, self.n), dtype=torch.float32).pin_memory()
+        lib = _cabi.lib()
+        dev_plan = self._device_plan(device)
+        need = lib.rayen_host_workspace_bytes(dev_plan.handle, B)
+        ws = getattr(self, "_host_ws", None)
+        if ws is None or ws.numel() < need or ws.device != device:
+            ws = torch.empty((max(int(need), 256),), dtype=torch.uint8, device=device)
+            self._host_ws = ws
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            rc = lib.rayen_forward_backward_host_f32(dev_plan.handle, v_host.data_ptr(), gy_host.data_ptr(),
+                                                     y_host.data_ptr(), gv_host.data_ptr(), B, ws.data_ptr(),
+                                                     ctypes.c_void_p(stream))
+        _cabi.check(rc, "rayen_forward_backward_host_f32")
+        return y_host, gv_host
+
     def last_kappa_and_active(self):
         """(kappa[B], active[B]) of the most recent forward: active = family << 24 | constraint index."""
         return self._last

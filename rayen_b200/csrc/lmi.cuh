@@ -107,115 +107,128 @@ struct LmiSolver {
   }
 
   // ---- 2. Householder tridiagonalisation.  Afterwards sd()/se() hold the diagonal / sub-diagonal and,
-  //         if WANT_GRAD, row k of A holds this lane's part of reflector k.
-  template <int K>
-  __device__ __forceinline__ void householder_step(float (&dd)[4], float (&ee)[4]) {
-    constexpr int q1 = (K + 1) % LPM, t1 = (K + 1) / LPM;
-    float xo[4];
+  //         if WANT_GRAD, the dead column k of A (in its owner lane) holds reflector k.
+  // The RP-2 reduction steps run as 4 runtime loops ("stages") instead of RP-2 unrolled bodies: stage S
+  // covers k in [LPM*S, LPM*(S+1)), during which column slots < S are dead, slot S is partly live and
+  // rows < LPM*S are dead -- all compile-time facts, so the register file is still indexed statically
+  // while the code stays small enough for the instruction cache.
+  template <int S>
+  __device__ __forceinline__ void householder_stage() {
+    constexpr int R0 = LPM * S;
+    constexpr int K_END = (LPM * (S + 1) < RP - 2) ? LPM * (S + 1) : RP - 2;
+    constexpr int I4 = R0 / 4;      // first float4 of rows that can be live
+    constexpr int EDGE = R0 + LPM;  // rows <= EDGE change role with k inside the stage
+    if constexpr (R0 < RP - 2) {
+      for (int k = R0; k < K_END; ++k) {
+        const int kk = k - R0;
+        if (q == kk) {
+          // the owner of column k builds the reflector from its column (= row k, by symmetry)
+          float tail2 = 0.f, xk1 = 0.f, dk = 0.f;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) xo[t] = (q + LPM * t > K) ? A[K][t] : 0.f;
-    const float xk1 = __shfl_sync(0xffffffffu, A[K][t1], grp_base + q1);
-    float loc = 0.f;
+          for (int i = 4 * I4; i < RP; ++i) {
+            const float c = A[i][S];
+            if (i <= EDGE) {
+              if (i == k) dk = c;
+              if (i == k + 1) xk1 = c;
+              if (i > k + 1) tail2 = fmaf(c, c, tail2);
+            } else {
+              tail2 = fmaf(c, c, tail2);
+            }
+          }
+          const float sigma = fmaf(xk1, xk1, tail2);
+          const float rt = sqrtf(sigma);
+          const float alpha = (xk1 >= 0.f) ? -rt : rt;
+          const bool skip = !(tail2 > 0.f);  // column already tridiagonal (also covers zero padding)
+          const float tau = skip ? 0.f : 1.0f / fmaf(fabsf(xk1), rt, sigma);
+          sd()[k] = dk;
+          se()[k] = skip ? xk1 : alpha;
+          sx0()[0] = tau;
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
-      if (q + LPM * t > K + 1) loc = fmaf(xo[t], xo[t], loc);
-    const float tail2 = group_sum<LPM>(loc);
-    const float sigma = fmaf(xk1, xk1, tail2);
-    const float rt = sqrtf(sigma);
-    const float alpha = (xk1 >= 0.f) ? -rt : rt;
-    const bool skip = !(tail2 > 0.f);  // column already tridiagonal (also covers zero padding)
-    const float tau = skip ? 0.f : 1.0f / fmaf(fabsf(xk1), rt, sigma);
-    const float ek = skip ? xk1 : alpha;
-    if (q == K % LPM) {
-      dd[K / LPM] = A[K][K / LPM];
-      ee[K / LPM] = ek;
-    }
-    float vo[4];
+          for (int i4 = I4; i4 < RP / 4; ++i4) {
+            float vv[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      vo[t] = xo[t];
-      if (q + LPM * t == K + 1) vo[t] = xk1 - alpha;
-      if (skip) vo[t] = 0.f;
-      sv()[q + LPM * t] = vo[t];
-    }
-    __syncwarp();
-    // p = tau * A v over the live rows (> K); slot t is live while it still has a column > K
-    constexpr int I4 = (K + 1) / 4;
-    float vr[RP];
-#pragma unroll
-    for (int i4 = I4; i4 < RP / 4; ++i4) {
-      const float4 x = ld4(sv() + 4 * i4);
-      vr[4 * i4 + 0] = x.x;
-      vr[4 * i4 + 1] = x.y;
-      vr[4 * i4 + 2] = x.z;
-      vr[4 * i4 + 3] = x.w;
-    }
-    float p[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = K + 1; i < RP; ++i)
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (LPM * t + LPM - 1 > K) p[t] = fmaf(A[i][t], vr[i], p[t]);
-    loc = 0.f;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      p[t] *= tau;
-      loc = fmaf(vo[t], p[t], loc);
-    }
-    const float Kc = 0.5f * tau * group_sum<LPM>(loc);
-    float wo[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      wo[t] = (q + LPM * t > K) ? fmaf(-Kc, vo[t], p[t]) : 0.f;
-      sw()[q + LPM * t] = wo[t];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i4 = I4; i4 < RP / 4; ++i4) {
-      const float4 x = ld4(sw() + 4 * i4);
-      const float wr[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-      for (int ii = 0; ii < 4; ++ii) {
-        const int i = 4 * i4 + ii;
-        if (i > K) {
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            if (LPM * t + LPM - 1 > K) A[i][t] = fmaf(-vr[i], wo[t], fmaf(-wr[ii], vo[t], A[i][t]));
+            for (int ii = 0; ii < 4; ++ii) {
+              const int i = 4 * i4 + ii;
+              float val = A[i][S];
+              if (i <= EDGE) val = (i > k + 1) ? val : ((i == k + 1) ? (xk1 - alpha) : 0.f);
+              if (skip) val = 0.f;
+              vv[ii] = val;
+              if constexpr (WANT_GRAD) A[i][S] = val;
+            }
+            *reinterpret_cast<float4*>(sv() + 4 * i4) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+          }
         }
-      }
-    }
-    if constexpr (WANT_GRAD) {
+        __syncwarp();
+        const float tau = sx0()[0];
+        float vr[RP];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) A[K][t] = vo[t];
-    }
-    __syncwarp();  // scratch v/w are rewritten by the next step
-  }
-
-  template <int K>
-  __device__ __forceinline__ void householder_all(float (&dd)[4], float (&ee)[4]) {
-    if constexpr (K < RP - 2) {
-      householder_step<K>(dd, ee);
-      householder_all<K + 1>(dd, ee);
+        for (int i4 = I4; i4 < RP / 4; ++i4) {
+          const float4 x = ld4(sv() + 4 * i4);
+          vr[4 * i4 + 0] = x.x;
+          vr[4 * i4 + 1] = x.y;
+          vr[4 * i4 + 2] = x.z;
+          vr[4 * i4 + 3] = x.w;
+        }
+        float vo[4], p[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          vo[t] = (t >= S) ? sv()[q + LPM * t] : 0.f;
+          p[t] = 0.f;
+        }
+        // p = tau * A v (dead rows carry v_i = 0)
+#pragma unroll
+        for (int i = 4 * I4; i < RP; ++i)
+#pragma unroll
+          for (int t = S; t < 4; ++t) p[t] = fmaf(A[i][t], vr[i], p[t]);
+        float loc = 0.f;
+#pragma unroll
+        for (int t = S; t < 4; ++t) {
+          p[t] *= tau;
+          loc = fmaf(vo[t], p[t], loc);
+        }
+        const float Kc = 0.5f * tau * group_sum<LPM>(loc);
+        float wo[4];
+#pragma unroll
+        for (int t = S; t < 4; ++t) {
+          const bool live = (t > S) || (q > kk);
+          wo[t] = live ? fmaf(-Kc, vo[t], p[t]) : 0.f;
+          sw()[q + LPM * t] = wo[t];
+        }
+        __syncwarp();
+        // A <- A - v w' - w v'
+#pragma unroll
+        for (int i4 = I4; i4 < RP / 4; ++i4) {
+          const float4 x = ld4(sw() + 4 * i4);
+          const float wr[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const int i = 4 * i4 + ii;
+#pragma unroll
+            for (int t = S; t < 4; ++t) A[i][t] = fmaf(-vr[i], wo[t], fmaf(-wr[ii], vo[t], A[i][t]));
+          }
+        }
+        __syncwarp();  // scratch v/w/tau are rewritten by the next step
+      }
     }
   }
 
   __device__ __forceinline__ void tridiagonalize() {
-    float dd[4] = {0.f, 0.f, 0.f, 0.f}, ee[4] = {0.f, 0.f, 0.f, 0.f};
-    householder_all<0>(dd, ee);
+    // sw must start clean: entries of dead column slots are read (times v_i = 0) but never rewritten
+#pragma unroll
+    for (int t = 0; t < 4; ++t) sw()[q + LPM * t] = 0.f;
+    householder_stage<0>();
+    householder_stage<1>();
+    householder_stage<2>();
+    householder_stage<3>();
     // trailing 2x2 block
     constexpr int K2 = RP - 2, K1 = RP - 1;
     if (q == K2 % LPM) {
-      dd[K2 / LPM] = A[K2][K2 / LPM];
-      ee[K2 / LPM] = A[K1][K2 / LPM];
+      sd()[K2] = A[K2][K2 / LPM];
+      se()[K2] = A[K1][K2 / LPM];
     }
     if (q == K1 % LPM) {
-      dd[K1 / LPM] = A[K1][K1 / LPM];
-      ee[K1 / LPM] = 0.f;
-    }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      sd()[q + LPM * t] = dd[t];
-      se()[q + LPM * t] = ee[t];
+      sd()[K1] = A[K1][K1 / LPM];
+      se()[K1] = 0.f;
     }
     __syncwarp();
   }
@@ -264,7 +277,7 @@ struct LmiSolver {
         if constexpr (!WANT_GRAD) {
 #pragma unroll
           for (int i = 0; i < RP; ++i) {
-            piv = (d[i] - x) - (i == 0 ? 0.f : e2[i] * __frcp_rn(piv));
+            piv = (d[i] - x) - (i == 0 ? 0.f : __fdividef(e2[i], piv));
             if (fabsf(piv) < pivmin) piv = -pivmin;
             neg += (piv < 0.f) ? 1 : 0;
           }
@@ -272,7 +285,7 @@ struct LmiSolver {
           float eprev = 0.f;
           for (int i = 0; i < RP; ++i) {
             const float di = sd()[i];
-            piv = (di - x) - (i == 0 ? 0.f : eprev * eprev * __frcp_rn(piv));
+            piv = (di - x) - (i == 0 ? 0.f : __fdividef(eprev * eprev, piv));
             if (fabsf(piv) < pivmin) piv = -pivmin;
             neg += (piv < 0.f) ? 1 : 0;
             eprev = se()[i];
@@ -291,7 +304,7 @@ struct LmiSolver {
   }
 
   // ---- 4. unit eigenvector of lambda (backward only): twisted factorisation of T - lambda I on one
-  // lane per matrix, then q = H_0 ... H_{RP-3} z with the reflectors kept in the dead rows of A.
+  // lane per matrix, then q = H_0 ... H_{RP-3} z with the reflectors kept in the dead columns of A.
   __device__ __forceinline__ void eigenvector(float lam, float (&qo)[4]) {
     static_assert(WANT_GRAD, "eigenvector needs the reflectors");
     float* dp = sx0();
@@ -341,37 +354,54 @@ struct LmiSolver {
       for (int i = 0; i < RP; ++i) z[i] *= inv;
     }
     __syncwarp();
+    // q = H_0 ... H_{RP-3} z, in place in the scratch; reflector k sits in the dead column k of its owner lane
+    back_stage<3>(z);
+    back_stage<2>(z);
+    back_stage<1>(z);
+    back_stage<0>(z);
 #pragma unroll
     for (int t = 0; t < 4; ++t) qo[t] = z[q + LPM * t];
-    __syncwarp();
-    back_transform<RP - 3>(qo);
   }
 
-  template <int K>
-  __device__ __forceinline__ void back_transform(float (&qo)[4]) {
-    if constexpr (K >= 0) {
-      float dot = 0.f, vv = 0.f;
+  template <int S>
+  __device__ __forceinline__ void back_stage(float* z) {
+    constexpr int R0 = LPM * S;
+    constexpr int K_END = (LPM * (S + 1) < RP - 2) ? LPM * (S + 1) : RP - 2;
+    constexpr int I4 = R0 / 4;
+    if constexpr (R0 < RP - 2) {
+      for (int k = K_END - 1; k >= R0; --k) {
+        if (q == k - R0) {
+          float zz[RP];
+          float dot = 0.f, vv = 0.f;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        dot = fmaf(A[K][t], qo[t], dot);
-        vv = fmaf(A[K][t], A[K][t], vv);
+          for (int i4 = I4; i4 < RP / 4; ++i4) {
+            const float4 x = ld4(z + 4 * i4);
+            zz[4 * i4 + 0] = x.x;
+            zz[4 * i4 + 1] = x.y;
+            zz[4 * i4 + 2] = x.z;
+            zz[4 * i4 + 3] = x.w;
+          }
+#pragma unroll
+          for (int i = 4 * I4; i < RP; ++i) {
+            dot = fmaf(A[i][S], zz[i], dot);
+            vv = fmaf(A[i][S], A[i][S], vv);
+          }
+          const float c = vv > 0.f ? 2.0f * dot / vv : 0.f;
+#pragma unroll
+          for (int i4 = I4; i4 < RP / 4; ++i4)
+            *reinterpret_cast<float4*>(z + 4 * i4) =
+                make_float4(fmaf(-c, A[4 * i4 + 0][S], zz[4 * i4 + 0]), fmaf(-c, A[4 * i4 + 1][S], zz[4 * i4 + 1]),
+                            fmaf(-c, A[4 * i4 + 2][S], zz[4 * i4 + 2]), fmaf(-c, A[4 * i4 + 3][S], zz[4 * i4 + 3]));
+        }
+        __syncwarp();
       }
-      dot = group_sum<LPM>(dot);
-      vv = group_sum<LPM>(vv);
-      const float c = vv > 0.f ? 2.0f * dot / vv : 0.f;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) qo[t] = fmaf(-c, A[K][t], qo[t]);
-      back_transform<K - 1>(qo);
     }
   }
 
   // d kappa/du_a = q' F~z_a q for the entries a = q + LPM*slot owned by this lane
   __device__ __forceinline__ void eig_gradient(const float* __restrict__ F, int n, const float (&qo)[4],
                                                float (&dk)[C::NPL]) {
-    float* qs = sw();
-#pragma unroll
-    for (int t = 0; t < 4; ++t) qs[q + LPM * t] = qo[t];
-    __syncwarp();
+    const float* qs = sv();  // left there by eigenvector()
     float qa[RP];
 #pragma unroll
     for (int i4 = 0; i4 < RP / 4; ++i4) {
@@ -521,16 +551,16 @@ __global__ void __launch_bounds__(kLmiThreads, 1)
 // Only the samples whose binding constraint is the LMI and whose gradient needs d kappa/du are
 // processed; everything else was written by lqs_backward_kernel.  The work list is the batch itself:
 // a matrix group whose sample is not one of those skips to the next (warp-uniform when none is).
-template <int RP, bool F_SMEM>
+template <int RP>
 __global__ void __launch_bounds__(kLmiThreads, 1)
     lmi_backward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, const float* __restrict__ gy,
                         const float* __restrict__ kappa, const int* __restrict__ active, float* __restrict__ gv,
                         long long ldgv, long long B, int mode) {
   using C = LmiCfg<RP>;
+  constexpr bool F_SMEM = false;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  float* scratch_base;
-  const float* F = lmi_stage<RP, F_SMEM>(P, smem_raw, bars, &scratch_base);
+  float* scratch_base = reinterpret_cast<float*>(smem_raw + 64);
+  const float* F = P.blob + P.off_lmi;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   LmiSolver<RP, true, F_SMEM> S;
@@ -542,7 +572,6 @@ __global__ void __launch_bounds__(kLmiThreads, 1)
   const float* nmat = P.blob + P.off_nmat;
   const long long warp_id = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
   const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-  bool staged = !F_SMEM;
 
   for (long long base = warp_id * C::MPW; base < B; base += n_warps * C::MPW) {
     const long long b = base + grp;
@@ -555,10 +584,6 @@ __global__ void __launch_bounds__(kLmiThreads, 1)
     const float s = S.load_direction(v + b * ldv, n, mine);
     if (mine && mode == RAYEN_MODE_RAYEN) mine = (1.0f / kap < s);
     if (__ballot_sync(0xffffffffu, mine) == 0u) continue;  // warp-uniform
-    if (!staged) {
-      mbar_wait(&bars[0], 0);
-      staged = true;
-    }
     // groups that are not `mine` run on u = 0 (a zero matrix) and write nothing
     if (!mine) {
       for (int a = S.q; a < kLmiMaxN; a += C::LPM) S.su()[a] = 0.f;
@@ -620,9 +645,6 @@ __global__ void __launch_bounds__(kLmiThreads, 1)
       if (mode == RAYEN_MODE_RAYEN_OLD && S.q == 0) gv[b * ldgv + n] = gbeta;
     }
     __syncwarp();
-  }
-  if constexpr (F_SMEM) {
-    if (!staged) mbar_wait(&bars[0], 0);
   }
 }
 

@@ -23,7 +23,7 @@ struct rayen_plan {
   float* d_blob;
   bool lqs_smem;  // LQS constants fit in shared memory
   bool lmi_smem;  // LMI matrices fit in shared memory
-  size_t lqs_smem_bytes, lmi_smem_bytes;
+  size_t lqs_smem_bytes, lmi_smem_bytes, lmi_bwd_smem_bytes;
   bool has_lqs;   // any linear row / quadratic / cone (the linear section always has >= 1 row)
 };
 
@@ -98,12 +98,14 @@ static LmiFwdFn lmi_fwd_fn(int rp, bool smem) {
     default: return smem ? lmi_forward_kernel<32, true> : lmi_forward_kernel<32, false>;
   }
 }
-static LmiBwdFn lmi_bwd_fn(int rp, bool smem) {
+// the backward LMI kernel reads F~z through L1/L2: only the few samples whose binding constraint is the
+// LMI need it, so staging 128 KB per CTA would cost more than it saves
+static LmiBwdFn lmi_bwd_fn(int rp) {
   switch (rp) {
-    case 4: return smem ? lmi_backward_kernel<4, true> : lmi_backward_kernel<4, false>;
-    case 8: return smem ? lmi_backward_kernel<8, true> : lmi_backward_kernel<8, false>;
-    case 16: return smem ? lmi_backward_kernel<16, true> : lmi_backward_kernel<16, false>;
-    default: return smem ? lmi_backward_kernel<32, true> : lmi_backward_kernel<32, false>;
+    case 4: return lmi_backward_kernel<4>;
+    case 8: return lmi_backward_kernel<8>;
+    case 16: return lmi_backward_kernel<16>;
+    default: return lmi_backward_kernel<32>;
   }
 }
 static size_t lmi_smem(int rp, bool smem, int n, int threads) {
@@ -214,7 +216,8 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
     p->lmi_smem = p->lmi_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
     if (!p->lmi_smem) p->lmi_smem_bytes = lmi_smem(v.lmi_rp, false, v.n, kLmiThreads);
     rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_fn(v.lmi_rp, p->lmi_smem)), p->lmi_smem_bytes);
-    if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_bwd_fn(v.lmi_rp, p->lmi_smem)), p->lmi_smem_bytes);
+    p->lmi_bwd_smem_bytes = lmi_smem(v.lmi_rp, false, v.n, kLmiThreads);
+    if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_bwd_fn(v.lmi_rp)), p->lmi_bwd_smem_bytes);
   }
   cudaSetDevice(prev);
   if (rc != 0) {
@@ -257,7 +260,7 @@ extern "C" int rayen_plan_kernel_info(const rayen_plan_t* p, RayenKernelInfo* ou
   if (p->dev.lmi_r > 0) {
     RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_fwd_fn(p->dev.lmi_rp, p->lmi_smem))));
     out->regs_lmi_fwd = a.numRegs;
-    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_bwd_fn(p->dev.lmi_rp, p->lmi_smem))));
+    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_bwd_fn(p->dev.lmi_rp))));
     out->regs_lmi_bwd = a.numRegs;
   }
   out->smem_lqs_bytes = static_cast<int>(p->lqs_smem_bytes);
@@ -282,39 +285,37 @@ struct LqsGeom {
   int tm, lanes, block, grid;
 };
 
-// One wave of persistent CTAs: pick the samples-per-thread tile TM (register reuse of every LDS) and
-// the lanes-per-sample split L (parallelism when the batch alone cannot fill 148 SMs).
+// Pick the samples-per-thread tile TM (register reuse of every LDS.128) and the lanes-per-sample split L
+// (parallelism when the batch alone cannot fill 148 SMs).  Rule fitted to a sweep on B200
+// (scripts/sweep_lqs.py): aim at ~8 warps per SM; prefer TM = 2 for 32-wide directions (128 registers,
+// no spills) and TM = 4 below; never split a sample over more than 8 lanes.
 static LqsGeom lqs_geometry(const rayen_plan* p, long long B) {
   const PlanDev& v = p->dev;
   int items = v.m_pad / 4;
   if (v.n_quad > items) items = v.n_quad;
   if (v.n_soc > items) items = v.n_soc;
-  const int max_lanes = ceil_pow2(items) > 32 ? 32 : ceil_pow2(items);
+  int max_lanes = ceil_pow2(items);
+  if (max_lanes > 8) max_lanes = 8;
+  const long long target = static_cast<long long>(p->sm_count) * 256;
   LqsGeom g{};
   int tm = p->tune_tm;
+  int lanes = p->tune_lanes;
   if (tm == 0) {
-    tm = 1;
-    for (int cand = 4; cand >= 1; cand /= 2) {
-      const long long cap = static_cast<long long>(p->sm_count) * lqs_max_threads(v.np, cand);
+    for (int cand = (v.np >= 32 ? 2 : 4); cand >= 1; cand /= 2) {
       const long long tiles = (B + cand - 1) / cand;
-      long long lanes = cap / (tiles > 0 ? tiles : 1);
-      if (lanes > max_lanes) lanes = max_lanes;
-      if (lanes < 1) lanes = 1;
-      if (tiles * floor_pow2(lanes) * 2 >= cap || cand == 1) {
-        tm = cand;
-        break;
-      }
+      long long l = floor_pow2(target / (tiles > 0 ? tiles : 1) > 0 ? target / (tiles > 0 ? tiles : 1) : 1);
+      if (l > max_lanes) l = max_lanes;
+      tm = cand;
+      if (tiles * l * 2 >= target) break;
     }
   }
-  const long long cap = static_cast<long long>(p->sm_count) * lqs_max_threads(v.np, tm);
   const long long tiles = (B + tm - 1) / tm;
-  int lanes = p->tune_lanes;
   if (lanes == 0) {
-    long long l = cap / (tiles > 0 ? tiles : 1);
-    if (l < 1) l = 1;
-    lanes = floor_pow2(l);
+    long long l = target / (tiles > 0 ? tiles : 1);
+    lanes = floor_pow2(l > 0 ? l : 1);
     if (lanes > max_lanes) lanes = max_lanes;
   }
+  const long long cap = static_cast<long long>(p->sm_count) * lqs_max_threads(v.np, tm);
   const long long threads = tiles * lanes;
   int block = lqs_max_threads(v.np, tm);
   if (threads <= cap) {
@@ -342,8 +343,24 @@ static int check_io(const rayen_plan* p, const void* a, const void* b, long long
 }
 
 // ----------------------------------------------------------------------------- forward / backward
+static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa, int32_t* active,
+                        int64_t B, int mode, void* stream_, int stage_mask);
+
 extern "C" int rayen_forward_f32(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa,
                                  int32_t* active, int64_t B, int mode, void* stream_) {
+  return forward_impl(p, v, ldv, y, kappa, active, B, mode, stream_, 3);
+}
+extern "C" int rayen_forward_stage_f32(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa,
+                                       int32_t* active, int64_t B, int mode, int stage_mask, void* stream_) {
+  if (stage_mask < 1 || stage_mask > 3) return fail(RAYEN_ERR_BAD_ARGUMENT, "stage_mask must be 1, 2 or 3");
+  return forward_impl(p, v, ldv, y, kappa, active, B, mode, stream_, stage_mask);
+}
+extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, int64_t ldv, const float* gy,
+                                        const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
+                                        int mode, int stage_mask, void* stream_);
+
+static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa, int32_t* active,
+                        int64_t B, int mode, void* stream_, int stage_mask) {
   int rc = check_io(p, v, y, B, mode);
   if (rc) return rc;
   if (B == 0) return RAYEN_OK;
@@ -358,12 +375,15 @@ extern "C" int rayen_forward_f32(const rayen_plan_t* p, const float* v, int64_t 
   RAYEN_CUDA(cudaGetDevice(&prev));
   if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
 
-  const LqsGeom g = lqs_geometry(p, B);
-  LqsFwdFn f = lqs_fwd_fn(d.np, g.tm, p->lqs_smem);
-  f<<<g.grid, g.block, p->lqs_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode, g.lanes, has_lmi ? 0 : 1);
-  g_launches.fetch_add(1);
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess && has_lmi) {
+  cudaError_t e = cudaSuccess;
+  if (stage_mask & 1) {
+    const LqsGeom g = lqs_geometry(p, B);
+    LqsFwdFn f = lqs_fwd_fn(d.np, g.tm, p->lqs_smem);
+    f<<<g.grid, g.block, p->lqs_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode, g.lanes, has_lmi ? 0 : 1);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && has_lmi && (stage_mask & 2)) {
     const int mpw = 32 / (d.lmi_rp / 4);
     long long blocks = (B + static_cast<long long>(mpw) * (kLmiThreads / 32) - 1) / (static_cast<long long>(mpw) * (kLmiThreads / 32));
     if (blocks > p->sm_count) blocks = p->sm_count;
@@ -380,6 +400,13 @@ extern "C" int rayen_forward_f32(const rayen_plan_t* p, const float* v, int64_t 
 extern "C" int rayen_backward_f32(const rayen_plan_t* p, const float* v, int64_t ldv, const float* gy,
                                   const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
                                   int mode, void* stream_) {
+  return rayen_backward_stage_f32(p, v, ldv, gy, kappa, active, gv, ldgv, B, mode, 3, stream_);
+}
+
+extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, int64_t ldv, const float* gy,
+                                        const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
+                                        int mode, int stage_mask, void* stream_) {
+  if (stage_mask < 1 || stage_mask > 3) return fail(RAYEN_ERR_BAD_ARGUMENT, "stage_mask must be 1, 2 or 3");
   int rc = check_io(p, v, gy, B, mode);
   if (rc) return rc;
   if (B == 0) return RAYEN_OK;
@@ -398,16 +425,19 @@ extern "C" int rayen_backward_f32(const rayen_plan_t* p, const float* v, int64_t
   long long grid = (B + block - 1) / block;
   const long long cap = static_cast<long long>(p->sm_count) * 16;
   if (grid > cap) grid = cap;
-  LqsBwdFn f = lqs_bwd_fn(d.np);
-  f<<<static_cast<int>(grid), block, 0, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
-  g_launches.fetch_add(1);
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess && d.lmi_r > 0) {
+  cudaError_t e = cudaSuccess;
+  if (stage_mask & 1) {
+    LqsBwdFn f = lqs_bwd_fn(d.np);
+    f<<<static_cast<int>(grid), block, 0, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && d.lmi_r > 0 && (stage_mask & 2)) {
     const int mpw = 32 / (d.lmi_rp / 4);
     long long blocks = (B + static_cast<long long>(mpw) * (kLmiThreads / 32) - 1) / (static_cast<long long>(mpw) * (kLmiThreads / 32));
     if (blocks > p->sm_count) blocks = p->sm_count;
-    LmiBwdFn lf = lmi_bwd_fn(d.lmi_rp, p->lmi_smem);
-    lf<<<static_cast<int>(blocks), kLmiThreads, p->lmi_smem_bytes, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
+    LmiBwdFn lf = lmi_bwd_fn(d.lmi_rp);
+    lf<<<static_cast<int>(blocks), kLmiThreads, p->lmi_bwd_smem_bytes, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
     g_launches.fetch_add(1);
     e = cudaGetLastError();
   }
