@@ -120,10 +120,19 @@ class TorchOracle:
         alpha = torch.minimum(1 / kap, norm_v)
         return self.NA_E @ (self.z0 + alpha * u) + self.yp
 
-    def forward_backward(self, v, gy):
-        """Returns (y:[B,k], g_v:[B,n]) for the scalar loss sum(y * gy), via autograd like the reference."""
-        v = v.detach().clone().to(self.dtype).reshape(v.shape[0], self.n).requires_grad_(True)
-        y = self.forward(v)
+    def forward_old(self, q):
+        """forwardForRAYENOld (constraint_module.py:460-466).  q:[B,n+1] (beta last) -> y:[B,k,1]."""
+        q = q.reshape(q.shape[0], self.n + 1, 1).to(self.dtype)
+        v, beta = q[:, 0:self.n, 0:1], q[:, self.n:self.n + 1, 0:1]
+        u = torch.nn.functional.normalize(v, dim=1)
+        alpha = 1 / (torch.exp(beta) + self.kappa(u))
+        return self.NA_E @ (self.z0 + alpha * u) + self.yp
+
+    def forward_backward(self, v, gy, method="RAYEN"):
+        """Returns (y:[B,k], g_v:[B,n(+1)]) for the scalar loss sum(y * gy), via autograd like the reference."""
+        cols = self.n if method == "RAYEN" else self.n + 1
+        v = v.detach().clone().to(self.dtype).reshape(v.shape[0], cols).requires_grad_(True)
+        y = self.forward(v) if method == "RAYEN" else self.forward_old(v)
         (y[:, :, 0] * gy.to(self.dtype).reshape(y.shape[0], self.k)).sum().backward()
         return y.detach()[:, :, 0], v.grad.detach()
 

@@ -128,7 +128,7 @@ class ConstraintModule(nn.Module):
             all_delta, all_phi = [], []
             for P, q, r in zip(all_P, all_q, all_r):
                 w = y0.T @ P + q.T
-                level = float(0.5 * y0.T @ P @ y0 + q.T @ y0 + r)
+                level = (0.5 * y0.T @ P @ y0 + q.T @ y0 + r).item()
                 sigma = 2.0 * level
                 all_phi.append(-w / sigma)
                 all_delta.append((w.T @ w - 2.0 * level * P) / sigma ** 2)

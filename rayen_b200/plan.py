@@ -142,7 +142,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None):
     quad_f64 = []
     for i, (P, q, r) in enumerate(qcs):
         P, q, r = f64(P), f64(q).reshape(-1, 1), float(np.asarray(r).reshape(-1)[0])
-        level = float(0.5 * y0.T @ P @ y0 + q.T @ y0 + r)
+        level = (0.5 * y0.T @ P @ y0 + q.T @ y0 + r).item()
         if level >= 0:
             raise PlanError(f"y0 is not strictly inside quadratic constraint {i} (g(y0)={level})")
         sigma = 2.0 * level
@@ -164,8 +164,8 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None):
     for j, (M, s, c, d) in enumerate(socs):
         M, s, c, d = f64(M), f64(s).reshape(-1, 1), f64(c).reshape(-1, 1), float(np.asarray(d).reshape(-1)[0])
         beta = M @ y0 + s
-        tau = float(c.T @ y0 + d)
-        A = tau * tau - float(beta.T @ beta)
+        tau = (c.T @ y0 + d).item()
+        A = tau * tau - (beta.T @ beta).item()
         if not (A > 0 and tau > 0):
             raise PlanError(f"y0 is not strictly inside SOC constraint {j}")
         Mz = M @ N

@@ -47,7 +47,7 @@ def random_spec(k, m=0, eta=0, mu=0, r_M=0, r=0, seed=0):
         T = rng.uniform(-1.0, 1.0, size=(k, k))
         E = T @ T.T / k + 0.1 * np.eye(k)
         c = rng.uniform(-1.0, 1.0, size=(k, 1))
-        c *= 0.5 / np.sqrt(float(c.T @ E @ c))
+        c *= 0.5 / np.sqrt((c.T @ E @ c).item())
         spec["qcs"].append((2.0 * E, -2.0 * E @ c, c.T @ E @ c - 1.0))
     for _ in range(mu):
         M = rng.uniform(-1.0, 1.0, size=(r_M, k))

@@ -118,6 +118,30 @@ def make_one(ref, name, spec, batch, scale, store_spec=True):
           f"(max|y32-y64|={np.abs(y32-y64).max():.2e})")
 
 
+def make_old(ref, name, spec, batch, scale):
+    """method='RAYEN_old' (reference constraint_module.py:460-466): inputs have n+1 columns, the last is beta."""
+    cs = synthetic.build_constraints(spec)
+    q, gy = synthetic.sample_inputs(batch, cs.n + 1, cs.k, dtype=torch.float64, scale=scale)
+    q32, gy32 = q.float(), gy.float()
+    out = {}
+    for tag, dtype in (("32", torch.float32), ("64", torch.float64)):
+        torch.set_default_dtype(dtype)
+        try:
+            cs_ref = synthetic.build_constraints(spec, module=ref.constraints)
+            layer = ref.constraint_module.ConstraintModule(cs_ref, method="RAYEN_old", create_map=False)
+            x = q32.to(dtype).reshape(batch, -1, 1).clone().requires_grad_(True)
+            y = layer(x)
+            (y[:, :, 0] * gy32.to(dtype)).sum().backward()
+            out["y" + tag], out["gv" + tag] = y.detach()[:, :, 0].numpy(), x.grad[:, :, 0].numpy()
+        finally:
+            torch.set_default_dtype(torch.float32)
+    arrays = dict(v=q32.numpy(), gy=gy32.numpy(), digest=np.array(spec_digest(spec)), zero_row_ok=np.array(True), **out)
+    arrays.update(spec_to_arrays(spec))
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name:12s} (RAYEN_old) k={cs.k} n={cs.n} B={batch} -> {os.path.getsize(path)/1024:.1f} KiB")
+
+
 def main():
     warnings.filterwarnings("ignore")
     ref = load_reference()
@@ -125,6 +149,11 @@ def main():
         make_one(ref, f"example_{ex}", synthetic.example_spec(ex), GOLDEN_BATCH["example"], scale=5.0)
     for cfg in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5"):
         make_one(ref, cfg, synthetic.config_spec(cfg), GOLDEN_BATCH[cfg], scale=2.0)
+    for ex in ("readme", 13, 1):
+        make_old(ref, f"old_example_{ex}", synthetic.example_spec(ex), 64, scale=3.0)
+    spec = synthetic.random_spec(k=8, m=24, eta=3, mu=3, r_M=8, r=8, seed=3)
+    spec["b1"] = spec["b1"] * 3.0
+    make_old(ref, "old_mixed8", spec, 64, scale=2.0)
     # "balanced" variants: linear rows loosened so that every family is active for some samples
     for cfg in ("cfg2", "cfg3", "cfg5"):
         spec = synthetic.config_spec(cfg)

@@ -1,0 +1,302 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI by the
+drop-in ConstraintModule, against (1) the golden vectors produced by the unmodified reference, (2) the
+oracle on seeded inputs, (3) closed-form geometry, (4) size-independent properties at BASELINE.json's full
+batch sizes.  Tolerance of the graded dtype: 1e-5 relative (max-norm), written below as TOL."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden_names, load_golden
+from oracle.rayen_oracle import OracleSet, TorchOracle, closed_form_numpy, max_violation
+from rayen_b200 import _cabi, synthetic
+from rayen_b200.constraint_module import ConstraintModule
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5          # BASELINE.json north_star: "within 1e-5 relative fp32"
+TOL_GRAD = 2e-5     # gradients of LMI-bound samples are eigengap-sensitive (reference fp32 vs fp64: 1.2e-5 worst)
+DEV = "cuda:0"
+
+
+def run_layer(cs, v, gy, method="RAYEN", **kw):
+    layer = ConstraintModule(cs, create_map=False, method=method).to(DEV)
+    x = torch.as_tensor(v, dtype=torch.float32).to(DEV).requires_grad_(True)
+    y = layer(x.unsqueeze(2))
+    (y[:, :, 0] * torch.as_tensor(gy, dtype=torch.float32).to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    return layer, y.detach()[:, :, 0].cpu().numpy().astype(np.float64), x.grad.cpu().numpy().astype(np.float64)
+
+
+def rel(a, b, rows=None):
+    if rows is not None:
+        a, b = a[rows], b[rows]
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_library_loaded():
+    lib = _cabi.lib()                      # fails loudly if librayen_b200.so is missing
+    before = _cabi.launch_count()
+    yield
+    assert _cabi.launch_count() > before, "no CUDA kernel of librayen_b200.so was launched by these tests"
+
+
+# ----------------------------------------------------------------------------- golden vectors of the reference
+@pytest.mark.parametrize("name", golden_names())
+def test_golden(name):
+    g = load_golden(name)
+    cs = synthetic.build_constraints(g["spec"])
+    method = "RAYEN_old" if name.startswith("old_") else "RAYEN"
+    layer, y, gv = run_layer(cs, g["v"], g["gy"], method)
+    assert np.isfinite(y).all() and np.isfinite(gv).all()
+    assert rel(y, g["y32"]) <= TOL and rel(y, g["y64"]) <= TOL
+    fin = np.isfinite(g["gv64"]).all(axis=1) & np.isfinite(g["gv32"]).all(axis=1)   # reference NaN at v = 0 (sqrt'(0))
+    if method == "RAYEN":
+        cf = closed_form_numpy(OracleSet.from_constraints(cs), g["v"], g["gy"])
+        fin &= cf["margin"] > 1e-4                                                  # argmax near-ties: gradient is discontinuous
+    assert fin.sum() >= 0.75 * len(fin)
+    assert rel(gv, g["gv64"], fin) <= TOL_GRAD and rel(gv, g["gv32"], fin) <= TOL_GRAD
+    s = g["spec"]
+    viol = max_violation(OracleSet.from_constraints(cs), y, s["A1"], s["b1"], s["A2"], s["b2"])
+    assert viol <= 1e-5 * max(1.0, np.abs(y).max())
+
+
+def test_zero_direction_gives_interior_point():
+    """v = 0: y = y0 and g_v = 0 (the reference itself is NaN there for SOC sets)."""
+    for ex in ("readme", 11, 13, 2):
+        cs = synthetic.build_constraints(synthetic.example_spec(ex))
+        v = np.zeros((8, cs.n), dtype=np.float32)
+        _, y, gv = run_layer(cs, v, np.ones((8, cs.k), dtype=np.float32))
+        np.testing.assert_allclose(y, np.repeat(cs.y0.T, 8, axis=0), atol=1e-6)
+        assert np.all(gv == 0)
+
+
+# ----------------------------------------------------------------------------- oracle on seeded inputs, ragged sizes
+@pytest.mark.parametrize("cfg,batch", [("cfg2", 1), ("cfg2", 3), ("cfg2", 33), ("cfg2", 1000), ("cfg3", 257),
+                                       ("cfg4", 5), ("cfg4", 130), ("cfg5", 67), ("cfg5", 513)])
+def test_oracle_ragged_batches(cfg, batch):
+    spec = synthetic.config_spec(cfg)
+    if spec["b1"] is not None:
+        spec["b1"] = spec["b1"] * 4.0      # loosen the rows so that every family binds for some samples
+    cs = synthetic.build_constraints(spec)
+    v, gy = synthetic.sample_inputs(batch, cs.n, cs.k, seed_v=batch, seed_g=batch + 1)
+    _, y, gv = run_layer(cs, v, gy)
+    oset = OracleSet.from_constraints(cs)
+    y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v.double(), gy.double())
+    cf = closed_form_numpy(oset, v.numpy(), gy.numpy())
+    ok = cf["margin"] > 1e-4
+    assert rel(y, y_ref.numpy()) <= TOL
+    assert rel(gv, g_ref.numpy(), ok) <= TOL_GRAD
+
+
+def test_empty_batch():
+    cs = synthetic.build_constraints(synthetic.config_spec("cfg2"))
+    layer = ConstraintModule(cs, create_map=False).to(DEV)
+    x = torch.zeros((0, cs.n, 1), device=DEV, requires_grad=True)
+    y = layer(x)
+    assert y.shape == (0, cs.k, 1)
+    y.sum().backward()
+    assert x.grad.shape == x.shape
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_shapes_vs_oracle(seed):
+    """n < k (equalities), n not a multiple of 4, missing families, LMI sizes that need padding."""
+    rng = np.random.default_rng(100 + seed)
+    k = int(rng.integers(2, 33))
+    spec = synthetic.random_spec(k=k, m=int(rng.integers(1, 60)), eta=int(rng.integers(0, 4)),
+                                 mu=int(rng.integers(0, 4)), r_M=int(rng.integers(1, 2 * k + 1)),
+                                 r=int(rng.integers(0, 2)) * int(rng.integers(2, 33)), seed=seed)
+    spec["b1"] = spec["b1"] * 3.0
+    if seed % 2 == 1 and k > 2:   # an equality constraint through the origin keeps y0 = 0 interior
+        spec["A2"], spec["b2"] = rng.uniform(-1, 1, size=(1, k)), np.zeros((1, 1))
+    cs = synthetic.build_constraints(spec)
+    v, gy = synthetic.sample_inputs(300, cs.n, cs.k, seed_v=seed)
+    _, y, gv = run_layer(cs, v, gy)
+    oset = OracleSet.from_constraints(cs)
+    y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v.double(), gy.double())
+    ok = closed_form_numpy(oset, v.numpy(), gy.numpy())["margin"] > 1e-4
+    assert rel(y, y_ref.numpy()) <= TOL
+    assert rel(gv, g_ref.numpy(), ok) <= TOL_GRAD
+    assert max_violation(oset, y, spec["A1"], spec["b1"], spec["A2"], spec["b2"]) <= 1e-5 * max(1.0, np.abs(y).max())
+
+
+# ----------------------------------------------------------------------------- closed-form geometry (KATs)
+def test_kat_sphere_and_box_and_psd_cone():
+    # sphere of radius R centred at y0 = 0: kappa == 1/R for every direction
+    R = 2.0
+    spec = synthetic.example_spec(2)
+    spec["y0"] = np.zeros((3, 1))
+    cs = synthetic.build_constraints(spec)
+    v, gy = synthetic.sample_inputs(64, 3, 3, scale=5.0)
+    layer, y, _ = run_layer(cs, v, gy)
+    kap, act = layer.last_kappa_and_active()
+    np.testing.assert_allclose(kap.cpu().numpy(), 1.0 / R, rtol=2e-6)
+    assert np.all((act.cpu().numpy() >> 24) == _cabi.FAM_QUAD)
+    far = np.linalg.norm(v.numpy(), axis=1) > R
+    np.testing.assert_allclose(np.linalg.norm(y[far], axis=1), R, rtol=5e-6)
+    # unit box centred at y0: kappa = max_i |u_i| / 0.5
+    A1 = np.concatenate((np.eye(3), -np.eye(3)))
+    spec = dict(A1=A1, b1=0.5 * np.ones((6, 1)), A2=None, b2=None, qcs=[], socs=[], lmi=None, y0=np.zeros((3, 1)))
+    cs = synthetic.build_constraints(spec)
+    layer, y, _ = run_layer(cs, v, gy)
+    u = v.numpy() / np.linalg.norm(v.numpy(), axis=1, keepdims=True)
+    np.testing.assert_allclose(layer.last_kappa_and_active()[0].cpu().numpy(), np.abs(u).max(axis=1) / 0.5, rtol=2e-6)
+    # 2x2 PSD cone from y0 = (1, 0, 1): H = I, kappa = relu(lambda_max(-S(u)))
+    spec = synthetic.example_spec(12)
+    spec["y0"] = np.array([[1.0], [0.0], [1.0]])
+    cs = synthetic.build_constraints(spec)
+    layer, y, _ = run_layer(cs, v, gy)
+    lam = np.array([np.linalg.eigvalsh(-np.array([[a, b], [b, c]]))[-1] for a, b, c in u])
+    np.testing.assert_allclose(layer.last_kappa_and_active()[0].cpu().numpy(), np.maximum(lam, 0), rtol=5e-6, atol=1e-7)
+
+
+def test_unbounded_directions_pass_through():
+    """Half-space only: directions that never hit the boundary give kappa = 0, y = y0 + v, g_v = g_y."""
+    spec = dict(A1=np.array([[1.0, 0.0]]), b1=np.array([[1.0]]), A2=None, b2=None, qcs=[], socs=[], lmi=None,
+                y0=np.zeros((2, 1)))
+    cs = synthetic.build_constraints(spec)
+    v = np.array([[-3.0, 2.0], [-0.1, -7.0], [5.0, 1.0]], dtype=np.float32)
+    gy = np.array([[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]], dtype=np.float32)
+    layer, y, gv = run_layer(cs, v, gy)
+    np.testing.assert_allclose(y[:2], v[:2], rtol=1e-6)
+    np.testing.assert_allclose(gv[:2], gy[:2], rtol=1e-6)
+    assert abs(y[2, 0] - 1.0) < 1e-6          # the third ray is clipped at x = 1
+
+
+# ----------------------------------------------------------------------------- full BASELINE.json sizes: properties
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "cfg5"])
+def test_full_size_properties(cfg):
+    shp = synthetic.CONFIG_SHAPES[cfg]
+    spec = synthetic.config_spec(cfg)
+    cs = synthetic.build_constraints(spec)
+    B = shp["batch"]
+    v, gy = synthetic.sample_inputs(B, cs.n, cs.k)
+    layer = ConstraintModule(cs, create_map=False).to(DEV)
+    x = v.to(DEV).requires_grad_(True)
+    y = layer(x.unsqueeze(2))[:, :, 0]
+    (y * gy.to(DEV)).sum().backward()
+    kap, act = layer.last_kappa_and_active()
+    yn, kn = y.detach().cpu().numpy().astype(np.float64), kap.cpu().numpy().astype(np.float64)
+    s = np.linalg.norm(v.numpy().astype(np.float64), axis=1)
+    assert np.isfinite(yn).all() and np.isfinite(x.grad.cpu().numpy()).all()
+    # 1. every output is feasible (fp64 residuals of the ORIGINAL constraints; sub-sampled for the eigen check)
+    sub = slice(0, 8192)
+    oset = OracleSet.from_constraints(cs)
+    assert max_violation(oset, yn[sub], spec["A1"], spec["b1"], spec["A2"], spec["b2"]) <= 1e-5
+    # 2. interior samples are mapped to y0 + v exactly (up to rounding); boundary samples have |y - y0| = 1/kappa
+    interior = s * kn <= 1.0
+    d = np.linalg.norm(yn - cs.y0.T, axis=1)
+    np.testing.assert_allclose(d[interior], s[interior], rtol=1e-5)
+    np.testing.assert_allclose(d[~interior] * kn[~interior], 1.0, rtol=1e-5)
+    # 3. the map is positively homogeneous of degree 0 on the boundary: scaling v does not move y
+    y2 = layer((3.0 * x.detach()).unsqueeze(2))[:, :, 0].cpu().numpy()
+    assert np.abs(y2[~interior] - yn[~interior]).max() <= 1e-5 * np.abs(yn).max()
+    # 4. idempotence: z = y - y0 is feasible, so shooting it again returns the same point
+    y3 = layer((y.detach() - torch.tensor(cs.y0.T, dtype=torch.float32, device=DEV)).unsqueeze(2))[:, :, 0].cpu().numpy()
+    assert np.abs(y3 - yn).max() <= 2e-5 * np.abs(yn).max()
+    # 5. a sub-sample against the oracle
+    idx = np.arange(0, B, max(1, B // 512))[:512]
+    y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v[idx].double(), gy[idx].double())
+    assert rel(yn[idx], y_ref.numpy()) <= TOL
+    ok = closed_form_numpy(oset, v[idx].numpy(), gy[idx].numpy())["margin"] > 1e-4
+    assert rel(x.grad.cpu().numpy().astype(np.float64)[idx], g_ref.numpy(), ok) <= TOL_GRAD
+
+
+# ----------------------------------------------------------------------------- the boundary itself
+def test_launch_geometry_does_not_change_results():
+    spec = synthetic.config_spec("cfg3")
+    spec["b1"] = spec["b1"] * 4.0
+    cs = synthetic.build_constraints(spec)
+    v, gy = synthetic.sample_inputs(777, cs.n, cs.k)
+    layer = ConstraintModule(cs, create_map=False).to(DEV)
+    x = v.to(DEV)
+    base = layer(x.unsqueeze(2)).cpu()
+    for tm in (1, 2, 4):
+        for lanes in (1, 2, 4, 8, 16, 32):
+            layer.set_tuning(tm, lanes, device=DEV)
+            out = layer(x.unsqueeze(2)).cpu()
+            assert torch.equal(out, base) or (out - base).abs().max() <= 1e-6 * base.abs().max(), (tm, lanes)
+
+
+def test_host_buffer_path_matches_device_path():
+    spec = synthetic.config_spec("cfg5")
+    spec["b1"] = spec["b1"] * 4.0
+    cs = synthetic.build_constraints(spec)
+    v, gy = synthetic.sample_inputs(1000, cs.n, cs.k)
+    layer, y, gv = run_layer(cs, v, gy)
+    yh, gvh = layer.forward_backward_host(v.pin_memory(), gy.pin_memory(), device=DEV)
+    np.testing.assert_array_equal(yh.numpy(), y.astype(np.float32))
+    np.testing.assert_array_equal(gvh.numpy(), gv.astype(np.float32))
+
+
+def test_non_contiguous_and_other_dtypes():
+    cs = synthetic.build_constraints(synthetic.config_spec("cfg2"))
+    v, gy = synthetic.sample_inputs(100, cs.n, cs.k)
+    layer = ConstraintModule(cs, create_map=False).to(DEV)
+    ref = layer(v.to(DEV).unsqueeze(2))
+    wide = torch.zeros(100, 2 * cs.n, device=DEV)
+    wide[:, ::2] = v.to(DEV)
+    torch.testing.assert_close(layer(wide[:, ::2].unsqueeze(2)), ref, rtol=0, atol=0)
+    padded = torch.zeros(100, cs.n + 4, device=DEV)
+    padded[:, :cs.n] = v.to(DEV)
+    torch.testing.assert_close(layer(padded[:, :cs.n].unsqueeze(2)), ref, rtol=0, atol=0)
+    with pytest.warns(UserWarning):
+        out64 = layer(v.double().to(DEV).unsqueeze(2))
+    assert out64.dtype == torch.float64
+    torch.testing.assert_close(out64.float(), ref, rtol=0, atol=1e-6)
+
+
+def test_readme_model_trains():
+    """The README usage (readme.md:76-81): Sequential(Linear, ReLU, Linear, ReLU, ConstraintModule) + backward."""
+    from rayen import constraints, constraint_module
+    cs = synthetic.build_constraints(synthetic.example_spec("readme"), module=constraints)
+    model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3, 64), torch.nn.ReLU(), torch.nn.Linear(64, 64),
+                                torch.nn.ReLU(), constraint_module.ConstraintModule(cs, input_dim=64, create_map=True)).to(DEV)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    x = torch.rand(500, 3, 1, device=DEV) * 2 - 1
+    target = torch.tensor([[0.2], [0.2], [0.6]], device=DEV)
+    losses = []
+    for _ in range(30):
+        opt.zero_grad()
+        y = model(x)
+        loss = ((y - target) ** 2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert y.shape == (500, 3, 1)
+    assert losses[-1] < losses[0]
+    yn = y.detach()[:, :, 0].cpu().numpy().astype(np.float64)
+    s = synthetic.example_spec("readme")
+    assert max_violation(OracleSet.from_constraints(cs), yn, s["A1"], s["b1"], s["A2"], s["b2"]) <= 1e-5
+
+
+def test_state_dict_reload_on_gpu():
+    cs = synthetic.build_constraints(synthetic.example_spec(13))
+    a = ConstraintModule(cs, create_map=False).to(DEV)
+    spec_b = synthetic.example_spec(13)
+    spec_b["y0"] = np.array([[0.6], [0.0], [0.8]])
+    b = ConstraintModule(synthetic.build_constraints(spec_b), create_map=False).to(DEV)
+    v, _ = synthetic.sample_inputs(200, 3, 3, scale=5.0)
+    x = v.to(DEV).unsqueeze(2)
+    assert (a(x) - b(x)).abs().max() > 1e-3
+    b.load_state_dict(a.state_dict())
+    assert (a(x) - b(x)).abs().max() <= 2e-6
+
+
+def test_c_abi_error_codes_on_gpu():
+    lib = _cabi.lib()
+    cs = synthetic.build_constraints(synthetic.config_spec("cfg4"))
+    layer = ConstraintModule(cs, create_map=False).to(DEV)
+    plan = layer._device_plan(torch.device(DEV))
+    v = torch.zeros(4, cs.n, device=DEV)
+    y = torch.zeros(4, cs.k, device=DEV)
+    null = ctypes.c_void_p(0)
+    # LMI plans need the kappa / active outputs
+    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n, y.data_ptr(), null, null, 4, 0, null) == -1
+    assert b"kappa" in lib.rayen_last_error()
+    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n - 1, y.data_ptr(), null, null, 4, 0, null) == -1
+    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n, y.data_ptr(), null, null, 4, 7, null) == -1
+    info = plan.kernel_info()
+    assert info["sm_count"] >= 100 and info["regs_lmi_fwd"] > 0

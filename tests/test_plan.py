@@ -1,0 +1,82 @@
+"""Host-side plan packer: the packed float32 block decodes (in float64 numpy) to the oracle's answers."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden_names, load_golden
+from oracle.rayen_oracle import OracleSet, closed_form_numpy
+from rayen_b200 import plan, synthetic
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("old_")])
+def test_packed_plan_reproduces_oracle(name):
+    g = load_golden(name)
+    cs = synthetic.build_constraints(g["spec"])
+    p = plan.build_plan_from_constraints(cs)
+    y, kap, act = plan.evaluate_plan_numpy(p, g["v"])
+    cf = closed_form_numpy(OracleSet.from_constraints(cs), g["v"])
+    scale = np.abs(cf["y"]).max()
+    assert np.abs(y - cf["y"]).max() <= 2e-6 * scale      # float32 rounding of the constants only
+    assert np.abs(kap - cf["kappa"]).max() <= 2e-6 * max(1.0, cf["kappa"].max())
+    clear = cf["margin"] > 1e-4
+    assert np.array_equal((act >> 24)[clear], cf["family"][clear])
+    lin = clear & (cf["family"] == 1)
+    assert np.array_equal((act & 0xFFFFFF)[lin], cf["index"][lin])
+
+
+def test_layout_invariants():
+    cs = synthetic.build_constraints(synthetic.config_spec("cfg5"))
+    p = plan.build_plan_from_constraints(cs)
+    f = p.fields
+    assert p.blob.dtype == np.float32 and p.blob.size % 4 == 0
+    offs = [f[k] for k in ("off_lin", "off_quad", "off_soc", "off_nmat", "off_y0", "off_lmi")]
+    assert offs == sorted(offs) and all(o % 4 == 0 for o in offs)
+    assert f["np"] == 32 and f["lmi_rp"] == 32 and f["n_is_identity"] == 1
+    assert f["quad_stride"] % 32 == 4 and f["soc_stride"] % 32 == 4 and f["lin_chunk_stride"] == 4 * 32 + 4
+    assert (f["off_lmi"] - f["off_lin"]) * 4 + 64 <= 227 * 1024      # the LQS constants fit one CTA's shared memory
+    assert f["n"] * f["lmi_rp"] ** 2 * 4 == 131072                   # F~z: 128 KiB
+
+
+def test_equality_constraints_give_a_subspace_plan():
+    cs = synthetic.build_constraints(synthetic.example_spec("readme"))
+    p = plan.build_plan_from_constraints(cs)
+    assert (p.fields["n"], p.fields["k"], p.fields["np"], p.fields["n_is_identity"]) == (2, 3, 4, 0)
+    assert p.fields["lmi_r"] == 2 and p.fields["lmi_rp"] == 4
+
+
+def test_rejects_boundary_or_exterior_points():
+    spec = synthetic.example_spec(2)       # sphere of radius 2
+    spec["y0"] = np.array([[2.0], [0.0], [0.0]])
+    cs = synthetic.build_constraints(spec)
+    with pytest.raises(plan.PlanError):
+        plan.build_plan_from_constraints(cs)
+    spec = synthetic.example_spec(0)
+    spec["y0"] = np.array([[1.0], [0.0], [0.0]])   # on a face of the cube
+    with pytest.raises(plan.PlanError):
+        plan.build_plan_from_constraints(synthetic.build_constraints(spec))
+
+
+def test_unsupported_sizes_fail_loudly():
+    with pytest.raises(plan.PlanError, match="n=40"):
+        plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=40, m=8)))
+    with pytest.raises(plan.PlanError, match="r=40"):
+        plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=4, r=40)))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shapes(seed):
+    rng = np.random.default_rng(seed)
+    k = int(rng.integers(1, 33))
+    spec = synthetic.random_spec(k=k, m=int(rng.integers(0, 40)), eta=int(rng.integers(0, 4)),
+                                 mu=int(rng.integers(0, 4)), r_M=int(rng.integers(1, 2 * k + 1)),
+                                 r=int(rng.integers(0, 2)) * int(rng.integers(2, 33)), seed=seed)
+    if spec["A1"] is None and not spec["qcs"] and not spec["socs"] and spec["lmi"] is None:
+        spec = synthetic.random_spec(k=k, m=5, seed=seed)
+    if spec["b1"] is not None:
+        spec["b1"] = spec["b1"] * 3
+    cs = synthetic.build_constraints(spec)
+    p = plan.build_plan_from_constraints(cs)
+    v, _ = synthetic.sample_inputs(64, cs.n, cs.k, seed_v=seed, dtype=torch.float64)
+    y, kap, _ = plan.evaluate_plan_numpy(p, v.numpy())
+    cf = closed_form_numpy(OracleSet.from_constraints(cs), v.numpy())
+    assert np.abs(y - cf["y"]).max() <= 5e-6 * max(1.0, np.abs(cf["y"]).max())
