@@ -231,7 +231,7 @@ class ConstraintModule(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, x):
         # x: [B, numel_input_mapper, 1] (anything that views to [B, -1]), as in the reference
-        q = self.mapper(x.view(x.size(0), -1))
+        q = self.mapper(x.view(x.size(0), x[0].numel() if x.size(0) else int(np.prod(x.shape[1:]))))
         utils.verify(q.shape[1] == self.dim_after_map,
                      f"the layer expects {self.dim_after_map} values per sample, got {q.shape[1]}")
         if q.dtype == torch.float64 and not getattr(self, "_warned_f64", False):
