@@ -22,7 +22,8 @@
 
 namespace rayen {
 
-constexpr int kLmiThreads = 256;
+constexpr int kLmiThreads = 256;     // backward kernel (keeps the reflectors: needs the registers)
+constexpr int kLmiFwdThreads = 384;  // forward kernel: 12 warps per SM
 constexpr int kLmiMaxN = 32;
 
 template <int RP>
@@ -107,59 +108,63 @@ struct LmiSolver {
   }
 
   // ---- 2. Householder tridiagonalisation.  Afterwards sd()/se() hold the diagonal / sub-diagonal and,
-  //         if WANT_GRAD, the dead column k of A (in its owner lane) holds reflector k.
+  //         if WANT_GRAD, row k of A holds this lane's part of reflector k (zeros in dead columns).
   // The RP-2 reduction steps run as 4 runtime loops ("stages") instead of RP-2 unrolled bodies: stage S
   // covers k in [LPM*S, LPM*(S+1)), during which column slots < S are dead, slot S is partly live and
   // rows < LPM*S are dead -- all compile-time facts, so the register file is still indexed statically
-  // while the code stays small enough for the instruction cache.
+  // while the code stays small enough for the instruction cache.  The pivot row k (= column k, by
+  // symmetry) is carried from step to step in xo[]: it is picked out of the register file with a few
+  // predicated moves while the previous step updates the LPM rows that can be next.
   template <int S>
-  __device__ __forceinline__ void householder_stage() {
+  __device__ __forceinline__ void householder_stage(float (&xo)[4]) {
     constexpr int R0 = LPM * S;
     constexpr int K_END = (LPM * (S + 1) < RP - 2) ? LPM * (S + 1) : RP - 2;
-    constexpr int I4 = R0 / 4;      // first float4 of rows that can be live
-    constexpr int EDGE = R0 + LPM;  // rows <= EDGE change role with k inside the stage
+    constexpr int I4 = R0 / 4;                                       // first float4 of rows that can be live
+    constexpr int EDGE = (R0 + LPM < RP - 1) ? R0 + LPM : RP - 1;    // last row that can become the pivot row
     if constexpr (R0 < RP - 2) {
       for (int k = R0; k < K_END; ++k) {
         const int kk = k - R0;
-        if (q == kk) {
-          // the owner of column k builds the reflector from its column (= row k, by symmetry)
-          float tail2 = 0.f, xk1 = 0.f, dk = 0.f;
+        if (q == kk) sd()[k] = xo[S];  // d_k: column k lives in lane kk, slot S
+        // x_{k+1} = A[k][k+1] lives in lane (kk+1) % LPM, slot S or (when the lane index wraps) S+1
+        const bool wrap = (kk + 1 == LPM);
+        float cand = xo[S];
+        if constexpr (S < 3) {
+          if (wrap) cand = xo[S + 1];
+        }
+        const float xk1 = __shfl_sync(0xffffffffu, cand, grp_base + (wrap ? 0 : kk + 1));
+        float loc = 0.f;
 #pragma unroll
-          for (int i = 4 * I4; i < RP; ++i) {
-            const float c = A[i][S];
-            if (i <= EDGE) {
-              if (i == k) dk = c;
-              if (i == k + 1) xk1 = c;
-              if (i > k + 1) tail2 = fmaf(c, c, tail2);
-            } else {
-              tail2 = fmaf(c, c, tail2);
+        for (int t = S; t < 4; ++t) {
+          const int j = q + LPM * t;
+          if (j > k + 1) loc = fmaf(xo[t], xo[t], loc);
+        }
+        const float tail2 = group_sum<LPM>(loc);
+        const float sigma = fmaf(xk1, xk1, tail2);
+        const float rt = sqrtf(sigma);
+        const float alpha = (xk1 >= 0.f) ? -rt : rt;
+        const bool skip = !(tail2 > 0.f);  // column already tridiagonal (also covers zero padding)
+        const float tau = skip ? 0.f : 1.0f / fmaf(fabsf(xk1), rt, sigma);
+        if (q == kk) se()[k] = skip ? xk1 : alpha;
+        float vo[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) vo[t] = 0.f;
+#pragma unroll
+        for (int t = S; t < 4; ++t) {
+          const int j = q + LPM * t;
+          float val = (j > k + 1) ? xo[t] : ((j == k + 1) ? (xk1 - alpha) : 0.f);
+          if (skip) val = 0.f;
+          vo[t] = val;
+          sv()[j] = val;
+        }
+        if constexpr (WANT_GRAD) {
+#pragma unroll
+          for (int i = R0; i < K_END; ++i)
+            if (i == k) {
+#pragma unroll
+              for (int t = S; t < 4; ++t) A[i][t] = vo[t];
             }
-          }
-          const float sigma = fmaf(xk1, xk1, tail2);
-          const float rt = sqrtf(sigma);
-          const float alpha = (xk1 >= 0.f) ? -rt : rt;
-          const bool skip = !(tail2 > 0.f);  // column already tridiagonal (also covers zero padding)
-          const float tau = skip ? 0.f : 1.0f / fmaf(fabsf(xk1), rt, sigma);
-          sd()[k] = dk;
-          se()[k] = skip ? xk1 : alpha;
-          sx0()[0] = tau;
-#pragma unroll
-          for (int i4 = I4; i4 < RP / 4; ++i4) {
-            float vv[4];
-#pragma unroll
-            for (int ii = 0; ii < 4; ++ii) {
-              const int i = 4 * i4 + ii;
-              float val = A[i][S];
-              if (i <= EDGE) val = (i > k + 1) ? val : ((i == k + 1) ? (xk1 - alpha) : 0.f);
-              if (skip) val = 0.f;
-              vv[ii] = val;
-              if constexpr (WANT_GRAD) A[i][S] = val;
-            }
-            *reinterpret_cast<float4*>(sv() + 4 * i4) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-          }
         }
         __syncwarp();
-        const float tau = sx0()[0];
         float vr[RP];
 #pragma unroll
         for (int i4 = I4; i4 < RP / 4; ++i4) {
@@ -169,18 +174,13 @@ struct LmiSolver {
           vr[4 * i4 + 2] = x.z;
           vr[4 * i4 + 3] = x.w;
         }
-        float vo[4], p[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          vo[t] = (t >= S) ? sv()[q + LPM * t] : 0.f;
-          p[t] = 0.f;
-        }
         // p = tau * A v (dead rows carry v_i = 0)
+        float p[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 4 * I4; i < RP; ++i)
 #pragma unroll
           for (int t = S; t < 4; ++t) p[t] = fmaf(A[i][t], vr[i], p[t]);
-        float loc = 0.f;
+        loc = 0.f;
 #pragma unroll
         for (int t = S; t < 4; ++t) {
           p[t] *= tau;
@@ -190,12 +190,12 @@ struct LmiSolver {
         float wo[4];
 #pragma unroll
         for (int t = S; t < 4; ++t) {
-          const bool live = (t > S) || (q > kk);
-          wo[t] = live ? fmaf(-Kc, vo[t], p[t]) : 0.f;
-          sw()[q + LPM * t] = wo[t];
+          const int j = q + LPM * t;
+          wo[t] = (j > k) ? fmaf(-Kc, vo[t], p[t]) : 0.f;
+          sw()[j] = wo[t];
         }
         __syncwarp();
-        // A <- A - v w' - w v'
+        // A <- A - v w' - w v'; the row that becomes the next pivot row is copied out on the way
 #pragma unroll
         for (int i4 = I4; i4 < RP / 4; ++i4) {
           const float4 x = ld4(sw() + 4 * i4);
@@ -205,21 +205,32 @@ struct LmiSolver {
             const int i = 4 * i4 + ii;
 #pragma unroll
             for (int t = S; t < 4; ++t) A[i][t] = fmaf(-vr[i], wo[t], fmaf(-wr[ii], vo[t], A[i][t]));
+            if (i > R0 && i <= EDGE) {
+              if (i == k + 1) {
+#pragma unroll
+                for (int t = S; t < 4; ++t) xo[t] = A[i][t];
+              }
+            }
           }
         }
-        __syncwarp();  // scratch v/w/tau are rewritten by the next step
+        __syncwarp();  // scratch v/w are rewritten by the next step
       }
     }
   }
 
   __device__ __forceinline__ void tridiagonalize() {
     // sw must start clean: entries of dead column slots are read (times v_i = 0) but never rewritten
+    float xo[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) sw()[q + LPM * t] = 0.f;
-    householder_stage<0>();
-    householder_stage<1>();
-    householder_stage<2>();
-    householder_stage<3>();
+    for (int t = 0; t < 4; ++t) {
+      sw()[q + LPM * t] = 0.f;
+      sv()[q + LPM * t] = 0.f;
+      xo[t] = A[0][t];
+    }
+    householder_stage<0>(xo);
+    householder_stage<1>(xo);
+    householder_stage<2>(xo);
+    householder_stage<3>(xo);
     // trailing 2x2 block
     constexpr int K2 = RP - 2, K1 = RP - 1;
     if (q == K2 % LPM) {
@@ -304,7 +315,7 @@ struct LmiSolver {
   }
 
   // ---- 4. unit eigenvector of lambda (backward only): twisted factorisation of T - lambda I on one
-  // lane per matrix, then q = H_0 ... H_{RP-3} z with the reflectors kept in the dead columns of A.
+  // lane per matrix, then q = H_0 ... H_{RP-3} z with the reflectors kept in the dead rows of A.
   __device__ __forceinline__ void eigenvector(float lam, float (&qo)[4]) {
     static_assert(WANT_GRAD, "eigenvector needs the reflectors");
     float* dp = sx0();
@@ -354,46 +365,43 @@ struct LmiSolver {
       for (int i = 0; i < RP; ++i) z[i] *= inv;
     }
     __syncwarp();
-    // q = H_0 ... H_{RP-3} z, in place in the scratch; reflector k sits in the dead column k of its owner lane
-    back_stage<3>(z);
-    back_stage<2>(z);
-    back_stage<1>(z);
-    back_stage<0>(z);
 #pragma unroll
     for (int t = 0; t < 4; ++t) qo[t] = z[q + LPM * t];
+    // q = H_0 ... H_{RP-3} z; reflector k sits in row k of A (this lane's columns)
+    back_stage<3>(qo);
+    back_stage<2>(qo);
+    back_stage<1>(qo);
+    back_stage<0>(qo);
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) z[q + LPM * t] = qo[t];
+    __syncwarp();
   }
 
   template <int S>
-  __device__ __forceinline__ void back_stage(float* z) {
+  __device__ __forceinline__ void back_stage(float (&qo)[4]) {
     constexpr int R0 = LPM * S;
     constexpr int K_END = (LPM * (S + 1) < RP - 2) ? LPM * (S + 1) : RP - 2;
-    constexpr int I4 = R0 / 4;
     if constexpr (R0 < RP - 2) {
       for (int k = K_END - 1; k >= R0; --k) {
-        if (q == k - R0) {
-          float zz[RP];
-          float dot = 0.f, vv = 0.f;
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i4 = I4; i4 < RP / 4; ++i4) {
-            const float4 x = ld4(z + 4 * i4);
-            zz[4 * i4 + 0] = x.x;
-            zz[4 * i4 + 1] = x.y;
-            zz[4 * i4 + 2] = x.z;
-            zz[4 * i4 + 3] = x.w;
+        for (int i = R0; i < K_END; ++i)
+          if (i == k) {
+#pragma unroll
+            for (int t = S; t < 4; ++t) r[t] = A[i][t];
           }
+        float dot = 0.f, vv = 0.f;
 #pragma unroll
-          for (int i = 4 * I4; i < RP; ++i) {
-            dot = fmaf(A[i][S], zz[i], dot);
-            vv = fmaf(A[i][S], A[i][S], vv);
-          }
-          const float c = vv > 0.f ? 2.0f * dot / vv : 0.f;
-#pragma unroll
-          for (int i4 = I4; i4 < RP / 4; ++i4)
-            *reinterpret_cast<float4*>(z + 4 * i4) =
-                make_float4(fmaf(-c, A[4 * i4 + 0][S], zz[4 * i4 + 0]), fmaf(-c, A[4 * i4 + 1][S], zz[4 * i4 + 1]),
-                            fmaf(-c, A[4 * i4 + 2][S], zz[4 * i4 + 2]), fmaf(-c, A[4 * i4 + 3][S], zz[4 * i4 + 3]));
+        for (int t = S; t < 4; ++t) {
+          dot = fmaf(r[t], qo[t], dot);
+          vv = fmaf(r[t], r[t], vv);
         }
-        __syncwarp();
+        dot = group_sum<LPM>(dot);
+        vv = group_sum<LPM>(vv);
+        const float c = vv > 0.f ? 2.0f * dot / vv : 0.f;
+#pragma unroll
+        for (int t = S; t < 4; ++t) qo[t] = fmaf(-c, r[t], qo[t]);
       }
     }
   }
@@ -471,8 +479,8 @@ __device__ __forceinline__ const float* lmi_stage(const PlanDev& P, unsigned cha
 
 // ----------------------------------------------------------------------------- forward
 // prior kappa/tag (from lqs_forward_kernel) are merged when has_prior != 0; y, kappa, active are written.
-template <int RP, bool F_SMEM>
-__global__ void __launch_bounds__(kLmiThreads, 1)
+template <int RP, bool F_SMEM, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
     lmi_forward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, float* __restrict__ y,
                        float* __restrict__ kappa_io, int* __restrict__ active_io, long long B, int mode,
                        int has_prior) {

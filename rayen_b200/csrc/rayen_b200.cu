@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -20,6 +21,7 @@ struct rayen_plan {
   int sm_count;
   int max_smem_optin;
   int tune_tm, tune_lanes;
+  int lmi_fwd_threads;  // 256 or 384 (RAYEN_LMI_THREADS overrides)
   float* d_blob;
   bool lqs_smem;  // LQS constants fit in shared memory
   bool lmi_smem;  // LMI matrices fit in shared memory
@@ -90,13 +92,17 @@ static LqsBwdFn lqs_bwd_fn(int np) {
     default: return lqs_backward_kernel<32>;
   }
 }
-static LmiFwdFn lmi_fwd_fn(int rp, bool smem) {
+template <int THREADS>
+static LmiFwdFn lmi_fwd_fn_t(int rp, bool smem) {
   switch (rp) {
-    case 4: return smem ? lmi_forward_kernel<4, true> : lmi_forward_kernel<4, false>;
-    case 8: return smem ? lmi_forward_kernel<8, true> : lmi_forward_kernel<8, false>;
-    case 16: return smem ? lmi_forward_kernel<16, true> : lmi_forward_kernel<16, false>;
-    default: return smem ? lmi_forward_kernel<32, true> : lmi_forward_kernel<32, false>;
+    case 4: return smem ? lmi_forward_kernel<4, true, THREADS> : lmi_forward_kernel<4, false, THREADS>;
+    case 8: return smem ? lmi_forward_kernel<8, true, THREADS> : lmi_forward_kernel<8, false, THREADS>;
+    case 16: return smem ? lmi_forward_kernel<16, true, THREADS> : lmi_forward_kernel<16, false, THREADS>;
+    default: return smem ? lmi_forward_kernel<32, true, THREADS> : lmi_forward_kernel<32, false, THREADS>;
   }
+}
+static LmiFwdFn lmi_fwd_fn(int rp, bool smem, int threads) {
+  return threads == 384 ? lmi_fwd_fn_t<384>(rp, smem) : lmi_fwd_fn_t<256>(rp, smem);
 }
 // the backward LMI kernel reads F~z through L1/L2: only the few samples whose binding constraint is the
 // LMI need it, so staging 128 KB per CTA would cost more than it saves
@@ -212,10 +218,14 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   for (int tm = 1; tm <= 4 && rc == 0; tm *= 2)
     rc = allow_smem(reinterpret_cast<const void*>(lqs_fwd_fn(v.np, tm, p->lqs_smem)), p->lqs_smem_bytes);
   if (rc == 0 && v.lmi_r > 0) {
-    p->lmi_smem_bytes = lmi_smem(v.lmi_rp, true, v.n, kLmiThreads);
+    {
+      const char* env = getenv("RAYEN_LMI_THREADS");
+      p->lmi_fwd_threads = (env && atoi(env) == 256) ? 256 : ((env && atoi(env) == 384) ? 384 : kLmiFwdThreads);
+    }
+    p->lmi_smem_bytes = lmi_smem(v.lmi_rp, true, v.n, p->lmi_fwd_threads);
     p->lmi_smem = p->lmi_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
-    if (!p->lmi_smem) p->lmi_smem_bytes = lmi_smem(v.lmi_rp, false, v.n, kLmiThreads);
-    rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_fn(v.lmi_rp, p->lmi_smem)), p->lmi_smem_bytes);
+    if (!p->lmi_smem) p->lmi_smem_bytes = lmi_smem(v.lmi_rp, false, v.n, p->lmi_fwd_threads);
+    rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_fn(v.lmi_rp, p->lmi_smem, p->lmi_fwd_threads)), p->lmi_smem_bytes);
     p->lmi_bwd_smem_bytes = lmi_smem(v.lmi_rp, false, v.n, kLmiThreads);
     if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_bwd_fn(v.lmi_rp)), p->lmi_bwd_smem_bytes);
   }
@@ -258,7 +268,7 @@ extern "C" int rayen_plan_kernel_info(const rayen_plan_t* p, RayenKernelInfo* ou
   RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lqs_bwd_fn(p->dev.np))));
   out->regs_lqs_bwd = a.numRegs;
   if (p->dev.lmi_r > 0) {
-    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_fwd_fn(p->dev.lmi_rp, p->lmi_smem))));
+    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_fwd_fn(p->dev.lmi_rp, p->lmi_smem, p->lmi_fwd_threads))));
     out->regs_lmi_fwd = a.numRegs;
     RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_bwd_fn(p->dev.lmi_rp))));
     out->regs_lmi_bwd = a.numRegs;
@@ -385,10 +395,11 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
   }
   if (e == cudaSuccess && has_lmi && (stage_mask & 2)) {
     const int mpw = 32 / (d.lmi_rp / 4);
-    long long blocks = (B + static_cast<long long>(mpw) * (kLmiThreads / 32) - 1) / (static_cast<long long>(mpw) * (kLmiThreads / 32));
+    const int threads = p->lmi_fwd_threads;
+    long long blocks = (B + static_cast<long long>(mpw) * (threads / 32) - 1) / (static_cast<long long>(mpw) * (threads / 32));
     if (blocks > p->sm_count) blocks = p->sm_count;
-    LmiFwdFn lf = lmi_fwd_fn(d.lmi_rp, p->lmi_smem);
-    lf<<<static_cast<int>(blocks), kLmiThreads, p->lmi_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode, 1);
+    LmiFwdFn lf = lmi_fwd_fn(d.lmi_rp, p->lmi_smem, threads);
+    lf<<<static_cast<int>(blocks), threads, p->lmi_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode, 1);
     g_launches.fetch_add(1);
     e = cudaGetLastError();
   }
