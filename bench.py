@@ -170,18 +170,20 @@ class DeviceBench:
             self.sets.append(dict(
                 v=v.to(device), gy=gy.to(device),
                 y=torch.empty((batch, self.k), device=device), gv=torch.empty((batch, self.n), device=device),
-                kappa=torch.empty((batch,), device=device), active=torch.empty((batch,), dtype=torch.int32, device=device)))
+                kappa=torch.empty((batch,), device=device), active=torch.empty((batch,), dtype=torch.int32, device=device),
+                ws=torch.empty((max(self.plan.workspace_bytes(batch), 16),), dtype=torch.uint8, device=device)))
         self.stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
     def forward(self, s, stage=3):
         rc = self.lib.rayen_forward_stage_f32(self.plan.handle, s["v"].data_ptr(), self.n, s["y"].data_ptr(),
-                                              s["kappa"].data_ptr(), s["active"].data_ptr(), self.B, 0, stage, self.stream)
+                                              s["kappa"].data_ptr(), s["active"].data_ptr(), self.B, 0, stage,
+                                              s["ws"].data_ptr(), self.stream)
         self.cabi.check(rc, "rayen_forward_stage_f32")
 
     def backward(self, s, stage=3):
         rc = self.lib.rayen_backward_stage_f32(self.plan.handle, s["v"].data_ptr(), self.n, s["gy"].data_ptr(),
                                                s["kappa"].data_ptr(), s["active"].data_ptr(), s["gv"].data_ptr(),
-                                               self.n, self.B, 0, stage, self.stream)
+                                               self.n, self.B, 0, stage, s["ws"].data_ptr(), self.stream)
         self.cabi.check(rc, "rayen_backward_stage_f32")
 
     def step(self, i):
@@ -326,14 +328,17 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- per-kernel durations (CUDA events on the launching stream) and the roofline of the dominant one
     has_lmi = shp["r"] > 0
-    kernels = {"lqs_forward_kernel": lambda i: bench.forward(bench.sets[i % POOL], 1),
-               "lqs_backward_kernel": lambda i: bench.backward(bench.sets[i % POOL], 1)}
-    if has_lmi:
-        kernels["lmi_forward_kernel"] = lambda i: bench.forward(bench.sets[i % POOL], 2)
-        kernels["lmi_backward_kernel"] = lambda i: bench.backward(bench.sets[i % POOL], 2)
-    for i in range(POOL):  # make kappa/active valid in every set before timing single stages
+    # Single-stage launches must see the state the previous stage leaves behind (kappa/active and the work
+    # lists), so: full forward everywhere, then the two backward stages, then the two forward stages.
+    for i in range(POOL):
         bench.forward(bench.sets[i])
-    durs = {name: bench.time_loop(fn, steps, warmup) for name, fn in kernels.items()}
+    durs = {}
+    durs["lqs_backward_kernel"] = bench.time_loop(lambda i: bench.backward(bench.sets[i % POOL], 1), steps, POOL)
+    if has_lmi:
+        durs["lmi_backward_kernel"] = bench.time_loop(lambda i: bench.backward(bench.sets[i % POOL], 2), steps, POOL)
+    durs["lqs_forward_kernel"] = bench.time_loop(lambda i: bench.forward(bench.sets[i % POOL], 1), steps, POOL)
+    if has_lmi:
+        durs["lmi_forward_kernel"] = bench.time_loop(lambda i: bench.forward(bench.sets[i % POOL], 2), steps, POOL)
     dominant = max(durs, key=durs.get)
     fwd_bytes, bwd_bytes = batch * 4 * (n + k), batch * 4 * (2 * n + k)
     alg_bytes = fwd_bytes if "forward" in dominant else bwd_bytes

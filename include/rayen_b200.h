@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RAYEN_ABI_VERSION 3
+#define RAYEN_ABI_VERSION 4
 
 /* error codes (negative); positive return values are cudaError_t */
 #define RAYEN_OK 0
@@ -59,6 +59,9 @@ extern "C" {
  *           triangular factor R (R'R = M_z' M_z) packed like G, then {A = tau^2 - beta'beta, 0,0,0}
  *   NMAT    k rows of N (= NA_E), row stride np+4 (absent when N is the identity)
  *   Y0      y0 = N z0 + yp, k_pad words
+ *   BOUND   (plans with an LMI) t[np] (t_a = tr F~z_a), the packed triangular factor T of the Gram matrix
+ *           [tr(F~z_a F~z_b)]_ab, then {r, 0, 0, 0}: the Wolkowicz-Styan bound
+ *           lambda_max(S~(u)) <= t.u/r + sqrt((r-1)/r) sqrt(|T u|^2 - (t.u)^2/r) that prunes the eigen-solve
  *   LMI     F~z_a = sum_i N[i][a] * (-L' F_i L), a < n, each rp x rp (rp = r rounded up to 4, 8, 16
  *           or 32, zero padded), stored [a][row i][lane q][slot t] with column j = q + (rp/4)*t
  */
@@ -78,8 +81,8 @@ typedef struct RayenPlanDesc {
   int32_t lin_chunk_stride;
   int32_t quad_stride;
   int32_t soc_stride;
-  int32_t reserved0;
-  int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_lmi;
+  int32_t lmi_prune; /* 1: the BOUND section is valid and pruning may be used */
+  int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi;
   int64_t blob_words;
   const float* blob; /* host pointer, blob_words floats */
 } RayenPlanDesc;
@@ -97,6 +100,15 @@ void rayen_plan_destroy(rayen_plan_t* plan);
 /* Optional launch tuning for sweeps: samples per thread (1, 2 or 4; 0 = auto) and lanes per sample
  * (power of two <= 32; 0 = auto) of the linear/quadratic/SOC kernel. */
 int rayen_plan_set_tuning(rayen_plan_t* plan, int samples_per_thread, int lanes_per_sample);
+/* LMI pruning on (1, default) / off (0): with pruning the eigen-solve only runs for the samples whose
+ * Wolkowicz-Styan bound does not already prove kappa_LMI < kappa of the other families.  Results are
+ * identical either way (the bound is a proof, not an approximation). */
+int rayen_plan_set_pruning(rayen_plan_t* plan, int enabled);
+
+/* Device scratch the forward / backward calls need for a batch of B samples (work lists of the samples
+ * that still need the LMI kernels).  0 for plans without an LMI.  The caller owns the buffer; it must
+ * not be shared by calls that may run concurrently. */
+int64_t rayen_workspace_bytes(const rayen_plan_t* plan, int64_t B);
 
 /*
  * Forward: replaces forwardForRAYEN / forwardForRAYENOld + computeKappa + getyFromz
@@ -104,9 +116,10 @@ int rayen_plan_set_tuning(rayen_plan_t* plan, int samples_per_thread, int lanes_
  *   v      [B, ldv]  (ldv >= n, or >= n+1 for RAYEN_OLD), y [B, k]
  *   kappa  [B] and active [B] receive kappa and (family << 24 | index) of the binding constraint;
  *          they are what backward needs.  They may be NULL only for plans without an LMI.
+ *   workspace  rayen_workspace_bytes(plan, B) bytes of device memory (may be NULL when that is 0)
  */
 int rayen_forward_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, float* y, float* kappa,
-                      int32_t* active, int64_t B, int mode, void* cuda_stream);
+                      int32_t* active, int64_t B, int mode, void* workspace, void* cuda_stream);
 
 /*
  * Backward: the closed form of what autograd derives from the reference forward.
@@ -114,16 +127,17 @@ int rayen_forward_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, flo
  */
 int rayen_backward_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, const float* gy,
                        const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
-                       int mode, void* cuda_stream);
+                       int mode, void* workspace, void* cuda_stream);
 
 /* Per-kernel launches for profiling and the roofline measurement in bench.py: stage_mask bit 0 = the
  * linear/quadratic/SOC kernel, bit 1 = the LMI kernel (3 = what rayen_forward_f32 / rayen_backward_f32
- * launch).  With stage_mask == 2 the kappa/active buffers must already hold the first stage's result. */
+ * launch).  With stage_mask == 2 the kappa/active buffers and the workspace must already hold the first stage's result. */
 int rayen_forward_stage_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, float* y, float* kappa,
-                            int32_t* active, int64_t B, int mode, int stage_mask, void* cuda_stream);
+                            int32_t* active, int64_t B, int mode, int stage_mask, void* workspace,
+                            void* cuda_stream);
 int rayen_backward_stage_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, const float* gy,
                              const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
-                             int mode, int stage_mask, void* cuda_stream);
+                             int mode, int stage_mask, void* workspace, void* cuda_stream);
 
 /* Host-buffer variants (the end-to-end path): host->device copies, the kernels, device->host
  * copies, all on `cuda_stream`, which is synchronised before returning.  Host buffers should be

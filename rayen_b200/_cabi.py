@@ -16,7 +16,7 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "rayen_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MODE_RAYEN, MODE_RAYEN_OLD = 0, 1
 FAM_NONE, FAM_LINEAR, FAM_QUAD, FAM_SOC, FAM_LMI = 0, 1, 2, 3, 4
 
@@ -24,9 +24,9 @@ FAM_NONE, FAM_LINEAR, FAM_QUAD, FAM_SOC, FAM_LMI = 0, 1, 2, 3, 4
 class RayenPlanDesc(ctypes.Structure):
     _fields_ = [(name, ctypes.c_int32) for name in (
         "abi_version", "n", "k", "np", "k_pad", "m", "m_pad", "n_quad", "n_soc", "lmi_r", "lmi_rp",
-        "n_is_identity", "lin_chunk_stride", "quad_stride", "soc_stride", "reserved0")] + [
+        "n_is_identity", "lin_chunk_stride", "quad_stride", "soc_stride", "lmi_prune")] + [
         (name, ctypes.c_int64) for name in (
-            "off_lin", "off_quad", "off_soc", "off_nmat", "off_y0", "off_lmi", "blob_words")] + [
+            "off_lin", "off_quad", "off_soc", "off_nmat", "off_y0", "off_bound", "off_lmi", "blob_words")] + [
         ("blob", ctypes.POINTER(ctypes.c_float))]
 
 
@@ -44,13 +44,15 @@ SYMBOLS = {
     "rayen_plan_create": (ctypes.c_int, [ctypes.POINTER(RayenPlanDesc), ctypes.c_int, ctypes.POINTER(_P)]),
     "rayen_plan_destroy": (None, [_P]),
     "rayen_plan_set_tuning": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int]),
-    "rayen_forward_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, ctypes.c_int64, ctypes.c_int, _P]),
+    "rayen_plan_set_pruning": (ctypes.c_int, [_P, ctypes.c_int]),
+    "rayen_workspace_bytes": (ctypes.c_int64, [_P, ctypes.c_int64]),
+    "rayen_forward_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, ctypes.c_int64, ctypes.c_int, _P, _P]),
     "rayen_backward_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_int64,
-                                          ctypes.c_int, _P]),
+                                          ctypes.c_int, _P, _P]),
     "rayen_forward_stage_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, ctypes.c_int64, ctypes.c_int,
-                                               ctypes.c_int, _P]),
+                                               ctypes.c_int, _P, _P]),
     "rayen_backward_stage_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, _P, ctypes.c_int64,
-                                                ctypes.c_int64, ctypes.c_int, ctypes.c_int, _P]),
+                                                ctypes.c_int64, ctypes.c_int, ctypes.c_int, _P, _P]),
     "rayen_host_workspace_bytes": (ctypes.c_int64, [_P, ctypes.c_int64]),
     "rayen_forward_backward_host_f32": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int64, _P, _P]),
     "rayen_launch_count": (ctypes.c_int64, []),
@@ -131,6 +133,12 @@ class DevicePlan:
 
     def set_tuning(self, samples_per_thread=0, lanes_per_sample=0):
         check(lib().rayen_plan_set_tuning(self._handle, samples_per_thread, lanes_per_sample), "rayen_plan_set_tuning")
+
+    def set_pruning(self, enabled=True):
+        check(lib().rayen_plan_set_pruning(self._handle, 1 if enabled else 0), "rayen_plan_set_pruning")
+
+    def workspace_bytes(self, batch):
+        return int(lib().rayen_workspace_bytes(self._handle, int(batch)))
 
     def kernel_info(self):
         info = RayenKernelInfo()

@@ -56,10 +56,12 @@ class _RayShoot(torch.autograd.Function):
         y = torch.empty((B, k), dtype=torch.float32, device=v.device)
         kappa = torch.empty((B,), dtype=torch.float32, device=v.device)
         active = torch.empty((B,), dtype=torch.int32, device=v.device)
+        ws = torch.empty((max(dev_plan.workspace_bytes(B), 16),), dtype=torch.uint8, device=v.device)
         with torch.cuda.device(v.device):
             stream = torch.cuda.current_stream(v.device).cuda_stream
             rc = lib.rayen_forward_f32(dev_plan.handle, v.data_ptr(), v.stride(0) if B > 0 else cols, y.data_ptr(),
-                                       kappa.data_ptr(), active.data_ptr(), B, mode, ctypes.c_void_p(stream))
+                                       kappa.data_ptr(), active.data_ptr(), B, mode, ws.data_ptr(),
+                                       ctypes.c_void_p(stream))
         _cabi.check(rc, "rayen_forward_f32")
         ctx.module = module
         ctx.in_dtype = q.dtype
@@ -79,11 +81,12 @@ class _RayShoot(torch.autograd.Function):
         B, cols = v.shape
         gv = torch.empty((B, cols), dtype=torch.float32, device=v.device)
         dev_plan = module._device_plan(v.device)
+        ws = torch.empty((max(dev_plan.workspace_bytes(B), 16),), dtype=torch.uint8, device=v.device)
         with torch.cuda.device(v.device):
             stream = torch.cuda.current_stream(v.device).cuda_stream
             rc = lib.rayen_backward_f32(dev_plan.handle, v.data_ptr(), v.stride(0) if B > 0 else cols, gy.data_ptr(),
                                         kappa.data_ptr(), active.data_ptr(), gv.data_ptr(), cols, B, module._mode,
-                                        ctypes.c_void_p(stream))
+                                        ws.data_ptr(), ctypes.c_void_p(stream))
         _cabi.check(rc, "rayen_backward_f32")
         return (gv if ctx.in_dtype == torch.float32 else gv.to(ctx.in_dtype)), None
 
@@ -210,6 +213,11 @@ class ConstraintModule(nn.Module):
                                                      ctypes.c_void_p(stream))
         _cabi.check(rc, "rayen_forward_backward_host_f32")
         return y_host, gv_host
+
+    def set_pruning(self, enabled=True, device=None):
+        """LMI pruning on/off (results are identical; see include/rayen_b200.h)."""
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._device_plan(device).set_pruning(enabled)
 
     def last_kappa_and_active(self):
         """(kappa[B], active[B]) of the most recent forward: active = family << 24 | constraint index."""

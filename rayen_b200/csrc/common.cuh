@@ -12,10 +12,10 @@ struct PlanDev {
   const float* blob;
   int n, k, np, k_pad;
   int m, m_pad, n_quad, n_soc;
-  int lmi_r, lmi_rp, n_is_identity;
+  int lmi_r, lmi_rp, n_is_identity, lmi_prune;
   int lin_stride, quad_stride, soc_stride;
-  int off_lin, off_quad, off_soc, off_nmat, off_y0, off_lmi;
-  int lqs_words;   // words [off_lin, off_lin + lqs_words) = LIN | QUAD | SOC | NMAT | Y0, staged to smem
+  int off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi;
+  int lqs_words;   // words [off_lin, off_lin + lqs_words) = LIN | QUAD | SOC | NMAT | Y0 | BOUND, staged to smem
   int lmi_words;   // n * rp * rp
 };
 

@@ -23,7 +23,7 @@
 namespace rayen {
 
 constexpr int kLmiThreads = 256;     // backward kernel (keeps the reflectors: needs the registers)
-constexpr int kLmiFwdThreads = 384;  // forward kernel: 12 warps per SM
+constexpr int kLmiFwdThreads = 256;  // forward kernel default (384 = 12 warps/SM with spills: RAYEN_LMI_THREADS=384)
 constexpr int kLmiMaxN = 32;
 
 template <int RP>
@@ -483,7 +483,7 @@ template <int RP, bool F_SMEM, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
     lmi_forward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, float* __restrict__ y,
                        float* __restrict__ kappa_io, int* __restrict__ active_io, long long B, int mode,
-                       int has_prior) {
+                       int has_prior, const int* __restrict__ work_list, const int* __restrict__ work_count) {
   using C = LmiCfg<RP>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -503,9 +503,12 @@ __global__ void __launch_bounds__(THREADS, 1)
   const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
   bool staged = !F_SMEM;
 
-  for (long long base = warp_id * C::MPW; base < B; base += n_warps * C::MPW) {
-    const long long b = base + grp;
-    const bool valid = b < B;
+  // dense mode: every sample; list mode: only the samples the LQS kernel could not prune
+  const long long total = work_list ? static_cast<long long>(*work_count) : B;
+  for (long long base = warp_id * C::MPW; base < total; base += n_warps * C::MPW) {
+    const long long idx = base + grp;
+    const bool valid = idx < total;
+    const long long b = valid ? (work_list ? static_cast<long long>(work_list[idx]) : idx) : 0;
     const float s = S.load_direction(v + b * ldv, n, valid);
     if (!staged) {
       mbar_wait(&bars[0], 0);
@@ -557,13 +560,14 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 // ----------------------------------------------------------------------------- backward
 // Only the samples whose binding constraint is the LMI and whose gradient needs d kappa/du are
-// processed; everything else was written by lqs_backward_kernel.  The work list is the batch itself:
-// a matrix group whose sample is not one of those skips to the next (warp-uniform when none is).
+// processed; everything else was written by lqs_backward_kernel, which also queued those samples in
+// the work list (dense mode without a list: every group checks its own sample).
 template <int RP>
 __global__ void __launch_bounds__(kLmiThreads, 1)
     lmi_backward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, const float* __restrict__ gy,
                         const float* __restrict__ kappa, const int* __restrict__ active, float* __restrict__ gv,
-                        long long ldgv, long long B, int mode) {
+                        long long ldgv, long long B, int mode, const int* __restrict__ work_list,
+                        const int* __restrict__ work_count) {
   using C = LmiCfg<RP>;
   constexpr bool F_SMEM = false;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -581,11 +585,13 @@ __global__ void __launch_bounds__(kLmiThreads, 1)
   const long long warp_id = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
   const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
 
-  for (long long base = warp_id * C::MPW; base < B; base += n_warps * C::MPW) {
-    const long long b = base + grp;
+  const long long total = work_list ? static_cast<long long>(*work_count) : B;
+  for (long long base = warp_id * C::MPW; base < total; base += n_warps * C::MPW) {
+    const long long idx = base + grp;
+    const long long b = (idx < total) ? (work_list ? static_cast<long long>(work_list[idx]) : idx) : 0;
     bool mine = false;
     float kap = 0.f;
-    if (b < B) {
+    if (idx < total) {
       kap = __ldg(kappa + b);
       mine = tag_family(__ldg(active + b)) == RAYEN_FAM_LMI && kap > 0.f;
     }

@@ -190,7 +190,8 @@ template <int NP, int TM, bool SMEM>
 __global__ void __launch_bounds__(lqs_max_threads(NP, TM), 1)
     lqs_forward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, float* __restrict__ y,
                        float* __restrict__ kappa_out, int* __restrict__ active_out, long long B, int mode,
-                       int L, int write_y) {
+                       int L, int lmi_follows, int prune, int* __restrict__ work_list,
+                       int* __restrict__ work_count) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   const float* cst;
@@ -256,6 +257,29 @@ __global__ void __launch_bounds__(lqs_max_threads(NP, TM), 1)
 #pragma unroll
     for (int t = 0; t < TM; ++t) group_argmax(best[t], tag[t], L);
 
+    // ---- LMI pruning: an upper bound of lambda_max(S~(u)) that needs no eigen-solve.  If it is below the
+    // kappa found so far, the LMI cannot bind and this kernel finishes the sample itself.
+    bool pruned[TM];
+#pragma unroll
+    for (int t = 0; t < TM; ++t) pruned[t] = false;
+    if (lmi_follows && prune) {
+      constexpr int TRI = (NP / 4) * (NP / 4 + 1) * 8;
+      const float* bnd = cst + (P.off_bound - P.off_lin);
+      float tu[TM], nrm2[TM];
+      dot_np<NP, TM>(bnd, u, tu);
+      tri_norm2<NP, TM>(bnd + NP, u, nrm2);
+      const float r = bnd[NP + TRI];
+      const float inv_r = 1.0f / r;
+#pragma unroll
+      for (int t = 0; t < TM; ++t) {
+        const float mean = tu[t] * inv_r;
+        const float dev2 = fmaxf(fmaf(-tu[t], mean, nrm2[t]), 0.f);
+        const float ub = mean + sqrtf((r - 1.0f) * inv_r * dev2);
+        // safety margin for the float32 rounding of the bound; being conservative only costs time
+        pruned[t] = fmaf(1e-4f, fabsf(ub), ub) + 1e-30f < best[t];
+      }
+    }
+
     const float* y0 = cst + (P.off_y0 - P.off_lin);
     const float* nmat = cst + (P.off_nmat - P.off_lin);
 #pragma unroll
@@ -264,11 +288,13 @@ __global__ void __launch_bounds__(lqs_max_threads(NP, TM), 1)
       const bool valid = (tile < n_tiles) && (b < B);
       if (!valid) continue;
       const float kap = best[t];
+      const bool finish = !lmi_follows || pruned[t];
       if (lane_l == 0) {
         if (kappa_out) kappa_out[b] = kap;
         if (active_out) active_out[b] = tag[t];
+        if (!finish && work_list) work_list[atomicAdd(work_count, 1)] = static_cast<int>(b);
       }
-      if (!write_y) continue;
+      if (!finish) continue;
       // shift-and-scale (reference constraint_module.py:472-474 / :464-465, :512-514)
       float alpha;
       if (mode == RAYEN_MODE_RAYEN_OLD)
@@ -476,12 +502,13 @@ __device__ __forceinline__ void store_row(float* __restrict__ row, int n, bool v
 }
 
 // One thread per sample.  Samples whose binding constraint is the LMI (and that need d kappa/du) are
-// left to lmi_backward_kernel.
+// appended to a work list for lmi_backward_kernel.
 template <int NP>
 __global__ void __launch_bounds__(256)
     lqs_backward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, const float* __restrict__ gy,
                         const float* __restrict__ kappa, const int* __restrict__ active, float* __restrict__ gv,
-                        long long ldgv, long long B, int mode) {
+                        long long ldgv, long long B, int mode, int* __restrict__ work_list,
+                        int* __restrict__ work_count) {
   const int n = P.n;
   const bool vec_v = ((n & 3) == 0) && ((ldv & 3) == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
   const bool vec_gy = ((P.k & 3) == 0) && ((reinterpret_cast<uintptr_t>(gy) & 15) == 0);
@@ -495,7 +522,11 @@ __global__ void __launch_bounds__(256)
     const float s = normalize_row<NP>(u);
     const float beta = (mode == RAYEN_MODE_RAYEN_OLD) ? __ldg(v + b * ldv + n) : 0.f;
     const bool boundary = (mode == RAYEN_MODE_RAYEN_OLD) ? (kap > 0.f) : (1.0f / kap < s);
-    if (boundary && tag_family(tag) == RAYEN_FAM_LMI) continue;
+    if (boundary && tag_family(tag) == RAYEN_FAM_LMI) {
+      // needs the eigenvector: queued for lmi_backward_kernel
+      if (work_list) work_list[atomicAdd(work_count, 1)] = static_cast<int>(b);
+      continue;
+    }
     float gz[NP], dk[NP], g[NP];
     load_gz<NP>(P, gy + b * P.k, vec_gy, gz);
     if (boundary) {

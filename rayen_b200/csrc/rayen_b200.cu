@@ -26,7 +26,8 @@ struct rayen_plan {
   bool lqs_smem;  // LQS constants fit in shared memory
   bool lmi_smem;  // LMI matrices fit in shared memory
   size_t lqs_smem_bytes, lmi_smem_bytes, lmi_bwd_smem_bytes;
-  bool has_lqs;   // any linear row / quadratic / cone (the linear section always has >= 1 row)
+  bool has_lqs;   // any non-zero linear row / quadratic / cone: otherwise the LQS forward kernel is skipped
+  bool prune;     // LMI pruning enabled (needs has_lqs and a BOUND section)
 };
 
 static thread_local char g_err[512] = "";
@@ -54,12 +55,14 @@ extern "C" const char* rayen_last_error(void) { return g_err; }
 extern "C" int64_t rayen_launch_count(void) { return g_launches.load(); }
 
 // ----------------------------------------------------------------------------- kernel tables
-typedef void (*LqsFwdFn)(const PlanDev, const float*, long long, float*, float*, int*, long long, int, int, int);
+typedef void (*LqsFwdFn)(const PlanDev, const float*, long long, float*, float*, int*, long long, int, int, int, int,
+                         int*, int*);
 typedef void (*LqsBwdFn)(const PlanDev, const float*, long long, const float*, const float*, const int*, float*,
-                         long long, long long, int);
-typedef void (*LmiFwdFn)(const PlanDev, const float*, long long, float*, float*, int*, long long, int, int);
+                         long long, long long, int, int*, int*);
+typedef void (*LmiFwdFn)(const PlanDev, const float*, long long, float*, float*, int*, long long, int, int,
+                         const int*, const int*);
 typedef void (*LmiBwdFn)(const PlanDev, const float*, long long, const float*, const float*, const int*, float*,
-                         long long, long long, int);
+                         long long, long long, int, const int*, const int*);
 
 static int np_index(int np) { return np == 4 ? 0 : np == 8 ? 1 : np == 16 ? 2 : np == 32 ? 3 : -1; }
 static int tm_index(int tm) { return tm == 1 ? 0 : tm == 2 ? 1 : tm == 4 ? 2 : -1; }
@@ -146,8 +149,8 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
     return fail(RAYEN_ERR_BAD_ARGUMENT, "bad padding m=%d m_pad=%d k=%d k_pad=%d", d->m, d->m_pad, d->k, d->k_pad);
   if (!d->blob || d->blob_words <= 0 || d->blob_words % 4)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "bad constant block (%lld words)", static_cast<long long>(d->blob_words));
-  const int64_t offs[6] = {d->off_lin, d->off_quad, d->off_soc, d->off_nmat, d->off_y0, d->off_lmi};
-  for (int i = 0; i < 6; ++i) {
+  const int64_t offs[7] = {d->off_lin, d->off_quad, d->off_soc, d->off_nmat, d->off_y0, d->off_bound, d->off_lmi};
+  for (int i = 0; i < 7; ++i) {
     if (offs[i] < 0 || offs[i] % 4 || offs[i] >= d->blob_words ||
         (i > 0 && offs[i] < offs[i - 1]))
       return fail(RAYEN_ERR_BAD_ARGUMENT, "section offset %d = %lld is invalid", i, static_cast<long long>(offs[i]));
@@ -164,7 +167,9 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
     return fail(RAYEN_ERR_BAD_ARGUMENT, "SOC section does not fit its slot");
   if (!d->n_is_identity && d->off_nmat + static_cast<int64_t>(d->k) * (d->np + 4) > d->off_y0)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "N section does not fit its slot");
-  if (d->off_y0 + d->k_pad > d->off_lmi) return fail(RAYEN_ERR_BAD_ARGUMENT, "y0 section does not fit its slot");
+  if (d->off_y0 + d->k_pad > d->off_bound) return fail(RAYEN_ERR_BAD_ARGUMENT, "y0 section does not fit its slot");
+  if (d->lmi_prune && d->off_bound + d->np + tri + 4 > d->off_lmi)
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "bound section does not fit its slot");
   if (d->lmi_r > 0 && d->off_lmi + static_cast<int64_t>(d->n) * d->lmi_rp * d->lmi_rp > d->blob_words)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "LMI section does not fit the block");
   if (d->blob_words > (1ll << 30)) return fail(RAYEN_ERR_UNSUPPORTED, "constant block too large");
@@ -206,11 +211,19 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   v.lin_stride = d->lin_chunk_stride; v.quad_stride = d->quad_stride; v.soc_stride = d->soc_stride;
   v.off_lin = static_cast<int>(d->off_lin); v.off_quad = static_cast<int>(d->off_quad);
   v.off_soc = static_cast<int>(d->off_soc); v.off_nmat = static_cast<int>(d->off_nmat);
-  v.off_y0 = static_cast<int>(d->off_y0); v.off_lmi = static_cast<int>(d->off_lmi);
+  v.off_y0 = static_cast<int>(d->off_y0); v.off_bound = static_cast<int>(d->off_bound);
+  v.off_lmi = static_cast<int>(d->off_lmi);
+  v.lmi_prune = (d->lmi_prune && d->lmi_r > 0) ? 1 : 0;
   v.lqs_words = static_cast<int>(d->off_lmi - d->off_lin);
   v.lmi_words = d->lmi_r > 0 ? d->n * d->lmi_rp * d->lmi_rp : 0;
 
-  p->has_lqs = true;
+  p->has_lqs = d->n_quad > 0 || d->n_soc > 0;
+  for (int64_t i = d->off_lin; i < d->off_quad && !p->has_lqs; ++i) p->has_lqs = d->blob[i] != 0.0f;
+  p->prune = p->has_lqs && v.lmi_prune;
+  {
+    const char* env = getenv("RAYEN_LMI_PRUNE");
+    if (env && atoi(env) == 0) p->prune = false;
+  }
   p->lqs_smem_bytes = 64 + static_cast<size_t>(v.lqs_words) * 4;
   p->lqs_smem = p->lqs_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
   if (!p->lqs_smem) p->lqs_smem_bytes = 64;
@@ -257,6 +270,20 @@ extern "C" int rayen_plan_set_tuning(rayen_plan_t* p, int tm, int lanes) {
   p->tune_tm = tm;
   p->tune_lanes = lanes;
   return RAYEN_OK;
+}
+
+extern "C" int rayen_plan_set_pruning(rayen_plan_t* p, int enabled) {
+  if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "null plan");
+  p->prune = enabled && p->has_lqs && p->dev.lmi_prune;
+  return RAYEN_OK;
+}
+
+// workspace: [fwd counter, bwd counter, pad to 256 B][forward work list: B ints][backward work list: B ints]
+static int64_t ws_list_bytes(int64_t B) { return (B * 4 + 255) / 256 * 256; }
+extern "C" int64_t rayen_workspace_bytes(const rayen_plan_t* p, int64_t B) {
+  if (!p || B < 0) return -1;
+  if (p->dev.lmi_r == 0) return 0;
+  return 256 + 2 * ws_list_bytes(B);
 }
 
 extern "C" int rayen_plan_kernel_info(const rayen_plan_t* p, RayenKernelInfo* out) {
@@ -354,23 +381,24 @@ static int check_io(const rayen_plan* p, const void* a, const void* b, long long
 
 // ----------------------------------------------------------------------------- forward / backward
 static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa, int32_t* active,
-                        int64_t B, int mode, void* stream_, int stage_mask);
+                        int64_t B, int mode, void* workspace, void* stream_, int stage_mask);
 
 extern "C" int rayen_forward_f32(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa,
-                                 int32_t* active, int64_t B, int mode, void* stream_) {
-  return forward_impl(p, v, ldv, y, kappa, active, B, mode, stream_, 3);
+                                 int32_t* active, int64_t B, int mode, void* workspace, void* stream_) {
+  return forward_impl(p, v, ldv, y, kappa, active, B, mode, workspace, stream_, 3);
 }
 extern "C" int rayen_forward_stage_f32(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa,
-                                       int32_t* active, int64_t B, int mode, int stage_mask, void* stream_) {
+                                       int32_t* active, int64_t B, int mode, int stage_mask, void* workspace,
+                                       void* stream_) {
   if (stage_mask < 1 || stage_mask > 3) return fail(RAYEN_ERR_BAD_ARGUMENT, "stage_mask must be 1, 2 or 3");
-  return forward_impl(p, v, ldv, y, kappa, active, B, mode, stream_, stage_mask);
+  return forward_impl(p, v, ldv, y, kappa, active, B, mode, workspace, stream_, stage_mask);
 }
 extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, int64_t ldv, const float* gy,
                                         const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
-                                        int mode, int stage_mask, void* stream_);
+                                        int mode, int stage_mask, void* workspace, void* stream_);
 
 static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa, int32_t* active,
-                        int64_t B, int mode, void* stream_, int stage_mask) {
+                        int64_t B, int mode, void* workspace, void* stream_, int stage_mask) {
   int rc = check_io(p, v, y, B, mode);
   if (rc) return rc;
   if (B == 0) return RAYEN_OK;
@@ -385,13 +413,23 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
   RAYEN_CUDA(cudaGetDevice(&prev));
   if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
 
+  if (has_lmi && !workspace) return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the workspace buffer");
+  int* counters = static_cast<int*>(workspace);
+  int* fwd_list = has_lmi ? reinterpret_cast<int*>(static_cast<char*>(workspace) + 256) : nullptr;
+  const bool run_lqs = p->has_lqs || !has_lmi;
+  const bool use_list = has_lmi && run_lqs && p->prune;
   cudaError_t e = cudaSuccess;
-  if (stage_mask & 1) {
+  if ((stage_mask & 1) && run_lqs) {
+    if (use_list) e = cudaMemsetAsync(counters, 0, sizeof(int), stream);
     const LqsGeom g = lqs_geometry(p, B);
     LqsFwdFn f = lqs_fwd_fn(d.np, g.tm, p->lqs_smem);
-    f<<<g.grid, g.block, p->lqs_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode, g.lanes, has_lmi ? 0 : 1);
-    g_launches.fetch_add(1);
-    e = cudaGetLastError();
+    if (e == cudaSuccess) {
+      f<<<g.grid, g.block, p->lqs_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode, g.lanes, has_lmi ? 1 : 0,
+                                                        use_list ? 1 : 0, use_list ? fwd_list : nullptr,
+                                                        use_list ? counters : nullptr);
+      g_launches.fetch_add(1);
+      e = cudaGetLastError();
+    }
   }
   if (e == cudaSuccess && has_lmi && (stage_mask & 2)) {
     const int mpw = 32 / (d.lmi_rp / 4);
@@ -399,7 +437,9 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
     long long blocks = (B + static_cast<long long>(mpw) * (threads / 32) - 1) / (static_cast<long long>(mpw) * (threads / 32));
     if (blocks > p->sm_count) blocks = p->sm_count;
     LmiFwdFn lf = lmi_fwd_fn(d.lmi_rp, p->lmi_smem, threads);
-    lf<<<static_cast<int>(blocks), threads, p->lmi_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode, 1);
+    lf<<<static_cast<int>(blocks), threads, p->lmi_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode,
+                                                                         run_lqs ? 1 : 0, use_list ? fwd_list : nullptr,
+                                                                         use_list ? counters : nullptr);
     g_launches.fetch_add(1);
     e = cudaGetLastError();
   }
@@ -410,13 +450,13 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
 
 extern "C" int rayen_backward_f32(const rayen_plan_t* p, const float* v, int64_t ldv, const float* gy,
                                   const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
-                                  int mode, void* stream_) {
-  return rayen_backward_stage_f32(p, v, ldv, gy, kappa, active, gv, ldgv, B, mode, 3, stream_);
+                                  int mode, void* workspace, void* stream_) {
+  return rayen_backward_stage_f32(p, v, ldv, gy, kappa, active, gv, ldgv, B, mode, 3, workspace, stream_);
 }
 
 extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, int64_t ldv, const float* gy,
                                         const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
-                                        int mode, int stage_mask, void* stream_) {
+                                        int mode, int stage_mask, void* workspace, void* stream_) {
   if (stage_mask < 1 || stage_mask > 3) return fail(RAYEN_ERR_BAD_ARGUMENT, "stage_mask must be 1, 2 or 3");
   int rc = check_io(p, v, gy, B, mode);
   if (rc) return rc;
@@ -436,19 +476,28 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
   long long grid = (B + block - 1) / block;
   const long long cap = static_cast<long long>(p->sm_count) * 16;
   if (grid > cap) grid = cap;
+  const bool has_lmi = d.lmi_r > 0;
+  if (has_lmi && !workspace) return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the workspace buffer");
+  int* counters = static_cast<int*>(workspace);
+  int* bwd_list = has_lmi ? reinterpret_cast<int*>(static_cast<char*>(workspace) + 256 + ws_list_bytes(B)) : nullptr;
   cudaError_t e = cudaSuccess;
   if (stage_mask & 1) {
+    if (has_lmi) e = cudaMemsetAsync(counters + 1, 0, sizeof(int), stream);
     LqsBwdFn f = lqs_bwd_fn(d.np);
-    f<<<static_cast<int>(grid), block, 0, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
-    g_launches.fetch_add(1);
-    e = cudaGetLastError();
+    if (e == cudaSuccess) {
+      f<<<static_cast<int>(grid), block, 0, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode, bwd_list,
+                                                      has_lmi ? counters + 1 : nullptr);
+      g_launches.fetch_add(1);
+      e = cudaGetLastError();
+    }
   }
-  if (e == cudaSuccess && d.lmi_r > 0 && (stage_mask & 2)) {
+  if (e == cudaSuccess && has_lmi && (stage_mask & 2)) {
     const int mpw = 32 / (d.lmi_rp / 4);
     long long blocks = (B + static_cast<long long>(mpw) * (kLmiThreads / 32) - 1) / (static_cast<long long>(mpw) * (kLmiThreads / 32));
     if (blocks > p->sm_count) blocks = p->sm_count;
     LmiBwdFn lf = lmi_bwd_fn(d.lmi_rp);
-    lf<<<static_cast<int>(blocks), kLmiThreads, p->lmi_bwd_smem_bytes, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
+    lf<<<static_cast<int>(blocks), kLmiThreads, p->lmi_bwd_smem_bytes, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv,
+                                                                                B, mode, bwd_list, counters + 1);
     g_launches.fetch_add(1);
     e = cudaGetLastError();
   }
@@ -463,7 +512,7 @@ extern "C" int64_t rayen_host_workspace_bytes(const rayen_plan_t* p, int64_t B) 
   const int64_t n = p->dev.n, k = p->dev.k;
   // v | gy | y | gv | kappa | active, each rounded up to 256 B
   auto r = [](int64_t x) { return (x + 255) / 256 * 256; };
-  return r(B * n * 4) * 2 + r(B * k * 4) * 2 + r(B * 4) * 2;
+  return r(B * n * 4) * 2 + r(B * k * 4) * 2 + r(B * 4) * 2 + rayen_workspace_bytes(p, B);
 }
 
 extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* p, const float* v_host, const float* gy_host,
@@ -481,17 +530,18 @@ extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* p, const floa
   float* y = reinterpret_cast<float*>(w); w += r(B * k * 4);
   float* gv = reinterpret_cast<float*>(w); w += r(B * n * 4);
   float* kappa = reinterpret_cast<float*>(w); w += r(B * 4);
-  int32_t* active = reinterpret_cast<int32_t*>(w);
+  int32_t* active = reinterpret_cast<int32_t*>(w); w += r(B * 4);
+  void* ws = rayen_workspace_bytes(p, B) > 0 ? static_cast<void*>(w) : nullptr;
   int prev = 0;
   RAYEN_CUDA(cudaGetDevice(&prev));
   if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
   int rc = 0;
   cudaError_t e = cudaMemcpyAsync(v, v_host, B * n * 4, cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(gy, gy_host, B * k * 4, cudaMemcpyHostToDevice, stream);
-  if (e == cudaSuccess) rc = rayen_forward_f32(p, v, n, y, kappa, active, B, RAYEN_MODE_RAYEN, stream);
+  if (e == cudaSuccess) rc = rayen_forward_f32(p, v, n, y, kappa, active, B, RAYEN_MODE_RAYEN, ws, stream);
   if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(y_host, y, B * k * 4, cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess && rc == 0)
-    rc = rayen_backward_f32(p, v, n, gy, kappa, active, gv, n, B, RAYEN_MODE_RAYEN, stream);
+    rc = rayen_backward_f32(p, v, n, gy, kappa, active, gv, n, B, RAYEN_MODE_RAYEN, ws, stream);
   if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(gv_host, gv, B * n * 4, cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(stream);
   if (prev != p->device) cudaSetDevice(prev);

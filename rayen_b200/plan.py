@@ -19,7 +19,7 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_NP = 32
 MAX_LMI = 32
 
@@ -179,19 +179,9 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None):
         soc_f64.append((cz, h, Mz, A, R))
     off_soc = add(soc) if len(socs) else add(np.zeros(4))
 
-    # ---- N and y0
-    n_is_identity = int(k == n and np.array_equal(N, np.eye(k)))
-    nm = np.zeros((k, np_ + 4))
-    nm[:, :n] = N
-    off_nmat = add(nm) if not n_is_identity else add(np.zeros(4))
-    y0p = np.zeros(k_pad)
-    y0p[:k] = y0[:, 0]
-    off_y0 = add(y0p)
-
     # ---- LMI (reference constraint_module.py:43-52 and :412-421, congruence folded into the constants)
     lmi_r = lmi_rp = 0
-    off_lmi = add(np.zeros(4))
-    Fz = None
+    Fz = Fperm = None
     if lmi is not None:
         allF = np.asarray([f64(F) for F in lmi])
         lmi_r = allF.shape[1]
@@ -211,7 +201,27 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None):
         Fpad[:, :lmi_r, :lmi_r] = Fz
         # [a][i][q][t] with column j = q + lpm*t
         Fperm = Fpad.reshape(n, lmi_rp, 4, lpm).transpose(0, 1, 3, 2)
-        off_lmi = add(Fperm)
+
+    # ---- N and y0
+    n_is_identity = int(k == n and np.array_equal(N, np.eye(k)))
+    nm = np.zeros((k, np_ + 4))
+    nm[:, :n] = N
+    off_nmat = add(nm) if not n_is_identity else add(np.zeros(4))
+    y0p = np.zeros(k_pad)
+    y0p[:k] = y0[:, 0]
+    off_y0 = add(y0p)
+
+    # ---- pruning bound of the LMI: lambda_max(S) <= tr(S)/r + sqrt((r-1)/r) sqrt(|S|_F^2 - tr(S)^2/r)
+    # (Wolkowicz-Styan), with tr(S~(u)) = t.u and |S~(u)|_F = |T u|, T'T = [tr(F~z_a F~z_b)]_ab.  Lets the
+    # linear/quadratic/SOC kernel prove, for most samples, that the LMI cannot be the binding constraint.
+    bound = np.zeros(np_ + tri_words + 4)
+    if lmi is not None:
+        bound[:n] = np.trace(Fz, axis1=1, axis2=2)
+        gram = np.einsum("aij,bij->ab", Fz, Fz)
+        bound[np_:np_ + tri_words] = _pack_triangular(_triangular_factor(gram, np_))
+        bound[np_ + tri_words] = float(lmi_r)
+    off_bound = add(bound)
+    off_lmi = add(Fperm) if lmi is not None else add(np.zeros(4))
 
     blob = np.concatenate(sections).astype(np.float32)
     assert blob.size == cursor and cursor % 4 == 0
@@ -220,7 +230,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None):
                        lmi_r=lmi_r, lmi_rp=lmi_rp, n_is_identity=n_is_identity,
                        lin_chunk_stride=lin_stride, quad_stride=quad_stride, soc_stride=soc_stride,
                        off_lin=off_lin, off_quad=off_quad, off_soc=off_soc, off_nmat=off_nmat,
-                       off_y0=off_y0, off_lmi=off_lmi)
+                       off_y0=off_y0, off_bound=off_bound, off_lmi=off_lmi, lmi_prune=int(lmi is not None))
     plan.f64 = dict(D=D, N=N, y0=y0, z0=z0, yp=yp, quads=quad_f64, socs=soc_f64, Fz=Fz)
     return plan
 

@@ -17,11 +17,13 @@ for arg in sys.argv[1:]:
     db = B.DeviceBench(layer, batch, dev, pool=max(2, min(16, int(300e6 // per_set) + 1)))
     for i in range(db.pool): db.forward(db.sets[i])
     out = {}
-    out["lqs_fwd"] = db.time_loop(lambda i: db.forward(db.sets[i % db.pool], 1), 20, 3)
-    out["lqs_bwd"] = db.time_loop(lambda i: db.backward(db.sets[i % db.pool], 1), 20, 3)
+    P = db.pool
+    out["lqs_bwd"] = db.time_loop(lambda i: db.backward(db.sets[i % P], 1), 20, P)
     if cs.has_lmi_constraints:
-        out["lmi_fwd"] = db.time_loop(lambda i: db.forward(db.sets[i % db.pool], 2), 20, 3)
-        out["lmi_bwd"] = db.time_loop(lambda i: db.backward(db.sets[i % db.pool], 2), 20, 3)
+        out["lmi_bwd"] = db.time_loop(lambda i: db.backward(db.sets[i % P], 2), 20, P)
+    out["lqs_fwd"] = db.time_loop(lambda i: db.forward(db.sets[i % P], 1), 20, P)
+    if cs.has_lmi_constraints:
+        out["lmi_fwd"] = db.time_loop(lambda i: db.forward(db.sets[i % P], 2), 20, P)
     out["step"] = db.time_loop(db.step, 20, 3)
     act = db.sets[0]["active"].cpu().numpy() >> 24
     import numpy as np

@@ -220,6 +220,30 @@ def test_launch_geometry_does_not_change_results():
             assert torch.equal(out, base) or (out - base).abs().max() <= 1e-6 * base.abs().max(), (tm, lanes)
 
 
+def test_lmi_pruning_does_not_change_results():
+    """The Wolkowicz-Styan pruning bound is a proof, not an approximation: kappa, the binding constraint and
+    g_v are bit-identical; y may differ in the last bit because the two kernels sum |v|^2 in a different order."""
+    for loosen in (1.0, 4.0):
+        spec = synthetic.config_spec("cfg5")
+        spec["b1"] = spec["b1"] * loosen
+        cs = synthetic.build_constraints(spec)
+        v, gy = synthetic.sample_inputs(3000, cs.n, cs.k)
+        outs = []
+        for enabled in (True, False):
+            layer = ConstraintModule(cs, create_map=False).to(DEV)
+            layer.set_pruning(enabled, device=DEV)
+            x = v.to(DEV).requires_grad_(True)
+            y = layer(x.unsqueeze(2))
+            (y[:, :, 0] * gy.to(DEV)).sum().backward()
+            kap, act = layer.last_kappa_and_active()
+            outs.append((y.detach().cpu(), x.grad.cpu(), kap.cpu(), act.cpu()))
+        assert (outs[0][0] - outs[1][0]).abs().max() <= 2e-7 * outs[1][0].abs().max()
+        for a, b in zip(outs[0][1:], outs[1][1:]):
+            assert torch.equal(a, b)
+        if loosen > 1.0:
+            assert int(((outs[0][3] >> 24) == _cabi.FAM_LMI).sum()) > 50   # the LMI really binds for some samples
+
+
 def test_host_buffer_path_matches_device_path():
     spec = synthetic.config_spec("cfg5")
     spec["b1"] = spec["b1"] * 4.0
@@ -293,10 +317,16 @@ def test_c_abi_error_codes_on_gpu():
     v = torch.zeros(4, cs.n, device=DEV)
     y = torch.zeros(4, cs.k, device=DEV)
     null = ctypes.c_void_p(0)
-    # LMI plans need the kappa / active outputs
-    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n, y.data_ptr(), null, null, 4, 0, null) == -1
+    # LMI plans need the kappa / active outputs and the workspace
+    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n, y.data_ptr(), null, null, 4, 0, null, null) == -1
     assert b"kappa" in lib.rayen_last_error()
-    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n - 1, y.data_ptr(), null, null, 4, 0, null) == -1
-    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n, y.data_ptr(), null, null, 4, 7, null) == -1
+    kap = torch.zeros(4, device=DEV)
+    act = torch.zeros(4, dtype=torch.int32, device=DEV)
+    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n, y.data_ptr(), kap.data_ptr(), act.data_ptr(), 4, 0,
+                                 null, null) == -1
+    assert b"workspace" in lib.rayen_last_error()
+    assert plan.workspace_bytes(4) >= 256 + 32
+    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n - 1, y.data_ptr(), null, null, 4, 0, null, null) == -1
+    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n, y.data_ptr(), null, null, 4, 7, null, null) == -1
     info = plan.kernel_info()
     assert info["sm_count"] >= 100 and info["regs_lmi_fwd"] > 0
