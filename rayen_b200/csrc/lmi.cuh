@@ -248,7 +248,7 @@ struct LmiSolver {
   // count(x) = #negative pivots of the LDL' of T - xI = #eigenvalues below x (quotient-form Sturm
   // sequence with the usual pivmin guard); x is above the spectrum iff count == RP.
   __device__ __forceinline__ float lambda_max_relu() {
-    float d[WANT_GRAD ? 1 : RP], e2[WANT_GRAD ? 1 : RP];
+    float d[RP], e2[RP];
     float dmax = -3.0e38f, hi = -3.0e38f, lo_g = 3.0e38f;
     {
       float eprev = 0.f;
@@ -262,10 +262,8 @@ struct LmiSolver {
           dmax = fmaxf(dmax, da[ii]);
           hi = fmaxf(hi, da[ii] + rad);
           lo_g = fminf(lo_g, da[ii] - rad);
-          if constexpr (!WANT_GRAD) {
-            d[4 * i4 + ii] = da[ii];
-            e2[4 * i4 + ii] = eprev * eprev;  // e2[i] couples rows i-1 and i
-          }
+          d[4 * i4 + ii] = da[ii];
+          e2[4 * i4 + ii] = eprev * eprev;  // e2[i] couples rows i-1 and i
           eprev = ea[ii];
         }
       }
@@ -285,22 +283,11 @@ struct LmiSolver {
         const float x = fmaf(h, static_cast<float>(pt + 1), lo);
         int neg = 0;
         float piv = 1.f;
-        if constexpr (!WANT_GRAD) {
 #pragma unroll
-          for (int i = 0; i < RP; ++i) {
-            piv = (d[i] - x) - (i == 0 ? 0.f : __fdividef(e2[i], piv));
-            if (fabsf(piv) < pivmin) piv = -pivmin;
-            neg += (piv < 0.f) ? 1 : 0;
-          }
-        } else {
-          float eprev = 0.f;
-          for (int i = 0; i < RP; ++i) {
-            const float di = sd()[i];
-            piv = (di - x) - (i == 0 ? 0.f : __fdividef(eprev * eprev, piv));
-            if (fabsf(piv) < pivmin) piv = -pivmin;
-            neg += (piv < 0.f) ? 1 : 0;
-            eprev = se()[i];
-          }
+        for (int i = 0; i < RP; ++i) {
+          piv = (d[i] - x) - (i == 0 ? 0.f : __fdividef(e2[i], piv));
+          if (fabsf(piv) < pivmin) piv = -pivmin;
+          neg += (piv < 0.f) ? 1 : 0;
         }
         bits |= (neg == RP) ? (1 << pt) : 0;
       }
@@ -499,7 +486,9 @@ __global__ void __launch_bounds__(THREADS, 1)
   const int n = P.n, k = P.k;
   const float* y0 = P.blob + P.off_y0;
   const float* nmat = P.blob + P.off_nmat;
-  const long long warp_id = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  // chunk c of MPW samples goes to CTA c % gridDim, warp c / gridDim: a short work list spreads over all SMs
+  // instead of filling the first CTAs (the per-SM shared-memory pipe is what the contraction saturates)
+  const long long warp_id = static_cast<long long>(warp) * gridDim.x + blockIdx.x;
   const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
   bool staged = !F_SMEM;
 
@@ -582,7 +571,9 @@ __global__ void __launch_bounds__(kLmiThreads, 1)
   S.scr = scratch_base + (warp * C::MPW + grp) * C::SCR;
   const int n = P.n, k = P.k;
   const float* nmat = P.blob + P.off_nmat;
-  const long long warp_id = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  // chunk c of MPW samples goes to CTA c % gridDim, warp c / gridDim: a short work list spreads over all SMs
+  // instead of filling the first CTAs (the per-SM shared-memory pipe is what the contraction saturates)
+  const long long warp_id = static_cast<long long>(warp) * gridDim.x + blockIdx.x;
   const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
 
   const long long total = work_list ? static_cast<long long>(*work_count) : B;
