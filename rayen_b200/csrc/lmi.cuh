@@ -445,7 +445,7 @@ __host__ __device__ constexpr size_t lmi_smem_bytes(int n, int threads) {
 
 template <int RP, bool F_SMEM>
 __device__ __forceinline__ const float* lmi_stage(const PlanDev& P, unsigned char* smem_raw, uint64_t* bars,
-                                                  float** scratch_base) {
+                                                  float** scratch_base, bool has_work) {
   const float* F;
   if constexpr (F_SMEM) {
     float* fs = reinterpret_cast<float*>(smem_raw + 64);
@@ -454,7 +454,7 @@ __device__ __forceinline__ const float* lmi_stage(const PlanDev& P, unsigned cha
       fence_mbar_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0) stage_bulk(fs, P.blob + P.off_lmi, P.lmi_words, &bars[0]);
+    if (threadIdx.x == 0 && has_work) stage_bulk(fs, P.blob + P.off_lmi, P.lmi_words, &bars[0]);
     F = fs;
     *scratch_base = fs + P.lmi_words;
   } else {
@@ -475,7 +475,11 @@ __global__ void __launch_bounds__(THREADS, 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float* scratch_base;
-  const float* F = lmi_stage<RP, F_SMEM>(P, smem_raw, bars, &scratch_base);
+  // dense mode: every sample; list mode: only the samples the LQS kernel could not prune
+  const long long total = work_list ? static_cast<long long>(*work_count) : B;
+  // chunk c (MPW samples) belongs to CTA c % gridDim: a CTA without a chunk does not stage F~z at all
+  const bool cta_has_work = static_cast<long long>(blockIdx.x) * C::MPW < total;
+  const float* F = lmi_stage<RP, F_SMEM>(P, smem_raw, bars, &scratch_base, cta_has_work);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   LmiSolver<RP, false, F_SMEM> S;
@@ -492,8 +496,6 @@ __global__ void __launch_bounds__(THREADS, 1)
   const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
   bool staged = !F_SMEM;
 
-  // dense mode: every sample; list mode: only the samples the LQS kernel could not prune
-  const long long total = work_list ? static_cast<long long>(*work_count) : B;
   for (long long base = warp_id * C::MPW; base < total; base += n_warps * C::MPW) {
     const long long idx = base + grp;
     const bool valid = idx < total;
@@ -543,7 +545,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     __syncwarp();  // the scratch (u) is rewritten by the next sample
   }
   if constexpr (F_SMEM) {
-    if (!staged) mbar_wait(&bars[0], 0);
+    if (!staged && cta_has_work) mbar_wait(&bars[0], 0);  // never exit with a bulk copy in flight
   }
 }
 
@@ -551,17 +553,21 @@ __global__ void __launch_bounds__(THREADS, 1)
 // Only the samples whose binding constraint is the LMI and whose gradient needs d kappa/du are
 // processed; everything else was written by lqs_backward_kernel, which also queued those samples in
 // the work list (dense mode without a list: every group checks its own sample).
-template <int RP>
+template <int RP, bool F_SMEM>
 __global__ void __launch_bounds__(kLmiThreads, 1)
     lmi_backward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, const float* __restrict__ gy,
                         const float* __restrict__ kappa, const int* __restrict__ active, float* __restrict__ gv,
                         long long ldgv, long long B, int mode, const int* __restrict__ work_list,
                         const int* __restrict__ work_count) {
   using C = LmiCfg<RP>;
-  constexpr bool F_SMEM = false;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* scratch_base = reinterpret_cast<float*>(smem_raw + 64);
-  const float* F = P.blob + P.off_lmi;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* scratch_base;
+  const long long total = work_list ? static_cast<long long>(*work_count) : B;
+  // only the CTAs that own a chunk of the (usually short) work list stage F~z
+  const bool cta_has_work = static_cast<long long>(blockIdx.x) * C::MPW < total;
+  const float* F = lmi_stage<RP, F_SMEM>(P, smem_raw, bars, &scratch_base, cta_has_work);
+  bool staged = !F_SMEM;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   LmiSolver<RP, true, F_SMEM> S;
@@ -576,7 +582,6 @@ __global__ void __launch_bounds__(kLmiThreads, 1)
   const long long warp_id = static_cast<long long>(warp) * gridDim.x + blockIdx.x;
   const long long n_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
 
-  const long long total = work_list ? static_cast<long long>(*work_count) : B;
   for (long long base = warp_id * C::MPW; base < total; base += n_warps * C::MPW) {
     const long long idx = base + grp;
     const long long b = (idx < total) ? (work_list ? static_cast<long long>(work_list[idx]) : idx) : 0;
@@ -589,6 +594,10 @@ __global__ void __launch_bounds__(kLmiThreads, 1)
     const float s = S.load_direction(v + b * ldv, n, mine);
     if (mine && mode == RAYEN_MODE_RAYEN) mine = (1.0f / kap < s);
     if (__ballot_sync(0xffffffffu, mine) == 0u) continue;  // warp-uniform
+    if (!staged) {
+      mbar_wait(&bars[0], 0);
+      staged = true;
+    }
     // groups that are not `mine` run on u = 0 (a zero matrix) and write nothing
     if (!mine) {
       for (int a = S.q; a < kLmiMaxN; a += C::LPM) S.su()[a] = 0.f;
@@ -650,6 +659,9 @@ __global__ void __launch_bounds__(kLmiThreads, 1)
       if (mode == RAYEN_MODE_RAYEN_OLD && S.q == 0) gv[b * ldgv + n] = gbeta;
     }
     __syncwarp();
+  }
+  if constexpr (F_SMEM) {
+    if (!staged && cta_has_work) mbar_wait(&bars[0], 0);
   }
 }
 

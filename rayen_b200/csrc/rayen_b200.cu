@@ -107,14 +107,12 @@ static LmiFwdFn lmi_fwd_fn_t(int rp, bool smem) {
 static LmiFwdFn lmi_fwd_fn(int rp, bool smem, int threads) {
   return threads == 384 ? lmi_fwd_fn_t<384>(rp, smem) : lmi_fwd_fn_t<256>(rp, smem);
 }
-// the backward LMI kernel reads F~z through L1/L2: only the few samples whose binding constraint is the
-// LMI need it, so staging 128 KB per CTA would cost more than it saves
-static LmiBwdFn lmi_bwd_fn(int rp) {
+static LmiBwdFn lmi_bwd_fn(int rp, bool smem) {
   switch (rp) {
-    case 4: return lmi_backward_kernel<4>;
-    case 8: return lmi_backward_kernel<8>;
-    case 16: return lmi_backward_kernel<16>;
-    default: return lmi_backward_kernel<32>;
+    case 4: return smem ? lmi_backward_kernel<4, true> : lmi_backward_kernel<4, false>;
+    case 8: return smem ? lmi_backward_kernel<8, true> : lmi_backward_kernel<8, false>;
+    case 16: return smem ? lmi_backward_kernel<16, true> : lmi_backward_kernel<16, false>;
+    default: return smem ? lmi_backward_kernel<32, true> : lmi_backward_kernel<32, false>;
   }
 }
 static size_t lmi_smem(int rp, bool smem, int n, int threads) {
@@ -239,8 +237,8 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
     p->lmi_smem = p->lmi_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
     if (!p->lmi_smem) p->lmi_smem_bytes = lmi_smem(v.lmi_rp, false, v.n, p->lmi_fwd_threads);
     rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_fn(v.lmi_rp, p->lmi_smem, p->lmi_fwd_threads)), p->lmi_smem_bytes);
-    p->lmi_bwd_smem_bytes = lmi_smem(v.lmi_rp, false, v.n, kLmiThreads);
-    if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_bwd_fn(v.lmi_rp)), p->lmi_bwd_smem_bytes);
+    p->lmi_bwd_smem_bytes = lmi_smem(v.lmi_rp, p->lmi_smem, v.n, kLmiThreads);
+    if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_bwd_fn(v.lmi_rp, p->lmi_smem)), p->lmi_bwd_smem_bytes);
   }
   cudaSetDevice(prev);
   if (rc != 0) {
@@ -297,7 +295,7 @@ extern "C" int rayen_plan_kernel_info(const rayen_plan_t* p, RayenKernelInfo* ou
   if (p->dev.lmi_r > 0) {
     RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_fwd_fn(p->dev.lmi_rp, p->lmi_smem, p->lmi_fwd_threads))));
     out->regs_lmi_fwd = a.numRegs;
-    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_bwd_fn(p->dev.lmi_rp))));
+    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_bwd_fn(p->dev.lmi_rp, p->lmi_smem))));
     out->regs_lmi_bwd = a.numRegs;
   }
   out->smem_lqs_bytes = static_cast<int>(p->lqs_smem_bytes);
@@ -495,7 +493,7 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
     const int mpw = 32 / (d.lmi_rp / 4);
     long long blocks = (B + static_cast<long long>(mpw) * (kLmiThreads / 32) - 1) / (static_cast<long long>(mpw) * (kLmiThreads / 32));
     if (blocks > p->sm_count) blocks = p->sm_count;
-    LmiBwdFn lf = lmi_bwd_fn(d.lmi_rp);
+    LmiBwdFn lf = lmi_bwd_fn(d.lmi_rp, p->lmi_smem);
     lf<<<static_cast<int>(blocks), kLmiThreads, p->lmi_bwd_smem_bytes, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv,
                                                                                 B, mode, bwd_list, counters + 1);
     g_launches.fetch_add(1);
