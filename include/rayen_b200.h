@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RAYEN_ABI_VERSION 4
+#define RAYEN_ABI_VERSION 5
 
 /* error codes (negative); positive return values are cudaError_t */
 #define RAYEN_OK 0
@@ -64,6 +64,11 @@ extern "C" {
  *           lambda_max(S~(u)) <= t.u/r + sqrt((r-1)/r) sqrt(|T u|^2 - (t.u)^2/r) that prunes the eigen-solve
  *   LMI     F~z_a = sum_i N[i][a] * (-L' F_i L), a < n, each rp x rp (rp = r rounded up to 4, 8, 16
  *           or 32, zero padded), stored [a][row i][lane q][slot t] with column j = q + (rp/4)*t
+ *   TC      the LIN/QUAD/SOC/BOUND constants again as the B operand of a tcgen05 GEMM (lqs_tc.cuh): a table
+ *           of tc_panels x 24 words {kind, first row, 6 x (item type, item index), pad, 8 item scalars}, then
+ *           per panel W_hi and W_lo (96 x tc_kp each, TF32 split) in the K-major no-swizzle operand layout
+ *           [k/4][row/8][row%8][k%4].  A linear panel holds 96 rows of D; an item panel holds 96/(ch+kp)
+ *           items of ch header rows (phi | c_z, h | t) followed by the kp rows of the triangular factor.
  */
 typedef struct RayenPlanDesc {
   int32_t abi_version; /* must be RAYEN_ABI_VERSION */
@@ -82,7 +87,9 @@ typedef struct RayenPlanDesc {
   int32_t quad_stride;
   int32_t soc_stride;
   int32_t lmi_prune; /* 1: the BOUND section is valid and pruning may be used */
-  int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi;
+  int32_t tc_panels; /* number of 96-row panels of the tensor-core section */
+  int32_t tc_kp;     /* K of the tensor-core GEMM: max(8, np) */
+  int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi, off_tc;
   int64_t blob_words;
   const float* blob; /* host pointer, blob_words floats */
 } RayenPlanDesc;
@@ -104,6 +111,8 @@ int rayen_plan_set_tuning(rayen_plan_t* plan, int samples_per_thread, int lanes_
  * Wolkowicz-Styan bound does not already prove kappa_LMI < kappa of the other families.  Results are
  * identical either way (the bound is a proof, not an approximation). */
 int rayen_plan_set_pruning(rayen_plan_t* plan, int enabled);
+/* Linear/quadratic/SOC forward on the tensor cores (tcgen05 3xTF32 GEMM, default) or on the FP32 pipe (0). */
+int rayen_plan_set_tensor_cores(rayen_plan_t* plan, int enabled);
 
 /* Device scratch the forward / backward calls need for a batch of B samples (work lists of the samples
  * that still need the LMI kernels).  0 for plans without an LMI.  The caller owns the buffer; it must

@@ -11,12 +11,12 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "librayen_b200.so")
-SOURCES = ["rayen_b200.cu", "lqs.cuh", "lmi.cuh", "common.cuh"]
+SOURCES = ["rayen_b200.cu", "lqs.cuh", "lqs_tc.cuh", "lmi.cuh", "common.cuh"]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "rayen_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MODE_RAYEN, MODE_RAYEN_OLD = 0, 1
 FAM_NONE, FAM_LINEAR, FAM_QUAD, FAM_SOC, FAM_LMI = 0, 1, 2, 3, 4
 
@@ -24,9 +24,9 @@ FAM_NONE, FAM_LINEAR, FAM_QUAD, FAM_SOC, FAM_LMI = 0, 1, 2, 3, 4
 class RayenPlanDesc(ctypes.Structure):
     _fields_ = [(name, ctypes.c_int32) for name in (
         "abi_version", "n", "k", "np", "k_pad", "m", "m_pad", "n_quad", "n_soc", "lmi_r", "lmi_rp",
-        "n_is_identity", "lin_chunk_stride", "quad_stride", "soc_stride", "lmi_prune")] + [
+        "n_is_identity", "lin_chunk_stride", "quad_stride", "soc_stride", "lmi_prune", "tc_panels", "tc_kp")] + [
         (name, ctypes.c_int64) for name in (
-            "off_lin", "off_quad", "off_soc", "off_nmat", "off_y0", "off_bound", "off_lmi", "blob_words")] + [
+            "off_lin", "off_quad", "off_soc", "off_nmat", "off_y0", "off_bound", "off_lmi", "off_tc", "blob_words")] + [
         ("blob", ctypes.POINTER(ctypes.c_float))]
 
 
@@ -45,6 +45,7 @@ SYMBOLS = {
     "rayen_plan_destroy": (None, [_P]),
     "rayen_plan_set_tuning": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int]),
     "rayen_plan_set_pruning": (ctypes.c_int, [_P, ctypes.c_int]),
+    "rayen_plan_set_tensor_cores": (ctypes.c_int, [_P, ctypes.c_int]),
     "rayen_workspace_bytes": (ctypes.c_int64, [_P, ctypes.c_int64]),
     "rayen_forward_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, ctypes.c_int64, ctypes.c_int, _P, _P]),
     "rayen_backward_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_int64,
@@ -136,6 +137,9 @@ class DevicePlan:
 
     def set_pruning(self, enabled=True):
         check(lib().rayen_plan_set_pruning(self._handle, 1 if enabled else 0), "rayen_plan_set_pruning")
+
+    def set_tensor_cores(self, enabled=True):
+        check(lib().rayen_plan_set_tensor_cores(self._handle, 1 if enabled else 0), "rayen_plan_set_tensor_cores")
 
     def workspace_bytes(self, batch):
         return int(lib().rayen_workspace_bytes(self._handle, int(batch)))

@@ -219,6 +219,11 @@ class ConstraintModule(nn.Module):
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._device_plan(device).set_pruning(enabled)
 
+    def set_tensor_cores(self, enabled=True, device=None):
+        """Linear/quadratic/SOC forward on tcgen05 tensor cores (default) or on the FP32 pipe."""
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._device_plan(device).set_tensor_cores(enabled)
+
     def last_kappa_and_active(self):
         """(kappa[B], active[B]) of the most recent forward: active = family << 24 | constraint index."""
         return self._last

@@ -17,6 +17,7 @@ struct PlanDev {
   int off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi;
   int lqs_words;   // words [off_lin, off_lin + lqs_words) = LIN | QUAD | SOC | NMAT | Y0 | BOUND, staged to smem
   int lmi_words;   // n * rp * rp
+  int off_tc, tc_panels, tc_kp;  // tensor-core section (see rayen_b200.h)
 };
 
 constexpr int kFamShift = 24;

@@ -1,0 +1,353 @@
+// Linear / quadratic / SOC kappa on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Every constraint of these families is a set of dot products with the unit direction u: a row of D, the
+// vectors phi / c_z / h, the rows of the triangular factors G and R (and of the pruning bound's factor).
+// Stacked, they are ONE matrix W [rows x K] (K = n padded to 8/16/32), and the work of a tile of 128 samples
+// is the GEMM  D = U W'  with U [128 x K].  This kernel runs that GEMM with tcgen05.mma (kind::tf32,
+// M = 128, N = 96, K = 8 per instruction), error-compensated as 3xTF32
+//     U W' ~= U_hi W_hi' + U_lo W_hi' + U_hi W_lo'        (drops only the 2^-22 term U_lo W_lo')
+// with the accumulator in tensor memory.  The TMEM layout -- lane = sample, column = constraint row -- is
+// exactly what the reduction needs: each epilogue thread owns one sample, reads its row of D with
+// tcgen05.ld and takes the running max / sums of squares in registers, with no cross-lane traffic at all.
+//
+// Roles (warp-specialised, one CTA per SM, persistent over super-tiles of 2 x 128 samples):
+//   warps 0-7  load v, normalise, write U_hi/U_lo as K-major operand tiles; later read D from TMEM and reduce;
+//              finally apply the scale step and write y / kappa / active (and the LMI work list)
+//   warp 8     TMA producer: streams the 96-row panels of W (hi + lo) through a 3-stage shared-memory ring
+//   warp 9     MMA issuer (one elected lane) and owner of the TMEM allocation
+// Pipelines: W ring full/empty, TMEM accumulator full/empty (two 96-column buffers per sample tile), U ready.
+#pragma once
+#include "common.cuh"
+#include "lqs.cuh"
+
+namespace rayen {
+
+constexpr int kTcPanel = 96;
+constexpr int kTcStages = 3;
+constexpr int kTcEpiWarps = 8;
+constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
+constexpr int kTcTableWords = 24;
+
+// ----------------------------------------------------------------------------- tcgen05 / mbarrier helpers
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 bytes; LBO = byte stride between the two 16-byte K chunks of
+  // one MMA, SBO = byte stride between 8-row groups; bits [46,48) = descriptor version 1 (sm_100)
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+  // c = F32 (bits 4-5), a = b = TF32 (bits 7-9, 10-12), both K-major, n >> 3 at bit 17, m >> 4 at bit 24
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <int KP>
+__host__ __device__ constexpr size_t lqs_tc_smem_bytes(int n_panels) {
+  return 256 + static_cast<size_t>((n_panels * kTcTableWords + 3) / 4 * 4) * 4 + 4 * static_cast<size_t>(KP) * 128 * 4 +
+         static_cast<size_t>(kTcStages) * 2 * KP * kTcPanel * 4;
+}
+
+// ----------------------------------------------------------------------------- the kernel
+template <int KP>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    lqs_tc_forward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, float* __restrict__ y,
+                          float* __restrict__ kappa_out, int* __restrict__ active_out, long long B, int mode,
+                          int lmi_follows, int prune, int* __restrict__ work_list, int* __restrict__ work_count) {
+  constexpr int CH = (KP >= 16) ? 16 : 8;   // header rows of an item (phi | c_z, h | t), padded
+  constexpr int IW = CH + KP;               // rows (= TMEM columns) per item
+  constexpr int IPP = kTcPanel / IW;        // items per panel
+  constexpr int KC = KP / 4;                // 16-byte chunks along K
+  constexpr int A_TILE = KP * 128;          // floats of one U operand tile (hi or lo)
+  constexpr int W_TILE = KP * kTcPanel;     // floats of one W operand tile (hi or lo)
+  constexpr uint32_t LBO_A = (128 / 8) * 128, LBO_W = (kTcPanel / 8) * 128, SBO = 128;
+  constexpr uint32_t IDESC = umma_idesc_tf32(128, kTcPanel);
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* a_full = &bars[0];
+  uint64_t* w_full = &bars[1];                 // [kTcStages]
+  uint64_t* w_empty = &bars[1 + kTcStages];    // [kTcStages]
+  uint64_t* d_full = &bars[1 + 2 * kTcStages];  // [2]
+  uint64_t* d_empty = &bars[3 + 2 * kTcStages]; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[5 + 2 * kTcStages]);
+  float* table = reinterpret_cast<float*>(smem_raw + 256);
+  const int n_panels = P.tc_panels;
+  float* a_tiles = table + (n_panels * kTcTableWords + 3) / 4 * 4;  // [tile 0/1][hi, lo][A_TILE]
+  float* w_ring = a_tiles + 4 * A_TILE;                              // [stage][hi, lo][W_TILE]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* tc_base = P.blob + P.off_tc;
+  const float* w_src = tc_base + n_panels * kTcTableWords;
+
+  if (tid == 0) {
+    mbar_init(a_full, kTcEpiWarps);
+    for (int i = 0; i < kTcStages; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d_full[i], 1);
+      mbar_init(&d_empty[i], kTcEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  for (int i = tid; i < n_panels * kTcTableWords; i += kTcThreads) table[i] = tc_base[i];
+  if (warp == kTcEpiWarps + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long n_super = (B + 255) / 256;
+  const int n = P.n, k = P.k;
+
+  if (warp == kTcEpiWarps) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t g = 0;  // running panel counter: ring stage g % stages, use g / stages
+      for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
+        for (int p = 0; p < n_panels; ++p, ++g) {
+          const uint32_t stage = g % kTcStages, use = g / kTcStages;
+          mbar_wait(&w_empty[stage], (use & 1) ^ 1);
+          mbar_expect_tx(&w_full[stage], 2 * W_TILE * 4);
+          bulk_g2s(w_ring + stage * 2 * W_TILE, w_src + static_cast<size_t>(p) * 2 * W_TILE, 2 * W_TILE * 4, &w_full[stage]);
+        }
+      }
+    }
+  } else if (warp == kTcEpiWarps + 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t g = 0, s_local = 0;
+      for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++s_local) {
+        mbar_wait(a_full, s_local & 1);
+        tc_fence_after();
+        for (int p = 0; p < n_panels; ++p, ++g) {
+          const uint32_t stage = g % kTcStages, use = g / kTcStages;
+          const uint32_t buf = g & 1, buf_use = g >> 1;
+          mbar_wait(&w_full[stage], use & 1);
+          mbar_wait(&d_empty[buf], (buf_use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t w_hi = smem_u32(w_ring + stage * 2 * W_TILE), w_lo = w_hi + W_TILE * 4;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t u_hi = smem_u32(a_tiles + (2 * t) * A_TILE), u_lo = u_hi + A_TILE * 4;
+            const uint32_t d_tmem = tmem_base + (2 * t + buf) * kTcPanel;
+#pragma unroll
+            for (int ks = 0; ks < KP / 8; ++ks) {
+              const uint64_t d_uhi = umma_smem_desc(u_hi + 2 * ks * LBO_A, LBO_A, SBO);
+              const uint64_t d_ulo = umma_smem_desc(u_lo + 2 * ks * LBO_A, LBO_A, SBO);
+              const uint64_t d_whi = umma_smem_desc(w_hi + 2 * ks * LBO_W, LBO_W, SBO);
+              const uint64_t d_wlo = umma_smem_desc(w_lo + 2 * ks * LBO_W, LBO_W, SBO);
+              umma_tf32(d_tmem, d_uhi, d_whi, IDESC, ks > 0 ? 1u : 0u);
+              umma_tf32(d_tmem, d_ulo, d_whi, IDESC, 1u);
+              umma_tf32(d_tmem, d_uhi, d_wlo, IDESC, 1u);
+            }
+          }
+          umma_commit(&w_empty[stage]);  // the ring slot is free once these MMAs have read it
+          umma_commit(&d_full[buf]);     // ... and the accumulator is complete
+        }
+      }
+    }
+  } else {
+    // ===================================================================== operand prep + reduction + scale step
+    const int t = warp >> 2, quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const bool vec_in = ((n & 3) == 0) && ((ldv & 3) == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
+    const bool vec_out = ((k & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    const float* y0 = P.blob + P.off_y0;
+    const float* nmat = P.blob + P.off_nmat;
+    uint32_t g = 0;
+    for (long long st = blockIdx.x; st < n_super; st += gridDim.x) {
+      const long long b = st * 256 + t * 128 + row;
+      const bool valid = b < B;
+      float u[KP];
+      load_row<KP>(v + b * ldv, n, vec_in, valid, u);
+      const float beta = (mode == RAYEN_MODE_RAYEN_OLD && valid) ? __ldg(v + b * ldv + n) : 0.f;
+      const float s = normalize_row<KP>(u);
+      {
+        float* hi = a_tiles + (2 * t) * A_TILE + ((row >> 3) * 32 + (row & 7) * 4);
+        float* lo = hi + A_TILE;
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc) {
+          float4 h4, l4;
+          h4.x = tf32_rna(u[4 * kc + 0]); l4.x = tf32_rna(u[4 * kc + 0] - h4.x);
+          h4.y = tf32_rna(u[4 * kc + 1]); l4.y = tf32_rna(u[4 * kc + 1] - h4.y);
+          h4.z = tf32_rna(u[4 * kc + 2]); l4.z = tf32_rna(u[4 * kc + 2] - h4.z);
+          h4.w = tf32_rna(u[4 * kc + 3]); l4.w = tf32_rna(u[4 * kc + 3] - h4.w);
+          *reinterpret_cast<float4*>(hi + kc * 16 * 32) = h4;
+          *reinterpret_cast<float4*>(lo + kc * 16 * 32) = l4;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full);
+
+      float best = 0.f;
+      int tag = make_tag(RAYEN_FAM_NONE, 0);
+      float ub = 3.0e38f;  // pruning bound of the LMI (stays +inf without one)
+      for (int p = 0; p < n_panels; ++p, ++g) {
+        const uint32_t buf = g & 1, buf_use = g >> 1;
+        mbar_wait(&d_full[buf], buf_use & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (2 * t + buf) * kTcPanel;
+        const int* pt = reinterpret_cast<const int*>(table + p * kTcTableWords);
+        if (pt[0] == 0) {
+          // ---- 96 rows of D: kappa_j = D_j . u                   (reference constraint_module.py:353)
+          const int base = pt[1];
+#pragma unroll
+          for (int c = 0; c < kTcPanel / 32; ++c) {
+            float x[32];
+            tmem_ld16(taddr + 32 * c, x);
+            tmem_ld16(taddr + 32 * c + 16, x + 16);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (x[j] > best) {
+                best = x[j];
+                tag = make_tag(RAYEN_FAM_LINEAR, base + 32 * c + j);
+              }
+          }
+        } else {
+          // ---- items: header rows (phi | c_z, h | t) then the KP rows of a triangular factor
+#pragma unroll
+          for (int sl = 0; sl < IPP; ++sl) {
+            const int type = pt[2 + 2 * sl], idx = pt[3 + 2 * sl];
+            if (type == 0) continue;  // uniform across the CTA: no divergence around the collective loads
+            const float scal = table[p * kTcTableWords + 16 + sl];
+            float h[CH], x[KP];
+            if constexpr (CH == 16) {
+              tmem_ld16(taddr + sl * IW, h);
+#pragma unroll
+              for (int c = 0; c < KP / 16; ++c) tmem_ld16(taddr + sl * IW + CH + 16 * c, x + 16 * c);
+            } else {
+              tmem_ld8(taddr + sl * IW, h);
+              tmem_ld8(taddr + sl * IW + CH, x);
+            }
+            tmem_wait_ld();
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < KP; ++j) ss = fmaf(x[j], x[j], ss);
+            if (type == RAYEN_FAM_QUAD) {          // kappa = phi_z.u + |G u|       (reference :360-381)
+              const float kap = h[0] + sqrtf(ss);
+              if (kap > best) {
+                best = kap;
+                tag = make_tag(RAYEN_FAM_QUAD, idx);
+              }
+            } else if (type == RAYEN_FAM_SOC) {    // largest root                  (reference :383-399)
+              const float cq = fmaf(-h[0], h[0], ss);
+              const float kap = soc_root(scal, h[1], cq, nullptr);
+              if (kap > best) {
+                best = kap;
+                tag = make_tag(RAYEN_FAM_SOC, idx);
+              }
+            } else {                               // Wolkowicz-Styan bound of lambda_max (LMI pruning)
+              const float inv_r = 1.0f / scal;
+              const float mean = h[0] * inv_r;
+              const float dev2 = fmaxf(fmaf(-h[0], mean, ss), 0.f);
+              ub = mean + sqrtf((scal - 1.0f) * inv_r * dev2);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d_empty[buf]);
+      }
+
+      // ---- merge / prune / scale step for this thread's sample
+      if (!valid) continue;
+      const bool pruned = lmi_follows && prune && (fmaf(1e-4f, fabsf(ub), ub) + 1e-30f < best);
+      const bool finish = !lmi_follows || pruned;
+      if (kappa_out) kappa_out[b] = best;
+      if (active_out) active_out[b] = tag;
+      if (!finish) {
+        if (work_list) work_list[atomicAdd(work_count, 1)] = static_cast<int>(b);
+        continue;
+      }
+      float alpha;
+      if (mode == RAYEN_MODE_RAYEN_OLD)
+        alpha = 1.0f / (expf(beta) + best);
+      else
+        alpha = fminf(1.0f / best, s);
+      float* yrow = y + b * k;
+      if (P.n_is_identity) {
+#pragma unroll
+        for (int kk = 0; kk < KP / 4; ++kk) {
+          if (4 * kk < k) {
+            float4 o;
+            o.x = fmaf(alpha, u[4 * kk + 0], __ldg(y0 + 4 * kk + 0));
+            o.y = fmaf(alpha, u[4 * kk + 1], __ldg(y0 + 4 * kk + 1));
+            o.z = fmaf(alpha, u[4 * kk + 2], __ldg(y0 + 4 * kk + 2));
+            o.w = fmaf(alpha, u[4 * kk + 3], __ldg(y0 + 4 * kk + 3));
+            if (vec_out) {
+              *reinterpret_cast<float4*>(yrow + 4 * kk) = o;
+            } else {
+              if (4 * kk + 0 < k) yrow[4 * kk + 0] = o.x;
+              if (4 * kk + 1 < k) yrow[4 * kk + 1] = o.y;
+              if (4 * kk + 2 < k) yrow[4 * kk + 2] = o.z;
+              if (4 * kk + 3 < k) yrow[4 * kk + 3] = o.w;
+            }
+          }
+        }
+      } else {
+        for (int i = 0; i < k; ++i) {
+          const float* nrow = nmat + i * (P.np + 4);
+          float acc = 0.f;
+#pragma unroll
+          for (int a = 0; a < KP; ++a)
+            if (a < P.np) acc = fmaf(__ldg(nrow + a), u[a], acc);
+          yrow[i] = fmaf(alpha, acc, __ldg(y0 + i));
+        }
+      }
+    }
+  }
+
+  // ---- teardown: nobody may still be reading TMEM when it is released
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kTcEpiWarps + 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+}  // namespace rayen

@@ -11,6 +11,7 @@
 
 #include "lmi.cuh"
 #include "lqs.cuh"
+#include "lqs_tc.cuh"
 
 using namespace rayen;
 
@@ -28,6 +29,8 @@ struct rayen_plan {
   size_t lqs_smem_bytes, lmi_smem_bytes, lmi_bwd_smem_bytes;
   bool has_lqs;   // any non-zero linear row / quadratic / cone: otherwise the LQS forward kernel is skipped
   bool prune;     // LMI pruning enabled (needs has_lqs and a BOUND section)
+  bool use_tc;    // tensor-core (tcgen05) linear/quadratic/SOC forward kernel
+  size_t tc_smem_bytes;
 };
 
 static thread_local char g_err[512] = "";
@@ -85,6 +88,22 @@ static LqsFwdFn lqs_fwd_fn(int np, int tm, bool smem) {
     case 8: return lqs_fwd_pick_tm<8>(tm, smem);
     case 16: return lqs_fwd_pick_tm<16>(tm, smem);
     default: return lqs_fwd_pick_tm<32>(tm, smem);
+  }
+}
+typedef void (*LqsTcFn)(const PlanDev, const float*, long long, float*, float*, int*, long long, int, int, int, int*,
+                        int*);
+static LqsTcFn lqs_tc_fn(int kp) {
+  switch (kp) {
+    case 8: return lqs_tc_forward_kernel<8>;
+    case 16: return lqs_tc_forward_kernel<16>;
+    default: return lqs_tc_forward_kernel<32>;
+  }
+}
+static size_t lqs_tc_smem(int kp, int panels) {
+  switch (kp) {
+    case 8: return lqs_tc_smem_bytes<8>(panels);
+    case 16: return lqs_tc_smem_bytes<16>(panels);
+    default: return lqs_tc_smem_bytes<32>(panels);
   }
 }
 static LqsBwdFn lqs_bwd_fn(int np) {
@@ -171,6 +190,10 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   if (d->lmi_r > 0 && d->off_lmi + static_cast<int64_t>(d->n) * d->lmi_rp * d->lmi_rp > d->blob_words)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "LMI section does not fit the block");
   if (d->blob_words > (1ll << 30)) return fail(RAYEN_ERR_UNSUPPORTED, "constant block too large");
+  if (d->tc_panels < 1 || (d->tc_kp != 8 && d->tc_kp != 16 && d->tc_kp != 32) || d->tc_kp < d->np || d->off_tc % 4 ||
+      d->off_tc < d->off_lmi ||
+      d->off_tc + static_cast<int64_t>(d->tc_panels) * (24 + 2 * 96 * d->tc_kp) > d->blob_words)
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "tensor-core section does not fit the block");
 
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
@@ -214,6 +237,7 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   v.lmi_prune = (d->lmi_prune && d->lmi_r > 0) ? 1 : 0;
   v.lqs_words = static_cast<int>(d->off_lmi - d->off_lin);
   v.lmi_words = d->lmi_r > 0 ? d->n * d->lmi_rp * d->lmi_rp : 0;
+  v.off_tc = static_cast<int>(d->off_tc); v.tc_panels = d->tc_panels; v.tc_kp = d->tc_kp;
 
   p->has_lqs = d->n_quad > 0 || d->n_soc > 0;
   for (int64_t i = d->off_lin; i < d->off_quad && !p->has_lqs; ++i) p->has_lqs = d->blob[i] != 0.0f;
@@ -225,7 +249,17 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   p->lqs_smem_bytes = 64 + static_cast<size_t>(v.lqs_words) * 4;
   p->lqs_smem = p->lqs_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
   if (!p->lqs_smem) p->lqs_smem_bytes = 64;
+  p->tc_smem_bytes = lqs_tc_smem(v.tc_kp, v.tc_panels);
+  // measured on B200 (scripts/time_kernels.py): the GEMM formulation wins from K = 16 up; at K = 8 the FP32-pipe
+  // kernel is faster (the GEMM is too thin to pay for the TMEM round trip)
+  p->use_tc = p->tc_smem_bytes <= static_cast<size_t>(p->max_smem_optin) && v.np >= 16;
+  {
+    const char* env = getenv("RAYEN_LQS_TC");
+    if (env) p->use_tc = p->use_tc && atoi(env) != 0;
+  }
   int rc = 0;
+  if (p->tc_smem_bytes <= static_cast<size_t>(p->max_smem_optin))
+    rc = allow_smem(reinterpret_cast<const void*>(lqs_tc_fn(v.tc_kp)), p->tc_smem_bytes);
   for (int tm = 1; tm <= 4 && rc == 0; tm *= 2)
     rc = allow_smem(reinterpret_cast<const void*>(lqs_fwd_fn(v.np, tm, p->lqs_smem)), p->lqs_smem_bytes);
   if (rc == 0 && v.lmi_r > 0) {
@@ -267,6 +301,12 @@ extern "C" int rayen_plan_set_tuning(rayen_plan_t* p, int tm, int lanes) {
     return fail(RAYEN_ERR_BAD_ARGUMENT, "lanes_per_sample must be 0 or a power of two <= 32");
   p->tune_tm = tm;
   p->tune_lanes = lanes;
+  return RAYEN_OK;
+}
+
+extern "C" int rayen_plan_set_tensor_cores(rayen_plan_t* p, int enabled) {
+  if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "null plan");
+  p->use_tc = enabled && p->tc_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
   return RAYEN_OK;
 }
 
@@ -419,9 +459,19 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
   cudaError_t e = cudaSuccess;
   if ((stage_mask & 1) && run_lqs) {
     if (use_list) e = cudaMemsetAsync(counters, 0, sizeof(int), stream);
-    const LqsGeom g = lqs_geometry(p, B);
-    LqsFwdFn f = lqs_fwd_fn(d.np, g.tm, p->lqs_smem);
-    if (e == cudaSuccess) {
+    if (e == cudaSuccess && p->use_tc) {
+      long long grid = (B + 255) / 256;
+      if (grid > p->sm_count) grid = p->sm_count;
+      LqsTcFn f = lqs_tc_fn(d.tc_kp);
+      f<<<static_cast<int>(grid), kTcThreads, p->tc_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode,
+                                                                           has_lmi ? 1 : 0, use_list ? 1 : 0,
+                                                                           use_list ? fwd_list : nullptr,
+                                                                           use_list ? counters : nullptr);
+      g_launches.fetch_add(1);
+      e = cudaGetLastError();
+    } else if (e == cudaSuccess) {
+      const LqsGeom g = lqs_geometry(p, B);
+      LqsFwdFn f = lqs_fwd_fn(d.np, g.tm, p->lqs_smem);
       f<<<g.grid, g.block, p->lqs_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode, g.lanes, has_lmi ? 1 : 0,
                                                         use_list ? 1 : 0, use_list ? fwd_list : nullptr,
                                                         use_list ? counters : nullptr);

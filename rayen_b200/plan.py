@@ -19,7 +19,7 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_NP = 32
 MAX_LMI = 32
 
@@ -69,6 +69,28 @@ def packed_triangular_words(np_):
     return sum(np_ - (i // 4) * 4 for i in range(np_))
 
 
+TC_PANEL = 96   # rows of W per tensor-core panel (MMA N)
+
+
+def split_tf32(x):
+    """x (float32) = hi + lo with both parts representable in TF32 (10-bit mantissa), round-to-nearest-away
+    like ``cvt.rna.tf32.f32``; the residual x - hi - lo is below 2^-22 |x|."""
+    def rna(a):
+        bits = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+        return ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    hi = rna(x)
+    lo = rna(x - hi)
+    return hi, lo
+
+
+def operand_layout(tile):
+    """[rows, K] float32 -> the K-major, no-swizzle shared-memory layout of a tcgen05 operand:
+    [k/4][row/8][row%8][k%4] (8x16-byte core matrices; LBO = rows*16 bytes, SBO = 128 bytes)."""
+    rows, kdim = tile.shape
+    return np.ascontiguousarray(tile.reshape(rows // 8, 8, kdim // 4, 4).transpose(2, 0, 1, 3)).reshape(-1)
+
+
 class PackedPlan:
     """Float32 blob + the integers of ``RayenPlanDesc``; also keeps the float64 pieces for tests."""
 
@@ -106,6 +128,14 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None):
     plan = PackedPlan()
     sections = []
     cursor = 0
+
+    exact = []   # (offset, float32 array) payloads that must reach the blob bit for bit (int tables, TF32 splits)
+
+    def add_f32(arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1)
+        off = add(np.zeros(arr.size))
+        exact.append((off, arr))
+        return off
 
     def add(arr):
         nonlocal cursor
@@ -223,14 +253,74 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None):
     off_bound = add(bound)
     off_lmi = add(Fperm) if lmi is not None else add(np.zeros(4))
 
+    # ---- tensor-core layout of the same linear/quadratic/SOC/bound constants (lqs_tc.cuh): every constraint
+    # becomes rows of one [rows x K] matrix W, so that all dot products of a 128-sample tile are ONE tcgen05
+    # GEMM D = U W' with the result in tensor memory.  Rows are grouped in panels of 96; operands are split
+    # W = W_hi + W_lo (both TF32-representable) for the error-compensated 3xTF32 product.
+    kp = max(8, np_)
+    ch = 16 if kp >= 16 else 8
+    iw = ch + kp
+    ipp = TC_PANEL // iw
+    Wrows, table = [], []
+
+    def tri_dense(T):          # [np_, np_] upper triangular -> [kp, kp]
+        out = np.zeros((kp, kp))
+        out[:np_, :np_] = T
+        return out
+
+    Dk = np.zeros((m_pad, kp))
+    Dk[:m, :n] = D
+    for base in range(0, m_pad, TC_PANEL):
+        blk = np.zeros((TC_PANEL, kp))
+        rows = Dk[base:base + TC_PANEL]
+        blk[:rows.shape[0]] = rows
+        Wrows.append(blk)
+        table.append(([0, base] + [0] * 12, [0.0] * 8))
+    items = []
+    for i, (phi_z, Delta_z, G) in enumerate(quad_f64):
+        hdr = np.zeros((ch, kp))
+        hdr[0, :n] = phi_z
+        items.append((2, i, 0.0, np.concatenate((hdr, tri_dense(G)))))
+    for j, (cz, h, Mz, A, R) in enumerate(soc_f64):
+        hdr = np.zeros((ch, kp))
+        hdr[0, :n] = cz
+        hdr[1, :n] = h
+        items.append((3, j, A, np.concatenate((hdr, tri_dense(R)))))
+    if lmi is not None:
+        hdr = np.zeros((ch, kp))
+        hdr[0, :n] = np.trace(Fz, axis1=1, axis2=2)
+        items.append((5, 0, float(lmi_r), np.concatenate((hdr, tri_dense(_triangular_factor(gram, np_))))))
+    for base in range(0, len(items), ipp):
+        blk = np.zeros((TC_PANEL, kp))
+        ints, flts = [1, 0] + [0] * 12, [0.0] * 8
+        for s_, (typ, idx, scal, rows) in enumerate(items[base:base + ipp]):
+            blk[s_ * iw:(s_ + 1) * iw] = rows
+            ints[2 + 2 * s_], ints[3 + 2 * s_] = typ, idx
+            flts[s_] = scal
+        Wrows.append(blk)
+        table.append((ints, flts))
+    tc_panels = len(Wrows)
+    tab = np.zeros((tc_panels, 24), dtype=np.float32)
+    for pi, (ints, flts) in enumerate(table):
+        tab[pi, :14] = np.asarray(ints, dtype=np.int32).view(np.float32)
+        tab[pi, 16:24] = np.asarray(flts, dtype=np.float32)
+    off_tc = add_f32(tab)
+    for blk in Wrows:
+        hi, lo = split_tf32(blk.astype(np.float32))
+        add_f32(operand_layout(hi))
+        add_f32(operand_layout(lo))
+
     blob = np.concatenate(sections).astype(np.float32)
     assert blob.size == cursor and cursor % 4 == 0
+    for off, arr in exact:
+        blob[off:off + arr.size] = arr
     plan.blob = np.ascontiguousarray(blob)
     plan.fields = dict(n=n, k=k, np=np_, k_pad=k_pad, m=m, m_pad=m_pad, n_quad=len(qcs), n_soc=len(socs),
                        lmi_r=lmi_r, lmi_rp=lmi_rp, n_is_identity=n_is_identity,
                        lin_chunk_stride=lin_stride, quad_stride=quad_stride, soc_stride=soc_stride,
                        off_lin=off_lin, off_quad=off_quad, off_soc=off_soc, off_nmat=off_nmat,
-                       off_y0=off_y0, off_bound=off_bound, off_lmi=off_lmi, lmi_prune=int(lmi is not None))
+                       off_y0=off_y0, off_bound=off_bound, off_lmi=off_lmi, lmi_prune=int(lmi is not None),
+                       off_tc=off_tc, tc_panels=tc_panels, tc_kp=kp)
     plan.f64 = dict(D=D, N=N, y0=y0, z0=z0, yp=yp, quads=quad_f64, socs=soc_f64, Fz=Fz)
     return plan
 
