@@ -235,36 +235,42 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (pt[0] == 0) {
           // ---- 96 rows of D: kappa_j = D_j . u                   (reference constraint_module.py:353)
           const int base = pt[1];
+          float x[kTcPanel];
 #pragma unroll
-          for (int c = 0; c < kTcPanel / 32; ++c) {
-            float x[32];
-            tmem_ld16(taddr + 32 * c, x);
-            tmem_ld16(taddr + 32 * c + 16, x + 16);
-            tmem_wait_ld();
+          for (int c = 0; c < kTcPanel / 16; ++c) tmem_ld16(taddr + 16 * c, x + 16 * c);
+          tmem_wait_ld();
+          // max first (3-input max tree), index only when the running best actually moves: the best of a
+          // sample changes O(log rows) times, so the per-column compare/select chain is almost never needed
+          float mx = x[0];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (x[j] > best) {
-                best = x[j];
-                tag = make_tag(RAYEN_FAM_LINEAR, base + 32 * c + j);
-              }
+          for (int j = 1; j + 1 < kTcPanel; j += 2) mx = fmaxf(mx, fmaxf(x[j], x[j + 1]));
+          mx = fmaxf(mx, x[kTcPanel - 1]);
+          if (mx > best) {
+            best = mx;
+            int arg = 0;
+#pragma unroll
+            for (int j = kTcPanel - 1; j >= 0; --j)
+              if (x[j] == mx) arg = j;  // first index on ties, like torch.max
+            tag = make_tag(RAYEN_FAM_LINEAR, base + arg);
           }
         } else {
           // ---- items: header rows (phi | c_z, h | t) then the KP rows of a triangular factor
+          float xi[IPP * IW];
+#pragma unroll
+          for (int c = 0; c < IPP * IW / CH; ++c) {
+            if constexpr (CH == 16)
+              tmem_ld16(taddr + CH * c, xi + CH * c);
+            else
+              tmem_ld8(taddr + CH * c, xi + CH * c);
+          }
+          tmem_wait_ld();
 #pragma unroll
           for (int sl = 0; sl < IPP; ++sl) {
             const int type = pt[2 + 2 * sl], idx = pt[3 + 2 * sl];
-            if (type == 0) continue;  // uniform across the CTA: no divergence around the collective loads
+            if (type == 0) continue;
             const float scal = table[p * kTcTableWords + 16 + sl];
-            float h[CH], x[KP];
-            if constexpr (CH == 16) {
-              tmem_ld16(taddr + sl * IW, h);
-#pragma unroll
-              for (int c = 0; c < KP / 16; ++c) tmem_ld16(taddr + sl * IW + CH + 16 * c, x + 16 * c);
-            } else {
-              tmem_ld8(taddr + sl * IW, h);
-              tmem_ld8(taddr + sl * IW + CH, x);
-            }
-            tmem_wait_ld();
+            const float* h = xi + sl * IW;
+            const float* x = h + CH;
             float ss = 0.f;
 #pragma unroll
             for (int j = 0; j < KP; ++j) ss = fmaf(x[j], x[j], ss);

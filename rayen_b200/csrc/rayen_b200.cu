@@ -255,7 +255,7 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   p->use_tc = p->tc_smem_bytes <= static_cast<size_t>(p->max_smem_optin) && v.np >= 16;
   {
     const char* env = getenv("RAYEN_LQS_TC");
-    if (env) p->use_tc = p->use_tc && atoi(env) != 0;
+    if (env) p->use_tc = atoi(env) != 0 && p->tc_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
   }
   int rc = 0;
   if (p->tc_smem_bytes <= static_cast<size_t>(p->max_smem_optin))

@@ -275,6 +275,7 @@ def test_non_contiguous_and_other_dtypes():
 def test_readme_model_trains():
     """The README usage (readme.md:76-81): Sequential(Linear, ReLU, Linear, ReLU, ConstraintModule) + backward."""
     from rayen import constraints, constraint_module
+    torch.manual_seed(0)
     cs = synthetic.build_constraints(synthetic.example_spec("readme"), module=constraints)
     model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3, 64), torch.nn.ReLU(), torch.nn.Linear(64, 64),
                                 torch.nn.ReLU(), constraint_module.ConstraintModule(cs, input_dim=64, create_map=True)).to(DEV)
