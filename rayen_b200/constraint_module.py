@@ -37,58 +37,96 @@ def _as_buffer(array_like):
 
 
 class _RayShoot(torch.autograd.Function):
-    """q:[B, n(+1)] -> y:[B, k] through the C ABI; backward is the closed form."""
+    """q:[B, n(+1)] -> y:[B, k] through the C ABI; backward is the closed form.
+
+    The Python around the two C calls is kept minimal (one scratch allocation per call, cached handles): at
+    the named batch sizes the kernels take 0.1-0.2 ms, so interpreter overhead is what a training loop sees.
+    """
 
     @staticmethod
     def forward(ctx, q, module):
         if not q.is_cuda:
             raise RuntimeError("rayen_b200.ConstraintModule runs on CUDA (sm_100a) only; move the model and its "
                                "inputs to a B200 device. There is no CPU path.")
-        lib = _cabi.lib()
         v = q.detach()
         if v.dtype != torch.float32:
             v = v.float()
         if v.stride(1) != 1 or v.stride(0) < v.shape[1]:
             v = v.contiguous()
         B, cols = v.shape
-        k, mode = module.k, module._mode
-        dev_plan = module._device_plan(v.device)
-        y = torch.empty((B, k), dtype=torch.float32, device=v.device)
-        kappa = torch.empty((B,), dtype=torch.float32, device=v.device)
-        active = torch.empty((B,), dtype=torch.int32, device=v.device)
-        ws = torch.empty((max(dev_plan.workspace_bytes(B), 16),), dtype=torch.uint8, device=v.device)
-        with torch.cuda.device(v.device):
-            stream = torch.cuda.current_stream(v.device).cuda_stream
-            rc = lib.rayen_forward_f32(dev_plan.handle, v.data_ptr(), v.stride(0) if B > 0 else cols, y.data_ptr(),
-                                       kappa.data_ptr(), active.data_ptr(), B, mode, ws.data_ptr(),
-                                       ctypes.c_void_p(stream))
-        _cabi.check(rc, "rayen_forward_f32")
-        ctx.module = module
-        ctx.in_dtype = q.dtype
-        ctx.save_for_backward(v, kappa, active)
-        module._last = (kappa, active)
+        device = v.device
+        st = module._launch_state(device)
+        k = module.k
+        ws_words = st.ws_words(B)
+        # one scratch tensor: kappa [B] | active [B] (int32 bits) | work lists; y is what autograd sees
+        aux = torch.empty((2 * B + ws_words,), dtype=torch.float32, device=device)
+        y = torch.empty((B, k), dtype=torch.float32, device=device)
+        base = aux.data_ptr()
+        switch = torch.cuda.current_device() != st.index
+        if switch:
+            prev = torch.cuda.current_device()
+            torch.cuda.set_device(st.index)
+        try:
+            rc = st.forward(st.handle, v.data_ptr(), v.stride(0) if B > 0 else cols, y.data_ptr(), base, base + 4 * B, B,
+                            module._mode, base + 8 * B, torch.cuda.current_stream(device).cuda_stream)
+        finally:
+            if switch:
+                torch.cuda.set_device(prev)
+        if rc != 0:
+            _cabi.check(rc, "rayen_forward_f32")
+        ctx.module, ctx.in_dtype, ctx.aux = module, q.dtype, aux
+        ctx.save_for_backward(v)
+        module._last_aux = (aux, B)
         return y if q.dtype == torch.float32 else y.to(q.dtype)
 
     @staticmethod
     def backward(ctx, gy):
-        lib = _cabi.lib()
-        v, kappa, active = ctx.saved_tensors
-        module = ctx.module
+        (v,) = ctx.saved_tensors
+        module, aux = ctx.module, ctx.aux
         gy = gy.detach()
         if gy.dtype != torch.float32:
             gy = gy.float()
-        gy = gy.contiguous()
+        if not gy.is_contiguous():
+            gy = gy.contiguous()
         B, cols = v.shape
-        gv = torch.empty((B, cols), dtype=torch.float32, device=v.device)
-        dev_plan = module._device_plan(v.device)
-        ws = torch.empty((max(dev_plan.workspace_bytes(B), 16),), dtype=torch.uint8, device=v.device)
-        with torch.cuda.device(v.device):
-            stream = torch.cuda.current_stream(v.device).cuda_stream
-            rc = lib.rayen_backward_f32(dev_plan.handle, v.data_ptr(), v.stride(0) if B > 0 else cols, gy.data_ptr(),
-                                        kappa.data_ptr(), active.data_ptr(), gv.data_ptr(), cols, B, module._mode,
-                                        ws.data_ptr(), ctypes.c_void_p(stream))
-        _cabi.check(rc, "rayen_backward_f32")
+        device = v.device
+        st = module._launch_state(device)
+        gv = torch.empty((B, cols), dtype=torch.float32, device=device)
+        base = aux.data_ptr()
+        switch = torch.cuda.current_device() != st.index
+        if switch:
+            prev = torch.cuda.current_device()
+            torch.cuda.set_device(st.index)
+        try:
+            rc = st.backward(st.handle, v.data_ptr(), v.stride(0) if B > 0 else cols, gy.data_ptr(), base, base + 4 * B,
+                             gv.data_ptr(), cols, B, module._mode, base + 8 * B,
+                             torch.cuda.current_stream(device).cuda_stream)
+        finally:
+            if switch:
+                torch.cuda.set_device(prev)
+        if rc != 0:
+            _cabi.check(rc, "rayen_backward_f32")
         return (gv if ctx.in_dtype == torch.float32 else gv.to(ctx.in_dtype)), None
+
+
+class _LaunchState:
+    """Per-(module, device) cache of everything the hot path needs: plan handle, C entry points, sizes."""
+
+    def __init__(self, dev_plan):
+        lib = _cabi.lib()
+        self.plan = dev_plan
+        self.handle = dev_plan.handle
+        self.index = dev_plan.device_index
+        self.forward = lib.rayen_forward_f32
+        self.backward = lib.rayen_backward_f32
+        self._ws = {}
+
+    def ws_words(self, batch):
+        w = self._ws.get(batch)
+        if w is None:
+            w = (self.plan.workspace_bytes(batch) + 3) // 4 + 4
+            self._ws[batch] = w
+        return w
 
 
 class ConstraintModule(nn.Module):
@@ -148,7 +186,8 @@ class ConstraintModule(nn.Module):
         # host-side packed plan (float64 math, float32 block) and its per-GPU uploads
         self._packed = plan_mod.build_plan_from_constraints(cs)
         self._plans = {}
-        self._last = None
+        self._states = {}
+        self._last_aux = None
 
     # ------------------------------------------------------------------ plan management
     def _device_plan(self, device):
@@ -158,6 +197,22 @@ class ConstraintModule(nn.Module):
             dev_plan = _cabi.DevicePlan(self._packed, index)
             self._plans[index] = dev_plan
         return dev_plan
+
+    def __getstate__(self):
+        # ctypes handles / device plans are per process: drop them when the module is pickled (torch.save(model))
+        state = self.__dict__.copy()
+        for key in ("_plans", "_states"):
+            state[key] = {}
+        state["_last_aux"] = None
+        state.pop("_host_ws", None)
+        return state
+
+    def _launch_state(self, device):
+        st = self._states.get(device)
+        if st is None:
+            st = _LaunchState(self._device_plan(device))
+            self._states[device] = st
+        return st
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
@@ -179,6 +234,7 @@ class ConstraintModule(nn.Module):
         for dev_plan in self._plans.values():
             dev_plan.close()
         self._plans = {}
+        self._states = {}
 
     def set_tuning(self, samples_per_thread=0, lanes_per_sample=0, device=None):
         """Override the launch geometry of the linear/quadratic/SOC kernel (0 = automatic)."""
@@ -226,7 +282,10 @@ class ConstraintModule(nn.Module):
 
     def last_kappa_and_active(self):
         """(kappa[B], active[B]) of the most recent forward: active = family << 24 | constraint index."""
-        return self._last
+        if self._last_aux is None:
+            return None
+        aux, B = self._last_aux
+        return aux[:B], aux[B:2 * B].view(torch.int32)
 
     # ------------------------------------------------------------------ reference helper methods
     def getDimAfterMap(self):
