@@ -14,7 +14,7 @@
 //   warps 0-7  load v, normalise, write U_hi/U_lo as K-major operand tiles; later read D from TMEM and reduce;
 //              finally apply the scale step and write y / kappa / active (and the LMI work list)
 //   warp 8     TMA producer: streams the 96-row panels of W (hi + lo) through a 3-stage shared-memory ring
-//   warp 9     MMA issuer (one elected lane) and owner of the TMEM allocation
+//   warps 9,10 MMA issuers (one elected lane each, one per sample tile); warp 9 owns the TMEM allocation
 // Pipelines: W ring full/empty, TMEM accumulator full/empty (two 96-column buffers per sample tile), U ready.
 #pragma once
 #include "common.cuh"
@@ -22,10 +22,17 @@
 
 namespace rayen {
 
+#ifdef RAYEN_TC_TRACE
+__device__ long long g_tc_trace[4096];
+#define TC_STAMP(slot) do { if (blockIdx.x == 0) g_tc_trace[(slot)] = clock64(); } while (0)
+#else
+#define TC_STAMP(slot) do { } while (0)
+#endif
+
 constexpr int kTcPanel = 96;
-constexpr int kTcStages = 3;
+constexpr int kTcStages = 4;
 constexpr int kTcEpiWarps = 8;
-constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
+constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;  // + TMA warp + two MMA-issuing warps (one per sample tile)
 constexpr int kTcTableWords = 24;
 
 // ----------------------------------------------------------------------------- tcgen05 / mbarrier helpers
@@ -121,10 +128,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     mbar_init(a_full, kTcEpiWarps);
     for (int i = 0; i < kTcStages; ++i) {
       mbar_init(&w_full[i], 1);
-      mbar_init(&w_empty[i], 1);
+      mbar_init(&w_empty[i], 2);  // one tcgen05.commit per MMA-issuing warp
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&d_full[i], 1);
+      mbar_init(&d_full[i], 2);
       mbar_init(&d_empty[i], kTcEpiWarps);
     }
     fence_mbar_init();
@@ -141,6 +148,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   const long long n_super = (B + 255) / 256;
   const int n = P.n, k = P.k;
+  if (tid == 0) TC_STAMP(1000);
+#ifdef RAYEN_TC_TRACE
+  if (tid == 0) g_tc_trace[2200 + blockIdx.x] = clock64();
+  long long gt0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0)); if (tid == 0) g_tc_trace[2400 + blockIdx.x] = gt0;
+#endif
 
   if (warp == kTcEpiWarps) {
     // ===================================================================== TMA producer
@@ -150,13 +162,23 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int p = 0; p < n_panels; ++p, ++g) {
           const uint32_t stage = g % kTcStages, use = g / kTcStages;
           mbar_wait(&w_empty[stage], (use & 1) ^ 1);
+          TC_STAMP(8 * p + 7);
           mbar_expect_tx(&w_full[stage], 2 * W_TILE * 4);
-          bulk_g2s(w_ring + stage * 2 * W_TILE, w_src + static_cast<size_t>(p) * 2 * W_TILE, 2 * W_TILE * 4, &w_full[stage]);
+          // several smaller bulk copies keep more requests in flight than one 24 KB copy
+          constexpr int PIECES = (KP >= 32) ? 4 : 2;
+          constexpr int PIECE = 2 * W_TILE / PIECES;
+#pragma unroll
+          for (int c = 0; c < PIECES; ++c)
+            bulk_g2s(w_ring + stage * 2 * W_TILE + c * PIECE, w_src + static_cast<size_t>(p) * 2 * W_TILE + c * PIECE,
+                     PIECE * 4, &w_full[stage]);
         }
       }
     }
-  } else if (warp == kTcEpiWarps + 1) {
-    // ===================================================================== MMA issuer
+  } else if (warp > kTcEpiWarps) {
+    // ===================================================================== MMA issuers: warp 9 -> sample tile 0,
+    // warp 10 -> sample tile 1.  Two issuing threads keep the tensor pipe fed while the other one is busy
+    // with its commits / barrier waits (a single issuer left the pipe idle ~25 % of every panel).
+    const int t = warp - (kTcEpiWarps + 1);
     if (lane == 0) {
       uint32_t g = 0, s_local = 0;
       for (long long st = blockIdx.x; st < n_super; st += gridDim.x, ++s_local) {
@@ -165,12 +187,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int p = 0; p < n_panels; ++p, ++g) {
           const uint32_t stage = g % kTcStages, use = g / kTcStages;
           const uint32_t buf = g & 1, buf_use = g >> 1;
+          TC_STAMP(8 * p + 0);
           mbar_wait(&w_full[stage], use & 1);
+          TC_STAMP(8 * p + 1);
           mbar_wait(&d_empty[buf], (buf_use & 1) ^ 1);
           tc_fence_after();
+          TC_STAMP(8 * p + 2);
           const uint32_t w_hi = smem_u32(w_ring + stage * 2 * W_TILE), w_lo = w_hi + W_TILE * 4;
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
+          {
             const uint32_t u_hi = smem_u32(a_tiles + (2 * t) * A_TILE), u_lo = u_hi + A_TILE * 4;
             const uint32_t d_tmem = tmem_base + (2 * t + buf) * kTcPanel;
 #pragma unroll
@@ -184,6 +208,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               umma_tf32(d_tmem, d_uhi, d_wlo, IDESC, 1u);
             }
           }
+          TC_STAMP(8 * p + 3);
           umma_commit(&w_empty[stage]);  // the ring slot is free once these MMAs have read it
           umma_commit(&d_full[buf]);     // ... and the accumulator is complete
         }
@@ -228,8 +253,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       float ub = 3.0e38f;  // pruning bound of the LMI (stays +inf without one)
       for (int p = 0; p < n_panels; ++p, ++g) {
         const uint32_t buf = g & 1, buf_use = g >> 1;
+        if (warp == 0 && lane == 0) TC_STAMP(8 * p + 4);
         mbar_wait(&d_full[buf], buf_use & 1);
         tc_fence_after();
+        if (warp == 0 && lane == 0) TC_STAMP(8 * p + 5);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (2 * t + buf) * kTcPanel;
         const int* pt = reinterpret_cast<const int*>(table + p * kTcTableWords);
         if (pt[0] == 0) {
@@ -295,6 +322,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
           }
         }
+        if (warp == 0 && lane == 0) TC_STAMP(8 * p + 6);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d_empty[buf]);
@@ -351,6 +379,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   // ---- teardown: nobody may still be reading TMEM when it is released
   tc_fence_before();
   __syncthreads();
+#ifdef RAYEN_TC_TRACE
+  if (tid == 0) { g_tc_trace[2000 + blockIdx.x] = clock64() - g_tc_trace[2200 + blockIdx.x]; long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1)); g_tc_trace[2600 + blockIdx.x] = gt1; }
+#endif
   if (warp == kTcEpiWarps + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
   }

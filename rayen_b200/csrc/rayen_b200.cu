@@ -310,6 +310,27 @@ extern "C" int rayen_plan_set_tensor_cores(rayen_plan_t* p, int enabled) {
   return RAYEN_OK;
 }
 
+#ifdef RAYEN_TC_TRACE
+extern "C" int rayen_tc_trace_dump(void) {
+  static long long h[4096];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, rayen::g_tc_trace, sizeof(h));
+  const long long t0 = h[1000];
+  fprintf(stderr, "panel: mma[pre_wfull wfull dempty issued] epi[pre_dfull dfull loaded] prod[issue]  (cycles since kernel start)\n");
+  for (int p = 0; p < 20; ++p) {
+    fprintf(stderr, "%2d:", p);
+    for (int j = 0; j < 8; ++j) fprintf(stderr, " %7lld", h[8 * p + j] - t0);
+    fprintf(stderr, "\n");
+  }
+  long long gmin = h[2400], gmax = h[2600];
+  for (int b = 0; b < 128; ++b) { if (h[2400 + b] < gmin) gmin = h[2400 + b]; if (h[2600 + b] > gmax) gmax = h[2600 + b]; }
+  fprintf(stderr, "per-CTA: start offset ns / duration cycles\n");
+  for (int b = 0; b < 128; b += 8) fprintf(stderr, "cta %3d: start +%6lld ns, end +%6lld ns, cycles %7lld\n", b, h[2400 + b] - gmin, h[2600 + b] - gmin, h[2000 + b]);
+  fprintf(stderr, "span %lld ns\n", gmax - gmin);
+  return 0;
+}
+#endif
+
 extern "C" int rayen_plan_set_pruning(rayen_plan_t* p, int enabled) {
   if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "null plan");
   p->prune = enabled && p->has_lqs && p->dev.lmi_prune;
