@@ -166,6 +166,7 @@ class DeviceBench:
         self.plan = layer._device_plan(device)
         self.sets = []
         self.pool = pool
+        self.want_grad = 1   # forward leaves d kappa/du of the LMI-bound samples for backward (training step)
         for i in range(pool):
             v, gy = synthetic.sample_inputs(batch, self.n, self.k, seed_v=seed + i, seed_g=7 + i)
             self.sets.append(dict(
@@ -177,14 +178,15 @@ class DeviceBench:
 
     def forward(self, s, stage=3):
         rc = self.lib.rayen_forward_stage_f32(self.plan.handle, s["v"].data_ptr(), self.n, s["y"].data_ptr(),
-                                              s["kappa"].data_ptr(), s["active"].data_ptr(), self.B, 0, stage,
-                                              s["ws"].data_ptr(), self.stream)
+                                              s["kappa"].data_ptr(), s["active"].data_ptr(), self.B, 0, self.want_grad,
+                                              stage, s["ws"].data_ptr(), self.stream)
         self.cabi.check(rc, "rayen_forward_stage_f32")
 
     def backward(self, s, stage=3):
         rc = self.lib.rayen_backward_stage_f32(self.plan.handle, s["v"].data_ptr(), self.n, s["gy"].data_ptr(),
                                                s["kappa"].data_ptr(), s["active"].data_ptr(), s["gv"].data_ptr(),
-                                               self.n, self.B, 0, stage, s["ws"].data_ptr(), self.stream)
+                                               self.n, self.B, 0, self.want_grad, stage, s["ws"].data_ptr(),
+                                               self.stream)
         self.cabi.check(rc, "rayen_backward_stage_f32")
 
     def step(self, i):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RAYEN_ABI_VERSION 5
+#define RAYEN_ABI_VERSION 6
 
 /* error codes (negative); positive return values are cudaError_t */
 #define RAYEN_OK 0
@@ -115,7 +115,7 @@ int rayen_plan_set_pruning(rayen_plan_t* plan, int enabled);
 int rayen_plan_set_tensor_cores(rayen_plan_t* plan, int enabled);
 
 /* Device scratch the forward / backward calls need for a batch of B samples (work lists of the samples
- * that still need the LMI kernels).  0 for plans without an LMI.  The caller owns the buffer; it must
+ * that still need the LMI kernels, and d kappa/du of the LMI-bound samples).  0 for plans without an LMI.  The caller owns the buffer; it must
  * not be shared by calls that may run concurrently. */
 int64_t rayen_workspace_bytes(const rayen_plan_t* plan, int64_t B);
 
@@ -125,28 +125,34 @@ int64_t rayen_workspace_bytes(const rayen_plan_t* plan, int64_t B);
  *   v      [B, ldv]  (ldv >= n, or >= n+1 for RAYEN_OLD), y [B, k]
  *   kappa  [B] and active [B] receive kappa and (family << 24 | index) of the binding constraint;
  *          they are what backward needs.  They may be NULL only for plans without an LMI.
- *   workspace  rayen_workspace_bytes(plan, B) bytes of device memory (may be NULL when that is 0)
+ *   want_grad  != 0: a backward call will follow.  For plans with an LMI the forward then also computes, for the
+ *          samples whose binding constraint is the LMI, d kappa/du (top eigenvector, q' F q) while the
+ *          tridiagonal form is still in registers, and leaves it in the workspace for backward.
+ *   workspace  rayen_workspace_bytes(plan, B) bytes of device memory (may be NULL when that is 0); the
+ *          backward call of the same batch must get the same buffer
  */
 int rayen_forward_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, float* y, float* kappa,
-                      int32_t* active, int64_t B, int mode, void* workspace, void* cuda_stream);
+                      int32_t* active, int64_t B, int mode, int want_grad, void* workspace, void* cuda_stream);
 
 /*
  * Backward: the closed form of what autograd derives from the reference forward.
  *   gy [B, k], kappa/active from the forward call on the same v, gv [B, ldv_g] (ldv_g = n or n+1).
+ *   have_dkappa != 0: the forward call ran with want_grad != 0 on this workspace (no LMI kernel is launched);
+ *   0: the LMI-bound samples are recomputed by a separate kernel.
  */
 int rayen_backward_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, const float* gy,
                        const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
-                       int mode, void* workspace, void* cuda_stream);
+                       int mode, int have_dkappa, void* workspace, void* cuda_stream);
 
 /* Per-kernel launches for profiling and the roofline measurement in bench.py: stage_mask bit 0 = the
  * linear/quadratic/SOC kernel, bit 1 = the LMI kernel (3 = what rayen_forward_f32 / rayen_backward_f32
  * launch).  With stage_mask == 2 the kappa/active buffers and the workspace must already hold the first stage's result. */
 int rayen_forward_stage_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, float* y, float* kappa,
-                            int32_t* active, int64_t B, int mode, int stage_mask, void* workspace,
+                            int32_t* active, int64_t B, int mode, int want_grad, int stage_mask, void* workspace,
                             void* cuda_stream);
 int rayen_backward_stage_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, const float* gy,
                              const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
-                             int mode, int stage_mask, void* workspace, void* cuda_stream);
+                             int mode, int have_dkappa, int stage_mask, void* workspace, void* cuda_stream);
 
 /* Host-buffer variants (the end-to-end path): host->device copies, the kernels, device->host
  * copies, all on `cuda_stream`, which is synchronised before returning.  Host buffers should be

@@ -67,14 +67,15 @@ class _RayShoot(torch.autograd.Function):
             prev = torch.cuda.current_device()
             torch.cuda.set_device(st.index)
         try:
+            want_grad = 1 if ctx.needs_input_grad[0] else 0
             rc = st.forward(st.handle, v.data_ptr(), v.stride(0) if B > 0 else cols, y.data_ptr(), base, base + 4 * B, B,
-                            module._mode, base + 8 * B, torch.cuda.current_stream(device).cuda_stream)
+                            module._mode, want_grad, base + 8 * B, torch.cuda.current_stream(device).cuda_stream)
         finally:
             if switch:
                 torch.cuda.set_device(prev)
         if rc != 0:
             _cabi.check(rc, "rayen_forward_f32")
-        ctx.module, ctx.in_dtype, ctx.aux = module, q.dtype, aux
+        ctx.module, ctx.in_dtype, ctx.aux, ctx.have_dkappa = module, q.dtype, aux, want_grad
         ctx.save_for_backward(v)
         module._last_aux = (aux, B)
         return y if q.dtype == torch.float32 else y.to(q.dtype)
@@ -99,7 +100,7 @@ class _RayShoot(torch.autograd.Function):
             torch.cuda.set_device(st.index)
         try:
             rc = st.backward(st.handle, v.data_ptr(), v.stride(0) if B > 0 else cols, gy.data_ptr(), base, base + 4 * B,
-                             gv.data_ptr(), cols, B, module._mode, base + 8 * B,
+                             gv.data_ptr(), cols, B, module._mode, ctx.have_dkappa, base + 8 * B,
                              torch.cuda.current_stream(device).cuda_stream)
         finally:
             if switch:

@@ -466,11 +466,15 @@ __device__ __forceinline__ const float* lmi_stage(const PlanDev& P, unsigned cha
 
 // ----------------------------------------------------------------------------- forward
 // prior kappa/tag (from lqs_forward_kernel) are merged when has_prior != 0; y, kappa, active are written.
-template <int RP, bool F_SMEM, int THREADS>
+// WITH_GRAD: additionally, for the samples whose binding constraint turns out to be the LMI (and whose gradient
+// needs it), finish the job while the tridiagonal form and the reflectors are still in registers: top eigenvector,
+// d kappa/du_a = q' F~z_a q, stored to dkappa[b, :].  Backward then needs no LMI kernel at all.
+template <int RP, bool F_SMEM, int THREADS, bool WITH_GRAD>
 __global__ void __launch_bounds__(THREADS, 1)
     lmi_forward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, float* __restrict__ y,
                        float* __restrict__ kappa_io, int* __restrict__ active_io, long long B, int mode,
-                       int has_prior, const int* __restrict__ work_list, const int* __restrict__ work_count) {
+                       int has_prior, const int* __restrict__ work_list, const int* __restrict__ work_count,
+                       float* __restrict__ dkappa) {
   using C = LmiCfg<RP>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   const float* F = lmi_stage<RP, F_SMEM>(P, smem_raw, bars, &scratch_base, cta_has_work);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  LmiSolver<RP, false, F_SMEM> S;
+  LmiSolver<RP, WITH_GRAD, F_SMEM> S;
   S.q = lane % C::LPM;
   S.grp_base = lane - S.q;
   const int grp = lane / C::LPM;
@@ -539,6 +543,24 @@ __global__ void __launch_bounds__(THREADS, 1)
           float acc = 0.f;
           for (int a = 0; a < n; ++a) acc = fmaf(__ldg(nrow + a), u[a], acc);
           yrow[i] = fmaf(alpha, acc, __ldg(y0 + i));
+        }
+      }
+    }
+    if constexpr (WITH_GRAD) {
+      bool need = valid && tag_family(tag) == RAYEN_FAM_LMI && kap > 0.f;
+      if (need && mode == RAYEN_MODE_RAYEN) need = (1.0f / kap < s);
+      if (__ballot_sync(0xffffffffu, need) != 0u) {  // warp-uniform: the other matrices of the warp just ride along
+        __syncwarp();
+        float qo[4];
+        S.eigenvector(lam, qo);
+        float dk[C::NPL];
+        S.eig_gradient(F, n, qo, dk);
+        if (need) {
+#pragma unroll
+          for (int sl = 0; sl < C::NPL; ++sl) {
+            const int a = S.q + C::LPM * sl;
+            if (a < n) dkappa[b * n + a] = dk[sl];
+          }
         }
       }
     }

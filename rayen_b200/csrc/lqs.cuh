@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(256)
     lqs_backward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, const float* __restrict__ gy,
                         const float* __restrict__ kappa, const int* __restrict__ active, float* __restrict__ gv,
                         long long ldgv, long long B, int mode, int* __restrict__ work_list,
-                        int* __restrict__ work_count) {
+                        int* __restrict__ work_count, const float* __restrict__ dkappa) {
   const int n = P.n;
   const bool vec_v = ((n & 3) == 0) && ((ldv & 3) == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
   const bool vec_gy = ((P.k & 3) == 0) && ((reinterpret_cast<uintptr_t>(gy) & 15) == 0);
@@ -522,14 +522,18 @@ __global__ void __launch_bounds__(256)
     const float s = normalize_row<NP>(u);
     const float beta = (mode == RAYEN_MODE_RAYEN_OLD) ? __ldg(v + b * ldv + n) : 0.f;
     const bool boundary = (mode == RAYEN_MODE_RAYEN_OLD) ? (kap > 0.f) : (1.0f / kap < s);
-    if (boundary && tag_family(tag) == RAYEN_FAM_LMI) {
-      // needs the eigenvector: queued for lmi_backward_kernel
+    const bool lmi_bound = boundary && tag_family(tag) == RAYEN_FAM_LMI;
+    if (lmi_bound && !dkappa) {
+      // needs the eigenvector and the forward pass did not leave d kappa/du behind: queued for lmi_backward_kernel
       if (work_list) work_list[atomicAdd(work_count, 1)] = static_cast<int>(b);
       continue;
     }
     float gz[NP], dk[NP], g[NP];
     load_gz<NP>(P, gy + b * P.k, vec_gy, gz);
-    if (boundary) {
+    if (lmi_bound) {
+#pragma unroll
+      for (int a = 0; a < NP; ++a) dk[a] = (a < n) ? __ldg(dkappa + b * n + a) : 0.f;
+    } else if (boundary) {
       dkappa_lqs<NP>(P, tag, kap, u, dk);
     } else {
 #pragma unroll

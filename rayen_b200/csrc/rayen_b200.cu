@@ -26,7 +26,7 @@ struct rayen_plan {
   float* d_blob;
   bool lqs_smem;  // LQS constants fit in shared memory
   bool lmi_smem;  // LMI matrices fit in shared memory
-  size_t lqs_smem_bytes, lmi_smem_bytes, lmi_bwd_smem_bytes;
+  size_t lqs_smem_bytes, lmi_smem_bytes, lmi_bwd_smem_bytes, lmi_grad_smem_bytes;
   bool has_lqs;   // any non-zero linear row / quadratic / cone: otherwise the LQS forward kernel is skipped
   bool prune;     // LMI pruning enabled (needs has_lqs and a BOUND section)
   bool use_tc;    // tensor-core (tcgen05) linear/quadratic/SOC forward kernel
@@ -61,9 +61,9 @@ extern "C" int64_t rayen_launch_count(void) { return g_launches.load(); }
 typedef void (*LqsFwdFn)(const PlanDev, const float*, long long, float*, float*, int*, long long, int, int, int, int,
                          int*, int*);
 typedef void (*LqsBwdFn)(const PlanDev, const float*, long long, const float*, const float*, const int*, float*,
-                         long long, long long, int, int*, int*);
+                         long long, long long, int, int*, int*, const float*);
 typedef void (*LmiFwdFn)(const PlanDev, const float*, long long, float*, float*, int*, long long, int, int,
-                         const int*, const int*);
+                         const int*, const int*, float*);
 typedef void (*LmiBwdFn)(const PlanDev, const float*, long long, const float*, const float*, const int*, float*,
                          long long, long long, int, const int*, const int*);
 
@@ -114,17 +114,19 @@ static LqsBwdFn lqs_bwd_fn(int np) {
     default: return lqs_backward_kernel<32>;
   }
 }
-template <int THREADS>
+template <int THREADS, bool GRAD>
 static LmiFwdFn lmi_fwd_fn_t(int rp, bool smem) {
   switch (rp) {
-    case 4: return smem ? lmi_forward_kernel<4, true, THREADS> : lmi_forward_kernel<4, false, THREADS>;
-    case 8: return smem ? lmi_forward_kernel<8, true, THREADS> : lmi_forward_kernel<8, false, THREADS>;
-    case 16: return smem ? lmi_forward_kernel<16, true, THREADS> : lmi_forward_kernel<16, false, THREADS>;
-    default: return smem ? lmi_forward_kernel<32, true, THREADS> : lmi_forward_kernel<32, false, THREADS>;
+    case 4: return smem ? lmi_forward_kernel<4, true, THREADS, GRAD> : lmi_forward_kernel<4, false, THREADS, GRAD>;
+    case 8: return smem ? lmi_forward_kernel<8, true, THREADS, GRAD> : lmi_forward_kernel<8, false, THREADS, GRAD>;
+    case 16: return smem ? lmi_forward_kernel<16, true, THREADS, GRAD> : lmi_forward_kernel<16, false, THREADS, GRAD>;
+    default: return smem ? lmi_forward_kernel<32, true, THREADS, GRAD> : lmi_forward_kernel<32, false, THREADS, GRAD>;
   }
 }
-static LmiFwdFn lmi_fwd_fn(int rp, bool smem, int threads) {
-  return threads == 384 ? lmi_fwd_fn_t<384>(rp, smem) : lmi_fwd_fn_t<256>(rp, smem);
+// the gradient-carrying variant keeps the reflectors in registers: 256 threads only
+static LmiFwdFn lmi_fwd_fn(int rp, bool smem, int threads, bool grad) {
+  if (grad) return lmi_fwd_fn_t<256, true>(rp, smem);
+  return threads == 384 ? lmi_fwd_fn_t<384, false>(rp, smem) : lmi_fwd_fn_t<256, false>(rp, smem);
 }
 static LmiBwdFn lmi_bwd_fn(int rp, bool smem) {
   switch (rp) {
@@ -270,7 +272,9 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
     p->lmi_smem_bytes = lmi_smem(v.lmi_rp, true, v.n, p->lmi_fwd_threads);
     p->lmi_smem = p->lmi_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
     if (!p->lmi_smem) p->lmi_smem_bytes = lmi_smem(v.lmi_rp, false, v.n, p->lmi_fwd_threads);
-    rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_fn(v.lmi_rp, p->lmi_smem, p->lmi_fwd_threads)), p->lmi_smem_bytes);
+    rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_fn(v.lmi_rp, p->lmi_smem, p->lmi_fwd_threads, false)), p->lmi_smem_bytes);
+    p->lmi_grad_smem_bytes = lmi_smem(v.lmi_rp, p->lmi_smem, v.n, 256);
+    if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_fn(v.lmi_rp, p->lmi_smem, 256, true)), p->lmi_grad_smem_bytes);
     p->lmi_bwd_smem_bytes = lmi_smem(v.lmi_rp, p->lmi_smem, v.n, kLmiThreads);
     if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_bwd_fn(v.lmi_rp, p->lmi_smem)), p->lmi_bwd_smem_bytes);
   }
@@ -338,11 +342,15 @@ extern "C" int rayen_plan_set_pruning(rayen_plan_t* p, int enabled) {
 }
 
 // workspace: [fwd counter, bwd counter, pad to 256 B][forward work list: B ints][backward work list: B ints]
+//            [d kappa/du of the LMI-bound samples: B x n floats, written by forward when want_grad != 0]
 static int64_t ws_list_bytes(int64_t B) { return (B * 4 + 255) / 256 * 256; }
 extern "C" int64_t rayen_workspace_bytes(const rayen_plan_t* p, int64_t B) {
   if (!p || B < 0) return -1;
   if (p->dev.lmi_r == 0) return 0;
-  return 256 + 2 * ws_list_bytes(B);
+  return 256 + 2 * ws_list_bytes(B) + (B * p->dev.n * 4 + 255) / 256 * 256;
+}
+static float* ws_dkappa(void* workspace, int64_t B) {
+  return reinterpret_cast<float*>(static_cast<char*>(workspace) + 256 + 2 * ws_list_bytes(B));
 }
 
 extern "C" int rayen_plan_kernel_info(const rayen_plan_t* p, RayenKernelInfo* out) {
@@ -354,7 +362,7 @@ extern "C" int rayen_plan_kernel_info(const rayen_plan_t* p, RayenKernelInfo* ou
   RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lqs_bwd_fn(p->dev.np))));
   out->regs_lqs_bwd = a.numRegs;
   if (p->dev.lmi_r > 0) {
-    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_fwd_fn(p->dev.lmi_rp, p->lmi_smem, p->lmi_fwd_threads))));
+    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_fwd_fn(p->dev.lmi_rp, p->lmi_smem, p->lmi_fwd_threads, false))));
     out->regs_lmi_fwd = a.numRegs;
     RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lmi_bwd_fn(p->dev.lmi_rp, p->lmi_smem))));
     out->regs_lmi_bwd = a.numRegs;
@@ -440,24 +448,24 @@ static int check_io(const rayen_plan* p, const void* a, const void* b, long long
 
 // ----------------------------------------------------------------------------- forward / backward
 static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa, int32_t* active,
-                        int64_t B, int mode, void* workspace, void* stream_, int stage_mask);
+                        int64_t B, int mode, int want_grad, void* workspace, void* stream_, int stage_mask);
 
 extern "C" int rayen_forward_f32(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa,
-                                 int32_t* active, int64_t B, int mode, void* workspace, void* stream_) {
-  return forward_impl(p, v, ldv, y, kappa, active, B, mode, workspace, stream_, 3);
+                                 int32_t* active, int64_t B, int mode, int want_grad, void* workspace, void* stream_) {
+  return forward_impl(p, v, ldv, y, kappa, active, B, mode, want_grad, workspace, stream_, 3);
 }
 extern "C" int rayen_forward_stage_f32(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa,
-                                       int32_t* active, int64_t B, int mode, int stage_mask, void* workspace,
-                                       void* stream_) {
+                                       int32_t* active, int64_t B, int mode, int want_grad, int stage_mask,
+                                       void* workspace, void* stream_) {
   if (stage_mask < 1 || stage_mask > 3) return fail(RAYEN_ERR_BAD_ARGUMENT, "stage_mask must be 1, 2 or 3");
-  return forward_impl(p, v, ldv, y, kappa, active, B, mode, workspace, stream_, stage_mask);
+  return forward_impl(p, v, ldv, y, kappa, active, B, mode, want_grad, workspace, stream_, stage_mask);
 }
 extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, int64_t ldv, const float* gy,
                                         const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
-                                        int mode, int stage_mask, void* workspace, void* stream_);
+                                        int mode, int have_dkappa, int stage_mask, void* workspace, void* stream_);
 
 static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa, int32_t* active,
-                        int64_t B, int mode, void* workspace, void* stream_, int stage_mask) {
+                        int64_t B, int mode, int want_grad, void* workspace, void* stream_, int stage_mask) {
   int rc = check_io(p, v, y, B, mode);
   if (rc) return rc;
   if (B == 0) return RAYEN_OK;
@@ -502,13 +510,14 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
   }
   if (e == cudaSuccess && has_lmi && (stage_mask & 2)) {
     const int mpw = 32 / (d.lmi_rp / 4);
-    const int threads = p->lmi_fwd_threads;
+    const bool grad = want_grad != 0;
+    const int threads = grad ? 256 : p->lmi_fwd_threads;
     long long blocks = (B + static_cast<long long>(mpw) * (threads / 32) - 1) / (static_cast<long long>(mpw) * (threads / 32));
     if (blocks > p->sm_count) blocks = p->sm_count;
-    LmiFwdFn lf = lmi_fwd_fn(d.lmi_rp, p->lmi_smem, threads);
-    lf<<<static_cast<int>(blocks), threads, p->lmi_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode,
-                                                                         run_lqs ? 1 : 0, use_list ? fwd_list : nullptr,
-                                                                         use_list ? counters : nullptr);
+    LmiFwdFn lf = lmi_fwd_fn(d.lmi_rp, p->lmi_smem, threads, grad);
+    lf<<<static_cast<int>(blocks), threads, grad ? p->lmi_grad_smem_bytes : p->lmi_smem_bytes, stream>>>(
+        d, v, ldv, y, kappa, active, B, mode, run_lqs ? 1 : 0, use_list ? fwd_list : nullptr,
+        use_list ? counters : nullptr, grad ? ws_dkappa(workspace, B) : nullptr);
     g_launches.fetch_add(1);
     e = cudaGetLastError();
   }
@@ -519,13 +528,13 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
 
 extern "C" int rayen_backward_f32(const rayen_plan_t* p, const float* v, int64_t ldv, const float* gy,
                                   const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
-                                  int mode, void* workspace, void* stream_) {
-  return rayen_backward_stage_f32(p, v, ldv, gy, kappa, active, gv, ldgv, B, mode, 3, workspace, stream_);
+                                  int mode, int have_dkappa, void* workspace, void* stream_) {
+  return rayen_backward_stage_f32(p, v, ldv, gy, kappa, active, gv, ldgv, B, mode, have_dkappa, 3, workspace, stream_);
 }
 
 extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, int64_t ldv, const float* gy,
                                         const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
-                                        int mode, int stage_mask, void* workspace, void* stream_) {
+                                        int mode, int have_dkappa, int stage_mask, void* workspace, void* stream_) {
   if (stage_mask < 1 || stage_mask > 3) return fail(RAYEN_ERR_BAD_ARGUMENT, "stage_mask must be 1, 2 or 3");
   int rc = check_io(p, v, gy, B, mode);
   if (rc) return rc;
@@ -555,12 +564,13 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
     LqsBwdFn f = lqs_bwd_fn(d.np);
     if (e == cudaSuccess) {
       f<<<static_cast<int>(grid), block, 0, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode, bwd_list,
-                                                      has_lmi ? counters + 1 : nullptr);
+                                                      has_lmi ? counters + 1 : nullptr,
+                                                      (has_lmi && have_dkappa) ? ws_dkappa(workspace, B) : nullptr);
       g_launches.fetch_add(1);
       e = cudaGetLastError();
     }
   }
-  if (e == cudaSuccess && has_lmi && (stage_mask & 2)) {
+  if (e == cudaSuccess && has_lmi && !have_dkappa && (stage_mask & 2)) {
     const int mpw = 32 / (d.lmi_rp / 4);
     long long blocks = (B + static_cast<long long>(mpw) * (kLmiThreads / 32) - 1) / (static_cast<long long>(mpw) * (kLmiThreads / 32));
     if (blocks > p->sm_count) blocks = p->sm_count;
@@ -607,10 +617,10 @@ extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* p, const floa
   int rc = 0;
   cudaError_t e = cudaMemcpyAsync(v, v_host, B * n * 4, cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(gy, gy_host, B * k * 4, cudaMemcpyHostToDevice, stream);
-  if (e == cudaSuccess) rc = rayen_forward_f32(p, v, n, y, kappa, active, B, RAYEN_MODE_RAYEN, ws, stream);
+  if (e == cudaSuccess) rc = rayen_forward_f32(p, v, n, y, kappa, active, B, RAYEN_MODE_RAYEN, 1, ws, stream);
   if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(y_host, y, B * k * 4, cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess && rc == 0)
-    rc = rayen_backward_f32(p, v, n, gy, kappa, active, gv, n, B, RAYEN_MODE_RAYEN, ws, stream);
+    rc = rayen_backward_f32(p, v, n, gy, kappa, active, gv, n, B, RAYEN_MODE_RAYEN, 1, ws, stream);
   if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(gv_host, gv, B * n * 4, cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(stream);
   if (prev != p->device) cudaSetDevice(prev);

@@ -25,6 +25,9 @@ for arg in sys.argv[1:]:
     if cs.has_lmi_constraints:
         out["lmi_fwd"] = db.time_loop(lambda i: db.forward(db.sets[i % P], 2), 20, P)
     out["step"] = db.time_loop(db.step, 20, 3)
+    db.want_grad = 0
+    out["fwd_nograd"] = db.time_loop(lambda i: db.forward(db.sets[i % P]), 20, 3)
+    db.want_grad = 1
     act = db.sets[0]["active"].cpu().numpy() >> 24
     import numpy as np
     print(name, batch, {k: round(v * 1e3, 1) for k, v in out.items()}, "us; fam", np.bincount(act, minlength=5).tolist(), flush=True)

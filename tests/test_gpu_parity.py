@@ -244,6 +244,38 @@ def test_lmi_pruning_does_not_change_results():
             assert int(((outs[0][3] >> 24) == _cabi.FAM_LMI).sum()) > 50   # the LMI really binds for some samples
 
 
+def test_forward_computed_lmi_gradient_matches_backward_kernel():
+    """want_grad=1 (d kappa/du of LMI-bound samples computed inside the forward kernel) and the stand-alone
+    LMI backward kernel (have_dkappa=0) give the same g_v; no_grad forward equals the grad-enabled forward."""
+    lib = _cabi.lib()
+    spec = synthetic.config_spec("cfg5")
+    spec["b1"] = spec["b1"] * 4.0
+    cs = synthetic.build_constraints(spec)
+    B = 2000
+    v, gy = synthetic.sample_inputs(B, cs.n, cs.k, scale=8.0)
+    layer, y, gv = run_layer(cs, v, gy)                       # autograd path: want_grad = 1
+    _, act = layer.last_kappa_and_active()
+    assert int(((act >> 24) == _cabi.FAM_LMI).sum()) > 50
+    with torch.no_grad():
+        y_ng = layer(v.to(DEV).unsqueeze(2))[:, :, 0].cpu().numpy()
+    np.testing.assert_array_equal(y_ng.astype(np.float64), y)
+    plan = layer._device_plan(torch.device(DEV))
+    vd, gyd = v.to(DEV), gy.to(DEV)
+    yd = torch.empty(B, cs.k, device=DEV)
+    kap = torch.empty(B, device=DEV)
+    actd = torch.empty(B, dtype=torch.int32, device=DEV)
+    gvd = torch.empty(B, cs.n, device=DEV)
+    ws = torch.empty(plan.workspace_bytes(B), dtype=torch.uint8, device=DEV)
+    null = ctypes.c_void_p(0)
+    assert lib.rayen_forward_f32(plan.handle, vd.data_ptr(), cs.n, yd.data_ptr(), kap.data_ptr(), actd.data_ptr(), B, 0,
+                                 0, ws.data_ptr(), null) == 0
+    assert lib.rayen_backward_f32(plan.handle, vd.data_ptr(), cs.n, gyd.data_ptr(), kap.data_ptr(), actd.data_ptr(),
+                                  gvd.data_ptr(), cs.n, B, 0, 0, ws.data_ptr(), null) == 0
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(yd.cpu().numpy().astype(np.float64), y)
+    np.testing.assert_allclose(gvd.cpu().numpy().astype(np.float64), gv, rtol=0, atol=1e-6 * np.abs(gv).max())
+
+
 def test_host_buffer_path_matches_device_path():
     spec = synthetic.config_spec("cfg5")
     spec["b1"] = spec["b1"] * 4.0
@@ -319,15 +351,15 @@ def test_c_abi_error_codes_on_gpu():
     y = torch.zeros(4, cs.k, device=DEV)
     null = ctypes.c_void_p(0)
     # LMI plans need the kappa / active outputs and the workspace
-    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n, y.data_ptr(), null, null, 4, 0, null, null) == -1
+    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n, y.data_ptr(), null, null, 4, 0, 0, null, null) == -1
     assert b"kappa" in lib.rayen_last_error()
     kap = torch.zeros(4, device=DEV)
     act = torch.zeros(4, dtype=torch.int32, device=DEV)
     assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n, y.data_ptr(), kap.data_ptr(), act.data_ptr(), 4, 0,
-                                 null, null) == -1
+                                 0, null, null) == -1
     assert b"workspace" in lib.rayen_last_error()
     assert plan.workspace_bytes(4) >= 256 + 32
-    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n - 1, y.data_ptr(), null, null, 4, 0, null, null) == -1
-    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n, y.data_ptr(), null, null, 4, 7, null, null) == -1
+    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n - 1, y.data_ptr(), null, null, 4, 0, 0, null, null) == -1
+    assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n, y.data_ptr(), null, null, 4, 7, 0, null, null) == -1
     info = plan.kernel_info()
     assert info["sm_count"] >= 100 and info["regs_lmi_fwd"] > 0
