@@ -245,8 +245,8 @@ struct LmiSolver {
   }
 
   // ---- 3. largest eigenvalue of the tridiagonal matrix, clipped at 0 (kappa = relu(lambda_max)).
-  // count(x) = #negative pivots of the LDL' of T - xI = #eigenvalues below x (quotient-form Sturm
-  // sequence with the usual pivmin guard); x is above the spectrum iff count == RP.
+  // Parallel multisection: 8 probes per matrix and round (one per lane), each probe decides "x above the
+  // whole spectrum?" with a Sturm sequence; 8 rounds shrink the Gershgorin interval by 9^8.
   __device__ __forceinline__ float lambda_max_relu() {
     float d[RP], e2[RP];
     float dmax = -3.0e38f, hi = -3.0e38f, lo_g = 3.0e38f;
@@ -268,10 +268,20 @@ struct LmiSolver {
         }
       }
     }
+    // Work on T / scale so that |d_i - x| <= 2 and e_i^2 <= 1, in the PRODUCT form of the Sturm sequence
+    //   p_0 = 1, p_1 = d_0 - x, p_{i+1} = (d_i - x) p_i - e_i^2 p_{i-1}
+    // (two dependent FMAs per step instead of a reciprocal): x is above the whole spectrum iff consecutive
+    // p's strictly alternate in sign.  Only signs matter, so (p_{i-1}, p_i) is rescaled by a positive power of
+    // two every 4 steps to stay clear of overflow / underflow.
     const float scale = fmaxf(fmaxf(fabsf(hi), fabsf(lo_g)), 1e-30f);
-    const float pivmin = 1e-25f * scale;
-    float lo = fmaxf(dmax, 0.f);
-    hi = fmaf(1e-6f, scale, hi);
+    const float inv_scale = 1.0f / scale;
+#pragma unroll
+    for (int i = 0; i < RP; ++i) {
+      d[i] *= inv_scale;
+      e2[i] *= inv_scale * inv_scale;
+    }
+    float lo = fmaxf(dmax, 0.f) * inv_scale;
+    hi = fmaf(1e-6f, scale, hi) * inv_scale;
     hi = fmaxf(hi, lo);  // whole spectrum <= 0: degenerate interval, the rounds below return lo = 0 (no early
                          // exit: the shuffles below need every lane of the warp)
     for (int round = 0; round < C::ROUNDS; ++round) {
@@ -281,15 +291,22 @@ struct LmiSolver {
       for (int pp = 0; pp < C::PPL; ++pp) {
         const int pt = q * C::PPL + pp;
         const float x = fmaf(h, static_cast<float>(pt + 1), lo);
-        int neg = 0;
-        float piv = 1.f;
+        float p0 = 1.f, p1 = d[0] - x;
+        bool above = p1 < 0.f;
 #pragma unroll
-        for (int i = 0; i < RP; ++i) {
-          piv = (d[i] - x) - (i == 0 ? 0.f : __fdividef(e2[i], piv));
-          if (fabsf(piv) < pivmin) piv = -pivmin;
-          neg += (piv < 0.f) ? 1 : 0;
+        for (int i = 1; i < RP; ++i) {
+          const float pn = fmaf(d[i] - x, p1, -e2[i] * p0);
+          above = above && ((__float_as_int(pn) ^ __float_as_int(p1)) < 0) && (pn != 0.f);
+          p0 = p1;
+          p1 = pn;
+          if ((i & 3) == 3) {
+            const int ex = (__float_as_int(fmaxf(fabsf(p0), fabsf(p1))) >> 23) & 0xff;
+            const float sc = __int_as_float((254 - max(min(ex, 253), 1)) << 23);
+            p0 *= sc;
+            p1 *= sc;
+          }
         }
-        bits |= (neg == RP) ? (1 << pt) : 0;
+        bits |= above ? (1 << pt) : 0;
       }
       const int mask = group_or<LPM>(bits) & 0xff;
       const int first = mask ? (__ffs(mask) - 1) : 8;
@@ -298,6 +315,8 @@ struct LmiSolver {
       lo = new_lo;
       hi = new_hi;
     }
+    lo *= scale;
+    hi *= scale;
     return 0.5f * (lo + hi);
   }
 

@@ -276,6 +276,32 @@ def test_forward_computed_lmi_gradient_matches_backward_kernel():
     np.testing.assert_allclose(gvd.cpu().numpy().astype(np.float64), gv, rtol=0, atol=1e-6 * np.abs(gv).max())
 
 
+def test_tensor_core_and_fp32_pipe_kernels_agree():
+    """The tcgen05 3xTF32 GEMM formulation and the FP32-pipe kernel compute the same kappa (to 3xTF32 accuracy),
+    pick the same binding constraint away from near-ties, and both match the oracle."""
+    for cfg in ("cfg3", "cfg5"):
+        spec = synthetic.config_spec(cfg)
+        spec["b1"] = spec["b1"] * 4.0
+        cs = synthetic.build_constraints(spec)
+        v, gy = synthetic.sample_inputs(5000, cs.n, cs.k)
+        res = {}
+        for tc in (True, False):
+            layer = ConstraintModule(cs, create_map=False).to(DEV)
+            layer.set_tensor_cores(tc, device=DEV)
+            before = _cabi.launch_count()
+            y = layer(v.to(DEV).unsqueeze(2))[:, :, 0].cpu().double().numpy()
+            kap, act = layer.last_kappa_and_active()
+            res[tc] = (y, kap.cpu().double().numpy(), act.cpu().numpy())
+        y_tc, k_tc, a_tc = res[True]
+        y_fp, k_fp, a_fp = res[False]
+        assert np.abs(k_tc - k_fp).max() <= 2e-6 * np.abs(k_fp).max()
+        assert rel(y_tc, y_fp) <= 2e-6
+        cf = closed_form_numpy(OracleSet.from_constraints(cs), v.numpy())
+        clear = cf["margin"] > 1e-4
+        assert np.array_equal(a_tc[clear], a_fp[clear])
+        assert rel(y_tc, cf["y"]) <= TOL and rel(y_fp, cf["y"]) <= TOL
+
+
 def test_host_buffer_path_matches_device_path():
     spec = synthetic.config_spec("cfg5")
     spec["b1"] = spec["b1"] * 4.0
