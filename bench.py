@@ -392,6 +392,8 @@ def run_b200(args, rank, local_rank, world):
     sub = min(batch, 4096)
     line["max_violation"] = max_violation(OracleSet.from_constraints(cs), s0["y"][:sub].cpu().numpy(),
                                           spec["A1"], spec["b1"], spec["A2"], spec["b2"])
+    # ... and of the FULL batch on the GPU (rayen_violation_f32, float32 residuals)
+    line["max_violation_gpu_full_batch"] = float(layer.violation(s0["y"]).max())
     act = s0["active"].cpu().numpy() >> 24
     line["active_family_hist"] = {name: int(c) for name, c in zip(["none", "linear", "quad", "soc", "lmi"],
                                                                   np.bincount(act, minlength=5))}

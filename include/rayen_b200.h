@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RAYEN_ABI_VERSION 6
+#define RAYEN_ABI_VERSION 7
 
 /* error codes (negative); positive return values are cudaError_t */
 #define RAYEN_OK 0
@@ -69,6 +69,10 @@ extern "C" {
  *           per panel W_hi and W_lo (96 x tc_kp each, TF32 split) in the K-major no-swizzle operand layout
  *           [k/4][row/8][row%8][k%4].  A linear panel holds 96 rows of D; an item panel holds 96/(ch+kp)
  *           items of ch header rows (phi | c_z, h | t) followed by the kp rows of the triangular factor.
+ *   VIOL    the ORIGINAL constraints in the ambient space for rayen_violation_f32 (k4 = k rounded up to 4):
+ *           viol_in rows {a[k4], b, 0,0,0} of A1 y <= b1, viol_eq rows of A2 y = b2, per quadratic
+ *           {P[k4][k4], q[k4], r,0,0,0}, per cone {r_M, d, 0, 0, c[k4], r_M rows {M_i[k4], s_i,0,0,0}}
+ *   LMINEG  -F_0 .. -F_k laid out like LMI ([a][row][lane][slot]): lambda_max(sum_a (y,1)_a (-F_a)) = -lambda_min(F(y))
  */
 typedef struct RayenPlanDesc {
   int32_t abi_version; /* must be RAYEN_ABI_VERSION */
@@ -89,7 +93,9 @@ typedef struct RayenPlanDesc {
   int32_t lmi_prune; /* 1: the BOUND section is valid and pruning may be used */
   int32_t tc_panels; /* number of 96-row panels of the tensor-core section */
   int32_t tc_kp;     /* K of the tensor-core GEMM: max(8, np) */
-  int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi, off_tc;
+  int32_t viol_in;   /* inequality rows of the VIOL section */
+  int32_t viol_eq;   /* equality rows of the VIOL section */
+  int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi, off_tc, off_viol, off_lmineg;
   int64_t blob_words;
   const float* blob; /* host pointer, blob_words floats */
 } RayenPlanDesc;
@@ -161,6 +167,15 @@ int64_t rayen_host_workspace_bytes(const rayen_plan_t* plan, int64_t B);
 int rayen_forward_backward_host_f32(const rayen_plan_t* plan, const float* v_host, const float* gy_host,
                                     float* y_host, float* gv_host, int64_t B, void* workspace,
                                     void* cuda_stream);
+
+/*
+ * Max constraint residual per sample (<= 0 is feasible), float32, of y [B, ldy] against the ORIGINAL constraints:
+ * max(A1 y - b1, |A2 y - b2|, g_i(y), ||M_j y + s_j|| - c_j'y - d_j, relu(-lambda_min(F(y)))).  Replaces the
+ * per-sample cvxpy projection distance of constraints.py:549-559 / examples/main.py:176 as the violation metric.
+ *   viol [B]
+ */
+int rayen_violation_f32(const rayen_plan_t* plan, const float* y, int64_t ldy, float* viol, int64_t B,
+                        void* cuda_stream);
 
 /* Number of kernels this library has launched in the calling process (all plans, all threads). */
 int64_t rayen_launch_count(void);

@@ -16,7 +16,7 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "rayen_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MODE_RAYEN, MODE_RAYEN_OLD = 0, 1
 FAM_NONE, FAM_LINEAR, FAM_QUAD, FAM_SOC, FAM_LMI = 0, 1, 2, 3, 4
 
@@ -24,9 +24,11 @@ FAM_NONE, FAM_LINEAR, FAM_QUAD, FAM_SOC, FAM_LMI = 0, 1, 2, 3, 4
 class RayenPlanDesc(ctypes.Structure):
     _fields_ = [(name, ctypes.c_int32) for name in (
         "abi_version", "n", "k", "np", "k_pad", "m", "m_pad", "n_quad", "n_soc", "lmi_r", "lmi_rp",
-        "n_is_identity", "lin_chunk_stride", "quad_stride", "soc_stride", "lmi_prune", "tc_panels", "tc_kp")] + [
+        "n_is_identity", "lin_chunk_stride", "quad_stride", "soc_stride", "lmi_prune", "tc_panels", "tc_kp",
+        "viol_in", "viol_eq")] + [
         (name, ctypes.c_int64) for name in (
-            "off_lin", "off_quad", "off_soc", "off_nmat", "off_y0", "off_bound", "off_lmi", "off_tc", "blob_words")] + [
+            "off_lin", "off_quad", "off_soc", "off_nmat", "off_y0", "off_bound", "off_lmi", "off_tc", "off_viol",
+            "off_lmineg", "blob_words")] + [
         ("blob", ctypes.POINTER(ctypes.c_float))]
 
 
@@ -57,6 +59,7 @@ SYMBOLS = {
                                                 ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P]),
     "rayen_host_workspace_bytes": (ctypes.c_int64, [_P, ctypes.c_int64]),
     "rayen_forward_backward_host_f32": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int64, _P, _P]),
+    "rayen_violation_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, ctypes.c_int64, _P]),
     "rayen_launch_count": (ctypes.c_int64, []),
     "rayen_plan_kernel_info": (ctypes.c_int, [_P, ctypes.POINTER(RayenKernelInfo)]),
 }

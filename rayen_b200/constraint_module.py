@@ -231,7 +231,10 @@ class ConstraintModule(nn.Module):
             y0 = g("y0")
             constant = allF[-1] - np.einsum("a,aij->ij", y0[:, 0], allF[:-1])  # undo the H accumulation
             lmi = [F for F in allF[:-1]] + [constant]
-        self._packed = plan_mod.build_plan(g("A_p"), g("b_p"), g("NA_E"), g("yp"), g("z0"), qcs, socs, lmi)
+        # the loaded buffers may describe another set than self.cs: the violation checker then uses the polyhedron
+        # encoded by A_p, b_p and N (lin_rows=None) instead of the original rows
+        self._packed = plan_mod.build_plan(g("A_p"), g("b_p"), g("NA_E"), g("yp"), g("z0"), qcs, socs, lmi,
+                                           lin_rows=None)
         for dev_plan in self._plans.values():
             dev_plan.close()
         self._plans = {}
@@ -280,6 +283,22 @@ class ConstraintModule(nn.Module):
         """Linear/quadratic/SOC forward on tcgen05 tensor cores (default) or on the FP32 pipe."""
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._device_plan(device).set_tensor_cores(enabled)
+
+    def violation(self, y):
+        """Max constraint residual of every sample of ``y`` ([B, k] or [B, k, 1], CUDA) against the original
+        constraints, computed on the GPU by ``rayen_violation_f32`` (<= 0 means feasible)."""
+        if not y.is_cuda:
+            raise RuntimeError("ConstraintModule.violation needs a CUDA tensor")
+        yy = y.detach().reshape(y.shape[0], -1).float().contiguous()
+        utils.verify(yy.shape[1] == self.k, f"expected {self.k} values per sample")
+        out = torch.empty((yy.shape[0],), dtype=torch.float32, device=yy.device)
+        plan = self._device_plan(yy.device)
+        with torch.cuda.device(yy.device):
+            rc = _cabi.lib().rayen_violation_f32(plan.handle, yy.data_ptr(), yy.stride(0) if yy.shape[0] else self.k,
+                                                 out.data_ptr(), yy.shape[0],
+                                                 ctypes.c_void_p(torch.cuda.current_stream(yy.device).cuda_stream))
+        _cabi.check(rc, "rayen_violation_f32")
+        return out
 
     def last_kappa_and_active(self):
         """(kappa[B], active[B]) of the most recent forward: active = family << 24 | constraint index."""

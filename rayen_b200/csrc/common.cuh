@@ -18,6 +18,7 @@ struct PlanDev {
   int lqs_words;   // words [off_lin, off_lin + lqs_words) = LIN | QUAD | SOC | NMAT | Y0 | BOUND, staged to smem
   int lmi_words;   // n * rp * rp
   int off_tc, tc_panels, tc_kp;  // tensor-core section (see rayen_b200.h)
+  int off_viol, off_lmineg, viol_in, viol_eq;  // violation checker sections
 };
 
 constexpr int kFamShift = 24;

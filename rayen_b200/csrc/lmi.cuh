@@ -107,6 +107,33 @@ struct LmiSolver {
     }
   }
 
+  // same contraction with the coefficients read from global memory and a trailing coefficient of 1 (the
+  // constant matrix of the LMI): used by the violation checker, S = -F(y)
+  __device__ __forceinline__ void contract_affine(const float* __restrict__ F, const float* __restrict__ coef, int k,
+                                                  bool valid) {
+#pragma unroll
+    for (int i = 0; i < RP; ++i)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) A[i][t] = 0.f;
+    const float* Fq = F + 4 * q;
+    for (int a = 0; a <= k; ++a) {
+      const float ua = valid ? (a < k ? __ldg(coef + a) : 1.0f) : 0.f;
+      const float* Fa = Fq + a * (RP * RP);
+#pragma unroll
+      for (int i = 0; i < RP; ++i) {
+        float4 f;
+        if constexpr (F_SMEM)
+          f = ld4(Fa + i * RP);
+        else
+          f = __ldg(reinterpret_cast<const float4*>(Fa + i * RP));
+        A[i][0] = fmaf(ua, f.x, A[i][0]);
+        A[i][1] = fmaf(ua, f.y, A[i][1]);
+        A[i][2] = fmaf(ua, f.z, A[i][2]);
+        A[i][3] = fmaf(ua, f.w, A[i][3]);
+      }
+    }
+  }
+
   // ---- 2. Householder tridiagonalisation.  Afterwards sd()/se() hold the diagonal / sub-diagonal and,
   //         if WANT_GRAD, row k of A holds this lane's part of reflector k (zeros in dead columns).
   // The RP-2 reduction steps run as 4 runtime loops ("stages") instead of RP-2 unrolled bodies: stage S

@@ -12,6 +12,7 @@
 #include "lmi.cuh"
 #include "lqs.cuh"
 #include "lqs_tc.cuh"
+#include "viol.cuh"
 
 using namespace rayen;
 
@@ -26,7 +27,8 @@ struct rayen_plan {
   float* d_blob;
   bool lqs_smem;  // LQS constants fit in shared memory
   bool lmi_smem;  // LMI matrices fit in shared memory
-  size_t lqs_smem_bytes, lmi_smem_bytes, lmi_bwd_smem_bytes, lmi_grad_smem_bytes;
+  size_t lqs_smem_bytes, lmi_smem_bytes, lmi_bwd_smem_bytes, lmi_grad_smem_bytes, viol_lmi_smem_bytes;
+  bool viol_lmi_smem;
   bool has_lqs;   // any non-zero linear row / quadratic / cone: otherwise the LQS forward kernel is skipped
   bool prune;     // LMI pruning enabled (needs has_lqs and a BOUND section)
   bool use_tc;    // tensor-core (tcgen05) linear/quadratic/SOC forward kernel
@@ -136,6 +138,15 @@ static LmiBwdFn lmi_bwd_fn(int rp, bool smem) {
     default: return smem ? lmi_backward_kernel<32, true> : lmi_backward_kernel<32, false>;
   }
 }
+typedef void (*ViolLmiFn)(const PlanDev, const float*, long long, float*, long long);
+static ViolLmiFn viol_lmi_fn(int rp, bool smem) {
+  switch (rp) {
+    case 4: return smem ? viol_lmi_kernel<4, true> : viol_lmi_kernel<4, false>;
+    case 8: return smem ? viol_lmi_kernel<8, true> : viol_lmi_kernel<8, false>;
+    case 16: return smem ? viol_lmi_kernel<16, true> : viol_lmi_kernel<16, false>;
+    default: return smem ? viol_lmi_kernel<32, true> : viol_lmi_kernel<32, false>;
+  }
+}
 static size_t lmi_smem(int rp, bool smem, int n, int threads) {
   switch (rp) {
     case 4: return smem ? lmi_smem_bytes<4, true>(n, threads) : lmi_smem_bytes<4, false>(n, threads);
@@ -192,6 +203,10 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   if (d->lmi_r > 0 && d->off_lmi + static_cast<int64_t>(d->n) * d->lmi_rp * d->lmi_rp > d->blob_words)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "LMI section does not fit the block");
   if (d->blob_words > (1ll << 30)) return fail(RAYEN_ERR_UNSUPPORTED, "constant block too large");
+  if (d->off_viol < 0 || d->off_viol % 4 || d->off_viol >= d->blob_words || d->off_lmineg < d->off_viol || d->off_lmineg % 4 ||
+      d->off_lmineg >= d->blob_words || d->viol_in < 0 || d->viol_eq < 0 ||
+      (d->lmi_r > 0 && d->off_lmineg + static_cast<int64_t>(d->k + 1) * d->lmi_rp * d->lmi_rp > d->blob_words))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "violation sections do not fit the block");
   if (d->tc_panels < 1 || (d->tc_kp != 8 && d->tc_kp != 16 && d->tc_kp != 32) || d->tc_kp < d->np || d->off_tc % 4 ||
       d->off_tc < d->off_lmi ||
       d->off_tc + static_cast<int64_t>(d->tc_panels) * (24 + 2 * 96 * d->tc_kp) > d->blob_words)
@@ -240,6 +255,8 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   v.lqs_words = static_cast<int>(d->off_lmi - d->off_lin);
   v.lmi_words = d->lmi_r > 0 ? d->n * d->lmi_rp * d->lmi_rp : 0;
   v.off_tc = static_cast<int>(d->off_tc); v.tc_panels = d->tc_panels; v.tc_kp = d->tc_kp;
+  v.off_viol = static_cast<int>(d->off_viol); v.off_lmineg = static_cast<int>(d->off_lmineg);
+  v.viol_in = d->viol_in; v.viol_eq = d->viol_eq;
 
   p->has_lqs = d->n_quad > 0 || d->n_soc > 0;
   for (int64_t i = d->off_lin; i < d->off_quad && !p->has_lqs; ++i) p->has_lqs = d->blob[i] != 0.0f;
@@ -274,6 +291,10 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
     if (!p->lmi_smem) p->lmi_smem_bytes = lmi_smem(v.lmi_rp, false, v.n, p->lmi_fwd_threads);
     rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_fn(v.lmi_rp, p->lmi_smem, p->lmi_fwd_threads, false)), p->lmi_smem_bytes);
     p->lmi_grad_smem_bytes = lmi_smem(v.lmi_rp, p->lmi_smem, v.n, 256);
+    p->viol_lmi_smem_bytes = lmi_smem(v.lmi_rp, true, v.k + 1, kLmiThreads);
+    p->viol_lmi_smem = p->viol_lmi_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
+    if (!p->viol_lmi_smem) p->viol_lmi_smem_bytes = lmi_smem(v.lmi_rp, false, v.k + 1, kLmiThreads);
+    if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(viol_lmi_fn(v.lmi_rp, p->viol_lmi_smem)), p->viol_lmi_smem_bytes);
     if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_fn(v.lmi_rp, p->lmi_smem, 256, true)), p->lmi_grad_smem_bytes);
     p->lmi_bwd_smem_bytes = lmi_smem(v.lmi_rp, p->lmi_smem, v.n, kLmiThreads);
     if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_bwd_fn(v.lmi_rp, p->lmi_smem)), p->lmi_bwd_smem_bytes);
@@ -582,6 +603,39 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
   }
   if (prev != p->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return cuda_fail(e, "backward launch");
+  return RAYEN_OK;
+}
+
+// ----------------------------------------------------------------------------- violation metric
+extern "C" int rayen_violation_f32(const rayen_plan_t* p, const float* y, int64_t ldy, float* viol, int64_t B,
+                                   void* stream_) {
+  if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "null plan");
+  if (B < 0 || (B > 0 && (!y || !viol))) return fail(RAYEN_ERR_BAD_ARGUMENT, "bad arguments");
+  if (B == 0) return RAYEN_OK;
+  const PlanDev& d = p->dev;
+  if (ldy < d.k) return fail(RAYEN_ERR_BAD_ARGUMENT, "ldy=%lld < k=%d", static_cast<long long>(ldy), d.k);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int prev = 0;
+  RAYEN_CUDA(cudaGetDevice(&prev));
+  if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
+  const int warps = kViolThreads / 32;
+  long long grid = (B + warps - 1) / warps;
+  if (grid > static_cast<long long>(p->sm_count) * 8) grid = static_cast<long long>(p->sm_count) * 8;
+  const size_t smem = static_cast<size_t>(warps) * ((d.k + 3) / 4 * 4) * sizeof(float);
+  viol_lqs_kernel<<<static_cast<int>(grid), kViolThreads, smem, stream>>>(d, y, ldy, viol, B);
+  g_launches.fetch_add(1);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && d.lmi_r > 0) {
+    const int mpw = 32 / (d.lmi_rp / 4);
+    long long blocks = (B + static_cast<long long>(mpw) * (kLmiThreads / 32) - 1) / (static_cast<long long>(mpw) * (kLmiThreads / 32));
+    if (blocks > p->sm_count) blocks = p->sm_count;
+    ViolLmiFn f = viol_lmi_fn(d.lmi_rp, p->viol_lmi_smem);
+    f<<<static_cast<int>(blocks), kLmiThreads, p->viol_lmi_smem_bytes, stream>>>(d, y, ldy, viol, B);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+  }
+  if (prev != p->device) cudaSetDevice(prev);
+  if (e != cudaSuccess) return cuda_fail(e, "violation launch");
   return RAYEN_OK;
 }
 

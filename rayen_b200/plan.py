@@ -19,7 +19,7 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_NP = 32
 MAX_LMI = 32
 
@@ -110,11 +110,13 @@ class PackedPlan:
         return d
 
 
-def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None):
+def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None):
     """Pack a preprocessed feasible set.
 
     ``A_p, b_p, NA_E, yp, z0`` are the fields of ``ConvexConstraints`` (reference constraints.py:366-436),
     ``qcs`` = [(P,q,r)], ``socs`` = [(M,s,c,d)], ``lmi`` = [F_0..F_k] or None, all in the ambient space.
+    ``lin_rows`` = (A1, b1, A2, b2) of the original LinearConstraint (entries may be None); only the violation
+    checker uses them.  Without them the checker tests the same polyhedron through A_p, b_p and N.
     """
     f64 = lambda a: np.asarray(a, dtype=np.float64)
     A_p, N = f64(A_p), f64(NA_E)
@@ -310,6 +312,53 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None):
         add_f32(operand_layout(hi))
         add_f32(operand_layout(lo))
 
+    # ---- violation checker (rayen_violation_f32): the ORIGINAL constraints in the ambient space
+    k4 = (k + 3) // 4 * 4
+    if lin_rows is not None:
+        A1, b1, A2, b2 = lin_rows
+    else:  # same polyhedron from the preprocessed fields: A_p N'(y - yp) <= b_p and (I - N N')(y - yp) = 0
+        A1, b1 = A_p @ N.T, b_p + A_p @ N.T @ yp
+        proj = np.eye(k) - N @ N.T
+        A2, b2 = (proj, proj @ yp) if n < k else (None, None)
+
+    def rows_block(A, b):
+        if A is None:
+            return np.zeros((0, k4 + 4))
+        A, b = f64(A), f64(b).reshape(-1)
+        keep = np.any(A != 0, axis=1) | (b < 0)       # drop the reference's "no constraint" placeholder 0 <= 1
+        A, b = A[keep], b[keep]
+        blk = np.zeros((A.shape[0], k4 + 4))
+        blk[:, :k] = A
+        blk[:, k4] = b
+        return blk
+
+    vin, veq = rows_block(A1, b1), rows_block(A2, b2)
+    vparts = [vin.reshape(-1), veq.reshape(-1)]
+    for (P, q, r) in qcs:
+        Pp = np.zeros((k4, k4))
+        Pp[:k, :k] = f64(P)
+        qp = np.zeros(k4)
+        qp[:k] = f64(q).reshape(-1)
+        vparts += [Pp.reshape(-1), qp, np.array([float(np.asarray(r).reshape(-1)[0]), 0.0, 0.0, 0.0])]
+    for (M, s_, c, d) in socs:
+        M, s_, c = f64(M), f64(s_).reshape(-1), f64(c).reshape(-1)
+        cp = np.zeros(k4)
+        cp[:k] = c
+        rows = np.zeros((M.shape[0], k4 + 4))
+        rows[:, :k] = M
+        rows[:, k4] = s_
+        vparts += [np.array([float(M.shape[0]), float(np.asarray(d).reshape(-1)[0]), 0.0, 0.0]), cp, rows.reshape(-1)]
+    off_viol = add(np.concatenate(vparts) if sum(v.size for v in vparts) else np.zeros(4))
+    viol_in, viol_eq = vin.shape[0], veq.shape[0]
+    off_lmineg = add(np.zeros(4))
+    if lmi is not None:
+        # lambda_max(-F(y)) = -lambda_min(F(y)): the same solver on the k+1 matrices -F_0..-F_k with u = (y, 1)
+        allF = np.asarray([f64(F) for F in lmi])
+        lpm = lmi_rp // 4
+        Fneg = np.zeros((k + 1, lmi_rp, lmi_rp))
+        Fneg[:, :lmi_r, :lmi_r] = -0.5 * (allF + allF.transpose(0, 2, 1))
+        off_lmineg = add(Fneg.reshape(k + 1, lmi_rp, 4, lpm).transpose(0, 1, 3, 2))
+
     blob = np.concatenate(sections).astype(np.float32)
     assert blob.size == cursor and cursor % 4 == 0
     for off, arr in exact:
@@ -320,7 +369,8 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None):
                        lin_chunk_stride=lin_stride, quad_stride=quad_stride, soc_stride=soc_stride,
                        off_lin=off_lin, off_quad=off_quad, off_soc=off_soc, off_nmat=off_nmat,
                        off_y0=off_y0, off_bound=off_bound, off_lmi=off_lmi, lmi_prune=int(lmi is not None),
-                       off_tc=off_tc, tc_panels=tc_panels, tc_kp=kp)
+                       off_tc=off_tc, tc_panels=tc_panels, tc_kp=kp,
+                       off_viol=off_viol, off_lmineg=off_lmineg, viol_in=viol_in, viol_eq=viol_eq)
     plan.f64 = dict(D=D, N=N, y0=y0, z0=z0, yp=yp, quads=quad_f64, socs=soc_f64, Fz=Fz)
     return plan
 
@@ -330,7 +380,9 @@ def build_plan_from_constraints(cs):
     qcs = [(qc.P, qc.q, qc.r) for qc in cs.qcs]
     socs = [(sc.M, sc.s, sc.c, sc.d) for sc in cs.socs]
     lmi = list(cs.lmic.all_F) if cs.lmic is not None else None
-    return build_plan(cs.A_p, cs.b_p, cs.NA_E, cs.yp, cs.z0, qcs, socs, lmi)
+    lc = getattr(cs, "lc", None)
+    lin_rows = (lc.A1, lc.b1, lc.A2, lc.b2) if lc is not None else (None, None, None, None)
+    return build_plan(cs.A_p, cs.b_p, cs.NA_E, cs.yp, cs.z0, qcs, socs, lmi, lin_rows=lin_rows)
 
 
 # --------------------------------------------------------------------------- numpy model of the kernels

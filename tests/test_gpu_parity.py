@@ -302,6 +302,33 @@ def test_tensor_core_and_fp32_pipe_kernels_agree():
         assert rel(y_tc, cf["y"]) <= TOL and rel(y_fp, cf["y"]) <= TOL
 
 
+@pytest.mark.parametrize("which", ["readme", 13, 11, 6, "cfg3", "cfg5"])
+def test_gpu_violation_metric(which):
+    """rayen_violation_f32 against the float64 residuals of the original constraints, on feasible outputs of the
+    layer and on arbitrary (infeasible) points."""
+    spec = synthetic.config_spec(which) if isinstance(which, str) and which.startswith("cfg") else synthetic.example_spec(which)
+    cs = synthetic.build_constraints(spec)
+    layer = ConstraintModule(cs, create_map=False).to(DEV)
+    v, _ = synthetic.sample_inputs(700, cs.n, cs.k, scale=4.0)
+    y_feas = layer(v.to(DEV).unsqueeze(2))[:, :, 0]
+    gen = torch.Generator().manual_seed(3)
+    y_rand = (torch.rand(700, cs.k, generator=gen) * 2 - 1) * 2.0 + torch.tensor(cs.y0.T, dtype=torch.float32)
+    for yy in (y_feas, y_rand.to(DEV)):
+        got = layer.violation(yy.unsqueeze(2)).cpu().double().numpy()
+        ref = cs.residuals(yy.cpu().double().numpy().T)
+        if cs.lmic is not None:      # the kernel reports relu(-lambda_min) for the LMI part
+            lmi = np.maximum(cs.lmic.residual(yy.cpu().double().numpy().T), 0.0)
+            others = np.full(len(ref), -np.inf)
+            if cs.lc is not None:
+                others = np.maximum(others, cs.lc.residual(yy.cpu().double().numpy().T))
+            for c in list(cs.qcs) + list(cs.socs):
+                others = np.maximum(others, c.residual(yy.cpu().double().numpy().T))
+            ref = np.maximum(others, lmi)
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert np.abs(got - ref).max() <= 2e-5 * scale, which
+    assert float(layer.violation(y_feas).max()) <= 1e-5
+
+
 def test_host_buffer_path_matches_device_path():
     spec = synthetic.config_spec("cfg5")
     spec["b1"] = spec["b1"] * 4.0
