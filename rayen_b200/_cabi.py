@@ -10,8 +10,9 @@ import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "librayen_b200.so")
-SOURCES = ["rayen_b200.cu", "lqs.cuh", "lqs_tc.cuh", "lmi.cuh", "common.cuh"]
+# RAYEN_B200_LIB points development scripts at an instrumented build of the same sources (scripts/lmi_trace.py)
+LIB_PATH = os.environ.get("RAYEN_B200_LIB") or os.path.join(CSRC, "librayen_b200.so")
+SOURCES = ["rayen_b200.cu", "lqs.cuh", "lqs_tc.cuh", "lmi.cuh", "viol.cuh", "common.cuh"]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "rayen_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]

@@ -22,6 +22,18 @@
 
 namespace rayen {
 
+#ifdef RAYEN_LMI_TRACE
+// development build only (scripts/lmi_trace.py): phase time stamps of warp 0 / warp 7 of the first CTAs
+__device__ long long g_lmi_trace[4096];
+#define LMI_STAMP(slot)                                                                      \
+  do {                                                                                       \
+    if (blockIdx.x < 16 && (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) == 0 || (threadIdx.x >> 5) == 7)) \
+      g_lmi_trace[blockIdx.x * 64 + ((threadIdx.x >> 5) ? 32 : 0) + (slot)] = clock64();     \
+  } while (0)
+#else
+#define LMI_STAMP(slot) do { } while (0)
+#endif
+
 constexpr int kLmiThreads = 256;     // backward kernel (keeps the reflectors: needs the registers)
 constexpr int kLmiFwdThreads = 256;  // forward kernel default (384 = 12 warps/SM with spills: RAYEN_LMI_THREADS=384)
 constexpr int kLmiMaxN = 32;
@@ -34,7 +46,7 @@ struct LmiCfg {
   static constexpr int ROUNDS = 8;               // 9^8 = 4.3e7 > 2^25
   // scratch floats per matrix; the pad makes consecutive matrices start LPM (>= 4) banks apart so that
   // neither the float4 broadcasts nor the scalar stores of the matrices of one warp collide
-  static constexpr int SCR = kLmiMaxN + 6 * RP + (LPM >= 4 ? LPM : 4);
+  static constexpr int SCR = kLmiMaxN + 7 * RP + (LPM >= 4 ? LPM : 4);
   static constexpr int NPL = kLmiMaxN / LPM;     // entries of an n-vector per lane
 };
 
@@ -45,7 +57,7 @@ __device__ __forceinline__ int group_or(int x) {
   return x;
 }
 
-// scratch layout (floats): [0,32) u | v | w | d | e | aux0 | aux1   (each RP long after u)
+// scratch layout (floats): [0,32) u | v | w | d | e | aux0 | aux1 | tau   (each RP long after u)
 template <int RP, bool WANT_GRAD, bool F_SMEM>
 struct LmiSolver {
   using C = LmiCfg<RP>;
@@ -63,6 +75,7 @@ struct LmiSolver {
   __device__ __forceinline__ float* se() { return scr + kLmiMaxN + 3 * RP; }
   __device__ __forceinline__ float* sx0() { return scr + kLmiMaxN + 4 * RP; }
   __device__ __forceinline__ float* sx1() { return scr + kLmiMaxN + 5 * RP; }
+  __device__ __forceinline__ float* stau() { return scr + kLmiMaxN + 6 * RP; }  // 2 / |v_k|^2 of reflector k
 
   // ---- 0. u = v / max(|v|, eps) into the scratch; returns |v|
   __device__ __forceinline__ float load_direction(const float* __restrict__ vrow, int n, bool valid) {
@@ -171,7 +184,10 @@ struct LmiSolver {
         const float alpha = (xk1 >= 0.f) ? -rt : rt;
         const bool skip = !(tail2 > 0.f);  // column already tridiagonal (also covers zero padding)
         const float tau = skip ? 0.f : 1.0f / fmaf(fabsf(xk1), rt, sigma);
-        if (q == kk) se()[k] = skip ? xk1 : alpha;
+        if (q == kk) {
+          se()[k] = skip ? xk1 : alpha;
+          if constexpr (WANT_GRAD) stau()[k] = tau;  // = 2 / v'v: the back-transform needs no second reduction
+        }
         float vo[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) vo[t] = 0.f;
@@ -295,11 +311,11 @@ struct LmiSolver {
         }
       }
     }
-    // Work on T / scale so that |d_i - x| <= 2 and e_i^2 <= 1, in the PRODUCT form of the Sturm sequence
-    //   p_0 = 1, p_1 = d_0 - x, p_{i+1} = (d_i - x) p_i - e_i^2 p_{i-1}
-    // (two dependent FMAs per step instead of a reciprocal): x is above the whole spectrum iff consecutive
-    // p's strictly alternate in sign.  Only signs matter, so (p_{i-1}, p_i) is rescaled by a positive power of
-    // two every 4 steps to stay clear of overflow / underflow.
+    // Work on T / scale so that |d_i - x| <= 2 and e_i^2 <= 1, in the PRODUCT form of the Sturm sequence with the
+    // alternating sign folded in:  s_0 = 1, s_1 = x - d_0, s_{i+1} = (x - d_i) s_i - e_i^2 s_{i-1}
+    // (s_i = (-1)^i det(T_i - x I); two dependent FMAs per step instead of a reciprocal): x is above the whole
+    // spectrum iff every s_i is strictly positive, i.e. iff the running minimum is.  Only signs matter, so
+    // (s_{i-1}, s_i) is rescaled by a positive power of two every 4 steps to stay clear of overflow / underflow.
     const float scale = fmaxf(fmaxf(fabsf(hi), fabsf(lo_g)), 1e-30f);
     const float inv_scale = 1.0f / scale;
 #pragma unroll
@@ -318,22 +334,22 @@ struct LmiSolver {
       for (int pp = 0; pp < C::PPL; ++pp) {
         const int pt = q * C::PPL + pp;
         const float x = fmaf(h, static_cast<float>(pt + 1), lo);
-        float p0 = 1.f, p1 = d[0] - x;
-        bool above = p1 < 0.f;
+        float s0 = 1.f, s1 = x - d[0];
+        float mn = s1;
 #pragma unroll
         for (int i = 1; i < RP; ++i) {
-          const float pn = fmaf(d[i] - x, p1, -e2[i] * p0);
-          above = above && ((__float_as_int(pn) ^ __float_as_int(p1)) < 0) && (pn != 0.f);
-          p0 = p1;
-          p1 = pn;
-          if ((i & 3) == 3) {
-            const int ex = (__float_as_int(fmaxf(fabsf(p0), fabsf(p1))) >> 23) & 0xff;
+          const float sn = fmaf(x - d[i], s1, -e2[i] * s0);
+          mn = fminf(mn, sn);
+          s0 = s1;
+          s1 = sn;
+          if ((i & 3) == 3 && i + 1 < RP) {
+            const int ex = (__float_as_int(fmaxf(fabsf(s0), fabsf(s1))) >> 23) & 0xff;
             const float sc = __int_as_float((254 - max(min(ex, 253), 1)) << 23);
-            p0 *= sc;
-            p1 *= sc;
+            s0 *= sc;
+            s1 *= sc;
           }
         }
-        bits |= above ? (1 << pt) : 0;
+        bits |= (mn > 0.f) ? (1 << pt) : 0;
       }
       const int mask = group_or<LPM>(bits) & 0xff;
       const int first = mask ? (__ffs(mask) - 1) : 8;
@@ -354,52 +370,109 @@ struct LmiSolver {
     float* dp = sx0();
     float* dm = sx1();
     float* z = sv();
-    if (q == 0) {
-      const float* d = sd();
-      const float* e = se();
-      float scale = 0.f;
-      for (int i = 0; i < RP; ++i) scale = fmaxf(scale, fabsf(d[i]) + fabsf(e[i]));
-      const float tiny = fmaxf(1e-12f * scale, 1e-30f);
-      float piv = d[0] - lam;
-      for (int i = 0; i < RP; ++i) {
-        if (i > 0) piv = (d[i] - lam) - e[i - 1] * e[i - 1] / piv;
-        if (fabsf(piv) < tiny) piv = -tiny;
-        dp[i] = piv;
-      }
-      piv = d[RP - 1] - lam;
-      for (int i = RP - 1; i >= 0; --i) {
-        if (i < RP - 1) piv = (d[i] - lam) - e[i] * e[i] / piv;
-        if (fabsf(piv) < tiny) piv = -tiny;
-        dm[i] = piv;
-      }
-      int kt = 0;
-      float best = 3.0e38f;
-      for (int i = 0; i < RP; ++i) {
-        const float gam = fabsf(dp[i] + dm[i] - (d[i] - lam));
-        if (gam < best) {
-          best = gam;
-          kt = i;
+    float* rr = sw();  // recurrence ratios of z (the w scratch is free after the tridiagonalisation)
+    const float* d = sd();
+    const float* e = se();
+    // Gershgorin-type scale, every lane for itself (RP independent loads, no cross-lane traffic)
+    float scale = 0.f;
+#pragma unroll
+    for (int i4 = 0; i4 < RP / 4; ++i4) {
+      const float4 dv = ld4(d + 4 * i4), ev = ld4(e + 4 * i4);
+      scale = fmaxf(scale, fmaxf(fmaxf(fabsf(dv.x) + fabsf(ev.x), fabsf(dv.y) + fabsf(ev.y)),
+                                 fmaxf(fabsf(dv.z) + fabsf(ev.z), fabsf(dv.w) + fabsf(ev.w))));
+    }
+    const float tiny = fmaxf(1e-12f * scale, 1e-30f);
+    // the two pivot recurrences of the twisted factorisation run on two different lanes at the same time
+    constexpr int QB = (LPM > 1) ? 1 : 0;  // lane of the backward recurrence
+    // (same instruction stream, direction chosen per lane: divergent branches would serialise them)
+    auto pivots = [&](bool fw) {
+      float* out = fw ? dp : dm;
+      const int di = fw ? 1 : -1;
+      int i = fw ? 0 : RP - 1;
+      float piv = d[i] - lam;
+#pragma unroll 8
+      for (int t = 0; t < RP; ++t) {
+        if (t > 0) {
+          const float ee = fw ? e[i - 1] : e[i];
+          piv = fmaf(-ee * ee, __frcp_rn(piv), d[i] - lam);
         }
+        if (fabsf(piv) < tiny) piv = -tiny;
+        out[i] = piv;
+        i += di;
       }
-      z[kt] = 1.f;
-      float zi = 1.f, nrm = 1.f;
-      for (int i = kt; i > 0; --i) {
-        zi = -e[i - 1] * zi / dp[i - 1];
-        z[i - 1] = zi;
-        nrm = fmaf(zi, zi, nrm);
+    };
+    if constexpr (QB == 0) {
+      if (q == 0) {
+        pivots(true);
+        pivots(false);
       }
-      zi = 1.f;
-      for (int i = kt; i < RP - 1; ++i) {
-        zi = -e[i] * zi / dm[i + 1];
-        z[i + 1] = zi;
-        nrm = fmaf(zi, zi, nrm);
-      }
-      const float inv = rsqrtf(nrm);
-      for (int i = 0; i < RP; ++i) z[i] *= inv;
+    } else {
+      if (q <= QB) pivots(q == 0);
     }
     __syncwarp();
+    // twist index: argmin_i |dp_i + dm_i - (d_i - lam)|, lowest index on ties; every lane looks at its 4 entries
+    float best = 3.0e38f;
+    int kt = 0;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) qo[t] = z[q + LPM * t];
+    for (int t = 0; t < 4; ++t) {
+      const int i = q + LPM * t;
+      const float gam = fabsf(dp[i] + dm[i] - (d[i] - lam));
+      if (gam < best) {
+        best = gam;
+        kt = i;
+      }
+    }
+#pragma unroll
+    for (int off = LPM >> 1; off > 0; off >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int ok = __shfl_xor_sync(0xffffffffu, kt, off);
+      if (ob < best || (ob == best && ok < kt)) {
+        best = ob;
+        kt = ok;
+      }
+    }
+    // z_{i-1} = -e_{i-1}/dp_{i-1} z_i below the twist, z_{i+1} = -e_i/dm_{i+1} z_i above it: the ratios are
+    // independent of each other, so all lanes compute them first and the serial part is one multiply per entry
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = q + LPM * t;
+      float r = 0.f;
+      if (i < kt) r = -e[i] * __frcp_rn(dp[i]);                 // multiplies z_{i+1} to give z_i
+      else if (i > kt) r = -e[i - 1] * __frcp_rn(dm[i]);        // multiplies z_{i-1} to give z_i
+      rr[i] = r;
+    }
+    __syncwarp();
+    float nrm = 0.f;
+    auto fill = [&](bool down) {
+      const int di = down ? -1 : 1;
+      float zi = 1.f;
+      int i = kt + di;
+      for (int t = 1; t < RP; ++t) {
+        if (i >= 0 && i < RP) {
+          zi *= rr[i];
+          z[i] = zi;
+          nrm = fmaf(zi, zi, nrm);
+        }
+        i += di;
+      }
+    };
+    if constexpr (QB == 0) {
+      if (q == 0) {
+        fill(true);
+        fill(false);
+      }
+    } else {
+      if (q <= QB) fill(q == 0);
+    }
+    if (q == 0) {
+      z[kt] = 1.f;
+      nrm += 1.f;
+    }
+    nrm = group_sum<LPM>(nrm);  // lanes other than 0 / QB contribute 0
+    const float inv = rsqrtf(nrm);
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) qo[t] = z[q + LPM * t] * inv;
     // q = H_0 ... H_{RP-3} z; reflector k sits in row k of A (this lane's columns)
     back_stage<3>(qo);
     back_stage<2>(qo);
@@ -424,15 +497,10 @@ struct LmiSolver {
 #pragma unroll
             for (int t = S; t < 4; ++t) r[t] = A[i][t];
           }
-        float dot = 0.f, vv = 0.f;
+        float dot = 0.f;
 #pragma unroll
-        for (int t = S; t < 4; ++t) {
-          dot = fmaf(r[t], qo[t], dot);
-          vv = fmaf(r[t], r[t], vv);
-        }
-        dot = group_sum<LPM>(dot);
-        vv = group_sum<LPM>(vv);
-        const float c = vv > 0.f ? 2.0f * dot / vv : 0.f;
+        for (int t = S; t < 4; ++t) dot = fmaf(r[t], qo[t], dot);
+        const float c = stau()[k] * group_sum<LPM>(dot);  // tau_k = 2 / v_k'v_k (0 for a skipped step)
 #pragma unroll
         for (int t = S; t < 4; ++t) qo[t] = fmaf(-c, r[t], qo[t]);
       }
@@ -529,7 +597,9 @@ __global__ void __launch_bounds__(THREADS, 1)
   const long long total = work_list ? static_cast<long long>(*work_count) : B;
   // chunk c (MPW samples) belongs to CTA c % gridDim: a CTA without a chunk does not stage F~z at all
   const bool cta_has_work = static_cast<long long>(blockIdx.x) * C::MPW < total;
+  LMI_STAMP(0);
   const float* F = lmi_stage<RP, F_SMEM>(P, smem_raw, bars, &scratch_base, cta_has_work);
+  LMI_STAMP(1);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   LmiSolver<RP, WITH_GRAD, F_SMEM> S;
@@ -550,14 +620,20 @@ __global__ void __launch_bounds__(THREADS, 1)
     const long long idx = base + grp;
     const bool valid = idx < total;
     const long long b = valid ? (work_list ? static_cast<long long>(work_list[idx]) : idx) : 0;
+    LMI_STAMP(2);
     const float s = S.load_direction(v + b * ldv, n, valid);
+    LMI_STAMP(3);
     if (!staged) {
       mbar_wait(&bars[0], 0);
       staged = true;
     }
+    LMI_STAMP(4);
     S.contract(F, n);
+    LMI_STAMP(5);
     S.tridiagonalize();
+    LMI_STAMP(6);
     const float lam = S.lambda_max_relu();
+    LMI_STAMP(7);
     float kap = fmaxf(lam, 0.f);
     int tag = kap > 0.f ? make_tag(RAYEN_FAM_LMI, 0) : make_tag(RAYEN_FAM_NONE, 0);
     if (has_prior && valid) {
@@ -592,6 +668,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
       }
     }
+    LMI_STAMP(8);
     if constexpr (WITH_GRAD) {
       bool need = valid && tag_family(tag) == RAYEN_FAM_LMI && kap > 0.f;
       if (need && mode == RAYEN_MODE_RAYEN) need = (1.0f / kap < s);
@@ -599,8 +676,10 @@ __global__ void __launch_bounds__(THREADS, 1)
         __syncwarp();
         float qo[4];
         S.eigenvector(lam, qo);
+        LMI_STAMP(9);
         float dk[C::NPL];
         S.eig_gradient(F, n, qo, dk);
+        LMI_STAMP(10);
         if (need) {
 #pragma unroll
           for (int sl = 0; sl < C::NPL; ++sl) {
@@ -611,6 +690,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
     }
     __syncwarp();  // the scratch (u) is rewritten by the next sample
+    LMI_STAMP(11);
   }
   if constexpr (F_SMEM) {
     if (!staged && cta_has_work) mbar_wait(&bars[0], 0);  // never exit with a bulk copy in flight

@@ -356,6 +356,15 @@ extern "C" int rayen_tc_trace_dump(void) {
 }
 #endif
 
+#ifdef RAYEN_LMI_TRACE
+// development build only: copies the phase stamps of lmi_forward_kernel (see LMI_STAMP) to `out` (4096 values)
+extern "C" int rayen_lmi_trace_read(long long* out) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out, rayen::g_lmi_trace, sizeof(long long) * 4096);
+  return static_cast<int>(e);
+}
+#endif
+
 extern "C" int rayen_plan_set_pruning(rayen_plan_t* p, int enabled) {
   if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "null plan");
   p->prune = enabled && p->has_lqs && p->dev.lmi_prune;
