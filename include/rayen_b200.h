@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RAYEN_ABI_VERSION 7
+#define RAYEN_ABI_VERSION 8
 
 /* error codes (negative); positive return values are cudaError_t */
 #define RAYEN_OK 0
@@ -72,6 +72,10 @@ extern "C" {
  *   VIOL    the ORIGINAL constraints in the ambient space for rayen_violation_f32 (k4 = k rounded up to 4):
  *           viol_in rows {a[k4], b, 0,0,0} of A1 y <= b1, viol_eq rows of A2 y = b2, per quadratic
  *           {P[k4][k4], q[k4], r,0,0,0}, per cone {r_M, d, 0, 0, c[k4], r_M rows {M_i[k4], s_i,0,0,0}}
+ *   LMITC   (lmi_rp >= 16) the LMI matrices again as the B operand of the contraction GEMM S = U W' (lmi_tc.cuh):
+ *           lmitc_panels = rp*rp/128 panels of 128 entries, entry e = i*rp + 4q + t <-> F~z_a[i][q + (rp/4)*t]
+ *           (the LMI section's order), per panel W_hi and W_lo (128 x tc_kp each, TF32 split) in the operand
+ *           layout [k/4][row/8][row%8][k%4]
  *   LMINEG  -F_0 .. -F_k laid out like LMI ([a][row][lane][slot]): lambda_max(sum_a (y,1)_a (-F_a)) = -lambda_min(F(y))
  */
 typedef struct RayenPlanDesc {
@@ -95,7 +99,9 @@ typedef struct RayenPlanDesc {
   int32_t tc_kp;     /* K of the tensor-core GEMM: max(8, np) */
   int32_t viol_in;   /* inequality rows of the VIOL section */
   int32_t viol_eq;   /* equality rows of the VIOL section */
-  int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi, off_tc, off_viol, off_lmineg;
+  int32_t lmitc_panels; /* 128-entry panels of the LMITC section (0: none) */
+  int32_t reserved0;
+  int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi, off_tc, off_viol, off_lmineg, off_lmitc;
   int64_t blob_words;
   const float* blob; /* host pointer, blob_words floats */
 } RayenPlanDesc;
@@ -119,6 +125,11 @@ int rayen_plan_set_tuning(rayen_plan_t* plan, int samples_per_thread, int lanes_
 int rayen_plan_set_pruning(rayen_plan_t* plan, int enabled);
 /* Linear/quadratic/SOC forward on the tensor cores (tcgen05 3xTF32 GEMM, default) or on the FP32 pipe (0). */
 int rayen_plan_set_tensor_cores(rayen_plan_t* plan, int enabled);
+/* LMI contraction sum_a u_a F~z_a (reference constraint_module.py:412-421) as a tcgen05 3xTF32 GEMM inside the LMI
+ * forward kernel (lmi_tc.cuh; needs lmi_rp >= 16) or on the FP32 pipe out of shared memory (lmi.cuh).
+ * mode: 0 never, 1 wherever available, 2 automatic (default): the measured policy -- tensor cores when K = 32 and
+ * the call carries no gradient work.  RAYEN_LMI_TC=0/1/2 sets the default of new plans. */
+int rayen_plan_set_lmi_tensor_cores(rayen_plan_t* plan, int mode);
 
 /* Device scratch the forward / backward calls need for a batch of B samples (work lists of the samples
  * that still need the LMI kernels, and d kappa/du of the LMI-bound samples).  0 for plans without an LMI.  The caller owns the buffer; it must
@@ -160,9 +171,12 @@ int rayen_backward_stage_f32(const rayen_plan_t* plan, const float* v, int64_t l
                              const float* kappa, const int32_t* active, float* gv, int64_t ldgv, int64_t B,
                              int mode, int have_dkappa, int stage_mask, void* workspace, void* cuda_stream);
 
-/* Host-buffer variants (the end-to-end path): host->device copies, the kernels, device->host
- * copies, all on `cuda_stream`, which is synchronised before returning.  Host buffers should be
- * pinned.  `workspace` is a device buffer of rayen_host_workspace_bytes(plan, B) bytes. */
+/* Host-buffer variant (the end-to-end path): the batch is cut into chunks; host->device copies run on an internal
+ * copy-in stream, the kernels on `cuda_stream`, device->host copies on an internal copy-out stream, so that the two
+ * directions of the link and the SMs work at the same time.  Everything is ordered after what the caller queued on
+ * `cuda_stream`, which is complete (and synchronised) when the call returns.  Host buffers should be pinned.
+ * `workspace` is a device buffer of rayen_host_workspace_bytes(plan, B) bytes.  Calls on one plan are serialised
+ * (the copy streams belong to the plan); RAYEN_HOST_CHUNKS=1..8 overrides the chunk count. */
 int64_t rayen_host_workspace_bytes(const rayen_plan_t* plan, int64_t B);
 int rayen_forward_backward_host_f32(const rayen_plan_t* plan, const float* v_host, const float* gy_host,
                                     float* y_host, float* gv_host, int64_t B, void* workspace,

@@ -12,12 +12,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # RAYEN_B200_LIB points development scripts at an instrumented build of the same sources (scripts/lmi_trace.py)
 LIB_PATH = os.environ.get("RAYEN_B200_LIB") or os.path.join(CSRC, "librayen_b200.so")
-SOURCES = ["rayen_b200.cu", "lqs.cuh", "lqs_tc.cuh", "lmi.cuh", "viol.cuh", "common.cuh"]
+SOURCES = ["rayen_b200.cu", "lqs.cuh", "lqs_tc.cuh", "lmi.cuh", "lmi_tc.cuh", "viol.cuh", "common.cuh"]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "rayen_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MODE_RAYEN, MODE_RAYEN_OLD = 0, 1
 FAM_NONE, FAM_LINEAR, FAM_QUAD, FAM_SOC, FAM_LMI = 0, 1, 2, 3, 4
 
@@ -26,10 +26,10 @@ class RayenPlanDesc(ctypes.Structure):
     _fields_ = [(name, ctypes.c_int32) for name in (
         "abi_version", "n", "k", "np", "k_pad", "m", "m_pad", "n_quad", "n_soc", "lmi_r", "lmi_rp",
         "n_is_identity", "lin_chunk_stride", "quad_stride", "soc_stride", "lmi_prune", "tc_panels", "tc_kp",
-        "viol_in", "viol_eq")] + [
+        "viol_in", "viol_eq", "lmitc_panels", "reserved0")] + [
         (name, ctypes.c_int64) for name in (
             "off_lin", "off_quad", "off_soc", "off_nmat", "off_y0", "off_bound", "off_lmi", "off_tc", "off_viol",
-            "off_lmineg", "blob_words")] + [
+            "off_lmineg", "off_lmitc", "blob_words")] + [
         ("blob", ctypes.POINTER(ctypes.c_float))]
 
 
@@ -49,6 +49,7 @@ SYMBOLS = {
     "rayen_plan_set_tuning": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int]),
     "rayen_plan_set_pruning": (ctypes.c_int, [_P, ctypes.c_int]),
     "rayen_plan_set_tensor_cores": (ctypes.c_int, [_P, ctypes.c_int]),
+    "rayen_plan_set_lmi_tensor_cores": (ctypes.c_int, [_P, ctypes.c_int]),
     "rayen_workspace_bytes": (ctypes.c_int64, [_P, ctypes.c_int64]),
     "rayen_forward_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, ctypes.c_int64, ctypes.c_int,
                                          ctypes.c_int, _P, _P]),
@@ -145,6 +146,11 @@ class DevicePlan:
 
     def set_tensor_cores(self, enabled=True):
         check(lib().rayen_plan_set_tensor_cores(self._handle, 1 if enabled else 0), "rayen_plan_set_tensor_cores")
+
+    def set_lmi_tensor_cores(self, mode):
+        """0 / False: never, 1 / True: wherever available, 2 / None: automatic."""
+        mode = 2 if mode is None else int(mode)
+        check(lib().rayen_plan_set_lmi_tensor_cores(self._handle, mode), "rayen_plan_set_lmi_tensor_cores")
 
     def workspace_bytes(self, batch):
         return int(lib().rayen_workspace_bytes(self._handle, int(batch)))

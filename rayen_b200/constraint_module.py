@@ -284,6 +284,12 @@ class ConstraintModule(nn.Module):
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._device_plan(device).set_tensor_cores(enabled)
 
+    def set_lmi_tensor_cores(self, mode=None, device=None):
+        """LMI contraction ``sum_a u_a F_a`` as a tcgen05 GEMM inside the LMI kernel (True / 1: wherever the LMI is
+        larger than 8x8), on the FP32 pipe (False / 0), or by the measured policy (None / 2, the default)."""
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._device_plan(device).set_lmi_tensor_cores(mode)
+
     def violation(self, y):
         """Max constraint residual of every sample of ``y`` ([B, k] or [B, k, 1], CUDA) against the original
         constraints, computed on the GPU by ``rayen_violation_f32`` (<= 0 means feasible)."""

@@ -19,6 +19,7 @@ struct PlanDev {
   int lmi_words;   // n * rp * rp
   int off_tc, tc_panels, tc_kp;  // tensor-core section (see rayen_b200.h)
   int off_viol, off_lmineg, viol_in, viol_eq;  // violation checker sections
+  int off_lmitc, lmitc_panels, lmitc_stages;   // LMI matrices as a tcgen05 B operand (lmi_tc.cuh); ring depth
 };
 
 constexpr int kFamShift = 24;

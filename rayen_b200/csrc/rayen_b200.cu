@@ -10,6 +10,7 @@
 #include <new>
 
 #include "lmi.cuh"
+#include "lmi_tc.cuh"
 #include "lqs.cuh"
 #include "lqs_tc.cuh"
 #include "viol.cuh"
@@ -33,6 +34,18 @@ struct rayen_plan {
   bool prune;     // LMI pruning enabled (needs has_lqs and a BOUND section)
   bool use_tc;    // tensor-core (tcgen05) linear/quadratic/SOC forward kernel
   size_t tc_smem_bytes;
+  int lmi_tc_mode;        // LMI contraction as a tcgen05 GEMM inside the LMI forward kernel (lmi_tc.cuh):
+                          // 0 never, 1 wherever available, 2 automatic (the measured policy in lmi_use_tc)
+  bool lmi_tc_ok;         // ... available for this plan (rp >= 16, section present, fits in shared memory)
+  bool lmi_tc_grad_fsmem; // the gradient variant keeps F~z in shared memory next to the GEMM buffers
+  size_t lmi_tc_smem_bytes, lmi_tc_grad_smem_bytes;
+  // host-buffer path only (rayen_forward_backward_host_f32): copy streams and events, created on first use and
+  // serialised by host_mu -- the device-pointer entry points never touch them, so the plan stays re-entrant there
+  std::mutex* host_mu;
+  cudaStream_t host_in, host_out;
+  cudaEvent_t host_ev[2 * 8 + 2];
+  bool host_ready;
+  int host_chunks;  // 0 = automatic (RAYEN_HOST_CHUNKS overrides)
 };
 
 static thread_local char g_err[512] = "";
@@ -130,6 +143,17 @@ static LmiFwdFn lmi_fwd_fn(int rp, bool smem, int threads, bool grad) {
   if (grad) return lmi_fwd_fn_t<256, true>(rp, smem);
   return threads == 384 ? lmi_fwd_fn_t<384, false>(rp, smem) : lmi_fwd_fn_t<256, false>(rp, smem);
 }
+static LmiFwdFn lmi_fwd_tc_fn(int rp, bool fsmem, bool grad) {
+  if (rp == 16) {
+    if (!grad) return lmi_forward_tc_kernel<16, false, false>;
+    return fsmem ? lmi_forward_tc_kernel<16, true, true> : lmi_forward_tc_kernel<16, false, true>;
+  }
+  if (!grad) return lmi_forward_tc_kernel<32, false, false>;
+  return fsmem ? lmi_forward_tc_kernel<32, true, true> : lmi_forward_tc_kernel<32, false, true>;
+}
+static size_t lmi_tc_smem(int rp, int n, int kp, int stages, bool fsmem) {
+  return rp == 16 ? lmi_tc_smem_bytes<16>(n, kp, stages, fsmem) : lmi_tc_smem_bytes<32>(n, kp, stages, fsmem);
+}
 static LmiBwdFn lmi_bwd_fn(int rp, bool smem) {
   switch (rp) {
     case 4: return smem ? lmi_backward_kernel<4, true> : lmi_backward_kernel<4, false>;
@@ -212,6 +236,11 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
       d->off_tc + static_cast<int64_t>(d->tc_panels) * (24 + 2 * 96 * d->tc_kp) > d->blob_words)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "tensor-core section does not fit the block");
 
+  if (d->lmitc_panels < 0 || d->off_lmitc < 0 || d->off_lmitc % 4 || d->off_lmitc >= d->blob_words ||
+      (d->lmitc_panels > 0 && (d->lmi_rp < 16 || d->lmitc_panels != d->lmi_rp * d->lmi_rp / 128 ||
+                               d->off_lmitc + static_cast<int64_t>(d->lmitc_panels) * 2 * 128 * d->tc_kp > d->blob_words)))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "LMI tensor-core section does not fit the block");
+
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
     return fail(RAYEN_ERR_NO_DEVICE, "CUDA device %d is not available (%d devices visible)", device, count);
@@ -230,6 +259,12 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "out of host memory");
   memset(p, 0, sizeof(*p));
   p->device = device;
+  p->host_mu = new (std::nothrow) std::mutex();
+  {
+    const char* env = getenv("RAYEN_HOST_CHUNKS");
+    p->host_chunks = env ? atoi(env) : 0;
+    if (p->host_chunks < 0 || p->host_chunks > 8) p->host_chunks = 0;
+  }
   p->sm_count = prop.multiProcessorCount;
   p->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
   cudaError_t e = cudaMalloc(&p->d_blob, d->blob_words * sizeof(float));
@@ -237,6 +272,7 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
     e = cudaMemcpy(p->d_blob, d->blob, d->blob_words * sizeof(float), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     if (p->d_blob) cudaFree(p->d_blob);
+    delete p->host_mu;
     delete p;
     cudaSetDevice(prev);
     return cuda_fail(e, "uploading the constant block");
@@ -257,6 +293,7 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   v.off_tc = static_cast<int>(d->off_tc); v.tc_panels = d->tc_panels; v.tc_kp = d->tc_kp;
   v.off_viol = static_cast<int>(d->off_viol); v.off_lmineg = static_cast<int>(d->off_lmineg);
   v.viol_in = d->viol_in; v.viol_eq = d->viol_eq;
+  v.off_lmitc = static_cast<int>(d->off_lmitc); v.lmitc_panels = d->lmitc_panels;
 
   p->has_lqs = d->n_quad > 0 || d->n_soc > 0;
   for (int64_t i = d->off_lin; i < d->off_quad && !p->has_lqs; ++i) p->has_lqs = d->blob[i] != 0.0f;
@@ -298,10 +335,31 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
     if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_fn(v.lmi_rp, p->lmi_smem, 256, true)), p->lmi_grad_smem_bytes);
     p->lmi_bwd_smem_bytes = lmi_smem(v.lmi_rp, p->lmi_smem, v.n, kLmiThreads);
     if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_bwd_fn(v.lmi_rp, p->lmi_smem)), p->lmi_bwd_smem_bytes);
+    if (v.lmitc_panels > 0) {
+      // ring depth: all panels resident if that fits, else as many stages (>= 2) as the budget allows
+      int stages = v.lmitc_panels < kLmiTcMaxStages ? v.lmitc_panels : kLmiTcMaxStages;
+      while (stages > 2 && lmi_tc_smem(v.lmi_rp, v.n, v.tc_kp, stages, false) > static_cast<size_t>(p->max_smem_optin))
+        --stages;
+      v.lmitc_stages = stages;
+      p->lmi_tc_smem_bytes = lmi_tc_smem(v.lmi_rp, v.n, v.tc_kp, stages, false);
+      p->lmi_tc_grad_smem_bytes = lmi_tc_smem(v.lmi_rp, v.n, v.tc_kp, stages, true);
+      p->lmi_tc_grad_fsmem = p->lmi_tc_grad_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
+      if (!p->lmi_tc_grad_fsmem) p->lmi_tc_grad_smem_bytes = p->lmi_tc_smem_bytes;  // F~z through L1/L2 instead
+      p->lmi_tc_ok = p->lmi_tc_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
+      p->lmi_tc_mode = 2;
+      const char* env = getenv("RAYEN_LMI_TC");
+      if (env && atoi(env) >= 0 && atoi(env) <= 2) p->lmi_tc_mode = atoi(env);
+      if (rc == 0 && p->lmi_tc_ok)
+        rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_tc_fn(v.lmi_rp, false, false)), p->lmi_tc_smem_bytes);
+      if (rc == 0 && p->lmi_tc_ok)
+        rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_tc_fn(v.lmi_rp, p->lmi_tc_grad_fsmem, true)),
+                        p->lmi_tc_grad_smem_bytes);
+    }
   }
   cudaSetDevice(prev);
   if (rc != 0) {
     cudaFree(p->d_blob);
+    delete p->host_mu;
     delete p;
     return rc;
   }
@@ -315,7 +373,13 @@ extern "C" void rayen_plan_destroy(rayen_plan_t* p) {
   cudaGetDevice(&prev);
   cudaSetDevice(p->device);
   cudaFree(p->d_blob);
+  if (p->host_ready) {
+    cudaStreamDestroy(p->host_in);
+    cudaStreamDestroy(p->host_out);
+    for (cudaEvent_t ev : p->host_ev) cudaEventDestroy(ev);
+  }
   cudaSetDevice(prev);
+  delete p->host_mu;
   delete p;
 }
 
@@ -364,6 +428,24 @@ extern "C" int rayen_lmi_trace_read(long long* out) {
   return static_cast<int>(e);
 }
 #endif
+
+extern "C" int rayen_plan_set_lmi_tensor_cores(rayen_plan_t* p, int mode) {
+  if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "null plan");
+  if (mode < 0 || mode > 2) return fail(RAYEN_ERR_BAD_ARGUMENT, "mode must be 0 (never), 1 (always) or 2 (automatic)");
+  p->lmi_tc_mode = mode;
+  return RAYEN_OK;
+}
+
+// Measured on B200 (scripts/lmi_dense_compare.py, scripts/time_kernels.py): the tensor-core
+// contraction wins when the GEMM is deep (K = 32: -10 % at r = 32, -23 % at r = 16) and the launch carries no
+// gradient work; at K <= 16 the FP32-pipe contraction is cheaper than the GEMM phase's fixed cost, and with
+// want_grad the F~z matrices no longer fit in shared memory next to the GEMM buffers.
+// A pruned work list is short (one partial pass per CTA): there the GEMM phase's fixed cost is not amortised either.
+static bool lmi_use_tc(const rayen_plan* p, bool want_grad, bool list_mode) {
+  if (!p->lmi_tc_ok || p->lmi_tc_mode == 0) return false;
+  if (p->lmi_tc_mode == 1) return true;
+  return p->dev.tc_kp >= 32 && !want_grad && !list_mode;
+}
 
 extern "C" int rayen_plan_set_pruning(rayen_plan_t* p, int enabled) {
   if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "null plan");
@@ -541,13 +623,24 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
   if (e == cudaSuccess && has_lmi && (stage_mask & 2)) {
     const int mpw = 32 / (d.lmi_rp / 4);
     const bool grad = want_grad != 0;
-    const int threads = grad ? 256 : p->lmi_fwd_threads;
-    long long blocks = (B + static_cast<long long>(mpw) * (threads / 32) - 1) / (static_cast<long long>(mpw) * (threads / 32));
-    if (blocks > p->sm_count) blocks = p->sm_count;
-    LmiFwdFn lf = lmi_fwd_fn(d.lmi_rp, p->lmi_smem, threads, grad);
-    lf<<<static_cast<int>(blocks), threads, grad ? p->lmi_grad_smem_bytes : p->lmi_smem_bytes, stream>>>(
-        d, v, ldv, y, kappa, active, B, mode, run_lqs ? 1 : 0, use_list ? fwd_list : nullptr,
-        use_list ? counters : nullptr, grad ? ws_dkappa(workspace, B) : nullptr);
+    if (lmi_use_tc(p, grad, use_list)) {
+      // one CTA per SM, persistent over passes of 8 warps x mpw samples; short batches still start one CTA per
+      // warp's worth of samples so that the kernel can spread them (it re-derives the split from the list length)
+      long long blocks = (B + mpw - 1) / mpw;
+      if (blocks > p->sm_count) blocks = p->sm_count;
+      LmiFwdFn lf = lmi_fwd_tc_fn(d.lmi_rp, grad && p->lmi_tc_grad_fsmem, grad);
+      lf<<<static_cast<int>(blocks), kLmiTcThreads, grad ? p->lmi_tc_grad_smem_bytes : p->lmi_tc_smem_bytes, stream>>>(
+          d, v, ldv, y, kappa, active, B, mode, run_lqs ? 1 : 0, use_list ? fwd_list : nullptr,
+          use_list ? counters : nullptr, grad ? ws_dkappa(workspace, B) : nullptr);
+    } else {
+      const int threads = grad ? 256 : p->lmi_fwd_threads;
+      long long blocks = (B + static_cast<long long>(mpw) * (threads / 32) - 1) / (static_cast<long long>(mpw) * (threads / 32));
+      if (blocks > p->sm_count) blocks = p->sm_count;
+      LmiFwdFn lf = lmi_fwd_fn(d.lmi_rp, p->lmi_smem, threads, grad);
+      lf<<<static_cast<int>(blocks), threads, grad ? p->lmi_grad_smem_bytes : p->lmi_smem_bytes, stream>>>(
+          d, v, ldv, y, kappa, active, B, mode, run_lqs ? 1 : 0, use_list ? fwd_list : nullptr,
+          use_list ? counters : nullptr, grad ? ws_dkappa(workspace, B) : nullptr);
+    }
     g_launches.fetch_add(1);
     e = cudaGetLastError();
   }
@@ -649,43 +742,131 @@ extern "C" int rayen_violation_f32(const rayen_plan_t* p, const float* y, int64_
 }
 
 // ----------------------------------------------------------------------------- host-buffer path
+// The batch is cut into C chunks and the three engines of the GPU work at the same time:
+//   copy-in stream   H2D v_0 .. v_{C-1}, then gy_0 .. gy_{C-1}            (event after each)
+//   caller's stream  forward_0 .. forward_{C-1}, then backward_0 .. backward_{C-1}   (each waits for its input)
+//   copy-out stream  D2H y_c as soon as forward_c is done, then gv_c after backward_c
+// PCIe is full duplex, so the step costs about max(bytes in, bytes out) / link rate plus one chunk of compute
+// instead of the sum of all three.
+constexpr int kHostMaxChunks = 8;
+static int64_t round256(int64_t x) { return (x + 255) / 256 * 256; }
+
 extern "C" int64_t rayen_host_workspace_bytes(const rayen_plan_t* p, int64_t B) {
   if (!p || B < 0) return -1;
   const int64_t n = p->dev.n, k = p->dev.k;
-  // v | gy | y | gv | kappa | active, each rounded up to 256 B
-  auto r = [](int64_t x) { return (x + 255) / 256 * 256; };
-  return r(B * n * 4) * 2 + r(B * k * 4) * 2 + r(B * 4) * 2 + rayen_workspace_bytes(p, B);
+  // v | gy | y | gv | kappa | active, each rounded up to 256 B, then one kernel workspace per chunk
+  return round256(B * n * 4) * 2 + round256(B * k * 4) * 2 + round256(B * 4) * 2 + rayen_workspace_bytes(p, B) +
+         kHostMaxChunks * (p->dev.lmi_r > 0 ? 2048 : 0);
 }
 
-extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* p, const float* v_host, const float* gy_host,
+static int host_chunk_count(const rayen_plan* p, int64_t B) {
+  int c = p->host_chunks;
+  if (c == 0) {
+    // measured on B200 (scripts/e2e_sweep.py): two chunks pay once each direction moves >= 4 MB; more chunks lose,
+    // every extra chunk costs a set of launches (and, with an LMI, the eigen-solver's fixed latency)
+    const int64_t bytes = B * (p->dev.n + p->dev.k) * 4;
+    c = bytes >= (8ll << 20) ? 2 : 1;
+  }
+  if (c > kHostMaxChunks) c = kHostMaxChunks;
+  if (c > B) c = static_cast<int>(B);
+  if (c < 1) c = 1;
+  return c;
+}
+
+extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* cp, const float* v_host, const float* gy_host,
                                                float* y_host, float* gv_host, int64_t B, void* workspace,
                                                void* stream_) {
-  if (!p || !v_host || !gy_host || !y_host || !gv_host || (!workspace && B > 0))
+  if (!cp || !v_host || !gy_host || !y_host || !gv_host || (!workspace && B > 0))
     return fail(RAYEN_ERR_BAD_ARGUMENT, "null argument");
   if (B == 0) return RAYEN_OK;
+  rayen_plan* p = const_cast<rayen_plan*>(cp);
+  if (!p->host_mu) return fail(RAYEN_ERR_BAD_ARGUMENT, "plan has no host-path state");
+  std::lock_guard<std::mutex> guard(*p->host_mu);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int64_t n = p->dev.n, k = p->dev.k;
-  auto r = [](int64_t x) { return (x + 255) / 256 * 256; };
   char* w = static_cast<char*>(workspace);
-  float* v = reinterpret_cast<float*>(w); w += r(B * n * 4);
-  float* gy = reinterpret_cast<float*>(w); w += r(B * k * 4);
-  float* y = reinterpret_cast<float*>(w); w += r(B * k * 4);
-  float* gv = reinterpret_cast<float*>(w); w += r(B * n * 4);
-  float* kappa = reinterpret_cast<float*>(w); w += r(B * 4);
-  int32_t* active = reinterpret_cast<int32_t*>(w); w += r(B * 4);
-  void* ws = rayen_workspace_bytes(p, B) > 0 ? static_cast<void*>(w) : nullptr;
+  float* v = reinterpret_cast<float*>(w); w += round256(B * n * 4);
+  float* gy = reinterpret_cast<float*>(w); w += round256(B * k * 4);
+  float* y = reinterpret_cast<float*>(w); w += round256(B * k * 4);
+  float* gv = reinterpret_cast<float*>(w); w += round256(B * n * 4);
+  float* kappa = reinterpret_cast<float*>(w); w += round256(B * 4);
+  int32_t* active = reinterpret_cast<int32_t*>(w); w += round256(B * 4);
   int prev = 0;
   RAYEN_CUDA(cudaGetDevice(&prev));
   if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
+  cudaError_t e = cudaSuccess;
+  if (!p->host_ready) {
+    e = cudaStreamCreateWithFlags(&p->host_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->host_out, cudaStreamNonBlocking);
+    for (cudaEvent_t& ev : p->host_ev)
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      if (prev != p->device) cudaSetDevice(prev);
+      return cuda_fail(e, "creating the copy streams of the host-buffer path");
+    }
+    p->host_ready = true;
+  }
+  const int C = host_chunk_count(p, B);
+  const int64_t per = ((B + C - 1) / C + 255) / 256 * 256;  // chunk size, multiple of the TC kernel's super-tile
+  cudaEvent_t* ev_v = p->host_ev;                    // [c]     v_c is on the device
+  cudaEvent_t* ev_g = p->host_ev + kHostMaxChunks;   // [c]     gy_c is on the device, later reused: backward_c done
+  cudaEvent_t ev_start = p->host_ev[2 * kHostMaxChunks], ev_done = p->host_ev[2 * kHostMaxChunks + 1];
   int rc = 0;
-  cudaError_t e = cudaMemcpyAsync(v, v_host, B * n * 4, cudaMemcpyHostToDevice, stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(gy, gy_host, B * k * 4, cudaMemcpyHostToDevice, stream);
-  if (e == cudaSuccess) rc = rayen_forward_f32(p, v, n, y, kappa, active, B, RAYEN_MODE_RAYEN, 1, ws, stream);
-  if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(y_host, y, B * k * 4, cudaMemcpyDeviceToHost, stream);
-  if (e == cudaSuccess && rc == 0)
-    rc = rayen_backward_f32(p, v, n, gy, kappa, active, gv, n, B, RAYEN_MODE_RAYEN, 1, ws, stream);
-  if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(gv_host, gv, B * n * 4, cudaMemcpyDeviceToHost, stream);
-  if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(stream);
+  // the copy streams must not start before what the caller queued on `stream` (e.g. a previous use of the workspace)
+  e = cudaEventRecord(ev_start, stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(p->host_in, ev_start, 0);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(p->host_out, ev_start, 0);
+  void* ws_c[kHostMaxChunks];
+  int64_t lo[kHostMaxChunks], cnt[kHostMaxChunks];
+  int used = 0;
+  for (int c = 0; c < C; ++c) {
+    const int64_t b0 = c * per;
+    if (b0 >= B) break;
+    lo[used] = b0;
+    cnt[used] = (B - b0 < per) ? B - b0 : per;
+    const int64_t wb = rayen_workspace_bytes(p, cnt[used]);
+    ws_c[used] = wb > 0 ? static_cast<void*>(w) : nullptr;
+    w += wb;
+    ++used;
+  }
+  for (int c = 0; c < used && e == cudaSuccess; ++c) {
+    e = cudaMemcpyAsync(v + lo[c] * n, v_host + lo[c] * n, cnt[c] * n * 4, cudaMemcpyHostToDevice, p->host_in);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_v[c], p->host_in);
+  }
+  for (int c = 0; c < used && e == cudaSuccess; ++c) {
+    e = cudaMemcpyAsync(gy + lo[c] * k, gy_host + lo[c] * k, cnt[c] * k * 4, cudaMemcpyHostToDevice, p->host_in);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_g[c], p->host_in);
+  }
+  for (int c = 0; c < used && e == cudaSuccess && rc == 0; ++c) {
+    e = cudaStreamWaitEvent(stream, ev_v[c], 0);
+    if (e == cudaSuccess)
+      rc = rayen_forward_f32(p, v + lo[c] * n, n, y + lo[c] * k, kappa + lo[c], active + lo[c], cnt[c],
+                             RAYEN_MODE_RAYEN, 1, ws_c[c], stream);
+    if (e == cudaSuccess && rc == 0) e = cudaEventRecord(ev_v[c], stream);  // reused: forward_c done
+    if (e == cudaSuccess && rc == 0) e = cudaStreamWaitEvent(p->host_out, ev_v[c], 0);
+    if (e == cudaSuccess && rc == 0)
+      e = cudaMemcpyAsync(y_host + lo[c] * k, y + lo[c] * k, cnt[c] * k * 4, cudaMemcpyDeviceToHost, p->host_out);
+  }
+  for (int c = 0; c < used && e == cudaSuccess && rc == 0; ++c) {
+    e = cudaStreamWaitEvent(stream, ev_g[c], 0);
+    if (e == cudaSuccess)
+      rc = rayen_backward_f32(p, v + lo[c] * n, n, gy + lo[c] * k, kappa + lo[c], active + lo[c], gv + lo[c] * n, n,
+                              cnt[c], RAYEN_MODE_RAYEN, 1, ws_c[c], stream);
+    if (e == cudaSuccess && rc == 0) e = cudaEventRecord(ev_g[c], stream);  // reused: backward_c done
+    if (e == cudaSuccess && rc == 0) e = cudaStreamWaitEvent(p->host_out, ev_g[c], 0);
+    if (e == cudaSuccess && rc == 0)
+      e = cudaMemcpyAsync(gv_host + lo[c] * n, gv + lo[c] * n, cnt[c] * n * 4, cudaMemcpyDeviceToHost, p->host_out);
+  }
+  // join: the caller's stream is complete only when the last copy-out is, then block the host as documented
+  cudaError_t e2 = cudaEventRecord(ev_done, p->host_out);
+  if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(stream, ev_done, 0);
+  cudaError_t e3 = cudaStreamSynchronize(p->host_in);
+  cudaError_t e4 = cudaStreamSynchronize(p->host_out);
+  cudaError_t e5 = cudaStreamSynchronize(stream);
+  if (e == cudaSuccess) e = e2;
+  if (e == cudaSuccess) e = e3;
+  if (e == cudaSuccess) e = e4;
+  if (e == cudaSuccess) e = e5;
   if (prev != p->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return cuda_fail(e, "host-buffer forward+backward");
   return rc;

@@ -19,7 +19,7 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_NP = 32
 MAX_LMI = 32
 
@@ -70,6 +70,7 @@ def packed_triangular_words(np_):
 
 
 TC_PANEL = 96   # rows of W per tensor-core panel (MMA N)
+LMI_TC_PANEL = 128  # entries of the LMI matrix per panel of the contraction GEMM (MMA N)
 
 
 def split_tf32(x):
@@ -359,6 +360,21 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
         Fneg[:, :lmi_r, :lmi_r] = -0.5 * (allF + allF.transpose(0, 2, 1))
         off_lmineg = add(Fneg.reshape(k + 1, lmi_rp, 4, lpm).transpose(0, 1, 3, 2))
 
+    # ---- LMI matrices as the B operand of the contraction GEMM S = U W' (lmi_tc.cuh): W [rp*rp, kp] with
+    # row e = i*rp + 4q + t holding F~z_.[i][q + lpm*t] (the LMI section's order), in 128-row panels, TF32 split
+    off_lmitc = add(np.zeros(4))
+    lmitc_panels = 0
+    if lmi is not None and lmi_rp >= 16:
+        Wl = np.zeros((lmi_rp * lmi_rp, kp), dtype=np.float32)
+        Wl[:, :n] = np.asarray(Fperm, dtype=np.float64).reshape(n, lmi_rp * lmi_rp).T.astype(np.float32)
+        lmitc_panels = lmi_rp * lmi_rp // LMI_TC_PANEL
+        for pi in range(lmitc_panels):
+            hi, lo = split_tf32(Wl[pi * LMI_TC_PANEL:(pi + 1) * LMI_TC_PANEL])
+            off = add_f32(operand_layout(hi))
+            add_f32(operand_layout(lo))
+            if pi == 0:
+                off_lmitc = off
+
     blob = np.concatenate(sections).astype(np.float32)
     assert blob.size == cursor and cursor % 4 == 0
     for off, arr in exact:
@@ -370,7 +386,8 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
                        off_lin=off_lin, off_quad=off_quad, off_soc=off_soc, off_nmat=off_nmat,
                        off_y0=off_y0, off_bound=off_bound, off_lmi=off_lmi, lmi_prune=int(lmi is not None),
                        off_tc=off_tc, tc_panels=tc_panels, tc_kp=kp,
-                       off_viol=off_viol, off_lmineg=off_lmineg, viol_in=viol_in, viol_eq=viol_eq)
+                       off_viol=off_viol, off_lmineg=off_lmineg, viol_in=viol_in, viol_eq=viol_eq,
+                       off_lmitc=off_lmitc, lmitc_panels=lmitc_panels)
     plan.f64 = dict(D=D, N=N, y0=y0, z0=z0, yp=yp, quads=quad_f64, socs=soc_f64, Fz=Fz)
     return plan
 

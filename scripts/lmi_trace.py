@@ -29,11 +29,13 @@ for arg in sys.argv[1:]:
     fn.argtypes = [ctypes.c_void_p]
     fn(buf)
     h = np.array(buf[:], dtype=np.int64).reshape(64, 64)[:16]
+    if os.environ.get("RAYEN_LMI_TC", "1") != "0":
+        NAMES[:] = ["start", "setup", "iter0", "dir", "Uready", "W0ok", "mma0_issued", "ahead_issued"] + [f"{w}{p}" for p in range(8) for w in ("m", "d")] + ["Aregs", "tridiag", "sturm", "end"]
     print(f"== {name} B={batch}: cycles since kernel start of the LAST loop iteration's phases (warp 0 | warp 7)")
     for cta in (0, 1, 7, 15):
         for w, off in (("w0", 0), ("w7", 32)):
-            t = h[cta, off:off + 12]
+            t = h[cta, off:off + len(NAMES)]
             t0 = h[cta, 0]
-            print(f"cta{cta:2d} {w}: " + " ".join(f"{NAMES[i]}={int(t[i] - t0):7d}" for i in range(12)))
+            print(f"cta{cta:2d} {w}: " + " ".join(f"{NAMES[i]}={int(t[i] - t0)}" for i in range(len(NAMES)) if NAMES[i] != "?"))
     del db, layer
     torch.cuda.empty_cache()

@@ -256,6 +256,11 @@ def test_forward_computed_lmi_gradient_matches_backward_kernel():
     layer, y, gv = run_layer(cs, v, gy)                       # autograd path: want_grad = 1
     _, act = layer.last_kappa_and_active()
     assert int(((act >> 24) == _cabi.FAM_LMI).sum()) > 50
+    layer.set_lmi_tensor_cores(True, device=DEV)              # the no-grad forward contracts on the tensor cores
+    with torch.no_grad():
+        y_ng = layer(v.to(DEV).unsqueeze(2))[:, :, 0].cpu().numpy()
+    assert rel(y_ng.astype(np.float64), y) <= 3e-6
+    layer.set_lmi_tensor_cores(False, device=DEV)             # same contraction arithmetic everywhere: bit-equal
     with torch.no_grad():
         y_ng = layer(v.to(DEV).unsqueeze(2))[:, :, 0].cpu().numpy()
     np.testing.assert_array_equal(y_ng.astype(np.float64), y)
@@ -302,6 +307,41 @@ def test_tensor_core_and_fp32_pipe_kernels_agree():
         assert rel(y_tc, cf["y"]) <= TOL and rel(y_fp, cf["y"]) <= TOL
 
 
+@pytest.mark.parametrize("k,r,m,batch", [(8, 32, 0, 4096), (8, 32, 0, 37), (32, 32, 40, 3000), (5, 12, 0, 1500),
+                                           (16, 16, 20, 700), (3, 9, 0, 2), (20, 27, 0, 10000)])
+def test_lmi_tensor_core_contraction_agrees_with_fp32_pipe(k, r, m, batch):
+    """The tcgen05 contraction (lmi_tc.cuh: S = U W' as 3xTF32, drained through shared memory into the solver) and
+    the FP32-pipe contraction of lmi.cuh give the same kappa / y / g_v, and both match the float64 oracle.
+    Covers padded LMI sizes 16 and 32, K paddings 8/16/32, dense (no other family) and work-list launches,
+    batches shorter than one pass per CTA and longer than one."""
+    spec = synthetic.random_spec(k=k, m=m, r=r, seed=11 + r)
+    if m:
+        spec["b1"] = spec["b1"] * 6.0
+    cs = synthetic.build_constraints(spec)
+    v, gy = synthetic.sample_inputs(batch, cs.n, cs.k, scale=6.0)
+    res = {}
+    for tc in (True, False):
+        layer = ConstraintModule(cs, create_map=False).to(DEV)
+        layer.set_lmi_tensor_cores(tc, device=DEV)
+        x = v.to(DEV).requires_grad_(True)
+        y = layer(x.unsqueeze(2))
+        (y[:, :, 0] * gy.to(DEV)).sum().backward()
+        kap, act = layer.last_kappa_and_active()
+        res[tc] = (y[:, :, 0].detach().cpu().double().numpy(), x.grad.cpu().double().numpy(),
+                   kap.cpu().double().numpy(), act.cpu().numpy())
+    y_tc, g_tc, k_tc, a_tc = res[True]
+    y_fp, g_fp, k_fp, a_fp = res[False]
+    assert int(((a_tc >> 24) == _cabi.FAM_LMI).sum()) > 0
+    assert np.abs(k_tc - k_fp).max() <= 3e-6 * np.abs(k_fp).max()
+    assert rel(y_tc, y_fp) <= 3e-6
+    oset = OracleSet.from_constraints(cs)
+    y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v.double(), gy.double())
+    ok = closed_form_numpy(oset, v.numpy(), gy.numpy())["margin"] > 1e-4
+    assert np.array_equal(a_tc[ok], a_fp[ok])
+    assert rel(y_tc, y_ref.numpy()) <= TOL and rel(y_fp, y_ref.numpy()) <= TOL
+    assert rel(g_tc, g_ref.numpy(), ok) <= TOL_GRAD and rel(g_fp, g_ref.numpy(), ok) <= TOL_GRAD
+
+
 @pytest.mark.parametrize("which", ["readme", 13, 11, 6, "cfg3", "cfg5"])
 def test_gpu_violation_metric(which):
     """rayen_violation_f32 against the float64 residuals of the original constraints, on feasible outputs of the
@@ -338,6 +378,22 @@ def test_host_buffer_path_matches_device_path():
     yh, gvh = layer.forward_backward_host(v.pin_memory(), gy.pin_memory(), device=DEV)
     np.testing.assert_array_equal(yh.numpy(), y.astype(np.float32))
     np.testing.assert_array_equal(gvh.numpy(), gv.astype(np.float32))
+
+
+@pytest.mark.parametrize("chunks,batch", [(1, 777), (3, 5000), (8, 2500), (8, 5)])
+def test_host_buffer_path_chunked_pipeline(monkeypatch, chunks, batch):
+    """The host path overlaps copy-in, kernels and copy-out over `chunks` pieces of the batch (RAYEN_HOST_CHUNKS is
+    read when the plan is created); samples are independent, so the result is the device path's, bit for bit."""
+    monkeypatch.setenv("RAYEN_HOST_CHUNKS", str(chunks))
+    spec = synthetic.config_spec("cfg5")
+    spec["b1"] = spec["b1"] * 4.0
+    cs = synthetic.build_constraints(spec)
+    v, gy = synthetic.sample_inputs(batch, cs.n, cs.k)
+    layer, y, gv = run_layer(cs, v, gy)
+    for _ in range(2):  # the second call reuses the plan's copy streams and events
+        yh, gvh = layer.forward_backward_host(v.pin_memory(), gy.pin_memory(), device=DEV)
+        np.testing.assert_array_equal(yh.numpy(), y.astype(np.float32))
+        np.testing.assert_array_equal(gvh.numpy(), gv.astype(np.float32))
 
 
 def test_non_contiguous_and_other_dtypes():
