@@ -548,6 +548,52 @@ struct LmiSolver {
     }
     __syncwarp();
   }
+
+  // The same quantity with the whole warp working on the matrix of lane group G (its unit eigenvector was left in
+  // that group's scratch by eigenvector()): lane group h takes a = h, h + MPW, ... and writes d kappa/du_a straight
+  // to out_row[a].  When one sample of a warp needs the gradient -- the usual case behind a pruned work list --
+  // this is MPW times shorter than every group walking all n matrices for its own sample.
+  // Writes out[row_off + a].
+  __device__ __forceinline__ void eig_gradient_coop(const float* __restrict__ F, int n, int G, int my_grp,
+                                                    float* __restrict__ out, long long row_off) {
+    const float* qs = scr + (G - my_grp) * C::SCR + kLmiMaxN;  // sv() of group G
+    float qa[RP], qo[4];
+#pragma unroll
+    for (int i4 = 0; i4 < RP / 4; ++i4) {
+      const float4 x = ld4(qs + 4 * i4);
+      qa[4 * i4 + 0] = x.x;
+      qa[4 * i4 + 1] = x.y;
+      qa[4 * i4 + 2] = x.z;
+      qa[4 * i4 + 3] = x.w;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) qo[t] = qs[q + LPM * t];
+    const float* Fq = F + 4 * q;
+    // the trip count is the same for every lane (the group sums below are full-warp shuffles): groups whose a
+    // falls beyond n redo the last matrix and write nothing
+    for (int a0 = 0; a0 < n; a0 += C::MPW) {
+      const int a = a0 + my_grp;
+      const float* Fa = Fq + (a < n ? a : n - 1) * (RP * RP);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < RP; ++i) {
+        float4 f;
+        if constexpr (F_SMEM)
+          f = ld4(Fa + i * RP);
+        else
+          f = __ldg(reinterpret_cast<const float4*>(Fa + i * RP));
+        acc[0] = fmaf(qa[i], f.x, acc[0]);
+        acc[1] = fmaf(qa[i], f.y, acc[1]);
+        acc[2] = fmaf(qa[i], f.z, acc[2]);
+        acc[3] = fmaf(qa[i], f.w, acc[3]);
+      }
+      float part = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) part = fmaf(acc[t], qo[t], part);
+      part = group_sum<LPM>(part);
+      if (q == 0 && a < n) out[row_off + a] = part;
+    }
+  }
 };
 
 // dynamic smem: 64 B barriers | F (if F_SMEM) | per-warp scratch
@@ -677,16 +723,16 @@ __global__ void __launch_bounds__(THREADS, 1)
         float qo[4];
         S.eigenvector(lam, qo);
         LMI_STAMP(9);
-        float dk[C::NPL];
-        S.eig_gradient(F, n, qo, dk);
-        LMI_STAMP(10);
-        if (need) {
-#pragma unroll
-          for (int sl = 0; sl < C::NPL; ++sl) {
-            const int a = S.q + C::LPM * sl;
-            if (a < n) dkappa[b * n + a] = dk[sl];
-          }
+        // one needing sample after the other, the whole warp on each
+        const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+#pragma unroll 1
+        for (int G = 0; G < C::MPW; ++G) {
+          if (!((need_mask >> (G * C::LPM)) & 1u)) continue;
+          // (sample indices fit 32 bits: the work lists are int32)
+          const int bG = __shfl_sync(0xffffffffu, static_cast<int>(b), G * C::LPM);
+          S.eig_gradient_coop(F, n, G, grp, dkappa, static_cast<long long>(bG) * n);
         }
+        LMI_STAMP(10);
       }
     }
     __syncwarp();  // the scratch (u) is rewritten by the next sample

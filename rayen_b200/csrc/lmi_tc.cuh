@@ -338,14 +338,13 @@ __global__ void __launch_bounds__(kLmiTcThreads, 1)
           mbar_wait(f_bar, 0);
           f_ready = true;
         }
-        float dk[C::NPL];
-        S.eig_gradient(F, n, qo, dk);
-        if (need) {
-#pragma unroll
-          for (int sl = 0; sl < C::NPL; ++sl) {
-            const int a = S.q + C::LPM * sl;
-            if (a < n) dkappa[b * n + a] = dk[sl];
-          }
+        const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+#pragma unroll 1
+        for (int G = 0; G < C::MPW; ++G) {
+          if (!((need_mask >> (G * C::LPM)) & 1u)) continue;
+          // (sample indices fit 32 bits: the work lists are int32)
+          const int bG = __shfl_sync(0xffffffffu, static_cast<int>(b), G * C::LPM);
+          S.eig_gradient_coop(F, n, G, grp, dkappa, static_cast<long long>(bG) * n);
         }
       }
     }

@@ -501,48 +501,121 @@ __device__ __forceinline__ void store_row(float* __restrict__ row, int n, bool v
   }
 }
 
-// One thread per sample.  Samples whose binding constraint is the LMI (and that need d kappa/du) are
-// appended to a work list for lmi_backward_kernel.
+// ---- warp-tile row I/O: the 32 rows of a warp are one contiguous chunk of a dense [B, NP] tensor, so the warp
+// moves it with fully coalesced 16-byte accesses (512 B per instruction) and transposes through a padded
+// shared-memory tile; per-thread row accesses touch 32 different lines per instruction and lean on L1 instead.
 template <int NP>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void warp_load_rows(const float* __restrict__ base, int rows_valid, float* tile, int lane,
+                                               float (&x)[NP]) {
+  constexpr int C4 = NP / 4, TS = NP + 4;
+  const float4* src = reinterpret_cast<const float4*>(base);
+#pragma unroll
+  for (int it = 0; it < C4; ++it) {
+    const int i = it * 32 + lane;
+    const int r = i / C4, c4 = i % C4;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows_valid) t = __ldg(src + i);
+    *reinterpret_cast<float4*>(tile + r * TS + 4 * c4) = t;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int kk = 0; kk < C4; ++kk) {
+    const float4 t = *reinterpret_cast<const float4*>(tile + lane * TS + 4 * kk);
+    x[4 * kk + 0] = t.x;
+    x[4 * kk + 1] = t.y;
+    x[4 * kk + 2] = t.z;
+    x[4 * kk + 3] = t.w;
+  }
+  __syncwarp();
+}
+template <int NP>
+__device__ __forceinline__ void warp_store_rows(float* __restrict__ base, int rows_valid, float* tile, int lane,
+                                                const float (&x)[NP]) {
+  constexpr int C4 = NP / 4, TS = NP + 4;
+#pragma unroll
+  for (int kk = 0; kk < C4; ++kk)
+    *reinterpret_cast<float4*>(tile + lane * TS + 4 * kk) = make_float4(x[4 * kk], x[4 * kk + 1], x[4 * kk + 2], x[4 * kk + 3]);
+  __syncwarp();
+  float4* dst = reinterpret_cast<float4*>(base);
+#pragma unroll
+  for (int it = 0; it < C4; ++it) {
+    const int i = it * 32 + lane;
+    const int r = i / C4, c4 = i % C4;
+    if (r < rows_valid) dst[i] = *reinterpret_cast<const float4*>(tile + r * TS + 4 * c4);
+  }
+  __syncwarp();
+}
+
+constexpr int kBwdThreads = 128;
+template <int NP>
+__host__ __device__ constexpr size_t lqs_bwd_smem_bytes() {
+  return static_cast<size_t>(kBwdThreads / 32) * 32 * (NP + 4) * sizeof(float);
+}
+
+// One thread per sample, one warp per 32 consecutive samples.  Samples whose binding constraint is the LMI (and
+// that need d kappa/du the forward pass did not leave behind) are appended to a work list for lmi_backward_kernel.
+template <int NP>
+__global__ void __launch_bounds__(kBwdThreads)
     lqs_backward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, const float* __restrict__ gy,
                         const float* __restrict__ kappa, const int* __restrict__ active, float* __restrict__ gv,
                         long long ldgv, long long B, int mode, int* __restrict__ work_list,
                         int* __restrict__ work_count, const float* __restrict__ dkappa) {
+  extern __shared__ __align__(16) float bwd_tiles[];
   const int n = P.n;
+  const int lane = threadIdx.x & 31;
+  float* tile = bwd_tiles + (threadIdx.x >> 5) * 32 * (NP + 4);
   const bool vec_v = ((n & 3) == 0) && ((ldv & 3) == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
   const bool vec_gy = ((P.k & 3) == 0) && ((reinterpret_cast<uintptr_t>(gy) & 15) == 0);
   const bool vec_gv = ((n & 3) == 0) && ((ldgv & 3) == 0) && ((reinterpret_cast<uintptr_t>(gv) & 15) == 0);
+  // dense contiguous tensors of full width: the warp-tile path
+  const bool tile_v = vec_v && n == NP && ldv == n;
+  const bool tile_gy = vec_gy && P.n_is_identity && P.k == NP;
+  const bool tile_gv = vec_gv && n == NP && ldgv == n;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; b < B; b += stride) {
-    const float kap = __ldg(kappa + b);
-    const int tag = __ldg(active + b);
+  for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x + (threadIdx.x & ~31); base < B; base += stride) {
+    const long long b = base + lane;
+    const bool valid = b < B;
+    const int rows_valid = (B - base < 32) ? static_cast<int>(B - base) : 32;
+    const float kap = valid ? __ldg(kappa + b) : 1.f;
+    const int tag = valid ? __ldg(active + b) : 0;
     float u[NP];
-    load_row<NP>(v + b * ldv, n, vec_v, true, u);
+    if (tile_v)
+      warp_load_rows<NP>(v + base * n, rows_valid, tile, lane, u);
+    else
+      load_row<NP>(v + b * ldv, n, vec_v, valid, u);
     const float s = normalize_row<NP>(u);
-    const float beta = (mode == RAYEN_MODE_RAYEN_OLD) ? __ldg(v + b * ldv + n) : 0.f;
-    const bool boundary = (mode == RAYEN_MODE_RAYEN_OLD) ? (kap > 0.f) : (1.0f / kap < s);
+    const float beta = (mode == RAYEN_MODE_RAYEN_OLD && valid) ? __ldg(v + b * ldv + n) : 0.f;
+    const bool boundary = valid && ((mode == RAYEN_MODE_RAYEN_OLD) ? (kap > 0.f) : (1.0f / kap < s));
     const bool lmi_bound = boundary && tag_family(tag) == RAYEN_FAM_LMI;
-    if (lmi_bound && !dkappa) {
-      // needs the eigenvector and the forward pass did not leave d kappa/du behind: queued for lmi_backward_kernel
-      if (work_list) work_list[atomicAdd(work_count, 1)] = static_cast<int>(b);
-      continue;
-    }
+    // needs the eigenvector and the forward pass did not leave d kappa/du behind: queued for lmi_backward_kernel
+    const bool queued = lmi_bound && !dkappa;
+    if (queued && work_list) work_list[atomicAdd(work_count, 1)] = static_cast<int>(b);
     float gz[NP], dk[NP], g[NP];
-    load_gz<NP>(P, gy + b * P.k, vec_gy, gz);
-    if (lmi_bound) {
+    if (tile_gy) {
+      warp_load_rows<NP>(gy + base * P.k, rows_valid, tile, lane, gz);
+    } else if (valid) {
+      load_gz<NP>(P, gy + b * P.k, vec_gy, gz);
+    } else {
+#pragma unroll
+      for (int a = 0; a < NP; ++a) gz[a] = 0.f;
+    }
+    if (lmi_bound && !queued) {
 #pragma unroll
       for (int a = 0; a < NP; ++a) dk[a] = (a < n) ? __ldg(dkappa + b * n + a) : 0.f;
-    } else if (boundary) {
+    } else if (boundary && !queued) {
       dkappa_lqs<NP>(P, tag, kap, u, dk);
     } else {
 #pragma unroll
       for (int a = 0; a < NP; ++a) dk[a] = 0.f;
     }
     float gbeta = 0.f;
-    backward_tail<NP>(mode, s, kap, beta, u, gz, dk, boundary, g, &gbeta);
-    store_row<NP>(gv + b * ldgv, n, vec_gv, g);
-    if (mode == RAYEN_MODE_RAYEN_OLD) gv[b * ldgv + n] = gbeta;
+    backward_tail<NP>(mode, s, kap, beta, u, gz, dk, boundary && !queued, g, &gbeta);
+    if (tile_gv && __all_sync(0xffffffffu, !queued)) {
+      warp_store_rows<NP>(gv + base * n, rows_valid, tile, lane, g);
+    } else if (valid && !queued) {
+      store_row<NP>(gv + b * ldgv, n, vec_gv, g);
+    }
+    if (valid && !queued && mode == RAYEN_MODE_RAYEN_OLD) gv[b * ldgv + n] = gbeta;
   }
 }
 

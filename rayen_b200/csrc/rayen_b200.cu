@@ -673,9 +673,9 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
   RAYEN_CUDA(cudaGetDevice(&prev));
   if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
 
-  const int block = 128;
+  const int block = kBwdThreads;
   long long grid = (B + block - 1) / block;
-  const long long cap = static_cast<long long>(p->sm_count) * 16;
+  const long long cap = static_cast<long long>(p->sm_count) * 12;  // 12 blocks x 18 KB of tile memory per SM at n = 32
   if (grid > cap) grid = cap;
   const bool has_lmi = d.lmi_r > 0;
   if (has_lmi && !workspace) return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the workspace buffer");
@@ -686,7 +686,8 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
     if (has_lmi) e = cudaMemsetAsync(counters + 1, 0, sizeof(int), stream);
     LqsBwdFn f = lqs_bwd_fn(d.np);
     if (e == cudaSuccess) {
-      f<<<static_cast<int>(grid), block, 0, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode, bwd_list,
+      const size_t tile_bytes = static_cast<size_t>(block / 32) * 32 * (d.np + 4) * sizeof(float);
+      f<<<static_cast<int>(grid), block, tile_bytes, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode, bwd_list,
                                                       has_lmi ? counters + 1 : nullptr,
                                                       (has_lmi && have_dkappa) ? ws_dkappa(workspace, B) : nullptr);
       g_launches.fetch_add(1);
