@@ -321,6 +321,26 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     e2e_ms = max_over_ranks(e2e_ms)
 
+    # the link this box gives the step: one 64 MB pinned copy each way, alone (explains e2e, which moves
+    # batch*4*(n+k) bytes in each direction per step)
+    link = {}
+    try:
+        hbuf = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+        dbuf = torch.empty(64 << 20, dtype=torch.uint8, device=device)
+        for label, (src, dst) in (("h2d_gbs", (hbuf, dbuf)), ("d2h_gbs", (dbuf, hbuf))):
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize(device)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(4):
+                dst.copy_(src, non_blocking=True)
+            c1.record()
+            torch.cuda.synchronize(device)
+            link[label] = 4 * (64 << 20) / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del hbuf, dbuf
+    except Exception as exc:  # noqa: BLE001 - informational
+        link["error"] = repr(exc)[:120]
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -341,8 +361,12 @@ def run_b200(args, rank, local_rank, world):
                    "reasons": clock_info["reasons"], "samples": clock_info["samples"]},
         "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": batch * 4 * (n + k), "d2h_bytes_per_step": batch * 4 * (n + k),
-                "ms_per_step": e2e_ms, "path": "ConstraintModule.forward_backward_host -> rayen_forward_backward_host_f32 "
-                                               "(pinned host buffers)"},
+                "ms_per_step": e2e_ms, "link": link,
+                "copy_floor_ms": (batch * 4 * (n + k) / 1e6 / max(min(link.get("h2d_gbs", 0.0), link.get("d2h_gbs", 0.0)), 1e-9)
+                                  if "h2d_gbs" in link and "d2h_gbs" in link else None),
+                "path": "ConstraintModule.forward_backward_host -> rayen_forward_backward_host_f32 "
+                                               "(pinned host buffers; copy-in, kernels and copy-out on three streams, "
+                                               "synchronous per step)"},
         "gpu_launches": int(launches),
         "module_autograd": {"value": world * batch / (ms_module * 1e-3), "ms_per_step": ms_module,
                             "path": "nn.Module forward + autograd backward (PyTorch eager overhead included)"},
@@ -363,6 +387,8 @@ def run_b200(args, rank, local_rank, world):
     durs["lqs_forward_kernel"] = bench.time_loop(lambda i: bench.forward(bench.sets[i % POOL], 1), steps, POOL)
     if has_lmi:
         durs["lmi_forward_kernel"] = bench.time_loop(lambda i: bench.forward(bench.sets[i % POOL], 2), steps, POOL)
+    kernel_names = {"lqs_forward_kernel": "lqs_tc_forward_kernel (tcgen05)" if n >= 16 else "lqs_forward_kernel (FP32 pipe)",
+                    "lmi_forward_kernel": "lmi_forward_kernel<WITH_GRAD> (FP32-pipe contraction; the step carries gradient work)"}
     dominant = max(durs, key=durs.get)
     fwd_bytes, bwd_bytes = batch * 4 * (n + k), batch * 4 * (2 * n + k)
     alg_bytes = fwd_bytes if "forward" in dominant else bwd_bytes
@@ -377,12 +403,25 @@ def run_b200(args, rank, local_rank, world):
         "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": durs[dominant],
-        "kernel_ms_all": durs, "kernel_share_of_step": durs[dominant] / sum(durs.values()),
+        "kernel_ms_all": durs, "kernel_names": kernel_names,
+        "kernel_share_of_step": durs[dominant] / sum(durs.values()),
         "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (direct_ms * 1e-3) / 1e9,
                        "frac": step_bytes / (direct_ms * 1e-3) / 1e9 / peak},
         "note": "the named shapes are FP32-issue/LSU bound, not HBM bound (DESIGN.md, Roofline); the HBM fraction "
                 "is reported as the contract asks",
     }
+
+    # ---- LMI forward without gradient work (inference): FP32-pipe contraction vs the tcgen05 contraction, forced
+    if has_lmi:
+        lmi_modes = {}
+        for label, mode in (("fp32_pipe", 0), ("tcgen05", 1)):
+            layer.set_lmi_tensor_cores(mode, device=device)
+            bench.want_grad = 0
+            lmi_modes[label + "_fwd_nograd_ms"] = bench.time_loop(lambda i: bench.forward(bench.sets[i % POOL]), steps, 3)
+        layer.set_lmi_tensor_cores(None, device=device)
+        bench.want_grad = 1
+        line["lmi_contraction"] = dict(lmi_modes, note="whole forward (LQS + LMI kernels), want_grad=0; automatic policy: "
+                                       "tcgen05 for K=32 dense launches without gradient work, FP32 pipe otherwise")
 
     # ---- feasibility of the outputs (fp64 residuals of every constraint on a sub-sample)
     from oracle.rayen_oracle import OracleSet, max_violation

@@ -763,10 +763,12 @@ extern "C" int64_t rayen_host_workspace_bytes(const rayen_plan_t* p, int64_t B) 
 static int host_chunk_count(const rayen_plan* p, int64_t B) {
   int c = p->host_chunks;
   if (c == 0) {
-    // measured on B200 (scripts/e2e_sweep.py): two chunks pay once each direction moves >= 4 MB; more chunks lose,
-    // every extra chunk costs a set of launches (and, with an LMI, the eigen-solver's fixed latency)
+    // measured on B200 (scripts/e2e_sweep.py, RAYEN_HOST_TRACE=1): the copies of v / gy / y / gv already overlap
+    // each other and the kernels with ONE chunk (gy goes in under the forward kernels, y comes out under the
+    // backward kernel).  A second chunk pays only for sets without an LMI once each direction moves >= 8 MB; the
+    // eigen-solver's latency-bound kernels take as long on half a batch as on a whole one.
     const int64_t bytes = B * (p->dev.n + p->dev.k) * 4;
-    c = bytes >= (8ll << 20) ? 2 : 1;
+    c = (p->dev.lmi_r == 0 && bytes >= (16ll << 20)) ? 2 : 1;
   }
   if (c > kHostMaxChunks) c = kHostMaxChunks;
   if (c > B) c = static_cast<int>(B);
@@ -807,6 +809,17 @@ extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* cp, const flo
     }
     p->host_ready = true;
   }
+  // RAYEN_HOST_TRACE=1: print the device-side timeline of this call (development aid, adds event records)
+  static const bool trace = getenv("RAYEN_HOST_TRACE") && atoi(getenv("RAYEN_HOST_TRACE")) != 0;
+  cudaEvent_t tev[40];
+  const char* tname[40];
+  int ntev = 0;
+  auto mark = [&](cudaStream_t st, const char* name) {
+    if (!trace || ntev >= 40) return;
+    cudaEventCreate(&tev[ntev]);
+    cudaEventRecord(tev[ntev], st);
+    tname[ntev++] = name;
+  };
   const int C = host_chunk_count(p, B);
   const int64_t per = ((B + C - 1) / C + 255) / 256 * 256;  // chunk size, multiple of the TC kernel's super-tile
   cudaEvent_t* ev_v = p->host_ev;                    // [c]     v_c is on the device
@@ -814,6 +827,7 @@ extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* cp, const flo
   cudaEvent_t ev_start = p->host_ev[2 * kHostMaxChunks], ev_done = p->host_ev[2 * kHostMaxChunks + 1];
   int rc = 0;
   // the copy streams must not start before what the caller queued on `stream` (e.g. a previous use of the workspace)
+  mark(stream, "start");
   e = cudaEventRecord(ev_start, stream);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(p->host_in, ev_start, 0);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(p->host_out, ev_start, 0);
@@ -833,30 +847,36 @@ extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* cp, const flo
   for (int c = 0; c < used && e == cudaSuccess; ++c) {
     e = cudaMemcpyAsync(v + lo[c] * n, v_host + lo[c] * n, cnt[c] * n * 4, cudaMemcpyHostToDevice, p->host_in);
     if (e == cudaSuccess) e = cudaEventRecord(ev_v[c], p->host_in);
+    mark(p->host_in, "h2d v");
   }
   for (int c = 0; c < used && e == cudaSuccess; ++c) {
     e = cudaMemcpyAsync(gy + lo[c] * k, gy_host + lo[c] * k, cnt[c] * k * 4, cudaMemcpyHostToDevice, p->host_in);
     if (e == cudaSuccess) e = cudaEventRecord(ev_g[c], p->host_in);
+    mark(p->host_in, "h2d gy");
   }
   for (int c = 0; c < used && e == cudaSuccess && rc == 0; ++c) {
     e = cudaStreamWaitEvent(stream, ev_v[c], 0);
     if (e == cudaSuccess)
       rc = rayen_forward_f32(p, v + lo[c] * n, n, y + lo[c] * k, kappa + lo[c], active + lo[c], cnt[c],
                              RAYEN_MODE_RAYEN, 1, ws_c[c], stream);
+    mark(stream, "forward");
     if (e == cudaSuccess && rc == 0) e = cudaEventRecord(ev_v[c], stream);  // reused: forward_c done
     if (e == cudaSuccess && rc == 0) e = cudaStreamWaitEvent(p->host_out, ev_v[c], 0);
     if (e == cudaSuccess && rc == 0)
       e = cudaMemcpyAsync(y_host + lo[c] * k, y + lo[c] * k, cnt[c] * k * 4, cudaMemcpyDeviceToHost, p->host_out);
+    mark(p->host_out, "d2h y");
   }
   for (int c = 0; c < used && e == cudaSuccess && rc == 0; ++c) {
     e = cudaStreamWaitEvent(stream, ev_g[c], 0);
     if (e == cudaSuccess)
       rc = rayen_backward_f32(p, v + lo[c] * n, n, gy + lo[c] * k, kappa + lo[c], active + lo[c], gv + lo[c] * n, n,
                               cnt[c], RAYEN_MODE_RAYEN, 1, ws_c[c], stream);
+    mark(stream, "backward");
     if (e == cudaSuccess && rc == 0) e = cudaEventRecord(ev_g[c], stream);  // reused: backward_c done
     if (e == cudaSuccess && rc == 0) e = cudaStreamWaitEvent(p->host_out, ev_g[c], 0);
     if (e == cudaSuccess && rc == 0)
       e = cudaMemcpyAsync(gv_host + lo[c] * n, gv + lo[c] * n, cnt[c] * n * 4, cudaMemcpyDeviceToHost, p->host_out);
+    mark(p->host_out, "d2h gv");
   }
   // join: the caller's stream is complete only when the last copy-out is, then block the host as documented
   cudaError_t e2 = cudaEventRecord(ev_done, p->host_out);
@@ -868,6 +888,15 @@ extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* cp, const flo
   if (e == cudaSuccess) e = e3;
   if (e == cudaSuccess) e = e4;
   if (e == cudaSuccess) e = e5;
+  if (trace && ntev > 0) {
+    fprintf(stderr, "rayen host path, %d chunk(s), B = %lld: end of each piece, us after the start\n", used, static_cast<long long>(B));
+    for (int i = 1; i < ntev; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tev[0], tev[i]);
+      fprintf(stderr, "  %-9s %8.1f\n", tname[i], ms * 1e3f);
+    }
+    for (int i = 0; i < ntev; ++i) cudaEventDestroy(tev[i]);
+  }
   if (prev != p->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return cuda_fail(e, "host-buffer forward+backward");
   return rc;
