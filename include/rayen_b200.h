@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RAYEN_ABI_VERSION 8
+#define RAYEN_ABI_VERSION 9
 
 /* error codes (negative); positive return values are cudaError_t */
 #define RAYEN_OK 0
@@ -150,6 +150,19 @@ int64_t rayen_workspace_bytes(const rayen_plan_t* plan, int64_t B);
  */
 int rayen_forward_f32(const rayen_plan_t* plan, const float* v, int64_t ldv, float* y, float* kappa,
                       int32_t* active, int64_t B, int mode, int want_grad, void* workspace, void* cuda_stream);
+
+/*
+ * Forward with the layer's mapper fused in (reference constraint_module.py:261 and :525: q = nn.Linear(input_dim, n)(x)
+ * followed by forwardForRAYEN): x [B, in_dim] (row stride ldx), weight [n, in_dim] (row stride ldw), bias [n] or NULL.
+ * The linear/quadratic/SOC kernel computes v = W x + b itself, writes it to v_out [B, n] (dense; pass it as `v` to
+ * rayen_backward_f32, whose g_v is then the gradient w.r.t. the mapper's output) and continues as rayen_forward_f32
+ * (mode RAYEN).  RAYEN_ERR_UNSUPPORTED when in_dim / ldx / ldw are not multiples of 4 floats, the tensors are not
+ * 16-byte aligned, or the plan has no linear/quadratic/SOC kernel to host the mapper (LMI-only sets): the caller then
+ * runs the mapper itself and calls rayen_forward_f32.
+ */
+int rayen_forward_mapped_f32(const rayen_plan_t* plan, const float* x, int64_t ldx, int32_t in_dim, const float* weight,
+                             int64_t ldw, const float* bias, float* v_out, float* y, float* kappa, int32_t* active,
+                             int64_t B, int want_grad, void* workspace, void* cuda_stream);
 
 /*
  * Backward: the closed form of what autograd derives from the reference forward.

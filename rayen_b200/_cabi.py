@@ -17,7 +17,7 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "rayen_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MODE_RAYEN, MODE_RAYEN_OLD = 0, 1
 FAM_NONE, FAM_LINEAR, FAM_QUAD, FAM_SOC, FAM_LMI = 0, 1, 2, 3, 4
 
@@ -53,6 +53,8 @@ SYMBOLS = {
     "rayen_workspace_bytes": (ctypes.c_int64, [_P, ctypes.c_int64]),
     "rayen_forward_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, ctypes.c_int64, ctypes.c_int,
                                          ctypes.c_int, _P, _P]),
+    "rayen_forward_mapped_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P, ctypes.c_int64, _P, _P, _P,
+                                                _P, _P, ctypes.c_int64, ctypes.c_int, _P, _P]),
     "rayen_backward_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_int64,
                                           ctypes.c_int, ctypes.c_int, _P, _P]),
     "rayen_forward_stage_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, ctypes.c_int64, ctypes.c_int,

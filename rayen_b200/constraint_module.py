@@ -110,6 +110,61 @@ class _RayShoot(torch.autograd.Function):
         return (gv if ctx.in_dtype == torch.float32 else gv.to(ctx.in_dtype)), None
 
 
+class _MappedRayShoot(torch.autograd.Function):
+    """x:[B, input_dim], weight:[n, input_dim], bias:[n] -> y:[B, k] with the mapper fused into the forward kernel
+    (``rayen_forward_mapped_f32``): the linear/quadratic/SOC kernel computes ``q = x W' + b`` itself, so
+    ``q`` is written once (backward needs it) instead of making the round trip of a separate GEMM launch.
+    Backward: ``g_q`` from ``rayen_backward_f32``, then the three products of ``nn.Linear``'s own backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, module):
+        B, in_dim = x.shape
+        device = x.device
+        st = module._launch_state(device)
+        n, k = module.n, module.k
+        ws_words = st.ws_words(B)
+        aux = torch.empty((2 * B + ws_words,), dtype=torch.float32, device=device)
+        q = torch.empty((B, n), dtype=torch.float32, device=device)
+        y = torch.empty((B, k), dtype=torch.float32, device=device)
+        base = aux.data_ptr()
+        want_grad = 1 if any(ctx.needs_input_grad[:3]) else 0
+        with torch.cuda.device(device):
+            rc = st.forward_mapped(st.handle, x.data_ptr(), x.stride(0) if B > 0 else in_dim, in_dim, weight.data_ptr(),
+                                   weight.stride(0), bias.data_ptr() if bias is not None else None, q.data_ptr(),
+                                   y.data_ptr(), base, base + 4 * B, B, want_grad, base + 8 * B,
+                                   torch.cuda.current_stream(device).cuda_stream)
+        if rc != 0:
+            _cabi.check(rc, "rayen_forward_mapped_f32")
+        ctx.module, ctx.aux, ctx.have_dkappa, ctx.has_bias = module, aux, want_grad, bias is not None
+        ctx.save_for_backward(x, weight, q)
+        module._last_aux = (aux, B)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, q = ctx.saved_tensors
+        module, aux = ctx.module, ctx.aux
+        gy = gy.detach()
+        if gy.dtype != torch.float32:
+            gy = gy.float()
+        if not gy.is_contiguous():
+            gy = gy.contiguous()
+        B, n = q.shape
+        device = q.device
+        st = module._launch_state(device)
+        gq = torch.empty((B, n), dtype=torch.float32, device=device)
+        base = aux.data_ptr()
+        with torch.cuda.device(device):
+            rc = st.backward(st.handle, q.data_ptr(), n, gy.data_ptr(), base, base + 4 * B, gq.data_ptr(), n, B,
+                             module._mode, ctx.have_dkappa, base + 8 * B, torch.cuda.current_stream(device).cuda_stream)
+        if rc != 0:
+            _cabi.check(rc, "rayen_backward_f32")
+        gx = gq @ weight if ctx.needs_input_grad[0] else None
+        gw = gq.t() @ x if ctx.needs_input_grad[1] else None
+        gb = gq.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb, None
+
+
 class _LaunchState:
     """Per-(module, device) cache of everything the hot path needs: plan handle, C entry points, sizes."""
 
@@ -119,6 +174,7 @@ class _LaunchState:
         self.handle = dev_plan.handle
         self.index = dev_plan.device_index
         self.forward = lib.rayen_forward_f32
+        self.forward_mapped = lib.rayen_forward_mapped_f32
         self.backward = lib.rayen_backward_f32
         self._ws = {}
 
@@ -184,6 +240,12 @@ class ConstraintModule(nn.Module):
         else:
             self.mapper = nn.Sequential()  # mapper does nothing
 
+        # fold the mapper into the forward kernel when the input layout allows it (False: always run nn.Linear itself);
+        # the kernel that hosts it runs unless the set is an LMI alone (same rule as the C side's has_lqs)
+        self.fuse_mapper = True
+        self._lqs_kernel_runs = bool(cs.has_quadratic_constraints or cs.has_soc_constraints or np.any(np.asarray(D) != 0)
+                                     or not cs.has_lmi_constraints)
+
         # host-side packed plan (float64 math, float32 block) and its per-GPU uploads
         self._packed = plan_mod.build_plan_from_constraints(cs)
         self._plans = {}
@@ -235,6 +297,7 @@ class ConstraintModule(nn.Module):
         # encoded by A_p, b_p and N (lin_rows=None) instead of the original rows
         self._packed = plan_mod.build_plan(g("A_p"), g("b_p"), g("NA_E"), g("yp"), g("z0"), qcs, socs, lmi,
                                            lin_rows=None)
+        self._lqs_kernel_runs = bool(qcs or socs or np.any(g("D") != 0) or lmi is None)
         for dev_plan in self._plans.values():
             dev_plan.close()
         self._plans = {}
@@ -327,9 +390,21 @@ class ConstraintModule(nn.Module):
         return self.NA_E.T @ (y - self.yp)
 
     # ------------------------------------------------------------------ forward
+    def _can_fuse_mapper(self, x2d):
+        """The mapper is folded into the forward kernel when the layout allows it (see rayen_forward_mapped_f32)."""
+        m = self.mapper
+        return (self.fuse_mapper and isinstance(m, nn.Linear) and self._mode == _cabi.MODE_RAYEN and x2d.is_cuda
+                and x2d.dtype == torch.float32 and m.weight.dtype == torch.float32 and x2d.shape[0] > 0
+                and x2d.shape[1] % 4 == 0 and x2d.stride(1) == 1 and x2d.stride(0) % 4 == 0
+                and x2d.data_ptr() % 16 == 0 and m.weight.is_contiguous() and m.weight.data_ptr() % 16 == 0
+                and self._lqs_kernel_runs)
+
     def forward(self, x):
         # x: [B, numel_input_mapper, 1] (anything that views to [B, -1]), as in the reference
-        q = self.mapper(x.view(x.size(0), x[0].numel() if x.size(0) else int(np.prod(x.shape[1:]))))
+        x2d = x.view(x.size(0), x[0].numel() if x.size(0) else int(np.prod(x.shape[1:])))
+        if self._can_fuse_mapper(x2d):
+            return _MappedRayShoot.apply(x2d, self.mapper.weight, self.mapper.bias, self).unsqueeze(2)
+        q = self.mapper(x2d)
         utils.verify(q.shape[1] == self.dim_after_map,
                      f"the layer expects {self.dim_after_map} values per sample, got {q.shape[1]}")
         if q.dtype == torch.float64 and not getattr(self, "_warned_f64", False):

@@ -22,6 +22,19 @@ struct PlanDev {
   int off_lmitc, lmitc_panels, lmitc_stages;   // LMI matrices as a tcgen05 B operand (lmi_tc.cuh); ring depth
 };
 
+// Fused mapper (reference constraint_module.py:261, :525: q = nn.Linear(input_dim, n)(x)): when x != nullptr the
+// linear/quadratic/SOC forward kernel computes its own v = W x + b from the layer input, writes it to v_out (the
+// backward pass and the LMI kernel need it) and goes on; q never makes the HBM round trip of a separate GEMM launch.
+struct MapArgs {
+  const float* x;     // [B, in_dim], row stride ldx (multiple of 4, 16-byte aligned rows)
+  const float* w;     // [n, in_dim], row stride ldw (multiple of 4, 16-byte aligned rows)
+  const float* bias;  // [n] or nullptr
+  float* v_out;       // [B, n] dense
+  long long ldx, ldw;
+  int in_dim;         // multiple of 4
+  int pad;
+};
+
 constexpr int kFamShift = 24;
 __host__ __device__ inline int make_tag(int fam, int idx) { return (fam << kFamShift) | idx; }
 __host__ __device__ inline int tag_family(int tag) { return tag >> kFamShift; }
@@ -80,6 +93,30 @@ __device__ __forceinline__ void stage_bulk(float* dst_smem, const float* src, in
 
 // ----------------------------------------------------------------------------- small helpers
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// v[a] = bias[a] + sum_k W[a][k] x[b][k] for a < n (0 beyond): the weight rows are warp-uniform 16-byte loads (L1
+// broadcast), the input row is this thread's own.
+template <int NP>
+__device__ __forceinline__ void map_row(const MapArgs& M, long long b, int n, bool valid, float (&u)[NP]) {
+#pragma unroll
+  for (int a = 0; a < NP; ++a) u[a] = (valid && a < n && M.bias) ? __ldg(M.bias + a) : 0.f;
+  if (!valid) return;
+  const float* xr = M.x + b * M.ldx;
+  for (int k = 0; k < M.in_dim; k += 4) {
+    const float4 x4 = __ldg(reinterpret_cast<const float4*>(xr + k));
+#pragma unroll
+    for (int a = 0; a < NP; ++a) {
+      if (a < n) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(M.w + a * M.ldw + k));
+        u[a] = fmaf(w4.x, x4.x, fmaf(w4.y, x4.y, fmaf(w4.z, x4.z, fmaf(w4.w, x4.w, u[a]))));
+      }
+    }
+  }
+  float* out = M.v_out + b * n;
+#pragma unroll
+  for (int a = 0; a < NP; ++a)
+    if (a < n) out[a] = u[a];
+}
 
 // (value, tag) max over a group of `width` consecutive lanes; ties go to the smaller tag, which is
 // the reference's evaluation order (linear rows, then quadratics, cones, LMI; torch.max first index).

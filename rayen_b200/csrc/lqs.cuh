@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(lqs_max_threads(NP, TM), 1)
     lqs_forward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, float* __restrict__ y,
                        float* __restrict__ kappa_out, int* __restrict__ active_out, long long B, int mode,
                        int L, int lmi_follows, int prune, int* __restrict__ work_list,
-                       int* __restrict__ work_count) {
+                       int* __restrict__ work_count, const MapArgs M) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   const float* cst;
@@ -233,7 +233,10 @@ __global__ void __launch_bounds__(lqs_max_threads(NP, TM), 1)
     for (int t = 0; t < TM; ++t) {
       const long long b = tile * TM + t;
       const bool valid = (tile < n_tiles) && (b < B);
-      load_row<NP>(v + b * ldv, n, vec_in, valid, u[t]);
+      if (M.x)  // fused mapper: every lane of the sample computes the same row (the v_out stores coincide)
+        map_row<NP>(M, b, n, valid, u[t]);
+      else
+        load_row<NP>(v + b * ldv, n, vec_in, valid, u[t]);
       beta[t] = (mode == RAYEN_MODE_RAYEN_OLD && valid) ? __ldg(v + b * ldv + n) : 0.f;
       s[t] = normalize_row<NP>(u[t]);
     }

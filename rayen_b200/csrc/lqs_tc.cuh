@@ -97,7 +97,8 @@ template <int KP>
 __global__ void __launch_bounds__(kTcThreads, 1)
     lqs_tc_forward_kernel(const PlanDev P, const float* __restrict__ v, long long ldv, float* __restrict__ y,
                           float* __restrict__ kappa_out, int* __restrict__ active_out, long long B, int mode,
-                          int lmi_follows, int prune, int* __restrict__ work_list, int* __restrict__ work_count) {
+                          int lmi_follows, int prune, int* __restrict__ work_list, int* __restrict__ work_count,
+                          const MapArgs M) {
   constexpr int CH = (KP >= 16) ? 16 : 8;   // header rows of an item (phi | c_z, h | t), padded
   constexpr int IW = CH + KP;               // rows (= TMEM columns) per item
   constexpr int IPP = kTcPanel / IW;        // items per panel
@@ -227,7 +228,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const long long b = st * 256 + t * 128 + row;
       const bool valid = b < B;
       float u[KP];
-      load_row<KP>(v + b * ldv, n, vec_in, valid, u);
+      if (M.x)
+        map_row<KP>(M, b, n, valid, u);  // fused mapper: v = W x + b, also written to M.v_out
+      else
+        load_row<KP>(v + b * ldv, n, vec_in, valid, u);
       const float beta = (mode == RAYEN_MODE_RAYEN_OLD && valid) ? __ldg(v + b * ldv + n) : 0.f;
       const float s = normalize_row<KP>(u);
       {

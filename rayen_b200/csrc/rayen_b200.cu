@@ -74,7 +74,7 @@ extern "C" int64_t rayen_launch_count(void) { return g_launches.load(); }
 
 // ----------------------------------------------------------------------------- kernel tables
 typedef void (*LqsFwdFn)(const PlanDev, const float*, long long, float*, float*, int*, long long, int, int, int, int,
-                         int*, int*);
+                         int*, int*, const MapArgs);
 typedef void (*LqsBwdFn)(const PlanDev, const float*, long long, const float*, const float*, const int*, float*,
                          long long, long long, int, int*, int*, const float*);
 typedef void (*LmiFwdFn)(const PlanDev, const float*, long long, float*, float*, int*, long long, int, int,
@@ -106,7 +106,7 @@ static LqsFwdFn lqs_fwd_fn(int np, int tm, bool smem) {
   }
 }
 typedef void (*LqsTcFn)(const PlanDev, const float*, long long, float*, float*, int*, long long, int, int, int, int*,
-                        int*);
+                        int*, const MapArgs);
 static LqsTcFn lqs_tc_fn(int kp) {
   switch (kp) {
     case 8: return lqs_tc_forward_kernel<8>;
@@ -560,11 +560,30 @@ static int check_io(const rayen_plan* p, const void* a, const void* b, long long
 
 // ----------------------------------------------------------------------------- forward / backward
 static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa, int32_t* active,
-                        int64_t B, int mode, int want_grad, void* workspace, void* stream_, int stage_mask);
+                        int64_t B, int mode, int want_grad, void* workspace, void* stream_, int stage_mask,
+                        const MapArgs* map = nullptr);
 
 extern "C" int rayen_forward_f32(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa,
                                  int32_t* active, int64_t B, int mode, int want_grad, void* workspace, void* stream_) {
   return forward_impl(p, v, ldv, y, kappa, active, B, mode, want_grad, workspace, stream_, 3);
+}
+
+extern "C" int rayen_forward_mapped_f32(const rayen_plan_t* p, const float* x, int64_t ldx, int32_t in_dim,
+                                        const float* weight, int64_t ldw, const float* bias, float* v_out, float* y,
+                                        float* kappa, int32_t* active, int64_t B, int want_grad, void* workspace,
+                                        void* stream_) {
+  if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "null plan");
+  if (B < 0 || in_dim < 1) return fail(RAYEN_ERR_BAD_ARGUMENT, "bad batch or input dimension");
+  if (B > 0 && (!x || !weight || !v_out)) return fail(RAYEN_ERR_BAD_ARGUMENT, "null tensor");
+  if (!(p->has_lqs || p->dev.lmi_r == 0))
+    return fail(RAYEN_ERR_UNSUPPORTED, "the fused mapper lives in the linear/quadratic/SOC kernel; this plan has only an LMI");
+  if ((in_dim & 3) || (ldx & 3) || (ldw & 3) || ldx < in_dim || ldw < in_dim ||
+      (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(weight) & 15))
+    return fail(RAYEN_ERR_UNSUPPORTED, "the fused mapper needs input_dim and the row strides to be multiples of 4 "
+                                       "floats and 16-byte aligned tensors");
+  MapArgs m{};
+  m.x = x; m.w = weight; m.bias = bias; m.v_out = v_out; m.ldx = ldx; m.ldw = ldw; m.in_dim = in_dim;
+  return forward_impl(p, v_out, p->dev.n, y, kappa, active, B, RAYEN_MODE_RAYEN, want_grad, workspace, stream_, 3, &m);
 }
 extern "C" int rayen_forward_stage_f32(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa,
                                        int32_t* active, int64_t B, int mode, int want_grad, int stage_mask,
@@ -577,7 +596,9 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
                                         int mode, int have_dkappa, int stage_mask, void* workspace, void* stream_);
 
 static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, float* y, float* kappa, int32_t* active,
-                        int64_t B, int mode, int want_grad, void* workspace, void* stream_, int stage_mask) {
+                        int64_t B, int mode, int want_grad, void* workspace, void* stream_, int stage_mask,
+                        const MapArgs* map) {
+  const MapArgs margs = map ? *map : MapArgs{};
   int rc = check_io(p, v, y, B, mode);
   if (rc) return rc;
   if (B == 0) return RAYEN_OK;
@@ -607,7 +628,7 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
       f<<<static_cast<int>(grid), kTcThreads, p->tc_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode,
                                                                            has_lmi ? 1 : 0, use_list ? 1 : 0,
                                                                            use_list ? fwd_list : nullptr,
-                                                                           use_list ? counters : nullptr);
+                                                                           use_list ? counters : nullptr, margs);
       g_launches.fetch_add(1);
       e = cudaGetLastError();
     } else if (e == cudaSuccess) {
@@ -615,7 +636,7 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
       LqsFwdFn f = lqs_fwd_fn(d.np, g.tm, p->lqs_smem);
       f<<<g.grid, g.block, p->lqs_smem_bytes, stream>>>(d, v, ldv, y, kappa, active, B, mode, g.lanes, has_lmi ? 1 : 0,
                                                         use_list ? 1 : 0, use_list ? fwd_list : nullptr,
-                                                        use_list ? counters : nullptr);
+                                                        use_list ? counters : nullptr, margs);
       g_launches.fetch_add(1);
       e = cudaGetLastError();
     }

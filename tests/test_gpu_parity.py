@@ -396,6 +396,48 @@ def test_host_buffer_path_chunked_pipeline(monkeypatch, chunks, batch):
         np.testing.assert_array_equal(gvh.numpy(), gv.astype(np.float32))
 
 
+@pytest.mark.parametrize("which,input_dim,batch", [("readme", 64, 500), ("cfg2", 64, 3000), ("cfg5", 64, 2048),
+                                                    ("cfg3", 20, 777), ("example11", 8, 100)])
+def test_fused_mapper_matches_unfused(which, input_dim, batch):
+    """with ``create_map=True`` the forward kernel computes ``q = mapper(x)`` itself
+    (``rayen_forward_mapped_f32``).  Outputs, input gradients and the mapper's weight/bias gradients must match the
+    unfused path (``nn.Linear`` then the layer) and the float64 oracle applied to the mapper's output."""
+    if which == "readme":
+        spec = synthetic.example_spec("readme")
+    elif which.startswith("example"):
+        spec = synthetic.example_spec(int(which[7:]))
+    else:
+        spec = synthetic.config_spec(which)
+    cs = synthetic.build_constraints(spec)
+    torch.manual_seed(3)
+    layer = ConstraintModule(cs, input_dim=input_dim, create_map=True).to(DEV)
+    x = (torch.rand(batch, input_dim, 1, generator=torch.Generator().manual_seed(5)) * 2 - 1).to(DEV)
+    gy = torch.randn(batch, cs.k, 1, generator=torch.Generator().manual_seed(6)).to(DEV)
+    out = {}
+    for fused in (True, False):
+        layer.fuse_mapper = fused
+        layer.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        before = _cabi.launch_count()
+        y = layer(xi)
+        y.backward(gy)
+        out[fused] = (y.detach().cpu().double().numpy()[:, :, 0], xi.grad.cpu().double().numpy()[:, :, 0],
+                      layer.mapper.weight.grad.cpu().double().numpy(), layer.mapper.bias.grad.cpu().double().numpy(),
+                      _cabi.launch_count() - before)
+    (y_f, gx_f, gw_f, gb_f, n_f), (y_u, gx_u, gw_u, gb_u, n_u) = out[True], out[False]
+    assert n_f == n_u                      # same kernels of this library; the cuBLAS GEMM + bias launches are gone
+    assert rel(y_f, y_u) <= 5e-6
+    q = (x[:, :, 0] @ layer.mapper.weight.t() + layer.mapper.bias).detach().cpu()
+    oset = OracleSet.from_constraints(cs)
+    ok = closed_form_numpy(oset, q.numpy())["margin"] > 1e-3   # away from argmax ties: the two q differ by rounding
+    assert ok.sum() >= 0.7 * batch
+    assert rel(gx_f, gx_u, ok) <= 5e-5
+    y_ref, _ = TorchOracle(oset, torch.float64).forward_backward(q.double(), gy[:, :, 0].cpu().double())
+    assert rel(y_f, y_ref.numpy()) <= TOL
+    if ok.all():
+        assert rel(gw_f, gw_u) <= 5e-5 and rel(gb_f, gb_u) <= 5e-5
+
+
 def test_non_contiguous_and_other_dtypes():
     cs = synthetic.build_constraints(synthetic.config_spec("cfg2"))
     v, gy = synthetic.sample_inputs(100, cs.n, cs.k)
