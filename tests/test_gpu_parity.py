@@ -426,6 +426,8 @@ def test_fused_mapper_matches_unfused(which, input_dim, batch):
                       _cabi.launch_count() - before)
     (y_f, gx_f, gw_f, gb_f, n_f), (y_u, gx_u, gw_u, gb_u, n_u) = out[True], out[False]
     assert n_f == n_u                      # same kernels of this library; the cuBLAS GEMM + bias launches are gone
+    layer.fuse_mapper = "auto"             # the default policy: fused in the launch-bound regime only
+    assert layer._can_fuse_mapper(x[:, :, 0]) == (batch <= 4096)
     assert rel(y_f, y_u) <= 5e-6
     q = (x[:, :, 0] @ layer.mapper.weight.t() + layer.mapper.bias).detach().cpu()
     oset = OracleSet.from_constraints(cs)
