@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RAYEN_ABI_VERSION 9
+#define RAYEN_ABI_VERSION 10
 
 /* error codes (negative); positive return values are cudaError_t */
 #define RAYEN_OK 0
@@ -194,6 +194,16 @@ int64_t rayen_host_workspace_bytes(const rayen_plan_t* plan, int64_t B);
 int rayen_forward_backward_host_f32(const rayen_plan_t* plan, const float* v_host, const float* gy_host,
                                     float* y_host, float* gv_host, int64_t B, void* workspace,
                                     void* cuda_stream);
+
+/* The same step, queued without blocking: several steps can be in flight, so that the copy-in of step i+1 overlaps the
+ * kernels and the copy-out of step i (a double-buffered input pipeline).  `slot` (0..3) names the step for
+ * rayen_forward_backward_host_wait, which blocks until its y_host / gv_host are complete.  Each slot in flight needs
+ * its own `workspace` and host buffers; a slot may be submitted again only after it has been waited for.  The caller's
+ * stream is NOT ordered after the copy-out of a submitted step. */
+int rayen_forward_backward_host_submit_f32(const rayen_plan_t* plan, const float* v_host, const float* gy_host,
+                                           float* y_host, float* gv_host, int64_t B, void* workspace, void* cuda_stream,
+                                           int slot);
+int rayen_forward_backward_host_wait(const rayen_plan_t* plan, int slot);
 
 /*
  * Max constraint residual per sample (<= 0 is feasible), float32, of y [B, ldy] against the ORIGINAL constraints:

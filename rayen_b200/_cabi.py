@@ -17,7 +17,7 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "rayen_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 MODE_RAYEN, MODE_RAYEN_OLD = 0, 1
 FAM_NONE, FAM_LINEAR, FAM_QUAD, FAM_SOC, FAM_LMI = 0, 1, 2, 3, 4
 
@@ -63,6 +63,8 @@ SYMBOLS = {
                                                 ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P]),
     "rayen_host_workspace_bytes": (ctypes.c_int64, [_P, ctypes.c_int64]),
     "rayen_forward_backward_host_f32": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int64, _P, _P]),
+    "rayen_forward_backward_host_submit_f32": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int]),
+    "rayen_forward_backward_host_wait": (ctypes.c_int, [_P, ctypes.c_int]),
     "rayen_violation_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, ctypes.c_int64, _P]),
     "rayen_launch_count": (ctypes.c_int64, []),
     "rayen_plan_kernel_info": (ctypes.c_int, [_P, ctypes.POINTER(RayenKernelInfo)]),

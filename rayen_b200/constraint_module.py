@@ -313,10 +313,14 @@ class ConstraintModule(nn.Module):
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._device_plan(device).set_tuning(samples_per_thread, lanes_per_sample)
 
-    def forward_backward_host(self, v_host, gy_host, y_host=None, gv_host=None, device=None):
+    def forward_backward_host(self, v_host, gy_host, y_host=None, gv_host=None, device=None, slot=None):
         """End-to-end step on HOST buffers through ``rayen_forward_backward_host_f32``: copies ``v_host`` [B,n]
         and ``gy_host`` [B,k] (float32, ideally pinned) to the GPU, runs forward + backward, copies ``y`` [B,k]
-        and ``g_v`` [B,n] back and synchronises.  method='RAYEN' only.  Returns (y_host, gv_host)."""
+        and ``g_v`` [B,n] back and synchronises.  method='RAYEN' only.  Returns (y_host, gv_host).
+
+        ``slot=0..3`` queues the step without blocking (``rayen_forward_backward_host_submit_f32``): several steps can be
+        in flight, each in its own slot with its own host buffers; ``host_wait(slot)`` blocks until that step's outputs are
+        complete, and a slot may be reused only after it has been waited for."""
         utils.verify(self._mode == _cabi.MODE_RAYEN, "forward_backward_host supports method='RAYEN'")
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         for t in (v_host, gy_host):
@@ -330,17 +334,29 @@ class ConstraintModule(nn.Module):
         lib = _cabi.lib()
         dev_plan = self._device_plan(device)
         need = lib.rayen_host_workspace_bytes(dev_plan.handle, B)
-        ws = getattr(self, "_host_ws", None)
-        if ws is None or ws.numel() < need or ws.device != device:
+        pool = self.__dict__.setdefault("_host_ws", {})
+        key = (device.index, 0 if slot is None else int(slot))
+        ws = pool.get(key)
+        if ws is None or ws.numel() < need:
             ws = torch.empty((max(int(need), 256),), dtype=torch.uint8, device=device)
-            self._host_ws = ws
+            pool[key] = ws
         with torch.cuda.device(device):
-            stream = torch.cuda.current_stream(device).cuda_stream
-            rc = lib.rayen_forward_backward_host_f32(dev_plan.handle, v_host.data_ptr(), gy_host.data_ptr(),
-                                                     y_host.data_ptr(), gv_host.data_ptr(), B, ws.data_ptr(),
-                                                     ctypes.c_void_p(stream))
-        _cabi.check(rc, "rayen_forward_backward_host_f32")
+            stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            if slot is None:
+                rc = lib.rayen_forward_backward_host_f32(dev_plan.handle, v_host.data_ptr(), gy_host.data_ptr(),
+                                                         y_host.data_ptr(), gv_host.data_ptr(), B, ws.data_ptr(), stream)
+            else:
+                rc = lib.rayen_forward_backward_host_submit_f32(dev_plan.handle, v_host.data_ptr(), gy_host.data_ptr(),
+                                                                y_host.data_ptr(), gv_host.data_ptr(), B, ws.data_ptr(),
+                                                                stream, int(slot))
+        _cabi.check(rc, "rayen_forward_backward_host_f32" if slot is None else "rayen_forward_backward_host_submit_f32")
         return y_host, gv_host
+
+    def host_wait(self, slot, device=None):
+        """Block until the step submitted in ``slot`` by ``forward_backward_host(..., slot=slot)`` is complete."""
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        _cabi.check(_cabi.lib().rayen_forward_backward_host_wait(self._device_plan(device).handle, int(slot)),
+                    "rayen_forward_backward_host_wait")
 
     def set_pruning(self, enabled=True, device=None):
         """LMI pruning on/off (results are identical; see include/rayen_b200.h)."""

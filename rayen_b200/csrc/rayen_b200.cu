@@ -43,7 +43,7 @@ struct rayen_plan {
   // serialised by host_mu -- the device-pointer entry points never touch them, so the plan stays re-entrant there
   std::mutex* host_mu;
   cudaStream_t host_in, host_out;
-  cudaEvent_t host_ev[2 * 8 + 2];
+  cudaEvent_t host_ev[4][2 * 8 + 2];  // per slot: v_c / gy_c landed (reused: forward_c / backward_c done), start, done
   bool host_ready;
   int host_chunks;  // 0 = automatic (RAYEN_HOST_CHUNKS overrides)
 };
@@ -376,7 +376,8 @@ extern "C" void rayen_plan_destroy(rayen_plan_t* p) {
   if (p->host_ready) {
     cudaStreamDestroy(p->host_in);
     cudaStreamDestroy(p->host_out);
-    for (cudaEvent_t ev : p->host_ev) cudaEventDestroy(ev);
+    for (auto& slot_ev : p->host_ev)
+      for (cudaEvent_t ev : slot_ev) cudaEventDestroy(ev);
   }
   cudaSetDevice(prev);
   delete p->host_mu;
@@ -797,16 +798,14 @@ static int host_chunk_count(const rayen_plan* p, int64_t B) {
   return c;
 }
 
-extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* cp, const float* v_host, const float* gy_host,
-                                               float* y_host, float* gv_host, int64_t B, void* workspace,
-                                               void* stream_) {
-  if (!cp || !v_host || !gy_host || !y_host || !gv_host || (!workspace && B > 0))
-    return fail(RAYEN_ERR_BAD_ARGUMENT, "null argument");
-  if (B == 0) return RAYEN_OK;
-  rayen_plan* p = const_cast<rayen_plan*>(cp);
-  if (!p->host_mu) return fail(RAYEN_ERR_BAD_ARGUMENT, "plan has no host-path state");
+constexpr int kHostSlots = 4;
+
+// Queues one forward+backward step on host buffers (see the header).  join_and_sync: order the caller's stream after
+// the copy-out and block the host (the synchronous entry point); otherwise return as soon as everything is queued and
+// leave completion to rayen_forward_backward_host_wait(slot).
+static int host_step(rayen_plan* p, const float* v_host, const float* gy_host, float* y_host, float* gv_host, int64_t B,
+                     void* workspace, cudaStream_t stream, int slot, bool join_and_sync) {
   std::lock_guard<std::mutex> guard(*p->host_mu);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int64_t n = p->dev.n, k = p->dev.k;
   char* w = static_cast<char*>(workspace);
   float* v = reinterpret_cast<float*>(w); w += round256(B * n * 4);
@@ -822,16 +821,18 @@ extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* cp, const flo
   if (!p->host_ready) {
     e = cudaStreamCreateWithFlags(&p->host_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->host_out, cudaStreamNonBlocking);
-    for (cudaEvent_t& ev : p->host_ev)
-      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto& slot_ev : p->host_ev)
+      for (cudaEvent_t& ev : slot_ev)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
       if (prev != p->device) cudaSetDevice(prev);
       return cuda_fail(e, "creating the copy streams of the host-buffer path");
     }
     p->host_ready = true;
   }
-  // RAYEN_HOST_TRACE=1: print the device-side timeline of this call (development aid, adds event records)
-  static const bool trace = getenv("RAYEN_HOST_TRACE") && atoi(getenv("RAYEN_HOST_TRACE")) != 0;
+  // RAYEN_HOST_TRACE=1: print the device-side timeline of a synchronous call (development aid, adds event records)
+  static const bool trace_env = getenv("RAYEN_HOST_TRACE") && atoi(getenv("RAYEN_HOST_TRACE")) != 0;
+  const bool trace = trace_env && join_and_sync;
   cudaEvent_t tev[40];
   const char* tname[40];
   int ntev = 0;
@@ -843,9 +844,9 @@ extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* cp, const flo
   };
   const int C = host_chunk_count(p, B);
   const int64_t per = ((B + C - 1) / C + 255) / 256 * 256;  // chunk size, multiple of the TC kernel's super-tile
-  cudaEvent_t* ev_v = p->host_ev;                    // [c]     v_c is on the device
-  cudaEvent_t* ev_g = p->host_ev + kHostMaxChunks;   // [c]     gy_c is on the device, later reused: backward_c done
-  cudaEvent_t ev_start = p->host_ev[2 * kHostMaxChunks], ev_done = p->host_ev[2 * kHostMaxChunks + 1];
+  cudaEvent_t* ev_v = p->host_ev[slot];                    // [c]     v_c is on the device
+  cudaEvent_t* ev_g = p->host_ev[slot] + kHostMaxChunks;   // [c]     gy_c is on the device, later reused: backward_c done
+  cudaEvent_t ev_start = p->host_ev[slot][2 * kHostMaxChunks], ev_done = p->host_ev[slot][2 * kHostMaxChunks + 1];
   int rc = 0;
   // the copy streams must not start before what the caller queued on `stream` (e.g. a previous use of the workspace)
   mark(stream, "start");
@@ -899,16 +900,20 @@ extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* cp, const flo
       e = cudaMemcpyAsync(gv_host + lo[c] * n, gv + lo[c] * n, cnt[c] * n * 4, cudaMemcpyDeviceToHost, p->host_out);
     mark(p->host_out, "d2h gv");
   }
-  // join: the caller's stream is complete only when the last copy-out is, then block the host as documented
+  // completion of this step = its last copy-out
   cudaError_t e2 = cudaEventRecord(ev_done, p->host_out);
-  if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(stream, ev_done, 0);
-  cudaError_t e3 = cudaStreamSynchronize(p->host_in);
-  cudaError_t e4 = cudaStreamSynchronize(p->host_out);
-  cudaError_t e5 = cudaStreamSynchronize(stream);
   if (e == cudaSuccess) e = e2;
-  if (e == cudaSuccess) e = e3;
-  if (e == cudaSuccess) e = e4;
-  if (e == cudaSuccess) e = e5;
+  if (join_and_sync) {
+    // the caller's stream is complete only when the last copy-out is, then block the host as documented
+    e2 = cudaStreamWaitEvent(stream, ev_done, 0);
+    cudaError_t e3 = cudaStreamSynchronize(p->host_in);
+    cudaError_t e4 = cudaStreamSynchronize(p->host_out);
+    cudaError_t e5 = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = e2;
+    if (e == cudaSuccess) e = e3;
+    if (e == cudaSuccess) e = e4;
+    if (e == cudaSuccess) e = e5;
+  }
   if (trace && ntev > 0) {
     fprintf(stderr, "rayen host path, %d chunk(s), B = %lld: end of each piece, us after the start\n", used, static_cast<long long>(B));
     for (int i = 1; i < ntev; ++i) {
@@ -921,4 +926,42 @@ extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* cp, const flo
   if (prev != p->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return cuda_fail(e, "host-buffer forward+backward");
   return rc;
+}
+
+static int host_check(const rayen_plan_t* cp, const void* a, const void* b, const void* c, const void* d, int64_t B,
+                      const void* workspace) {
+  if (!cp || !a || !b || !c || !d || (!workspace && B > 0)) return fail(RAYEN_ERR_BAD_ARGUMENT, "null argument");
+  if (B < 0) return fail(RAYEN_ERR_BAD_ARGUMENT, "negative batch");
+  if (!cp->host_mu) return fail(RAYEN_ERR_BAD_ARGUMENT, "plan has no host-path state");
+  return 0;
+}
+
+extern "C" int rayen_forward_backward_host_f32(const rayen_plan_t* cp, const float* v_host, const float* gy_host,
+                                               float* y_host, float* gv_host, int64_t B, void* workspace,
+                                               void* stream_) {
+  const int rc = host_check(cp, v_host, gy_host, y_host, gv_host, B, workspace);
+  if (rc) return rc;
+  if (B == 0) return RAYEN_OK;
+  return host_step(const_cast<rayen_plan*>(cp), v_host, gy_host, y_host, gv_host, B, workspace,
+                   static_cast<cudaStream_t>(stream_), 0, true);
+}
+
+extern "C" int rayen_forward_backward_host_submit_f32(const rayen_plan_t* cp, const float* v_host, const float* gy_host,
+                                                      float* y_host, float* gv_host, int64_t B, void* workspace,
+                                                      void* stream_, int slot) {
+  const int rc = host_check(cp, v_host, gy_host, y_host, gv_host, B, workspace);
+  if (rc) return rc;
+  if (slot < 0 || slot >= kHostSlots) return fail(RAYEN_ERR_BAD_ARGUMENT, "slot must be 0..%d", kHostSlots - 1);
+  if (B == 0) return fail(RAYEN_ERR_BAD_ARGUMENT, "empty batch");
+  return host_step(const_cast<rayen_plan*>(cp), v_host, gy_host, y_host, gv_host, B, workspace,
+                   static_cast<cudaStream_t>(stream_), slot, false);
+}
+
+extern "C" int rayen_forward_backward_host_wait(const rayen_plan_t* cp, int slot) {
+  if (!cp) return fail(RAYEN_ERR_BAD_ARGUMENT, "null plan");
+  if (slot < 0 || slot >= kHostSlots) return fail(RAYEN_ERR_BAD_ARGUMENT, "slot must be 0..%d", kHostSlots - 1);
+  if (!cp->host_ready) return fail(RAYEN_ERR_BAD_ARGUMENT, "nothing was submitted on this plan");
+  cudaError_t e = cudaEventSynchronize(cp->host_ev[slot][2 * kHostMaxChunks + 1]);
+  if (e != cudaSuccess) return cuda_fail(e, "waiting for a submitted host-buffer step");
+  return RAYEN_OK;
 }

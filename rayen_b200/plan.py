@@ -19,7 +19,7 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_NP = 32
 MAX_LMI = 32
 

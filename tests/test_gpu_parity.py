@@ -396,6 +396,30 @@ def test_host_buffer_path_chunked_pipeline(monkeypatch, chunks, batch):
         np.testing.assert_array_equal(gvh.numpy(), gv.astype(np.float32))
 
 
+def test_host_buffer_path_submit_and_wait():
+    """Several host-buffer steps in flight (slots) give, each, the synchronous call's result."""
+    spec = synthetic.config_spec("cfg5")
+    spec["b1"] = spec["b1"] * 4.0
+    cs = synthetic.build_constraints(spec)
+    layer = ConstraintModule(cs, create_map=False).to(DEV)
+    steps = []
+    for i in range(6):
+        v, gy = synthetic.sample_inputs(3000 + 100 * i, cs.n, cs.k, seed_v=20 + i, seed_g=40 + i)
+        steps.append((v.pin_memory(), gy.pin_memory()))
+    want = [layer.forward_backward_host(v, gy, device=DEV) for v, gy in steps]
+    want = [(y.clone(), g.clone()) for y, g in want]
+    got = [None] * len(steps)
+    for i, (v, gy) in enumerate(steps):
+        if i >= 3:
+            layer.host_wait((i - 3) % 4, device=DEV)
+        got[i] = layer.forward_backward_host(v, gy, device=DEV, slot=i % 4)
+    for i in range(len(steps) - 3, len(steps)):
+        layer.host_wait(i % 4, device=DEV)
+    for (y, g), (yw, gw) in zip(got, want):
+        np.testing.assert_array_equal(y.numpy(), yw.numpy())
+        np.testing.assert_array_equal(g.numpy(), gw.numpy())
+
+
 @pytest.mark.parametrize("which,input_dim,batch", [("readme", 64, 500), ("cfg2", 64, 3000), ("cfg5", 64, 2048),
                                                     ("cfg3", 20, 777), ("example11", 8, 100)])
 def test_fused_mapper_matches_unfused(which, input_dim, batch):
