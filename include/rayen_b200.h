@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RAYEN_ABI_VERSION 10
+#define RAYEN_ABI_VERSION 11
 
 /* error codes (negative); positive return values are cudaError_t */
 #define RAYEN_OK 0
@@ -65,10 +65,10 @@ extern "C" {
  *   LMI     F~z_a = sum_i N[i][a] * (-L' F_i L), a < n, each rp x rp (rp = r rounded up to 4, 8, 16
  *           or 32, zero padded), stored [a][row i][lane q][slot t] with column j = q + (rp/4)*t
  *   TC      the LIN/QUAD/SOC/BOUND constants again as the B operand of a tcgen05 GEMM (lqs_tc.cuh): a table
- *           of tc_panels x 24 words {kind, first row, 6 x (item type, item index), pad, 8 item scalars}, then
- *           per panel W_hi and W_lo (96 x tc_kp each, TF32 split) in the K-major no-swizzle operand layout
- *           [k/4][row/8][row%8][k%4].  A linear panel holds 96 rows of D; an item panel holds 96/(ch+kp)
- *           items of ch header rows (phi | c_z, h | t) followed by the kp rows of the triangular factor.
+ *           of tc_panels x 32 words {kind, first row, 8 x (item type, item index), pad to 24, 8 item scalars}, then
+ *           per panel W_hi and W_lo (128 x tc_kp each, TF32 split) in the K-major no-swizzle operand layout
+ *           [k/4][row/8][row%8][k%4].  A linear panel holds 128 rows of D; an item panel holds 128/(8+kp)
+ *           items of 8 header rows (phi | c_z, h | t) followed by the kp rows of the triangular factor.
  *   VIOL    the ORIGINAL constraints in the ambient space for rayen_violation_f32 (k4 = k rounded up to 4):
  *           viol_in rows {a[k4], b, 0,0,0} of A1 y <= b1, viol_eq rows of A2 y = b2, per quadratic
  *           {P[k4][k4], q[k4], r,0,0,0}, per cone {r_M, d, 0, 0, c[k4], r_M rows {M_i[k4], s_i,0,0,0}}
@@ -95,7 +95,7 @@ typedef struct RayenPlanDesc {
   int32_t quad_stride;
   int32_t soc_stride;
   int32_t lmi_prune; /* 1: the BOUND section is valid and pruning may be used */
-  int32_t tc_panels; /* number of 96-row panels of the tensor-core section */
+  int32_t tc_panels; /* number of 128-row panels of the tensor-core section */
   int32_t tc_kp;     /* K of the tensor-core GEMM: max(8, np) */
   int32_t viol_in;   /* inequality rows of the VIOL section */
   int32_t viol_eq;   /* equality rows of the VIOL section */

@@ -17,7 +17,7 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "rayen_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 MODE_RAYEN, MODE_RAYEN_OLD = 0, 1
 FAM_NONE, FAM_LINEAR, FAM_QUAD, FAM_SOC, FAM_LMI = 0, 1, 2, 3, 4
 

@@ -13,9 +13,9 @@
 // Roles (warp-specialised, one CTA per SM, persistent over super-tiles of 2 x 128 samples):
 //   warps 0-7  load v, normalise, write U_hi/U_lo as K-major operand tiles; later read D from TMEM and reduce;
 //              finally apply the scale step and write y / kappa / active (and the LMI work list)
-//   warp 8     TMA producer: streams the 96-row panels of W (hi + lo) through a 3-stage shared-memory ring
+//   warp 8     TMA producer: streams the 128-row panels of W (hi + lo) through a 4-stage shared-memory ring
 //   warps 9,10 MMA issuers (one elected lane each, one per sample tile); warp 9 owns the TMEM allocation
-// Pipelines: W ring full/empty, TMEM accumulator full/empty (two 96-column buffers per sample tile), U ready.
+// Pipelines: W ring full/empty, TMEM accumulator full/empty (two 128-column buffers per sample tile), U ready.
 #pragma once
 #include "common.cuh"
 #include "lqs.cuh"
@@ -29,11 +29,11 @@ __device__ long long g_tc_trace[4096];
 #define TC_STAMP(slot) do { } while (0)
 #endif
 
-constexpr int kTcPanel = 96;
+constexpr int kTcPanel = 128;  // rows of W per panel = MMA N (N = 128: 65 cycles per MMA against 57 at N = 96, scripts/mma_probe.cu)
 constexpr int kTcStages = 4;
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;  // + TMA warp + two MMA-issuing warps (one per sample tile)
-constexpr int kTcTableWords = 24;
+constexpr int kTcTableWords = 32;  // per panel: kind, first row, 8 x (item type, item index), pad to 24, 8 item scalars
 
 // ----------------------------------------------------------------------------- tcgen05 / mbarrier helpers
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                           float* __restrict__ kappa_out, int* __restrict__ active_out, long long B, int mode,
                           int lmi_follows, int prune, int* __restrict__ work_list, int* __restrict__ work_count,
                           const MapArgs M) {
-  constexpr int CH = (KP >= 16) ? 16 : 8;   // header rows of an item (phi | c_z, h | t), padded
+  constexpr int CH = 8;                     // header rows of an item (phi | c_z, h | t), padded
   constexpr int IW = CH + KP;               // rows (= TMEM columns) per item
   constexpr int IPP = kTcPanel / IW;        // items per panel
   constexpr int KC = KP / 4;                // 16-byte chunks along K
@@ -264,44 +264,42 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (2 * t + buf) * kTcPanel;
         const int* pt = reinterpret_cast<const int*>(table + p * kTcTableWords);
         if (pt[0] == 0) {
-          // ---- 96 rows of D: kappa_j = D_j . u                   (reference constraint_module.py:353)
+          // ---- 128 rows of D, 64 at a time: kappa_j = D_j . u         (reference constraint_module.py:353)
           const int base = pt[1];
-          float x[kTcPanel];
 #pragma unroll
-          for (int c = 0; c < kTcPanel / 16; ++c) tmem_ld16(taddr + 16 * c, x + 16 * c);
-          tmem_wait_ld();
-          // max first (3-input max tree), index only when the running best actually moves: the best of a
-          // sample changes O(log rows) times, so the per-column compare/select chain is almost never needed
-          float mx = x[0];
+          for (int hh = 0; hh < 2; ++hh) {
+            float x[64];
 #pragma unroll
-          for (int j = 1; j + 1 < kTcPanel; j += 2) mx = fmaxf(mx, fmaxf(x[j], x[j + 1]));
-          mx = fmaxf(mx, x[kTcPanel - 1]);
-          if (mx > best) {
-            best = mx;
-            int arg = 0;
+            for (int c = 0; c < 4; ++c) tmem_ld16(taddr + 64 * hh + 16 * c, x + 16 * c);
+            tmem_wait_ld();
+            // max first (3-input max tree), index only when the running best actually moves: the best of a
+            // sample changes O(log rows) times, so the per-column compare/select chain is almost never needed
+            float mx = x[0];
 #pragma unroll
-            for (int j = kTcPanel - 1; j >= 0; --j)
-              if (x[j] == mx) arg = j;  // first index on ties, like torch.max
-            tag = make_tag(RAYEN_FAM_LINEAR, base + arg);
+            for (int j = 1; j + 1 < 64; j += 2) mx = fmaxf(mx, fmaxf(x[j], x[j + 1]));
+            mx = fmaxf(mx, x[63]);
+            if (mx > best) {
+              best = mx;
+              int arg = 0;
+#pragma unroll
+              for (int j = 63; j >= 0; --j)
+                if (x[j] == mx) arg = j;  // first index on ties, like torch.max
+              tag = make_tag(RAYEN_FAM_LINEAR, base + 64 * hh + arg);
+            }
           }
         } else {
-          // ---- items: header rows (phi | c_z, h | t) then the KP rows of a triangular factor
-          float xi[IPP * IW];
-#pragma unroll
-          for (int c = 0; c < IPP * IW / CH; ++c) {
-            if constexpr (CH == 16)
-              tmem_ld16(taddr + CH * c, xi + CH * c);
-            else
-              tmem_ld8(taddr + CH * c, xi + CH * c);
-          }
-          tmem_wait_ld();
+          // ---- items, one after the other: 8 header rows (phi | c_z, h | t) then the KP rows of a triangular factor
 #pragma unroll
           for (int sl = 0; sl < IPP; ++sl) {
             const int type = pt[2 + 2 * sl], idx = pt[3 + 2 * sl];
-            if (type == 0) continue;
-            const float scal = table[p * kTcTableWords + 16 + sl];
-            const float* h = xi + sl * IW;
-            const float* x = h + CH;
+            if (type == 0) continue;  // the table is the same for every thread
+            float xi[IW];
+#pragma unroll
+            for (int c = 0; c < IW / 8; ++c) tmem_ld8(taddr + sl * IW + 8 * c, xi + 8 * c);
+            tmem_wait_ld();
+            const float scal = table[p * kTcTableWords + 24 + sl];
+            const float* h = xi;
+            const float* x = xi + CH;
             float ss = 0.f;
 #pragma unroll
             for (int j = 0; j < KP; ++j) ss = fmaf(x[j], x[j], ss);

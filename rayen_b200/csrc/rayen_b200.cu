@@ -233,7 +233,7 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
     return fail(RAYEN_ERR_BAD_ARGUMENT, "violation sections do not fit the block");
   if (d->tc_panels < 1 || (d->tc_kp != 8 && d->tc_kp != 16 && d->tc_kp != 32) || d->tc_kp < d->np || d->off_tc % 4 ||
       d->off_tc < d->off_lmi ||
-      d->off_tc + static_cast<int64_t>(d->tc_panels) * (24 + 2 * 96 * d->tc_kp) > d->blob_words)
+      d->off_tc + static_cast<int64_t>(d->tc_panels) * (kTcTableWords + 2 * kTcPanel * d->tc_kp) > d->blob_words)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "tensor-core section does not fit the block");
 
   if (d->lmitc_panels < 0 || d->off_lmitc < 0 || d->off_lmitc % 4 || d->off_lmitc >= d->blob_words ||

@@ -19,7 +19,7 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_NP = 32
 MAX_LMI = 32
 
@@ -69,7 +69,8 @@ def packed_triangular_words(np_):
     return sum(np_ - (i // 4) * 4 for i in range(np_))
 
 
-TC_PANEL = 96   # rows of W per tensor-core panel (MMA N)
+TC_PANEL = 128  # rows of W per tensor-core panel (MMA N)
+TC_TABLE_WORDS = 32
 LMI_TC_PANEL = 128  # entries of the LMI matrix per panel of the contraction GEMM (MMA N)
 
 
@@ -258,10 +259,10 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
 
     # ---- tensor-core layout of the same linear/quadratic/SOC/bound constants (lqs_tc.cuh): every constraint
     # becomes rows of one [rows x K] matrix W, so that all dot products of a 128-sample tile are ONE tcgen05
-    # GEMM D = U W' with the result in tensor memory.  Rows are grouped in panels of 96; operands are split
+    # GEMM D = U W' with the result in tensor memory.  Rows are grouped in panels of 128; operands are split
     # W = W_hi + W_lo (both TF32-representable) for the error-compensated 3xTF32 product.
     kp = max(8, np_)
-    ch = 16 if kp >= 16 else 8
+    ch = 8
     iw = ch + kp
     ipp = TC_PANEL // iw
     Wrows, table = [], []
@@ -278,7 +279,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
         rows = Dk[base:base + TC_PANEL]
         blk[:rows.shape[0]] = rows
         Wrows.append(blk)
-        table.append(([0, base] + [0] * 12, [0.0] * 8))
+        table.append(([0, base] + [0] * 16, [0.0] * 8))
     items = []
     for i, (phi_z, Delta_z, G) in enumerate(quad_f64):
         hdr = np.zeros((ch, kp))
@@ -295,7 +296,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
         items.append((5, 0, float(lmi_r), np.concatenate((hdr, tri_dense(_triangular_factor(gram, np_))))))
     for base in range(0, len(items), ipp):
         blk = np.zeros((TC_PANEL, kp))
-        ints, flts = [1, 0] + [0] * 12, [0.0] * 8
+        ints, flts = [1, 0] + [0] * 16, [0.0] * 8
         for s_, (typ, idx, scal, rows) in enumerate(items[base:base + ipp]):
             blk[s_ * iw:(s_ + 1) * iw] = rows
             ints[2 + 2 * s_], ints[3 + 2 * s_] = typ, idx
@@ -303,10 +304,10 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
         Wrows.append(blk)
         table.append((ints, flts))
     tc_panels = len(Wrows)
-    tab = np.zeros((tc_panels, 24), dtype=np.float32)
+    tab = np.zeros((tc_panels, TC_TABLE_WORDS), dtype=np.float32)
     for pi, (ints, flts) in enumerate(table):
-        tab[pi, :14] = np.asarray(ints, dtype=np.int32).view(np.float32)
-        tab[pi, 16:24] = np.asarray(flts, dtype=np.float32)
+        tab[pi, :18] = np.asarray(ints, dtype=np.int32).view(np.float32)
+        tab[pi, 24:32] = np.asarray(flts, dtype=np.float32)
     off_tc = add_f32(tab)
     for blk in Wrows:
         hi, lo = split_tf32(blk.astype(np.float32))
