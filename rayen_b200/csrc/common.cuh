@@ -91,6 +91,14 @@ __device__ __forceinline__ void stage_bulk(float* dst_smem, const float* src, in
   }
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// The LMI forward kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization right behind the
+// linear/quadratic/SOC kernel: its CTAs are scheduled (and run their prologue: barrier init, TMEM allocation, the TMA
+// staging of the constant matrices) while the previous kernel drains, and pdl_wait() blocks until that kernel has
+// completed and its writes (kappa, active, the work list) are visible.  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- small helpers
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 

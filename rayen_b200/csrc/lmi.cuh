@@ -639,6 +639,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float* scratch_base;
+  pdl_wait();  // launched behind the linear/quadratic/SOC kernel: its kappa / active / work list must be complete
   // dense mode: every sample; list mode: only the samples the LQS kernel could not prune
   const long long total = work_list ? static_cast<long long>(*work_count) : B;
   // chunk c (MPW samples) belongs to CTA c % gridDim: a CTA without a chunk does not stage F~z at all

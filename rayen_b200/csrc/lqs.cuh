@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(lqs_max_threads(NP, TM), 1)
                        float* __restrict__ kappa_out, int* __restrict__ active_out, long long B, int mode,
                        int L, int lmi_follows, int prune, int* __restrict__ work_list,
                        int* __restrict__ work_count, const MapArgs M) {
+  pdl_launch_dependents();  // see common.cuh
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   const float* cst;

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   constexpr uint32_t LBO_A = (128 / 8) * 128, LBO_W = (kTcPanel / 8) * 128, SBO = 128;
   constexpr uint32_t IDESC = umma_idesc_tf32(128, kTcPanel);
 
+  pdl_launch_dependents();  // the LMI kernel behind this one may start scheduling its CTAs (it waits before it reads)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* a_full = &bars[0];

@@ -180,6 +180,25 @@ static size_t lmi_smem(int rp, bool smem, int n, int threads) {
   }
 }
 
+// Launch `fn` behind the previous kernel of the stream with programmatic stream serialization (see common.cuh):
+// its CTAs may be scheduled while that kernel drains; the kernel itself waits (pdl_wait) before it reads.
+static cudaError_t launch_lmi_forward(LmiFwdFn fn, int blocks, int threads, size_t smem, cudaStream_t stream, bool pdl,
+                                      const PlanDev& d, const float* v, long long ldv, float* y, float* kappa,
+                                      int* active, long long B, int mode, int has_prior, const int* list,
+                                      const int* count, float* dkappa) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, fn, d, v, ldv, y, kappa, active, B, mode, has_prior, list, count, dkappa);
+}
+
 static int allow_smem(const void* fn, size_t bytes) {
   if (bytes > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
@@ -645,26 +664,31 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
   if (e == cudaSuccess && has_lmi && (stage_mask & 2)) {
     const int mpw = 32 / (d.lmi_rp / 4);
     const bool grad = want_grad != 0;
+    // the kernel right before this one in the stream is our own linear/quadratic/SOC kernel: launch behind it
+    static const bool pdl_on = !(getenv("RAYEN_PDL") && atoi(getenv("RAYEN_PDL")) == 0);
+    const bool behind_lqs = pdl_on && (stage_mask & 1) && run_lqs;
     if (lmi_use_tc(p, grad, use_list)) {
       // one CTA per SM, persistent over passes of 8 warps x mpw samples; short batches still start one CTA per
       // warp's worth of samples so that the kernel can spread them (it re-derives the split from the list length)
       long long blocks = (B + mpw - 1) / mpw;
       if (blocks > p->sm_count) blocks = p->sm_count;
       LmiFwdFn lf = lmi_fwd_tc_fn(d.lmi_rp, grad && p->lmi_tc_grad_fsmem, grad);
-      lf<<<static_cast<int>(blocks), kLmiTcThreads, grad ? p->lmi_tc_grad_smem_bytes : p->lmi_tc_smem_bytes, stream>>>(
-          d, v, ldv, y, kappa, active, B, mode, run_lqs ? 1 : 0, use_list ? fwd_list : nullptr,
-          use_list ? counters : nullptr, grad ? ws_dkappa(workspace, B) : nullptr);
+      e = launch_lmi_forward(lf, static_cast<int>(blocks), kLmiTcThreads,
+                             grad ? p->lmi_tc_grad_smem_bytes : p->lmi_tc_smem_bytes, stream, behind_lqs, d, v, ldv, y,
+                             kappa, active, B, mode, run_lqs ? 1 : 0, use_list ? fwd_list : nullptr,
+                             use_list ? counters : nullptr, grad ? ws_dkappa(workspace, B) : nullptr);
     } else {
       const int threads = grad ? 256 : p->lmi_fwd_threads;
       long long blocks = (B + static_cast<long long>(mpw) * (threads / 32) - 1) / (static_cast<long long>(mpw) * (threads / 32));
       if (blocks > p->sm_count) blocks = p->sm_count;
       LmiFwdFn lf = lmi_fwd_fn(d.lmi_rp, p->lmi_smem, threads, grad);
-      lf<<<static_cast<int>(blocks), threads, grad ? p->lmi_grad_smem_bytes : p->lmi_smem_bytes, stream>>>(
-          d, v, ldv, y, kappa, active, B, mode, run_lqs ? 1 : 0, use_list ? fwd_list : nullptr,
-          use_list ? counters : nullptr, grad ? ws_dkappa(workspace, B) : nullptr);
+      e = launch_lmi_forward(lf, static_cast<int>(blocks), threads, grad ? p->lmi_grad_smem_bytes : p->lmi_smem_bytes,
+                             stream, behind_lqs, d, v, ldv, y, kappa, active, B, mode, run_lqs ? 1 : 0,
+                             use_list ? fwd_list : nullptr, use_list ? counters : nullptr,
+                             grad ? ws_dkappa(workspace, B) : nullptr);
     }
     g_launches.fetch_add(1);
-    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
   }
   if (prev != p->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return cuda_fail(e, "forward launch");
