@@ -262,7 +262,18 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group(backend="nccl", device_id=device)
+        # NCCL prints its version banner to stdout (C level) at communicator creation: keep stdout for the JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group(backend="nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize(device)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     shp = synthetic.CONFIG_SHAPES[args.workload]
     batch = args.batch or shp["batch"]
