@@ -532,6 +532,40 @@ __device__ __forceinline__ void warp_load_rows(const float* __restrict__ base, i
   }
   __syncwarp();
 }
+// Two tensors at once: all global loads are issued before the first shared-memory store, so the two tiles cost one
+// memory round trip instead of two.
+template <int NP>
+__device__ __forceinline__ void warp_load_rows2(const float* __restrict__ base_a, const float* __restrict__ base_b,
+                                                int rows_valid, float* tile_a, float* tile_b, int lane,
+                                                float (&xa)[NP], float (&xb)[NP]) {
+  constexpr int C4 = NP / 4, TS = NP + 4;
+  const float4* sa = reinterpret_cast<const float4*>(base_a);
+  const float4* sb = reinterpret_cast<const float4*>(base_b);
+  float4 ta[C4], tb[C4];
+#pragma unroll
+  for (int it = 0; it < C4; ++it) {
+    const int i = it * 32 + lane;
+    const bool ok = i / C4 < rows_valid;
+    ta[it] = ok ? __ldg(sa + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    tb[it] = ok ? __ldg(sb + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int it = 0; it < C4; ++it) {
+    const int i = it * 32 + lane;
+    const int r = i / C4, c4 = i % C4;
+    *reinterpret_cast<float4*>(tile_a + r * TS + 4 * c4) = ta[it];
+    *reinterpret_cast<float4*>(tile_b + r * TS + 4 * c4) = tb[it];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int kk = 0; kk < C4; ++kk) {
+    const float4 a = *reinterpret_cast<const float4*>(tile_a + lane * TS + 4 * kk);
+    const float4 b = *reinterpret_cast<const float4*>(tile_b + lane * TS + 4 * kk);
+    xa[4 * kk + 0] = a.x; xa[4 * kk + 1] = a.y; xa[4 * kk + 2] = a.z; xa[4 * kk + 3] = a.w;
+    xb[4 * kk + 0] = b.x; xb[4 * kk + 1] = b.y; xb[4 * kk + 2] = b.z; xb[4 * kk + 3] = b.w;
+  }
+  __syncwarp();
+}
 template <int NP>
 __device__ __forceinline__ void warp_store_rows(float* __restrict__ base, int rows_valid, float* tile, int lane,
                                                 const float (&x)[NP]) {
@@ -553,7 +587,7 @@ __device__ __forceinline__ void warp_store_rows(float* __restrict__ base, int ro
 constexpr int kBwdThreads = 128;
 template <int NP>
 __host__ __device__ constexpr size_t lqs_bwd_smem_bytes() {
-  return static_cast<size_t>(kBwdThreads / 32) * 32 * (NP + 4) * sizeof(float);
+  return static_cast<size_t>(kBwdThreads / 32) * 2 * 32 * (NP + 4) * sizeof(float);  // two tiles per warp
 }
 
 // One thread per sample, one warp per 32 consecutive samples.  Samples whose binding constraint is the LMI (and
@@ -567,7 +601,8 @@ __global__ void __launch_bounds__(kBwdThreads)
   extern __shared__ __align__(16) float bwd_tiles[];
   const int n = P.n;
   const int lane = threadIdx.x & 31;
-  float* tile = bwd_tiles + (threadIdx.x >> 5) * 32 * (NP + 4);
+  float* tile = bwd_tiles + (threadIdx.x >> 5) * 2 * 32 * (NP + 4);
+  float* tile2 = tile + 32 * (NP + 4);
   const bool vec_v = ((n & 3) == 0) && ((ldv & 3) == 0) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
   const bool vec_gy = ((P.k & 3) == 0) && ((reinterpret_cast<uintptr_t>(gy) & 15) == 0);
   const bool vec_gv = ((n & 3) == 0) && ((ldgv & 3) == 0) && ((reinterpret_cast<uintptr_t>(gv) & 15) == 0);
@@ -582,35 +617,51 @@ __global__ void __launch_bounds__(kBwdThreads)
     const int rows_valid = (B - base < 32) ? static_cast<int>(B - base) : 32;
     const float kap = valid ? __ldg(kappa + b) : 1.f;
     const int tag = valid ? __ldg(active + b) : 0;
-    float u[NP];
-    if (tile_v)
-      warp_load_rows<NP>(v + base * n, rows_valid, tile, lane, u);
-    else
-      load_row<NP>(v + b * ldv, n, vec_v, valid, u);
+    float u[NP], gz[NP], dk[NP], g[NP];
+    if (tile_v && tile_gy) {
+      warp_load_rows2<NP>(v + base * n, gy + base * P.k, rows_valid, tile, tile2, lane, u, gz);
+    } else {
+      if (tile_v)
+        warp_load_rows<NP>(v + base * n, rows_valid, tile, lane, u);
+      else
+        load_row<NP>(v + b * ldv, n, vec_v, valid, u);
+      if (tile_gy) {
+        warp_load_rows<NP>(gy + base * P.k, rows_valid, tile, lane, gz);
+      } else if (valid) {
+        load_gz<NP>(P, gy + b * P.k, vec_gy, gz);
+      } else {
+#pragma unroll
+        for (int a = 0; a < NP; ++a) gz[a] = 0.f;
+      }
+    }
+    // the row of D of a linear-bound sample is fetched as soon as the tag is known (before |v| says whether the
+    // sample sits on the boundary at all): one more load in flight next to the tiles
+    const int fam = tag_family(tag);
+#pragma unroll
+    for (int a = 0; a < NP; ++a) dk[a] = 0.f;
+    if (valid && fam == RAYEN_FAM_LINEAR) {
+      const float* p = P.blob + P.off_lin + (tag_index(tag) >> 2) * P.lin_stride + (tag_index(tag) & 3) * 4;
+#pragma unroll
+      for (int kk = 0; kk < NP / 4; ++kk) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(p + kk * 16));
+        dk[4 * kk + 0] = d.x;
+        dk[4 * kk + 1] = d.y;
+        dk[4 * kk + 2] = d.z;
+        dk[4 * kk + 3] = d.w;
+      }
+    }
     const float s = normalize_row<NP>(u);
     const float beta = (mode == RAYEN_MODE_RAYEN_OLD && valid) ? __ldg(v + b * ldv + n) : 0.f;
     const bool boundary = valid && ((mode == RAYEN_MODE_RAYEN_OLD) ? (kap > 0.f) : (1.0f / kap < s));
-    const bool lmi_bound = boundary && tag_family(tag) == RAYEN_FAM_LMI;
+    const bool lmi_bound = boundary && fam == RAYEN_FAM_LMI;
     // needs the eigenvector and the forward pass did not leave d kappa/du behind: queued for lmi_backward_kernel
     const bool queued = lmi_bound && !dkappa;
     if (queued && work_list) work_list[atomicAdd(work_count, 1)] = static_cast<int>(b);
-    float gz[NP], dk[NP], g[NP];
-    if (tile_gy) {
-      warp_load_rows<NP>(gy + base * P.k, rows_valid, tile, lane, gz);
-    } else if (valid) {
-      load_gz<NP>(P, gy + b * P.k, vec_gy, gz);
-    } else {
-#pragma unroll
-      for (int a = 0; a < NP; ++a) gz[a] = 0.f;
-    }
     if (lmi_bound && !queued) {
 #pragma unroll
       for (int a = 0; a < NP; ++a) dk[a] = (a < n) ? __ldg(dkappa + b * n + a) : 0.f;
-    } else if (boundary && !queued) {
+    } else if (boundary && !queued && fam != RAYEN_FAM_LINEAR) {
       dkappa_lqs<NP>(P, tag, kap, u, dk);
-    } else {
-#pragma unroll
-      for (int a = 0; a < NP; ++a) dk[a] = 0.f;
     }
     float gbeta = 0.f;
     backward_tail<NP>(mode, s, kap, beta, u, gz, dk, boundary && !queued, g, &gbeta);

@@ -732,7 +732,7 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
     if (has_lmi) e = cudaMemsetAsync(counters + 1, 0, sizeof(int), stream);
     LqsBwdFn f = lqs_bwd_fn(d.np);
     if (e == cudaSuccess) {
-      const size_t tile_bytes = static_cast<size_t>(block / 32) * 32 * (d.np + 4) * sizeof(float);
+      const size_t tile_bytes = static_cast<size_t>(block / 32) * 2 * 32 * (d.np + 4) * sizeof(float);
       f<<<static_cast<int>(grid), block, tile_bytes, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode, bwd_list,
                                                       has_lmi ? counters + 1 : nullptr,
                                                       (has_lmi && have_dkappa) ? ws_dkappa(workspace, B) : nullptr);
