@@ -584,6 +584,70 @@ __device__ __forceinline__ void warp_store_rows(float* __restrict__ base, int ro
   __syncwarp();
 }
 
+// d kappa/du of ONE quadratic- or cone-bound sample with the whole warp on it (lane j owns component j).  All NP rows
+// of the packed triangular factor are loaded first (one coalesced line each, one L2 round trip), T u is NP
+// independent warp shuffle sums, T'(T u) one FMA per row.  The per-thread dkappa_lqs walks ~270 dependent 16-byte
+// loads and ~1000 FMAs on a single lane: with one or two such samples in a warp that was the tail of the whole
+// backward kernel (CTAs with such a sample: 6.4-7.3 us, CTAs without: 2.9 us; scripts/bwd_trace.py).
+template <int NP>
+__device__ __forceinline__ float dkappa_tri_warp(const PlanDev& P, int fam, int idx, float kap, float uj, int lane) {
+  constexpr int TRI = (NP / 4) * (NP / 4 + 1) * 8;
+  const bool soc = fam == RAYEN_FAM_SOC;
+  const float* item = soc ? P.blob + P.off_soc + idx * P.soc_stride : P.blob + P.off_quad + idx * P.quad_stride;
+  const float* tri = item + (soc ? 2 * NP : NP);
+  const bool in = lane < NP;
+  float t[NP], w[NP];
+  {
+    int pos = 0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int c0 = 4 * (i / 4);
+      t[i] = (in && lane >= c0) ? __ldg(tri + pos + (lane - c0)) : 0.f;
+      pos += NP - c0;
+    }
+  }
+  const float cj = in ? __ldg(item + lane) : 0.f;                 // phi_z (quadratic) or c_z (cone)
+  const float hj = (in && soc) ? __ldg(item + NP + lane) : 0.f;
+  const float A = soc ? __ldg(item + 2 * NP + TRI) : 1.f;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) w[i] = t[i] * uj;
+  float cu = cj * uj, hb = hj * uj;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) w[i] += __shfl_xor_sync(0xffffffffu, w[i], off);
+    cu += __shfl_xor_sync(0xffffffffu, cu, off);
+    hb += __shfl_xor_sync(0xffffffffu, hb, off);
+  }
+  float g = 0.f, ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    ss = fmaf(w[i], w[i], ss);
+    g = fmaf(w[i], t[i], g);
+  }
+  if (!soc) {
+    const float root = sqrtf(ss);
+    const float inv = root > 0.f ? 1.0f / root : 0.f;
+    return fmaf(g, inv, cj);                                      // phi_z + G'(G u)/|G u|   (reference :360-381)
+  }
+  float root;
+  (void)soc_root(A, hb, fmaf(-cu, cu, ss), &root);
+  // (kappa h + R'R u - (c_z.u) c_z)/sqrt(disc) (reference :383-399, :339-348); the reference's autograd is NaN at
+  // disc == 0 (tangent ray, measure zero) -- emit 0 there
+  const float inv = root > 0.f ? 1.0f / root : 0.f;
+  return (fmaf(kap, hj, g) - cu * cj) * inv;
+}
+
+#ifdef RAYEN_BWD_TRACE
+// development build only (scripts/bwd_trace.py): per-CTA globaltimer start/end and phase stamps of warp 0
+__device__ long long g_bwd_trace[8192];
+#define BWD_STAMP(slot) do { if ((threadIdx.x & 127) == 0 && blockIdx.x < 256) g_bwd_trace[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+#define BWD_GT(slot) do { if (threadIdx.x == 0 && blockIdx.x < 256) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_bwd_trace[4096 + blockIdx.x * 2 + (slot)] = t_; } } while (0)
+#else
+#define BWD_STAMP(slot) do { } while (0)
+#define BWD_GT(slot) do { } while (0)
+#endif
+
 constexpr int kBwdThreads = 128;
 template <int NP>
 __host__ __device__ constexpr size_t lqs_bwd_smem_bytes() {
@@ -599,6 +663,8 @@ __global__ void __launch_bounds__(kBwdThreads)
                         long long ldgv, long long B, int mode, int* __restrict__ work_list,
                         int* __restrict__ work_count, const float* __restrict__ dkappa) {
   extern __shared__ __align__(16) float bwd_tiles[];
+  BWD_GT(0);
+  BWD_STAMP(0);
   const int n = P.n;
   const int lane = threadIdx.x & 31;
   float* tile = bwd_tiles + (threadIdx.x >> 5) * 2 * 32 * (NP + 4);
@@ -650,7 +716,9 @@ __global__ void __launch_bounds__(kBwdThreads)
         dk[4 * kk + 3] = d.w;
       }
     }
+    BWD_STAMP(1);
     const float s = normalize_row<NP>(u);
+    BWD_STAMP(2);
     const float beta = (mode == RAYEN_MODE_RAYEN_OLD && valid) ? __ldg(v + b * ldv + n) : 0.f;
     const bool boundary = valid && ((mode == RAYEN_MODE_RAYEN_OLD) ? (kap > 0.f) : (1.0f / kap < s));
     const bool lmi_bound = boundary && fam == RAYEN_FAM_LMI;
@@ -660,18 +728,51 @@ __global__ void __launch_bounds__(kBwdThreads)
     if (lmi_bound && !queued) {
 #pragma unroll
       for (int a = 0; a < NP; ++a) dk[a] = (a < n) ? __ldg(dkappa + b * n + a) : 0.f;
-    } else if (boundary && !queued && fam != RAYEN_FAM_LINEAR) {
+    }
+    // quadratic / cone gradients: a few such samples per warp are taken one at a time by the whole warp (the row
+    // tiles still hold the raw v); many of them run in parallel, one per thread
+    const bool needs_tri = boundary && !queued && (fam == RAYEN_FAM_QUAD || fam == RAYEN_FAM_SOC);
+    unsigned todo = __ballot_sync(0xffffffffu, needs_tri);
+    if (tile_v && tile_gy && todo != 0u && __popc(todo) <= 6) {
+      constexpr int TS = NP + 4;
+      const float inv_s = 1.0f / fmaxf(s, kNormEps);
+      while (todo) {
+        const int r = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int fam_r = __shfl_sync(0xffffffffu, fam, r), idx_r = __shfl_sync(0xffffffffu, tag_index(tag), r);
+        const float kap_r = __shfl_sync(0xffffffffu, kap, r), inv_r = __shfl_sync(0xffffffffu, inv_s, r);
+        const float uj = (lane < NP) ? tile[r * TS + lane] * inv_r : 0.f;
+        const float dj = dkappa_tri_warp<NP>(P, fam_r, idx_r, kap_r, uj, lane);
+        if (lane < NP) tile2[r * TS + lane] = dj;   // g_y of this row is already in registers
+        __syncwarp();
+        if (lane == r) {
+#pragma unroll
+          for (int kk = 0; kk < NP / 4; ++kk) {
+            const float4 d = *reinterpret_cast<const float4*>(tile2 + r * TS + 4 * kk);
+            dk[4 * kk + 0] = d.x;
+            dk[4 * kk + 1] = d.y;
+            dk[4 * kk + 2] = d.z;
+            dk[4 * kk + 3] = d.w;
+          }
+        }
+      }
+      __syncwarp();
+    } else if (needs_tri) {
       dkappa_lqs<NP>(P, tag, kap, u, dk);
     }
+    BWD_STAMP(3);
     float gbeta = 0.f;
     backward_tail<NP>(mode, s, kap, beta, u, gz, dk, boundary && !queued, g, &gbeta);
+    BWD_STAMP(4);
     if (tile_gv && __all_sync(0xffffffffu, !queued)) {
       warp_store_rows<NP>(gv + base * n, rows_valid, tile, lane, g);
     } else if (valid && !queued) {
       store_row<NP>(gv + b * ldgv, n, vec_gv, g);
     }
     if (valid && !queued && mode == RAYEN_MODE_RAYEN_OLD) gv[b * ldgv + n] = gbeta;
+    BWD_STAMP(5);
   }
+  BWD_GT(1);
 }
 
 }  // namespace rayen

@@ -440,6 +440,13 @@ extern "C" int rayen_tc_trace_dump(void) {
 }
 #endif
 
+#ifdef RAYEN_BWD_TRACE
+extern "C" int rayen_bwd_trace_read(long long* out) {
+  cudaDeviceSynchronize();
+  return static_cast<int>(cudaMemcpyFromSymbol(out, rayen::g_bwd_trace, sizeof(long long) * 8192));
+}
+#endif
+
 #ifdef RAYEN_LMI_TRACE
 // development build only: copies the phase stamps of lmi_forward_kernel (see LMI_STAMP) to `out` (4096 values)
 extern "C" int rayen_lmi_trace_read(long long* out) {
@@ -729,7 +736,8 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
   int* bwd_list = has_lmi ? reinterpret_cast<int*>(static_cast<char*>(workspace) + 256 + ws_list_bytes(B)) : nullptr;
   cudaError_t e = cudaSuccess;
   if (stage_mask & 1) {
-    if (has_lmi) e = cudaMemsetAsync(counters + 1, 0, sizeof(int), stream);
+    // the backward work list exists only when the LMI gradients were not left behind by the forward call
+    if (has_lmi && !have_dkappa) e = cudaMemsetAsync(counters + 1, 0, sizeof(int), stream);
     LqsBwdFn f = lqs_bwd_fn(d.np);
     if (e == cudaSuccess) {
       const size_t tile_bytes = static_cast<size_t>(block / 32) * 2 * 32 * (d.np + 4) * sizeof(float);
