@@ -80,3 +80,60 @@ def test_random_shapes(seed):
     y, kap, _ = plan.evaluate_plan_numpy(p, v.numpy())
     cf = closed_form_numpy(OracleSet.from_constraints(cs), v.numpy())
     assert np.abs(y - cf["y"]).max() <= 5e-6 * max(1.0, np.abs(cf["y"]).max())
+
+
+def _decode_operand(words, rows, kdim):
+    """Inverse of plan.operand_layout: [k/4][row/8][row%8][k%4] -> [rows, kdim]."""
+    return words.reshape(kdim // 4, rows // 8, 8, 4).transpose(1, 2, 0, 3).reshape(rows, kdim)
+
+
+@pytest.mark.parametrize("cfg", ["cfg3", "cfg5"])
+def test_tensor_core_sections_decode_to_the_fp32_sections(cfg):
+    """The B operands of the two tcgen05 GEMMs (TC: linear rows + items of the linear/quadratic/SOC kernel; LMITC: the
+    LMI matrices) are the SAME constants as the FP32-pipe sections, split hi + lo: hi and lo are TF32-representable
+    (13 low mantissa bits zero), hi + lo reproduces the float32 value to 2^-22, panels and tables have the shape the
+    kernels assume."""
+    cs = synthetic.build_constraints(synthetic.config_spec(cfg))
+    p = plan.build_plan_from_constraints(cs)
+    f, blob = p.fields, p.blob
+    kp, panels = f["tc_kp"], f["tc_panels"]
+    tab = blob[f["off_tc"]:f["off_tc"] + panels * plan.TC_TABLE_WORDS].reshape(panels, plan.TC_TABLE_WORDS)
+    ints = tab.view(np.int32)
+    w0 = f["off_tc"] + panels * plan.TC_TABLE_WORDS
+    tile = plan.TC_PANEL * kp
+    rows = []
+    for pi in range(panels):
+        hi = blob[w0 + (2 * pi) * tile: w0 + (2 * pi + 1) * tile]
+        lo = blob[w0 + (2 * pi + 1) * tile: w0 + (2 * pi + 2) * tile]
+        for part in (hi, lo):
+            assert not np.any(part.view(np.uint32) & np.uint32(0x1FFF))            # TF32-representable
+        rows.append(_decode_operand(hi.astype(np.float64) + lo.astype(np.float64), plan.TC_PANEL, kp))
+    # linear panels first: their rows are D
+    D = np.asarray(p.f64["D"])
+    m = D.shape[0]
+    lin = np.concatenate([rows[pi] for pi in range(panels) if ints[pi, 0] == 0])[:m, :cs.n]
+    assert np.abs(lin - D).max() <= 2.0 ** -21 * max(1.0, np.abs(D).max())
+    assert [int(ints[pi, 1]) for pi in range(panels) if ints[pi, 0] == 0] == list(range(0, f["m_pad"], plan.TC_PANEL))
+    # item panels: 8 header rows + kp factor rows per item, item types in family order, |T u|^2 == u' S u
+    iw = 8 + kp
+    types = [int(ints[pi, 2 + 2 * s]) for pi in range(panels) if ints[pi, 0] == 1 for s in range(plan.TC_PANEL // iw)]
+    types = [t for t in types if t != 0]
+    n_lmi = 1 if cs.has_lmi_constraints else 0
+    assert types == [2] * len(cs.qcs) + [3] * len(cs.socs) + [5] * n_lmi
+    first_item_panel = next(pi for pi in range(panels) if ints[pi, 0] == 1)
+    T = rows[first_item_panel][8:8 + kp, :kp]
+    assert np.allclose(np.tril(T, -1), 0.0)                                        # upper triangular factor
+    if f["lmitc_panels"]:
+        rp, n = f["lmi_rp"], cs.n
+        assert f["lmitc_panels"] == rp * rp // plan.LMI_TC_PANEL
+        ltile = plan.LMI_TC_PANEL * kp
+        W = []
+        for pi in range(f["lmitc_panels"]):
+            o = f["off_lmitc"] + 2 * pi * ltile
+            hi, lo = blob[o:o + ltile], blob[o + ltile:o + 2 * ltile]
+            assert not np.any(hi.view(np.uint32) & np.uint32(0x1FFF)) and not np.any(lo.view(np.uint32) & np.uint32(0x1FFF))
+            W.append(_decode_operand(hi.astype(np.float64) + lo.astype(np.float64), plan.LMI_TC_PANEL, kp))
+        W = np.concatenate(W)                                                      # [rp*rp, kp], row e = i*rp + 4q + t
+        F32 = blob[f["off_lmi"]:f["off_lmi"] + n * rp * rp].reshape(n, rp * rp).astype(np.float64)
+        assert np.abs(W[:, :n].T - F32).max() <= 2.0 ** -21 * np.abs(F32).max()
+        assert not np.any(W[:, n:])
