@@ -332,15 +332,24 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
 
       // ---- merge / prune / scale step for this thread's sample
-      if (!valid) continue;
       const bool pruned = lmi_follows && prune && (fmaf(1e-4f, fabsf(ub), ub) + 1e-30f < best);
       const bool finish = !lmi_follows || pruned;
+      {
+        // samples the LMI kernel still has to look at: one atomicAdd per warp, not per sample
+        const bool enq = valid && !finish && work_list != nullptr;
+        const unsigned m = __ballot_sync(0xffffffffu, enq);
+        if (m != 0u) {
+          const int leader = __ffs(m) - 1;
+          int slot0 = 0;
+          if (lane == leader) slot0 = atomicAdd(work_count, __popc(m));
+          slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+          if (enq) work_list[slot0 + __popc(m & ((1u << lane) - 1u))] = static_cast<int>(b);
+        }
+      }
+      if (!valid) continue;
       if (kappa_out) kappa_out[b] = best;
       if (active_out) active_out[b] = tag;
-      if (!finish) {
-        if (work_list) work_list[atomicAdd(work_count, 1)] = static_cast<int>(b);
-        continue;
-      }
+      if (!finish) continue;
       float alpha;
       if (mode == RAYEN_MODE_RAYEN_OLD)
         alpha = 1.0f / (expf(beta) + best);
