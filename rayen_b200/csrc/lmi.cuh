@@ -30,8 +30,17 @@ __device__ long long g_lmi_trace[4096];
     if (blockIdx.x < 16 && (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) == 0 || (threadIdx.x >> 5) == 7)) \
       g_lmi_trace[blockIdx.x * 64 + ((threadIdx.x >> 5) ? 32 : 0) + (slot)] = clock64();     \
   } while (0)
+#define LMI_GT(slot)                                                                         \
+  do {                                                                                       \
+    if (threadIdx.x == 0 && blockIdx.x < 256) {                                              \
+      long long t_;                                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                 \
+      g_lmi_trace[2048 + blockIdx.x * 2 + (slot)] = t_;                                      \
+    }                                                                                        \
+  } while (0)
 #else
 #define LMI_STAMP(slot) do { } while (0)
+#define LMI_GT(slot) do { } while (0)
 #endif
 
 constexpr int kLmiThreads = 256;     // backward kernel (keeps the reflectors: needs the registers)
@@ -639,6 +648,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float* scratch_base;
+  LMI_GT(0);
   pdl_wait();  // launched behind the linear/quadratic/SOC kernel: its kappa / active / work list must be complete
   // dense mode: every sample; list mode: only the samples the LQS kernel could not prune
   const long long total = work_list ? static_cast<long long>(*work_count) : B;
@@ -742,6 +752,10 @@ __global__ void __launch_bounds__(THREADS, 1)
   if constexpr (F_SMEM) {
     if (!staged && cta_has_work) mbar_wait(&bars[0], 0);  // never exit with a bulk copy in flight
   }
+#ifdef RAYEN_LMI_TRACE
+  __syncthreads();
+  LMI_GT(1);
+#endif
 }
 
 // ----------------------------------------------------------------------------- backward

@@ -37,5 +37,12 @@ for arg in sys.argv[1:]:
             t = h[cta, off:off + len(NAMES)]
             t0 = h[cta, 0]
             print(f"cta{cta:2d} {w}: " + " ".join(f"{NAMES[i]}={int(t[i] - t0)}" for i in range(len(NAMES)) if NAMES[i] != "?"))
+    gt = np.array(buf[2048:2048 + 512], dtype=np.int64).reshape(256, 2)[:148]
+    live = gt[:, 1] > gt[:, 0]
+    if live.any():
+        g0 = gt[live, 0].min()
+        end = np.sort(gt[live, 1] - g0)
+        print(f"CTA end times (ns after the first CTA start), {int(live.sum())} CTAs: median {int(np.median(end))} p90 {int(end[int(0.9 * len(end))])} "
+              f"last five {end[-5:].tolist()}; start spread {int((gt[live, 0] - g0).max())} ns")
     del db, layer
     torch.cuda.empty_cache()
