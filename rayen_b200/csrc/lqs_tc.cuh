@@ -86,6 +86,31 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
+// FP32-pipe re-evaluation of one cone's kappa from the FP32 constants (SOC section of the blob), for the rare sample
+// whose ray is nearly tangent to the cone: there (h.u)^2 + A c' cancels, d kappa/d(h.u) = (1 + h.u/sqrt(disc))/A is
+// large, and the 3xTF32 dot products (a few 1e-7 of sum|h_a u_a|) are not good enough.  One thread, ~600 FMAs.
+template <int KP>
+__device__ __forceinline__ float soc_kappa_fp32(const float* __restrict__ item, const float (&u)[KP]) {
+  constexpr int TRI = (KP / 4) * (KP / 4 + 1) * 8;
+  float cu = 0.f, hb = 0.f, ss = 0.f;
+#pragma unroll
+  for (int a = 0; a < KP; ++a) {
+    cu = fmaf(__ldg(item + a), u[a], cu);
+    hb = fmaf(__ldg(item + KP + a), u[a], hb);
+  }
+  const float* tri = item + 2 * KP;
+  int pos = 0;
+#pragma unroll
+  for (int i = 0; i < KP; ++i) {
+    float r = 0.f;
+#pragma unroll
+    for (int j = 4 * (i / 4); j < KP; ++j) r = fmaf(__ldg(tri + pos + j - 4 * (i / 4)), u[j], r);
+    pos += KP - 4 * (i / 4);
+    ss = fmaf(r, r, ss);
+  }
+  return soc_root(__ldg(item + 2 * KP + TRI), hb, fmaf(-cu, cu, ss), nullptr);
+}
+
 template <int KP>
 __host__ __device__ constexpr size_t lqs_tc_smem_bytes(int n_panels) {
   return 256 + static_cast<size_t>((n_panels * kTcTableWords + 3) / 4 * 4) * 4 + 4 * static_cast<size_t>(KP) * 128 * 4 +
@@ -256,6 +281,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       float best = 0.f;
       int tag = make_tag(RAYEN_FAM_NONE, 0);
       float ub = 3.0e38f;  // pruning bound of the LMI (stays +inf without one)
+      int soc_fix = -1;    // a cone whose kappa is ill-conditioned for this sample (see soc_kappa_fp32)
       for (int p = 0; p < n_panels; ++p, ++g) {
         const uint32_t buf = g & 1, buf_use = g >> 1;
         if (warp == 0 && lane == 0) TC_STAMP(8 * p + 4);
@@ -313,7 +339,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             } else if (type == RAYEN_FAM_SOC) {    // largest root                  (reference :383-399)
               const float cq = fmaf(-h[0], h[0], ss);
               const float kap = soc_root(scal, h[1], cq, nullptr);
-              if (kap > best) {
+              // nearly tangent ray (the discriminant cancels to < 1 % of its terms) that can matter for this sample:
+              // the first such cone is left out of the running max and evaluated on the FP32 pipe after the panel loop
+              if (soc_fix < 0 && KP == P.np && fmaf(h[1], h[1], scal * cq) < 1e-2f * h[1] * h[1] && kap > 0.9f * best) {
+                soc_fix = idx;
+              } else if (kap > best) {
                 best = kap;
                 tag = make_tag(RAYEN_FAM_SOC, idx);
               }
@@ -331,6 +361,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (lane == 0) mbar_arrive(&d_empty[buf]);
       }
 
+      // ---- the rare near-tangent cone that was left out above, in FP32
+      if (soc_fix >= 0) {
+        const float kap = soc_kappa_fp32<KP>(P.blob + P.off_soc + soc_fix * P.soc_stride, u);
+        if (kap > best) {
+          best = kap;
+          tag = make_tag(RAYEN_FAM_SOC, soc_fix);
+        }
+      }
       // ---- merge / prune / scale step for this thread's sample
       const bool pruned = lmi_follows && prune && (fmaf(1e-4f, fabsf(ub), ub) + 1e-30f < best);
       const bool finish = !lmi_follows || pruned;
