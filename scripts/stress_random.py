@@ -26,14 +26,17 @@ for seed in range(int(sys.argv[1]) if len(sys.argv) > 1 else 60):
     cs = synthetic.build_constraints(spec)
     B = int(rng.choice([1, 7, 64, 300, 1111, 5000]))
     v, gy = synthetic.sample_inputs(B, cs.n, cs.k, seed_v=seed, scale=float(rng.uniform(0.5, 8.0)))
-    layer = ConstraintModule(cs, create_map=False).to(dev)
+    method = "RAYEN_old" if seed % 4 == 3 else "RAYEN"
+    if method == "RAYEN_old":   # one more input column: beta
+        v = torch.cat((v, torch.randn(B, 1, generator=torch.Generator().manual_seed(seed))), dim=1)
+    layer = ConstraintModule(cs, create_map=False, method=method).to(dev)
     x = v.to(dev).requires_grad_(True)
     y = layer(x.unsqueeze(2))
     (y[:, :, 0] * gy.to(dev)).sum().backward()
     yy, gg = y[:, :, 0].detach().cpu().double().numpy(), x.grad.cpu().double().numpy()
     oset = OracleSet.from_constraints(cs)
-    y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v.double(), gy.double())
-    ok = closed_form_numpy(oset, v.numpy(), gy.numpy())["margin"] > 1e-4
+    y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v.double(), gy.double(), method)
+    ok = closed_form_numpy(oset, v.numpy()[:, :cs.n], gy.numpy())["margin"] > 1e-4
     ey = float(np.abs(yy - y_ref.numpy()).max() / max(np.abs(y_ref.numpy()).max(), 1e-30))
     eg = float(np.abs(gg - g_ref.numpy())[ok].max() / max(np.abs(g_ref.numpy())[ok].max(), 1e-30)) if ok.any() else 0.0
     viol = max_violation(oset, yy, spec["A1"], spec["b1"], spec["A2"], spec["b2"]) / max(1.0, np.abs(yy).max())
@@ -41,6 +44,6 @@ for seed in range(int(sys.argv[1]) if len(sys.argv) > 1 else 60):
     bad = ey > 1e-5 or eg > 2e-5 or viol > 1e-5 or not np.isfinite(yy).all() or not np.isfinite(gg).all()
     fails += bad
     if bad:
-        print("FAIL seed", seed, dict(k=k, n=cs.n, B=B, ey=ey, eg=eg, viol=viol), flush=True)
+        print("FAIL seed", seed, method, dict(k=k, n=cs.n, B=B, ey=ey, eg=eg, viol=viol), flush=True)
 # (near-tangent cone rays are ill-conditioned in float32 by nature: see DESIGN.md section 3)
 print(f"done: worst rel err y {worst_y:.2e}, g_v {worst_g:.2e}, violation {worst_v:.2e}, failures {fails}")
