@@ -146,7 +146,8 @@ def closed_form_numpy(oset, v, gy=None):
     """Analytic forward (+ backward if gy is given) in float64 numpy.
 
     Returns a dict: y[B,k], kappa[B], family[B], index[B], case[B], margin[B] (relative gap between the
-    two largest kappas, for near-tie masking) and, when gy is given, gv[B,n].
+    two largest kappas, for near-tie masking), cone_cond[B] (sqrt(disc)/|b'| of a binding cone, 1 otherwise: small
+    means a nearly tangent ray, ill-conditioned in float32) and, when gy is given, gv[B,n].
     """
     v = np.asarray(v, dtype=np.float64).reshape(-1, oset.n)
     B, n, k = v.shape[0], oset.n, oset.k
@@ -155,11 +156,11 @@ def closed_form_numpy(oset, v, gy=None):
     u = v / np.maximum(s, 1e-12)[:, None]
     rho = u @ N.T                                           # [B,k]
 
-    kappas, grads, fams = [], [], []                        # grads: d kappa / d u, each [B,n]
+    kappas, grads, fams, conds = [], [], [], []             # grads: d kappa / d u, each [B,n]
     D = oset.A_p / (oset.b_p - oset.A_p @ oset.z0)
     lin = u @ D.T                                           # [B,m]
     j = np.argmax(lin, axis=1)
-    kappas.append(lin[np.arange(B), j]); grads.append(D[j]); fams.append((FAM_LINEAR, j))
+    kappas.append(lin[np.arange(B), j]); grads.append(D[j]); fams.append((FAM_LINEAR, j)); conds.append(np.ones(B))
     for i, (P, q, r) in enumerate(oset.qcs):
         w = P @ y0 + q[:, 0]
         a = 0.5 * y0 @ P @ y0 + q[:, 0] @ y0 + r[0, 0]
@@ -169,7 +170,7 @@ def closed_form_numpy(oset, v, gy=None):
         root = np.sqrt(np.einsum("bi,ij,bj->b", rho, Delta, rho))
         kap = rho @ phi + root
         dk_drho = phi[None, :] + (rho @ Delta) / np.where(root > 0, root, 1.0)[:, None]
-        kappas.append(kap); grads.append(dk_drho @ N); fams.append((FAM_QUAD, np.full(B, i)))
+        kappas.append(kap); grads.append(dk_drho @ N); fams.append((FAM_QUAD, np.full(B, i))); conds.append(np.ones(B))
     for i, (M, sv, c, d) in enumerate(oset.socs):
         beta = M @ y0 + sv[:, 0]
         tau = c[:, 0] @ y0 + d[0, 0]
@@ -184,6 +185,9 @@ def closed_form_numpy(oset, v, gy=None):
         denom = 2 * a_p * kap + b_p
         dk_drho = -(kap[:, None] * grad_b[None, :] + grad_c) / np.where(denom != 0, denom, 1.0)[:, None]
         kappas.append(kap); grads.append(dk_drho @ N); fams.append((FAM_SOC, np.full(B, i)))
+        # sqrt(disc)/|b'|: small for a ray nearly tangent to the cone, where kappa is ill-conditioned in any float32
+        # evaluation (d kappa/d b' = -(1 + b'/sqrt(disc))/(2a'))
+        conds.append(np.sqrt(disc) / np.maximum(np.abs(b_p), 1e-300))
     if oset.lmi is not None:
         allF = np.asarray(oset.lmi)
         H = allF[-1] + np.einsum("a,aij->ij", y0, allF[:-1])
@@ -194,6 +198,7 @@ def closed_form_numpy(oset, v, gy=None):
         qv = vec[:, :, -1]
         dk_drho = np.einsum("bi,aij,bj->ba", qv, Ft, qv)
         kappas.append(lam[:, -1]); grads.append(dk_drho @ N); fams.append((FAM_LMI, np.zeros(B, dtype=int)))
+        conds.append(np.ones(B))
 
     K = np.stack(kappas, axis=1)                            # [B, 1+eta+mu+lmi]
     best = np.argmax(K, axis=1)
@@ -209,13 +214,15 @@ def closed_form_numpy(oset, v, gy=None):
     family = np.array([f[0] for f in fams])[best]
     index = np.stack([f[1] for f in fams], axis=1)[np.arange(B), best]
     family = np.where(kap > 0, family, FAM_NONE)
+    cone_cond = np.stack(conds, axis=1)[np.arange(B), best]
 
     with np.errstate(divide="ignore"):
         inv_kappa = np.where(kap > 0, 1.0 / np.where(kap > 0, kap, 1.0), np.inf)
     alpha = np.minimum(inv_kappa, s)
     y = (z0[None, :] + alpha[:, None] * u) @ N.T + yp[None, :]
     case = np.where(s == 0, CASE_ZERO, np.where(s <= inv_kappa, CASE_INTERIOR, CASE_BOUNDARY))
-    out = dict(y=y, kappa=kap, family=family, index=index, case=case, margin=margin, alpha=alpha, s=s)
+    out = dict(y=y, kappa=kap, family=family, index=index, case=case, margin=margin, alpha=alpha, s=s,
+               cone_cond=cone_cond)
     if gy is not None:
         gz = np.asarray(gy, dtype=np.float64).reshape(B, k) @ N
         safe_k = np.where(kap > 0, kap, 1.0)

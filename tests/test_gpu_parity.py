@@ -122,6 +122,46 @@ def test_random_shapes_vs_oracle(seed):
     assert max_violation(oset, y, spec["A1"], spec["b1"], spec["A2"], spec["b2"]) <= 1e-5 * max(1.0, np.abs(y).max())
 
 
+@pytest.mark.parametrize("seed", list(range(24)) + [1016, 1086, 1184])
+def test_random_stress_both_methods(seed):
+    """Random sets (n = 1..32, all families, equalities, batches 1..5000), every fourth with RAYEN_old, against the
+    float64 oracle.  Seeds 1016 / 1086 / 1184 are the cases a 200-set run (scripts/stress_random.py) flagged: cone-bound
+    samples on nearly tangent rays, where kappa is ill-conditioned in float32 (oracle's cone_cond); well-conditioned
+    samples must meet the usual bars, the others a bar scaled by 1/cone_cond."""
+    rng = np.random.default_rng(seed if seed >= 1000 else 1000 + seed)
+    base = seed - 1000 if seed >= 1000 else seed
+    k = int(rng.integers(1, 33))
+    spec = synthetic.random_spec(k=k, m=int(rng.integers(0, 80)), eta=int(rng.integers(0, 5)), mu=int(rng.integers(0, 5)),
+                                 r_M=int(rng.integers(1, 2 * k + 1)), r=int(rng.integers(0, 2)) * int(rng.integers(2, 33)),
+                                 seed=base)
+    if spec["A1"] is None and not spec["qcs"] and not spec["socs"] and spec["lmi"] is None:
+        spec = synthetic.random_spec(k=k, m=5, seed=base)
+    if spec["b1"] is not None:
+        spec["b1"] = spec["b1"] * float(rng.uniform(1.0, 6.0))
+    if base % 3 == 1 and k > 2:
+        spec["A2"], spec["b2"] = rng.uniform(-1, 1, size=(1, k)), np.zeros((1, 1))
+    cs = synthetic.build_constraints(spec)
+    B = int(rng.choice([1, 7, 64, 300, 1111, 5000]))
+    v, gy = synthetic.sample_inputs(B, cs.n, cs.k, seed_v=base, scale=float(rng.uniform(0.5, 8.0)))
+    method = "RAYEN_old" if base % 4 == 3 else "RAYEN"
+    if method == "RAYEN_old":
+        v = torch.cat((v, torch.randn(B, 1, generator=torch.Generator().manual_seed(base))), dim=1)
+    _, y, gv = run_layer(cs, v, gy, method)
+    oset = OracleSet.from_constraints(cs)
+    y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v.double(), gy.double(), method)
+    y_ref, g_ref = y_ref.numpy(), g_ref.numpy()
+    cf = closed_form_numpy(oset, v.numpy()[:, :cs.n], gy.numpy())
+    well = cf["cone_cond"] > 0.05
+    scale_y, scale_g = max(np.abs(y_ref).max(), 1e-30), max(np.abs(g_ref).max(), 1e-30)
+    err_y = np.abs(y - y_ref).max(axis=1) / scale_y
+    assert err_y[well].max(initial=0.0) <= TOL
+    assert (err_y * np.minimum(cf["cone_cond"], 1.0)).max() <= TOL          # ill-conditioned: bar / cone_cond
+    ok = (cf["margin"] > 1e-4) & well
+    if ok.any():
+        assert (np.abs(gv - g_ref).max(axis=1) / scale_g)[ok].max() <= 2 * TOL_GRAD
+    assert max_violation(oset, y, spec["A1"], spec["b1"], spec["A2"], spec["b2"]) <= 1e-5 * max(1.0, np.abs(y).max())
+
+
 # ----------------------------------------------------------------------------- closed-form geometry (KATs)
 def test_kat_sphere_and_box_and_psd_cone():
     # sphere of radius R centred at y0 = 0: kappa == 1/R for every direction
