@@ -432,10 +432,21 @@ def run_b200(args, rank, local_rank, world):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (durs[dominant] * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this workload
+    traffic, traffic_src = None, None
+    prof = os.path.join(ROOT, "profiles", "r01_lmi_forward.md")
+    if dominant == "lmi_forward_kernel" and args.workload == "cfg5" and batch == 32768 and os.path.isfile(prof):
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for row in open(prof):
+            f = [x.strip() for x in row.split("|")]
+            if len(f) > 3 and f[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in unit:
+                tot += float(f[3]) * unit[f[2]]
+        traffic, traffic_src = tot, "profiles/r01_lmi_forward.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
     step_bytes = fwd_bytes + bwd_bytes
     line["roofline"] = {
         "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": durs[dominant],
         "kernel_ms_all": durs, "kernel_names": kernel_names,
         "kernel_share_of_step": durs[dominant] / sum(durs.values()),
