@@ -486,9 +486,9 @@ def run_b200(args, rank, local_rank, world):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sample = min(batch, 4096)
-        rate, mean_t, best_t = cpu_oracle_rate(args.workload, sample, 3, 1, cores)
+        rate, mean_t, best_t = cpu_oracle_rate(args.workload, sample, 8, 1, cores)
         line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                                "sample": f"{sample} samples of the same workload, mean of 3 after 1 warm-up, "
+                                "sample": f"{sample} samples of the same workload, mean of 8 passes after 1 warm-up, "
                                           f"torch {torch.__version__} CPU fp32, {cores} threads, {mean_t * 1e3:.0f} ms/pass"}
 
     # ---- the other BASELINE.json configs at their named batch, and a large-batch point (not bench lines)
