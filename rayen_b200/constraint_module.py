@@ -26,6 +26,12 @@ import torch.nn as nn
 
 from . import _cabi, plan as plan_mod, utils
 
+try:  # raw handle of the current stream without building a torch.cuda.Stream object (11 us -> < 1 us per call)
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # pragma: no cover - older / newer torch without the private helper
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
+
 _SUPPORTED = ("RAYEN", "RAYEN_old")
 # B200, scripts/mapper_compare.py (input_dim 64, forward replayed from a CUDA graph): fused 6.3 vs 10.4 us at B = 500,
 # 10.3 vs 10.4 us at B = 4096, 37 vs 23 us at B = 16384 (the in-kernel mapper is per-thread FP32 FMAs; cuBLAS wins
@@ -73,7 +79,7 @@ class _RayShoot(torch.autograd.Function):
         try:
             want_grad = 1 if ctx.needs_input_grad[0] else 0
             rc = st.forward(st.handle, v.data_ptr(), v.stride(0) if B > 0 else cols, y.data_ptr(), base, base + 4 * B, B,
-                            module._mode, want_grad, base + 8 * B, torch.cuda.current_stream(device).cuda_stream)
+                            module._mode, want_grad, base + 8 * B, _raw_stream(st.index))
         finally:
             if switch:
                 torch.cuda.set_device(prev)
@@ -104,8 +110,7 @@ class _RayShoot(torch.autograd.Function):
             torch.cuda.set_device(st.index)
         try:
             rc = st.backward(st.handle, v.data_ptr(), v.stride(0) if B > 0 else cols, gy.data_ptr(), base, base + 4 * B,
-                             gv.data_ptr(), cols, B, module._mode, ctx.have_dkappa, base + 8 * B,
-                             torch.cuda.current_stream(device).cuda_stream)
+                             gv.data_ptr(), cols, B, module._mode, ctx.have_dkappa, base + 8 * B, _raw_stream(st.index))
         finally:
             if switch:
                 torch.cuda.set_device(prev)
