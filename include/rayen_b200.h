@@ -24,12 +24,12 @@
 extern "C" {
 #endif
 
-#define RAYEN_ABI_VERSION 11
+#define RAYEN_ABI_VERSION 12
 
 /* error codes (negative); positive return values are cudaError_t */
 #define RAYEN_OK 0
 #define RAYEN_ERR_BAD_ARGUMENT (-1)
-#define RAYEN_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels cover (n > 32, LMI size > 32) */
+#define RAYEN_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels cover (n > 4096, LMI size > 32, LMI with n > 32) */
 #define RAYEN_ERR_ABI (-3)
 #define RAYEN_ERR_NO_DEVICE (-4)
 
@@ -76,6 +76,16 @@ extern "C" {
  *           lmitc_panels = rp*rp/128 panels of 128 entries, entry e = i*rp + 4q + t <-> F~z_a[i][q + (rp/4)*t]
  *           (the LMI section's order), per panel W_hi and W_lo (128 x tc_kp each, TF32 split) in the operand
  *           layout [k/4][row/8][row%8][k%4]
+ *   WIDE    (wide == 1: 32 < n <= 4096, linear + quadratic + SOC; wide.cuh) 16 int32 words {magic 0x57494445, R_pad,
+ *           n_tasks, off_tasks, off_wt, off_nt, off_nrow, k32, np, off_items, n_quad, n_soc, off_soc_a, 0, 0, 0}
+ *           (offsets in words from `blob`), then
+ *             tasks   n_tasks x 8 words {kind 1 linear / 2 quadratic / 3 cone, first row, groups of 32 rows, index of
+ *                     the first row (linear) or of the item, float A of a cone, 0, 0, 0}: the unit of work of a warp
+ *             items   first row of every quadratic, then of every cone (int32), and the cones' A (float)
+ *             Wt      [n][R_pad], Wt[j][row] = W[row][j]; W stacks the rows of D (zero padded to 32), then per quadratic
+ *                     {phi_z, the n rows of G} and per cone {c_z, h, the n rows of R}, each item zero padded to 32 rows
+ *             NT      [n][k32] = N' and Nrow [k][np] = N (both absent when N is the identity)
+ *           The LIN/QUAD/SOC sections are still present (np = n rounded up to 4); TC is empty (tc_panels = 0).
  *   LMINEG  -F_0 .. -F_k laid out like LMI ([a][row][lane][slot]): lambda_max(sum_a (y,1)_a (-F_a)) = -lambda_min(F(y))
  */
 typedef struct RayenPlanDesc {
@@ -100,8 +110,9 @@ typedef struct RayenPlanDesc {
   int32_t viol_in;   /* inequality rows of the VIOL section */
   int32_t viol_eq;   /* equality rows of the VIOL section */
   int32_t lmitc_panels; /* 128-entry panels of the LMITC section (0: none) */
-  int32_t reserved0;
+  int32_t wide;         /* 1: n > 32 -- np is n rounded up to 4, the kernels of wide.cuh read the WIDE section */
   int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi, off_tc, off_viol, off_lmineg, off_lmitc;
+  int64_t off_wide;     /* WIDE section (0 when wide == 0) */
   int64_t blob_words;
   const float* blob; /* host pointer, blob_words floats */
 } RayenPlanDesc;

@@ -424,7 +424,7 @@ class ConstraintModule(nn.Module):
                 and x2d.dtype == torch.float32 and m.weight.dtype == torch.float32 and x2d.shape[0] > 0
                 and x2d.shape[1] % 4 == 0 and x2d.stride(1) == 1 and x2d.stride(0) % 4 == 0
                 and x2d.data_ptr() % 16 == 0 and m.weight.is_contiguous() and m.weight.data_ptr() % 16 == 0
-                and self._lqs_kernel_runs)
+                and self._lqs_kernel_runs and not self._packed.fields.get("wide"))
 
     def forward(self, x):
         # x: [B, numel_input_mapper, 1] (anything that views to [B, -1]), as in the reference

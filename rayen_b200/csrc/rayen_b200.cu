@@ -14,6 +14,7 @@
 #include "lqs.cuh"
 #include "lqs_tc.cuh"
 #include "viol.cuh"
+#include "wide.cuh"
 
 using namespace rayen;
 
@@ -30,6 +31,9 @@ struct rayen_plan {
   bool lmi_smem;  // LMI matrices fit in shared memory
   size_t lqs_smem_bytes, lmi_smem_bytes, lmi_bwd_smem_bytes, lmi_grad_smem_bytes, viol_lmi_smem_bytes;
   bool viol_lmi_smem;
+  bool wide;      // n > 32: the kernels of wide.cuh on the WIDE section (linear + quadratic + SOC, no LMI)
+  WideDev wdev;
+  size_t wide_fwd_smem_bytes, wide_bwd_smem_bytes;
   bool has_lqs;   // any non-zero linear row / quadratic / cone: otherwise the LQS forward kernel is skipped
   bool prune;     // LMI pruning enabled (needs has_lqs and a BOUND section)
   bool use_tc;    // tensor-core (tcgen05) linear/quadratic/SOC forward kernel
@@ -208,14 +212,17 @@ static int allow_smem(const void* fn, size_t bytes) {
 }
 
 // ----------------------------------------------------------------------------- plan create / destroy
+static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** out);
+
 extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_t** out) {
   if (!d || !out) return fail(RAYEN_ERR_BAD_ARGUMENT, "rayen_plan_create: null argument");
   *out = nullptr;
   if (d->abi_version != RAYEN_ABI_VERSION)
     return fail(RAYEN_ERR_ABI, "plan descriptor has ABI %d, library has %d", d->abi_version, RAYEN_ABI_VERSION);
   if (d->n < 1 || d->k < d->n) return fail(RAYEN_ERR_BAD_ARGUMENT, "bad dimensions n=%d k=%d", d->n, d->k);
+  if (d->wide) return create_wide_plan(d, device, out);
   if (np_index(d->np) < 0 || d->np < d->n)
-    return fail(RAYEN_ERR_UNSUPPORTED, "n=%d (np=%d): only n <= 32 is covered", d->n, d->np);
+    return fail(RAYEN_ERR_UNSUPPORTED, "n=%d (np=%d): the register-resident kernels cover n <= 32 (wide plans: wide = 1)", d->n, d->np);
   if (d->lmi_r > 0 && (np_index(d->lmi_rp) < 0 || d->lmi_rp < d->lmi_r))
     return fail(RAYEN_ERR_UNSUPPORTED, "LMI size %d (padded %d): only r <= 32 is covered", d->lmi_r, d->lmi_rp);
   if (d->m_pad % 4 || d->m_pad < d->m || d->m_pad < 4 || d->k_pad % 4 || d->k_pad < d->k)
@@ -386,6 +393,100 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   return RAYEN_OK;
 }
 
+// Wide plan (32 < n <= 4096; linear + quadratic + SOC): only the WIDE, Y0 and VIOL sections are used on the device.
+static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** out) {
+  if (d->n <= 32 || d->n > 4096 || d->np < d->n || d->np % 4)
+    return fail(RAYEN_ERR_UNSUPPORTED, "wide plan: n=%d (np=%d) outside 33..4096", d->n, d->np);
+  if (d->lmi_r > 0) return fail(RAYEN_ERR_UNSUPPORTED, "an LMI together with n=%d > 32 is not covered", d->n);
+  if (d->k_pad % 4 || d->k_pad < d->k) return fail(RAYEN_ERR_BAD_ARGUMENT, "bad padding k=%d k_pad=%d", d->k, d->k_pad);
+  if (!d->blob || d->blob_words <= 0 || d->blob_words % 4 || d->blob_words > (1ll << 30))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "bad constant block (%lld words)", static_cast<long long>(d->blob_words));
+  if (d->off_wide < 0 || d->off_wide % 4 || d->off_wide + 16 > d->blob_words || d->off_y0 < 0 || d->off_y0 % 4 ||
+      d->off_y0 + d->k_pad > d->blob_words || d->off_viol < 0 || d->off_viol % 4 || d->off_viol >= d->blob_words ||
+      d->viol_in < 0 || d->viol_eq < 0 || d->n_quad < 0 || d->n_soc < 0)
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "wide plan: section offsets are invalid");
+  const int32_t* h = reinterpret_cast<const int32_t*>(d->blob + d->off_wide);
+  WideDev w{};
+  w.n = d->n; w.k = d->k;
+  w.r_pad = h[1]; w.n_tasks = h[2]; w.off_tasks = h[3]; w.off_wt = h[4]; w.off_nt = h[5]; w.off_nrow = h[6];
+  w.k32 = h[7]; w.np = h[8]; w.off_items = h[9]; w.n_quad = h[10]; w.n_soc = h[11]; w.off_soc_a = h[12];
+  w.off_y0 = static_cast<int>(d->off_y0); w.n_is_identity = d->n_is_identity;
+  const int64_t words = d->blob_words;
+  if (h[0] != kWideMagic || w.r_pad < 32 || w.r_pad % 32 || w.n_tasks < 1 || w.off_tasks < 0 ||
+      w.off_tasks + static_cast<int64_t>(w.n_tasks) * 8 > words || w.off_wt < 0 ||
+      w.off_wt + static_cast<int64_t>(w.n) * w.r_pad > words || w.n_quad != d->n_quad || w.n_soc != d->n_soc ||
+      w.off_items < 0 || w.off_items + w.n_quad + w.n_soc > words || w.off_soc_a < 0 || w.off_soc_a + w.n_soc > words ||
+      w.np != d->np || w.k32 < d->k ||
+      (!d->n_is_identity && (w.off_nt <= 0 || w.off_nt + static_cast<int64_t>(w.n) * w.k32 > words || w.off_nrow <= 0 ||
+                             w.off_nrow + static_cast<int64_t>(w.k) * w.np > words)))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "wide plan: the WIDE header does not describe this block");
+  const int32_t* tasks = reinterpret_cast<const int32_t*>(d->blob + w.off_tasks);
+  for (int t = 0; t < w.n_tasks; ++t) {
+    const int kind = tasks[8 * t], rb = tasks[8 * t + 1], ng = tasks[8 * t + 2];
+    if (kind < 1 || kind > 3 || rb < 0 || rb % 32 || ng < 1 || rb + 32ll * ng > w.r_pad)
+      return fail(RAYEN_ERR_BAD_ARGUMENT, "wide plan: task %d is invalid", t);
+  }
+  const int32_t* items = reinterpret_cast<const int32_t*>(d->blob + w.off_items);
+  for (int i = 0; i < w.n_quad + w.n_soc; ++i)
+    if (items[i] < 0 || items[i] + (i < w.n_quad ? 1 : 2) + w.n > w.r_pad)
+      return fail(RAYEN_ERR_BAD_ARGUMENT, "wide plan: item %d is invalid", i);
+
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+    return fail(RAYEN_ERR_NO_DEVICE, "CUDA device %d is not available (%d devices visible)", device, count);
+  int prev = 0;
+  RAYEN_CUDA(cudaGetDevice(&prev));
+  RAYEN_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  RAYEN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    cudaSetDevice(prev);
+    return fail(RAYEN_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  }
+  rayen_plan* p = new (std::nothrow) rayen_plan();
+  if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "out of host memory");
+  memset(p, 0, sizeof(*p));
+  p->device = device;
+  p->host_mu = new (std::nothrow) std::mutex();
+  p->sm_count = prop.multiProcessorCount;
+  p->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+  p->wide = true;
+  p->has_lqs = true;
+  p->wide_fwd_smem_bytes = wide_fwd_smem_bytes(w.n);
+  p->wide_bwd_smem_bytes = wide_bwd_smem_bytes(w.n);
+  cudaError_t e = cudaMalloc(&p->d_blob, d->blob_words * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(p->d_blob, d->blob, d->blob_words * sizeof(float), cudaMemcpyHostToDevice);
+  int rc = 0;
+  if (e != cudaSuccess) rc = cuda_fail(e, "uploading the constant block");
+  // the attribute is per function, not per plan: always the device maximum, so that plans of different n coexist
+  if (rc == 0 && p->wide_fwd_smem_bytes > static_cast<size_t>(p->max_smem_optin))
+    rc = fail(RAYEN_ERR_UNSUPPORTED, "wide plan: n=%d needs %zu bytes of shared memory", w.n, p->wide_fwd_smem_bytes);
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel), p->max_smem_optin);
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_backward_kernel), p->max_smem_optin);
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(viol_lqs_kernel), p->max_smem_optin);
+  cudaSetDevice(prev);
+  if (rc != 0) {
+    if (p->d_blob) cudaFree(p->d_blob);
+    delete p->host_mu;
+    delete p;
+    return rc;
+  }
+  w.blob = p->d_blob;
+  p->wdev = w;
+  // the violation checker and the host-buffer path read these
+  PlanDev& v = p->dev;
+  v.blob = p->d_blob;
+  v.n = d->n; v.k = d->k; v.np = d->np; v.k_pad = d->k_pad;
+  v.m = d->m; v.m_pad = d->m_pad; v.n_quad = d->n_quad; v.n_soc = d->n_soc;
+  v.n_is_identity = d->n_is_identity;
+  v.off_y0 = static_cast<int>(d->off_y0);
+  v.off_viol = static_cast<int>(d->off_viol); v.off_lmineg = static_cast<int>(d->off_lmineg);
+  v.viol_in = d->viol_in; v.viol_eq = d->viol_eq;
+  *out = p;
+  return RAYEN_OK;
+}
+
 extern "C" void rayen_plan_destroy(rayen_plan_t* p) {
   if (!p) return;
   int prev = 0;
@@ -496,6 +597,15 @@ extern "C" int rayen_plan_kernel_info(const rayen_plan_t* p, RayenKernelInfo* ou
   if (!p || !out) return fail(RAYEN_ERR_BAD_ARGUMENT, "null argument");
   memset(out, 0, sizeof(*out));
   cudaFuncAttributes a;
+  if (p->wide) {
+    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(wide_forward_kernel)));
+    out->regs_lqs_fwd = a.numRegs;
+    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(wide_backward_kernel)));
+    out->regs_lqs_bwd = a.numRegs;
+    out->smem_lqs_bytes = static_cast<int>(p->wide_fwd_smem_bytes);
+    out->sm_count = p->sm_count;
+    return RAYEN_OK;
+  }
   RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lqs_fwd_fn(p->dev.np, 4, p->lqs_smem))));
   out->regs_lqs_fwd = a.numRegs;
   RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(lqs_bwd_fn(p->dev.np))));
@@ -640,6 +750,25 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
   RAYEN_CUDA(cudaGetDevice(&prev));
   if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
 
+  if (p->wide) {
+    if (map) {
+      if (prev != p->device) cudaSetDevice(prev);
+      return fail(RAYEN_ERR_UNSUPPORTED, "the fused mapper is not available for wide plans (n > 32)");
+    }
+    cudaError_t we = cudaSuccess;
+    if (stage_mask & 1) {
+      long long grid = (B + kWideTS - 1) / kWideTS;
+      const long long cap = static_cast<long long>(p->sm_count) * 32;
+      if (grid > cap) grid = cap;
+      wide_forward_kernel<<<static_cast<int>(grid), kWideThreads, p->wide_fwd_smem_bytes, stream>>>(p->wdev, v, ldv, y, kappa,
+                                                                                                  active, B, mode);
+      g_launches.fetch_add(1);
+      we = cudaGetLastError();
+    }
+    if (prev != p->device) cudaSetDevice(prev);
+    if (we != cudaSuccess) return cuda_fail(we, "forward launch (wide)");
+    return RAYEN_OK;
+  }
   if (has_lmi && !workspace) return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the workspace buffer");
   int* counters = static_cast<int*>(workspace);
   int* fwd_list = has_lmi ? reinterpret_cast<int*>(static_cast<char*>(workspace) + 256) : nullptr;
@@ -726,6 +855,21 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
   RAYEN_CUDA(cudaGetDevice(&prev));
   if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
 
+  if (p->wide) {
+    cudaError_t we = cudaSuccess;
+    if (stage_mask & 1) {
+      long long wgrid = B;
+      const long long wcap = static_cast<long long>(p->sm_count) * 64;
+      if (wgrid > wcap) wgrid = wcap;
+      wide_backward_kernel<<<static_cast<int>(wgrid), kWideBwdThreads, p->wide_bwd_smem_bytes, stream>>>(
+          p->wdev, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
+      g_launches.fetch_add(1);
+      we = cudaGetLastError();
+    }
+    if (prev != p->device) cudaSetDevice(prev);
+    if (we != cudaSuccess) return cuda_fail(we, "backward launch (wide)");
+    return RAYEN_OK;
+  }
   const int block = kBwdThreads;
   long long grid = (B + block - 1) / block;
   const long long cap = static_cast<long long>(p->sm_count) * 12;  // 12 blocks x 18 KB of tile memory per SM at n = 32
@@ -779,6 +923,10 @@ extern "C" int rayen_violation_f32(const rayen_plan_t* p, const float* y, int64_
   long long grid = (B + warps - 1) / warps;
   if (grid > static_cast<long long>(p->sm_count) * 8) grid = static_cast<long long>(p->sm_count) * 8;
   const size_t smem = static_cast<size_t>(warps) * ((d.k + 3) / 4 * 4) * sizeof(float);
+  if (smem > static_cast<size_t>(p->max_smem_optin)) {
+    if (prev != p->device) cudaSetDevice(prev);
+    return fail(RAYEN_ERR_UNSUPPORTED, "violation metric: k=%d needs %zu bytes of shared memory", d.k, smem);
+  }
   viol_lqs_kernel<<<static_cast<int>(grid), kViolThreads, smem, stream>>>(d, y, ldy, viol, B);
   g_launches.fetch_add(1);
   cudaError_t e = cudaGetLastError();

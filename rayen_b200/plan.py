@@ -19,8 +19,9 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 11
-MAX_NP = 32
+ABI_VERSION = 12
+MAX_NP = 32      # widest subspace of the register-resident kernels; beyond it the WIDE section / wide.cuh take over
+MAX_WIDE_N = 4096
 MAX_LMI = 32
 
 
@@ -72,6 +73,11 @@ def packed_triangular_words(np_):
 TC_PANEL = 128  # rows of W per tensor-core panel (MMA N)
 TC_TABLE_WORDS = 32
 LMI_TC_PANEL = 128  # entries of the LMI matrix per panel of the contraction GEMM (MMA N)
+WIDE_MAGIC = 0x57494445
+WIDE_HEADER_WORDS = 16
+WIDE_TASK_WORDS = 8
+WIDE_LIN, WIDE_QUAD, WIDE_SOC = 1, 2, 3
+WIDE_LIN_GROUPS = 4   # a linear task is up to 4 groups of 32 rows
 
 
 def split_tf32(x):
@@ -126,8 +132,14 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
     k, n = N.shape
     y0 = N @ z0 + yp
     np_ = _round_up_pow2(n)
-    if np_ is None:
-        raise PlanError(f"subspace dimension n={n} > {MAX_NP} is not covered by the sm_100a kernels yet")
+    wide = np_ is None
+    if wide:
+        # n > 32: the directions no longer fit a thread's registers; the WIDE section below feeds wide.cuh
+        if n > MAX_WIDE_N:
+            raise PlanError(f"subspace dimension n={n} > {MAX_WIDE_N} is not covered by the sm_100a kernels yet")
+        if lmi is not None:
+            raise PlanError(f"an LMI constraint together with n={n} > {MAX_NP} is not covered by the sm_100a kernels yet")
+        np_ = (n + 3) // 4 * 4
     k_pad = (k + 3) // 4 * 4
     plan = PackedPlan()
     sections = []
@@ -272,37 +284,38 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
         out[:np_, :np_] = T
         return out
 
-    Dk = np.zeros((m_pad, kp))
-    Dk[:m, :n] = D
-    for base in range(0, m_pad, TC_PANEL):
-        blk = np.zeros((TC_PANEL, kp))
-        rows = Dk[base:base + TC_PANEL]
-        blk[:rows.shape[0]] = rows
-        Wrows.append(blk)
-        table.append(([0, base] + [0] * 16, [0.0] * 8))
-    items = []
-    for i, (phi_z, Delta_z, G) in enumerate(quad_f64):
-        hdr = np.zeros((ch, kp))
-        hdr[0, :n] = phi_z
-        items.append((2, i, 0.0, np.concatenate((hdr, tri_dense(G)))))
-    for j, (cz, h, Mz, A, R) in enumerate(soc_f64):
-        hdr = np.zeros((ch, kp))
-        hdr[0, :n] = cz
-        hdr[1, :n] = h
-        items.append((3, j, A, np.concatenate((hdr, tri_dense(R)))))
-    if lmi is not None:
-        hdr = np.zeros((ch, kp))
-        hdr[0, :n] = np.trace(Fz, axis1=1, axis2=2)
-        items.append((5, 0, float(lmi_r), np.concatenate((hdr, tri_dense(_triangular_factor(gram, np_))))))
-    for base in range(0, len(items), ipp):
-        blk = np.zeros((TC_PANEL, kp))
-        ints, flts = [1, 0] + [0] * 16, [0.0] * 8
-        for s_, (typ, idx, scal, rows) in enumerate(items[base:base + ipp]):
-            blk[s_ * iw:(s_ + 1) * iw] = rows
-            ints[2 + 2 * s_], ints[3 + 2 * s_] = typ, idx
-            flts[s_] = scal
-        Wrows.append(blk)
-        table.append((ints, flts))
+    if not wide:   # the tcgen05 panels exist for K <= 32 only
+        Dk = np.zeros((m_pad, kp))
+        Dk[:m, :n] = D
+        for base in range(0, m_pad, TC_PANEL):
+            blk = np.zeros((TC_PANEL, kp))
+            rows = Dk[base:base + TC_PANEL]
+            blk[:rows.shape[0]] = rows
+            Wrows.append(blk)
+            table.append(([0, base] + [0] * 16, [0.0] * 8))
+        items = []
+        for i, (phi_z, Delta_z, G) in enumerate(quad_f64):
+            hdr = np.zeros((ch, kp))
+            hdr[0, :n] = phi_z
+            items.append((2, i, 0.0, np.concatenate((hdr, tri_dense(G)))))
+        for j, (cz, h, Mz, A, R) in enumerate(soc_f64):
+            hdr = np.zeros((ch, kp))
+            hdr[0, :n] = cz
+            hdr[1, :n] = h
+            items.append((3, j, A, np.concatenate((hdr, tri_dense(R)))))
+        if lmi is not None:
+            hdr = np.zeros((ch, kp))
+            hdr[0, :n] = np.trace(Fz, axis1=1, axis2=2)
+            items.append((5, 0, float(lmi_r), np.concatenate((hdr, tri_dense(_triangular_factor(gram, np_))))))
+        for base in range(0, len(items), ipp):
+            blk = np.zeros((TC_PANEL, kp))
+            ints, flts = [1, 0] + [0] * 16, [0.0] * 8
+            for s_, (typ, idx, scal, rows) in enumerate(items[base:base + ipp]):
+                blk[s_ * iw:(s_ + 1) * iw] = rows
+                ints[2 + 2 * s_], ints[3 + 2 * s_] = typ, idx
+                flts[s_] = scal
+            Wrows.append(blk)
+            table.append((ints, flts))
     tc_panels = len(Wrows)
     tab = np.zeros((tc_panels, TC_TABLE_WORDS), dtype=np.float32)
     for pi, (ints, flts) in enumerate(table):
@@ -376,6 +389,65 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
             if pi == 0:
                 off_lmitc = off
 
+    # ---- WIDE section (n > 32, wide.cuh): every constraint as rows of ONE matrix W [R_pad x n], stored transposed
+    # (Wt[j][row]) so that a warp's 32 lanes read 32 consecutive rows of a column with one coalesced load; rows are
+    # grouped in warp tasks (see rayen_b200.h).  N is kept twice: transposed for y = y0 + alpha N u (thread per
+    # ambient coordinate) and row-major for g_z = N' g_y (thread per subspace coordinate).
+    off_wide = 0
+    if wide:
+        c32 = lambda x: (x + 31) // 32 * 32
+        m32 = c32(m)
+        blocks = [np.zeros((m32, n))]
+        blocks[0][:m] = D
+        tasks = [(WIDE_LIN, g0 * 32, min(WIDE_LIN_GROUPS, m32 // 32 - g0), g0 * 32, 0.0)
+                 for g0 in range(0, m32 // 32, WIDE_LIN_GROUPS)]
+        row = m32
+        quad_begin, soc_begin, soc_A = [], [], []
+        for i, (phi_z, Delta_z, G) in enumerate(quad_f64):
+            blk = np.zeros((c32(1 + n), n))
+            blk[0] = phi_z
+            blk[1:1 + n] = G[:n, :n]
+            blocks.append(blk)
+            tasks.append((WIDE_QUAD, row, blk.shape[0] // 32, i, 0.0))
+            quad_begin.append(row)
+            row += blk.shape[0]
+        for j, (cz, h, Mz, A, R) in enumerate(soc_f64):
+            blk = np.zeros((c32(2 + n), n))
+            blk[0] = cz
+            blk[1] = h
+            blk[2:2 + n] = R[:n, :n]
+            blocks.append(blk)
+            tasks.append((WIDE_SOC, row, blk.shape[0] // 32, j, A))
+            soc_begin.append(row)
+            soc_A.append(A)
+            row += blk.shape[0]
+        r_pad = row
+        header = np.zeros(WIDE_HEADER_WORDS, dtype=np.int32)
+        off_wide = add_f32(header.view(np.float32))
+        header_slot = exact[-1]
+        ttab = np.zeros((len(tasks), WIDE_TASK_WORDS), dtype=np.float32)
+        for ti, (kind, rb, ng, idx, scal) in enumerate(tasks):
+            ttab[ti, :4] = np.asarray([kind, rb, ng, idx], dtype=np.int32).view(np.float32)
+            ttab[ti, 4] = scal
+        off_tasks = add_f32(ttab)
+        itab = np.asarray(quad_begin + soc_begin + [0], dtype=np.int32)   # row_begin of every item (quads, then cones)
+        off_items = add_f32(itab.view(np.float32))
+        off_soc_a = add(np.asarray(soc_A + [0.0]))
+        off_wt = add(np.concatenate(blocks).T)                           # [n][r_pad]
+        k32 = c32(k)
+        off_nt = off_nrow = 0
+        if not n_is_identity:
+            nt = np.zeros((n, k32))
+            nt[:, :k] = N.T
+            off_nt = add(nt)                                              # [n][k32]: NT[j][i] = N[i][j]
+            nr = np.zeros((k, np_))
+            nr[:, :n] = N
+            off_nrow = add(nr)                                            # [k][np]
+        header[:] = 0
+        header[:13] = [WIDE_MAGIC, r_pad, len(tasks), off_tasks, off_wt, off_nt, off_nrow, k32, np_, off_items,
+                       len(quad_begin), len(soc_begin), off_soc_a]
+        header_slot[1][:] = header.view(np.float32)
+
     blob = np.concatenate(sections).astype(np.float32)
     assert blob.size == cursor and cursor % 4 == 0
     for off, arr in exact:
@@ -388,7 +460,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
                        off_y0=off_y0, off_bound=off_bound, off_lmi=off_lmi, lmi_prune=int(lmi is not None),
                        off_tc=off_tc, tc_panels=tc_panels, tc_kp=kp,
                        off_viol=off_viol, off_lmineg=off_lmineg, viol_in=viol_in, viol_eq=viol_eq,
-                       off_lmitc=off_lmitc, lmitc_panels=lmitc_panels)
+                       off_lmitc=off_lmitc, lmitc_panels=lmitc_panels, wide=int(wide), off_wide=off_wide)
     plan.f64 = dict(D=D, N=N, y0=y0, z0=z0, yp=yp, quads=quad_f64, socs=soc_f64, Fz=Fz)
     return plan
 
@@ -472,4 +544,57 @@ def evaluate_plan_numpy(plan, v):
     else:
         Nm = blob[f["off_nmat"]:f["off_nmat"] + k * (np_ + 4)].reshape(k, np_ + 4)[:, :np_]
         rho = u @ Nm.T
+    return y0[None, :] + alpha[:, None] * rho, best, act
+
+
+def evaluate_wide_numpy(plan, v):
+    """Float64 evaluation of kappa, the binding constraint and y from the WIDE section of the packed blob, task by
+    task as ``wide_forward_kernel`` walks it (a CPU self-check of the layout; nothing in the product path calls it)."""
+    f = plan.fields
+    assert f["wide"], "not a wide plan"
+    blob32 = plan.blob
+    hdr = blob32[f["off_wide"]:f["off_wide"] + WIDE_HEADER_WORDS].view(np.int32)
+    assert hdr[0] == WIDE_MAGIC
+    r_pad, n_tasks, off_tasks, off_wt, off_nt, off_nrow, k32, np_ = (int(x) for x in hdr[1:9])
+    n, k = f["n"], f["k"]
+    blob = blob32.astype(np.float64)
+    Wt = blob[off_wt:off_wt + n * r_pad].reshape(n, r_pad)
+    v = np.asarray(v, dtype=np.float64).reshape(-1, n)
+    s = np.linalg.norm(v, axis=1)
+    u = v / np.maximum(s, 1e-12)[:, None]
+    P = u @ Wt                                   # [B, r_pad]: every dot product of the set
+    best = np.zeros(v.shape[0])
+    act = np.zeros(v.shape[0], dtype=np.int64)
+
+    def consider(val, tag):
+        nonlocal best, act
+        better = val > best
+        best = np.where(better, val, best)
+        act = np.where(better, tag, act)
+
+    for t in range(n_tasks):
+        words = blob32[off_tasks + t * WIDE_TASK_WORDS:off_tasks + (t + 1) * WIDE_TASK_WORDS]
+        kind, rb, ng, idx = (int(x) for x in words[:4].view(np.int32))
+        rows = P[:, rb:rb + 32 * ng]
+        if kind == WIDE_LIN:
+            for r in range(rows.shape[1]):
+                consider(rows[:, r], (1 << 24) | (idx + r))
+        elif kind == WIDE_QUAD:
+            consider(rows[:, 0] + np.sqrt(np.sum(rows[:, 1:] ** 2, axis=1)), (2 << 24) | idx)
+        else:
+            A = float(words[4])
+            cu, hb = rows[:, 0], rows[:, 1]
+            cq = np.sum(rows[:, 2:] ** 2, axis=1) - cu ** 2
+            root = np.sqrt(np.maximum(hb * hb + A * cq, 0.0))
+            consider((hb + root) / A, (3 << 24) | idx)
+    with np.errstate(divide="ignore"):
+        alpha = np.minimum(np.where(best > 0, 1.0 / np.where(best > 0, best, 1.0), np.inf), s)
+    y0 = blob[f["off_y0"]:f["off_y0"] + k]
+    if f["n_is_identity"]:
+        rho = u
+    else:
+        NT = blob[off_nt:off_nt + n * k32].reshape(n, k32)[:, :k]
+        Nrow = blob[off_nrow:off_nrow + k * np_].reshape(k, np_)[:, :n]
+        assert np.array_equal(NT.T, Nrow)
+        rho = u @ NT
     return y0[None, :] + alpha[:, None] * rho, best, act

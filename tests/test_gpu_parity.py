@@ -580,3 +580,87 @@ def test_c_abi_error_codes_on_gpu():
     assert lib.rayen_forward_f32(plan.handle, v.data_ptr(), cs.n, y.data_ptr(), null, null, 4, 7, 0, null, null) == -1
     info = plan.kernel_info()
     assert info["sm_count"] >= 100 and info["regs_lmi_fwd"] > 0
+
+
+# ----------------------------------------------------------------------------- wide sets (n > 32, wide.cuh)
+WIDE_CASES = [
+    # k, m, eta, mu, r_M, eq, batch, method
+    (40, 50, 2, 2, 20, 0, 300, "RAYEN"),
+    (48, 100, 3, 1, 60, 3, 257, "RAYEN"),        # n = 45: equalities, N is not the identity
+    (100, 300, 2, 2, 10, 5, 130, "RAYEN"),
+    (65, 0, 1, 1, 5, 0, 67, "RAYEN"),            # no linear rows, n odd
+    (33, 7, 0, 0, 0, 0, 9, "RAYEN"),             # one ragged linear task
+    (200, 700, 0, 0, 0, 0, 64, "RAYEN"),         # several linear tasks per warp
+    (64, 90, 9, 10, 30, 2, 1, "RAYEN"),          # more items than warps, a single sample
+    (40, 50, 2, 2, 20, 0, 100, "RAYEN_old"),
+    (48, 60, 1, 1, 16, 3, 33, "RAYEN_old"),
+]
+
+
+@pytest.mark.parametrize("k,m,eta,mu,r_M,eq,batch,method", WIDE_CASES)
+def test_wide_sets_match_the_oracle(k, m, eta, mu, r_M, eq, batch, method):
+    """n > 32: kappa, y and g_v of the wide kernels against the float64 oracle; outputs feasible; kappa / active against the
+    float64 evaluation of the same packed block."""
+    from rayen_b200 import plan as plan_mod
+    spec = synthetic.wide_spec(k, m, eta, mu, r_M, eq, seed=k + batch)
+    cs = synthetic.build_constraints(spec)
+    assert cs.n == k - eq and cs.n > 32
+    extra = 1 if method == "RAYEN_old" else 0
+    v, gy = synthetic.sample_inputs(batch, cs.n + extra, cs.k, seed_v=batch, seed_g=k, scale=2.0)
+    if batch > 4 and method == "RAYEN":
+        v[2] = 0.0          # v = 0 -> y = y0
+        v[3] *= 1e-3        # interior sample: identity map
+    layer, y, gv = run_layer(cs, v, gy, method)
+    assert layer._packed.fields["wide"] == 1
+    oset = OracleSet.from_constraints(cs)
+    y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v.double(), gy.double(), method=method)
+    assert np.isfinite(y).all() and np.isfinite(gv).all()
+    assert rel(y, y_ref.numpy()) <= TOL
+    vv = v.numpy()[:, :cs.n].astype(np.float64)
+    cf = closed_form_numpy(oset, vv, gy.numpy())
+    ok = (cf["margin"] > 1e-4) & (np.linalg.norm(vv, axis=1) > 0) & np.isfinite(g_ref.numpy()).all(axis=1)
+    assert ok.sum() >= 0.6 * len(ok)
+    assert rel(gv, g_ref.numpy(), ok) <= TOL_GRAD
+    assert max_violation(oset, y, spec["A1"], spec["b1"], spec["A2"], spec["b2"]) <= 1e-5 * max(1.0, np.abs(y).max())
+    kap, act = layer.last_kappa_and_active()
+    _, kap_np, act_np = plan_mod.evaluate_wide_numpy(layer._packed, vv)
+    assert np.abs(kap.cpu().numpy() - kap_np).max() <= 1e-5 * max(1.0, kap_np.max())
+    assert (act.cpu().numpy()[ok] == act_np[ok]).all()
+    if batch > 4 and method == "RAYEN":
+        np.testing.assert_allclose(y[2], cs.y0[:, 0], atol=1e-6)
+        assert np.all(gv[2] == 0)
+
+
+def test_wide_set_properties_and_violation_metric():
+    """A wide set at a larger batch: every output feasible (float64 residuals and the GPU violation metric), interior
+    samples map to y0 + N v, the grid-stride paths of both kernels (more tiles / samples than CTAs)."""
+    spec = synthetic.wide_spec(48, 120, 2, 2, 24, 2, seed=5)
+    cs = synthetic.build_constraints(spec)
+    B = 70_001
+    v, gy = synthetic.sample_inputs(B, cs.n, cs.k, seed_v=3, scale=1.5)
+    v[::7] *= 1e-3
+    layer, y, gv = run_layer(cs, v, gy)
+    oset = OracleSet.from_constraints(cs)
+    assert max_violation(oset, y, spec["A1"], spec["b1"], spec["A2"], spec["b2"]) <= 1e-5 * max(1.0, np.abs(y).max())
+    viol = layer.violation(torch.as_tensor(y, dtype=torch.float32, device=DEV))
+    assert float(viol.max()) <= 1e-4
+    inner = np.arange(0, B, 7)
+    np.testing.assert_allclose(y[inner], cs.y0[:, 0] + v.numpy()[inner].astype(np.float64) @ cs.NA_E.T, atol=2e-6)
+    sub = np.arange(0, B, 137)
+    y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v[sub].double(), gy[sub].double())
+    ok = closed_form_numpy(oset, v[sub].numpy(), gy[sub].numpy())["margin"] > 1e-4
+    assert rel(y[sub], y_ref.numpy()) <= TOL
+    assert rel(gv[sub], g_ref.numpy(), ok) <= TOL_GRAD
+
+
+def test_wide_module_with_mapper_trains():
+    """create_map=True on a wide set: the mapper runs as nn.Linear (no fused path for n > 32) and gradients reach it."""
+    cs = synthetic.build_constraints(synthetic.wide_spec(40, 60, 1, 1, 12, 0, seed=9))
+    torch.manual_seed(0)
+    layer = ConstraintModule(cs, input_dim=16, create_map=True).to(DEV)
+    x = torch.randn(64, 16, 1, device=DEV)
+    y = layer(x)
+    assert y.shape == (64, 40, 1)
+    y.square().sum().backward()
+    assert layer.mapper.weight.grad is not None and torch.isfinite(layer.mapper.weight.grad).all()
+    assert float(layer.mapper.weight.grad.abs().max()) > 0

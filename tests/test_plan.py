@@ -57,8 +57,10 @@ def test_rejects_boundary_or_exterior_points():
 
 
 def test_unsupported_sizes_fail_loudly():
-    with pytest.raises(plan.PlanError, match="n=40"):
-        plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=40, m=8)))
+    with pytest.raises(plan.PlanError, match="n=4100"):
+        plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=4100, m=2)))
+    with pytest.raises(plan.PlanError, match="LMI constraint together with n=40"):
+        plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=40, m=8, r=4)))
     with pytest.raises(plan.PlanError, match="r=40"):
         plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=4, r=40)))
 
@@ -137,3 +139,42 @@ def test_tensor_core_sections_decode_to_the_fp32_sections(cfg):
         F32 = blob[f["off_lmi"]:f["off_lmi"] + n * rp * rp].reshape(n, rp * rp).astype(np.float64)
         assert np.abs(W[:, :n].T - F32).max() <= 2.0 ** -21 * np.abs(F32).max()
         assert not np.any(W[:, n:])
+
+
+# ----------------------------------------------------------------------------- wide plans (n > 32)
+@pytest.mark.parametrize("k,m,eta,mu,r_M,eq", [(40, 50, 2, 2, 20, 0), (48, 100, 3, 1, 60, 3), (100, 300, 2, 2, 10, 5),
+                                               (65, 0, 1, 1, 5, 0), (33, 7, 0, 0, 0, 0)])
+def test_wide_plan_decodes_to_the_oracle(k, m, eta, mu, r_M, eq):
+    """n > 32: the WIDE section (transposed row matrix + warp tasks), decoded the way wide_forward_kernel walks it, gives
+    the oracle's kappa, binding constraint and y; tasks tile the rows; the LIN/QUAD/SOC sections agree with it."""
+    spec = synthetic.wide_spec(k, m, eta, mu, r_M, eq, seed=k)
+    cs = synthetic.build_constraints(spec)
+    p = plan.build_plan_from_constraints(cs)
+    f = p.fields
+    assert f["wide"] == 1 and f["np"] % 4 == 0 and f["np"] >= cs.n and f["tc_panels"] == 0 and f["off_wide"] % 4 == 0
+    hdr = p.blob[f["off_wide"]:f["off_wide"] + plan.WIDE_HEADER_WORDS].view(np.int32)
+    r_pad, n_tasks, off_tasks = int(hdr[1]), int(hdr[2]), int(hdr[3])
+    assert hdr[0] == plan.WIDE_MAGIC and r_pad % 32 == 0 and int(hdr[10]) == eta and int(hdr[11]) == mu
+    tasks = p.blob[off_tasks:off_tasks + n_tasks * plan.WIDE_TASK_WORDS].view(np.int32).reshape(n_tasks, -1)
+    covered = 0
+    for kind, rb, ng, idx in tasks[:, :4]:
+        assert kind in (plan.WIDE_LIN, plan.WIDE_QUAD, plan.WIDE_SOC) and rb == covered and ng >= 1
+        assert kind != plan.WIDE_LIN or (ng <= plan.WIDE_LIN_GROUPS and idx == rb)
+        covered += 32 * ng
+    assert covered == r_pad
+    v, _ = synthetic.sample_inputs(96, cs.n, cs.k, seed_v=k, dtype=torch.float64)
+    cf = closed_form_numpy(OracleSet.from_constraints(cs), v.numpy())
+    y, kap, act = plan.evaluate_wide_numpy(p, v.numpy())
+    assert np.abs(y - cf["y"]).max() <= 5e-6 * max(1.0, np.abs(cf["y"]).max())
+    assert np.abs(kap - cf["kappa"]).max() <= 5e-6 * max(1.0, cf["kappa"].max())
+    ok = cf["margin"] > 1e-4
+    assert ((act >> 24)[ok] == cf["family"][ok]).all()
+    ok &= cf["family"] != 0                       # kappa = 0: no binding constraint, the index means nothing
+    assert ((act & 0xFFFFFF)[ok] == cf["index"][ok]).all()
+    y2, kap2, act2 = plan.evaluate_plan_numpy(p, v.numpy())
+    assert np.abs(y2 - y).max() <= 1e-9 and (act2[ok] == act[ok]).all()
+
+
+def test_narrow_plans_are_not_wide():
+    p = plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.config_spec("cfg5")))
+    assert p.fields["wide"] == 0 and p.fields["off_wide"] == 0 and p.fields["tc_panels"] == 13

@@ -1,0 +1,118 @@
+"""The wide kernels (rayen_b200/csrc/wide.cuh, n > 32) compiled for the HOST under a SIMT emulator (tests/emu: one OS
+thread per CUDA thread, barriers for __syncthreads/__syncwarp, shuffles through a per-warp exchange buffer) and checked
+against the oracle.  This is test infrastructure only: it exercises the kernels' indexing, task walk, barrier and
+shuffle structure on the CPU, where the GPU is not available; the GPU parity tests are in test_gpu_parity.py.  The
+product never loads this library."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.rayen_oracle import OracleSet, TorchOracle, closed_form_numpy, max_violation
+from rayen_b200 import _cabi, plan, synthetic
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_F = ctypes.POINTER(ctypes.c_float)
+_I = ctypes.POINTER(ctypes.c_int32)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = tmp_path_factory.mktemp("wide_emu")
+    src = open(os.path.join(_cabi.CSRC, "wide.cuh")).read().splitlines(True)
+    kept = [l for l in src if l.strip() not in ('#include "common.cuh"', '#include "lqs.cuh"')]
+    assert len(kept) == len(src) - 2
+    with open(out / "wide_stripped.cuh", "w") as fh:
+        fh.writelines(kept)
+    lib_path = str(out / "libwide_emu.so")
+    cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-w", f"-I{out}", f"-I{os.path.join(HERE, 'emu')}",
+           "-o", lib_path, os.path.join(HERE, "emu", "wide_emu.cpp")]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    lib = ctypes.CDLL(lib_path)
+    lib.emu_wide_forward.restype = ctypes.c_int
+    lib.emu_wide_forward.argtypes = [_F, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F,
+                                     ctypes.c_longlong, _F, _F, _I, ctypes.c_longlong, ctypes.c_int, ctypes.c_int]
+    lib.emu_wide_backward.restype = ctypes.c_int
+    lib.emu_wide_backward.argtypes = [_F, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F,
+                                      ctypes.c_longlong, _F, _F, _I, _F, ctypes.c_longlong, ctypes.c_longlong,
+                                      ctypes.c_int, ctypes.c_int]
+    return lib
+
+
+def _ptr(a, t=_F):
+    return a.ctypes.data_as(t)
+
+
+def run_emulated(lib, p, v, gy, mode, grid_f=3, grid_b=5):
+    f = p.fields
+    n, k = f["n"], f["k"]
+    v = np.ascontiguousarray(v, dtype=np.float32)
+    gy = np.ascontiguousarray(gy, dtype=np.float32)
+    B, cols = v.shape
+    y = np.full((B, k), np.nan, dtype=np.float32)
+    kap = np.full((B,), np.nan, dtype=np.float32)
+    act = np.full((B,), -1, dtype=np.int32)
+    gv = np.full((B, cols), np.nan, dtype=np.float32)
+    blob = p.blob
+    rc = lib.emu_wide_forward(_ptr(blob), f["off_wide"], n, k, f["off_y0"], f["n_is_identity"], _ptr(v), cols, _ptr(y),
+                              _ptr(kap), _ptr(act, _I), B, mode, grid_f)
+    assert rc == 0
+    rc = lib.emu_wide_backward(_ptr(blob), f["off_wide"], n, k, f["off_y0"], f["n_is_identity"], _ptr(v), cols, _ptr(gy),
+                               _ptr(kap), _ptr(act, _I), _ptr(gv), cols, B, mode, grid_b)
+    assert rc == 0
+    return y.astype(np.float64), kap, act, gv.astype(np.float64)
+
+
+def rel(a, b, rows=None):
+    if rows is not None:
+        a, b = a[rows], b[rows]
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+CASES = [
+    # k, m, eta, mu, r_M, eq, batch, method
+    (40, 50, 2, 2, 20, 0, 37, "RAYEN"),
+    (45, 70, 3, 2, 50, 3, 26, "RAYEN"),          # equalities: N is not the identity, n = 42
+    (65, 0, 1, 1, 5, 0, 17, "RAYEN"),            # no linear rows
+    (33, 7, 0, 0, 0, 0, 9, "RAYEN"),
+    (70, 300, 0, 0, 0, 0, 16, "RAYEN"),          # several linear tasks per warp
+    (36, 40, 9, 10, 12, 2, 3, "RAYEN"),          # more items than warps
+    (40, 50, 2, 2, 20, 0, 21, "RAYEN_old"),
+    (45, 30, 1, 1, 16, 3, 10, "RAYEN_old"),
+]
+
+
+@pytest.mark.parametrize("k,m,eta,mu,r_M,eq,batch,method", CASES)
+def test_wide_kernels_under_the_emulator_match_the_oracle(emu, k, m, eta, mu, r_M, eq, batch, method):
+    spec = synthetic.wide_spec(k, m, eta, mu, r_M, eq, seed=k + batch)
+    cs = synthetic.build_constraints(spec)
+    p = plan.build_plan_from_constraints(cs)
+    assert p.fields["wide"] == 1
+    old = method == "RAYEN_old"
+    v, gy = synthetic.sample_inputs(batch, cs.n + (1 if old else 0), cs.k, seed_v=batch, seed_g=k)
+    if batch > 4 and not old:
+        v[2] = 0.0
+        v[3] *= 1e-3
+    y, kap, act, gv = run_emulated(emu, p, v.numpy(), gy.numpy(), _cabi.MODE_RAYEN_OLD if old else _cabi.MODE_RAYEN)
+    assert np.isfinite(y).all() and np.isfinite(gv).all() and np.isfinite(kap).all() and (act >= 0).all()
+    oset = OracleSet.from_constraints(cs)
+    y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v.double(), gy.double(), method=method)
+    assert rel(y, y_ref.numpy()) <= 1e-5
+    vv = v.numpy()[:, :cs.n].astype(np.float64)
+    cf = closed_form_numpy(oset, vv, gy.numpy())
+    ok = (cf["margin"] > 1e-4) & (np.linalg.norm(vv, axis=1) > 0) & np.isfinite(g_ref.numpy()).all(axis=1)
+    assert ok.sum() >= 0.6 * len(ok)
+    assert rel(gv, g_ref.numpy(), ok) <= 2e-5
+    assert max_violation(oset, y, spec["A1"], spec["b1"], spec["A2"], spec["b2"]) <= 1e-5 * max(1.0, np.abs(y).max())
+    _, kap_np, act_np = plan.evaluate_wide_numpy(p, vv)
+    assert np.abs(kap - kap_np).max() <= 1e-5 * max(1.0, kap_np.max())
+    assert (act[ok] == act_np[ok]).all()
+    fams = set((act >> 24).tolist())
+    assert fams <= {0, 1, 2, 3}
+    if batch > 4 and not old:
+        np.testing.assert_allclose(y[2], cs.y0[:, 0], atol=1e-6)
+        assert np.all(gv[2] == 0)
