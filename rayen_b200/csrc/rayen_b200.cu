@@ -33,7 +33,7 @@ struct rayen_plan {
   bool viol_lmi_smem;
   bool wide;      // n > 32: the kernels of wide.cuh on the WIDE section (linear + quadratic + SOC, no LMI)
   WideDev wdev;
-  size_t wide_fwd_smem_bytes, wide_bwd_smem_bytes;
+  size_t wide_fwd_smem_bytes[2], wide_bwd_smem_bytes;  // forward: tiles of 8 / 16 samples
   bool has_lqs;   // any non-zero linear row / quadratic / cone: otherwise the LQS forward kernel is skipped
   bool prune;     // LMI pruning enabled (needs has_lqs and a BOUND section)
   bool use_tc;    // tensor-core (tcgen05) linear/quadratic/SOC forward kernel
@@ -409,27 +409,43 @@ static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** o
   WideDev w{};
   w.n = d->n; w.k = d->k;
   w.r_pad = h[1]; w.n_tasks = h[2]; w.off_tasks = h[3]; w.off_wt = h[4]; w.off_nt = h[5]; w.off_nrow = h[6];
-  w.k32 = h[7]; w.np = h[8]; w.off_items = h[9]; w.n_quad = h[10]; w.n_soc = h[11]; w.off_soc_a = h[12];
+  w.k32 = h[7]; w.np = h[8]; w.off_items = h[9]; w.n_quad = h[10]; w.n_soc = h[11]; w.n_rounds = h[12]; w.off_rounds = h[13];
   w.off_y0 = static_cast<int>(d->off_y0); w.n_is_identity = d->n_is_identity;
   const int64_t words = d->blob_words;
-  if (h[0] != kWideMagic || w.r_pad < 32 || w.r_pad % 32 || w.n_tasks < 1 || w.off_tasks < 0 ||
+  const int n_items = w.n_quad + w.n_soc;
+  if (h[0] != kWideMagic || h[14] != kWideVersion || w.r_pad < 32 || w.r_pad % 32 || w.n_tasks < 1 || w.off_tasks < 0 ||
       w.off_tasks + static_cast<int64_t>(w.n_tasks) * 8 > words || w.off_wt < 0 ||
       w.off_wt + static_cast<int64_t>(w.n) * w.r_pad > words || w.n_quad != d->n_quad || w.n_soc != d->n_soc ||
-      w.off_items < 0 || w.off_items + w.n_quad + w.n_soc > words || w.off_soc_a < 0 || w.off_soc_a + w.n_soc > words ||
-      w.np != d->np || w.k32 < d->k ||
+      w.off_items < 0 || w.off_items + static_cast<int64_t>(n_items) * 8 > words || w.n_rounds < 1 || w.off_rounds < 0 ||
+      w.off_rounds + static_cast<int64_t>(w.n_rounds) * 4 > words || w.np != d->np || w.k32 < d->k ||
       (!d->n_is_identity && (w.off_nt <= 0 || w.off_nt + static_cast<int64_t>(w.n) * w.k32 > words || w.off_nrow <= 0 ||
                              w.off_nrow + static_cast<int64_t>(w.k) * w.np > words)))
     return fail(RAYEN_ERR_BAD_ARGUMENT, "wide plan: the WIDE header does not describe this block");
   const int32_t* tasks = reinterpret_cast<const int32_t*>(d->blob + w.off_tasks);
   for (int t = 0; t < w.n_tasks; ++t) {
-    const int kind = tasks[8 * t], rb = tasks[8 * t + 1], ng = tasks[8 * t + 2];
-    if (kind < 1 || kind > 3 || rb < 0 || rb % 32 || ng < 1 || rb + 32ll * ng > w.r_pad)
+    const int32_t* tk = tasks + 8 * t;
+    const int kind = tk[0], row = tk[1], j0 = tk[2], idx = tk[3], rl0 = tk[4], slot = tk[5];
+    if (kind < 1 || kind > 3 || row < 0 || row % 32 || row + 32 > w.r_pad || j0 < 0 || j0 % 4 || j0 > w.n || idx < 0 ||
+        rl0 < 0 || rl0 % 32 || (kind != 1 && (slot < 0 || slot >= kWideSlots || idx >= kWideRoundItems)))
       return fail(RAYEN_ERR_BAD_ARGUMENT, "wide plan: task %d is invalid", t);
   }
+  const int32_t* rounds = reinterpret_cast<const int32_t*>(d->blob + w.off_rounds);
+  for (int r = 0; r < w.n_rounds; ++r) {
+    const int32_t* rd = rounds + 4 * r;
+    if (rd[0] != (r ? rounds[4 * r - 3] : 0) || rd[1] < rd[0] || rd[1] > w.n_tasks || rd[2] != (r ? rounds[4 * r - 1] : 0) ||
+        rd[3] < rd[2] || rd[3] - rd[2] > kWideRoundItems || rd[3] > n_items)
+      return fail(RAYEN_ERR_BAD_ARGUMENT, "wide plan: round %d is invalid", r);
+  }
+  if (rounds[4 * w.n_rounds - 3] != w.n_tasks || rounds[4 * w.n_rounds - 1] != n_items)
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "wide plan: the rounds do not cover the tasks and items");
   const int32_t* items = reinterpret_cast<const int32_t*>(d->blob + w.off_items);
-  for (int i = 0; i < w.n_quad + w.n_soc; ++i)
-    if (items[i] < 0 || items[i] + (i < w.n_quad ? 1 : 2) + w.n > w.r_pad)
+  for (int i = 0; i < n_items; ++i) {
+    const int32_t* it = items + 8 * i;
+    const int kind = it[1];
+    if (it[0] < 0 || it[0] % 32 || kind != (i < w.n_quad ? 2 : 3) || it[0] + (kind == 2 ? 1 : 2) + w.n > w.r_pad ||
+        it[2] != (i < w.n_quad ? i : i - w.n_quad) || it[3] < 0 || it[4] < 1 || it[3] + it[4] > kWideSlots)
       return fail(RAYEN_ERR_BAD_ARGUMENT, "wide plan: item %d is invalid", i);
+  }
 
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
@@ -453,16 +469,18 @@ static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** o
   p->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
   p->wide = true;
   p->has_lqs = true;
-  p->wide_fwd_smem_bytes = wide_fwd_smem_bytes(w.n);
+  p->wide_fwd_smem_bytes[0] = wide_fwd_smem_bytes(w.n, 8);
+  p->wide_fwd_smem_bytes[1] = wide_fwd_smem_bytes(w.n, 16);
   p->wide_bwd_smem_bytes = wide_bwd_smem_bytes(w.n);
   cudaError_t e = cudaMalloc(&p->d_blob, d->blob_words * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(p->d_blob, d->blob, d->blob_words * sizeof(float), cudaMemcpyHostToDevice);
   int rc = 0;
   if (e != cudaSuccess) rc = cuda_fail(e, "uploading the constant block");
   // the attribute is per function, not per plan: always the device maximum, so that plans of different n coexist
-  if (rc == 0 && p->wide_fwd_smem_bytes > static_cast<size_t>(p->max_smem_optin))
-    rc = fail(RAYEN_ERR_UNSUPPORTED, "wide plan: n=%d needs %zu bytes of shared memory", w.n, p->wide_fwd_smem_bytes);
-  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel), p->max_smem_optin);
+  if (rc == 0 && p->wide_fwd_smem_bytes[0] > static_cast<size_t>(p->max_smem_optin))
+    rc = fail(RAYEN_ERR_UNSUPPORTED, "wide plan: n=%d needs %zu bytes of shared memory", w.n, p->wide_fwd_smem_bytes[0]);
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<8>), p->max_smem_optin);
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<16>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_backward_kernel), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(viol_lqs_kernel), p->max_smem_optin);
   cudaSetDevice(prev);
@@ -598,11 +616,11 @@ extern "C" int rayen_plan_kernel_info(const rayen_plan_t* p, RayenKernelInfo* ou
   memset(out, 0, sizeof(*out));
   cudaFuncAttributes a;
   if (p->wide) {
-    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(wide_forward_kernel)));
+    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(wide_forward_kernel<16>)));
     out->regs_lqs_fwd = a.numRegs;
     RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(wide_backward_kernel)));
     out->regs_lqs_bwd = a.numRegs;
-    out->smem_lqs_bytes = static_cast<int>(p->wide_fwd_smem_bytes);
+    out->smem_lqs_bytes = static_cast<int>(p->wide_fwd_smem_bytes[1]);
     out->sm_count = p->sm_count;
     return RAYEN_OK;
   }
@@ -757,11 +775,21 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
     }
     cudaError_t we = cudaSuccess;
     if (stage_mask & 1) {
-      long long grid = (B + kWideTS - 1) / kWideTS;
+      // tiles of 16 samples halve the L2 traffic of the row matrix; tiles of 8 keep every SM busy on short batches
+      static const int force_ts = getenv("RAYEN_WIDE_TS") ? atoi(getenv("RAYEN_WIDE_TS")) : 0;
+      bool ts16 = (B + 15) / 16 >= p->sm_count && p->wide_fwd_smem_bytes[1] <= static_cast<size_t>(p->max_smem_optin) / 2;
+      if (force_ts == 8) ts16 = false;
+      if (force_ts == 16 && p->wide_fwd_smem_bytes[1] <= static_cast<size_t>(p->max_smem_optin)) ts16 = true;
+      const int ts = ts16 ? 16 : 8;
+      long long grid = (B + ts - 1) / ts;
       const long long cap = static_cast<long long>(p->sm_count) * 32;
       if (grid > cap) grid = cap;
-      wide_forward_kernel<<<static_cast<int>(grid), kWideThreads, p->wide_fwd_smem_bytes, stream>>>(p->wdev, v, ldv, y, kappa,
-                                                                                                  active, B, mode);
+      if (ts16)
+        wide_forward_kernel<16><<<static_cast<int>(grid), kWideThreads, p->wide_fwd_smem_bytes[1], stream>>>(
+            p->wdev, v, ldv, y, kappa, active, B, mode);
+      else
+        wide_forward_kernel<8><<<static_cast<int>(grid), kWideThreads, p->wide_fwd_smem_bytes[0], stream>>>(
+            p->wdev, v, ldv, y, kappa, active, B, mode);
       g_launches.fetch_add(1);
       we = cudaGetLastError();
     }

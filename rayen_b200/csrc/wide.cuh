@@ -2,29 +2,35 @@
 // direction no longer fits a thread's registers.  Same arithmetic as lqs.cuh (reference constraint_module.py:351-399,
 // :468-474, :512-514), different mapping: the directions of a tile of samples sit in shared memory, every constraint is
 // a set of rows of ONE matrix W (plan section WIDE, stored transposed so that 32 lanes read 32 consecutive rows of a
-// column with one coalesced load), a lane owns a row and carries its dot products with the kWideTS samples of the
-// tile in registers, and a warp owns a task (up to 128 linear rows, or one quadratic / cone).
+// column with one coalesced load), a lane owns a row and carries its dot products with the TS (8 or 16) samples of
+// the tile in registers, and the unit of work of a warp is a task = one group of 32 rows; the groups of a quadratic /
+// cone leave partial sums in shared-memory slots that a finalize pass adds up in a fixed order (deterministic).
 #pragma once
 #include "common.cuh"
 #include "lqs.cuh"
 
 namespace rayen {
 
-constexpr int kWideTS = 8;            // samples per CTA tile (forward)
-constexpr int kWideThreads = 256;     // forward: 8 warps = 8 samples staged, 8 tasks in flight
+constexpr int kWideThreads = 256;     // forward: 8 warps
 constexpr int kWideWarps = kWideThreads / 32;
-constexpr int kWideBwdThreads = 128;  // backward: one CTA per sample
+constexpr int kWideBwdThreads = 256;  // backward: one CTA per sample
 constexpr int kWideMagic = 0x57494445;
+constexpr int kWideVersion = 2;
+constexpr int kWideSlots = 256;       // partial-sum slots per round (plan.py WIDE_SLOTS)
+constexpr int kWideRoundItems = 64;   // items per round (plan.py WIDE_ROUND_ITEMS)
 
 struct WideDev {
   const float* blob;
   int n, k;
-  int r_pad, n_tasks, off_tasks, off_wt, off_nt, off_nrow, k32, np, off_items, n_quad, n_soc, off_soc_a;
+  int r_pad, n_tasks, off_tasks, off_wt, off_nt, off_nrow, k32, np, off_items, n_quad, n_soc, n_rounds, off_rounds;
   int off_y0, n_is_identity;
 };
 
-__host__ __device__ inline size_t wide_fwd_smem_bytes(int n) {
-  return (static_cast<size_t>(n) * kWideTS + 4 * kWideTS + 2 * kWideWarps * kWideTS) * sizeof(float);
+// forward smem: us[n][TS] | s_norm, s_beta, s_alpha, sbest [TS each] | stag [TS] | wbest, wtag [warps][TS] |
+//               part_sq [slots][TS] | head [items][2][TS]
+__host__ __device__ inline size_t wide_fwd_smem_bytes(int n, int ts) {
+  return (static_cast<size_t>(n) * ts + 5 * ts + 2 * kWideWarps * ts + static_cast<size_t>(kWideSlots) * ts +
+          static_cast<size_t>(kWideRoundItems) * 2 * ts) * sizeof(float);
 }
 __host__ __device__ inline size_t wide_bwd_smem_bytes(int n) {
   // u, gz, dk: n each; t: n + 2 (+ pad); 8 words of reduction scratch
@@ -37,191 +43,208 @@ __device__ __forceinline__ float warp_sum32(float x) {
   return x;
 }
 
-// acc[s] = sum_j Wt[j][row] * us[j][s]: the column walk of one row against the tile's directions
-__device__ __forceinline__ void wide_dot(const float* __restrict__ wcol, int r_pad, int n, const float4* __restrict__ us4,
-                                         float (&acc)[kWideTS]) {
+template <int TS>
+__device__ __forceinline__ void wide_fma_col(float w, const float4* __restrict__ urow, float (&acc)[TS]) {
 #pragma unroll
-  for (int s = 0; s < kWideTS; ++s) acc[s] = 0.f;
-  int j = 0;
-  for (; j + 4 <= n; j += 4) {
-    float w[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) w[q] = __ldg(wcol + static_cast<size_t>(j + q) * r_pad);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 a = us4[2 * (j + q)], b = us4[2 * (j + q) + 1];
-      acc[0] = fmaf(w[q], a.x, acc[0]);
-      acc[1] = fmaf(w[q], a.y, acc[1]);
-      acc[2] = fmaf(w[q], a.z, acc[2]);
-      acc[3] = fmaf(w[q], a.w, acc[3]);
-      acc[4] = fmaf(w[q], b.x, acc[4]);
-      acc[5] = fmaf(w[q], b.y, acc[5]);
-      acc[6] = fmaf(w[q], b.z, acc[6]);
-      acc[7] = fmaf(w[q], b.w, acc[7]);
-    }
-  }
-  for (; j < n; ++j) {
-    const float w = __ldg(wcol + static_cast<size_t>(j) * r_pad);
-    const float4 a = us4[2 * j], b = us4[2 * j + 1];
-    acc[0] = fmaf(w, a.x, acc[0]);
-    acc[1] = fmaf(w, a.y, acc[1]);
-    acc[2] = fmaf(w, a.z, acc[2]);
-    acc[3] = fmaf(w, a.w, acc[3]);
-    acc[4] = fmaf(w, b.x, acc[4]);
-    acc[5] = fmaf(w, b.y, acc[5]);
-    acc[6] = fmaf(w, b.z, acc[6]);
-    acc[7] = fmaf(w, b.w, acc[7]);
+  for (int q = 0; q < TS / 4; ++q) {
+    const float4 a = urow[q];
+    acc[4 * q + 0] = fmaf(w, a.x, acc[4 * q + 0]);
+    acc[4 * q + 1] = fmaf(w, a.y, acc[4 * q + 1]);
+    acc[4 * q + 2] = fmaf(w, a.z, acc[4 * q + 2]);
+    acc[4 * q + 3] = fmaf(w, a.w, acc[4 * q + 3]);
   }
 }
 
-// value of x[lane] for lane < kWideTS without dynamic register indexing
-__device__ __forceinline__ float pick_lane(const float (&x)[kWideTS], int lane) {
+// acc[s] = sum_{j >= j0} Wt[j][row] * us[j][s]: the column walk of one row against the tile's directions; eight
+// column loads in flight per lane
+template <int TS>
+__device__ __forceinline__ void wide_dot(const float* __restrict__ wcol, int r_pad, int j0, int n,
+                                         const float4* __restrict__ us4, float (&acc)[TS]) {
+#pragma unroll
+  for (int s = 0; s < TS; ++s) acc[s] = 0.f;
+  int j = j0;
+  for (; j + 8 <= n; j += 8) {
+    float w[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) w[q] = __ldg(wcol + static_cast<size_t>(j + q) * r_pad);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) wide_fma_col<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), acc);
+  }
+  for (; j < n; ++j) wide_fma_col<TS>(__ldg(wcol + static_cast<size_t>(j) * r_pad), us4 + static_cast<size_t>(j) * (TS / 4), acc);
+}
+
+// value of x[lane] for lane < TS without dynamic register indexing
+template <int TS>
+__device__ __forceinline__ float pick_lane(const float (&x)[TS], int lane) {
   float r = x[0];
 #pragma unroll
-  for (int s = 1; s < kWideTS; ++s)
+  for (int s = 1; s < TS; ++s)
     if (lane == s) r = x[s];
   return r;
 }
 
+// (c, ct) replaces (best, tag) when larger; equal positive values go to the lower tag (the reference's order)
+__device__ __forceinline__ void wide_take(float c, int ct, float& best, int& tag) {
+  if (c > best || (c == best && c > 0.f && ct < tag)) {
+    best = c;
+    tag = ct;
+  }
+}
+
 // ----------------------------------------------------------------------------- forward
-// grid: one CTA per tile of kWideTS samples (grid-stride); dynamic smem = wide_fwd_smem_bytes(n).
+// grid: one CTA per tile of TS samples (grid-stride); dynamic smem = wide_fwd_smem_bytes(n, TS).
+template <int TS>
 __global__ void __launch_bounds__(kWideThreads)
     wide_forward_kernel(const WideDev P, const float* __restrict__ v, long long ldv, float* __restrict__ y,
                         float* __restrict__ kappa_out, int* __restrict__ active_out, long long B, int mode) {
   extern __shared__ __align__(16) float wide_smem[];
   const int n = P.n, k = P.k;
-  float* us = wide_smem;                                  // [n][kWideTS]
-  float* s_norm = us + static_cast<size_t>(n) * kWideTS;  // [kWideTS]
-  float* s_beta = s_norm + kWideTS;
-  float* s_alpha = s_beta + kWideTS;
-  float* s_pad = s_alpha + kWideTS;
-  float* wbest = s_pad + kWideTS;                         // [kWideWarps][kWideTS]
-  int* wtag = reinterpret_cast<int*>(wbest + kWideWarps * kWideTS);
+  float* us = wide_smem;                             // [n][TS]
+  float* s_norm = us + static_cast<size_t>(n) * TS;  // [TS]
+  float* s_beta = s_norm + TS;
+  float* s_alpha = s_beta + TS;
+  float* sbest = s_alpha + TS;
+  int* stag = reinterpret_cast<int*>(sbest + TS);
+  float* wbest = sbest + 2 * TS;                     // [kWideWarps][TS]
+  int* wtag = reinterpret_cast<int*>(wbest + kWideWarps * TS);
+  float* part_sq = wbest + 2 * kWideWarps * TS;      // [kWideSlots][TS]
+  float* head = part_sq + kWideSlots * TS;           // [kWideRoundItems][2][TS]
   const float4* us4 = reinterpret_cast<const float4*>(us);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* blob = P.blob;
   const int* tasks = reinterpret_cast<const int*>(blob + P.off_tasks);
+  const int* rounds = reinterpret_cast<const int*>(blob + P.off_rounds);
+  const int* items = reinterpret_cast<const int*>(blob + P.off_items);
   const float* wt = blob + P.off_wt;
   const float* y0 = blob + P.off_y0;
-  const long long n_tiles = (B + kWideTS - 1) / kWideTS;
+  const long long n_tiles = (B + TS - 1) / TS;
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncthreads();  // the previous tile's readers of us / s_alpha are done
-    // ---- stage: warp w normalises sample w of the tile (reference constraint_module.py:470)
-    {
-      const long long b = tile * kWideTS + warp;
+    // ---- stage: a warp normalises one sample of the tile at a time (reference constraint_module.py:470)
+    for (int sl = warp; sl < TS; sl += kWideWarps) {
+      const long long b = tile * TS + sl;
       const bool valid = b < B;
       const float* vrow = v + (valid ? b : 0) * ldv;
       float ss = 0.f;
       for (int j = lane; j < n; j += 32) {
         const float x = valid ? __ldg(vrow + j) : 0.f;
-        us[j * kWideTS + warp] = x;
+        us[j * TS + sl] = x;
         ss = fmaf(x, x, ss);
       }
       ss = warp_sum32(ss);
       const float s = sqrtf(ss);
       const float inv = 1.0f / fmaxf(s, kNormEps);
       __syncwarp();
-      for (int j = lane; j < n; j += 32) us[j * kWideTS + warp] *= inv;
+      for (int j = lane; j < n; j += 32) us[j * TS + sl] *= inv;
       if (lane == 0) {
-        s_norm[warp] = s;
-        s_beta[warp] = (valid && mode == RAYEN_MODE_RAYEN_OLD) ? __ldg(vrow + n) : 0.f;
+        s_norm[sl] = s;
+        s_beta[sl] = (valid && mode == RAYEN_MODE_RAYEN_OLD) ? __ldg(vrow + n) : 0.f;
+        sbest[sl] = 0.f;
+        stag[sl] = 0;
       }
     }
     __syncthreads();
 
-    // ---- tasks: lanes 0..kWideTS-1 of a warp keep the warp's running (kappa, tag) of sample `lane`
-    float wb = 0.f;
-    int wtg = 0;
-    for (int t = warp; t < P.n_tasks; t += kWideWarps) {
-      const int kind = __ldg(tasks + t * 8 + 0), rb = __ldg(tasks + t * 8 + 1), ng = __ldg(tasks + t * 8 + 2),
-                idx = __ldg(tasks + t * 8 + 3);
-      const float A = __int_as_float(__ldg(tasks + t * 8 + 4));
-      float cand;
-      int ctag;
-      if (kind == 1) {
-        // linear rows: kappa_j = D_j . u                       (reference constraint_module.py:353)
-        float mx[kWideTS];
-        int mr[kWideTS];
+    // ---- linear rows: every lane keeps the running (max, row) of the rows it has seen        (:353)
+    float mx[TS];
+    int mr[TS];
 #pragma unroll
-        for (int s = 0; s < kWideTS; ++s) {
-          mx[s] = 0.f;
-          mr[s] = 0;
-        }
-        for (int g = 0; g < ng; ++g) {
-          float acc[kWideTS];
-          wide_dot(wt + rb + g * 32 + lane, P.r_pad, n, us4, acc);
+    for (int s = 0; s < TS; ++s) {
+      mx[s] = 0.f;
+      mr[s] = 0;
+    }
+    for (int rd = 0; rd < P.n_rounds; ++rd) {
+      const int t0 = __ldg(rounds + 4 * rd), t1 = __ldg(rounds + 4 * rd + 1), i0 = __ldg(rounds + 4 * rd + 2),
+                i1 = __ldg(rounds + 4 * rd + 3);
+      // ---- tasks of the round: one group of 32 rows each, dealt to the warps in order (heaviest first)
+      for (int t = t0 + warp; t < t1; t += kWideWarps) {
+        const int* tk = tasks + t * 8;
+        const int kind = __ldg(tk), row = __ldg(tk + 1), j0 = __ldg(tk + 2), idx = __ldg(tk + 3), rl0 = __ldg(tk + 4),
+                  slot = __ldg(tk + 5);
+        float acc[TS];
+        wide_dot<TS>(wt + row + lane, P.r_pad, j0, n, us4, acc);
+        if (kind == 1) {
 #pragma unroll
-          for (int s = 0; s < kWideTS; ++s)
-            if (acc[s] > mx[s]) {
+          for (int s = 0; s < TS; ++s)
+            if (acc[s] > mx[s]) {  // a lane's rows arrive in ascending order: strict > keeps the lowest
               mx[s] = acc[s];
-              mr[s] = idx + g * 32 + lane;
+              mr[s] = idx + lane;
             }
-        }
+        } else {
+          // a group of a quadratic {phi_z | G} or a cone {c_z, h | R}: header dot products and a partial |T u|^2 (:360-399)
+          const int rl = rl0 + lane;
+          const int hdr = (kind == 2) ? 1 : 2;
+          const bool is_hdr = rl < hdr;
+          float part[TS];
 #pragma unroll
-        for (int s = 0; s < kWideTS; ++s) group_argmax(mx[s], mr[s], 32);  // ties -> lowest row
-        cand = pick_lane(mx, lane);
-        int row = mr[0];
+          for (int s = 0; s < TS; ++s) part[s] = warp_sum32(is_hdr ? 0.f : acc[s] * acc[s]);
+          if (lane < TS) part_sq[slot * TS + lane] = pick_lane<TS>(part, lane);
+          if (rl0 == 0) {
+            float h0[TS], h1[TS];
 #pragma unroll
-        for (int s = 1; s < kWideTS; ++s)
-          if (lane == s) row = mr[s];
-        ctag = make_tag(RAYEN_FAM_LINEAR, row);
-      } else {
-        // quadratic {phi_z | G}: kappa = phi_z.u + |G u|;  cone {c_z, h | R}: root of the quadratic (:360-399)
-        const int hdr = (kind == 2) ? 1 : 2;
-        float sq[kWideTS], a0[kWideTS], a1[kWideTS];
-#pragma unroll
-        for (int s = 0; s < kWideTS; ++s) sq[s] = a0[s] = a1[s] = 0.f;
-        for (int g = 0; g < ng; ++g) {
-          float acc[kWideTS];
-          wide_dot(wt + rb + g * 32 + lane, P.r_pad, n, us4, acc);
-          const int rl = g * 32 + lane;
-#pragma unroll
-          for (int s = 0; s < kWideTS; ++s) {
-            if (rl == 0) a0[s] = acc[s];
-            else if (rl < hdr) a1[s] = acc[s];
-            else sq[s] = fmaf(acc[s], acc[s], sq[s]);
+            for (int s = 0; s < TS; ++s) {
+              h0[s] = __shfl_sync(0xffffffffu, acc[s], 0);
+              h1[s] = __shfl_sync(0xffffffffu, acc[s], 1);
+            }
+            if (lane < TS) {
+              head[(idx * 2 + 0) * TS + lane] = pick_lane<TS>(h0, lane);
+              head[(idx * 2 + 1) * TS + lane] = pick_lane<TS>(h1, lane);
+            }
           }
         }
-        float kap[kWideTS];
-#pragma unroll
-        for (int s = 0; s < kWideTS; ++s) {
-          const float nrm2 = warp_sum32(sq[s]);
-          const float h0 = __shfl_sync(0xffffffffu, a0[s], 0);
-          const float h1 = __shfl_sync(0xffffffffu, a1[s], 1);
-          if (kind == 2) {
-            kap[s] = h0 + sqrtf(nrm2);
-          } else {
-            const float cq = fmaf(-h0, h0, nrm2);
-            kap[s] = soc_root(A, h1, cq, nullptr);
-          }
-        }
-        cand = pick_lane(kap, lane);
-        ctag = make_tag(kind == 2 ? RAYEN_FAM_QUAD : RAYEN_FAM_SOC, idx);
       }
-      if (cand > wb) {  // tasks arrive in tag order within a warp: strict > keeps the lowest tag
-        wb = cand;
-        wtg = ctag;
+      __syncthreads();
+      // ---- finalize the items of the round: a warp per sample, lanes over the items, parts added in slot order
+      if (i1 > i0) {
+        for (int sl = warp; sl < TS; sl += kWideWarps) {
+          float best = 0.f;
+          int tag = 0;
+          for (int il = lane; il < i1 - i0; il += 32) {
+            const int* it = items + (i0 + il) * 8;
+            const int kind = __ldg(it + 1), fidx = __ldg(it + 2), slot0 = __ldg(it + 3), nparts = __ldg(it + 4);
+            float nrm2 = 0.f;
+            for (int q = 0; q < nparts; ++q) nrm2 += part_sq[(slot0 + q) * TS + sl];
+            const float a0 = head[(il * 2 + 0) * TS + sl];
+            float kap;
+            if (kind == 2) {
+              kap = a0 + sqrtf(nrm2);
+            } else {
+              const float A = __int_as_float(__ldg(it + 5));
+              kap = soc_root(A, head[(il * 2 + 1) * TS + sl], fmaf(-a0, a0, nrm2), nullptr);
+            }
+            wide_take(kap, make_tag(kind == 2 ? RAYEN_FAM_QUAD : RAYEN_FAM_SOC, fidx), best, tag);
+          }
+          group_argmax(best, tag, 32);
+          if (lane == 0) {
+            float b0 = sbest[sl];
+            int t0s = stag[sl];
+            wide_take(best, tag, b0, t0s);
+            sbest[sl] = b0;
+            stag[sl] = t0s;
+          }
+        }
+        __syncthreads();  // the next round reuses the slots
       }
     }
-    if (lane < kWideTS) {
-      wbest[warp * kWideTS + lane] = wb;
-      wtag[warp * kWideTS + lane] = wtg;
+    // ---- linear rows: lanes -> warp (ties -> lowest row), warps -> CTA through shared memory
+#pragma unroll
+    for (int s = 0; s < TS; ++s) group_argmax(mx[s], mr[s], 32);
+    if (lane < TS) {
+      int row = mr[0];
+#pragma unroll
+      for (int s = 1; s < TS; ++s)
+        if (lane == s) row = mr[s];
+      wbest[warp * TS + lane] = pick_lane<TS>(mx, lane);
+      wtag[warp * TS + lane] = make_tag(RAYEN_FAM_LINEAR, row);
     }
     __syncthreads();
-    // ---- combine the warps (ties -> lowest tag = the reference's evaluation order), alpha (:472-474 / :464-465)
-    if (tid < kWideTS) {
-      float best = 0.f;
-      int tag = 0;
-      for (int w = 0; w < kWideWarps; ++w) {
-        const float c = wbest[w * kWideTS + tid];
-        const int ct = wtag[w * kWideTS + tid];
-        if (c > best || (c == best && c > 0.f && ct < tag)) {
-          best = c;
-          tag = ct;
-        }
-      }
-      const long long b = tile * kWideTS + tid;
+    // ---- combine (ties -> lowest tag = the reference's evaluation order), alpha (:472-474 / :464-465)
+    if (tid < TS) {
+      float best = sbest[tid];
+      int tag = stag[tid];
+      for (int w = 0; w < kWideWarps; ++w) wide_take(wbest[w * TS + tid], wtag[w * TS + tid], best, tag);
+      const long long b = tile * TS + tid;
       if (b < B) {
         if (kappa_out) kappa_out[b] = best;
         if (active_out) active_out[b] = tag;
@@ -231,20 +254,20 @@ __global__ void __launch_bounds__(kWideThreads)
     __syncthreads();
     // ---- y = y0 + alpha N u                                   (reference constraint_module.py:512-514)
     if (P.n_is_identity) {
-      for (int e = tid; e < kWideTS * k; e += kWideThreads) {
+      for (int e = tid; e < TS * k; e += kWideThreads) {
         const int s = e / k, j = e - s * k;
-        const long long b = tile * kWideTS + s;
-        if (b < B) y[b * k + j] = fmaf(s_alpha[s], us[j * kWideTS + s], __ldg(y0 + j));
+        const long long b = tile * TS + s;
+        if (b < B) y[b * k + j] = fmaf(s_alpha[s], us[j * TS + s], __ldg(y0 + j));
       }
     } else {
       const float* nt = blob + P.off_nt;
       for (int i = tid; i < k; i += kWideThreads) {
-        float acc[kWideTS];
-        wide_dot(nt + i, P.k32, n, us4, acc);
+        float acc[TS];
+        wide_dot<TS>(nt + i, P.k32, 0, n, us4, acc);
         const float c = __ldg(y0 + i);
 #pragma unroll
-        for (int s = 0; s < kWideTS; ++s) {
-          const long long b = tile * kWideTS + s;
+        for (int s = 0; s < TS; ++s) {
+          const long long b = tile * TS + s;
           if (b < B) y[b * k + i] = fmaf(s_alpha[s], acc[s], c);
         }
       }
@@ -305,6 +328,7 @@ __global__ void __launch_bounds__(kWideBwdThreads)
       const float* nrow = blob + P.off_nrow;
       for (int a = tid; a < n; a += kWideBwdThreads) {
         float acc = 0.f;
+#pragma unroll 8
         for (int i = 0; i < k; ++i) acc = fmaf(__ldg(nrow + static_cast<size_t>(i) * P.np + a), __ldg(gyrow + i), acc);
         gz[a] = acc;
       }
@@ -320,13 +344,24 @@ __global__ void __launch_bounds__(kWideBwdThreads)
       for (int j = tid; j < n; j += kWideBwdThreads) dk[j] = __ldg(wt + static_cast<size_t>(j) * P.r_pad + idx);
     } else if (boundary && (fam == RAYEN_FAM_QUAD || fam == RAYEN_FAM_SOC)) {
       const int hdr = (fam == RAYEN_FAM_QUAD) ? 1 : 2;
-      const int rb = __ldg(items + (fam == RAYEN_FAM_QUAD ? idx : P.n_quad + idx));
+      const int* it = items + (fam == RAYEN_FAM_QUAD ? idx : P.n_quad + idx) * 8;
+      const int rb = __ldg(it);
       const float* wi = wt + rb;
-      // t = W_item u: a thread per row, coalesced over the rows
+      // t = W_item u: a thread per row, coalesced over the rows; row hdr + i of the triangular factor starts at column i;
+      // sixteen column loads in flight per thread (the walk is L2-latency-bound)
       for (int r = tid; r < hdr + n; r += kWideBwdThreads) {
-        float acc = 0.f;
-        for (int j = 0; j < n; ++j) acc = fmaf(__ldg(wi + static_cast<size_t>(j) * P.r_pad + r), u[j], acc);
-        tt[r] = acc;
+        const float* wp = wi + r;
+        float a4[4] = {0.f, 0.f, 0.f, 0.f};
+        int j = (r < hdr) ? 0 : r - hdr;
+        for (; j + 16 <= n; j += 16) {
+          float w[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) w[q] = __ldg(wp + static_cast<size_t>(j + q) * P.r_pad);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) a4[q & 3] = fmaf(w[q], u[j + q], a4[q & 3]);
+        }
+        for (; j < n; ++j) a4[0] = fmaf(__ldg(wp + static_cast<size_t>(j) * P.r_pad), u[j], a4[0]);
+        tt[r] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
       }
       __syncthreads();
       float p2 = 0.f;
@@ -338,7 +373,7 @@ __global__ void __launch_bounds__(kWideBwdThreads)
         scale_g = root > 0.f ? 1.0f / root : 0.f;
         scale_c = 1.f;  // + phi_z
       } else {
-        const float A = __ldg(blob + P.off_soc_a + idx);
+        const float A = __int_as_float(__ldg(it + 5));
         const float cu = tt[0], hb = tt[1];
         const float cq = fmaf(-cu, cu, nrm2);
         float root;
@@ -349,16 +384,27 @@ __global__ void __launch_bounds__(kWideBwdThreads)
         scale_h = kap * inv;
         scale_c = -cu * inv;
       }
-      // (T'(T u))_a: a warp per component, lanes over the rows (coalesced), shuffle sum
-      for (int a = warp; a < n; a += kWideBwdThreads / 32) {
-        const float* col = wi + static_cast<size_t>(a) * P.r_pad;
-        float acc = 0.f;
-        for (int r = hdr + lane; r < hdr + n; r += 32) acc = fmaf(__ldg(col + r), tt[r], acc);
-        acc = warp_sum32(acc);
-        if (lane == 0) {
-          float d = scale_g * acc + scale_c * __ldg(col);
-          if (hdr == 2) d = fmaf(scale_h, __ldg(col + 1), d);
-          dk[a] = d;
+      // (T'(T u))_a = sum_{r <= a} T[r][a] t_r: a warp per four components, lanes over the rows (coalesced), shuffle sums
+      for (int a4 = warp * 4; a4 < n; a4 += (kWideBwdThreads / 32) * 4) {
+        const int amax = (a4 + 3 < n) ? a4 + 3 : n - 1;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int r = hdr + lane; r <= hdr + amax; r += 32) {
+          const float t = tt[r];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (a4 + q < n && r <= hdr + a4 + q)
+              acc[q] = fmaf(__ldg(wi + static_cast<size_t>(a4 + q) * P.r_pad + r), t, acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float g = warp_sum32(acc[q]);
+          if (lane == 0 && a4 + q < n) {
+            const float* col = wi + static_cast<size_t>(a4 + q) * P.r_pad;
+            float d = scale_g * g + scale_c * __ldg(col);
+            if (hdr == 2) d = fmaf(scale_h, __ldg(col + 1), d);
+            dk[a4 + q] = d;
+          }
         }
       }
     }

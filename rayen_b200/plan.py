@@ -74,10 +74,13 @@ TC_PANEL = 128  # rows of W per tensor-core panel (MMA N)
 TC_TABLE_WORDS = 32
 LMI_TC_PANEL = 128  # entries of the LMI matrix per panel of the contraction GEMM (MMA N)
 WIDE_MAGIC = 0x57494445
+WIDE_VERSION = 2
 WIDE_HEADER_WORDS = 16
 WIDE_TASK_WORDS = 8
+WIDE_ITEM_WORDS = 8
 WIDE_LIN, WIDE_QUAD, WIDE_SOC = 1, 2, 3
-WIDE_LIN_GROUPS = 4   # a linear task is up to 4 groups of 32 rows
+WIDE_SLOTS = 256        # partial-sum slots (groups of items) per round: wide.cuh kWideSlots
+WIDE_ROUND_ITEMS = 64   # items per round: wide.cuh kWideRoundItems
 
 
 def split_tf32(x):
@@ -390,49 +393,66 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
                 off_lmitc = off
 
     # ---- WIDE section (n > 32, wide.cuh): every constraint as rows of ONE matrix W [R_pad x n], stored transposed
-    # (Wt[j][row]) so that a warp's 32 lanes read 32 consecutive rows of a column with one coalesced load; rows are
-    # grouped in warp tasks (see rayen_b200.h).  N is kept twice: transposed for y = y0 + alpha N u (thread per
-    # ambient coordinate) and row-major for g_z = N' g_y (thread per subspace coordinate).
+    # (Wt[j][row]) so that a warp's 32 lanes read 32 consecutive rows of a column with one coalesced load.  The unit
+    # of work of a warp is a TASK = one group of 32 rows (see rayen_b200.h); the groups of an item leave partial sums
+    # in shared-memory slots that a finalize pass adds up in a fixed order, so items are processed in ROUNDS that fit
+    # the slot budget.  N is kept twice: transposed for y = y0 + alpha N u (thread per ambient coordinate) and
+    # row-major for g_z = N' g_y (thread per subspace coordinate).
     off_wide = 0
     if wide:
         c32 = lambda x: (x + 31) // 32 * 32
         m32 = c32(m)
         blocks = [np.zeros((m32, n))]
         blocks[0][:m] = D
-        tasks = [(WIDE_LIN, g0 * 32, min(WIDE_LIN_GROUPS, m32 // 32 - g0), g0 * 32, 0.0)
-                 for g0 in range(0, m32 // 32, WIDE_LIN_GROUPS)]
+        lin_tasks = [(WIDE_LIN, g * 32, 0, g * 32, 0, 0) for g in range(m32 // 32)]
         row = m32
-        quad_begin, soc_begin, soc_A = [], [], []
+        items = []          # (row_begin, kind, family index, groups, A)
         for i, (phi_z, Delta_z, G) in enumerate(quad_f64):
             blk = np.zeros((c32(1 + n), n))
             blk[0] = phi_z
-            blk[1:1 + n] = G[:n, :n]
+            blk[1:1 + n] = np.triu(G[:n, :n])
             blocks.append(blk)
-            tasks.append((WIDE_QUAD, row, blk.shape[0] // 32, i, 0.0))
-            quad_begin.append(row)
+            items.append((row, WIDE_QUAD, i, blk.shape[0] // 32, 0.0))
             row += blk.shape[0]
         for j, (cz, h, Mz, A, R) in enumerate(soc_f64):
             blk = np.zeros((c32(2 + n), n))
             blk[0] = cz
             blk[1] = h
-            blk[2:2 + n] = R[:n, :n]
+            blk[2:2 + n] = np.triu(R[:n, :n])
             blocks.append(blk)
-            tasks.append((WIDE_SOC, row, blk.shape[0] // 32, j, A))
-            soc_begin.append(row)
-            soc_A.append(A)
+            items.append((row, WIDE_SOC, j, blk.shape[0] // 32, A))
             row += blk.shape[0]
         r_pad = row
+        # rounds: as many whole items as fit WIDE_SLOTS partial-sum slots and WIDE_ROUND_ITEMS headers
+        rounds, tasks, itab = [], [], np.zeros((len(items) + 1, WIDE_ITEM_WORDS), dtype=np.float32)
+        cur_tasks, item_begin, slots = list(lin_tasks), 0, 0
+
+        def close_round(item_end):
+            nonlocal cur_tasks, item_begin, slots
+            # heaviest groups first (a triangular factor's later groups skip their leading zero columns), stable
+            cur_tasks.sort(key=lambda t: t[2])
+            rounds.append((len(tasks), len(tasks) + len(cur_tasks), item_begin, item_end))
+            tasks.extend(cur_tasks)
+            cur_tasks, item_begin, slots = [], item_end, 0
+
+        for ii, (rb, kind, fidx, groups, A) in enumerate(items):
+            if slots + groups > WIDE_SLOTS or ii - item_begin >= WIDE_ROUND_ITEMS:
+                close_round(ii)
+            hdr_rows = 1 if kind == WIDE_QUAD else 2
+            itab[ii, :5] = np.asarray([rb, kind, fidx, slots, groups], dtype=np.int32).view(np.float32)
+            itab[ii, 5] = A
+            for g in range(groups):
+                j0 = max(0, 32 * g - hdr_rows) // 4 * 4          # columns below it are zero in every row of the group
+                cur_tasks.append((kind, rb + 32 * g, j0, ii - item_begin, 32 * g, slots + g))
+            slots += groups
+        close_round(len(items))
         header = np.zeros(WIDE_HEADER_WORDS, dtype=np.int32)
         off_wide = add_f32(header.view(np.float32))
         header_slot = exact[-1]
-        ttab = np.zeros((len(tasks), WIDE_TASK_WORDS), dtype=np.float32)
-        for ti, (kind, rb, ng, idx, scal) in enumerate(tasks):
-            ttab[ti, :4] = np.asarray([kind, rb, ng, idx], dtype=np.int32).view(np.float32)
-            ttab[ti, 4] = scal
-        off_tasks = add_f32(ttab)
-        itab = np.asarray(quad_begin + soc_begin + [0], dtype=np.int32)   # row_begin of every item (quads, then cones)
-        off_items = add_f32(itab.view(np.float32))
-        off_soc_a = add(np.asarray(soc_A + [0.0]))
+        ttab = np.asarray([list(t) + [0, 0] for t in tasks], dtype=np.int32).reshape(len(tasks), WIDE_TASK_WORDS)
+        off_tasks = add_f32(ttab.view(np.float32))
+        off_rounds = add_f32(np.asarray(rounds, dtype=np.int32).reshape(-1).view(np.float32))
+        off_items = add_f32(itab)
         off_wt = add(np.concatenate(blocks).T)                           # [n][r_pad]
         k32 = c32(k)
         off_nt = off_nrow = 0
@@ -444,8 +464,8 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
             nr[:, :n] = N
             off_nrow = add(nr)                                            # [k][np]
         header[:] = 0
-        header[:13] = [WIDE_MAGIC, r_pad, len(tasks), off_tasks, off_wt, off_nt, off_nrow, k32, np_, off_items,
-                       len(quad_begin), len(soc_begin), off_soc_a]
+        header[:15] = [WIDE_MAGIC, r_pad, len(tasks), off_tasks, off_wt, off_nt, off_nrow, k32, np_, off_items,
+                       len(quad_f64), len(soc_f64), len(rounds), off_rounds, WIDE_VERSION]
         header_slot[1][:] = header.view(np.float32)
 
     blob = np.concatenate(sections).astype(np.float32)
@@ -548,45 +568,71 @@ def evaluate_plan_numpy(plan, v):
 
 
 def evaluate_wide_numpy(plan, v):
-    """Float64 evaluation of kappa, the binding constraint and y from the WIDE section of the packed blob, task by
-    task as ``wide_forward_kernel`` walks it (a CPU self-check of the layout; nothing in the product path calls it)."""
+    """Float64 evaluation of kappa, the binding constraint and y from the WIDE section of the packed blob, round by
+    round and task by task as ``wide_forward_kernel`` walks it, including the leading columns a task skips (a CPU
+    self-check of the layout; nothing in the product path calls it)."""
     f = plan.fields
     assert f["wide"], "not a wide plan"
     blob32 = plan.blob
     hdr = blob32[f["off_wide"]:f["off_wide"] + WIDE_HEADER_WORDS].view(np.int32)
-    assert hdr[0] == WIDE_MAGIC
-    r_pad, n_tasks, off_tasks, off_wt, off_nt, off_nrow, k32, np_ = (int(x) for x in hdr[1:9])
+    assert hdr[0] == WIDE_MAGIC and hdr[14] == WIDE_VERSION
+    r_pad, n_tasks, off_tasks, off_wt, off_nt, off_nrow, k32, np_, off_items, n_quad, n_soc, n_rounds, off_rounds = (
+        int(x) for x in hdr[1:14])
     n, k = f["n"], f["k"]
     blob = blob32.astype(np.float64)
     Wt = blob[off_wt:off_wt + n * r_pad].reshape(n, r_pad)
     v = np.asarray(v, dtype=np.float64).reshape(-1, n)
+    B = v.shape[0]
     s = np.linalg.norm(v, axis=1)
     u = v / np.maximum(s, 1e-12)[:, None]
-    P = u @ Wt                                   # [B, r_pad]: every dot product of the set
-    best = np.zeros(v.shape[0])
-    act = np.zeros(v.shape[0], dtype=np.int64)
+    best = np.zeros(B)
+    act = np.zeros(B, dtype=np.int64)
 
     def consider(val, tag):
         nonlocal best, act
-        better = val > best
+        better = (val > best) | ((val == best) & (val > 0) & (tag < act))
         best = np.where(better, val, best)
         act = np.where(better, tag, act)
 
-    for t in range(n_tasks):
-        words = blob32[off_tasks + t * WIDE_TASK_WORDS:off_tasks + (t + 1) * WIDE_TASK_WORDS]
-        kind, rb, ng, idx = (int(x) for x in words[:4].view(np.int32))
-        rows = P[:, rb:rb + 32 * ng]
-        if kind == WIDE_LIN:
-            for r in range(rows.shape[1]):
-                consider(rows[:, r], (1 << 24) | (idx + r))
-        elif kind == WIDE_QUAD:
-            consider(rows[:, 0] + np.sqrt(np.sum(rows[:, 1:] ** 2, axis=1)), (2 << 24) | idx)
-        else:
-            A = float(words[4])
-            cu, hb = rows[:, 0], rows[:, 1]
-            cq = np.sum(rows[:, 2:] ** 2, axis=1) - cu ** 2
-            root = np.sqrt(np.maximum(hb * hb + A * cq, 0.0))
-            consider((hb + root) / A, (3 << 24) | idx)
+    tasks = blob32[off_tasks:off_tasks + n_tasks * WIDE_TASK_WORDS].view(np.int32).reshape(n_tasks, WIDE_TASK_WORDS)
+    rounds = blob32[off_rounds:off_rounds + 4 * n_rounds].view(np.int32).reshape(n_rounds, 4)
+    items = blob32[off_items:off_items + (n_quad + n_soc) * WIDE_ITEM_WORDS].reshape(n_quad + n_soc, WIDE_ITEM_WORDS)
+    seen_tasks = 0
+    for (t0, t1, i0, i1) in rounds:
+        assert t0 == seen_tasks and i1 - i0 <= WIDE_ROUND_ITEMS
+        seen_tasks = t1
+        part = np.zeros((WIDE_SLOTS, B))
+        head = np.zeros((WIDE_ROUND_ITEMS, 2, B))
+        for kind, row, j0, idx, rl0, slot, _, _ in tasks[t0:t1]:
+            assert j0 % 4 == 0 and row % 32 == 0
+            assert not np.any(Wt[:j0, row:row + 32]), "a task skips non-zero columns"
+            P = u[:, j0:] @ Wt[j0:, row:row + 32]            # [B, 32]
+            if kind == WIDE_LIN:
+                for r in range(32):
+                    consider(P[:, r], (1 << 24) | (idx + r))
+                continue
+            hdr_rows = 1 if kind == WIDE_QUAD else 2
+            sq = P ** 2
+            if rl0 == 0:
+                head[idx, 0] = P[:, 0]
+                sq[:, 0] = 0
+                if hdr_rows == 2:
+                    head[idx, 1] = P[:, 1]
+                    sq[:, 1] = 0
+            assert 0 <= slot < WIDE_SLOTS
+            part[slot] = sq.sum(axis=1)
+        for ii in range(i0, i1):
+            rb, kind, fidx, slot0, nparts = (int(x) for x in items[ii, :5].view(np.int32))
+            nrm2 = part[slot0:slot0 + nparts].sum(axis=0)
+            a0, a1 = head[ii - i0]
+            if kind == WIDE_QUAD:
+                consider(a0 + np.sqrt(nrm2), (2 << 24) | fidx)
+            else:
+                A = float(items[ii, 5])
+                cq = nrm2 - a0 ** 2
+                root = np.sqrt(np.maximum(a1 * a1 + A * cq, 0.0))
+                consider((a1 + root) / A, (3 << 24) | fidx)
+    assert seen_tasks == n_tasks
     with np.errstate(divide="ignore"):
         alpha = np.minimum(np.where(best > 0, 1.0 / np.where(best > 0, best, 1.0), np.inf), s)
     y0 = blob[f["off_y0"]:f["off_y0"] + k]

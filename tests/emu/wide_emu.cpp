@@ -40,19 +40,24 @@ static WideDev make_dev(const float* blob, const int* h, int n, int k, int off_y
   WideDev w{};
   w.blob = blob; w.n = n; w.k = k;
   w.r_pad = h[1]; w.n_tasks = h[2]; w.off_tasks = h[3]; w.off_wt = h[4]; w.off_nt = h[5]; w.off_nrow = h[6];
-  w.k32 = h[7]; w.np = h[8]; w.off_items = h[9]; w.n_quad = h[10]; w.n_soc = h[11]; w.off_soc_a = h[12];
+  w.k32 = h[7]; w.np = h[8]; w.off_items = h[9]; w.n_quad = h[10]; w.n_soc = h[11]; w.n_rounds = h[12]; w.off_rounds = h[13];
   w.off_y0 = off_y0; w.n_is_identity = n_is_identity;
   return w;
 }
 
 extern "C" int emu_wide_forward(const float* blob, long long off_wide, int n, int k, int off_y0, int n_is_identity,
                                 const float* v, long long ldv, float* y, float* kappa, int* active, long long B, int mode,
-                                int grid) {
+                                int grid, int ts) {
   const int* h = reinterpret_cast<const int*>(blob + off_wide);
-  if (h[0] != kWideMagic) return -1;
-  if (wide_fwd_smem_bytes(n) > sizeof(wide_smem)) return -2;
+  if (h[0] != kWideMagic || h[14] != kWideVersion) return -1;
+  if (wide_fwd_smem_bytes(n, ts) > sizeof(wide_smem)) return -2;
   const WideDev w = make_dev(blob, h, n, k, off_y0, n_is_identity);
-  emu_launch(grid, kWideThreads, [&] { wide_forward_kernel(w, v, ldv, y, kappa, active, B, mode); });
+  if (ts == 16)
+    emu_launch(grid, kWideThreads, [&] { wide_forward_kernel<16>(w, v, ldv, y, kappa, active, B, mode); });
+  else if (ts == 8)
+    emu_launch(grid, kWideThreads, [&] { wide_forward_kernel<8>(w, v, ldv, y, kappa, active, B, mode); });
+  else
+    return -3;
   return 0;
 }
 

@@ -156,12 +156,20 @@ def test_wide_plan_decodes_to_the_oracle(k, m, eta, mu, r_M, eq):
     r_pad, n_tasks, off_tasks = int(hdr[1]), int(hdr[2]), int(hdr[3])
     assert hdr[0] == plan.WIDE_MAGIC and r_pad % 32 == 0 and int(hdr[10]) == eta and int(hdr[11]) == mu
     tasks = p.blob[off_tasks:off_tasks + n_tasks * plan.WIDE_TASK_WORDS].view(np.int32).reshape(n_tasks, -1)
-    covered = 0
-    for kind, rb, ng, idx in tasks[:, :4]:
-        assert kind in (plan.WIDE_LIN, plan.WIDE_QUAD, plan.WIDE_SOC) and rb == covered and ng >= 1
-        assert kind != plan.WIDE_LIN or (ng <= plan.WIDE_LIN_GROUPS and idx == rb)
-        covered += 32 * ng
-    assert covered == r_pad
+    assert int(hdr[14]) == plan.WIDE_VERSION
+    # every group of 32 rows is exactly one task; rounds tile the task list; a round fits the kernel's slot budget
+    assert sorted(tasks[:, 1].tolist()) == list(range(0, r_pad, 32))
+    n_rounds, off_rounds = int(hdr[12]), int(hdr[13])
+    rounds = p.blob[off_rounds:off_rounds + 4 * n_rounds].view(np.int32).reshape(n_rounds, 4)
+    assert rounds[0, 0] == 0 and rounds[-1, 1] == n_tasks and rounds[0, 2] == 0 and rounds[-1, 3] == eta + mu
+    for r in range(n_rounds):
+        t0, t1, i0, i1 = rounds[r]
+        part = tasks[t0:t1][tasks[t0:t1, 0] != plan.WIDE_LIN]
+        assert i1 - i0 <= plan.WIDE_ROUND_ITEMS and (part[:, 5] < plan.WIDE_SLOTS).all() and (part[:, 3] < i1 - i0).all()
+        assert len(set(part[:, 5].tolist())) == len(part)              # one slot per group
+        assert (np.diff(tasks[t0:t1, 2]) >= 0).all()                   # heaviest (fewest skipped columns) first
+    lin = tasks[tasks[:, 0] == plan.WIDE_LIN]
+    assert (np.diff(lin[:, 1]) > 0).all() and (lin[:, 3] == lin[:, 1]).all()   # linear rows in ascending order
     v, _ = synthetic.sample_inputs(96, cs.n, cs.k, seed_v=k, dtype=torch.float64)
     cf = closed_form_numpy(OracleSet.from_constraints(cs), v.numpy())
     y, kap, act = plan.evaluate_wide_numpy(p, v.numpy())
@@ -178,3 +186,16 @@ def test_wide_plan_decodes_to_the_oracle(k, m, eta, mu, r_M, eq):
 def test_narrow_plans_are_not_wide():
     p = plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.config_spec("cfg5")))
     assert p.fields["wide"] == 0 and p.fields["off_wide"] == 0 and p.fields["tc_panels"] == 13
+
+
+def test_wide_plan_with_more_items_than_a_round_holds():
+    """More items than WIDE_ROUND_ITEMS / more groups than WIDE_SLOTS: the items are processed in several rounds."""
+    spec = synthetic.wide_spec(34, 10, 40, 40, 3, 0, seed=4)
+    cs = synthetic.build_constraints(spec)
+    p = plan.build_plan_from_constraints(cs)
+    hdr = p.blob[p.fields["off_wide"]:p.fields["off_wide"] + plan.WIDE_HEADER_WORDS].view(np.int32)
+    assert int(hdr[12]) >= 2
+    v, _ = synthetic.sample_inputs(64, cs.n, cs.k, seed_v=2, dtype=torch.float64)
+    cf = closed_form_numpy(OracleSet.from_constraints(cs), v.numpy())
+    y, kap, act = plan.evaluate_wide_numpy(p, v.numpy())
+    assert np.abs(y - cf["y"]).max() <= 5e-6 * max(1.0, np.abs(cf["y"]).max())

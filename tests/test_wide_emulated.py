@@ -35,7 +35,7 @@ def emu(tmp_path_factory):
     lib = ctypes.CDLL(lib_path)
     lib.emu_wide_forward.restype = ctypes.c_int
     lib.emu_wide_forward.argtypes = [_F, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F,
-                                     ctypes.c_longlong, _F, _F, _I, ctypes.c_longlong, ctypes.c_int, ctypes.c_int]
+                                     ctypes.c_longlong, _F, _F, _I, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.emu_wide_backward.restype = ctypes.c_int
     lib.emu_wide_backward.argtypes = [_F, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F,
                                       ctypes.c_longlong, _F, _F, _I, _F, ctypes.c_longlong, ctypes.c_longlong,
@@ -47,7 +47,7 @@ def _ptr(a, t=_F):
     return a.ctypes.data_as(t)
 
 
-def run_emulated(lib, p, v, gy, mode, grid_f=3, grid_b=5):
+def run_emulated(lib, p, v, gy, mode, ts=8, grid_f=3, grid_b=5):
     f = p.fields
     n, k = f["n"], f["k"]
     v = np.ascontiguousarray(v, dtype=np.float32)
@@ -59,7 +59,7 @@ def run_emulated(lib, p, v, gy, mode, grid_f=3, grid_b=5):
     gv = np.full((B, cols), np.nan, dtype=np.float32)
     blob = p.blob
     rc = lib.emu_wide_forward(_ptr(blob), f["off_wide"], n, k, f["off_y0"], f["n_is_identity"], _ptr(v), cols, _ptr(y),
-                              _ptr(kap), _ptr(act, _I), B, mode, grid_f)
+                              _ptr(kap), _ptr(act, _I), B, mode, grid_f, ts)
     assert rc == 0
     rc = lib.emu_wide_backward(_ptr(blob), f["off_wide"], n, k, f["off_y0"], f["n_is_identity"], _ptr(v), cols, _ptr(gy),
                                _ptr(kap), _ptr(act, _I), _ptr(gv), cols, B, mode, grid_b)
@@ -81,13 +81,15 @@ CASES = [
     (33, 7, 0, 0, 0, 0, 9, "RAYEN"),
     (70, 300, 0, 0, 0, 0, 16, "RAYEN"),          # several linear tasks per warp
     (36, 40, 9, 10, 12, 2, 3, "RAYEN"),          # more items than warps
+    (34, 10, 40, 40, 3, 0, 11, "RAYEN"),         # 80 items: two rounds
     (40, 50, 2, 2, 20, 0, 21, "RAYEN_old"),
     (45, 30, 1, 1, 16, 3, 10, "RAYEN_old"),
 ]
 
 
+@pytest.mark.parametrize("ts", [8, 16])
 @pytest.mark.parametrize("k,m,eta,mu,r_M,eq,batch,method", CASES)
-def test_wide_kernels_under_the_emulator_match_the_oracle(emu, k, m, eta, mu, r_M, eq, batch, method):
+def test_wide_kernels_under_the_emulator_match_the_oracle(emu, k, m, eta, mu, r_M, eq, batch, method, ts):
     spec = synthetic.wide_spec(k, m, eta, mu, r_M, eq, seed=k + batch)
     cs = synthetic.build_constraints(spec)
     p = plan.build_plan_from_constraints(cs)
@@ -97,7 +99,7 @@ def test_wide_kernels_under_the_emulator_match_the_oracle(emu, k, m, eta, mu, r_
     if batch > 4 and not old:
         v[2] = 0.0
         v[3] *= 1e-3
-    y, kap, act, gv = run_emulated(emu, p, v.numpy(), gy.numpy(), _cabi.MODE_RAYEN_OLD if old else _cabi.MODE_RAYEN)
+    y, kap, act, gv = run_emulated(emu, p, v.numpy(), gy.numpy(), _cabi.MODE_RAYEN_OLD if old else _cabi.MODE_RAYEN, ts=ts)
     assert np.isfinite(y).all() and np.isfinite(gv).all() and np.isfinite(kap).all() and (act >= 0).all()
     oset = OracleSet.from_constraints(cs)
     y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v.double(), gy.double(), method=method)
