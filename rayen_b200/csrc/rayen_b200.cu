@@ -413,7 +413,7 @@ static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** o
   w.off_y0 = static_cast<int>(d->off_y0); w.n_is_identity = d->n_is_identity;
   const int64_t words = d->blob_words;
   const int n_items = w.n_quad + w.n_soc;
-  if (h[0] != kWideMagic || h[14] != kWideVersion || w.r_pad < 32 || w.r_pad % 32 || w.n_tasks < 1 || w.off_tasks < 0 ||
+  if (h[0] != kWideMagic || h[14] != kWideVersion || w.r_pad < kWideGroupRows || w.r_pad % kWideGroupRows || w.n_tasks < 1 || w.off_tasks < 0 ||
       w.off_tasks + static_cast<int64_t>(w.n_tasks) * 8 > words || w.off_wt < 0 ||
       w.off_wt + static_cast<int64_t>(w.n) * w.r_pad > words || w.n_quad != d->n_quad || w.n_soc != d->n_soc ||
       w.off_items < 0 || w.off_items + static_cast<int64_t>(n_items) * 8 > words || w.n_rounds < 1 || w.off_rounds < 0 ||
@@ -424,9 +424,10 @@ static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** o
   const int32_t* tasks = reinterpret_cast<const int32_t*>(d->blob + w.off_tasks);
   for (int t = 0; t < w.n_tasks; ++t) {
     const int32_t* tk = tasks + 8 * t;
-    const int kind = tk[0], row = tk[1], j0 = tk[2], idx = tk[3], rl0 = tk[4], slot = tk[5];
-    if (kind < 1 || kind > 3 || row < 0 || row % 32 || row + 32 > w.r_pad || j0 < 0 || j0 % 4 || j0 > w.n || idx < 0 ||
-        rl0 < 0 || rl0 % 32 || (kind != 1 && (slot < 0 || slot >= kWideSlots || idx >= kWideRoundItems)))
+    const int kind = tk[0], row = tk[1], j0 = tk[2], idx = tk[3], slot = tk[5];
+    if ((kind != 1 && kind != 2 && kind != 4) || row < 0 || row % kWideGroupRows || row + kWideGroupRows > w.r_pad || j0 < 0 ||
+        j0 % 4 || j0 > w.n || idx < 0 || (kind == 2 && (slot < 0 || slot >= kWideSlots || idx >= kWideRoundItems)) ||
+        (kind == 4 && idx >= kWideRoundItems))
       return fail(RAYEN_ERR_BAD_ARGUMENT, "wide plan: task %d is invalid", t);
   }
   const int32_t* rounds = reinterpret_cast<const int32_t*>(d->blob + w.off_rounds);
@@ -442,8 +443,9 @@ static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** o
   for (int i = 0; i < n_items; ++i) {
     const int32_t* it = items + 8 * i;
     const int kind = it[1];
-    if (it[0] < 0 || it[0] % 32 || kind != (i < w.n_quad ? 2 : 3) || it[0] + (kind == 2 ? 1 : 2) + w.n > w.r_pad ||
-        it[2] != (i < w.n_quad ? i : i - w.n_quad) || it[3] < 0 || it[4] < 1 || it[3] + it[4] > kWideSlots)
+    if (it[0] < 0 || it[0] % kWideGroupRows || kind != (i < w.n_quad ? 2 : 3) || it[0] + w.n > w.r_pad ||
+        it[2] != (i < w.n_quad ? i : i - w.n_quad) || it[3] < 0 || it[4] < 1 || it[3] + it[4] > kWideSlots || it[6] < 0 ||
+        it[6] % 2 || it[6] + 2 > w.r_pad)
       return fail(RAYEN_ERR_BAD_ARGUMENT, "wide plan: item %d is invalid", i);
   }
 
@@ -481,7 +483,8 @@ static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** o
     rc = fail(RAYEN_ERR_UNSUPPORTED, "wide plan: n=%d needs %zu bytes of shared memory", w.n, p->wide_fwd_smem_bytes[0]);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<8>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<16>), p->max_smem_optin);
-  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_backward_kernel), p->max_smem_optin);
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_backward_kernel<128>), p->max_smem_optin);
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_backward_kernel<256>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(viol_lqs_kernel), p->max_smem_optin);
   cudaSetDevice(prev);
   if (rc != 0) {
@@ -618,7 +621,7 @@ extern "C" int rayen_plan_kernel_info(const rayen_plan_t* p, RayenKernelInfo* ou
   if (p->wide) {
     RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(wide_forward_kernel<16>)));
     out->regs_lqs_fwd = a.numRegs;
-    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(wide_backward_kernel)));
+    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(wide_backward_kernel<256>)));
     out->regs_lqs_bwd = a.numRegs;
     out->smem_lqs_bytes = static_cast<int>(p->wide_fwd_smem_bytes[1]);
     out->sm_count = p->sm_count;
@@ -889,8 +892,12 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
       long long wgrid = B;
       const long long wcap = static_cast<long long>(p->sm_count) * 64;
       if (wgrid > wcap) wgrid = wcap;
-      wide_backward_kernel<<<static_cast<int>(wgrid), kWideBwdThreads, p->wide_bwd_smem_bytes, stream>>>(
-          p->wdev, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
+      if (p->wdev.n < kWideBwdSwitchN)
+        wide_backward_kernel<128><<<static_cast<int>(wgrid), 128, p->wide_bwd_smem_bytes, stream>>>(
+            p->wdev, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
+      else
+        wide_backward_kernel<256><<<static_cast<int>(wgrid), 256, p->wide_bwd_smem_bytes, stream>>>(
+            p->wdev, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
       g_launches.fetch_add(1);
       we = cudaGetLastError();
     }

@@ -3,7 +3,7 @@
 // :468-474, :512-514), different mapping: the directions of a tile of samples sit in shared memory, every constraint is
 // a set of rows of ONE matrix W (plan section WIDE, stored transposed so that 32 lanes read 32 consecutive rows of a
 // column with one coalesced load), a lane owns a row and carries its dot products with the TS (8 or 16) samples of
-// the tile in registers, and the unit of work of a warp is a task = one group of 32 rows; the groups of a quadratic /
+// the tile in registers, and the unit of work of a warp is a task = one group of 64 rows (two per lane); the groups of a quadratic /
 // cone leave partial sums in shared-memory slots that a finalize pass adds up in a fixed order (deterministic).
 #pragma once
 #include "common.cuh"
@@ -13,9 +13,12 @@ namespace rayen {
 
 constexpr int kWideThreads = 256;     // forward: 8 warps
 constexpr int kWideWarps = kWideThreads / 32;
-constexpr int kWideBwdThreads = 256;  // backward: one CTA per sample
+// backward: one CTA per sample, 128 threads (n < 512: the per-sample chain is latency-bound, small CTAs keep more samples
+// in flight per SM) or 256 threads (wider sets: more rows of the binding item in flight)
+constexpr int kWideBwdSwitchN = 512;
 constexpr int kWideMagic = 0x57494445;
-constexpr int kWideVersion = 2;
+constexpr int kWideVersion = 3;
+constexpr int kWideGroupRows = 64;   // rows per task: a lane owns two consecutive rows (one 8-byte load per column)
 constexpr int kWideSlots = 256;       // partial-sum slots per round (plan.py WIDE_SLOTS)
 constexpr int kWideRoundItems = 64;   // items per round (plan.py WIDE_ROUND_ITEMS)
 
@@ -71,6 +74,41 @@ __device__ __forceinline__ void wide_dot(const float* __restrict__ wcol, int r_p
     for (int q = 0; q < 8; ++q) wide_fma_col<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), acc);
   }
   for (; j < n; ++j) wide_fma_col<TS>(__ldg(wcol + static_cast<size_t>(j) * r_pad), us4 + static_cast<size_t>(j) * (TS / 4), acc);
+}
+
+// Two consecutive rows per lane (wcol2 points at the lane's row pair, 8-byte aligned): per column one 8-byte load and
+// TS/4 broadcast 16-byte loads of the tile feed 2*TS FMAs
+template <int TS>
+__device__ __forceinline__ void wide_fma_col2(float2 w, const float4* __restrict__ urow, float (&acc0)[TS], float (&acc1)[TS]) {
+#pragma unroll
+  for (int q = 0; q < TS / 4; ++q) {
+    const float4 a = urow[q];
+    acc0[4 * q + 0] = fmaf(w.x, a.x, acc0[4 * q + 0]);
+    acc0[4 * q + 1] = fmaf(w.x, a.y, acc0[4 * q + 1]);
+    acc0[4 * q + 2] = fmaf(w.x, a.z, acc0[4 * q + 2]);
+    acc0[4 * q + 3] = fmaf(w.x, a.w, acc0[4 * q + 3]);
+    acc1[4 * q + 0] = fmaf(w.y, a.x, acc1[4 * q + 0]);
+    acc1[4 * q + 1] = fmaf(w.y, a.y, acc1[4 * q + 1]);
+    acc1[4 * q + 2] = fmaf(w.y, a.z, acc1[4 * q + 2]);
+    acc1[4 * q + 3] = fmaf(w.y, a.w, acc1[4 * q + 3]);
+  }
+}
+template <int TS>
+__device__ __forceinline__ void wide_dot2(const float* __restrict__ wcol2, int r_pad, int j0, int n,
+                                          const float4* __restrict__ us4, float (&acc0)[TS], float (&acc1)[TS]) {
+#pragma unroll
+  for (int s = 0; s < TS; ++s) acc0[s] = acc1[s] = 0.f;
+  int j = j0;
+  for (; j + 8 <= n; j += 8) {
+    float2 w[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) w[q] = __ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j + q) * r_pad));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) wide_fma_col2<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), acc0, acc1);
+  }
+  for (; j < n; ++j)
+    wide_fma_col2<TS>(__ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j) * r_pad)),
+                      us4 + static_cast<size_t>(j) * (TS / 4), acc0, acc1);
 }
 
 // value of x[lane] for lane < TS without dynamic register indexing
@@ -157,39 +195,39 @@ __global__ void __launch_bounds__(kWideThreads)
     for (int rd = 0; rd < P.n_rounds; ++rd) {
       const int t0 = __ldg(rounds + 4 * rd), t1 = __ldg(rounds + 4 * rd + 1), i0 = __ldg(rounds + 4 * rd + 2),
                 i1 = __ldg(rounds + 4 * rd + 3);
-      // ---- tasks of the round: one group of 32 rows each, dealt to the warps in order (heaviest first)
+      // ---- tasks of the round: one group of 64 rows each (two per lane), dealt to the warps in order (heaviest first)
       for (int t = t0 + warp; t < t1; t += kWideWarps) {
         const int* tk = tasks + t * 8;
-        const int kind = __ldg(tk), row = __ldg(tk + 1), j0 = __ldg(tk + 2), idx = __ldg(tk + 3), rl0 = __ldg(tk + 4),
-                  slot = __ldg(tk + 5);
-        float acc[TS];
-        wide_dot<TS>(wt + row + lane, P.r_pad, j0, n, us4, acc);
+        const int kind = __ldg(tk), row = __ldg(tk + 1), j0 = __ldg(tk + 2), idx = __ldg(tk + 3), slot = __ldg(tk + 5);
+        float acc0[TS], acc1[TS];
+        wide_dot2<TS>(wt + row + 2 * lane, P.r_pad, j0, n, us4, acc0, acc1);
         if (kind == 1) {
+          // a lane's rows arrive in ascending order: strict > keeps the lowest
 #pragma unroll
-          for (int s = 0; s < TS; ++s)
-            if (acc[s] > mx[s]) {  // a lane's rows arrive in ascending order: strict > keeps the lowest
-              mx[s] = acc[s];
-              mr[s] = idx + lane;
+          for (int s = 0; s < TS; ++s) {
+            if (acc0[s] > mx[s]) {
+              mx[s] = acc0[s];
+              mr[s] = idx + 2 * lane;
             }
-        } else {
-          // a group of a quadratic {phi_z | G} or a cone {c_z, h | R}: header dot products and a partial |T u|^2 (:360-399)
-          const int rl = rl0 + lane;
-          const int hdr = (kind == 2) ? 1 : 2;
-          const bool is_hdr = rl < hdr;
+            if (acc1[s] > mx[s]) {
+              mx[s] = acc1[s];
+              mr[s] = idx + 2 * lane + 1;
+            }
+          }
+        } else if (kind == 2) {
+          // 64 rows of the triangular factor of a quadratic / cone: a partial |T u|^2                      (:360-399)
           float part[TS];
 #pragma unroll
-          for (int s = 0; s < TS; ++s) part[s] = warp_sum32(is_hdr ? 0.f : acc[s] * acc[s]);
+          for (int s = 0; s < TS; ++s) part[s] = warp_sum32(fmaf(acc0[s], acc0[s], acc1[s] * acc1[s]));
           if (lane < TS) part_sq[slot * TS + lane] = pick_lane<TS>(part, lane);
-          if (rl0 == 0) {
-            float h0[TS], h1[TS];
+        } else {
+          // header rows of 32 items of the round: {phi_z . u, 0} of a quadratic, {c_z . u, h . u} of a cone
+          const int il = idx + lane;
+          if (il < i1 - i0) {
 #pragma unroll
             for (int s = 0; s < TS; ++s) {
-              h0[s] = __shfl_sync(0xffffffffu, acc[s], 0);
-              h1[s] = __shfl_sync(0xffffffffu, acc[s], 1);
-            }
-            if (lane < TS) {
-              head[(idx * 2 + 0) * TS + lane] = pick_lane<TS>(h0, lane);
-              head[(idx * 2 + 1) * TS + lane] = pick_lane<TS>(h1, lane);
+              head[(il * 2 + 0) * TS + s] = acc0[s];
+              head[(il * 2 + 1) * TS + s] = acc1[s];
             }
           }
         }
@@ -276,7 +314,8 @@ __global__ void __launch_bounds__(kWideThreads)
 }
 
 // ----------------------------------------------------------------------------- backward
-// Sum over the CTA (kWideBwdThreads threads), same value in every thread, fixed order (deterministic).
+// Sum over the CTA (THREADS threads), same value in every thread, fixed order (deterministic).
+template <int THREADS>
 __device__ __forceinline__ float wide_block_sum(float x, float* red) {
   x = warp_sum32(x);
   __syncthreads();  // red may still be read from the previous call
@@ -284,12 +323,13 @@ __device__ __forceinline__ float wide_block_sum(float x, float* red) {
   __syncthreads();
   float total = 0.f;
 #pragma unroll
-  for (int w = 0; w < kWideBwdThreads / 32; ++w) total += red[w];
+  for (int w = 0; w < THREADS / 32; ++w) total += red[w];
   return total;
 }
 
 // One CTA per sample (grid-stride): the closed form of SURVEY 3.3 with the vectors in shared memory.
-__global__ void __launch_bounds__(kWideBwdThreads)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
     wide_backward_kernel(const WideDev P, const float* __restrict__ v, long long ldv, const float* __restrict__ gy,
                          const float* __restrict__ kappa, const int* __restrict__ active, float* __restrict__ gv,
                          long long ldgv, long long B, int mode) {
@@ -310,23 +350,23 @@ __global__ void __launch_bounds__(kWideBwdThreads)
     const float* vrow = v + b * ldv;
     const float* gyrow = gy + b * static_cast<long long>(k);
     float part = 0.f;
-    for (int j = tid; j < n; j += kWideBwdThreads) {
+    for (int j = tid; j < n; j += THREADS) {
       const float x = __ldg(vrow + j);
       u[j] = x;
       part = fmaf(x, x, part);
       dk[j] = 0.f;
     }
-    const float ss = wide_block_sum(part, red);
+    const float ss = wide_block_sum<THREADS>(part, red);
     const float s = sqrtf(ss);
     const float inv_norm = 1.0f / fmaxf(s, kNormEps);
-    for (int j = tid; j < n; j += kWideBwdThreads) u[j] *= inv_norm;
+    for (int j = tid; j < n; j += THREADS) u[j] *= inv_norm;
     const float beta = (mode == RAYEN_MODE_RAYEN_OLD) ? __ldg(vrow + n) : 0.f;
     // g_z = N' g_y
     if (P.n_is_identity) {
-      for (int j = tid; j < n; j += kWideBwdThreads) gz[j] = __ldg(gyrow + j);
+      for (int j = tid; j < n; j += THREADS) gz[j] = __ldg(gyrow + j);
     } else {
       const float* nrow = blob + P.off_nrow;
-      for (int a = tid; a < n; a += kWideBwdThreads) {
+      for (int a = tid; a < n; a += THREADS) {
         float acc = 0.f;
 #pragma unroll 8
         for (int i = 0; i < k; ++i) acc = fmaf(__ldg(nrow + static_cast<size_t>(i) * P.np + a), __ldg(gyrow + i), acc);
@@ -341,16 +381,17 @@ __global__ void __launch_bounds__(kWideBwdThreads)
 
     // ---- d kappa / du of the binding constraint (uniform per CTA)
     if (boundary && fam == RAYEN_FAM_LINEAR) {
-      for (int j = tid; j < n; j += kWideBwdThreads) dk[j] = __ldg(wt + static_cast<size_t>(j) * P.r_pad + idx);
+      for (int j = tid; j < n; j += THREADS) dk[j] = __ldg(wt + static_cast<size_t>(j) * P.r_pad + idx);
     } else if (boundary && (fam == RAYEN_FAM_QUAD || fam == RAYEN_FAM_SOC)) {
-      const int hdr = (fam == RAYEN_FAM_QUAD) ? 1 : 2;
+      const int hdr = 2;  // tt[0], tt[1]: the header dot products (phi_z.u | c_z.u, h.u); tt[2 + i]: row i of the factor
       const int* it = items + (fam == RAYEN_FAM_QUAD ? idx : P.n_quad + idx) * 8;
-      const int rb = __ldg(it);
-      const float* wi = wt + rb;
-      // t = W_item u: a thread per row, coalesced over the rows; row hdr + i of the triangular factor starts at column i;
+      const int rb = __ldg(it), hrow = __ldg(it + 6);
+      const float* wi = wt + rb;       // the n rows of the triangular factor
+      const float* wh = wt + hrow;     // the two header rows
+      // t = W_item u: a thread per row, coalesced over the rows; row i of the triangular factor starts at column i;
       // sixteen column loads in flight per thread (the walk is L2-latency-bound)
-      for (int r = tid; r < hdr + n; r += kWideBwdThreads) {
-        const float* wp = wi + r;
+      for (int r = tid; r < hdr + n; r += THREADS) {
+        const float* wp = (r < hdr) ? wh + r : wi + (r - hdr);
         float a4[4] = {0.f, 0.f, 0.f, 0.f};
         int j = (r < hdr) ? 0 : r - hdr;
         for (; j + 16 <= n; j += 16) {
@@ -365,8 +406,8 @@ __global__ void __launch_bounds__(kWideBwdThreads)
       }
       __syncthreads();
       float p2 = 0.f;
-      for (int r = hdr + tid; r < hdr + n; r += kWideBwdThreads) p2 = fmaf(tt[r], tt[r], p2);
-      const float nrm2 = wide_block_sum(p2, red);
+      for (int r = hdr + tid; r < hdr + n; r += THREADS) p2 = fmaf(tt[r], tt[r], p2);
+      const float nrm2 = wide_block_sum<THREADS>(p2, red);
       float scale_g, scale_h = 0.f, scale_c = 0.f;  // dk = scale_g * T'(T u) + scale_h * row1 + scale_c * row0
       if (fam == RAYEN_FAM_QUAD) {
         const float root = sqrtf(nrm2);
@@ -385,25 +426,23 @@ __global__ void __launch_bounds__(kWideBwdThreads)
         scale_c = -cu * inv;
       }
       // (T'(T u))_a = sum_{r <= a} T[r][a] t_r: a warp per four components, lanes over the rows (coalesced), shuffle sums
-      for (int a4 = warp * 4; a4 < n; a4 += (kWideBwdThreads / 32) * 4) {
+      for (int a4 = warp * 4; a4 < n; a4 += (THREADS / 32) * 4) {
         const int amax = (a4 + 3 < n) ? a4 + 3 : n - 1;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-        for (int r = hdr + lane; r <= hdr + amax; r += 32) {
-          const float t = tt[r];
+        for (int r = lane; r <= amax; r += 32) {
+          const float t = tt[hdr + r];
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            if (a4 + q < n && r <= hdr + a4 + q)
+            if (a4 + q < n && r <= a4 + q)
               acc[q] = fmaf(__ldg(wi + static_cast<size_t>(a4 + q) * P.r_pad + r), t, acc[q]);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float g = warp_sum32(acc[q]);
           if (lane == 0 && a4 + q < n) {
-            const float* col = wi + static_cast<size_t>(a4 + q) * P.r_pad;
-            float d = scale_g * g + scale_c * __ldg(col);
-            if (hdr == 2) d = fmaf(scale_h, __ldg(col + 1), d);
-            dk[a4 + q] = d;
+            const float* col = wh + static_cast<size_t>(a4 + q) * P.r_pad;
+            dk[a4 + q] = fmaf(scale_h, __ldg(col + 1), fmaf(scale_c, __ldg(col), scale_g * g));
           }
         }
       }
@@ -412,8 +451,8 @@ __global__ void __launch_bounds__(kWideBwdThreads)
 
     // ---- tail: g_u, projection onto the tangent of the unit sphere, 1/|v|  (same as lqs.cuh backward_tail)
     float pz = 0.f;
-    for (int j = tid; j < n; j += kWideBwdThreads) pz = fmaf(gz[j], u[j], pz);
-    const float gzu = wide_block_sum(pz, red);
+    for (int j = tid; j < n; j += THREADS) pz = fmaf(gz[j], u[j], pz);
+    const float gzu = wide_block_sum<THREADS>(pz, red);
     float* grow = gv + b * ldgv;
     float c1, c2;  // g_u = c1 g_z - c2 dk
     if (mode == RAYEN_MODE_RAYEN_OLD) {
@@ -424,7 +463,7 @@ __global__ void __launch_bounds__(kWideBwdThreads)
       if (tid == 0) grow[n] = -c2 * eb;
     } else {
       if (!boundary) {
-        for (int j = tid; j < n; j += kWideBwdThreads) grow[j] = (s > 0.f) ? gz[j] : 0.f;
+        for (int j = tid; j < n; j += THREADS) grow[j] = (s > 0.f) ? gz[j] : 0.f;
         continue;  // uniform per CTA
       }
       const float ik = 1.0f / kap;
@@ -432,14 +471,14 @@ __global__ void __launch_bounds__(kWideBwdThreads)
       c2 = gzu * ik * ik;
     }
     float pu = 0.f;
-    for (int j = tid; j < n; j += kWideBwdThreads) {
+    for (int j = tid; j < n; j += THREADS) {
       const float g = fmaf(c1, gz[j], -c2 * dk[j]);
       dk[j] = g;  // own entries only
       pu = fmaf(g, u[j], pu);
     }
-    float guu = wide_block_sum(pu, red);
+    float guu = wide_block_sum<THREADS>(pu, red);
     if (s < kNormEps) guu = 0.f;
-    for (int j = tid; j < n; j += kWideBwdThreads) grow[j] = (dk[j] - guu * u[j]) * inv_norm;
+    for (int j = tid; j < n; j += THREADS) grow[j] = (dk[j] - guu * u[j]) * inv_norm;
   }
 }
 

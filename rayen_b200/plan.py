@@ -74,11 +74,13 @@ TC_PANEL = 128  # rows of W per tensor-core panel (MMA N)
 TC_TABLE_WORDS = 32
 LMI_TC_PANEL = 128  # entries of the LMI matrix per panel of the contraction GEMM (MMA N)
 WIDE_MAGIC = 0x57494445
-WIDE_VERSION = 2
+WIDE_VERSION = 3
 WIDE_HEADER_WORDS = 16
 WIDE_TASK_WORDS = 8
 WIDE_ITEM_WORDS = 8
-WIDE_LIN, WIDE_QUAD, WIDE_SOC = 1, 2, 3
+WIDE_LIN, WIDE_QUAD, WIDE_SOC = 1, 2, 3     # linear-row task; kinds of an item
+WIDE_FACTOR, WIDE_HDR = 2, 4                # tasks of the items: a group of factor rows / of header rows
+WIDE_GROUP_ROWS = 64                        # rows per task: two per lane (one 8-byte load per column)
 WIDE_SLOTS = 256        # partial-sum slots (groups of items) per round: wide.cuh kWideSlots
 WIDE_ROUND_ITEMS = 64   # items per round: wide.cuh kWideRoundItems
 
@@ -400,52 +402,56 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
     # row-major for g_z = N' g_y (thread per subspace coordinate).
     off_wide = 0
     if wide:
-        c32 = lambda x: (x + 31) // 32 * 32
-        m32 = c32(m)
-        blocks = [np.zeros((m32, n))]
-        blocks[0][:m] = D
-        lin_tasks = [(WIDE_LIN, g * 32, 0, g * 32, 0, 0) for g in range(m32 // 32)]
-        row = m32
-        items = []          # (row_begin, kind, family index, groups, A)
-        for i, (phi_z, Delta_z, G) in enumerate(quad_f64):
-            blk = np.zeros((c32(1 + n), n))
-            blk[0] = phi_z
-            blk[1:1 + n] = np.triu(G[:n, :n])
-            blocks.append(blk)
-            items.append((row, WIDE_QUAD, i, blk.shape[0] // 32, 0.0))
-            row += blk.shape[0]
-        for j, (cz, h, Mz, A, R) in enumerate(soc_f64):
-            blk = np.zeros((c32(2 + n), n))
-            blk[0] = cz
-            blk[1] = h
-            blk[2:2 + n] = np.triu(R[:n, :n])
-            blocks.append(blk)
-            items.append((row, WIDE_SOC, j, blk.shape[0] // 32, A))
-            row += blk.shape[0]
-        r_pad = row
+        G_ROWS = WIDE_GROUP_ROWS
+        cg = lambda x: (x + G_ROWS - 1) // G_ROWS * G_ROWS
+        m_g = cg(m)
+        lin_block = np.zeros((m_g, n))
+        lin_block[:m] = D
+        blocks = [lin_block]
+        lin_tasks = [(WIDE_LIN, g * G_ROWS, 0, g * G_ROWS, 0, 0) for g in range(m_g // G_ROWS)]
+        row = m_g
+        groups_per_item = cg(n) // G_ROWS
+        raw_items = [(WIDE_QUAD, i, phi_z, None, G, 0.0) for i, (phi_z, Delta_z, G) in enumerate(quad_f64)] + \
+                    [(WIDE_SOC, j, cz, h, R, A) for j, (cz, h, Mz, A, R) in enumerate(soc_f64)]
         # rounds: as many whole items as fit WIDE_SLOTS partial-sum slots and WIDE_ROUND_ITEMS headers
-        rounds, tasks, itab = [], [], np.zeros((len(items) + 1, WIDE_ITEM_WORDS), dtype=np.float32)
-        cur_tasks, item_begin, slots = list(lin_tasks), 0, 0
-
-        def close_round(item_end):
-            nonlocal cur_tasks, item_begin, slots
-            # heaviest groups first (a triangular factor's later groups skip their leading zero columns), stable
+        per_round = max(1, min(WIDE_ROUND_ITEMS, WIDE_SLOTS // groups_per_item))
+        rounds, tasks = [], []
+        itab = np.zeros((len(raw_items) + 1, WIDE_ITEM_WORDS), dtype=np.float32)
+        first = True
+        for i0 in range(0, max(len(raw_items), 1), per_round):
+            chunk = raw_items[i0:i0 + per_round]
+            cur_tasks = list(lin_tasks) if first else []
+            first = False
+            # header rows of the round's items: rows 2*il (phi_z | c_z) and 2*il + 1 (h of a cone, 0 of a quadratic)
+            hdr_block = np.zeros((cg(2 * len(chunk)), n))
+            hdr_row0 = row
+            for il, (kind, fidx, a0, a1, T, A) in enumerate(chunk):
+                hdr_block[2 * il] = a0
+                if a1 is not None:
+                    hdr_block[2 * il + 1] = a1
+            if len(chunk):
+                blocks.append(hdr_block)
+                for hg in range(hdr_block.shape[0] // G_ROWS):
+                    cur_tasks.append((WIDE_HDR, row + hg * G_ROWS, 0, hg * (G_ROWS // 2), 0, 0))
+                row += hdr_block.shape[0]
+            slots = 0
+            for il, (kind, fidx, a0, a1, T, A) in enumerate(chunk):
+                blk = np.zeros((cg(n), n))
+                blk[:n] = np.triu(T[:n, :n])
+                blocks.append(blk)
+                itab[i0 + il, :5] = np.asarray([row, kind, fidx, slots, groups_per_item], dtype=np.int32).view(np.float32)
+                itab[i0 + il, 5] = A
+                itab[i0 + il, 6:7] = np.asarray([hdr_row0 + 2 * il], dtype=np.int32).view(np.float32)
+                for g in range(groups_per_item):
+                    # columns below the group's first row are zero in every row of the group
+                    cur_tasks.append((WIDE_FACTOR, row + g * G_ROWS, g * G_ROWS // 4 * 4, il, 0, slots + g))
+                slots += groups_per_item
+                row += blk.shape[0]
+            # heaviest groups first, stable (linear rows stay in ascending order)
             cur_tasks.sort(key=lambda t: t[2])
-            rounds.append((len(tasks), len(tasks) + len(cur_tasks), item_begin, item_end))
+            rounds.append((len(tasks), len(tasks) + len(cur_tasks), i0, i0 + len(chunk)))
             tasks.extend(cur_tasks)
-            cur_tasks, item_begin, slots = [], item_end, 0
-
-        for ii, (rb, kind, fidx, groups, A) in enumerate(items):
-            if slots + groups > WIDE_SLOTS or ii - item_begin >= WIDE_ROUND_ITEMS:
-                close_round(ii)
-            hdr_rows = 1 if kind == WIDE_QUAD else 2
-            itab[ii, :5] = np.asarray([rb, kind, fidx, slots, groups], dtype=np.int32).view(np.float32)
-            itab[ii, 5] = A
-            for g in range(groups):
-                j0 = max(0, 32 * g - hdr_rows) // 4 * 4          # columns below it are zero in every row of the group
-                cur_tasks.append((kind, rb + 32 * g, j0, ii - item_begin, 32 * g, slots + g))
-            slots += groups
-        close_round(len(items))
+        r_pad = row
         header = np.zeros(WIDE_HEADER_WORDS, dtype=np.int32)
         off_wide = add_f32(header.view(np.float32))
         header_slot = exact[-1]
@@ -454,7 +460,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
         off_rounds = add_f32(np.asarray(rounds, dtype=np.int32).reshape(-1).view(np.float32))
         off_items = add_f32(itab)
         off_wt = add(np.concatenate(blocks).T)                           # [n][r_pad]
-        k32 = c32(k)
+        k32 = (k + 31) // 32 * 32
         off_nt = off_nrow = 0
         if not n_is_identity:
             nt = np.zeros((n, k32))
@@ -603,26 +609,25 @@ def evaluate_wide_numpy(plan, v):
         seen_tasks = t1
         part = np.zeros((WIDE_SLOTS, B))
         head = np.zeros((WIDE_ROUND_ITEMS, 2, B))
-        for kind, row, j0, idx, rl0, slot, _, _ in tasks[t0:t1]:
-            assert j0 % 4 == 0 and row % 32 == 0
-            assert not np.any(Wt[:j0, row:row + 32]), "a task skips non-zero columns"
-            P = u[:, j0:] @ Wt[j0:, row:row + 32]            # [B, 32]
+        for kind, row, j0, idx, _, slot, _, _ in tasks[t0:t1]:
+            assert j0 % 4 == 0 and row % WIDE_GROUP_ROWS == 0
+            assert not np.any(Wt[:j0, row:row + WIDE_GROUP_ROWS]), "a task skips non-zero columns"
+            P = u[:, j0:] @ Wt[j0:, row:row + WIDE_GROUP_ROWS]            # [B, 64]: lane l owns rows 2l, 2l + 1
             if kind == WIDE_LIN:
-                for r in range(32):
+                for r in range(WIDE_GROUP_ROWS):
                     consider(P[:, r], (1 << 24) | (idx + r))
-                continue
-            hdr_rows = 1 if kind == WIDE_QUAD else 2
-            sq = P ** 2
-            if rl0 == 0:
-                head[idx, 0] = P[:, 0]
-                sq[:, 0] = 0
-                if hdr_rows == 2:
-                    head[idx, 1] = P[:, 1]
-                    sq[:, 1] = 0
-            assert 0 <= slot < WIDE_SLOTS
-            part[slot] = sq.sum(axis=1)
+            elif kind == WIDE_HDR:
+                for l in range(WIDE_GROUP_ROWS // 2):
+                    if idx + l < i1 - i0:
+                        head[idx + l, 0] = P[:, 2 * l]
+                        head[idx + l, 1] = P[:, 2 * l + 1]
+            else:
+                assert kind == WIDE_FACTOR and 0 <= slot < WIDE_SLOTS and 0 <= idx < i1 - i0
+                part[slot] = (P ** 2).sum(axis=1)
         for ii in range(i0, i1):
             rb, kind, fidx, slot0, nparts = (int(x) for x in items[ii, :5].view(np.int32))
+            hdr_row = int(items[ii, 6:7].view(np.int32)[0])
+            assert np.array_equal(u @ Wt[:, hdr_row], head[ii - i0, 0]) or np.allclose(u @ Wt[:, hdr_row], head[ii - i0, 0])
             nrm2 = part[slot0:slot0 + nparts].sum(axis=0)
             a0, a1 = head[ii - i0]
             if kind == WIDE_QUAD:

@@ -17,6 +17,7 @@ struct EmuDim3 { int x, y, z; };
 static thread_local EmuDim3 threadIdx{0, 0, 0};
 static thread_local EmuDim3 blockIdx{0, 0, 0};
 static EmuDim3 blockDim{1, 1, 1}, gridDim{1, 1, 1};
+struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 
 #define __global__

@@ -63,10 +63,15 @@ extern "C" int emu_wide_forward(const float* blob, long long off_wide, int n, in
 
 extern "C" int emu_wide_backward(const float* blob, long long off_wide, int n, int k, int off_y0, int n_is_identity,
                                  const float* v, long long ldv, const float* gy, const float* kappa, const int* active,
-                                 float* gv, long long ldgv, long long B, int mode, int grid) {
+                                 float* gv, long long ldgv, long long B, int mode, int grid, int threads) {
   const int* h = reinterpret_cast<const int*>(blob + off_wide);
   if (h[0] != kWideMagic) return -1;
   const WideDev w = make_dev(blob, h, n, k, off_y0, n_is_identity);
-  emu_launch(grid, kWideBwdThreads, [&] { wide_backward_kernel(w, v, ldv, gy, kappa, active, gv, ldgv, B, mode); });
+  if (threads == 128)
+    emu_launch(grid, 128, [&] { wide_backward_kernel<128>(w, v, ldv, gy, kappa, active, gv, ldgv, B, mode); });
+  else if (threads == 256)
+    emu_launch(grid, 256, [&] { wide_backward_kernel<256>(w, v, ldv, gy, kappa, active, gv, ldgv, B, mode); });
+  else
+    return -3;
   return 0;
 }

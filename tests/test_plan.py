@@ -154,18 +154,20 @@ def test_wide_plan_decodes_to_the_oracle(k, m, eta, mu, r_M, eq):
     assert f["wide"] == 1 and f["np"] % 4 == 0 and f["np"] >= cs.n and f["tc_panels"] == 0 and f["off_wide"] % 4 == 0
     hdr = p.blob[f["off_wide"]:f["off_wide"] + plan.WIDE_HEADER_WORDS].view(np.int32)
     r_pad, n_tasks, off_tasks = int(hdr[1]), int(hdr[2]), int(hdr[3])
-    assert hdr[0] == plan.WIDE_MAGIC and r_pad % 32 == 0 and int(hdr[10]) == eta and int(hdr[11]) == mu
+    assert hdr[0] == plan.WIDE_MAGIC and r_pad % plan.WIDE_GROUP_ROWS == 0 and int(hdr[10]) == eta and int(hdr[11]) == mu
     tasks = p.blob[off_tasks:off_tasks + n_tasks * plan.WIDE_TASK_WORDS].view(np.int32).reshape(n_tasks, -1)
     assert int(hdr[14]) == plan.WIDE_VERSION
-    # every group of 32 rows is exactly one task; rounds tile the task list; a round fits the kernel's slot budget
-    assert sorted(tasks[:, 1].tolist()) == list(range(0, r_pad, 32))
+    # every group of 64 rows is exactly one task; rounds tile the task list; a round fits the kernel's slot budget
+    assert sorted(tasks[:, 1].tolist()) == list(range(0, r_pad, plan.WIDE_GROUP_ROWS))
     n_rounds, off_rounds = int(hdr[12]), int(hdr[13])
     rounds = p.blob[off_rounds:off_rounds + 4 * n_rounds].view(np.int32).reshape(n_rounds, 4)
     assert rounds[0, 0] == 0 and rounds[-1, 1] == n_tasks and rounds[0, 2] == 0 and rounds[-1, 3] == eta + mu
     for r in range(n_rounds):
         t0, t1, i0, i1 = rounds[r]
-        part = tasks[t0:t1][tasks[t0:t1, 0] != plan.WIDE_LIN]
+        part = tasks[t0:t1][tasks[t0:t1, 0] == plan.WIDE_FACTOR]
+        heads = tasks[t0:t1][tasks[t0:t1, 0] == plan.WIDE_HDR]
         assert i1 - i0 <= plan.WIDE_ROUND_ITEMS and (part[:, 5] < plan.WIDE_SLOTS).all() and (part[:, 3] < i1 - i0).all()
+        assert len(heads) == (i1 - i0 + 31) // 32 and sorted(heads[:, 3].tolist()) == list(range(0, i1 - i0, 32))
         assert len(set(part[:, 5].tolist())) == len(part)              # one slot per group
         assert (np.diff(tasks[t0:t1, 2]) >= 0).all()                   # heaviest (fewest skipped columns) first
     lin = tasks[tasks[:, 0] == plan.WIDE_LIN]

@@ -39,7 +39,7 @@ def emu(tmp_path_factory):
     lib.emu_wide_backward.restype = ctypes.c_int
     lib.emu_wide_backward.argtypes = [_F, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F,
                                       ctypes.c_longlong, _F, _F, _I, _F, ctypes.c_longlong, ctypes.c_longlong,
-                                      ctypes.c_int, ctypes.c_int]
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return lib
 
 
@@ -62,7 +62,7 @@ def run_emulated(lib, p, v, gy, mode, ts=8, grid_f=3, grid_b=5):
                               _ptr(kap), _ptr(act, _I), B, mode, grid_f, ts)
     assert rc == 0
     rc = lib.emu_wide_backward(_ptr(blob), f["off_wide"], n, k, f["off_y0"], f["n_is_identity"], _ptr(v), cols, _ptr(gy),
-                               _ptr(kap), _ptr(act, _I), _ptr(gv), cols, B, mode, grid_b)
+                               _ptr(kap), _ptr(act, _I), _ptr(gv), cols, B, mode, grid_b, 128 if ts == 8 else 256)
     assert rc == 0
     return y.astype(np.float64), kap, act, gv.astype(np.float64)
 
