@@ -510,6 +510,19 @@ def run_b200(args, rank, local_rank, world):
                                           "hbm_frac": abytes / (ms * 1e-3) / 1e9 / peak}
                 del eb_bench, elayer
                 torch.cuda.empty_cache()
+        # wide sets (n > 32, wide.cuh): dim 64 (256 rows + 4 ellipsoids + 4 cones) and dim 256 (1024 rows)
+        for wname, (wk, wm, weta, wmu, wrm, wb) in (("wide_n64", (64, 256, 4, 4, 32, 65536)),
+                                                    ("wide_n256", (256, 1024, 0, 0, 0, 8192))):
+            ecs = synthetic.build_constraints(synthetic.wide_spec(wk, wm, weta, wmu, wrm, 0, seed=1))
+            elayer = ConstraintModule(ecs, create_map=False).to(device)
+            per_set = wb * 4 * (3 * elayer.n + 2 * elayer.k)
+            eb_bench = DeviceBench(elayer, wb, device, pool=max(2, min(POOL, int(300e6 // per_set) + 1)))
+            ms = eb_bench.time_loop(eb_bench.step, 20, 5)
+            fwd_ms = eb_bench.time_loop(lambda i: eb_bench.forward(eb_bench.sets[i % eb_bench.pool]), 20, 5)
+            extra[f"{wname}_B{wb}"] = {"fwd_bwd_samples_per_s": wb / (ms * 1e-3), "ms_per_step": ms, "fwd_ms": fwd_ms,
+                                       "hbm_frac": per_set / (ms * 1e-3) / 1e9 / peak}
+            del eb_bench, elayer
+            torch.cuda.empty_cache()
         line["extra"] = extra
 
     print(json.dumps(line), flush=True)

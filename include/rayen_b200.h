@@ -77,13 +77,19 @@ extern "C" {
  *           (the LMI section's order), per panel W_hi and W_lo (128 x tc_kp each, TF32 split) in the operand
  *           layout [k/4][row/8][row%8][k%4]
  *   WIDE    (wide == 1: 32 < n <= 4096, linear + quadratic + SOC; wide.cuh) 16 int32 words {magic 0x57494445, R_pad,
- *           n_tasks, off_tasks, off_wt, off_nt, off_nrow, k32, np, off_items, n_quad, n_soc, off_soc_a, 0, 0, 0}
- *           (offsets in words from `blob`), then
- *             tasks   n_tasks x 8 words {kind 1 linear / 2 quadratic / 3 cone, first row, groups of 32 rows, index of
- *                     the first row (linear) or of the item, float A of a cone, 0, 0, 0}: the unit of work of a warp
- *             items   first row of every quadratic, then of every cone (int32), and the cones' A (float)
- *             Wt      [n][R_pad], Wt[j][row] = W[row][j]; W stacks the rows of D (zero padded to 32), then per quadratic
- *                     {phi_z, the n rows of G} and per cone {c_z, h, the n rows of R}, each item zero padded to 32 rows
+ *           n_tasks, off_tasks, off_wt, off_nt, off_nrow, k32, np, off_items, n_quad, n_soc, n_rounds, off_rounds,
+ *           layout version 3, 0} (offsets in words from `blob`), then
+ *             Wt      [n][R_pad], Wt[j][row] = W[row][j]; W stacks the rows of D (zero padded to 64), then per round of
+ *                     items a block of header rows (row 2i: phi_z of a quadratic / c_z of a cone, row 2i+1: h of a
+ *                     cone / zeros; padded to 64) followed by the n rows of each item's upper-triangular factor
+ *                     (G: G'G = N'Delta N; R: R'R = (MN)'(MN); padded to 64)
+ *             tasks   n_tasks x 8 int32 {kind 1 linear / 2 factor / 4 header, first row (multiple of 64), first
+ *                     non-zero column (multiple of 4), index of the first row (linear) | item within the round
+ *                     (factor) | first item within the round (header), 0, partial-sum slot (factor), 0, 0}: a task is
+ *                     64 rows, two per lane; within a round the tasks are sorted heaviest first
+ *             rounds  n_rounds x 4 int32 {first task, end task, first item, end item}: at most 64 items and 256 slots
+ *             items   (n_quad + n_soc) x 8 words {first factor row, kind 2 quadratic / 3 cone, index in its family,
+ *                     first slot, slots, float A of a cone, first header row, 0}, quadratics first
  *             NT      [n][k32] = N' and Nrow [k][np] = N (both absent when N is the identity)
  *           The LIN/QUAD/SOC sections are still present (np = n rounded up to 4); TC is empty (tc_panels = 0).
  *   LMINEG  -F_0 .. -F_k laid out like LMI ([a][row][lane][slot]): lambda_max(sum_a (y,1)_a (-F_a)) = -lambda_min(F(y))
