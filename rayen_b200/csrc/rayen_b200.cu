@@ -382,6 +382,8 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
                         p->lmi_tc_grad_smem_bytes);
     }
   }
+  // the violation checker keeps one y row per warp in shared memory: large ambient dimensions need the opt-in limit
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(viol_lqs_kernel), p->max_smem_optin);
   cudaSetDevice(prev);
   if (rc != 0) {
     cudaFree(p->d_blob);

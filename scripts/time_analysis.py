@@ -1,0 +1,106 @@
+"""The reference's own timing sweep (examples/scripts/time_analysis.py:57-190: seconds per sample of one forward call on
+2000 samples, per family, over dimension and constraint count) on this library, for the sizes it covers (n <= 4096;
+LMI needs n <= 32 and is not part of this sweep).  Same random generators as the reference script.  Next to each point:
+the oracle port on the host cores (float64 like the reference script) when its cost is small enough, the maximum
+violation of the outputs (GPU metric) and the agreement with the float64 oracle on 16 samples.
+
+usage: python scripts/time_analysis.py [--budget-s 200] [--out gpurun_out/time_analysis.json]"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import bench as B
+from oracle.rayen_oracle import OracleSet, TorchOracle
+from rayen_b200 import constraints
+from rayen_b200.constraint_module import ConstraintModule
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--budget-s", type=float, default=200.0)
+ap.add_argument("--out", default="gpurun_out/time_analysis.json")
+ap.add_argument("--cpu-flop-limit", type=float, default=3e10)
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+NUM = 2000
+rng = np.random.default_rng(0)
+
+
+def linear_set(r, k):
+    A1 = rng.uniform(-1.0, 1.0, size=(r, k))
+    b1 = rng.uniform(0.1, 1.0, size=(r, 1))
+    lc = constraints.LinearConstraint(A1=A1, b1=b1, A2=None, b2=None)
+    return constraints.ConvexConstraints(lc=lc, qcs=[], socs=[], lmic=None, y0=np.zeros((k, 1)), do_preprocessing_linear=False)
+
+
+def qp_set(eta, k):
+    qcs = []
+    for _ in range(eta):
+        tmp = rng.uniform(-1.0, 1.0, size=(k, k))
+        qcs.append(constraints.ConvexQuadraticConstraint(P=tmp @ tmp.T, q=rng.uniform(-1.0, 1.0, size=(k, 1)),
+                                                         r=rng.uniform(-1.0, 0.0, size=(1, 1)), do_checks_P=False))
+    return constraints.ConvexConstraints(lc=None, qcs=qcs, socs=[], lmic=None, y0=np.zeros((k, 1)))
+
+
+def soc_set(r_M, mu, k):
+    socs = []
+    for _ in range(mu):
+        s = rng.uniform(-1.0, 1.0, size=(r_M, 1))
+        socs.append(constraints.SOCConstraint(rng.uniform(-1.0, 1.0, size=(r_M, k)), s, rng.uniform(-1.0, 1.0, size=(k, 1)),
+                                              np.linalg.norm(s) + np.array([[0.5]])))
+    return constraints.ConvexConstraints(lc=None, qcs=[], socs=socs, lmic=None, y0=np.zeros((k, 1)))
+
+
+points = []
+for r in (1, 10, 100, 500, 1000, 2000, 3000):
+    for k in (1, 10, 100, 1000, 2000, 3000, 4000):
+        points.append(("linear", dict(r_A1=r, k=k), lambda r=r, k=k: linear_set(r, k), 2.0 * r * k, r * k))
+for eta in (1, 10, 50):
+    for k in (1, 10, 100, 300, 500, 1000):
+        if eta * k * k <= 50 * 500 * 500:
+            points.append(("qp", dict(eta=eta, k=k), lambda eta=eta, k=k: qp_set(eta, k), 6.0 * eta * k * k, 40 * eta * k * k))
+for r_M, mu in ((10, 10), (100, 10), (100, 100)):
+    for k in (10, 100, 500):
+        points.append(("soc", dict(r_M=r_M, mu=mu, k=k), lambda r_M=r_M, mu=mu, k=k: soc_set(r_M, mu, k),
+                       mu * (4.0 * r_M * k + 6.0 * k * k), 40 * mu * k * k + mu * r_M * k))
+points.sort(key=lambda p: p[4])          # cheapest host-side packing first
+
+t_start = time.time()
+out, skipped = [], []
+for fam, params, make, flop_per_sample, _ in points:
+    if time.time() - t_start > args.budget_s:
+        skipped.append(dict(family=fam, **params))
+        continue
+    t0 = time.time()
+    cs = make()
+    layer = ConstraintModule(cs, create_map=False).to(dev)
+    db = B.DeviceBench(layer, NUM, dev, pool=2)
+    host_s = time.time() - t0
+    db.want_grad = 0
+    fwd = db.time_loop(lambda i: db.forward(db.sets[i % 2]), 10, 3)
+    db.want_grad = 1
+    step = db.time_loop(db.step, 10, 3)
+    s0 = db.sets[0]
+    viol = float(layer.violation(s0["y"]).max())
+    oset = OracleSet.from_constraints(cs)
+    orc = TorchOracle(oset, torch.float64)
+    sub = s0["v"][:16].cpu().double()
+    y_ref = orc.forward(sub.unsqueeze(2))[:, :, 0] if hasattr(orc, "forward") else None
+    err = float((s0["y"][:16].cpu().double() - y_ref).abs().max() / max(float(y_ref.abs().max()), 1e-30))
+    rec = dict(family=fam, **params, n=int(cs.n), wide=int(layer._packed.fields["wide"]), fwd_us=round(fwd * 1e3, 2),
+               fwd_s_per_sample=fwd * 1e-3 / NUM, fwd_bwd_us=round(step * 1e3, 2), max_violation=viol, rel_err_y_vs_oracle=err,
+               host_setup_s=round(host_s, 2))
+    if flop_per_sample * NUM <= args.cpu_flop_limit:
+        v64 = s0["v"].cpu().double().unsqueeze(2)
+        with torch.no_grad():
+            orc.forward(v64[:64])
+            t1 = time.perf_counter()
+            orc.forward(v64)
+            rec["cpu_port_s_per_sample"] = (time.perf_counter() - t1) / NUM
+        rec["cpu_threads"] = torch.get_num_threads()
+    print(json.dumps(rec), flush=True)
+    out.append(rec)
+    del db, layer
+    torch.cuda.empty_cache()
+os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+json.dump(dict(num_samples=NUM, points=out, skipped_for_time=skipped,
+               not_covered="linear k in {5000, 10000} (n > 4096); the LMI sweep (r_F >= 10 with k >= 100: an LMI needs n <= 32 here)"),
+          open(args.out, "w"), indent=1)
