@@ -594,6 +594,9 @@ WIDE_CASES = [
     (64, 90, 9, 10, 30, 2, 1, "RAYEN"),          # more items than warps, a single sample
     (40, 50, 2, 2, 20, 0, 100, "RAYEN_old"),
     (48, 60, 1, 1, 16, 3, 33, "RAYEN_old"),
+    (34, 10, 40, 40, 3, 0, 50, "RAYEN"),         # 80 items: two rounds of the slot scratch
+    (4096, 40, 0, 0, 0, 0, 20, "RAYEN"),         # the widest set the kernels take
+    (600, 100, 1, 1, 20, 0, 12, "RAYEN"),        # n >= 512: the 256-thread backward
 ]
 
 

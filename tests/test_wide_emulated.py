@@ -82,6 +82,7 @@ CASES = [
     (70, 300, 0, 0, 0, 0, 16, "RAYEN"),          # several linear tasks per warp
     (36, 40, 9, 10, 12, 2, 3, "RAYEN"),          # more items than warps
     (34, 10, 40, 40, 3, 0, 11, "RAYEN"),         # 80 items: two rounds
+    (4096, 40, 0, 0, 0, 0, 5, "RAYEN"),          # the widest set the kernels take
     (40, 50, 2, 2, 20, 0, 21, "RAYEN_old"),
     (45, 30, 1, 1, 16, 3, 10, "RAYEN_old"),
 ]
@@ -90,6 +91,8 @@ CASES = [
 @pytest.mark.parametrize("ts", [8, 16])
 @pytest.mark.parametrize("k,m,eta,mu,r_M,eq,batch,method", CASES)
 def test_wide_kernels_under_the_emulator_match_the_oracle(emu, k, m, eta, mu, r_M, eq, batch, method, ts):
+    if k == 4096 and ts == 16:
+        pytest.skip("tiles of 16 samples of a 4096-dimensional set exceed the shared memory of an SM (the launcher uses 8)")
     spec = synthetic.wide_spec(k, m, eta, mu, r_M, eq, seed=k + batch)
     cs = synthetic.build_constraints(spec)
     p = plan.build_plan_from_constraints(cs)
