@@ -667,3 +667,14 @@ def test_wide_module_with_mapper_trains():
     y.square().sum().backward()
     assert layer.mapper.weight.grad is not None and torch.isfinite(layer.mapper.weight.grad).all()
     assert float(layer.mapper.weight.grad.abs().max()) > 0
+
+
+def test_wide_host_buffer_path_matches_device_path():
+    """The pinned-host-buffer step (copy-in, wide kernels, copy-out) gives the device path's result bit for bit:
+    a sample's arithmetic does not depend on which tile or chunk it falls into."""
+    cs = synthetic.build_constraints(synthetic.wide_spec(72, 150, 2, 2, 30, 4, seed=8))
+    v, gy = synthetic.sample_inputs(3001, cs.n, cs.k, seed_v=5)
+    layer, y, gv = run_layer(cs, v, gy)
+    yh, gvh = layer.forward_backward_host(v.pin_memory(), gy.pin_memory(), device=DEV)
+    np.testing.assert_array_equal(yh.numpy(), y.astype(np.float32))
+    np.testing.assert_array_equal(gvh.numpy(), gv.astype(np.float32))
