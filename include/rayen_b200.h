@@ -91,7 +91,8 @@ extern "C" {
  *             items   (n_quad + n_soc) x 8 words {first factor row, kind 2 quadratic / 3 cone, index in its family,
  *                     first slot, slots, float A of a cone, first header row, 0}, quadratics first
  *             NT      [n][k32] = N' and Nrow [k][np] = N (both absent when N is the identity)
- *           The LIN/QUAD/SOC sections are still present (np = n rounded up to 4); TC is empty (tc_panels = 0).
+ *           The LIN/QUAD/SOC/NMAT/BOUND sections are empty placeholders (np = n rounded up to 4) and TC has no
+ *           panels (tc_panels = 0): a wide plan is WIDE + Y0 + VIOL.
  *   LMINEG  -F_0 .. -F_k laid out like LMI ([a][row][lane][slot]): lambda_max(sum_a (y,1)_a (-F_a)) = -lambda_min(F(y))
  */
 typedef struct RayenPlanDesc {

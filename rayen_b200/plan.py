@@ -179,8 +179,9 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
     Dp = np.zeros((m_pad, np_))
     Dp[:m, :n] = D
     lin_stride = 4 * np_ + 4
-    lin = np.zeros((m_pad // 4, lin_stride))
-    for c in range(m_pad // 4):
+    # (wide plans keep their constants in the WIDE section only: the register-layout sections below stay empty)
+    lin = np.zeros((m_pad // 4, lin_stride)) if not wide else np.zeros(4)
+    for c in range(m_pad // 4 if not wide else 0):
         # [kk][i][e] = D[4c+i][4kk+e]
         blockv = Dp[4 * c:4 * c + 4, :].reshape(4, np_ // 4, 4).transpose(1, 0, 2)
         lin[c, :4 * np_] = blockv.reshape(-1)
@@ -189,7 +190,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
     # ---- quadratic constraints (reference constraint_module.py:99-122)
     tri_words = packed_triangular_words(np_)
     quad_stride = _bank_stride(np_ + tri_words)
-    quad = np.zeros((max(len(qcs), 1), quad_stride))
+    quad = np.zeros((max(len(qcs), 1), quad_stride)) if not wide else None
     quad_f64 = []
     for i, (P, q, r) in enumerate(qcs):
         P, q, r = f64(P), f64(q).reshape(-1, 1), float(np.asarray(r).reshape(-1)[0])
@@ -203,14 +204,15 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
         phi_z = (N.T @ phi)[:, 0]
         Delta_z = N.T @ Delta @ N
         G = _triangular_factor(Delta_z, np_)
-        quad[i, :n] = phi_z
-        quad[i, np_:np_ + tri_words] = _pack_triangular(G)
+        if not wide:
+            quad[i, :n] = phi_z
+            quad[i, np_:np_ + tri_words] = _pack_triangular(G)
         quad_f64.append((phi_z, Delta_z, G))
-    off_quad = add(quad) if len(qcs) else add(np.zeros(4))
+    off_quad = add(quad) if len(qcs) and not wide else add(np.zeros(4))
 
     # ---- second-order cones (reference constraint_module.py:383-399)
     soc_stride = _bank_stride(2 * np_ + tri_words + 4)
-    soc = np.zeros((max(len(socs), 1), soc_stride))
+    soc = np.zeros((max(len(socs), 1), soc_stride)) if not wide else None
     soc_f64 = []
     for j, (M, s, c, d) in enumerate(socs):
         M, s, c, d = f64(M), f64(s).reshape(-1, 1), f64(c).reshape(-1, 1), float(np.asarray(d).reshape(-1)[0])
@@ -223,12 +225,13 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
         cz = (N.T @ c)[:, 0]
         h = (Mz.T @ beta)[:, 0] - tau * cz
         R = _triangular_factor(Mz.T @ Mz, np_)
-        soc[j, :n] = cz
-        soc[j, np_:np_ + n] = h
-        soc[j, 2 * np_:2 * np_ + tri_words] = _pack_triangular(R)
-        soc[j, 2 * np_ + tri_words] = A
+        if not wide:
+            soc[j, :n] = cz
+            soc[j, np_:np_ + n] = h
+            soc[j, 2 * np_:2 * np_ + tri_words] = _pack_triangular(R)
+            soc[j, 2 * np_ + tri_words] = A
         soc_f64.append((cz, h, Mz, A, R))
-    off_soc = add(soc) if len(socs) else add(np.zeros(4))
+    off_soc = add(soc) if len(socs) and not wide else add(np.zeros(4))
 
     # ---- LMI (reference constraint_module.py:43-52 and :412-421, congruence folded into the constants)
     lmi_r = lmi_rp = 0
@@ -257,7 +260,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
     n_is_identity = int(k == n and np.array_equal(N, np.eye(k)))
     nm = np.zeros((k, np_ + 4))
     nm[:, :n] = N
-    off_nmat = add(nm) if not n_is_identity else add(np.zeros(4))
+    off_nmat = add(nm) if not (n_is_identity or wide) else add(np.zeros(4))
     y0p = np.zeros(k_pad)
     y0p[:k] = y0[:, 0]
     off_y0 = add(y0p)
@@ -265,7 +268,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
     # ---- pruning bound of the LMI: lambda_max(S) <= tr(S)/r + sqrt((r-1)/r) sqrt(|S|_F^2 - tr(S)^2/r)
     # (Wolkowicz-Styan), with tr(S~(u)) = t.u and |S~(u)|_F = |T u|, T'T = [tr(F~z_a F~z_b)]_ab.  Lets the
     # linear/quadratic/SOC kernel prove, for most samples, that the LMI cannot be the binding constraint.
-    bound = np.zeros(np_ + tri_words + 4)
+    bound = np.zeros(np_ + tri_words + 4) if not wide else np.zeros(4)
     if lmi is not None:
         bound[:n] = np.trace(Fz, axis1=1, axis2=2)
         gram = np.einsum("aij,bij->ab", Fz, Fz)
@@ -504,11 +507,13 @@ def build_plan_from_constraints(cs):
 # --------------------------------------------------------------------------- numpy model of the kernels
 def evaluate_plan_numpy(plan, v):
     """Float64 evaluation of kappa and y straight from the PACKED blob (not from the original matrices).
+    Narrow plans (n <= 32) only: wide plans are decoded by ``evaluate_wide_numpy``.
 
     Host-side self-check of the packer: it decodes the same words the kernels decode, so a layout bug
     shows up on the CPU.  Not a fallback -- nothing in the product path calls it.
     """
     f = plan.fields
+    assert not f.get("wide"), "wide plans carry only the WIDE section: use evaluate_wide_numpy"
     blob = plan.blob.astype(np.float64)
     n, k, np_ = f["n"], f["k"], f["np"]
     v = np.asarray(v, dtype=np.float64).reshape(-1, n)

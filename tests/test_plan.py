@@ -146,7 +146,7 @@ def test_tensor_core_sections_decode_to_the_fp32_sections(cfg):
                                                (65, 0, 1, 1, 5, 0), (33, 7, 0, 0, 0, 0)])
 def test_wide_plan_decodes_to_the_oracle(k, m, eta, mu, r_M, eq):
     """n > 32: the WIDE section (transposed row matrix + warp tasks), decoded the way wide_forward_kernel walks it, gives
-    the oracle's kappa, binding constraint and y; tasks tile the rows; the LIN/QUAD/SOC sections agree with it."""
+    the oracle's kappa, binding constraint and y; tasks tile the rows."""
     spec = synthetic.wide_spec(k, m, eta, mu, r_M, eq, seed=k)
     cs = synthetic.build_constraints(spec)
     p = plan.build_plan_from_constraints(cs)
@@ -181,8 +181,11 @@ def test_wide_plan_decodes_to_the_oracle(k, m, eta, mu, r_M, eq):
     assert ((act >> 24)[ok] == cf["family"][ok]).all()
     ok &= cf["family"] != 0                       # kappa = 0: no binding constraint, the index means nothing
     assert ((act & 0xFFFFFF)[ok] == cf["index"][ok]).all()
-    y2, kap2, act2 = plan.evaluate_plan_numpy(p, v.numpy())
-    assert np.abs(y2 - y).max() <= 1e-9 and (act2[ok] == act[ok]).all()
+    # the register-layout sections stay empty for a wide plan: the block is the WIDE section + N + the checker's rows
+    k4 = (cs.k + 3) // 4 * 4
+    viol_words = (m + 2 * eq + 1) * (k4 + 4) + eta * (k4 * k4 + k4 + 4) + mu * (4 + k4 + r_M * (k4 + 4))
+    n_words = 0 if f["n_is_identity"] else cs.n * (cs.k + 32) + cs.k * f["np"]
+    assert p.blob.size <= cs.n * r_pad + viol_words + n_words + 8 * n_tasks + 8 * (eta + mu) + 2048
 
 
 def test_narrow_plans_are_not_wide():
