@@ -105,6 +105,28 @@ def test_state_dict_round_trip_repacks_the_plan():
     np.testing.assert_allclose(b._packed.blob, a._packed.blob, rtol=2e-5, atol=2e-6)  # rebuilt from fp32 buffers
 
 
+def test_wide_module_state_dict_round_trip_and_wide_descriptor():
+    """A set with n > 32: same buffers as the reference, a wide plan (descriptor flag + WIDE section), and a reload from
+    the float32 buffers of another module rebuilds a plan that maps the same inputs to the same outputs."""
+    from rayen_b200 import plan as plan_mod
+    cs_a = synthetic.build_constraints(synthetic.wide_spec(40, 30, 1, 1, 12, 2, seed=1))
+    cs_b = synthetic.build_constraints(synthetic.wide_spec(40, 30, 1, 1, 12, 2, seed=2))
+    a, b = ConstraintModule(cs_a, create_map=False), ConstraintModule(cs_b, create_map=False)
+    assert (a.k, a.n) == (40, 38) and a.D.shape == (cs_a.A_p.shape[0], 38) and a.all_delta.shape == (1, 40, 40)
+    desc = a._packed.desc()
+    assert desc.wide == 1 and desc.off_wide > 0 and desc.np == 40 and desc.tc_panels == 0 and desc.lmi_r == 0
+    v = np.random.default_rng(0).uniform(-2, 2, size=(32, 38))
+    ya, ka, ta = plan_mod.evaluate_wide_numpy(a._packed, v)
+    yb, _, _ = plan_mod.evaluate_wide_numpy(b._packed, v)
+    assert np.abs(ya - yb).max() > 1e-3
+    b.load_state_dict(a.state_dict())
+    yb, kb, tb = plan_mod.evaluate_wide_numpy(b._packed, v)
+    np.testing.assert_allclose(yb, ya, rtol=0, atol=2e-5 * np.abs(ya).max())
+    assert (tb == ta).mean() > 0.9
+    with pytest.raises(RuntimeError, match="CUDA"):
+        a(torch.randn(4, 38, 1))
+
+
 def test_product_package_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "rayen_b200")
     for dirpath, _, files in os.walk(pkg):
