@@ -47,7 +47,7 @@ def _ptr(a, t=_F):
     return a.ctypes.data_as(t)
 
 
-def run_emulated(lib, p, v, gy, mode, ts=8, grid_f=3, grid_b=5):
+def run_emulated(lib, p, v, gy, mode, ts=8, grid_f=3, grid_b=5, bthreads=None):
     f = p.fields
     n, k = f["n"], f["k"]
     v = np.ascontiguousarray(v, dtype=np.float32)
@@ -62,7 +62,7 @@ def run_emulated(lib, p, v, gy, mode, ts=8, grid_f=3, grid_b=5):
                               _ptr(kap), _ptr(act, _I), B, mode, grid_f, ts)
     assert rc == 0
     rc = lib.emu_wide_backward(_ptr(blob), f["off_wide"], n, k, f["off_y0"], f["n_is_identity"], _ptr(v), cols, _ptr(gy),
-                               _ptr(kap), _ptr(act, _I), _ptr(gv), cols, B, mode, grid_b, 128 if ts == 8 else 256)
+                               _ptr(kap), _ptr(act, _I), _ptr(gv), cols, B, mode, grid_b, bthreads or (128 if ts == 8 else 256))
     assert rc == 0
     return y.astype(np.float64), kap, act, gv.astype(np.float64)
 
@@ -121,3 +121,61 @@ def test_wide_kernels_under_the_emulator_match_the_oracle(emu, k, m, eta, mu, r_
     if batch > 4 and not old:
         np.testing.assert_allclose(y[2], cs.y0[:, 0], atol=1e-6)
         assert np.all(gv[2] == 0)
+
+
+# ----------------------------------------------------------------------------- ThreadSanitizer: the CPU racecheck
+@pytest.fixture(scope="module")
+def tsan_driver(tmp_path_factory):
+    out = tmp_path_factory.mktemp("wide_tsan")
+    src = open(os.path.join(_cabi.CSRC, "wide.cuh")).read().splitlines(True)
+    kept = [l for l in src if l.strip() not in ('#include "common.cuh"', '#include "lqs.cuh"')]
+    with open(out / "wide_stripped.cuh", "w") as fh:
+        fh.writelines(kept)
+    exe = str(out / "wide_emu_tsan")
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-pthread", "-w", f"-I{out}", f"-I{os.path.join(HERE, 'emu')}",
+           "-o", exe, os.path.join(HERE, "emu", "wide_emu_main.cpp")]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0 and "tsan" in (proc.stderr or "").lower():
+        pytest.skip("ThreadSanitizer runtime not available: " + proc.stderr[-200:])
+    assert proc.returncode == 0, proc.stderr
+    return exe, out
+
+
+@pytest.mark.parametrize("k,m,eta,mu,r_M,eq,batch,method,ts,bthreads", [
+    (45, 70, 3, 2, 50, 3, 19, "RAYEN", 8, 128),
+    (40, 50, 2, 2, 20, 0, 21, "RAYEN_old", 16, 256),
+    (34, 10, 40, 40, 3, 0, 9, "RAYEN", 16, 128),      # two rounds: the slot scratch is reused
+])
+def test_wide_kernels_have_no_data_race_under_thread_sanitizer(emu, tsan_driver, k, m, eta, mu, r_M, eq, batch, method, ts, bthreads):
+    """The kernels' barrier structure, checked like compute-sanitizer's racecheck would: under the emulator every CUDA
+    thread is an OS thread, shared memory is ordinary memory, __syncthreads/__syncwarp are barriers -- so a missing
+    barrier in wide.cuh is a data race that ThreadSanitizer reports.  Several tiles / samples per block (grid-stride)
+    exercise the reuse of the shared-memory buffers.  Outputs must equal the plain emulated build's, bit for bit."""
+    exe, out = tsan_driver
+    cs = synthetic.build_constraints(synthetic.wide_spec(k, m, eta, mu, r_M, eq, seed=k + batch))
+    p = plan.build_plan_from_constraints(cs)
+    f = p.fields
+    old = method == "RAYEN_old"
+    mode = _cabi.MODE_RAYEN_OLD if old else _cabi.MODE_RAYEN
+    v, gy = synthetic.sample_inputs(batch, cs.n + (1 if old else 0), cs.k, seed_v=batch, seed_g=k)
+    v32, gy32 = np.ascontiguousarray(v.numpy(), dtype=np.float32), np.ascontiguousarray(gy.numpy(), dtype=np.float32)
+    B, cols = v32.shape
+    hdr = np.asarray([f["n"], f["k"], f["off_y0"], f["n_is_identity"], f["off_wide"], p.blob.size, B, cols, mode, ts, bthreads,
+                      2, 3, 0, 0, 0], dtype=np.int64)
+    fin, fout = str(out / f"in_{k}_{batch}.bin"), str(out / f"out_{k}_{batch}.bin")
+    with open(fin, "wb") as fh:
+        fh.write(hdr.tobytes()); fh.write(p.blob.tobytes()); fh.write(v32.tobytes()); fh.write(gy32.tobytes())
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0")
+    proc = subprocess.run([exe, fin, fout], capture_output=True, text=True, env=env, timeout=900)
+    assert "ThreadSanitizer" not in proc.stderr, proc.stderr[:3000]
+    assert proc.returncode == 0, (proc.returncode, proc.stderr[:500])
+    raw = np.fromfile(fout, dtype=np.float32)
+    y = raw[:B * cs.k].reshape(B, cs.k)
+    kap = raw[B * cs.k:B * cs.k + B]
+    act = raw[B * cs.k + B:B * cs.k + 2 * B].view(np.int32)
+    gv = raw[B * cs.k + 2 * B:].reshape(B, cols)
+    y2, kap2, act2, gv2 = run_emulated(emu, p, v32, gy32, mode, ts=ts, grid_f=2, grid_b=3, bthreads=bthreads)
+    np.testing.assert_array_equal(y.astype(np.float64), y2)
+    np.testing.assert_array_equal(kap, kap2)
+    np.testing.assert_array_equal(act, act2)
+    np.testing.assert_array_equal(gv.astype(np.float64), gv2)
