@@ -124,19 +124,22 @@ def test_wide_kernels_under_the_emulator_match_the_oracle(emu, k, m, eta, mu, r_
 
 
 # ----------------------------------------------------------------------------- ThreadSanitizer: the CPU racecheck
-@pytest.fixture(scope="module")
-def tsan_driver(tmp_path_factory):
-    out = tmp_path_factory.mktemp("wide_tsan")
+@pytest.fixture(scope="module", params=["thread", "address"])
+def tsan_driver(request, tmp_path_factory):
+    """The stand-alone emulated build under ThreadSanitizer (the racecheck) or AddressSanitizer + UBSan (a memcheck of the
+    global-memory side: the constant block, v, g_y, y, kappa, active, g_v are exact-size heap buffers)."""
+    out = tmp_path_factory.mktemp("wide_" + request.param)
     src = open(os.path.join(_cabi.CSRC, "wide.cuh")).read().splitlines(True)
     kept = [l for l in src if l.strip() not in ('#include "common.cuh"', '#include "lqs.cuh"')]
     with open(out / "wide_stripped.cuh", "w") as fh:
         fh.writelines(kept)
-    exe = str(out / "wide_emu_tsan")
-    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-pthread", "-w", f"-I{out}", f"-I{os.path.join(HERE, 'emu')}",
+    exe = str(out / "wide_emu_san")
+    flag = "-fsanitize=thread" if request.param == "thread" else "-fsanitize=address,undefined"
+    cmd = ["g++", "-std=c++20", "-O1", "-g", flag, "-pthread", "-w", f"-I{out}", f"-I{os.path.join(HERE, 'emu')}",
            "-o", exe, os.path.join(HERE, "emu", "wide_emu_main.cpp")]
     proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0 and "tsan" in (proc.stderr or "").lower():
-        pytest.skip("ThreadSanitizer runtime not available: " + proc.stderr[-200:])
+    if proc.returncode != 0 and "san" in (proc.stderr or "").lower() and "cannot find" in (proc.stderr or "").lower():
+        pytest.skip("sanitizer runtime not available: " + proc.stderr[-200:])
     assert proc.returncode == 0, proc.stderr
     return exe, out
 
@@ -146,7 +149,7 @@ def tsan_driver(tmp_path_factory):
     (40, 50, 2, 2, 20, 0, 21, "RAYEN_old", 16, 256),
     (34, 10, 40, 40, 3, 0, 9, "RAYEN", 16, 128),      # two rounds: the slot scratch is reused
 ])
-def test_wide_kernels_have_no_data_race_under_thread_sanitizer(emu, tsan_driver, k, m, eta, mu, r_M, eq, batch, method, ts, bthreads):
+def test_wide_kernels_are_clean_under_thread_and_address_sanitizer(emu, tsan_driver, k, m, eta, mu, r_M, eq, batch, method, ts, bthreads):
     """The kernels' barrier structure, checked like compute-sanitizer's racecheck would: under the emulator every CUDA
     thread is an OS thread, shared memory is ordinary memory, __syncthreads/__syncwarp are barriers -- so a missing
     barrier in wide.cuh is a data race that ThreadSanitizer reports.  Several tiles / samples per block (grid-stride)
@@ -165,9 +168,9 @@ def test_wide_kernels_have_no_data_race_under_thread_sanitizer(emu, tsan_driver,
     fin, fout = str(out / f"in_{k}_{batch}.bin"), str(out / f"out_{k}_{batch}.bin")
     with open(fin, "wb") as fh:
         fh.write(hdr.tobytes()); fh.write(p.blob.tobytes()); fh.write(v32.tobytes()); fh.write(gy32.tobytes())
-    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0")
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0", ASAN_OPTIONS="detect_leaks=0")
     proc = subprocess.run([exe, fin, fout], capture_output=True, text=True, env=env, timeout=900)
-    assert "ThreadSanitizer" not in proc.stderr, proc.stderr[:3000]
+    assert "Sanitizer" not in proc.stderr and "runtime error" not in proc.stderr, proc.stderr[:3000]
     assert proc.returncode == 0, (proc.returncode, proc.stderr[:500])
     raw = np.fromfile(fout, dtype=np.float32)
     y = raw[:B * cs.k].reshape(B, cs.k)
