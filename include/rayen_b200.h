@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RAYEN_ABI_VERSION 12
+#define RAYEN_ABI_VERSION 13
 
 /* error codes (negative); positive return values are cudaError_t */
 #define RAYEN_OK 0
@@ -59,9 +59,12 @@ extern "C" {
  *           triangular factor R (R'R = M_z' M_z) packed like G, then {A = tau^2 - beta'beta, 0,0,0}
  *   NMAT    k rows of N (= NA_E), row stride np+4 (absent when N is the identity)
  *   Y0      y0 = N z0 + yp, k_pad words
- *   BOUND   (plans with an LMI) t[np] (t_a = tr F~z_a), the packed triangular factor T of the Gram matrix
- *           [tr(F~z_a F~z_b)]_ab, then {r, 0, 0, 0}: the Wolkowicz-Styan bound
- *           lambda_max(S~(u)) <= t.u/r + sqrt((r-1)/r) sqrt(|T u|^2 - (t.u)^2/r) that prunes the eigen-solve
+ *   BOUND   (plans with an LMI) t[np] (t_a = tr F~z_a), the packed triangular factor T_c of the CENTRED Gram matrix
+ *           [tr(F~z_a F~z_b) - tr F~z_a tr F~z_b / r]_ab, then {r, margin, 0, 0}: the Wolkowicz-Styan bound
+ *           lambda_max(S~(u)) <= t.u/r + sqrt((r-1)/r) |T_c u| that prunes the eigen-solve.  |T_c u|^2 is the squared
+ *           Frobenius norm of the trace-free part of S~(u) as a sum of squares (no float32 cancellation); a sample is
+ *           pruned only if bound + margin + 1e-5 |bound| < kappa of the other families, margin = lmi_bound_margin
+ *           covering the rounding of the two dot products
  *   LMI     F~z_a = sum_i N[i][a] * (-L' F_i L), a < n, each rp x rp (rp = r rounded up to 4, 8, 16
  *           or 32, zero padded), stored [a][row i][lane q][slot t] with column j = q + (rp/4)*t
  *   TC      the LIN/QUAD/SOC/BOUND constants again as the B operand of a tcgen05 GEMM (lqs_tc.cuh): a table
@@ -118,6 +121,7 @@ typedef struct RayenPlanDesc {
   int32_t viol_eq;   /* equality rows of the VIOL section */
   int32_t lmitc_panels; /* 128-entry panels of the LMITC section (0: none) */
   int32_t wide;         /* 1: n > 32 -- np is n rounded up to 4, the kernels of wide.cuh read the WIDE section */
+  float lmi_bound_margin; /* absolute float32-rounding allowance added to the pruning bound (see BOUND) */
   int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi, off_tc, off_viol, off_lmineg, off_lmitc;
   int64_t off_wide;     /* WIDE section (0 when wide == 0) */
   int64_t blob_words;
@@ -139,7 +143,8 @@ void rayen_plan_destroy(rayen_plan_t* plan);
 int rayen_plan_set_tuning(rayen_plan_t* plan, int samples_per_thread, int lanes_per_sample);
 /* LMI pruning on (1, default) / off (0): with pruning the eigen-solve only runs for the samples whose
  * Wolkowicz-Styan bound does not already prove kappa_LMI < kappa of the other families.  Results are
- * identical either way (the bound is a proof, not an approximation). */
+ * identical either way: the bound is evaluated in a cancellation-free form with an explicit allowance for its
+ * float32 rounding (see BOUND above), so a pruned sample's LMI cannot bind. */
 int rayen_plan_set_pruning(rayen_plan_t* plan, int enabled);
 /* Linear/quadratic/SOC forward on the tensor cores (tcgen05 3xTF32 GEMM, default) or on the FP32 pipe (0). */
 int rayen_plan_set_tensor_cores(rayen_plan_t* plan, int enabled);

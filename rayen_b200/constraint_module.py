@@ -85,7 +85,7 @@ class _RayShoot(torch.autograd.Function):
                 torch.cuda.set_device(prev)
         if rc != 0:
             _cabi.check(rc, "rayen_forward_f32")
-        ctx.module, ctx.in_dtype, ctx.aux, ctx.have_dkappa = module, q.dtype, aux, want_grad
+        ctx.module, ctx.in_dtype, ctx.aux, ctx.have_dkappa, ctx.state = module, q.dtype, aux, want_grad, st
         ctx.save_for_backward(v)
         module._last_aux = (aux, B)
         return y if q.dtype == torch.float32 else y.to(q.dtype)
@@ -101,7 +101,7 @@ class _RayShoot(torch.autograd.Function):
             gy = gy.contiguous()
         B, cols = v.shape
         device = v.device
-        st = module._launch_state(device)
+        st = ctx.state   # the plan the forward ran on (a load_state_dict in between builds new plans)
         gv = torch.empty((B, cols), dtype=torch.float32, device=device)
         base = aux.data_ptr()
         switch = torch.cuda.current_device() != st.index
@@ -144,7 +144,7 @@ class _MappedRayShoot(torch.autograd.Function):
                                    torch.cuda.current_stream(device).cuda_stream)
         if rc != 0:
             _cabi.check(rc, "rayen_forward_mapped_f32")
-        ctx.module, ctx.aux, ctx.have_dkappa, ctx.has_bias = module, aux, want_grad, bias is not None
+        ctx.module, ctx.aux, ctx.have_dkappa, ctx.has_bias, ctx.state = module, aux, want_grad, bias is not None, st
         ctx.save_for_backward(x, weight, q)
         module._last_aux = (aux, B)
         return y
@@ -160,7 +160,7 @@ class _MappedRayShoot(torch.autograd.Function):
             gy = gy.contiguous()
         B, n = q.shape
         device = q.device
-        st = module._launch_state(device)
+        st = ctx.state
         gq = torch.empty((B, n), dtype=torch.float32, device=device)
         base = aux.data_ptr()
         with torch.cuda.device(device):
@@ -287,12 +287,24 @@ class ConstraintModule(nn.Module):
             self._states[device] = st
         return st
 
+    _BUFFER_NAMES = ("D", "all_P", "all_q", "all_r", "all_M", "all_s", "all_c", "all_d", "all_F", "A_p", "b_p", "yp",
+                     "NA_E", "z0", "y0")
+
+    def _buffer_snapshot(self):
+        return {name: getattr(self, name).detach().cpu().clone() for name in self._BUFFER_NAMES}
+
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        before = self._buffer_snapshot()
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        after = self._buffer_snapshot()
+        # a state dict that carries this module's own constants (checkpoint / resume of the same set, EarlyStopping's
+        # reload) changes nothing: keep the plan packed from the float64 sources and the live device plans
+        if all(before[k].shape == after[k].shape and torch.equal(before[k], after[k]) for k in before):
+            return
         self._repack_from_buffers()
 
     def _repack_from_buffers(self):
-        """Rebuild the device plan from the registered buffers (after ``load_state_dict``)."""
+        """Rebuild the device plan from the registered buffers (after a ``load_state_dict`` that changed them)."""
         g = lambda name: getattr(self, name).detach().cpu().double().numpy()
         qcs = [(P, q, r) for P, q, r in zip(g("all_P"), g("all_q"), g("all_r"))] if self.all_P.numel() else []
         socs = [(M, s, c, d) for M, s, c, d in zip(g("all_M"), g("all_s"), g("all_c"), g("all_d"))] \
@@ -308,8 +320,9 @@ class ConstraintModule(nn.Module):
         self._packed = plan_mod.build_plan(g("A_p"), g("b_p"), g("NA_E"), g("yp"), g("z0"), qcs, socs, lmi,
                                            lin_rows=None)
         self._lqs_kernel_runs = bool(qcs or socs or np.any(g("D") != 0) or lmi is None)
-        for dev_plan in self._plans.values():
-            dev_plan.close()
+        # the old device plans are not destroyed here: an autograd context of a forward that has not run its backward
+        # yet keeps its own reference (ctx.state) and must find the plan its kappa / active / workspace belong to;
+        # DevicePlan.__del__ frees each plan with its last reference
         self._plans = {}
         self._states = {}
 
@@ -420,8 +433,14 @@ class ConstraintModule(nn.Module):
         """The mapper is folded into the forward kernel when the layout allows it (see rayen_forward_mapped_f32)."""
         m = self.mapper
         want = self.fuse_mapper if isinstance(self.fuse_mapper, bool) else x2d.shape[0] <= _FUSE_MAPPER_MAX_BATCH
+        # anything the kernel cannot take as it is (a width that is not the mapper's, tensors on different devices or of
+        # other dtypes, unaligned rows) goes through nn.Linear, which raises the usual shape / device errors
         return (want and isinstance(m, nn.Linear) and self._mode == _cabi.MODE_RAYEN and x2d.is_cuda
                 and x2d.dtype == torch.float32 and m.weight.dtype == torch.float32 and x2d.shape[0] > 0
+                and x2d.shape[1] == m.in_features and m.out_features == self.dim_after_map
+                and m.weight.device == x2d.device
+                and (m.bias is None or (m.bias.device == x2d.device and m.bias.dtype == torch.float32
+                                        and m.bias.is_contiguous()))
                 and x2d.shape[1] % 4 == 0 and x2d.stride(1) == 1 and x2d.stride(0) % 4 == 0
                 and x2d.data_ptr() % 16 == 0 and m.weight.is_contiguous() and m.weight.data_ptr() % 16 == 0
                 and self._lqs_kernel_runs and not self._packed.fields.get("wide"))

@@ -20,6 +20,7 @@ struct PlanDev {
   int off_tc, tc_panels, tc_kp;  // tensor-core section (see rayen_b200.h)
   int off_viol, off_lmineg, viol_in, viol_eq;  // violation checker sections
   int off_lmitc, lmitc_panels, lmitc_stages;   // LMI matrices as a tcgen05 B operand (lmi_tc.cuh); ring depth
+  float lmi_bound_margin;                      // float32-rounding allowance of the pruning bound (rayen_b200.h, BOUND)
 };
 
 // Fused mapper (reference constraint_module.py:261, :525: q = nn.Linear(input_dim, n)(x)): when x != nullptr the

@@ -108,6 +108,14 @@ __device__ __forceinline__ float soc_root(float A, float hb, float cq, float* ro
   return cq / den;
 }
 
+// Wolkowicz-Styan upper bound of lambda_max(S~(u)) = mean + radius (mean = tr S~/r, radius = sqrt((r-1)/r) times the
+// Frobenius norm of the trace-free part), plus what the float32 evaluation of its two dot products can be off by:
+// `margin` (absolute, from the plan: rayen_b200.h BOUND) and 1e-5 of the terms.  A sample is pruned iff this is below
+// the kappa of the other families; being conservative only costs time.
+__device__ __forceinline__ float lmi_upper_bound(float mean, float radius, float margin) {
+  return mean + radius + fmaf(1e-5f, fabsf(mean) + radius, margin);
+}
+
 template <int NP, int TM>
 __device__ __forceinline__ void kappa_lqs(const PlanDev& P, const float* __restrict__ cst,
                                           const float (&u)[TM][NP], int lane_l, int L, float (&best)[TM],
@@ -276,11 +284,9 @@ __global__ void __launch_bounds__(lqs_max_threads(NP, TM), 1)
       const float inv_r = 1.0f / r;
 #pragma unroll
       for (int t = 0; t < TM; ++t) {
-        const float mean = tu[t] * inv_r;
-        const float dev2 = fmaxf(fmaf(-tu[t], mean, nrm2[t]), 0.f);
-        const float ub = mean + sqrtf((r - 1.0f) * inv_r * dev2);
-        // safety margin for the float32 rounding of the bound; being conservative only costs time
-        pruned[t] = fmaf(1e-4f, fabsf(ub), ub) + 1e-30f < best[t];
+        // nrm2 = |T_c u|^2, T_c the factor of the CENTRED Gram matrix (a sum of squares: no cancellation)
+        const float ub = lmi_upper_bound(tu[t] * inv_r, sqrtf((r - 1.0f) * inv_r * nrm2[t]), P.lmi_bound_margin);
+        pruned[t] = ub < best[t];
       }
     }
 

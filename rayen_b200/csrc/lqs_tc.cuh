@@ -348,10 +348,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 tag = make_tag(RAYEN_FAM_SOC, idx);
               }
             } else {                               // Wolkowicz-Styan bound of lambda_max (LMI pruning)
+              // ss = |T_c u|^2 with T_c the factor of the CENTRED Gram matrix: the deviation term is a sum of
+              // squares, nothing cancels when S~(u) is close to a multiple of the identity
               const float inv_r = 1.0f / scal;
-              const float mean = h[0] * inv_r;
-              const float dev2 = fmaxf(fmaf(-h[0], mean, ss), 0.f);
-              ub = mean + sqrtf((scal - 1.0f) * inv_r * dev2);
+              ub = lmi_upper_bound(h[0] * inv_r, sqrtf((scal - 1.0f) * inv_r * ss), P.lmi_bound_margin);
             }
           }
         }
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
       }
       // ---- merge / prune / scale step for this thread's sample
-      const bool pruned = lmi_follows && prune && (fmaf(1e-4f, fabsf(ub), ub) + 1e-30f < best);
+      const bool pruned = lmi_follows && prune && (ub < best);  // ub already carries its rounding allowance
       const bool finish = !lmi_follows || pruned;
       {
         // samples the LMI kernel still has to look at: one atomicAdd per warp, not per sample

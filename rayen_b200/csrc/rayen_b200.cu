@@ -250,6 +250,8 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   if (d->off_y0 + d->k_pad > d->off_bound) return fail(RAYEN_ERR_BAD_ARGUMENT, "y0 section does not fit its slot");
   if (d->lmi_prune && d->off_bound + d->np + tri + 4 > d->off_lmi)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "bound section does not fit its slot");
+  if (d->lmi_prune && !(d->lmi_bound_margin >= 0.f))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "lmi_bound_margin must be >= 0");
   if (d->lmi_r > 0 && d->off_lmi + static_cast<int64_t>(d->n) * d->lmi_rp * d->lmi_rp > d->blob_words)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "LMI section does not fit the block");
   if (d->blob_words > (1ll << 30)) return fail(RAYEN_ERR_UNSUPPORTED, "constant block too large");
@@ -320,6 +322,7 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   v.off_viol = static_cast<int>(d->off_viol); v.off_lmineg = static_cast<int>(d->off_lmineg);
   v.viol_in = d->viol_in; v.viol_eq = d->viol_eq;
   v.off_lmitc = static_cast<int>(d->off_lmitc); v.lmitc_panels = d->lmitc_panels;
+  v.lmi_bound_margin = d->lmi_bound_margin;
 
   p->has_lqs = d->n_quad > 0 || d->n_soc > 0;
   for (int64_t i = d->off_lin; i < d->off_quad && !p->has_lqs; ++i) p->has_lqs = d->blob[i] != 0.0f;
@@ -768,6 +771,7 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
   const bool has_lmi = d.lmi_r > 0;
   if (has_lmi && (!kappa || !active))
     return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the kappa and active outputs");
+  if (has_lmi && !workspace) return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the workspace buffer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int prev = 0;
   RAYEN_CUDA(cudaGetDevice(&prev));
@@ -802,7 +806,6 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
     if (we != cudaSuccess) return cuda_fail(we, "forward launch (wide)");
     return RAYEN_OK;
   }
-  if (has_lmi && !workspace) return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the workspace buffer");
   int* counters = static_cast<int*>(workspace);
   int* fwd_list = has_lmi ? reinterpret_cast<int*>(static_cast<char*>(workspace) + 256) : nullptr;
   const bool run_lqs = p->has_lqs || !has_lmi;
@@ -883,6 +886,7 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
   if (ldv < need || ldgv < need)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "ldv=%lld / ldgv=%lld < %d", static_cast<long long>(ldv),
                 static_cast<long long>(ldgv), need);
+  if (d.lmi_r > 0 && !workspace) return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the workspace buffer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int prev = 0;
   RAYEN_CUDA(cudaGetDevice(&prev));
@@ -912,7 +916,6 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
   const long long cap = static_cast<long long>(p->sm_count) * 12;  // 12 blocks x 18 KB of tile memory per SM at n = 32
   if (grid > cap) grid = cap;
   const bool has_lmi = d.lmi_r > 0;
-  if (has_lmi && !workspace) return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the workspace buffer");
   int* counters = static_cast<int*>(workspace);
   int* bwd_list = has_lmi ? reinterpret_cast<int*>(static_cast<char*>(workspace) + 256 + ws_list_bytes(B)) : nullptr;
   cudaError_t e = cudaSuccess;
@@ -1065,11 +1068,18 @@ static int host_step(rayen_plan* p, const float* v_host, const float* gy_host, f
   cudaEvent_t* ev_g = p->host_ev[slot] + kHostMaxChunks;   // [c]     gy_c is on the device, later reused: backward_c done
   cudaEvent_t ev_start = p->host_ev[slot][2 * kHostMaxChunks], ev_done = p->host_ev[slot][2 * kHostMaxChunks + 1];
   int rc = 0;
-  // the copy streams must not start before what the caller queued on `stream` (e.g. a previous use of the workspace)
   mark(stream, "start");
-  e = cudaEventRecord(ev_start, stream);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(p->host_in, ev_start, 0);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(p->host_out, ev_start, 0);
+  if (join_and_sync) {
+    // synchronous call: everything is ordered after what the caller queued on `stream` (e.g. an earlier use of the
+    // workspace by the caller's own kernels)
+    e = cudaEventRecord(ev_start, stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(p->host_in, ev_start, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(p->host_out, ev_start, 0);
+  }
+  // submitted steps: the only earlier user of this slot's workspace and host buffers is the previous step of the
+  // same slot, which the caller has waited for (the contract of rayen_forward_backward_host_submit_f32).  The copy-in
+  // therefore starts at once -- under the kernels of the step before -- instead of behind everything queued on
+  // `stream`; the kernels themselves are ordered by `stream`, the copy-out by the events below.
   void* ws_c[kHostMaxChunks];
   int64_t lo[kHostMaxChunks], cnt[kHostMaxChunks];
   int used = 0;

@@ -9,6 +9,27 @@ namespace rayen {
 
 constexpr int kViolThreads = 256;
 
+// init + row . y over k4 (multiple of 4) entries.  Blocks of 64 terms are summed in float32 and the block sums added
+// with a compensated (Neumaier) sum: the metric of a 4000-dimensional row then carries ~1e-7 of the terms' scale
+// instead of the ~1e-5 of a plain running sum, i.e. it can certify the 1e-5 feasibility bar in wide sets too.
+__device__ __forceinline__ float viol_dot(const float* __restrict__ row, const float* __restrict__ yb, int k4, float init) {
+  float tot = init, comp = 0.f;
+  for (int i0 = 0; i0 < k4; i0 += 64) {
+    const int i1 = (i0 + 64 < k4) ? i0 + 64 : k4;
+    float acc = 0.f;
+    for (int i = i0; i < i1; i += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(row + i));
+      const float4 yy = ld4(yb + i);
+      acc = fmaf(a.x, yy.x, fmaf(a.y, yy.y, fmaf(a.z, yy.z, fmaf(a.w, yy.w, acc))));
+    }
+    const float sum = tot + acc;
+    const float bp = sum - tot;
+    comp += (tot - (sum - bp)) + (acc - bp);
+    tot = sum;
+  }
+  return tot + comp;
+}
+
 // One warp per sample; lanes split the rows of every constraint; y sits in shared memory.
 __global__ void __launch_bounds__(kViolThreads)
     viol_lqs_kernel(const PlanDev P, const float* __restrict__ y, long long ldy, float* __restrict__ viol, long long B) {
@@ -27,24 +48,14 @@ __global__ void __launch_bounds__(kViolThreads)
     // A1 y <= b1
     for (int j = lane; j < P.viol_in; j += 32) {
       const float* row = p + static_cast<size_t>(j) * row_w;
-      float acc = 0.f;
-      for (int i = 0; i < k4; i += 4) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(row + i));
-        const float4 yy = ld4(yb + i);
-        acc = fmaf(a.x, yy.x, fmaf(a.y, yy.y, fmaf(a.z, yy.z, fmaf(a.w, yy.w, acc))));
-      }
+      const float acc = viol_dot(row, yb, k4, 0.f);
       worst = fmaxf(worst, acc - __ldg(row + k4));
     }
     p += static_cast<size_t>(P.viol_in) * row_w;
     // A2 y = b2
     for (int j = lane; j < P.viol_eq; j += 32) {
       const float* row = p + static_cast<size_t>(j) * row_w;
-      float acc = 0.f;
-      for (int i = 0; i < k4; i += 4) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(row + i));
-        const float4 yy = ld4(yb + i);
-        acc = fmaf(a.x, yy.x, fmaf(a.y, yy.y, fmaf(a.z, yy.z, fmaf(a.w, yy.w, acc))));
-      }
+      const float acc = viol_dot(row, yb, k4, 0.f);
       worst = fmaxf(worst, fabsf(acc - __ldg(row + k4)));
     }
     p += static_cast<size_t>(P.viol_eq) * row_w;
@@ -53,12 +64,7 @@ __global__ void __launch_bounds__(kViolThreads)
       float part = 0.f;
       for (int r = lane; r < k; r += 32) {
         const float* row = p + static_cast<size_t>(r) * k4;
-        float acc = 0.f;
-        for (int i = 0; i < k4; i += 4) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(row + i));
-          const float4 yy = ld4(yb + i);
-          acc = fmaf(a.x, yy.x, fmaf(a.y, yy.y, fmaf(a.z, yy.z, fmaf(a.w, yy.w, acc))));
-        }
+        const float acc = viol_dot(row, yb, k4, 0.f);
         part = fmaf(yb[r], fmaf(0.5f, acc, __ldg(p + static_cast<size_t>(k4) * k4 + r)), part);
       }
       part = group_sum<32>(part);
@@ -75,12 +81,7 @@ __global__ void __launch_bounds__(kViolThreads)
       for (int i = lane; i < k; i += 32) cy = fmaf(__ldg(c + i), yb[i], cy);
       for (int r = lane; r < rm; r += 32) {
         const float* row = rows + static_cast<size_t>(r) * row_w;
-        float acc = __ldg(row + k4);
-        for (int i = 0; i < k4; i += 4) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(row + i));
-          const float4 yy = ld4(yb + i);
-          acc = fmaf(a.x, yy.x, fmaf(a.y, yy.y, fmaf(a.z, yy.z, fmaf(a.w, yy.w, acc))));
-        }
+        const float acc = viol_dot(row, yb, k4, __ldg(row + k4));
         ss = fmaf(acc, acc, ss);
       }
       cy = group_sum<32>(cy);

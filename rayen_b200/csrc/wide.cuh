@@ -58,22 +58,38 @@ __device__ __forceinline__ void wide_fma_col(float w, const float4* __restrict__
   }
 }
 
+// Columns are accumulated in blocks of kWideAccBlock and the block sums added to a running total: the rounding of a
+// float32 dot product of n terms then grows like sqrt(block) + sqrt(n / block) instead of sqrt(n) (n = 4000: ~2e-7 of
+// the terms' scale instead of ~2e-6, which at b_j ~ 1 was a constraint residual of up to 4e-5 in the round-1 sweep).
+constexpr int kWideAccBlock = 128;
+
 // acc[s] = sum_{j >= j0} Wt[j][row] * us[j][s]: the column walk of one row against the tile's directions; eight
 // column loads in flight per lane
 template <int TS>
 __device__ __forceinline__ void wide_dot(const float* __restrict__ wcol, int r_pad, int j0, int n,
-                                         const float4* __restrict__ us4, float (&acc)[TS]) {
+                                         const float4* __restrict__ us4, float (&tot)[TS]) {
+  float acc[TS];
 #pragma unroll
-  for (int s = 0; s < TS; ++s) acc[s] = 0.f;
+  for (int s = 0; s < TS; ++s) tot[s] = acc[s] = 0.f;
   int j = j0;
-  for (; j + 8 <= n; j += 8) {
-    float w[8];
+  while (j + 8 <= n) {
+    const int stop = (j + kWideAccBlock < n) ? j + kWideAccBlock : n;
+    for (; j + 8 <= stop; j += 8) {
+      float w[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) w[q] = __ldg(wcol + static_cast<size_t>(j + q) * r_pad);
+      for (int q = 0; q < 8; ++q) w[q] = __ldg(wcol + static_cast<size_t>(j + q) * r_pad);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) wide_fma_col<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), acc);
+      for (int q = 0; q < 8; ++q) wide_fma_col<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), acc);
+    }
+#pragma unroll
+    for (int s = 0; s < TS; ++s) {
+      tot[s] += acc[s];
+      acc[s] = 0.f;
+    }
   }
   for (; j < n; ++j) wide_fma_col<TS>(__ldg(wcol + static_cast<size_t>(j) * r_pad), us4 + static_cast<size_t>(j) * (TS / 4), acc);
+#pragma unroll
+  for (int s = 0; s < TS; ++s) tot[s] += acc[s];
 }
 
 // Two consecutive rows per lane (wcol2 points at the lane's row pair, 8-byte aligned): per column one 8-byte load and
@@ -95,23 +111,38 @@ __device__ __forceinline__ void wide_fma_col2(float2 w, const float4* __restrict
 }
 template <int TS>
 __device__ __forceinline__ void wide_dot2(const float* __restrict__ wcol2, int r_pad, int j0, int n,
-                                          const float4* __restrict__ us4, float (&acc0)[TS], float (&acc1)[TS]) {
+                                          const float4* __restrict__ us4, float (&tot0)[TS], float (&tot1)[TS]) {
   // eight columns in flight per lane (sixteen in the 8-sample kernel measured 2x SLOWER on B200: 26.6 -> 54.7 us at n = 64,
-  // 179 -> 354 us at n = 1000 -- kept at eight)
+  // 179 -> 354 us at n = 1000 -- kept at eight); block sums as in wide_dot
   constexpr int U = 8;
+  float acc0[TS], acc1[TS];
 #pragma unroll
-  for (int s = 0; s < TS; ++s) acc0[s] = acc1[s] = 0.f;
+  for (int s = 0; s < TS; ++s) tot0[s] = tot1[s] = acc0[s] = acc1[s] = 0.f;
   int j = j0;
-  for (; j + U <= n; j += U) {
-    float2 w[U];
+  while (j + U <= n) {
+    const int stop = (j + kWideAccBlock < n) ? j + kWideAccBlock : n;
+    for (; j + U <= stop; j += U) {
+      float2 w[U];
 #pragma unroll
-    for (int q = 0; q < U; ++q) w[q] = __ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j + q) * r_pad));
+      for (int q = 0; q < U; ++q) w[q] = __ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j + q) * r_pad));
 #pragma unroll
-    for (int q = 0; q < U; ++q) wide_fma_col2<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), acc0, acc1);
+      for (int q = 0; q < U; ++q) wide_fma_col2<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), acc0, acc1);
+    }
+#pragma unroll
+    for (int s = 0; s < TS; ++s) {
+      tot0[s] += acc0[s];
+      tot1[s] += acc1[s];
+      acc0[s] = acc1[s] = 0.f;
+    }
   }
   for (; j < n; ++j)
     wide_fma_col2<TS>(__ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j) * r_pad)),
                       us4 + static_cast<size_t>(j) * (TS / 4), acc0, acc1);
+#pragma unroll
+  for (int s = 0; s < TS; ++s) {
+    tot0[s] += acc0[s];
+    tot1[s] += acc1[s];
+  }
 }
 
 // value of x[lane] for lane < TS without dynamic register indexing

@@ -19,7 +19,7 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 MAX_NP = 32      # widest subspace of the register-resident kernels; beyond it the WIDE section / wide.cuh take over
 MAX_WIDE_N = 4096
 MAX_LMI = 32
@@ -268,12 +268,24 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
     # ---- pruning bound of the LMI: lambda_max(S) <= tr(S)/r + sqrt((r-1)/r) sqrt(|S|_F^2 - tr(S)^2/r)
     # (Wolkowicz-Styan), with tr(S~(u)) = t.u and |S~(u)|_F = |T u|, T'T = [tr(F~z_a F~z_b)]_ab.  Lets the
     # linear/quadratic/SOC kernel prove, for most samples, that the LMI cannot be the binding constraint.
+    # The Gram matrix is CENTRED, G_c = [tr(F~z_a F~z_b) - tr F~z_a tr F~z_b / r] (PSD by Cauchy-Schwarz: the Gram matrix
+    # of the trace-free parts), so that |S~|_F^2 - tr(S~)^2/r = |T_c u|^2 is a sum of squares: forming it as a difference
+    # in float32 cancels whenever S~(u) is close to a multiple of I (e.g. the epigraph form t I - A(y) >= 0) and the
+    # "bound" then drops below lambda_max.  `bound_margin` covers the float32 / 3xTF32 rounding of the two dot products
+    # (<= 5e-7 (|t|/r + |T_c|_F) for unit u) with 8x headroom; it is an absolute amount added to the bound.
     bound = np.zeros(np_ + tri_words + 4) if not wide else np.zeros(4)
+    bound_margin = 0.0
     if lmi is not None:
-        bound[:n] = np.trace(Fz, axis1=1, axis2=2)
+        tr_F = np.trace(Fz, axis1=1, axis2=2)
         gram = np.einsum("aij,bij->ab", Fz, Fz)
-        bound[np_:np_ + tri_words] = _pack_triangular(_triangular_factor(gram, np_))
+        gram_c = gram - np.outer(tr_F, tr_F) / float(lmi_r)
+        gram_c = 0.5 * (gram_c + gram_c.T)
+        bound_T = _triangular_factor(gram_c, np_)
+        bound_margin = 4e-6 * (float(np.sqrt(max(np.trace(gram_c), 0.0))) + float(np.linalg.norm(tr_F)) / lmi_r)
+        bound[:n] = tr_F
+        bound[np_:np_ + tri_words] = _pack_triangular(bound_T)
         bound[np_ + tri_words] = float(lmi_r)
+        bound[np_ + tri_words + 1] = bound_margin
     off_bound = add(bound)
     off_lmi = add(Fperm) if lmi is not None else add(np.zeros(4))
 
@@ -313,8 +325,8 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
             items.append((3, j, A, np.concatenate((hdr, tri_dense(R)))))
         if lmi is not None:
             hdr = np.zeros((ch, kp))
-            hdr[0, :n] = np.trace(Fz, axis1=1, axis2=2)
-            items.append((5, 0, float(lmi_r), np.concatenate((hdr, tri_dense(_triangular_factor(gram, np_))))))
+            hdr[0, :n] = tr_F
+            items.append((5, 0, float(lmi_r), np.concatenate((hdr, tri_dense(bound_T)))))
         for base in range(0, len(items), ipp):
             blk = np.zeros((TC_PANEL, kp))
             ints, flts = [1, 0] + [0] * 16, [0.0] * 8
@@ -489,8 +501,10 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
                        off_y0=off_y0, off_bound=off_bound, off_lmi=off_lmi, lmi_prune=int(lmi is not None),
                        off_tc=off_tc, tc_panels=tc_panels, tc_kp=kp,
                        off_viol=off_viol, off_lmineg=off_lmineg, viol_in=viol_in, viol_eq=viol_eq,
-                       off_lmitc=off_lmitc, lmitc_panels=lmitc_panels, wide=int(wide), off_wide=off_wide)
-    plan.f64 = dict(D=D, N=N, y0=y0, z0=z0, yp=yp, quads=quad_f64, socs=soc_f64, Fz=Fz)
+                       off_lmitc=off_lmitc, lmitc_panels=lmitc_panels, wide=int(wide), off_wide=off_wide,
+                       lmi_bound_margin=float(np.float32(bound_margin)))
+    plan.f64 = dict(D=D, N=N, y0=y0, z0=z0, yp=yp, quads=quad_f64, socs=soc_f64, Fz=Fz,
+                    bound=(tr_F, bound_T, lmi_r, bound_margin) if lmi is not None else None)
     return plan
 
 

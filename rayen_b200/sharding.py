@@ -3,8 +3,8 @@
 The ray-shooting map is sample-wise, so the data-parallel layout needs no collective in forward or backward:
 every rank holds a replica of the (KB-sized) plan and a contiguous slice of the batch.  The
 only exchange is optional: ``all_gather_outputs`` for a downstream loss that couples samples across the
-batch (NCCL all-gather forward; the backward is the matching slice of the incoming gradient, summed over
-ranks when the loss is replicated).  The reference has no distributed code (single device).
+batch (NCCL all-gather forward; the backward is the matching reduce-scatter of the incoming gradient: this rank's
+rows, summed over the ranks' copies of the loss).  The reference has no distributed code (single device).
 """
 import torch
 import torch.distributed as dist
@@ -47,11 +47,30 @@ class _AllGatherRows(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         # every rank holds the gradient w.r.t. the full gathered tensor of ITS copy of the loss; the gradient of
-        # this rank's rows is the sum of those copies' slices
-        g = g.contiguous()
-        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
-        lo = sum(ctx.sizes[:ctx.rank])
-        return g[lo:lo + ctx.sizes[ctx.rank]], None, None
+        # this rank's rows is the sum over ranks of those copies' slices: a reduce-scatter (1/world of the bytes an
+        # all-reduce of the whole [B, ...] gradient would move).  The incoming gradient is never modified in place:
+        # autograd may share it with other consumers (retain_grad, hooks).
+        sizes, rank, group = ctx.sizes, ctx.rank, ctx.group
+        world = len(sizes)
+        lo = sum(sizes[:rank])
+        if dist.get_backend(group) == "nccl":
+            if len(set(sizes)) == 1:
+                out = g.new_empty((sizes[rank],) + tuple(g.shape[1:]))
+                dist.reduce_scatter_tensor(out, g.contiguous(), op=dist.ReduceOp.SUM, group=group)
+                return out, None, None
+            top = max(sizes)
+            padded = g.new_zeros((world * top,) + tuple(g.shape[1:]))
+            off = 0
+            for r, s in enumerate(sizes):
+                padded[r * top:r * top + s] = g[off:off + s]
+                off += s
+            out = g.new_empty((top,) + tuple(g.shape[1:]))
+            dist.reduce_scatter_tensor(out, padded, op=dist.ReduceOp.SUM, group=group)
+            return out[:sizes[rank]], None, None
+        # backends without reduce-scatter (gloo, the CPU tests): all-reduce a private copy, keep this rank's rows
+        total = g.clone(memory_format=torch.contiguous_format)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        return total[lo:lo + sizes[rank]], None, None
 
 
 def all_gather_outputs(y_local, batch=None, group=None):

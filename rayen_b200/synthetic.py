@@ -191,6 +191,26 @@ def wide_spec(k, m=0, eta=0, mu=0, r_M=0, eq=0, seed=0, loosen=3.0):
     return spec
 
 
+def epigraph_lmi_spec(k, r, perturbation, delta=None, seed=0, sign=1.0):
+    """The epigraph form ``t I - A(y) >= 0`` (t = y_0), the commonest LMI there is: F_0 = sign * I, F_a = perturbation *
+    (a random symmetric matrix) for a >= 1, constant term I, y0 = 0.  S~(u) is then a multiple of the identity plus a
+    small perturbation -- the case in which a Frobenius-norm bound written as a DIFFERENCE cancels in float32.
+    ``delta`` (a list) adds one linear row per entry, -sign * (1 - d) y_0 <= 1, whose kappa lands within d of the LMI's
+    kappa for the directions in which the LMI can bind: the competing constraint that a wrong pruning decision needs."""
+    rng = np.random.default_rng(seed)
+    all_F = [sign * np.eye(r)]
+    for _ in range(k - 1):
+        T = rng.uniform(-1.0, 1.0, size=(r, r))
+        all_F.append(perturbation * 0.5 * (T + T.T))
+    all_F.append(np.eye(r))
+    spec = dict(A1=None, b1=None, A2=None, b2=None, qcs=[], socs=[], lmi=all_F, y0=np.zeros((k, 1)))
+    if delta:
+        A1 = np.zeros((len(delta), k))
+        A1[:, 0] = [-sign * (1.0 - d) for d in delta]
+        spec["A1"], spec["b1"] = A1, np.ones((len(delta), 1))
+    return spec
+
+
 def build_constraints(spec, module=constraints, y0="spec", do_preprocessing_linear=False):
     """Instantiate ``module``'s classes (this package's, or the reference's) from a spec."""
     lc = None

@@ -204,3 +204,95 @@ def test_wide_plan_with_more_items_than_a_round_holds():
     cf = closed_form_numpy(OracleSet.from_constraints(cs), v.numpy())
     y, kap, act = plan.evaluate_wide_numpy(p, v.numpy())
     assert np.abs(y - cf["y"]).max() <= 5e-6 * max(1.0, np.abs(cf["y"]).max())
+
+
+# ----------------------------------------------------------------------------- LMI pruning bound in float32
+def _bound_f32(p, u32, tf32=False):
+    """The pruning bound exactly as the kernels form it (lqs.cuh lmi_upper_bound), from the PACKED float32 block, with
+    float32 dot products accumulated term by term; ``tf32``: operands split hi + lo like the 3xTF32 GEMM of lqs_tc.cuh
+    (the lo*lo term dropped)."""
+    f = p.fields
+    np_, n = f["np"], f["n"]
+    tri_words = plan.packed_triangular_words(np_)
+    blob = p.blob
+    off = f["off_bound"]
+    t = blob[off:off + np_]
+    T = np.zeros((np_, np_), dtype=np.float32)
+    pos = off + np_
+    for i in range(np_):
+        c0 = (i // 4) * 4
+        T[i, c0:] = blob[pos:pos + np_ - c0]
+        pos += np_ - c0
+    r, margin = blob[off + np_ + tri_words], blob[off + np_ + tri_words + 1]
+    assert margin == np.float32(f["lmi_bound_margin"]) and margin > 0
+    W = np.concatenate((t[None, :], T), axis=0)                      # [1 + np, np]
+    U = np.zeros((u32.shape[0], np_), dtype=np.float32)
+    U[:, :n] = u32
+
+    def dots(Wm, Um):
+        acc = np.zeros((Um.shape[0], Wm.shape[0]), dtype=np.float32)
+        for j in range(np_):                                          # sequential float32 accumulation (fmaf ~ mul+add here)
+            acc = (acc + Um[:, j:j + 1] * Wm[None, :, j]).astype(np.float32)
+        return acc
+    if tf32:
+        Wh, Wl = plan.split_tf32(W)
+        Uh, Ul = plan.split_tf32(U)
+        d = (dots(Wh, Uh) + dots(Wh, Ul) + dots(Wl, Uh)).astype(np.float32)
+    else:
+        d = dots(W, U)
+    mean = (d[:, 0] / r).astype(np.float32)
+    ss = np.sum(d[:, 1:] * d[:, 1:], axis=1, dtype=np.float32)
+    radius = np.sqrt(((r - np.float32(1)) / r) * ss, dtype=np.float32)
+    return (mean + radius + (np.float32(1e-5) * (np.abs(mean) + radius) + margin)).astype(np.float32)
+
+
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+@pytest.mark.parametrize("perturbation", [1e-4, 1e-3, 1e-2, 1.0])
+def test_pruning_bound_is_float32_safe(perturbation, sign):
+    """on epigraph LMIs (one F_a = +-I, the others small) a bound that forms
+    |S|_F^2 - tr(S)^2/r as a difference cancels in float32 and fell BELOW lambda_max in 7.6 % of the cases.  The centred
+    form is a sum of squares: the float32 (and 3xTF32) evaluation must stay above the float64 lambda_max for every
+    direction, i.e. pruning remains a proof."""
+    worst = np.inf
+    for seed in range(5):
+        for (k, r) in ((8, 32), (5, 12), (32, 32), (3, 7)):
+            spec = synthetic.epigraph_lmi_spec(k, r, perturbation, seed=seed, sign=sign)
+            p = plan.build_plan_from_constraints(synthetic.build_constraints(spec))
+            Fz = p.f64["Fz"]
+            rng = np.random.default_rng(100 + seed)
+            u = rng.standard_normal((500, k))
+            u[:50, 0] = np.abs(u[:50, 0]) * 30.0 * -sign             # directions in which S~ ~ a positive multiple of I
+            u32 = (u / np.linalg.norm(u, axis=1, keepdims=True)).astype(np.float32)
+            lam = np.linalg.eigvalsh(np.einsum("ba,aij->bij", u32.astype(np.float64), Fz))[:, -1]
+            for tf32 in (False, True):
+                ub = _bound_f32(p, u32, tf32).astype(np.float64)
+                worst = min(worst, float((ub - lam).min()))
+                assert (ub >= lam).all(), (perturbation, sign, k, r, tf32, float((ub - lam).min()))
+    assert worst >= 0.0
+
+
+def test_pruning_bound_uncentred_form_would_fail():
+    """Negative control for the test above: the round-1 formula (uncentred Gram, dev2 = ss - tr^2/r in float32, relative
+    margin 1e-4) does fall below lambda_max on these sets -- the hazard is real and the test can see it."""
+    bad = 0
+    for seed in range(3):
+        spec = synthetic.epigraph_lmi_spec(8, 32, 1e-3, seed=seed)
+        p = plan.build_plan_from_constraints(synthetic.build_constraints(spec))
+        Fz = p.f64["Fz"]
+        tr = np.trace(Fz, axis1=1, axis2=2)
+        gram = np.einsum("aij,bij->ab", Fz, Fz)
+        T = plan._triangular_factor(gram, 8).astype(np.float32)
+        rng = np.random.default_rng(seed)
+        u = rng.standard_normal((2000, 8))
+        u[:, 0] = -np.abs(u[:, 0]) * 30.0
+        u32 = (u / np.linalg.norm(u, axis=1, keepdims=True)).astype(np.float32)
+        lam = np.linalg.eigvalsh(np.einsum("ba,aij->bij", u32.astype(np.float64), Fz))[:, -1]
+        h0 = (u32 @ tr.astype(np.float32)).astype(np.float32)
+        Tu = (u32 @ T.T).astype(np.float32)
+        ss = np.sum(Tu * Tu, axis=1, dtype=np.float32)
+        mean = h0 / np.float32(32)
+        dev2 = np.maximum(ss - h0 * mean, np.float32(0))
+        ub = mean + np.sqrt(np.float32(31.0 / 32.0) * dev2)
+        ub = ub + np.float32(1e-4) * np.abs(ub)
+        bad += int((ub.astype(np.float64) < lam).sum())
+    assert bad > 0
