@@ -79,6 +79,9 @@ extern "C" {
  *           lmitc_panels = rp*rp/128 panels of 128 entries, entry e = i*rp + 4q + t <-> F~z_a[i][q + (rp/4)*t]
  *           (the LMI section's order), per panel W_hi and W_lo (128 x tc_kp each, TF32 split) in the operand
  *           layout [k/4][row/8][row%8][k%4]
+ *   LMIW    (plans with an LMI) F~z_a once more for the filter + one-warp-per-matrix solver of lmi_warp.cuh: n matrices,
+ *           zero padded to 32 x 32, row-major with a row stride of 36 words ([a][row][36]); lane j of a warp reads
+ *           row j (= column j, the matrices are symmetric) as eight 16-byte loads, conflict-free in shared memory
  *   WIDE    (wide == 1: 32 < n <= 4096, linear + quadratic + SOC; wide.cuh) 16 int32 words {magic 0x57494445, R_pad,
  *           n_tasks, off_tasks, off_wt, off_nt, off_nrow, k32, np, off_items, n_quad, n_soc, n_rounds, off_rounds,
  *           layout version 3, 0} (offsets in words from `blob`), then
@@ -124,6 +127,7 @@ typedef struct RayenPlanDesc {
   float lmi_bound_margin; /* absolute float32-rounding allowance added to the pruning bound (see BOUND) */
   int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi, off_tc, off_viol, off_lmineg, off_lmitc;
   int64_t off_wide;     /* WIDE section (0 when wide == 0) */
+  int64_t off_lmiw;     /* LMIW section (0 without an LMI) */
   int64_t blob_words;
   const float* blob; /* host pointer, blob_words floats */
 } RayenPlanDesc;
@@ -153,6 +157,15 @@ int rayen_plan_set_tensor_cores(rayen_plan_t* plan, int enabled);
  * mode: 0 never, 1 wherever available, 2 automatic (default): the measured policy -- tensor cores when K = 32 and
  * the call carries no gradient work.  RAYEN_LMI_TC=0/1/2 sets the default of new plans. */
 int rayen_plan_set_lmi_tensor_cores(rayen_plan_t* plan, int mode);
+
+/* LMI forward for samples that carry a kappa of the other families (every set with an LMI and anything else): an exact
+ * definiteness filter -- LDL' of (kappa_prior - margin) I - S~(u), all pivots positive <=> the LMI cannot bind -- in
+ * front of a one-warp-per-matrix eigen-solver for the samples that fail it (lmi_warp.cuh).  Results are those of the
+ * unfiltered path (a passing sample keeps the prior kappa, which is what the merge after a full solve keeps).
+ * mode: 0 never (the 8-lanes-per-matrix kernels of lmi.cuh), 1 wherever available, 2 automatic (default: padded LMI
+ * sizes 16 and 32).  RAYEN_LMI_WARP=0/1/2 sets the default of new plans; RAYEN_LMI_FILTER=0 keeps the solver but skips
+ * the filter. */
+int rayen_plan_set_lmi_filter(rayen_plan_t* plan, int mode);
 
 /* Device scratch the forward / backward calls need for a batch of B samples (work lists of the samples
  * that still need the LMI kernels, and d kappa/du of the LMI-bound samples).  0 for plans without an LMI.  The caller owns the buffer; it must

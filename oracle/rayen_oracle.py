@@ -147,7 +147,8 @@ def closed_form_numpy(oset, v, gy=None):
 
     Returns a dict: y[B,k], kappa[B], family[B], index[B], case[B], margin[B] (relative gap between the
     two largest kappas, for near-tie masking), cone_cond[B] (sqrt(disc)/|b'| of a binding cone, 1 otherwise: small
-    means a nearly tangent ray, ill-conditioned in float32) and, when gy is given, gv[B,n].
+    means a nearly tangent ray, ill-conditioned in float32), lmi_gap[B] (relative gap between the two largest eigenvalues
+    when the LMI binds, 1 otherwise: the gradient of lambda_max is conditioned like 1/gap) and, when gy is given, gv[B,n].
     """
     v = np.asarray(v, dtype=np.float64).reshape(-1, oset.n)
     B, n, k = v.shape[0], oset.n, oset.k
@@ -199,6 +200,12 @@ def closed_form_numpy(oset, v, gy=None):
         dk_drho = np.einsum("bi,aij,bj->ba", qv, Ft, qv)
         kappas.append(lam[:, -1]); grads.append(dk_drho @ N); fams.append((FAM_LMI, np.zeros(B, dtype=int)))
         conds.append(np.ones(B))
+        # relative gap between the two largest eigenvalues: d lambda_max/du = q'F q has the condition number ~ 1/gap
+        # (the reference's own float32 gradient is off by ~ eps/gap there: SURVEY 3.3, "eigengap-sensitive")
+        if S.shape[1] > 1:
+            lmi_gap_all = (lam[:, -1] - lam[:, -2]) / np.maximum(np.abs(lam).max(axis=1), 1e-300)
+        else:
+            lmi_gap_all = np.ones(B)
 
     K = np.stack(kappas, axis=1)                            # [B, 1+eta+mu+lmi]
     best = np.argmax(K, axis=1)
@@ -215,6 +222,7 @@ def closed_form_numpy(oset, v, gy=None):
     index = np.stack([f[1] for f in fams], axis=1)[np.arange(B), best]
     family = np.where(kap > 0, family, FAM_NONE)
     cone_cond = np.stack(conds, axis=1)[np.arange(B), best]
+    lmi_gap = np.where(family == FAM_LMI, lmi_gap_all, 1.0) if oset.lmi is not None else np.ones(B)
 
     with np.errstate(divide="ignore"):
         inv_kappa = np.where(kap > 0, 1.0 / np.where(kap > 0, kap, 1.0), np.inf)
@@ -222,7 +230,7 @@ def closed_form_numpy(oset, v, gy=None):
     y = (z0[None, :] + alpha[:, None] * u) @ N.T + yp[None, :]
     case = np.where(s == 0, CASE_ZERO, np.where(s <= inv_kappa, CASE_INTERIOR, CASE_BOUNDARY))
     out = dict(y=y, kappa=kap, family=family, index=index, case=case, margin=margin, alpha=alpha, s=s,
-               cone_cond=cone_cond)
+               cone_cond=cone_cond, lmi_gap=lmi_gap)
     if gy is not None:
         gz = np.asarray(gy, dtype=np.float64).reshape(B, k) @ N
         safe_k = np.where(kap > 0, kap, 1.0)

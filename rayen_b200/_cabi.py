@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # RAYEN_B200_LIB points development scripts at an instrumented build of the same sources (scripts/lmi_trace.py)
 LIB_PATH = os.environ.get("RAYEN_B200_LIB") or os.path.join(CSRC, "librayen_b200.so")
-SOURCES = ["rayen_b200.cu", "lqs.cuh", "lqs_tc.cuh", "lmi.cuh", "lmi_tc.cuh", "viol.cuh", "wide.cuh", "common.cuh"]
+SOURCES = ["rayen_b200.cu", "lqs.cuh", "lqs_tc.cuh", "lmi.cuh", "lmi_tc.cuh", "lmi_warp.cuh", "viol.cuh", "wide.cuh",
+           "common.cuh"]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "rayen_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]
@@ -29,7 +30,7 @@ class RayenPlanDesc(ctypes.Structure):
         "viol_in", "viol_eq", "lmitc_panels", "wide")] + [("lmi_bound_margin", ctypes.c_float)] + [
         (name, ctypes.c_int64) for name in (
             "off_lin", "off_quad", "off_soc", "off_nmat", "off_y0", "off_bound", "off_lmi", "off_tc", "off_viol",
-            "off_lmineg", "off_lmitc", "off_wide", "blob_words")] + [
+            "off_lmineg", "off_lmitc", "off_wide", "off_lmiw", "blob_words")] + [
         ("blob", ctypes.POINTER(ctypes.c_float))]
 
 
@@ -50,6 +51,7 @@ SYMBOLS = {
     "rayen_plan_set_pruning": (ctypes.c_int, [_P, ctypes.c_int]),
     "rayen_plan_set_tensor_cores": (ctypes.c_int, [_P, ctypes.c_int]),
     "rayen_plan_set_lmi_tensor_cores": (ctypes.c_int, [_P, ctypes.c_int]),
+    "rayen_plan_set_lmi_filter": (ctypes.c_int, [_P, ctypes.c_int]),
     "rayen_workspace_bytes": (ctypes.c_int64, [_P, ctypes.c_int64]),
     "rayen_forward_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, ctypes.c_int64, ctypes.c_int,
                                          ctypes.c_int, _P, _P]),
@@ -155,6 +157,11 @@ class DevicePlan:
         """0 / False: never, 1 / True: wherever available, 2 / None: automatic."""
         mode = 2 if mode is None else int(mode)
         check(lib().rayen_plan_set_lmi_tensor_cores(self._handle, mode), "rayen_plan_set_lmi_tensor_cores")
+
+    def set_lmi_filter(self, mode):
+        """0 / False: never, 1 / True: wherever available, 2 / None: automatic."""
+        mode = 2 if mode is None else int(mode)
+        check(lib().rayen_plan_set_lmi_filter(self._handle, mode), "rayen_plan_set_lmi_filter")
 
     def workspace_bytes(self, batch):
         return int(lib().rayen_workspace_bytes(self._handle, int(batch)))

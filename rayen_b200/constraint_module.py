@@ -392,6 +392,12 @@ class ConstraintModule(nn.Module):
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._device_plan(device).set_lmi_tensor_cores(mode)
 
+    def set_lmi_filter(self, mode=None, device=None):
+        """LMI forward behind another family's kappa: definiteness filter + one-warp-per-matrix solver (True / 1), the
+        8-lanes-per-matrix kernels (False / 0), or automatic (None / 2, the default).  Results are identical."""
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._device_plan(device).set_lmi_filter(mode)
+
     def violation(self, y):
         """Max constraint residual of every sample of ``y`` ([B, k] or [B, k, 1], CUDA) against the original
         constraints, computed on the GPU by ``rayen_violation_f32`` (<= 0 means feasible)."""

@@ -21,6 +21,7 @@ struct PlanDev {
   int off_viol, off_lmineg, viol_in, viol_eq;  // violation checker sections
   int off_lmitc, lmitc_panels, lmitc_stages;   // LMI matrices as a tcgen05 B operand (lmi_tc.cuh); ring depth
   float lmi_bound_margin;                      // float32-rounding allowance of the pruning bound (rayen_b200.h, BOUND)
+  int off_lmiw;                                // LMI matrices for lmi_warp.cuh (0: none)
 };
 
 // Fused mapper (reference constraint_module.py:261, :525: q = nn.Linear(input_dim, n)(x)): when x != nullptr the
@@ -99,6 +100,11 @@ __device__ __forceinline__ void stage_bulk(float* dst_smem, const float* src, in
 // completed and its writes (kappa, active, the work list) are visible.  Both are no-ops for plain launches.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// A value the PREVIOUS kernel of the stream produced (a work-list counter), read behind pdl_wait().  A plain load through
+// a `const T* __restrict__` parameter is an invariant load to the compiler (LDG.CONSTANT) and may be hoisted above the
+// wait -- observed in SASS: the counter was read while the producer was still running, and came back as 0.  A volatile
+// load is neither hoisted nor served from the non-coherent path.
+__device__ __forceinline__ int ld_after_wait(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 // ----------------------------------------------------------------------------- small helpers
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }

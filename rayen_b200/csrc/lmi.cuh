@@ -337,12 +337,15 @@ struct LmiSolver {
     hi = fmaxf(hi, lo);  // whole spectrum <= 0: degenerate interval, the rounds below return lo = 0 (no early
                          // exit: the shuffles below need every lane of the warp)
     for (int round = 0; round < C::ROUNDS; ++round) {
-      const float h = (hi - lo) * (1.0f / 9.0f);
+      // the first round also probes x = lo itself (8 sections): lo = 0 above the whole spectrum means lambda_max < 0,
+      // and the answer is then exactly 0 (relu), not the midpoint of a tiny interval above it
+      const int shift = round ? 1 : 0;
+      const float h = (hi - lo) / static_cast<float>(8 + shift);
       int bits = 0;
 #pragma unroll
       for (int pp = 0; pp < C::PPL; ++pp) {
         const int pt = q * C::PPL + pp;
-        const float x = fmaf(h, static_cast<float>(pt + 1), lo);
+        const float x = fmaf(h, static_cast<float>(pt + shift), lo);
         float s0 = 1.f, s1 = x - d[0];
         float mn = s1;
 #pragma unroll
@@ -361,12 +364,15 @@ struct LmiSolver {
         bits |= (mn > 0.f) ? (1 << pt) : 0;
       }
       const int mask = group_or<LPM>(bits) & 0xff;
-      const int first = mask ? (__ffs(mask) - 1) : 8;
-      const float new_lo = (first == 0) ? lo : fmaf(h, static_cast<float>(first), lo);
-      const float new_hi = (first == 8) ? hi : fmaf(h, static_cast<float>(first + 1), lo);
+      const int first = mask ? (__ffs(mask) - 1) : 8;  // first probe above the spectrum
+      const float new_lo = (first + shift == 0) ? lo : fmaf(h, static_cast<float>(first + shift - 1), lo);
+      const float new_hi = (first == 8) ? hi : fmaf(h, static_cast<float>(first + shift), lo);
       lo = new_lo;
       hi = new_hi;
     }
+    // lo still 0: the interval is [0, ~3e-8 scale] -- lambda_max is 0 to the resolution of the matrix (a negative
+    // semi-definite S~, e.g. a zero-padded negative definite one): exactly 0, the same answer pruning gives
+    if (!(lo > 0.f)) return 0.f;
     lo *= scale;
     hi *= scale;
     return 0.5f * (lo + hi);
@@ -651,7 +657,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   LMI_GT(0);
   pdl_wait();  // launched behind the linear/quadratic/SOC kernel: its kappa / active / work list must be complete
   // dense mode: every sample; list mode: only the samples the LQS kernel could not prune
-  const long long total = work_list ? static_cast<long long>(*work_count) : B;
+  const long long total = work_list ? static_cast<long long>(ld_after_wait(work_count)) : B;
   // chunk c (MPW samples) belongs to CTA c % gridDim: a CTA without a chunk does not stage F~z at all
   const bool cta_has_work = static_cast<long long>(blockIdx.x) * C::MPW < total;
   LMI_STAMP(0);
@@ -772,7 +778,7 @@ __global__ void __launch_bounds__(kLmiThreads, 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float* scratch_base;
-  const long long total = work_list ? static_cast<long long>(*work_count) : B;
+  const long long total = work_list ? static_cast<long long>(ld_after_wait(work_count)) : B;
   // only the CTAs that own a chunk of the (usually short) work list stage F~z
   const bool cta_has_work = static_cast<long long>(blockIdx.x) * C::MPW < total;
   const float* F = lmi_stage<RP, F_SMEM>(P, smem_raw, bars, &scratch_base, cta_has_work);

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kLmiTcThreads, 1)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   LMI_STAMP(0);
   pdl_wait();  // launched behind the linear/quadratic/SOC kernel: its kappa / active / work list must be complete
-  const long long total = work_list ? static_cast<long long>(*work_count) : B;
+  const long long total = work_list ? static_cast<long long>(ld_after_wait(work_count)) : B;
   // samples per pass: a short list is spread over all CTAs (whole warps, at least one)
   int per_pass = T::SPP;
   if (total < static_cast<long long>(T::SPP) * gridDim.x) {

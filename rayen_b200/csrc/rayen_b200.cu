@@ -11,6 +11,7 @@
 
 #include "lmi.cuh"
 #include "lmi_tc.cuh"
+#include "lmi_warp.cuh"
 #include "lqs.cuh"
 #include "lqs_tc.cuh"
 #include "viol.cuh"
@@ -43,6 +44,12 @@ struct rayen_plan {
   bool lmi_tc_ok;         // ... available for this plan (rp >= 16, section present, fits in shared memory)
   bool lmi_tc_grad_fsmem; // the gradient variant keeps F~z in shared memory next to the GEMM buffers
   size_t lmi_tc_smem_bytes, lmi_tc_grad_smem_bytes;
+  // filter + one-warp-per-matrix solver (lmi_warp.cuh) for launches in which the samples carry a prior kappa
+  bool lmi_warp_ok;       // LMIW section present and the kernel's shared memory fits
+  int lmi_warp_mode;      // 0 never, 1 wherever available, 2 automatic (padded size >= 16)
+  bool lmi_warp_filter;   // the definiteness filter in front of the solver (RAYEN_LMI_FILTER=0: solver only)
+  int lmi_warp_solves;    // failing samples a warp of the filter kernel solves itself before it hands over (default 1)
+  size_t lmi_warp_smem_bytes;
   // host-buffer path only (rayen_forward_backward_host_f32): copy streams and events, created on first use and
   // serialised by host_mu -- the device-pointer entry points never touch them, so the plan stays re-entrant there
   std::mutex* host_mu;
@@ -269,6 +276,10 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
                                d->off_lmitc + static_cast<int64_t>(d->lmitc_panels) * 2 * 128 * d->tc_kp > d->blob_words)))
     return fail(RAYEN_ERR_BAD_ARGUMENT, "LMI tensor-core section does not fit the block");
 
+  if (d->off_lmiw < 0 || d->off_lmiw % 4 ||
+      (d->lmi_r > 0 && d->off_lmiw > 0 && d->off_lmiw + static_cast<int64_t>(d->n) * kLwMatWords > d->blob_words))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "LMIW section does not fit the block");
+
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
     return fail(RAYEN_ERR_NO_DEVICE, "CUDA device %d is not available (%d devices visible)", device, count);
@@ -323,6 +334,7 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   v.viol_in = d->viol_in; v.viol_eq = d->viol_eq;
   v.off_lmitc = static_cast<int>(d->off_lmitc); v.lmitc_panels = d->lmitc_panels;
   v.lmi_bound_margin = d->lmi_bound_margin;
+  v.off_lmiw = static_cast<int>(d->off_lmiw);
 
   p->has_lqs = d->n_quad > 0 || d->n_soc > 0;
   for (int64_t i = d->off_lin; i < d->off_quad && !p->has_lqs; ++i) p->has_lqs = d->blob[i] != 0.0f;
@@ -383,6 +395,22 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
       if (rc == 0 && p->lmi_tc_ok)
         rc = allow_smem(reinterpret_cast<const void*>(lmi_fwd_tc_fn(v.lmi_rp, p->lmi_tc_grad_fsmem, true)),
                         p->lmi_tc_grad_smem_bytes);
+    }
+  }
+  if (rc == 0 && v.lmi_r > 0 && v.off_lmiw > 0) {
+    p->lmi_warp_smem_bytes = lmi_warp_smem_bytes(v.n, kLwThreads);
+    p->lmi_warp_ok = p->lmi_warp_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
+    p->lmi_warp_mode = 2;
+    p->lmi_warp_filter = true;
+    p->lmi_warp_solves = 1;
+    if (const char* sv = getenv("RAYEN_LMI_WARP_SOLVES")) p->lmi_warp_solves = atoi(sv) < 0 ? 0 : atoi(sv);
+    const char* env = getenv("RAYEN_LMI_WARP");
+    if (env && atoi(env) >= 0 && atoi(env) <= 2) p->lmi_warp_mode = atoi(env);
+    env = getenv("RAYEN_LMI_FILTER");
+    if (env && atoi(env) == 0) p->lmi_warp_filter = false;
+    if (p->lmi_warp_ok) {
+      rc = allow_smem(reinterpret_cast<const void*>(lmi_forward_warp_kernel<false>), p->lmi_warp_smem_bytes);
+      if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_forward_warp_kernel<true>), p->lmi_warp_smem_bytes);
     }
   }
   // the violation checker keeps one y row per warp in shared memory: large ambient dimensions need the opt-in limit
@@ -574,6 +602,14 @@ extern "C" int rayen_bwd_trace_read(long long* out) {
 }
 #endif
 
+#ifdef RAYEN_LW_TRACE
+// development build only (scripts/lw_trace.py): the stamps of lmi_forward_warp_kernel (8192 values)
+extern "C" int rayen_lw_trace_read(long long* out) {
+  cudaDeviceSynchronize();
+  return static_cast<int>(cudaMemcpyFromSymbol(out, rayen::g_lw_trace, sizeof(long long) * 8192));
+}
+#endif
+
 #ifdef RAYEN_LMI_TRACE
 // development build only: copies the phase stamps of lmi_forward_kernel (see LMI_STAMP) to `out` (4096 values)
 extern "C" int rayen_lmi_trace_read(long long* out) {
@@ -599,6 +635,21 @@ static bool lmi_use_tc(const rayen_plan* p, bool want_grad, bool list_mode) {
   if (!p->lmi_tc_ok || p->lmi_tc_mode == 0) return false;
   if (p->lmi_tc_mode == 1) return true;
   return p->dev.tc_kp >= 32 && !want_grad && !list_mode;
+}
+
+extern "C" int rayen_plan_set_lmi_filter(rayen_plan_t* p, int mode) {
+  if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "null plan");
+  if (mode < 0 || mode > 2) return fail(RAYEN_ERR_BAD_ARGUMENT, "mode must be 0 (never), 1 (always) or 2 (automatic)");
+  p->lmi_warp_mode = mode;
+  return RAYEN_OK;
+}
+
+// The filter needs a prior kappa to test against (a set with an LMI alone has none: every sample is solved, and there
+// the 8-lanes-per-matrix layout of lmi.cuh has the higher throughput); automatic: padded LMI sizes 16 and 32.
+static bool lmi_use_warp(const rayen_plan* p, bool has_prior) {
+  if (!p->lmi_warp_ok || p->lmi_warp_mode == 0 || !has_prior) return false;
+  if (p->lmi_warp_mode == 1) return true;
+  return p->dev.lmi_rp >= 16;
 }
 
 extern "C" int rayen_plan_set_pruning(rayen_plan_t* p, int enabled) {
@@ -811,8 +862,10 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
   const bool run_lqs = p->has_lqs || !has_lmi;
   const bool use_list = has_lmi && run_lqs && p->prune;
   cudaError_t e = cudaSuccess;
+  const bool use_warp = has_lmi && lmi_use_warp(p, run_lqs);
+  // counters: [0] forward work list, [1] backward work list, [2] fail list of the filter kernel (lmi_warp.cuh)
   if ((stage_mask & 1) && run_lqs) {
-    if (use_list) e = cudaMemsetAsync(counters, 0, sizeof(int), stream);
+    if (use_list || use_warp) e = cudaMemsetAsync(counters, 0, 3 * sizeof(int), stream);
     if (e == cudaSuccess && p->use_tc) {
       long long grid = (B + 255) / 256;
       if (grid > p->sm_count) grid = p->sm_count;
@@ -839,7 +892,53 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
     // the kernel right before this one in the stream is our own linear/quadratic/SOC kernel: launch behind it
     static const bool pdl_on = !(getenv("RAYEN_PDL") && atoi(getenv("RAYEN_PDL")) == 0);
     const bool behind_lqs = pdl_on && (stage_mask & 1) && run_lqs;
-    if (lmi_use_tc(p, grad, use_list)) {
+    if (use_warp) {
+      // The filter kernel settles the samples whose LMI provably cannot bind, solves up to `solves_per_warp` of the
+      // others per warp itself (latency: usually there are only a handful) and leaves the rest in the fail list (the
+      // region of the backward work list, free until the backward call) for a second launch (usually an empty list).
+      int* fail_list = reinterpret_cast<int*>(static_cast<char*>(workspace) + 256 + ws_list_bytes(B));
+      if (!behind_lqs) e = cudaMemsetAsync(counters + 2, 0, sizeof(int), stream);  // else zeroed with the other counters
+      // chunks of 4 samples, dealt round-robin to the CTAs (the list length is only known on the device)
+      long long blocks = (B + kLwMT - 1) / kLwMT;
+      if (blocks > p->sm_count) blocks = p->sm_count;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(static_cast<unsigned>(blocks));
+      cfg.blockDim = dim3(kLwThreads);
+      cfg.dynamicSmemBytes = p->lmi_warp_smem_bytes;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = behind_lqs ? 1 : 0;
+      const int* list = use_list ? fwd_list : nullptr;
+      const int* cnt = use_list ? counters : nullptr;
+      float* dk = grad ? ws_dkappa(workspace, B) : nullptr;
+      const long long ldv_ = ldv, B_ = B;
+      const int filt = p->lmi_warp_filter ? 1 : 0;
+      const int budget = p->lmi_warp_solves;
+      int* fcnt = counters + 2;
+      if (e == cudaSuccess)
+        e = grad ? cudaLaunchKernelEx(&cfg, lmi_forward_warp_kernel<true>, d, v, ldv_, y, kappa, active, B_, mode, list, cnt, dk,
+                                      filt, budget, fail_list, fcnt)
+                 : cudaLaunchKernelEx(&cfg, lmi_forward_warp_kernel<false>, d, v, ldv_, y, kappa, active, B_, mode, list, cnt,
+                                      dk, filt, budget, fail_list, fcnt);
+      g_launches.fetch_add(1);
+      if (e == cudaSuccess) {
+        // the same kernel once more on the fail list, filter off, no budget: whoever solves a sample runs the same
+        // arithmetic, so results do not depend on how the batch was cut into chunks (bit-identical across pruning
+        // on / off, host-buffer chunking, list order)
+        cfg.numAttrs = pdl_on ? 1 : 0;
+        const int* flist = fail_list;
+        const int* fc = fcnt;
+        int* none = nullptr;
+        const int all = 0x7fffffff, nofilt = 0;
+        e = grad ? cudaLaunchKernelEx(&cfg, lmi_forward_warp_kernel<true>, d, v, ldv_, y, kappa, active, B_, mode, flist, fc, dk,
+                                      nofilt, all, none, none)
+                 : cudaLaunchKernelEx(&cfg, lmi_forward_warp_kernel<false>, d, v, ldv_, y, kappa, active, B_, mode, flist, fc,
+                                      dk, nofilt, all, none, none);
+      }
+    } else if (lmi_use_tc(p, grad, use_list)) {
       // one CTA per SM, persistent over passes of 8 warps x mpw samples; short batches still start one CTA per
       // warp's worth of samples so that the kernel can spread them (it re-derives the split from the list length)
       long long blocks = (B + mpw - 1) / mpw;

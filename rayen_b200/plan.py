@@ -73,6 +73,7 @@ def packed_triangular_words(np_):
 TC_PANEL = 128  # rows of W per tensor-core panel (MMA N)
 TC_TABLE_WORDS = 32
 LMI_TC_PANEL = 128  # entries of the LMI matrix per panel of the contraction GEMM (MMA N)
+LMIW_R, LMIW_ROW_STRIDE = 32, 36   # lmi_warp.cuh: kLwR, kLwRowStride
 WIDE_MAGIC = 0x57494445
 WIDE_VERSION = 3
 WIDE_HEADER_WORDS = 16
@@ -409,6 +410,14 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
             if pi == 0:
                 off_lmitc = off
 
+    # ---- LMIW (lmi_warp.cuh, the filter + one-warp-per-matrix solver): F~z_a row-major, zero padded to 32 x 32, with
+    # a row stride of 36 words so that 32 lanes reading 16 bytes of 32 different rows do not collide in shared memory
+    off_lmiw = 0
+    if lmi is not None:
+        Fw = np.zeros((n, LMIW_R, LMIW_ROW_STRIDE))
+        Fw[:, :lmi_r, :lmi_r] = Fz
+        off_lmiw = add(Fw)
+
     # ---- WIDE section (n > 32, wide.cuh): every constraint as rows of ONE matrix W [R_pad x n], stored transposed
     # (Wt[j][row]) so that a warp's 32 lanes read 32 consecutive rows of a column with one coalesced load.  The unit
     # of work of a warp is a TASK = one group of 32 rows (see rayen_b200.h); the groups of an item leave partial sums
@@ -502,6 +511,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
                        off_tc=off_tc, tc_panels=tc_panels, tc_kp=kp,
                        off_viol=off_viol, off_lmineg=off_lmineg, viol_in=viol_in, viol_eq=viol_eq,
                        off_lmitc=off_lmitc, lmitc_panels=lmitc_panels, wide=int(wide), off_wide=off_wide,
+                       off_lmiw=off_lmiw,
                        lmi_bound_margin=float(np.float32(bound_margin)))
     plan.f64 = dict(D=D, N=N, y0=y0, z0=z0, yp=yp, quads=quad_f64, socs=soc_f64, Fz=Fz,
                     bound=(tr_F, bound_T, lmi_r, bound_margin) if lmi is not None else None)

@@ -49,6 +49,21 @@ template <class T>
 inline T __shfl_xor_sync(unsigned, T v, int off) { return emu_exchange(v, (threadIdx.x & 31) ^ off); }
 template <class T>
 inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, src); }
+inline unsigned __ballot_sync(unsigned, bool pred) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  emu_slots[w][l] = pred ? 1u : 0u;
+  emu_warp_bar[w]->arrive_and_wait();
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= emu_slots[w][i] << i;
+  emu_warp_bar[w]->arrive_and_wait();
+  return r;
+}
+inline int __ffs(unsigned x) { return x ? __builtin_ctz(x) + 1 : 0; }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline float __frcp_rn(float x) { return 1.0f / x; }
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+inline int __float_as_int(float f) { int x; std::memcpy(&x, &f, 4); return x; }
 template <class T>
 inline T __ldg(const T* p) { return *p; }
 inline float __int_as_float(int x) { float f; std::memcpy(&f, &x, 4); return f; }
