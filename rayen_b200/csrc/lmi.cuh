@@ -370,12 +370,10 @@ struct LmiSolver {
       lo = new_lo;
       hi = new_hi;
     }
-    // lo still 0: the interval is [0, ~3e-8 scale] -- lambda_max is 0 to the resolution of the matrix (a negative
-    // semi-definite S~, e.g. a zero-padded negative definite one): exactly 0, the same answer pruning gives
-    if (!(lo > 0.f)) return 0.f;
-    lo *= scale;
-    hi *= scale;
-    return 0.5f * (lo + hi);
+    // below 1e-7 of the matrix scale lambda_max is 0 to the resolution of a float32 matrix (a negative semi-definite
+    // S~, e.g. a zero-padded negative definite one): exactly 0 then, the same answer pruning gives
+    const float mid = 0.5f * (lo + hi);
+    return (mid > 1e-7f) ? mid * scale : 0.f;
   }
 
   // ---- 4. unit eigenvector of lambda (backward only): twisted factorisation of T - lambda I on one

@@ -399,7 +399,9 @@ struct LwSolver {
           mn = fminf(mn, sn);
           s0 = s1;
           s1 = sn;
-          if ((i & 7) == 7 && i + 1 < kLwR) {  // (eight steps grow |s| by at most 3^8)
+          // every 4 steps: (x - d_i) can be ~1e-7 for several rows in a row (zero padding, clustered eigenvalues),
+          // and 8 such factors underflow
+          if ((i & 3) == 3 && i + 1 < kLwR) {
             const int ex = (__float_as_int(fmaxf(fabsf(s0), fabsf(s1))) >> 23) & 0xff;
             const float sc = __int_as_float((254 - max(min(ex, 253), 1)) << 23);
             s0 *= sc;
@@ -413,9 +415,10 @@ struct LwSolver {
         lo = new_lo;
         hi = new_hi;
       }
-      // lo still 0: the interval is [0, ~3e-8 scale] -- lambda_max is 0 to the resolution of the matrix (a negative
-      // semi-definite S~, e.g. a zero-padded negative definite one): exactly 0, the same answer pruning gives
-      return (lo > 0.f) ? 0.5f * (lo + hi) * scale : 0.f;
+      // below 1e-7 of the matrix scale lambda_max is 0 to the resolution of a float32 matrix (a negative semi-definite
+      // S~, e.g. a zero-padded negative definite one): exactly 0 then, the same answer pruning gives
+      const float mid = 0.5f * (lo + hi);
+      return (mid > 1e-7f) ? mid * scale : 0.f;
     }
   }
 

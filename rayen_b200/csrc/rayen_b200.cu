@@ -514,8 +514,10 @@ static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** o
   // the attribute is per function, not per plan: always the device maximum, so that plans of different n coexist
   if (rc == 0 && p->wide_fwd_smem_bytes[0] > static_cast<size_t>(p->max_smem_optin))
     rc = fail(RAYEN_ERR_UNSUPPORTED, "wide plan: n=%d needs %zu bytes of shared memory", w.n, p->wide_fwd_smem_bytes[0]);
-  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<8>), p->max_smem_optin);
-  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<16>), p->max_smem_optin);
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<8, false>), p->max_smem_optin);
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<16, false>), p->max_smem_optin);
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<8, true>), p->max_smem_optin);
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<16, true>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_backward_kernel<128>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_backward_kernel<256>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(viol_lqs_kernel), p->max_smem_optin);
@@ -675,7 +677,7 @@ extern "C" int rayen_plan_kernel_info(const rayen_plan_t* p, RayenKernelInfo* ou
   memset(out, 0, sizeof(*out));
   cudaFuncAttributes a;
   if (p->wide) {
-    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(wide_forward_kernel<16>)));
+    RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(wide_forward_kernel<16, false>)));
     out->regs_lqs_fwd = a.numRegs;
     RAYEN_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(wide_backward_kernel<256>)));
     out->regs_lqs_bwd = a.numRegs;
@@ -844,12 +846,11 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
       long long grid = (B + ts - 1) / ts;
       const long long cap = static_cast<long long>(p->sm_count) * 32;
       if (grid > cap) grid = cap;
-      if (ts16)
-        wide_forward_kernel<16><<<static_cast<int>(grid), kWideThreads, p->wide_fwd_smem_bytes[1], stream>>>(
-            p->wdev, v, ldv, y, kappa, active, B, mode);
-      else
-        wide_forward_kernel<8><<<static_cast<int>(grid), kWideThreads, p->wide_fwd_smem_bytes[0], stream>>>(
-            p->wdev, v, ldv, y, kappa, active, B, mode);
+      const bool blk = p->wdev.n >= kWideBlockedN;  // blocked accumulation of the long dot products (wide.cuh)
+      const size_t wsm = p->wide_fwd_smem_bytes[ts16 ? 1 : 0];
+      auto wf = ts16 ? (blk ? wide_forward_kernel<16, true> : wide_forward_kernel<16, false>)
+                     : (blk ? wide_forward_kernel<8, true> : wide_forward_kernel<8, false>);
+      wf<<<static_cast<int>(grid), kWideThreads, wsm, stream>>>(p->wdev, v, ldv, y, kappa, active, B, mode);
       g_launches.fetch_add(1);
       we = cudaGetLastError();
     }

@@ -58,16 +58,34 @@ __device__ __forceinline__ void wide_fma_col(float w, const float4* __restrict__
   }
 }
 
-// Columns are accumulated in blocks of kWideAccBlock and the block sums added to a running total: the rounding of a
-// float32 dot product of n terms then grows like sqrt(block) + sqrt(n / block) instead of sqrt(n) (n = 4000: ~2e-7 of
-// the terms' scale instead of ~2e-6, which at b_j ~ 1 was a constraint residual of up to 4e-5 in the round-1 sweep).
+// BLK (sets with n >= kWideBlockedN): columns are accumulated in blocks of kWideAccBlock and the block sums added to a
+// running total: the rounding of a float32 dot product of n terms then grows like sqrt(block) + sqrt(n / block) instead
+// of sqrt(n) (n = 4000: ~2e-7 of the terms' scale instead of ~2e-6).  The second set of accumulators costs registers
+// (measured: -28 % at n = 64, -41 % at n = 256 when applied everywhere), so narrower sets keep the plain running sum,
+// whose rounding is below 1e-6 there anyway.
 constexpr int kWideAccBlock = 128;
+constexpr int kWideBlockedN = 512;
 
 // acc[s] = sum_{j >= j0} Wt[j][row] * us[j][s]: the column walk of one row against the tile's directions; eight
 // column loads in flight per lane
-template <int TS>
+template <int TS, bool BLK>
 __device__ __forceinline__ void wide_dot(const float* __restrict__ wcol, int r_pad, int j0, int n,
                                          const float4* __restrict__ us4, float (&tot)[TS]) {
+  if constexpr (!BLK) {
+    // narrow enough for a plain running sum (no second set of accumulators: registers)
+#pragma unroll
+    for (int s = 0; s < TS; ++s) tot[s] = 0.f;
+    int j = j0;
+    for (; j + 8 <= n; j += 8) {
+      float w[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) w[q] = __ldg(wcol + static_cast<size_t>(j + q) * r_pad);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) wide_fma_col<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), tot);
+    }
+    for (; j < n; ++j) wide_fma_col<TS>(__ldg(wcol + static_cast<size_t>(j) * r_pad), us4 + static_cast<size_t>(j) * (TS / 4), tot);
+    return;
+  }
   float acc[TS];
 #pragma unroll
   for (int s = 0; s < TS; ++s) tot[s] = acc[s] = 0.f;
@@ -109,12 +127,28 @@ __device__ __forceinline__ void wide_fma_col2(float2 w, const float4* __restrict
     acc1[4 * q + 3] = fmaf(w.y, a.w, acc1[4 * q + 3]);
   }
 }
-template <int TS>
+template <int TS, bool BLK>
 __device__ __forceinline__ void wide_dot2(const float* __restrict__ wcol2, int r_pad, int j0, int n,
                                           const float4* __restrict__ us4, float (&tot0)[TS], float (&tot1)[TS]) {
   // eight columns in flight per lane (sixteen in the 8-sample kernel measured 2x SLOWER on B200: 26.6 -> 54.7 us at n = 64,
   // 179 -> 354 us at n = 1000 -- kept at eight); block sums as in wide_dot
   constexpr int U = 8;
+  if constexpr (!BLK) {
+#pragma unroll
+    for (int s = 0; s < TS; ++s) tot0[s] = tot1[s] = 0.f;
+    int j = j0;
+    for (; j + U <= n; j += U) {
+      float2 w[U];
+#pragma unroll
+      for (int q = 0; q < U; ++q) w[q] = __ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j + q) * r_pad));
+#pragma unroll
+      for (int q = 0; q < U; ++q) wide_fma_col2<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), tot0, tot1);
+    }
+    for (; j < n; ++j)
+      wide_fma_col2<TS>(__ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j) * r_pad)),
+                        us4 + static_cast<size_t>(j) * (TS / 4), tot0, tot1);
+    return;
+  }
   float acc0[TS], acc1[TS];
 #pragma unroll
   for (int s = 0; s < TS; ++s) tot0[s] = tot1[s] = acc0[s] = acc1[s] = 0.f;
@@ -165,7 +199,7 @@ __device__ __forceinline__ void wide_take(float c, int ct, float& best, int& tag
 
 // ----------------------------------------------------------------------------- forward
 // grid: one CTA per tile of TS samples (grid-stride); dynamic smem = wide_fwd_smem_bytes(n, TS).
-template <int TS>
+template <int TS, bool BLK>
 __global__ void __launch_bounds__(kWideThreads)
     wide_forward_kernel(const WideDev P, const float* __restrict__ v, long long ldv, float* __restrict__ y,
                         float* __restrict__ kappa_out, int* __restrict__ active_out, long long B, int mode) {
@@ -234,7 +268,7 @@ __global__ void __launch_bounds__(kWideThreads)
         const int* tk = tasks + t * 8;
         const int kind = __ldg(tk), row = __ldg(tk + 1), j0 = __ldg(tk + 2), idx = __ldg(tk + 3), slot = __ldg(tk + 5);
         float acc0[TS], acc1[TS];
-        wide_dot2<TS>(wt + row + 2 * lane, P.r_pad, j0, n, us4, acc0, acc1);
+        wide_dot2<TS, BLK>(wt + row + 2 * lane, P.r_pad, j0, n, us4, acc0, acc1);
         if (kind == 1) {
           // a lane's rows arrive in ascending order: strict > keeps the lowest
 #pragma unroll
@@ -335,7 +369,7 @@ __global__ void __launch_bounds__(kWideThreads)
       const float* nt = blob + P.off_nt;
       for (int i = tid; i < k; i += kWideThreads) {
         float acc[TS];
-        wide_dot<TS>(nt + i, P.k32, 0, n, us4, acc);
+        wide_dot<TS, BLK>(nt + i, P.k32, 0, n, us4, acc);
         const float c = __ldg(y0 + i);
 #pragma unroll
         for (int s = 0; s < TS; ++s) {
