@@ -2,11 +2,14 @@
 """bench.py -- ConstraintModule forward+backward samples/sec (BASELINE.json metric) on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg5] [--batch B]
+                    [--strong] [--gather] [--no-extra] [--no-cpu-baseline]
 
 One "step" = one forward + one backward of the layer over one batch of B samples per GPU.  The default
 workload is BASELINE.json's configs[4] ("Mixed L+Q+SOC+LMI, dim=32, batch=262144 sharded across 8xB200"):
 every GPU owns a 32768-sample shard (weak scaling; 8 GPUs = the named 262144 batch), no data-path
-collective.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+collective.  `--strong` keeps the global batch at 262144 and splits it over the ranks.  `--gather` adds the optional
+exchange step (NCCL all-gather of y, reduce-scatter of its gradient).  Prints ONE JSON line (rank 0).  See DESIGN.md
+"Measurement" for every field.
 """
 import argparse
 import ctypes
@@ -15,7 +18,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -27,6 +29,7 @@ import torch  # noqa: E402
 
 METRIC = "ConstraintModule fwd+bwd samples/sec"
 POOL = 16  # rotating buffer sets; their total size exceeds the 126 MB L2 for the default workload
+STRONG_GLOBAL_BATCH = 262144
 
 
 def parse_args():
@@ -37,8 +40,10 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the workload's named batch)")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: global batch fixed at 262144, split over the ranks")
+    ap.add_argument("--gather", action="store_true", help="also time the optional all-gather of y (+ reduce-scatter of g_y)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs / sweeps")
-    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (profiling runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference timing (profiling runs)")
     ap.add_argument("--tm", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0)
     return ap.parse_args()
@@ -55,6 +60,17 @@ def workload_desc(name, shp, batch, world):
     if shp["r"]:
         fam.append(f"one {shp['r']}x{shp['r']} LMI")
     return f"{name}: dim={shp['k']}, " + " + ".join(fam) + f", batch {batch}/GPU x {world} GPU"
+
+
+def flops_per_sample(shp):
+    """Algorithmic flops of one forward in the z-space formulation: linear 2mn, quadratic eta(2n^2+4n), SOC
+    mu(2 r_M n + 2n + 20), LMI contraction 2 n r^2 + eigen-solve 4/3 r^3, scale step 2kn; backward ~ one more pass."""
+    n = k = shp["k"]
+    r = shp["r"]
+    parts = {"linear": 2.0 * shp["m"] * n, "quadratic": shp["eta"] * (2.0 * n * n + 4 * n),
+             "soc": shp["mu"] * (2.0 * shp["r_M"] * n + 2 * n + 20), "lmi_contraction": 2.0 * n * r * r,
+             "lmi_eigen": 4.0 / 3.0 * r ** 3, "scale": 2.0 * k * n}
+    return parts
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -106,47 +122,88 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- the reference arm (CPU)
-def cpu_oracle_rate(spec_name, sample, repeats, warmup, threads):
-    """samples/sec of the op-for-op torch restatement of the reference (oracle port) on the host cores."""
-    from oracle.rayen_oracle import OracleSet, TorchOracle
-    from rayen_b200 import synthetic
-    torch.set_num_threads(threads)
-    spec = synthetic.config_spec(spec_name)
-    cs = synthetic.build_constraints(spec)
-    orc = TorchOracle(OracleSet.from_constraints(cs), torch.float32)
-    v, gy = synthetic.sample_inputs(sample, cs.n, cs.k)
-    times = []
-    for it in range(warmup + repeats):
-        t0 = time.perf_counter()
-        orc.forward_backward(v, gy)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    return sample / float(np.mean(times)), float(np.mean(times)), float(np.min(times))
+class CpuArm:
+    """The reference's own implementation of the path on the host cores: the UNMODIFIED reference package (from
+    oracle/_ref/, a verbatim git-ignored copy made by oracle/make_ref.py; kind "reference") when it is there, else the
+    op-for-op torch restatement in oracle/rayen_oracle.py (kind "port").  One pass = y = layer(v); (y*g_y).sum().backward()."""
+
+    def __init__(self, workload, threads):
+        from rayen_b200 import synthetic
+        from oracle import reference_loader
+        torch.set_num_threads(threads)
+        self.spec = synthetic.config_spec(workload)
+        self.kind = "port"
+        self.n = self.k = None
+        if reference_loader.reference_available():
+            try:
+                ref = reference_loader.load_reference()
+                prev = torch.get_default_dtype()
+                torch.set_default_dtype(torch.float32)
+                try:
+                    cs = synthetic.build_constraints(self.spec, module=ref.constraints)
+                    self.layer = ref.constraint_module.ConstraintModule(cs, method="RAYEN", create_map=False)
+                finally:
+                    torch.set_default_dtype(prev)
+                self.n, self.k = cs.n, cs.k
+                self.kind = "reference"
+            except Exception as exc:  # noqa: BLE001 - fall back to the port, say why
+                self.why_port = repr(exc)[:160]
+        if self.kind == "port":
+            from oracle.rayen_oracle import OracleSet, TorchOracle
+            cs = synthetic.build_constraints(self.spec)
+            self.orc = TorchOracle(OracleSet.from_constraints(cs), torch.float32)
+            self.n, self.k = cs.n, cs.k
+
+    def one_pass(self, v, gy):
+        if self.kind == "reference":
+            x = v.unsqueeze(2).clone().requires_grad_(True)
+            y = self.layer(x)
+            (y * gy.unsqueeze(2)).sum().backward()
+            return y, x.grad
+        return self.orc.forward_backward(v, gy)
+
+    def time(self, sample, steps, warmup):
+        from rayen_b200 import synthetic
+        v, gy = synthetic.sample_inputs(sample, self.n, self.k)
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            self.one_pass(v, gy)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+        return sample / float(np.mean(times)), float(np.mean(times))
+
+    def describe(self, sample, cores, per_pass_s):
+        what = ("the unmodified reference (rayen.constraint_module.ConstraintModule, method='RAYEN', from oracle/_ref)"
+                if self.kind == "reference" else "the oracle's op-for-op torch restatement of the reference")
+        return (f"{sample} samples of the workload per pass, {what}, torch {torch.__version__} CPU fp32, {cores} threads, "
+                f"{per_pass_s * 1e3:.0f} ms/pass")
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own PyTorch op sequence (oracle port; the reference is Python and
-    cannot travel to the GPU box) on the host cores, same workload, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, same workload; one
+    step = one forward+backward pass over a sample of the batch sized so that the whole run stays within minutes."""
     if rank != 0:
         return
     from rayen_b200 import synthetic
     shp = synthetic.CONFIG_SHAPES[args.workload]
-    batch = args.batch or shp["batch"]
+    batch = args.batch or (STRONG_GLOBAL_BATCH // world if args.strong else shp["batch"])
     cores = os.cpu_count() or 1
-    sample = min(batch, 2048)
-    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
-    # keep the whole run bounded: ~0.3 s per 2048-sample step of cfg5 on 8 cores
-    steps = min(steps, 40)
-    rate, mean_t, _ = cpu_oracle_rate(args.workload, sample, steps, warmup, cores)
+    arm = CpuArm(args.workload, cores)
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    probe_rate, _ = arm.time(min(batch, 1024), 1, 1)
+    budget_s = 150.0
+    sample = int(min(batch, max(1024, probe_rate * budget_s / (steps + warmup) // 1024 * 1024)))
+    rate, mean_t = arm.time(sample, steps, warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate * 1.0, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": mean_t * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_desc(args.workload, shp, batch, world), "sample_per_step": sample},
-        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} samples of the workload per step, torch {torch.__version__} CPU fp32, "
-                                   f"{cores} threads"},
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": mean_t * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_desc(args.workload, shp, batch, world), "batch_per_gpu": batch,
+                   "sample_per_step": sample, "same_batch_as_b200_arm": sample == batch},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": arm.kind,
+                         "sample": arm.describe(sample, cores, mean_t)},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -173,7 +230,7 @@ class DeviceBench:
                 v=v.to(device), gy=gy.to(device),
                 y=torch.empty((batch, self.k), device=device), gv=torch.empty((batch, self.n), device=device),
                 kappa=torch.empty((batch,), device=device), active=torch.empty((batch,), dtype=torch.int32, device=device),
-                ws=torch.empty((max(self.plan.workspace_bytes(batch), 16),), dtype=torch.uint8, device=device)))
+                ws=torch.zeros((max(self.plan.workspace_bytes(batch), 16),), dtype=torch.uint8, device=device)))
         self.stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
     def forward(self, s, stage=3):
@@ -205,6 +262,17 @@ class DeviceBench:
         e1.record()
         torch.cuda.synchronize(self.device)
         return e0.elapsed_time(e1) / steps  # ms per call
+
+    def time_loop_median(self, fn, steps, warmup, groups=5):
+        """Median over `groups` timed loops: a secondary figure that one host-side hiccup (the clocks sampler's
+        nvidia-smi poll holding a driver lock, a GC pause) must not decide."""
+        vals = [self.time_loop(fn, steps, warmup if g == 0 else 1) for g in range(groups)]
+        return float(np.median(vals))
+
+    def counters(self, s):
+        """(LMI work-list length, fail-list length) the last forward on this buffer set left in its workspace."""
+        c = s["ws"][:12].view(torch.int32).cpu().numpy()
+        return int(c[0]), int(c[2])
 
 
 def module_step_fn(layer, bench):
@@ -250,12 +318,28 @@ def e2e_pipelined_ms(layer, host, device, steps, warmup, in_flight=2):
     return (time.perf_counter() - t0) / steps * 1e3
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this round (profiles/r02_traffic.json, written
+    by scripts/summarize_profiles.py from `ncu --set full`: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.isfile(path):
+        return None, None
+    try:
+        table = json.load(open(path))
+    except ValueError:
+        return None, None
+    for name, entry in table.items():
+        if name == kernel:
+            return float(entry["dram_bytes"]), f"profiles/r02_traffic.json ({entry.get('source', 'ncu --set full')})"
+    return None, None
+
+
 def run_b200(args, rank, local_rank, world):
     from rayen_b200 import _cabi, synthetic
     from rayen_b200.constraint_module import ConstraintModule
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
-    _cabi.lib()
+    lib = _cabi.lib()
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     dist = None
@@ -276,7 +360,7 @@ def run_b200(args, rank, local_rank, world):
             os.close(saved_stdout)
 
     shp = synthetic.CONFIG_SHAPES[args.workload]
-    batch = args.batch or shp["batch"]
+    batch = args.batch or (STRONG_GLOBAL_BATCH // world if args.strong else shp["batch"])
     spec = synthetic.config_spec(args.workload)
     cs = synthetic.build_constraints(spec)
     layer = ConstraintModule(cs, create_map=False).to(device)
@@ -317,7 +401,7 @@ def run_b200(args, rank, local_rank, world):
     direct_ms = max_over_ranks(e0.elapsed_time(e1) / steps)
     # the same through nn.Module.forward + autograd backward (adds PyTorch's eager/autograd overhead per step)
     mod_fn = module_step_fn(layer, bench)
-    ms_module = max_over_ranks(bench.time_loop(mod_fn, steps, warmup))
+    ms_module = max_over_ranks(bench.time_loop_median(mod_fn, steps, warmup))
     # ... and replayed from CUDA graphs (one captured fwd+bwd per buffer set): launch overhead removed
     graph_ms = None
     try:
@@ -333,10 +417,12 @@ def run_b200(args, rank, local_rank, world):
                 graphs.append(gph)
         bench.stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         torch.cuda.synchronize(device)
-        graph_ms = max_over_ranks(bench.time_loop(lambda i: graphs[i % POOL].replay(), steps, warmup))
-    except Exception as exc:  # noqa: BLE001 - the graph variant is informational only
+        graph_ms = max_over_ranks(bench.time_loop_median(lambda i: graphs[i % POOL].replay(), steps, warmup))
+    except Exception:  # noqa: BLE001 - the graph variant is informational only
         bench.stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        graph_err = repr(exc)[:200]
+    # launch floor: a chain of as many empty kernels as one step launches
+    per_step_launches = max(1, int(round(launches / max(steps, 1))))
+    floor_ms = bench.time_loop_median(lambda i: lib.rayen_launch_empty(per_step_launches, bench.stream), 200, 20, groups=3)
     t_extra = time.time()
     while time.time() - t_extra < 0.5:
         bench.step(0)
@@ -350,6 +436,32 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     e2e_ms = max_over_ranks(e2e_ms)
     e2e_pipe_ms = max_over_ranks(e2e_pipelined_ms(layer, host, device, max(8, steps // 2), 4))
+    barrier()
+
+    # ---- optional exchange step: all-gather of y over NCCL, reduce-scatter of the gradient
+    gather = None
+    if args.gather and dist is not None:
+        from rayen_b200 import sharding
+        y_local = bench.sets[0]["y"].clone().requires_grad_(True)
+        g_full = torch.randn(batch * world, k, device=device)
+
+        def gather_fwd(i):
+            sharding.all_gather_outputs(y_local.detach())
+
+        def gather_both(i):
+            y_local.grad = None
+            sharding.all_gather_outputs(y_local).backward(g_full)
+        barrier()
+        fwd_ms = max_over_ranks(bench.time_loop_median(gather_fwd, 30, 5))
+        barrier()
+        both_ms = max_over_ranks(bench.time_loop_median(gather_both, 30, 5))
+        out_bytes = batch * world * k * 4
+        gather = {"all_gather_ms": fwd_ms, "all_gather_plus_reduce_scatter_ms": both_ms,
+                  "bytes_in_per_rank": batch * k * 4, "bytes_out_per_rank": out_bytes,
+                  "all_gather_bus_gbs": out_bytes * (world - 1) / world / (fwd_ms * 1e-3) / 1e9,
+                  "step_with_gather_ms": direct_ms + both_ms,
+                  "path": "rayen_b200.sharding.all_gather_outputs: dist.all_gather_into_tensor forward, "
+                          "dist.reduce_scatter_tensor backward (NCCL)"}
     barrier()
 
     # the link this box gives the step: one 64 MB pinned copy each way, alone (explains e2e, which moves
@@ -381,13 +493,14 @@ def run_b200(args, rank, local_rank, world):
     value = world * batch / (direct_ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": direct_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
+        "ms_per_step": direct_ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_desc(args.workload, shp, batch, world), "batch_per_gpu": batch,
                    "global_batch": batch * world, "n": n, "k": k,
                    "l2": f"inputs larger than L2: rotating pool of {POOL} buffer sets, "
                          f"{POOL * batch * 4 * (3 * n + 2 * k) / 1e6:.0f} MB of algorithmic traffic per cycle",
-                   "path": "rayen_forward_f32 + rayen_backward_f32 (C ABI) on device-resident buffers, plain launches"},
+                   "path": "rayen_forward_f32 + rayen_backward_f32 (C ABI; called here through their *_stage_* twins with "
+                           "stage_mask = 3, which launch exactly the same kernels) on device-resident buffers, plain launches"},
         "clocks": {"sm_mhz": clock_info["sm_mhz"], "sm_max_mhz": clock_info["sm_max_mhz"],
                    "reasons": clock_info["reasons"], "samples": clock_info["samples"]},
         "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "samples/s",
@@ -399,14 +512,17 @@ def run_b200(args, rank, local_rank, world):
                 "copy_floor_ms": (batch * 4 * (n + k) / 1e6 / max(min(link.get("h2d_gbs", 0.0), link.get("d2h_gbs", 0.0)), 1e-9)
                                   if "h2d_gbs" in link and "d2h_gbs" in link else None),
                 "path": "ConstraintModule.forward_backward_host -> rayen_forward_backward_host_f32 "
-                                               "(pinned host buffers; copy-in, kernels and copy-out on three streams, "
-                                               "synchronous per step)"},
+                        "(pinned host buffers; copy-in, kernels and copy-out on three streams, synchronous per step)"},
         "gpu_launches": int(launches),
+        "launch_floor_ms": floor_ms,
         "module_autograd": {"value": world * batch / (ms_module * 1e-3), "ms_per_step": ms_module,
-                            "path": "nn.Module forward + autograd backward (PyTorch eager overhead included)"},
+                            "path": "nn.Module forward + autograd backward (PyTorch eager overhead included); median of 5 loops"},
         "cuda_graph": ({"value": world * batch / (graph_ms * 1e-3), "ms_per_step": graph_ms,
-                        "path": "the C-ABI fwd+bwd of each buffer set captured once, replayed"} if graph_ms else None),
+                        "path": "the C-ABI fwd+bwd of each buffer set captured once, replayed; median of 5 loops"}
+                       if graph_ms else None),
     }
+    if gather is not None:
+        line["gather"] = gather
 
     # ---- per-kernel durations (CUDA events on the launching stream) and the roofline of the dominant one
     has_lmi = shp["r"] > 0
@@ -414,59 +530,78 @@ def run_b200(args, rank, local_rank, world):
     # lists), so: full forward everywhere, then the two backward stages, then the two forward stages.
     for i in range(POOL):
         bench.forward(bench.sets[i])
+    torch.cuda.synchronize(device)
+    list_len, fail_len = bench.counters(bench.sets[0]) if has_lmi else (0, 0)
     durs = {}
     durs["lqs_backward_kernel"] = bench.time_loop(lambda i: bench.backward(bench.sets[i % POOL], 1), steps, POOL)
-    if has_lmi:
-        durs["lmi_backward_kernel"] = bench.time_loop(lambda i: bench.backward(bench.sets[i % POOL], 2), steps, POOL)
     durs["lqs_forward_kernel"] = bench.time_loop(lambda i: bench.forward(bench.sets[i % POOL], 1), steps, POOL)
     if has_lmi:
         durs["lmi_forward_kernel"] = bench.time_loop(lambda i: bench.forward(bench.sets[i % POOL], 2), steps, POOL)
-    kernel_names = {"lqs_forward_kernel": "lqs_tc_forward_kernel (tcgen05)" if n >= 16 else "lqs_forward_kernel (FP32 pipe)",
-                    "lmi_forward_kernel": "lmi_forward_kernel<WITH_GRAD> (FP32-pipe contraction; the step carries gradient work)"}
+    warp_path = has_lmi and os.environ.get("RAYEN_LMI_WARP", "2") != "0" and n >= 1 and shp["r"] > 8 and (shp["m"] or shp["eta"] or shp["mu"])
+    kernel_names = {
+        "lqs_forward_kernel": "lqs_tc_forward_kernel (tcgen05 3xTF32 GEMM)" if n >= 16 else "lqs_forward_kernel (FP32 pipe)",
+        "lmi_forward_kernel": ("lmi_forward_warp_kernel<WITH_GRAD> x2 (definiteness filter + one-warp-per-matrix solver on the work "
+                               "list, then the same kernel on the fail list)" if warp_path else
+                               "lmi_forward_kernel<WITH_GRAD> (8 lanes per matrix, FP32-pipe contraction)"),
+        "lqs_backward_kernel": "lqs_backward_kernel (closed-form backward, all families)"}
     dominant = max(durs, key=durs.get)
-    fwd_bytes, bwd_bytes = batch * 4 * (n + k), batch * 4 * (2 * n + k)
-    alg_bytes = fwd_bytes if "forward" in dominant else bwd_bytes
+    fwd_bytes_s, bwd_bytes_s = 4 * (n + k), 4 * (2 * n + k)     # algorithmic bytes per sample
+    units = {"lqs_forward_kernel": batch, "lqs_backward_kernel": batch,
+             "lmi_forward_kernel": list_len if (has_lmi and shp["m"] + shp["eta"] + shp["mu"] > 0) else batch}
+    per_unit = bwd_bytes_s if "backward" in dominant else fwd_bytes_s
+    alg_bytes = units[dominant] * per_unit
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        peaks = json.load(open(peaks_path))
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        tensor_peak = float(peaks.get("bf16_tflops", 0.0)) or None
     else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        peak, peak_src, tensor_peak = 6650.0, "fallback (B200_PROFILING.md)", None
     achieved = alg_bytes / (durs[dominant] * 1e-3) / 1e9
-    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this workload
-    traffic, traffic_src = None, None
-    prof = os.path.join(ROOT, "profiles", "r01_lmi_forward.md")
-    if dominant == "lmi_forward_kernel" and args.workload == "cfg5" and batch == 32768 and os.path.isfile(prof):
-        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        tot = 0.0
-        for row in open(prof):
-            f = [x.strip() for x in row.split("|")]
-            if len(f) > 3 and f[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in unit:
-                tot += float(f[3]) * unit[f[2]]
-        traffic, traffic_src = tot, "profiles/r01_lmi_forward.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
-    step_bytes = fwd_bytes + bwd_bytes
+    traffic, traffic_src = measured_traffic(dominant)
+    step_bytes = batch * (fwd_bytes_s + bwd_bytes_s)
+    fl = flops_per_sample(shp)
+    fwd_flops = sum(fl.values())
+    # FP32 FMA peak of this GPU: 148 SMs x 128 lanes x 2 flop x SM clock; TF32 tensor peak taken as half the measured bf16
+    sm_ghz = (clock_info["sm_mhz"] or 1965.0) / 1e3
+    fp32_peak_tflops = 148 * 128 * 2 * sm_ghz / 1e3
+    lqs_flops = batch * (fl["linear"] + fl["quadratic"] + fl["soc"] + fl["scale"])
+    compute = {
+        "flops_per_sample_forward": fl, "flops_per_sample_forward_total": fwd_flops,
+        "whole_step_tflops": batch * 2 * fwd_flops / (direct_ms * 1e-3) / 1e12,
+        "fp32_fma_peak_tflops": fp32_peak_tflops,
+        "whole_step_frac_of_fp32_peak": batch * 2 * fwd_flops / (direct_ms * 1e-3) / 1e12 / fp32_peak_tflops,
+        "lqs_forward": {"algorithmic_tflops": lqs_flops / (durs["lqs_forward_kernel"] * 1e-3) / 1e12,
+                        "note": "on the tensor pipe the kernel issues 3 TF32 MMAs per product (3xTF32) over zero-padded "
+                                "128-row panels: issued flops are ~3.5x the algorithmic ones",
+                        "tf32_peak_tflops_assumed": (tensor_peak / 2 if tensor_peak else None)},
+    }
+    if has_lmi:
+        lmi_units = units["lmi_forward_kernel"]
+        compute["lmi_forward"] = {
+            "units_processed": lmi_units,
+            "algorithmic_tflops": lmi_units * (fl["lmi_contraction"] + fl["lmi_eigen"]) / (durs["lmi_forward_kernel"] * 1e-3) / 1e12,
+            "tensor_pipe": "none: the contraction of the surviving samples runs on the FP32 pipe, register-tiled 4 samples per "
+                           "F~ word (lmi_warp.cuh); the tcgen05 contraction (lmi_tc.cuh) serves dense LMI-only inference launches"}
     line["roofline"] = {
         "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+        "algorithmic_bytes_per_unit": per_unit, "units_processed": units[dominant],
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": durs[dominant],
         "kernel_ms_all": durs, "kernel_names": kernel_names,
         "kernel_share_of_step": durs[dominant] / sum(durs.values()),
         "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (direct_ms * 1e-3) / 1e9,
                        "frac": step_bytes / (direct_ms * 1e-3) / 1e9 / peak},
-        "note": "the named shapes are FP32-issue/LSU bound, not HBM bound (DESIGN.md, Roofline); the HBM fraction "
-                "is reported as the contract asks",
+        "compute": compute,
+        "launch_floor_ms": floor_ms,
+        "note": "the named shapes are FP32-issue / latency bound, not HBM bound (DESIGN.md, Roofline); the HBM fraction "
+                "is reported as the contract asks, on the units the launch really processes",
     }
-
-    # ---- LMI forward without gradient work (inference): FP32-pipe contraction vs the tcgen05 contraction, forced
     if has_lmi:
-        lmi_modes = {}
-        for label, mode in (("fp32_pipe", 0), ("tcgen05", 1)):
-            layer.set_lmi_tensor_cores(mode, device=device)
-            bench.want_grad = 0
-            lmi_modes[label + "_fwd_nograd_ms"] = bench.time_loop(lambda i: bench.forward(bench.sets[i % POOL]), steps, 3)
-        layer.set_lmi_tensor_cores(None, device=device)
-        bench.want_grad = 1
-        line["lmi_contraction"] = dict(lmi_modes, note="whole forward (LQS + LMI kernels), want_grad=0; automatic policy: "
-                                       "tcgen05 for K=32 dense launches without gradient work, FP32 pipe otherwise")
+        line["prune"] = {"batch": batch, "work_list": list_len, "prune_rate": 1.0 - list_len / batch,
+                         "failed_filter_beyond_in_kernel_budget": fail_len,
+                         "note": "work_list = samples the Wolkowicz-Styan bound could not settle; they go through the LDL' "
+                                 "definiteness filter, the ones that fail it through the eigen-solver"}
 
     # ---- feasibility of the outputs (fp64 residuals of every constraint on a sub-sample)
     from oracle.rayen_oracle import OracleSet, max_violation
@@ -482,47 +617,62 @@ def run_b200(args, rank, local_rank, world):
     line["active_family_hist"] = {name: int(c) for name, c in zip(["none", "linear", "quad", "soc", "lmi"],
                                                                   np.bincount(act, minlength=5))}
 
-    # ---- CPU baseline (oracle port) on this box's host cores, bounded sample; rank 0, N == 1 only
+    # ---- CPU baseline on this box's host cores, bounded sample; rank 0, N == 1 only
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = min(batch, 4096)
-        rate, mean_t, best_t = cpu_oracle_rate(args.workload, sample, 8, 1, cores)
-        line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                                "sample": f"{sample} samples of the same workload, mean of 8 passes after 1 warm-up, "
-                                          f"torch {torch.__version__} CPU fp32, {cores} threads, {mean_t * 1e3:.0f} ms/pass"}
+        arm = CpuArm(args.workload, cores)
+        sample = min(batch, 8192)
+        rate, mean_t = arm.time(sample, 4, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": cores, "kind": arm.kind,
+                                "sample": arm.describe(sample, cores, mean_t) + ", mean of 4 passes after 1 warm-up"}
 
-    # ---- the other BASELINE.json configs at their named batch, and a large-batch point (not bench lines)
+    # ---- the other BASELINE.json configs at their named batch, large-batch points, data-dependence of the headline
     if not args.no_extra and world == 1:
         extra = {}
+
+        def run_extra(label, ecs, eb, prune=True, steps_=30):
+            elayer = ConstraintModule(ecs, create_map=False).to(device)
+            if not prune:
+                elayer.set_pruning(False, device=device)
+            per_set = eb * 4 * (3 * elayer.n + 2 * elayer.k)
+            eb_bench = DeviceBench(elayer, eb, device, pool=max(2, min(POOL, int(300e6 // per_set) + 1)))
+            ms = eb_bench.time_loop(eb_bench.step, steps_, 5)
+            fwd_ms = eb_bench.time_loop(lambda i: eb_bench.forward(eb_bench.sets[i % eb_bench.pool]), steps_, 5)
+            entry = {"fwd_bwd_samples_per_s": eb / (ms * 1e-3), "ms_per_step": ms, "fwd_ms": fwd_ms,
+                     "hbm_frac": per_set / (ms * 1e-3) / 1e9 / peak}
+            if ecs.lmic is not None and (ecs.lc is not None or ecs.qcs or ecs.socs):
+                eb_bench.forward(eb_bench.sets[0])
+                torch.cuda.synchronize(device)
+                ll, fl_ = eb_bench.counters(eb_bench.sets[0])
+                entry["work_list"] = ll if prune else eb
+                entry["fail_list"] = fl_
+            extra[label] = entry
+            del eb_bench, elayer
+            torch.cuda.empty_cache()
+
         for name in ("cfg2", "cfg3", "cfg4", "cfg5"):
             eshp = synthetic.CONFIG_SHAPES[name]
-            for eb in sorted({eshp["batch"], 262144}):
+            ecs = synthetic.build_constraints(synthetic.config_spec(name))
+            for eb in sorted({eshp["batch"], 262144, 1 << 20} | ({1 << 22} if name in ("cfg2", "cfg3") else set())):
                 if name == args.workload and eb == batch:
                     continue
-                ecs = synthetic.build_constraints(synthetic.config_spec(name))
-                elayer = ConstraintModule(ecs, create_map=False).to(device)
-                per_set = eb * 4 * (3 * elayer.n + 2 * elayer.k)
-                eb_bench = DeviceBench(elayer, eb, device, pool=max(2, min(POOL, int(300e6 // per_set) + 1)))
-                ms = eb_bench.time_loop(eb_bench.step, 30, 5)
-                fwd_ms = eb_bench.time_loop(lambda i: eb_bench.forward(eb_bench.sets[i % eb_bench.pool]), 30, 5)
-                abytes = eb * 4 * (3 * elayer.n + 2 * elayer.k)
-                extra[f"{name}_B{eb}"] = {"fwd_bwd_samples_per_s": eb / (ms * 1e-3), "ms_per_step": ms, "fwd_ms": fwd_ms,
-                                          "hbm_frac": abytes / (ms * 1e-3) / 1e9 / peak}
-                del eb_bench, elayer
-                torch.cuda.empty_cache()
+                if name == "cfg4" and eb > 262144:
+                    continue           # dense 32x32 eigen-solves: 8 ms per 2^20, nothing new to learn
+                run_extra(f"{name}_B{eb}", ecs, eb, steps_=30 if eb <= 262144 else 10)
+        # how much the headline depends on the data: the same set with pruning off (every sample goes through the
+        # filter), and the "loose" variant (rows relaxed 4x: every family binds, the LMI for ~13 % of the samples)
+        ecs = synthetic.build_constraints(synthetic.config_spec("cfg5"))
+        run_extra("cfg5_B32768_noprune", ecs, 32768, prune=False)
+        lspec = synthetic.config_spec("cfg5")
+        lspec["b1"] = lspec["b1"] * 4.0
+        lcs = synthetic.build_constraints(lspec)
+        run_extra("cfg5_loose_B32768", lcs, 32768)
+        run_extra("cfg5_loose_B32768_noprune", lcs, 32768, prune=False)
         # wide sets (n > 32, wide.cuh): dim 64 (256 rows + 4 ellipsoids + 4 cones) and dim 256 (1024 rows)
         for wname, (wk, wm, weta, wmu, wrm, wb) in (("wide_n64", (64, 256, 4, 4, 32, 65536)),
                                                     ("wide_n256", (256, 1024, 0, 0, 0, 8192))):
             ecs = synthetic.build_constraints(synthetic.wide_spec(wk, wm, weta, wmu, wrm, 0, seed=1))
-            elayer = ConstraintModule(ecs, create_map=False).to(device)
-            per_set = wb * 4 * (3 * elayer.n + 2 * elayer.k)
-            eb_bench = DeviceBench(elayer, wb, device, pool=max(2, min(POOL, int(300e6 // per_set) + 1)))
-            ms = eb_bench.time_loop(eb_bench.step, 20, 5)
-            fwd_ms = eb_bench.time_loop(lambda i: eb_bench.forward(eb_bench.sets[i % eb_bench.pool]), 20, 5)
-            extra[f"{wname}_B{wb}"] = {"fwd_bwd_samples_per_s": wb / (ms * 1e-3), "ms_per_step": ms, "fwd_ms": fwd_ms,
-                                       "hbm_frac": per_set / (ms * 1e-3) / 1e9 / peak}
-            del eb_bench, elayer
-            torch.cuda.empty_cache()
+            run_extra(f"{wname}_B{wb}", ecs, wb, steps_=20)
         line["extra"] = extra
 
     print(json.dumps(line), flush=True)

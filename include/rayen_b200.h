@@ -171,6 +171,9 @@ int rayen_plan_set_lmi_filter(rayen_plan_t* plan, int mode);
  * that still need the LMI kernels, and d kappa/du of the LMI-bound samples).  0 for plans without an LMI.  The caller owns the buffer; it must
  * not be shared by calls that may run concurrently. */
 int64_t rayen_workspace_bytes(const rayen_plan_t* plan, int64_t B);
+/* (Layout, for diagnostics: the workspace starts with three int32 counters that a forward call leaves behind -- [0] the
+ * number of samples the pruning bound could not settle (the LMI work list), [2] how many of those failed the
+ * definiteness filter beyond the filter kernel's own solve budget; [1] is the backward work list's.) */
 
 /*
  * Forward: replaces forwardForRAYEN / forwardForRAYENOld + computeKappa + getyFromz
@@ -252,6 +255,9 @@ int rayen_violation_f32(const rayen_plan_t* plan, const float* y, int64_t ldy, f
 
 /* Number of kernels this library has launched in the calling process (all plans, all threads). */
 int64_t rayen_launch_count(void);
+/* Launches `count` empty kernels (148 x 128 threads) on the stream: the launch floor a chain of kernels pays on this
+ * GPU, measured by bench.py next to the kernel times (not counted by rayen_launch_count). */
+int rayen_launch_empty(int count, void* cuda_stream);
 
 /* Introspection for tests / bench: static shared memory, registers, and chosen launch geometry. */
 typedef struct RayenKernelInfo {

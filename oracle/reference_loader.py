@@ -1,11 +1,13 @@
 """Loader for the UNMODIFIED reference package (leggedrobotics/rayen) -- test infrastructure only.
 
-This file is part of the oracle (test infrastructure).  It is used ONLY in the build
-container, where the reference tree is mounted read-only at /root/reference, to
-  (a) validate the restatement in oracle/rayen_oracle.py against the real reference, and
-  (b) generate the committed golden vectors under tests/golden/ (tests/golden/make_golden.py).
-It is never imported by the product package (rayen_b200/), by `-m gpu` tests, by
-__graft_entry__.smoke() or by bench.py: /root/reference does not exist on the GPU box.
+This file is part of the oracle (test infrastructure).  It is used
+  (a) in the build container, where the reference tree is mounted read-only at /root/reference, to validate the
+      restatement in oracle/rayen_oracle.py against the real reference and to generate the committed golden vectors
+      under tests/golden/ (tests/golden/make_golden.py);
+  (b) by bench.py's CPU-baseline legs (`cpu_baseline`, `--impl reference`), which time the reference's own code on the
+      host cores from the verbatim copy oracle/make_ref.py leaves in oracle/_ref/ (git-ignored; /root/reference does not
+      exist on the GPU box).
+It is never imported by the product package (rayen_b200/), by `-m gpu` tests or by __graft_entry__.smoke().
 
 The reference imports four third-party modules that are absent here (cvxpy, cvxpylayers, cdd,
 colorama; rayen/constraints.py:7, rayen/constraint_module.py:10-12, rayen/utils.py:5-8).  None is
@@ -19,7 +21,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("RAYEN_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    """The mounted reference tree (build container), else the verbatim copy oracle/make_ref.py left in oracle/_ref/
+    (git-ignored; it travels to the GPU box with the snapshot so that bench.py can time the reference itself there)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    for root in (os.environ.get("RAYEN_REFERENCE_ROOT"), "/root/reference", os.path.join(here, "_ref")):
+        if root and os.path.isfile(os.path.join(root, "rayen", "constraint_module.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available():

@@ -69,6 +69,7 @@ SYMBOLS = {
     "rayen_forward_backward_host_wait": (ctypes.c_int, [_P, ctypes.c_int]),
     "rayen_violation_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, ctypes.c_int64, _P]),
     "rayen_launch_count": (ctypes.c_int64, []),
+    "rayen_launch_empty": (ctypes.c_int, [ctypes.c_int, _P]),
     "rayen_plan_kernel_info": (ctypes.c_int, [_P, ctypes.POINTER(RayenKernelInfo)]),
 }
 

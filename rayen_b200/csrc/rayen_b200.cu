@@ -79,6 +79,18 @@ static int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
+// An empty kernel, for the launch floor that bench.py reports next to the kernel times.
+__global__ void rayen_empty_kernel() {}
+extern "C" int rayen_launch_empty(int count, void* stream_) {
+  for (int i = 0; i < count; ++i) rayen_empty_kernel<<<148, 128, 0, static_cast<cudaStream_t>(stream_)>>>();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "rayen_launch_empty: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return RAYEN_OK;
+}
+
 extern "C" int rayen_abi_version(void) { return RAYEN_ABI_VERSION; }
 extern "C" const char* rayen_last_error(void) { return g_err; }
 extern "C" int64_t rayen_launch_count(void) { return g_launches.load(); }

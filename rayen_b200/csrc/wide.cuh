@@ -84,30 +84,30 @@ __device__ __forceinline__ void wide_dot(const float* __restrict__ wcol, int r_p
       for (int q = 0; q < 8; ++q) wide_fma_col<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), tot);
     }
     for (; j < n; ++j) wide_fma_col<TS>(__ldg(wcol + static_cast<size_t>(j) * r_pad), us4 + static_cast<size_t>(j) * (TS / 4), tot);
-    return;
-  }
-  float acc[TS];
+  } else {
+    float acc[TS];
 #pragma unroll
-  for (int s = 0; s < TS; ++s) tot[s] = acc[s] = 0.f;
-  int j = j0;
-  while (j + 8 <= n) {
-    const int stop = (j + kWideAccBlock < n) ? j + kWideAccBlock : n;
-    for (; j + 8 <= stop; j += 8) {
-      float w[8];
+    for (int s = 0; s < TS; ++s) tot[s] = acc[s] = 0.f;
+    int j = j0;
+    while (j + 8 <= n) {
+      const int stop = (j + kWideAccBlock < n) ? j + kWideAccBlock : n;
+      for (; j + 8 <= stop; j += 8) {
+        float w[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) w[q] = __ldg(wcol + static_cast<size_t>(j + q) * r_pad);
+        for (int q = 0; q < 8; ++q) w[q] = __ldg(wcol + static_cast<size_t>(j + q) * r_pad);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) wide_fma_col<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), acc);
+        for (int q = 0; q < 8; ++q) wide_fma_col<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), acc);
+      }
+#pragma unroll
+      for (int s = 0; s < TS; ++s) {
+        tot[s] += acc[s];
+        acc[s] = 0.f;
+      }
     }
+    for (; j < n; ++j) wide_fma_col<TS>(__ldg(wcol + static_cast<size_t>(j) * r_pad), us4 + static_cast<size_t>(j) * (TS / 4), acc);
 #pragma unroll
-    for (int s = 0; s < TS; ++s) {
-      tot[s] += acc[s];
-      acc[s] = 0.f;
-    }
+    for (int s = 0; s < TS; ++s) tot[s] += acc[s];
   }
-  for (; j < n; ++j) wide_fma_col<TS>(__ldg(wcol + static_cast<size_t>(j) * r_pad), us4 + static_cast<size_t>(j) * (TS / 4), acc);
-#pragma unroll
-  for (int s = 0; s < TS; ++s) tot[s] += acc[s];
 }
 
 // Two consecutive rows per lane (wcol2 points at the lane's row pair, 8-byte aligned): per column one 8-byte load and
@@ -147,35 +147,35 @@ __device__ __forceinline__ void wide_dot2(const float* __restrict__ wcol2, int r
     for (; j < n; ++j)
       wide_fma_col2<TS>(__ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j) * r_pad)),
                         us4 + static_cast<size_t>(j) * (TS / 4), tot0, tot1);
-    return;
-  }
-  float acc0[TS], acc1[TS];
+  } else {
+    float acc0[TS], acc1[TS];
 #pragma unroll
-  for (int s = 0; s < TS; ++s) tot0[s] = tot1[s] = acc0[s] = acc1[s] = 0.f;
-  int j = j0;
-  while (j + U <= n) {
-    const int stop = (j + kWideAccBlock < n) ? j + kWideAccBlock : n;
-    for (; j + U <= stop; j += U) {
-      float2 w[U];
+    for (int s = 0; s < TS; ++s) tot0[s] = tot1[s] = acc0[s] = acc1[s] = 0.f;
+    int j = j0;
+    while (j + U <= n) {
+      const int stop = (j + kWideAccBlock < n) ? j + kWideAccBlock : n;
+      for (; j + U <= stop; j += U) {
+        float2 w[U];
 #pragma unroll
-      for (int q = 0; q < U; ++q) w[q] = __ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j + q) * r_pad));
+        for (int q = 0; q < U; ++q) w[q] = __ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j + q) * r_pad));
 #pragma unroll
-      for (int q = 0; q < U; ++q) wide_fma_col2<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), acc0, acc1);
+        for (int q = 0; q < U; ++q) wide_fma_col2<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), acc0, acc1);
+      }
+#pragma unroll
+      for (int s = 0; s < TS; ++s) {
+        tot0[s] += acc0[s];
+        tot1[s] += acc1[s];
+        acc0[s] = acc1[s] = 0.f;
+      }
     }
+    for (; j < n; ++j)
+      wide_fma_col2<TS>(__ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j) * r_pad)),
+                        us4 + static_cast<size_t>(j) * (TS / 4), acc0, acc1);
 #pragma unroll
     for (int s = 0; s < TS; ++s) {
       tot0[s] += acc0[s];
       tot1[s] += acc1[s];
-      acc0[s] = acc1[s] = 0.f;
     }
-  }
-  for (; j < n; ++j)
-    wide_fma_col2<TS>(__ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j) * r_pad)),
-                      us4 + static_cast<size_t>(j) * (TS / 4), acc0, acc1);
-#pragma unroll
-  for (int s = 0; s < TS; ++s) {
-    tot0[s] += acc0[s];
-    tot1[s] += acc1[s];
   }
 }
 
