@@ -484,6 +484,29 @@ def run_b200(args, rank, local_rank, world):
     except Exception as exc:  # noqa: BLE001 - informational
         link["error"] = repr(exc)[:120]
 
+    # ... and what the step's copies alone cost when both directions run at once, as they do in the step: H2D of v and
+    # g_y on one stream, D2H of y and g_v on another, no kernels (the floor of ANY host-buffer implementation on this box)
+    try:
+        h = host[0]
+        s0 = bench.sets[0]
+        sin, sout = torch.cuda.Stream(device), torch.cuda.Stream(device)
+
+        def copies_only(i):
+            cur = torch.cuda.current_stream(device)
+            sin.wait_stream(cur)
+            sout.wait_stream(cur)
+            with torch.cuda.stream(sin):
+                s0["v"].copy_(h["v"], non_blocking=True)
+                s0["gy"].copy_(h["gy"], non_blocking=True)
+            with torch.cuda.stream(sout):
+                h["y"].copy_(s0["y"], non_blocking=True)
+                h["gv"].copy_(s0["gv"], non_blocking=True)
+            cur.wait_stream(sin)
+            cur.wait_stream(sout)
+        link["step_copies_both_directions_ms"] = bench.time_loop_median(copies_only, 20, 5, groups=3)
+    except Exception as exc:  # noqa: BLE001 - informational
+        link["copies_error"] = repr(exc)[:120]
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -511,8 +534,11 @@ def run_b200(args, rank, local_rank, world):
                                       "step's kernels and copy-out; wall clock, every step's H2D and D2H inside"},
                 "copy_floor_ms": (batch * 4 * (n + k) / 1e6 / max(min(link.get("h2d_gbs", 0.0), link.get("d2h_gbs", 0.0)), 1e-9)
                                   if "h2d_gbs" in link and "d2h_gbs" in link else None),
+                "copies_only_ms": link.get("step_copies_both_directions_ms"),
                 "path": "ConstraintModule.forward_backward_host -> rayen_forward_backward_host_f32 "
-                        "(pinned host buffers; copy-in, kernels and copy-out on three streams, synchronous per step)"},
+                        "(pinned host buffers; copy-in, kernels and copy-out on three streams, replayed from a CUDA graph, "
+                        "synchronous per step); copy_floor_ms = bytes of one direction / the slower direction's solo rate, "
+                        "copies_only_ms = the step's four copies with both directions busy and no kernels"},
         "gpu_launches": int(launches),
         "launch_floor_ms": floor_ms,
         "module_autograd": {"value": world * batch / (ms_module * 1e-3), "ms_per_step": ms_module,

@@ -580,7 +580,7 @@ __device__ __forceinline__ void lw_write_y(const LwCtx& C, float* __restrict__ y
       const float* nrow = C.nmat + i * C.nstride;
       for (int a = 0; a < C.n; ++a) rho = fmaf(__ldg(nrow + a), us[4 * a + m], rho);
     }
-    yrow[i] = fmaf(alpha, rho, __ldg(C.y0 + i));
+    yrow[i] = fmaf(alpha, rho, C.y0[i]);
   }
 }
 
@@ -722,7 +722,7 @@ __device__ __forceinline__ void lw_process_chunk(const LwCtx& C, const long long
 constexpr int kLwThreads = 256;
 
 __host__ __device__ constexpr size_t lmi_warp_smem_bytes(int n, int threads) {
-  return 64 + static_cast<size_t>(n) * kLwMatWords * 4 + static_cast<size_t>(threads / 32) * kLwScratch * 4;
+  return 192 + static_cast<size_t>(n) * kLwMatWords * 4 + static_cast<size_t>(threads / 32) * kLwScratch * 4;
 }
 
 // Samples come from the work list of the linear/quadratic/SOC kernel (list mode) or are the whole batch (dense mode,
@@ -741,13 +741,15 @@ __global__ void __launch_bounds__(kLwThreads, 1)
   pdl_launch_dependents();  // the fail list's consumer may be scheduled; it waits before it reads
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  float* fw = reinterpret_cast<float*>(smem_raw + 64);
+  float* y0s = reinterpret_cast<float*>(smem_raw + 64);   // y0 (k <= 32 words): read by every sample's scale step
+  float* fw = reinterpret_cast<float*>(smem_raw + 192);
   const int fw_words = P.n * kLwMatWords;
   LW_GT(0);
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);
     fence_mbar_init();
   }
+  if (threadIdx.x < 32) y0s[threadIdx.x] = (static_cast<int>(threadIdx.x) < P.k) ? P.blob[P.off_y0 + threadIdx.x] : 0.f;
   __syncthreads();
   pdl_wait();  // launched behind the linear/quadratic/SOC kernel: its kappa / active / work list must be complete
   const long long total = work_list ? static_cast<long long>(ld_after_wait(work_count)) : B;
@@ -762,7 +764,7 @@ __global__ void __launch_bounds__(kLwThreads, 1)
   LwCtx C;
   C.FW = fw;
   C.scr = fw + fw_words + warp * kLwScratch;
-  C.y0 = P.blob + P.off_y0;
+  C.y0 = (P.k <= 32) ? y0s : P.blob + P.off_y0;  // (more ambient coordinates than that: from L1/L2)
   C.nmat = P.blob + P.off_nmat;
   C.n = P.n; C.k = P.k; C.nstride = P.np + 4; C.n_is_identity = P.n_is_identity; C.mode = mode;
   bool staged = false;

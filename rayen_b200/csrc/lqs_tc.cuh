@@ -4,7 +4,7 @@
 // vectors phi / c_z / h, the rows of the triangular factors G and R (and of the pruning bound's factor).
 // Stacked, they are ONE matrix W [rows x K] (K = n padded to 8/16/32), and the work of a tile of 128 samples
 // is the GEMM  D = U W'  with U [128 x K].  This kernel runs that GEMM with tcgen05.mma (kind::tf32,
-// M = 128, N = 96, K = 8 per instruction), error-compensated as 3xTF32
+// M = 128, N <= 128, K = 8 per instruction), error-compensated as 3xTF32
 //     U W' ~= U_hi W_hi' + U_lo W_hi' + U_hi W_lo'        (drops only the 2^-22 term U_lo W_lo')
 // with the accumulator in tensor memory.  The TMEM layout -- lane = sample, column = constraint row -- is
 // exactly what the reduction needs: each epilogue thread owns one sample, reads its row of D with
@@ -16,6 +16,13 @@
 //   warp 8     TMA producer: streams the 128-row panels of W (hi + lo) through a 4-stage shared-memory ring
 //   warps 9,10 MMA issuers (one elected lane each, one per sample tile); warp 9 owns the TMEM allocation
 // Pipelines: W ring full/empty, TMEM accumulator full/empty (two 128-column buffers per sample tile), U ready.
+//
+// Panels.  128 rows of D are a panel.  The items (quadratics, cones, the LMI pruning bound) come in BATCHES of up to 12:
+// their upper-triangular factors are cut into blocks of 8 rows, and block j of all the items of a batch is one panel
+// (8 x items rows) whose columns left of 8j are zero -- its GEMM starts at K step j (10 instead of 16 K steps per batch at
+// K = 32) and only those K chunks of W are copied into the ring.  Block 0 also carries the two header rows of every item
+// (phi_z | c_z | t, then h).  An epilogue thread keeps the running sum of squares of every item of the batch and forms
+// the kappas when the last block has arrived.
 #pragma once
 #include "common.cuh"
 #include "lqs.cuh"
@@ -33,7 +40,12 @@ constexpr int kTcPanel = 128;  // rows of W per panel = MMA N (N = 128: 65 cycle
 constexpr int kTcStages = 4;
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;  // + TMA warp + two MMA-issuing warps (one per sample tile)
-constexpr int kTcTableWords = 32;  // per panel: kind, first row, 8 x (item type, item index), pad to 24, 8 item scalars
+// per panel (plan.py): int32 {kind 0 linear | 1 batch block, first row | block index j, MMA N, first K step, items in the
+// batch, last block of the batch, column of the header rows, cone mask | (1 + bound slot) << 16}, 12 x (item type,
+// item index) at words 8.., then 12 item
+// scalars (float: A of a cone, r of the bound) at words 32.. and their reciprocals at words 44..
+constexpr int kTcTableWords = 64;
+constexpr int kTcBatchItems = 12;  // items per batch: 8 x 12 = 96 factor rows per block panel + 24 header rows in block 0
 
 // ----------------------------------------------------------------------------- tcgen05 / mbarrier helpers
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -80,6 +92,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* r) {
                : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float tc_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float tc_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -124,14 +146,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                           float* __restrict__ kappa_out, int* __restrict__ active_out, long long B, int mode,
                           int lmi_follows, int prune, int* __restrict__ work_list, int* __restrict__ work_count,
                           const MapArgs M) {
-  constexpr int CH = 8;                     // header rows of an item (phi | c_z, h | t), padded
-  constexpr int IW = CH + KP;               // rows (= TMEM columns) per item
-  constexpr int IPP = kTcPanel / IW;        // items per panel
+  constexpr int IB = kTcBatchItems;         // items per batch
   constexpr int KC = KP / 4;                // 16-byte chunks along K
   constexpr int A_TILE = KP * 128;          // floats of one U operand tile (hi or lo)
   constexpr int W_TILE = KP * kTcPanel;     // floats of one W operand tile (hi or lo)
   constexpr uint32_t LBO_A = (128 / 8) * 128, LBO_W = (kTcPanel / 8) * 128, SBO = 128;
-  constexpr uint32_t IDESC = umma_idesc_tf32(128, kTcPanel);
 
   pdl_launch_dependents();  // the LMI kernel behind this one may start scheduling its CTAs (it waits before it reads)
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -190,14 +209,25 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const uint32_t stage = g % kTcStages, use = g / kTcStages;
           mbar_wait(&w_empty[stage], (use & 1) ^ 1);
           TC_STAMP(8 * p + 7);
-          mbar_expect_tx(&w_full[stage], 2 * W_TILE * 4);
-          // several smaller bulk copies keep more requests in flight than one 24 KB copy
-          constexpr int PIECES = (KP >= 32) ? 4 : 2;
-          constexpr int PIECE = 2 * W_TILE / PIECES;
+          // only the K chunks the panel's GEMM reads: from K step ks0 on (the leading columns of a block panel are zero)
+          const int ks0 = reinterpret_cast<const int*>(table + p * kTcTableWords)[3];
+          const uint32_t skip = static_cast<uint32_t>(2 * ks0) * (LBO_W / 4);   // floats of one operand that are not needed
+          const uint32_t part = W_TILE - skip;                                    // floats of W_hi (and of W_lo) to copy
+          mbar_expect_tx(&w_full[stage], 2 * part * 4);
+          const float* src = w_src + static_cast<size_t>(p) * 2 * W_TILE;
+          float* dst = w_ring + stage * 2 * W_TILE;
+          // several smaller bulk copies keep more requests in flight than one large copy
+          const uint32_t half = (part / 2) & ~3u;
 #pragma unroll
-          for (int c = 0; c < PIECES; ++c)
-            bulk_g2s(w_ring + stage * 2 * W_TILE + c * PIECE, w_src + static_cast<size_t>(p) * 2 * W_TILE + c * PIECE,
-                     PIECE * 4, &w_full[stage]);
+          for (int o = 0; o < 2; ++o) {       // W_hi, W_lo
+            const uint32_t base = o * W_TILE + skip;
+            if (half >= 1024) {
+              bulk_g2s(dst + base, src + base, half * 4, &w_full[stage]);
+              bulk_g2s(dst + base + half, src + base + half, (part - half) * 4, &w_full[stage]);
+            } else {
+              bulk_g2s(dst + base, src + base, part * 4, &w_full[stage]);
+            }
+          }
         }
       }
     }
@@ -222,17 +252,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           TC_STAMP(8 * p + 2);
           const uint32_t w_hi = smem_u32(w_ring + stage * 2 * W_TILE), w_lo = w_hi + W_TILE * 4;
           {
+            const int* pt = reinterpret_cast<const int*>(table + p * kTcTableWords);
+            const uint32_t idesc = umma_idesc_tf32(128, pt[2]);   // N of this panel (a multiple of 16, <= 128)
+            const int ks0 = pt[3];                                // first K step: the columns before it are zero
             const uint32_t u_hi = smem_u32(a_tiles + (2 * t) * A_TILE), u_lo = u_hi + A_TILE * 4;
             const uint32_t d_tmem = tmem_base + (2 * t + buf) * kTcPanel;
 #pragma unroll
             for (int ks = 0; ks < KP / 8; ++ks) {
-              const uint64_t d_uhi = umma_smem_desc(u_hi + 2 * ks * LBO_A, LBO_A, SBO);
-              const uint64_t d_ulo = umma_smem_desc(u_lo + 2 * ks * LBO_A, LBO_A, SBO);
-              const uint64_t d_whi = umma_smem_desc(w_hi + 2 * ks * LBO_W, LBO_W, SBO);
-              const uint64_t d_wlo = umma_smem_desc(w_lo + 2 * ks * LBO_W, LBO_W, SBO);
-              umma_tf32(d_tmem, d_uhi, d_whi, IDESC, ks > 0 ? 1u : 0u);
-              umma_tf32(d_tmem, d_ulo, d_whi, IDESC, 1u);
-              umma_tf32(d_tmem, d_uhi, d_wlo, IDESC, 1u);
+              if (ks >= ks0) {
+                const uint64_t d_uhi = umma_smem_desc(u_hi + 2 * ks * LBO_A, LBO_A, SBO);
+                const uint64_t d_ulo = umma_smem_desc(u_lo + 2 * ks * LBO_A, LBO_A, SBO);
+                const uint64_t d_whi = umma_smem_desc(w_hi + 2 * ks * LBO_W, LBO_W, SBO);
+                const uint64_t d_wlo = umma_smem_desc(w_lo + 2 * ks * LBO_W, LBO_W, SBO);
+                umma_tf32(d_tmem, d_uhi, d_whi, idesc, ks > ks0 ? 1u : 0u);
+                umma_tf32(d_tmem, d_ulo, d_whi, idesc, 1u);
+                umma_tf32(d_tmem, d_uhi, d_wlo, idesc, 1u);
+              }
             }
           }
           TC_STAMP(8 * p + 3);
@@ -282,6 +317,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       int tag = make_tag(RAYEN_FAM_NONE, 0);
       float ub = 3.0e38f;  // pruning bound of the LMI (stays +inf without one)
       int soc_fix = -1;    // a cone whose kappa is ill-conditioned for this sample (see soc_kappa_fp32)
+      int win = -1;        // (panel, slot) of the binding item, if an item binds (looked up in the table afterwards)
+      float ss[IB], hd[2 * IB];  // running |T u|^2 and the two header dot products of every item of the current batch
+#pragma unroll
+      for (int i = 0; i < IB; ++i) ss[i] = hd[2 * i] = hd[2 * i + 1] = 0.f;
       for (int p = 0; p < n_panels; ++p, ++g) {
         const uint32_t buf = g & 1, buf_use = g >> 1;
         if (warp == 0 && lane == 0) TC_STAMP(8 * p + 4);
@@ -301,12 +340,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             tmem_wait_ld();
             // max first (3-input max tree), index only when the running best actually moves: the best of a
             // sample changes O(log rows) times, so the per-column compare/select chain is almost never needed
-            float mx = x[0];
+            float m0 = x[0], m1 = x[1], m2 = x[2], m3 = x[3];
 #pragma unroll
-            for (int j = 1; j + 1 < 64; j += 2) mx = fmaxf(mx, fmaxf(x[j], x[j + 1]));
-            mx = fmaxf(mx, x[63]);
+            for (int j = 4; j < 64; j += 4) {
+              m0 = fmaxf(m0, x[j]);
+              m1 = fmaxf(m1, x[j + 1]);
+              m2 = fmaxf(m2, x[j + 2]);
+              m3 = fmaxf(m3, x[j + 3]);
+            }
+            const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
             if (mx > best) {
               best = mx;
+              win = -1;
               int arg = 0;
 #pragma unroll
               for (int j = 63; j >= 0; --j)
@@ -315,43 +360,74 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
           }
         } else {
-          // ---- items, one after the other: 8 header rows (phi | c_z, h | t) then the KP rows of a triangular factor
+          // ---- block j of a batch of items: 8 columns per item (rows 8j..8j+7 of its triangular factor times u); block 0
+          // also holds the items' header dot products behind them
+          const int jb = pt[1], nitems = pt[4];
 #pragma unroll
-          for (int sl = 0; sl < IPP; ++sl) {
-            const int type = pt[2 + 2 * sl], idx = pt[3 + 2 * sl];
-            if (type == 0) continue;  // the table is the same for every thread
-            float xi[IW];
+          for (int g = 0; g < IB * 8 / 48; ++g) {      // 48 columns = 6 items at a time
+            if (48 * g < 8 * nitems) {                  // (the table is the same for every thread)
+              float x[48];
 #pragma unroll
-            for (int c = 0; c < IW / 8; ++c) tmem_ld8(taddr + sl * IW + 8 * c, xi + 8 * c);
+              for (int c = 0; c < 3; ++c) tmem_ld16(taddr + 48 * g + 16 * c, x + 16 * c);
+              tmem_wait_ld();
+#pragma unroll
+              for (int q = 0; q < 6; ++q) {
+                float a = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) a = fmaf(x[8 * q + c], x[8 * q + c], a);
+                ss[6 * g + q] = (jb == 0) ? a : ss[6 * g + q] + a;
+              }
+            }
+          }
+          if (jb == 0) {
+            const int hoff = pt[6];
+#pragma unroll
+            for (int c = 0; c < 2 * IB / 8; ++c) {
+              if (8 * c < 2 * nitems) tmem_ld8(taddr + hoff + 8 * c, hd + 8 * c);
+            }
             tmem_wait_ld();
-            const float scal = table[p * kTcTableWords + 24 + sl];
-            const float* h = xi;
-            const float* x = xi + CH;
-            float ss = 0.f;
+          }
+          if (pt[5]) {
+            // ---- last block: the kappas of the batch, in item order (the reference's evaluation order).
+            // Branch-free and without loads: item types come as a bit mask, the winner is remembered as a (panel, slot)
+            // number that is looked up once after the panel loop, square roots / reciprocals are single MUFU instructions
+            // (~1 ulp; the IEEE sqrtf / division expand to a fix-up behind a branch to a slow path).  As a chain of
+            // `if (type == ...)` with a table load per item this was the longest phase of the kernel (device-clock
+            // trace: 2300-5600 cycles per batch of 11 items, against ~700 for draining a panel).  One ulp is well inside
+            // what the 3xTF32 dot products carry (3e-7).
+            const int meta = pt[7];
+            const int bslot = (meta >> 16) - 1;   // slot of the LMI pruning bound in this batch (-1: none)
+            float b_mean = 0.f, b_nrm = 0.f, b_fac = 0.f;
 #pragma unroll
-            for (int j = 0; j < KP; ++j) ss = fmaf(x[j], x[j], ss);
-            if (type == RAYEN_FAM_QUAD) {          // kappa = phi_z.u + |G u|       (reference :360-381)
-              const float kap = h[0] + sqrtf(ss);
-              if (kap > best) {
-                best = kap;
-                tag = make_tag(RAYEN_FAM_QUAD, idx);
-              }
-            } else if (type == RAYEN_FAM_SOC) {    // largest root                  (reference :383-399)
-              const float cq = fmaf(-h[0], h[0], ss);
-              const float kap = soc_root(scal, h[1], cq, nullptr);
-              // nearly tangent ray (the discriminant cancels to < 1 % of its terms) that can matter for this sample:
-              // the first such cone is left out of the running max and evaluated on the FP32 pipe after the panel loop
-              if (soc_fix < 0 && KP == P.np && fmaf(h[1], h[1], scal * cq) < 1e-2f * h[1] * h[1] && kap > 0.9f * best) {
-                soc_fix = idx;
-              } else if (kap > best) {
-                best = kap;
-                tag = make_tag(RAYEN_FAM_SOC, idx);
-              }
-            } else {                               // Wolkowicz-Styan bound of lambda_max (LMI pruning)
-              // ss = |T_c u|^2 with T_c the factor of the CENTRED Gram matrix: the deviation term is a sum of
-              // squares, nothing cancels when S~(u) is close to a multiple of the identity
-              const float inv_r = 1.0f / scal;
-              ub = lmi_upper_bound(h[0] * inv_r, sqrtf((scal - 1.0f) * inv_r * ss), P.lmi_bound_margin);
+            for (int sl = 0; sl < IB; ++sl) {
+              const float scal = table[p * kTcTableWords + 32 + sl], inv_scal = table[p * kTcTableWords + 44 + sl];
+              const float h0 = hd[2 * sl], h1 = hd[2 * sl + 1], sq = ss[sl];
+              const float nrm = tc_sqrt(sq);                          // |G u| (quadratic), |T_c u| (bound)
+              const float cq = fmaf(-h0, h0, sq);
+              const float disc = fmaf(h1, h1, scal * cq);
+              const float root = tc_sqrt(fmaxf(disc, 0.f));
+              // kappa = phi_z.u + |G u| (reference :360-381), or the largest root of the cone (:383-399) in the
+              // cancellation-free form of soc_root (lqs.cuh): (h1 + root)/A, or c'/(root - h1) when h1 < 0
+              const bool soc = (meta >> sl) & 1;
+              const float ksoc = (h1 >= 0.f) ? (h1 + root) * inv_scal : cq * tc_rcp(root - h1);
+              float kap = soc ? ksoc : h0 + nrm;
+              kap = (sl >= nitems || sl == bslot) ? -1.f : kap;       // no item here: never wins (best >= 0)
+              // (selects, not branches: a branch per item serialises the items' MUFU latencies)
+              b_mean = (sl == bslot) ? h0 * inv_scal : b_mean;
+              b_nrm = (sl == bslot) ? nrm : b_nrm;
+              b_fac = (sl == bslot) ? (scal - 1.0f) * inv_scal : b_fac;
+              // a nearly tangent cone (the discriminant cancels to < 1 % of its terms) that can matter for this sample: the
+              // first such cone is left out of the running max and evaluated on the FP32 pipe after the panel loop
+              const bool fix = soc && soc_fix < 0 && KP == P.np && disc < 1e-2f * h1 * h1 && kap > 0.9f * best;
+              const bool take = !fix && kap > best;
+              soc_fix = fix ? p * 16 + sl : soc_fix;
+              best = take ? kap : best;
+              win = take ? p * 16 + sl : win;
+            }
+            if (bslot >= 0) {
+              // Wolkowicz-Styan bound of lambda_max (LMI pruning); b_nrm = |T_c u| with T_c the factor of the CENTRED Gram
+              // matrix: the deviation term is a sum of squares, nothing cancels when S~(u) is close to a multiple of I
+              ub = lmi_upper_bound(b_mean, b_nrm * tc_sqrt(b_fac), P.lmi_bound_margin);
             }
           }
         }
@@ -361,12 +437,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (lane == 0) mbar_arrive(&d_empty[buf]);
       }
 
+      // ---- which item was that (type and index within its family)
+      if (win >= 0) {
+        const int* wt = reinterpret_cast<const int*>(table + (win >> 4) * kTcTableWords) + 8 + 2 * (win & 15);
+        tag = make_tag(wt[0], wt[1]);
+      }
       // ---- the rare near-tangent cone that was left out above, in FP32
       if (soc_fix >= 0) {
-        const float kap = soc_kappa_fp32<KP>(P.blob + P.off_soc + soc_fix * P.soc_stride, u);
+        const int cone = reinterpret_cast<const int*>(table + (soc_fix >> 4) * kTcTableWords)[9 + 2 * (soc_fix & 15)];
+        const float kap = soc_kappa_fp32<KP>(P.blob + P.off_soc + cone * P.soc_stride, u);
         if (kap > best) {
           best = kap;
-          tag = make_tag(RAYEN_FAM_SOC, soc_fix);
+          tag = make_tag(RAYEN_FAM_SOC, cone);
         }
       }
       // ---- merge / prune / scale step for this thread's sample

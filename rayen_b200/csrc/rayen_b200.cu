@@ -53,10 +53,24 @@ struct rayen_plan {
   // host-buffer path only (rayen_forward_backward_host_f32): copy streams and events, created on first use and
   // serialised by host_mu -- the device-pointer entry points never touch them, so the plan stays re-entrant there
   std::mutex* host_mu;
-  cudaStream_t host_in, host_out;
+  cudaStream_t host_in, host_out, host_main;  // copy-in, copy-out, kernels of the synchronous step
+  cudaEvent_t host_fork, host_join;           // caller's stream -> host_main and back
   cudaEvent_t host_ev[4][2 * 8 + 2];  // per slot: v_c / gy_c landed (reused: forward_c / backward_c done), start, done
   bool host_ready;
   int host_chunks;  // 0 = automatic (RAYEN_HOST_CHUNKS overrides)
+  // the synchronous host-buffer step as an instantiated CUDA graph per (buffers, batch): one cudaGraphLaunch instead of
+  // ~25 API calls per step (the step moves 2 x 8 MB over PCIe in ~0.2 ms: submission cost shows)
+  struct HostGraph {
+    const void *v, *gy, *y, *gv, *ws;
+    int64_t B;
+    cudaStream_t stream;
+    cudaGraphExec_t exec;
+    unsigned long long used;
+  };
+  HostGraph host_graphs[8];
+  int host_graph_count;
+  unsigned long long host_graph_clock;
+  bool host_graph_on;
 };
 
 static thread_local char g_err[512] = "";
@@ -316,6 +330,7 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
     p->host_chunks = env ? atoi(env) : 0;
     if (p->host_chunks < 0 || p->host_chunks > 8) p->host_chunks = 0;
   }
+  p->host_graph_on = !(getenv("RAYEN_HOST_GRAPH") && atoi(getenv("RAYEN_HOST_GRAPH")) == 0);
   p->sm_count = prop.multiProcessorCount;
   p->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
   cudaError_t e = cudaMalloc(&p->d_blob, d->blob_words * sizeof(float));
@@ -414,7 +429,10 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
     p->lmi_warp_ok = p->lmi_warp_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
     p->lmi_warp_mode = 2;
     p->lmi_warp_filter = true;
-    p->lmi_warp_solves = 1;
+    // Unlimited by default: every warp solves the failing samples of its own chunks, and there is no second launch.
+    // Failures are rare where the filter pays (cfg5: 1 in 2100) and spread evenly where they are not (chunks are dealt
+    // round-robin); RAYEN_LMI_WARP_SOLVES=k caps the solves per warp and hands the rest to a second launch.
+    p->lmi_warp_solves = 0x7fffffff;
     if (const char* sv = getenv("RAYEN_LMI_WARP_SOLVES")) p->lmi_warp_solves = atoi(sv) < 0 ? 0 : atoi(sv);
     const char* env = getenv("RAYEN_LMI_WARP");
     if (env && atoi(env) >= 0 && atoi(env) <= 2) p->lmi_warp_mode = atoi(env);
@@ -516,6 +534,7 @@ static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** o
   p->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
   p->wide = true;
   p->has_lqs = true;
+  p->host_graph_on = !(getenv("RAYEN_HOST_GRAPH") && atoi(getenv("RAYEN_HOST_GRAPH")) == 0);
   p->wide_fwd_smem_bytes[0] = wide_fwd_smem_bytes(w.n, 8);
   p->wide_fwd_smem_bytes[1] = wide_fwd_smem_bytes(w.n, 16);
   p->wide_bwd_smem_bytes = wide_bwd_smem_bytes(w.n);
@@ -561,9 +580,13 @@ extern "C" void rayen_plan_destroy(rayen_plan_t* p) {
   cudaGetDevice(&prev);
   cudaSetDevice(p->device);
   cudaFree(p->d_blob);
+  for (int i = 0; i < p->host_graph_count; ++i) cudaGraphExecDestroy(p->host_graphs[i].exec);
   if (p->host_ready) {
     cudaStreamDestroy(p->host_in);
     cudaStreamDestroy(p->host_out);
+    cudaStreamDestroy(p->host_main);
+    cudaEventDestroy(p->host_fork);
+    cudaEventDestroy(p->host_join);
     for (auto& slot_ev : p->host_ev)
       for (cudaEvent_t ev : slot_ev) cudaEventDestroy(ev);
   }
@@ -906,9 +929,9 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
     static const bool pdl_on = !(getenv("RAYEN_PDL") && atoi(getenv("RAYEN_PDL")) == 0);
     const bool behind_lqs = pdl_on && (stage_mask & 1) && run_lqs;
     if (use_warp) {
-      // The filter kernel settles the samples whose LMI provably cannot bind, solves up to `solves_per_warp` of the
-      // others per warp itself (latency: usually there are only a handful) and leaves the rest in the fail list (the
-      // region of the backward work list, free until the backward call) for a second launch (usually an empty list).
+      // The filter kernel settles the samples whose LMI provably cannot bind and solves the others itself (one warp per
+      // matrix).  With a cap on the solves per warp (RAYEN_LMI_WARP_SOLVES) the rest goes to a fail list (the region of
+      // the backward work list, free until the backward call) and a second launch of the same kernel.
       int* fail_list = reinterpret_cast<int*>(static_cast<char*>(workspace) + 256 + ws_list_bytes(B));
       if (!behind_lqs) e = cudaMemsetAsync(counters + 2, 0, sizeof(int), stream);  // else zeroed with the other counters
       // chunks of 4 samples, dealt round-robin to the CTAs (the list length is only known on the device)
@@ -936,8 +959,8 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
                                       filt, budget, fail_list, fcnt)
                  : cudaLaunchKernelEx(&cfg, lmi_forward_warp_kernel<false>, d, v, ldv_, y, kappa, active, B_, mode, list, cnt,
                                       dk, filt, budget, fail_list, fcnt);
-      g_launches.fetch_add(1);
-      if (e == cudaSuccess) {
+      if (e == cudaSuccess && budget != 0x7fffffff) {
+        g_launches.fetch_add(1);
         // the same kernel once more on the fail list, filter off, no budget: whoever solves a sample runs the same
         // arithmetic, so results do not depend on how the batch was cut into chunks (bit-identical across pruning
         // on / off, host-buffer chunking, list order)
@@ -1132,12 +1155,11 @@ static int host_chunk_count(const rayen_plan* p, int64_t B) {
 
 constexpr int kHostSlots = 4;
 
-// Queues one forward+backward step on host buffers (see the header).  join_and_sync: order the caller's stream after
-// the copy-out and block the host (the synchronous entry point); otherwise return as soon as everything is queued and
-// leave completion to rayen_forward_backward_host_wait(slot).
-static int host_step(rayen_plan* p, const float* v_host, const float* gy_host, float* y_host, float* gv_host, int64_t B,
-                     void* workspace, cudaStream_t stream, int slot, bool join_and_sync) {
-  std::lock_guard<std::mutex> guard(*p->host_mu);
+// Enqueues one forward+backward step on host buffers: copy-in on p->host_in, kernels on `main`, copy-out on
+// p->host_out (see the header), and finally makes `main` wait for the last copy-out.  Nothing here synchronises, so
+// the whole thing can be stream-captured with `main` as the origin stream.
+static int host_enqueue(rayen_plan* p, const float* v_host, const float* gy_host, float* y_host, float* gv_host, int64_t B,
+                        void* workspace, cudaStream_t main, int slot, bool order_after_main, bool join, bool trace) {
   const int64_t n = p->dev.n, k = p->dev.k;
   char* w = static_cast<char*>(workspace);
   float* v = reinterpret_cast<float*>(w); w += round256(B * n * 4);
@@ -1146,25 +1168,7 @@ static int host_step(rayen_plan* p, const float* v_host, const float* gy_host, f
   float* gv = reinterpret_cast<float*>(w); w += round256(B * n * 4);
   float* kappa = reinterpret_cast<float*>(w); w += round256(B * 4);
   int32_t* active = reinterpret_cast<int32_t*>(w); w += round256(B * 4);
-  int prev = 0;
-  RAYEN_CUDA(cudaGetDevice(&prev));
-  if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
   cudaError_t e = cudaSuccess;
-  if (!p->host_ready) {
-    e = cudaStreamCreateWithFlags(&p->host_in, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->host_out, cudaStreamNonBlocking);
-    for (auto& slot_ev : p->host_ev)
-      for (cudaEvent_t& ev : slot_ev)
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    if (e != cudaSuccess) {
-      if (prev != p->device) cudaSetDevice(prev);
-      return cuda_fail(e, "creating the copy streams of the host-buffer path");
-    }
-    p->host_ready = true;
-  }
-  // RAYEN_HOST_TRACE=1: print the device-side timeline of a synchronous call (development aid, adds event records)
-  static const bool trace_env = getenv("RAYEN_HOST_TRACE") && atoi(getenv("RAYEN_HOST_TRACE")) != 0;
-  const bool trace = trace_env && join_and_sync;
   cudaEvent_t tev[40];
   const char* tname[40];
   int ntev = 0;
@@ -1180,18 +1184,18 @@ static int host_step(rayen_plan* p, const float* v_host, const float* gy_host, f
   cudaEvent_t* ev_g = p->host_ev[slot] + kHostMaxChunks;   // [c]     gy_c is on the device, later reused: backward_c done
   cudaEvent_t ev_start = p->host_ev[slot][2 * kHostMaxChunks], ev_done = p->host_ev[slot][2 * kHostMaxChunks + 1];
   int rc = 0;
-  mark(stream, "start");
-  if (join_and_sync) {
-    // synchronous call: everything is ordered after what the caller queued on `stream` (e.g. an earlier use of the
-    // workspace by the caller's own kernels)
-    e = cudaEventRecord(ev_start, stream);
+  mark(main, "start");
+  if (order_after_main) {
+    // everything is ordered after what is queued on `main` (e.g. an earlier use of the workspace)
+    e = cudaEventRecord(ev_start, main);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(p->host_in, ev_start, 0);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(p->host_out, ev_start, 0);
   }
-  // submitted steps: the only earlier user of this slot's workspace and host buffers is the previous step of the
-  // same slot, which the caller has waited for (the contract of rayen_forward_backward_host_submit_f32).  The copy-in
-  // therefore starts at once -- under the kernels of the step before -- instead of behind everything queued on
-  // `stream`; the kernels themselves are ordered by `stream`, the copy-out by the events below.
+  // submitted steps (order_after_main == false): the only earlier user of this slot's workspace and host buffers is the
+  // previous step of the same slot, which the caller has waited for (the contract of
+  // rayen_forward_backward_host_submit_f32).  The copy-in therefore starts at once -- under the kernels of the step
+  // before -- instead of behind everything queued on `main`; the kernels themselves are ordered by `main`, the copy-out
+  // by the events below.
   void* ws_c[kHostMaxChunks];
   int64_t lo[kHostMaxChunks], cnt[kHostMaxChunks];
   int used = 0;
@@ -1216,24 +1220,24 @@ static int host_step(rayen_plan* p, const float* v_host, const float* gy_host, f
     mark(p->host_in, "h2d gy");
   }
   for (int c = 0; c < used && e == cudaSuccess && rc == 0; ++c) {
-    e = cudaStreamWaitEvent(stream, ev_v[c], 0);
+    e = cudaStreamWaitEvent(main, ev_v[c], 0);
     if (e == cudaSuccess)
       rc = rayen_forward_f32(p, v + lo[c] * n, n, y + lo[c] * k, kappa + lo[c], active + lo[c], cnt[c],
-                             RAYEN_MODE_RAYEN, 1, ws_c[c], stream);
-    mark(stream, "forward");
-    if (e == cudaSuccess && rc == 0) e = cudaEventRecord(ev_v[c], stream);  // reused: forward_c done
+                             RAYEN_MODE_RAYEN, 1, ws_c[c], main);
+    mark(main, "forward");
+    if (e == cudaSuccess && rc == 0) e = cudaEventRecord(ev_v[c], main);  // reused: forward_c done
     if (e == cudaSuccess && rc == 0) e = cudaStreamWaitEvent(p->host_out, ev_v[c], 0);
     if (e == cudaSuccess && rc == 0)
       e = cudaMemcpyAsync(y_host + lo[c] * k, y + lo[c] * k, cnt[c] * k * 4, cudaMemcpyDeviceToHost, p->host_out);
     mark(p->host_out, "d2h y");
   }
   for (int c = 0; c < used && e == cudaSuccess && rc == 0; ++c) {
-    e = cudaStreamWaitEvent(stream, ev_g[c], 0);
+    e = cudaStreamWaitEvent(main, ev_g[c], 0);
     if (e == cudaSuccess)
       rc = rayen_backward_f32(p, v + lo[c] * n, n, gy + lo[c] * k, kappa + lo[c], active + lo[c], gv + lo[c] * n, n,
-                              cnt[c], RAYEN_MODE_RAYEN, 1, ws_c[c], stream);
-    mark(stream, "backward");
-    if (e == cudaSuccess && rc == 0) e = cudaEventRecord(ev_g[c], stream);  // reused: backward_c done
+                              cnt[c], RAYEN_MODE_RAYEN, 1, ws_c[c], main);
+    mark(main, "backward");
+    if (e == cudaSuccess && rc == 0) e = cudaEventRecord(ev_g[c], main);  // reused: backward_c done
     if (e == cudaSuccess && rc == 0) e = cudaStreamWaitEvent(p->host_out, ev_g[c], 0);
     if (e == cudaSuccess && rc == 0)
       e = cudaMemcpyAsync(gv_host + lo[c] * n, gv + lo[c] * n, cnt[c] * n * 4, cudaMemcpyDeviceToHost, p->host_out);
@@ -1242,18 +1246,14 @@ static int host_step(rayen_plan* p, const float* v_host, const float* gy_host, f
   // completion of this step = its last copy-out
   cudaError_t e2 = cudaEventRecord(ev_done, p->host_out);
   if (e == cudaSuccess) e = e2;
-  if (join_and_sync) {
-    // the caller's stream is complete only when the last copy-out is, then block the host as documented
-    e2 = cudaStreamWaitEvent(stream, ev_done, 0);
-    cudaError_t e3 = cudaStreamSynchronize(p->host_in);
-    cudaError_t e4 = cudaStreamSynchronize(p->host_out);
-    cudaError_t e5 = cudaStreamSynchronize(stream);
+  if (join) {
+    e2 = cudaStreamWaitEvent(main, ev_done, 0);
     if (e == cudaSuccess) e = e2;
-    if (e == cudaSuccess) e = e3;
-    if (e == cudaSuccess) e = e4;
-    if (e == cudaSuccess) e = e5;
   }
   if (trace && ntev > 0) {
+    cudaStreamSynchronize(p->host_in);
+    cudaStreamSynchronize(p->host_out);
+    cudaStreamSynchronize(main);
     fprintf(stderr, "rayen host path, %d chunk(s), B = %lld: end of each piece, us after the start\n", used, static_cast<long long>(B));
     for (int i = 1; i < ntev; ++i) {
       float ms = 0.f;
@@ -1262,9 +1262,108 @@ static int host_step(rayen_plan* p, const float* v_host, const float* gy_host, f
     }
     for (int i = 0; i < ntev; ++i) cudaEventDestroy(tev[i]);
   }
-  if (prev != p->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return cuda_fail(e, "host-buffer forward+backward");
   return rc;
+}
+
+// One forward+backward step on host buffers (see the header).  join_and_sync: the synchronous entry point -- the step
+// runs on the plan's own main stream, ordered after the caller's stream, replayed from an instantiated CUDA graph when
+// the same buffers come back (one cudaGraphLaunch instead of ~25 API calls), and the host blocks until it is complete.
+// Otherwise everything is queued on the caller's stream and completion is left to
+// rayen_forward_backward_host_wait(slot).
+static int host_step(rayen_plan* p, const float* v_host, const float* gy_host, float* y_host, float* gv_host, int64_t B,
+                     void* workspace, cudaStream_t stream, int slot, bool join_and_sync) {
+  std::lock_guard<std::mutex> guard(*p->host_mu);
+  int prev = 0;
+  RAYEN_CUDA(cudaGetDevice(&prev));
+  if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
+  cudaError_t e = cudaSuccess;
+  if (!p->host_ready) {
+    e = cudaStreamCreateWithFlags(&p->host_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->host_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->host_main, cudaStreamNonBlocking);
+    for (auto& slot_ev : p->host_ev)
+      for (cudaEvent_t& ev : slot_ev)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->host_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->host_join, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      if (prev != p->device) cudaSetDevice(prev);
+      return cuda_fail(e, "creating the copy streams of the host-buffer path");
+    }
+    p->host_ready = true;
+  }
+  // RAYEN_HOST_TRACE=1: print the device-side timeline of a synchronous call (development aid, adds event records)
+  static const bool trace_env = getenv("RAYEN_HOST_TRACE") && atoi(getenv("RAYEN_HOST_TRACE")) != 0;
+  int rc = 0;
+  if (!join_and_sync) {
+    rc = host_enqueue(p, v_host, gy_host, y_host, gv_host, B, workspace, stream, slot, false, false, false);
+    if (prev != p->device) cudaSetDevice(prev);
+    return rc;
+  }
+  // ---- synchronous step on the plan's main stream, ordered after the caller's stream
+  cudaStream_t main = p->host_main;
+  e = cudaEventRecord(p->host_fork, stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(main, p->host_fork, 0);
+  const bool graph_ok = p->host_graph_on && !trace_env;
+  rayen_plan::HostGraph* hit = nullptr;
+  if (e == cudaSuccess && graph_ok) {
+    for (int i = 0; i < p->host_graph_count; ++i) {
+      rayen_plan::HostGraph& g = p->host_graphs[i];
+      if (g.v == v_host && g.gy == gy_host && g.y == y_host && g.gv == gv_host && g.ws == workspace && g.B == B) hit = &g;
+    }
+  }
+  if (e == cudaSuccess && hit) {
+    hit->used = ++p->host_graph_clock;
+    e = cudaGraphLaunch(hit->exec, main);
+  } else if (e == cudaSuccess && graph_ok) {
+    // first time with these buffers: capture the step (copy streams forked from and joined back into `main`), keep the
+    // instantiated graph, launch it
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamBeginCapture(main, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      rc = host_enqueue(p, v_host, gy_host, y_host, gv_host, B, workspace, main, slot, true, true, false);
+      cudaError_t e2 = cudaStreamEndCapture(main, &graph);
+      if (rc == 0 && e2 != cudaSuccess) e = e2;
+      cudaGraphExec_t exec = nullptr;
+      if (rc == 0 && e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (rc == 0 && e == cudaSuccess) {
+        int at = p->host_graph_count;
+        if (at == 8) {  // evict the least recently used entry
+          at = 0;
+          for (int i = 1; i < 8; ++i)
+            if (p->host_graphs[i].used < p->host_graphs[at].used) at = i;
+          cudaGraphExecDestroy(p->host_graphs[at].exec);
+        } else {
+          ++p->host_graph_count;
+        }
+        p->host_graphs[at] = {v_host, gy_host, y_host, gv_host, workspace, B, main, exec, ++p->host_graph_clock};
+        e = cudaGraphLaunch(exec, main);
+      }
+    }
+    if (rc == 0 && e != cudaSuccess) {
+      // the step could not be captured (e.g. pageable host buffers): run it the plain way, now and from now on
+      cudaGetLastError();
+      p->host_graph_on = false;
+      e = cudaSuccess;
+      rc = host_enqueue(p, v_host, gy_host, y_host, gv_host, B, workspace, main, slot, true, true, false);
+    }
+  } else if (e == cudaSuccess) {
+    rc = host_enqueue(p, v_host, gy_host, y_host, gv_host, B, workspace, main, slot, true, true, trace_env);
+  }
+  // the caller's stream is complete only when the step is, then block the host as documented
+  cudaError_t e2 = cudaEventRecord(p->host_join, main);
+  if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(stream, p->host_join, 0);
+  cudaError_t e3 = cudaStreamSynchronize(main);
+  cudaError_t e4 = cudaStreamSynchronize(stream);
+  if (e == cudaSuccess) e = e2;
+  if (e == cudaSuccess) e = e3;
+  if (e == cudaSuccess) e = e4;
+  if (prev != p->device) cudaSetDevice(prev);
+  if (rc != 0) return rc;
+  if (e != cudaSuccess) return cuda_fail(e, "host-buffer forward+backward");
+  return RAYEN_OK;
 }
 
 static int host_check(const rayen_plan_t* cp, const void* a, const void* b, const void* c, const void* d, int64_t B,

@@ -71,7 +71,8 @@ def packed_triangular_words(np_):
 
 
 TC_PANEL = 128  # rows of W per tensor-core panel (MMA N)
-TC_TABLE_WORDS = 32
+TC_TABLE_WORDS = 64
+TC_BATCH_ITEMS = 12   # items per batch of the tensor-core kernel (lqs_tc.cuh kTcBatchItems)
 LMI_TC_PANEL = 128  # entries of the LMI matrix per panel of the contraction GEMM (MMA N)
 LMIW_R, LMIW_ROW_STRIDE = 32, 36   # lmi_warp.cuh: kLwR, kLwRowStride
 WIDE_MAGIC = 0x57494445
@@ -294,11 +295,14 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
     # becomes rows of one [rows x K] matrix W, so that all dot products of a 128-sample tile are ONE tcgen05
     # GEMM D = U W' with the result in tensor memory.  Rows are grouped in panels of 128; operands are split
     # W = W_hi + W_lo (both TF32-representable) for the error-compensated 3xTF32 product.
+    # Panel kinds.  LINEAR: 128 rows of D.  BATCH: up to TC_BATCH_ITEMS items (quadratics, cones, the pruning bound) are
+    # taken together and their triangular factors cut into blocks of 8 rows: block j (rows 8j..8j+7 of every item of the
+    # batch, 8 x items rows in all) is one panel whose columns left of 8j are zero, so its GEMM starts at K step j
+    # (4 + 3 + 2 + 1 = 10 K steps per batch at K = 32 instead of 16); block 0 also carries the items' two header rows
+    # (phi_z | c_z | t, then h) behind its factor rows.  The per-item sums of squares are accumulated across the blocks.
     kp = max(8, np_)
-    ch = 8
-    iw = ch + kp
-    ipp = TC_PANEL // iw
-    Wrows, table = [], []
+    nblocks = kp // 8
+    Wrows, table = [], []   # table rows: (ints[32], floats[TC_BATCH_ITEMS])
 
     def tri_dense(T):          # [np_, np_] upper triangular -> [kp, kp]
         out = np.zeros((kp, kp))
@@ -313,35 +317,53 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
             rows = Dk[base:base + TC_PANEL]
             blk[:rows.shape[0]] = rows
             Wrows.append(blk)
-            table.append(([0, base] + [0] * 16, [0.0] * 8))
-        items = []
+            table.append(([0, base, TC_PANEL, 0] + [0] * 28, [0.0] * TC_BATCH_ITEMS))
+        items = []     # (type, index, scalar, header rows [2, kp], factor [kp, kp])
         for i, (phi_z, Delta_z, G) in enumerate(quad_f64):
-            hdr = np.zeros((ch, kp))
+            hdr = np.zeros((2, kp))
             hdr[0, :n] = phi_z
-            items.append((2, i, 0.0, np.concatenate((hdr, tri_dense(G)))))
+            items.append((2, i, 0.0, hdr, tri_dense(G)))
         for j, (cz, h, Mz, A, R) in enumerate(soc_f64):
-            hdr = np.zeros((ch, kp))
+            hdr = np.zeros((2, kp))
             hdr[0, :n] = cz
             hdr[1, :n] = h
-            items.append((3, j, A, np.concatenate((hdr, tri_dense(R)))))
+            items.append((3, j, A, hdr, tri_dense(R)))
         if lmi is not None:
-            hdr = np.zeros((ch, kp))
+            hdr = np.zeros((2, kp))
             hdr[0, :n] = tr_F
-            items.append((5, 0, float(lmi_r), np.concatenate((hdr, tri_dense(bound_T)))))
-        for base in range(0, len(items), ipp):
-            blk = np.zeros((TC_PANEL, kp))
-            ints, flts = [1, 0] + [0] * 16, [0.0] * 8
-            for s_, (typ, idx, scal, rows) in enumerate(items[base:base + ipp]):
-                blk[s_ * iw:(s_ + 1) * iw] = rows
-                ints[2 + 2 * s_], ints[3 + 2 * s_] = typ, idx
-                flts[s_] = scal
-            Wrows.append(blk)
-            table.append((ints, flts))
+            items.append((5, 0, float(lmi_r), hdr, tri_dense(bound_T)))
+        n_batches = -(-len(items) // TC_BATCH_ITEMS)
+        per_batch = -(-len(items) // n_batches) if n_batches else 0          # balanced batches
+        for b0 in range(0, len(items), max(per_batch, 1)):
+            batch = items[b0:b0 + per_batch]
+            nb = len(batch)
+            n_blk = (8 * nb + 15) // 16 * 16          # MMA N of a block panel (multiple of 16)
+            hoff = n_blk                              # header rows of block 0 start here
+            n0 = (hoff + 2 * nb + 15) // 16 * 16
+            assert n0 <= TC_PANEL
+            for jb in range(nblocks):
+                blk = np.zeros((TC_PANEL, kp))
+                # word 7: bit s set <=> item s of the batch is a cone; bits 16.. = 1 + slot of the pruning bound (0: none)
+                meta = sum(1 << s_ for s_, it in enumerate(batch) if it[0] == 3)
+                meta |= next((s_ + 1 for s_, it in enumerate(batch) if it[0] == 5), 0) << 16
+                ints = [1, jb, n0 if jb == 0 else n_blk, jb, nb, int(jb == nblocks - 1), hoff, meta] + [0] * 24
+                flts = [0.0] * TC_BATCH_ITEMS
+                for s_, (typ, idx, scal, hdr, T) in enumerate(batch):
+                    blk[8 * s_:8 * s_ + 8] = T[8 * jb:8 * jb + 8]
+                    assert not np.any(T[8 * jb:8 * jb + 8, :8 * jb])          # the K steps the GEMM skips are zero
+                    if jb == 0:
+                        blk[hoff + 2 * s_:hoff + 2 * s_ + 2] = hdr
+                    ints[8 + 2 * s_], ints[9 + 2 * s_] = typ, idx
+                    flts[s_] = scal
+                Wrows.append(blk)
+                table.append((ints, flts))
     tc_panels = len(Wrows)
     tab = np.zeros((tc_panels, TC_TABLE_WORDS), dtype=np.float32)
     for pi, (ints, flts) in enumerate(table):
-        tab[pi, :18] = np.asarray(ints, dtype=np.int32).view(np.float32)
-        tab[pi, 24:32] = np.asarray(flts, dtype=np.float32)
+        tab[pi, :32] = np.asarray(ints, dtype=np.int32).view(np.float32)
+        tab[pi, 32:32 + TC_BATCH_ITEMS] = np.asarray(flts, dtype=np.float32)
+        # reciprocals of the item scalars (1 / A of a cone, 1 / r of the bound): the kernel multiplies instead of dividing
+        tab[pi, 44:44 + TC_BATCH_ITEMS] = np.asarray([1.0 / f if f != 0.0 else 0.0 for f in flts], dtype=np.float32)
     off_tc = add_f32(tab)
     for blk in Wrows:
         hi, lo = split_tf32(blk.astype(np.float32))

@@ -116,15 +116,26 @@ def test_tensor_core_sections_decode_to_the_fp32_sections(cfg):
     lin = np.concatenate([rows[pi] for pi in range(panels) if ints[pi, 0] == 0])[:m, :cs.n]
     assert np.abs(lin - D).max() <= 2.0 ** -21 * max(1.0, np.abs(D).max())
     assert [int(ints[pi, 1]) for pi in range(panels) if ints[pi, 0] == 0] == list(range(0, f["m_pad"], plan.TC_PANEL))
-    # item panels: 8 header rows + kp factor rows per item, item types in family order, |T u|^2 == u' S u
-    iw = 8 + kp
-    types = [int(ints[pi, 2 + 2 * s]) for pi in range(panels) if ints[pi, 0] == 1 for s in range(plan.TC_PANEL // iw)]
-    types = [t for t in types if t != 0]
-    n_lmi = 1 if cs.has_lmi_constraints else 0
+    # batch panels: block j of every item's triangular factor (8 rows per item), headers behind block 0; item types in
+    # family order; the K steps a block panel skips are zero; the blocks of an item reassemble its factor
+    nblocks = kp // 8
+    batch_panels = [pi for pi in range(panels) if ints[pi, 0] == 1]
+    assert len(batch_panels) % nblocks == 0
+    types, n_lmi = [], (1 if cs.has_lmi_constraints else 0)
+    for b0 in range(0, len(batch_panels), nblocks):
+        grp = batch_panels[b0:b0 + nblocks]
+        nb, hoff = int(ints[grp[0], 4]), int(ints[grp[0], 6])
+        assert 1 <= nb <= plan.TC_BATCH_ITEMS and hoff % 16 == 0 and hoff >= 8 * nb
+        for j, pi in enumerate(grp):
+            kind, jb, N, ks0, nbj, last = (int(x) for x in ints[pi, :6])
+            assert (jb, ks0, nbj, last) == (j, j, nb, int(j == nblocks - 1)) and N % 16 == 0 and N <= plan.TC_PANEL
+            assert N >= (hoff + 2 * nb if j == 0 else 8 * nb)
+            assert not np.any(rows[pi][:, :8 * j])                                  # skipped K steps are zero
+            assert not np.any(rows[pi][N:])                                         # nothing beyond the MMA's N
+        types += [int(ints[grp[0], 8 + 2 * s]) for s in range(nb)]
+        T0 = np.concatenate([rows[pi][0:8, :kp] for pi in grp])                     # factor of the batch's first item
+        assert np.allclose(np.tril(T0, -1), 0.0)                                    # upper triangular
     assert types == [2] * len(cs.qcs) + [3] * len(cs.socs) + [5] * n_lmi
-    first_item_panel = next(pi for pi in range(panels) if ints[pi, 0] == 1)
-    T = rows[first_item_panel][8:8 + kp, :kp]
-    assert np.allclose(np.tril(T, -1), 0.0)                                        # upper triangular factor
     if f["lmitc_panels"]:
         rp, n = f["lmi_rp"], cs.n
         assert f["lmitc_panels"] == rp * rp // plan.LMI_TC_PANEL
@@ -190,7 +201,7 @@ def test_wide_plan_decodes_to_the_oracle(k, m, eta, mu, r_M, eq):
 
 def test_narrow_plans_are_not_wide():
     p = plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.config_spec("cfg5")))
-    assert p.fields["wide"] == 0 and p.fields["off_wide"] == 0 and p.fields["tc_panels"] == 13
+    assert p.fields["wide"] == 0 and p.fields["off_wide"] == 0 and p.fields["tc_panels"] == 14
 
 
 def test_wide_plan_with_more_items_than_a_round_holds():
