@@ -24,12 +24,12 @@
 extern "C" {
 #endif
 
-#define RAYEN_ABI_VERSION 13
+#define RAYEN_ABI_VERSION 14
 
 /* error codes (negative); positive return values are cudaError_t */
 #define RAYEN_OK 0
 #define RAYEN_ERR_BAD_ARGUMENT (-1)
-#define RAYEN_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels cover (n > 4096, LMI size > 32, LMI with n > 32) */
+#define RAYEN_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels cover (n > 4096, LMI size > 320) */
 #define RAYEN_ERR_ABI (-3)
 #define RAYEN_ERR_NO_DEVICE (-4)
 
@@ -99,6 +99,10 @@ extern "C" {
  *             NT      [n][k32] = N' and Nrow [k][np] = N (both absent when N is the identity)
  *           The LIN/QUAD/SOC/NMAT/BOUND sections are empty placeholders (np = n rounded up to 4) and TC has no
  *           panels (tc_panels = 0): a wide plan is WIDE + Y0 + VIOL.
+ *   LMIB    (lmi_big == 1: lmi_r > 32, or an LMI together with n > 32; lmi_big.cuh) F~z_a, a < n, as packed lower
+ *           triangles: entry (i, j), j <= i, at word i (i + 1) / 2 + j of a row of lmib_p4 words -- the [n x lmib_p4]
+ *           B operand of the contraction GEMM S~(v) = V . F (FP32 pipe); the eigen-solve runs one CTA per sample on the
+ *           result.  LMINEGB: -F_0 .. -F_k of the ambient space in the same packing ([k + 1][lmib_p4]).
  *   LMINEG  -F_0 .. -F_k laid out like LMI ([a][row][lane][slot]): lambda_max(sum_a (y,1)_a (-F_a)) = -lambda_min(F(y))
  */
 typedef struct RayenPlanDesc {
@@ -124,10 +128,16 @@ typedef struct RayenPlanDesc {
   int32_t viol_eq;   /* equality rows of the VIOL section */
   int32_t lmitc_panels; /* 128-entry panels of the LMITC section (0: none) */
   int32_t wide;         /* 1: n > 32 -- np is n rounded up to 4, the kernels of wide.cuh read the WIDE section */
+  int32_t lmi_big;      /* 1: the LMI is served by lmi_big.cuh (lmi_r > 32, or any lmi_r together with n > 32): section LMIB,
+                           lmi_rp = 0 and the register-resident LMI sections (LMI, LMIW, LMITC, LMINEG, BOUND) are empty */
+  int32_t lmib_p4;      /* words per packed lower triangle: lmi_r (lmi_r + 1) / 2 rounded up to 4 */
   float lmi_bound_margin; /* absolute float32-rounding allowance added to the pruning bound (see BOUND) */
   int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi, off_tc, off_viol, off_lmineg, off_lmitc;
   int64_t off_wide;     /* WIDE section (0 when wide == 0) */
   int64_t off_lmiw;     /* LMIW section (0 without an LMI) */
+  int64_t off_lmib;     /* LMIB section: F~z_a, a < n, lower triangles row-major packed ((i, j), j <= i, at i (i + 1) / 2 + j),
+                           lmib_p4 words each -- the B operand of the contraction GEMM S~(v) = V . F of lmi_big.cuh */
+  int64_t off_lminegb;  /* LMINEGB section: -F_0 .. -F_k of the ambient space in the same packing (violation metric) */
   int64_t blob_words;
   const float* blob; /* host pointer, blob_words floats */
 } RayenPlanDesc;

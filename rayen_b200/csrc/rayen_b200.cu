@@ -16,6 +16,7 @@
 #include "lqs_tc.cuh"
 #include "viol.cuh"
 #include "wide.cuh"
+#include "lmi_big.cuh"
 
 using namespace rayen;
 
@@ -35,6 +36,16 @@ struct rayen_plan {
   bool wide;      // n > 32: the kernels of wide.cuh on the WIDE section (linear + quadratic + SOC, no LMI)
   WideDev wdev;
   size_t wide_fwd_smem_bytes[2], wide_bwd_smem_bytes;  // forward: tiles of 8 / 16 samples
+  // LMI beyond the register-resident kernels (lmi_big.cuh): dev.lmi_r stays 0 (the narrow kernels see "no LMI"), the
+  // other families' kernel leaves the prior (kappa, tag, y) for every sample and the two kernels of lmi_big.cuh follow
+  bool lmi_big;
+  LmiBigDev bdev;
+  int lmib_threads;        // CTA size of the solve kernel: 64 / 128 / 256 / 320 (>= r)
+  bool lmib_global;        // r > 232: the square matrix lives in the workspace instead of shared memory
+  size_t lmib_smem_bytes;
+  int lmib_ctas_per_sm;
+  int64_t lmib_ws_cap;     // bytes of the contracted-matrix buffer a forward call may use (RAYEN_LMIB_WS_MB, default 512)
+  int off_lminegb;
   bool has_lqs;   // any non-zero linear row / quadratic / cone: otherwise the LQS forward kernel is skipped
   bool prune;     // LMI pruning enabled (needs has_lqs and a BOUND section)
   bool use_tc;    // tensor-core (tcgen05) linear/quadratic/SOC forward kernel
@@ -247,17 +258,124 @@ static int allow_smem(const void* fn, size_t bytes) {
 // ----------------------------------------------------------------------------- plan create / destroy
 static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** out);
 
+// ----------------------------------------------------------------------------- big LMI (lmi_big.cuh)
+typedef void (*LmibSolveFn)(const LmiBigDev, const float*, const float*, long long, float*, float*, int*, float*, float*,
+                            long long, int, int);
+static LmibSolveFn lmib_solve_fn(int threads, bool global_a) {
+  switch (threads) {
+    case 64: return global_a ? lmib_solve_kernel<64, true> : lmib_solve_kernel<64, false>;
+    case 128: return global_a ? lmib_solve_kernel<128, true> : lmib_solve_kernel<128, false>;
+    case 256: return global_a ? lmib_solve_kernel<256, true> : lmib_solve_kernel<256, false>;
+    default: return global_a ? lmib_solve_kernel<320, true> : lmib_solve_kernel<320, false>;
+  }
+}
+static int allow_smem(const void* fn, size_t bytes);
+static int lmib_validate(const RayenPlanDesc* d) {
+  if (d->lmi_r < 1 || d->lmi_r > kLbMaxR)
+    return fail(RAYEN_ERR_UNSUPPORTED, "LMI size %d: the one-CTA-per-matrix path covers 1 <= r <= %d", d->lmi_r, kLbMaxR);
+  const int64_t p4 = (static_cast<int64_t>(d->lmi_r) * (d->lmi_r + 1) / 2 + 3) / 4 * 4;
+  if (d->lmib_p4 != p4 || d->lmi_rp != 0 || d->off_lmib <= 0 || d->off_lmib % 4 ||
+      d->off_lmib + static_cast<int64_t>(d->n) * p4 > d->blob_words || d->off_lminegb <= 0 || d->off_lminegb % 4 ||
+      d->off_lminegb + static_cast<int64_t>(d->k + 1) * p4 > d->blob_words)
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "LMIB / LMINEGB sections do not fit the block");
+  return 0;
+}
+// device must be current; p->sm_count / max_smem_optin / d_blob set
+static int lmib_setup(rayen_plan* p, const RayenPlanDesc* d) {
+  p->lmi_big = true;
+  LmiBigDev& b = p->bdev;
+  b.blob = p->d_blob;
+  b.n = d->n; b.k = d->k; b.r = d->lmi_r; b.p4 = d->lmib_p4;
+  b.off_lmib = static_cast<int>(d->off_lmib);
+  b.off_y0 = static_cast<int>(d->off_y0);
+  p->off_lminegb = static_cast<int>(d->off_lminegb);
+  p->lmib_threads = b.r <= 64 ? 64 : (b.r <= 128 ? 128 : (b.r <= 256 ? 256 : 320));
+  p->lmib_global = lmib_smem_bytes(b.r, false) > static_cast<size_t>(p->max_smem_optin);
+  if (getenv("RAYEN_LMIB_GLOBAL") && atoi(getenv("RAYEN_LMIB_GLOBAL")) == 1) p->lmib_global = true;
+  p->lmib_smem_bytes = lmib_smem_bytes(b.r, p->lmib_global);
+  int per_sm = p->lmib_global ? 4 : static_cast<int>(static_cast<size_t>(p->max_smem_optin) / (p->lmib_smem_bytes + 1024));
+  const int by_threads = 2048 / p->lmib_threads;
+  if (per_sm > by_threads) per_sm = by_threads;
+  if (per_sm > 16) per_sm = 16;
+  if (per_sm < 1) per_sm = 1;
+  p->lmib_ctas_per_sm = per_sm;
+  p->lmib_ws_cap = 512ll << 20;
+  if (const char* env = getenv("RAYEN_LMIB_WS_MB")) {
+    const long long mb = atoll(env);
+    if (mb >= 1 && mb <= 65536) p->lmib_ws_cap = mb << 20;
+  }
+  // the attribute is per function: the device maximum, so that plans of different sizes coexist
+  int rc = 0;
+  for (int t : {64, 128, 256, 320})
+    for (int g = 0; g < 2 && rc == 0; ++g)
+      rc = allow_smem(reinterpret_cast<const void*>(lmib_solve_fn(t, g != 0)), p->max_smem_optin);
+  return rc;
+}
+// samples per chunk of the contraction buffer for a call of B samples (p4 words each)
+static int64_t lmib_chunk_rows(const rayen_plan* p, int64_t B, int p4) {
+  int64_t rows = p->lmib_ws_cap / (static_cast<int64_t>(p4) * 4);
+  rows = rows / kLbTileM * kLbTileM;
+  if (rows < kLbTileM) rows = kLbTileM;
+  return rows < B ? rows : B;
+}
+static int64_t lmib_solve_grid(const rayen_plan* p, int64_t rows) {
+  const int64_t cap = static_cast<int64_t>(p->sm_count) * p->lmib_ctas_per_sm;
+  return rows < cap ? (rows < 1 ? 1 : rows) : cap;
+}
+// bytes behind the common workspace prefix: the contraction buffer and, for GLOBAL_A, one square matrix per CTA
+static int64_t lmib_ws_extra(const rayen_plan* p, int64_t B, int p4) {
+  const int64_t rows = lmib_chunk_rows(p, B, p4);
+  int64_t bytes = 256 + (rows * p4 * 4 + 255) / 256 * 256;  // 256: the buffer is aligned up inside the caller's workspace
+  if (p->lmib_global) bytes += lmib_solve_grid(p, rows) * static_cast<int64_t>(lmib_square_words(p->bdev.r)) * 4;
+  return bytes;
+}
+// The two kernels of lmi_big.cuh over the batch, chunk by chunk.  F: [nv][p4] packed matrices (LMIB with V = v, or
+// LMINEGB with V = (y, 1)); buf: the contraction buffer (+ the GLOBAL_A scratch behind it).
+static cudaError_t lmib_run(const rayen_plan* p, const float* F, int nv, const float* V, int64_t ldv, float* y, float* kappa,
+                            int32_t* active, float* dkappa, void* buf, int64_t B, int mode, int flags, cudaStream_t stream,
+                            const float* C0 = nullptr) {
+  LmiBigDev b = p->bdev;
+  b.n = nv;
+  b.off_lmib = static_cast<int>(F - p->d_blob);
+  const int64_t rows = lmib_chunk_rows(p, B, b.p4);
+  buf = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(buf) + 255) / 256 * 256);  // 16-byte stores of the GEMM
+  float* S = static_cast<float*>(buf);
+  float* scratch = reinterpret_cast<float*>(static_cast<char*>(buf) + (rows * b.p4 * 4 + 255) / 256 * 256);
+  LmibSolveFn sf = lmib_solve_fn(p->lmib_threads, p->lmib_global);
+  const int tiles_n = (b.p4 + kLbTileN - 1) / kLbTileN;
+  for (int64_t c0 = 0; c0 < B; c0 += rows) {
+    const int64_t bc = (B - c0 < rows) ? B - c0 : rows;
+    const int64_t tiles_m = (bc + kLbTileM - 1) / kLbTileM;
+    lmib_contract_kernel<<<static_cast<unsigned>(tiles_n * tiles_m), kLbGemmThreads, 0, stream>>>(
+        V + c0 * ldv, ldv, F, nv, b.p4, S, bc, C0);
+    g_launches.fetch_add(1);
+    sf<<<static_cast<unsigned>(lmib_solve_grid(p, bc)), p->lmib_threads, p->lmib_smem_bytes, stream>>>(
+        b, S, V + c0 * ldv, ldv, y ? y + c0 * b.k : nullptr, kappa + c0, active ? active + c0 : nullptr,
+        dkappa ? dkappa + c0 * nv : nullptr, scratch, bc, mode, flags);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+
 extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_t** out) {
   if (!d || !out) return fail(RAYEN_ERR_BAD_ARGUMENT, "rayen_plan_create: null argument");
   *out = nullptr;
   if (d->abi_version != RAYEN_ABI_VERSION)
     return fail(RAYEN_ERR_ABI, "plan descriptor has ABI %d, library has %d", d->abi_version, RAYEN_ABI_VERSION);
   if (d->n < 1 || d->k < d->n) return fail(RAYEN_ERR_BAD_ARGUMENT, "bad dimensions n=%d k=%d", d->n, d->k);
+  if (d->lmi_big && d->lmi_r > 0) {
+    const int rcb = lmib_validate(d);
+    if (rcb) return rcb;
+  }
   if (d->wide) return create_wide_plan(d, device, out);
+  const int narrow_r = d->lmi_big ? 0 : d->lmi_r;  // LMI size as the register-resident kernels see it
   if (np_index(d->np) < 0 || d->np < d->n)
     return fail(RAYEN_ERR_UNSUPPORTED, "n=%d (np=%d): the register-resident kernels cover n <= 32 (wide plans: wide = 1)", d->n, d->np);
-  if (d->lmi_r > 0 && (np_index(d->lmi_rp) < 0 || d->lmi_rp < d->lmi_r))
-    return fail(RAYEN_ERR_UNSUPPORTED, "LMI size %d (padded %d): only r <= 32 is covered", d->lmi_r, d->lmi_rp);
+  if (narrow_r > 0 && (np_index(d->lmi_rp) < 0 || d->lmi_rp < d->lmi_r))
+    return fail(RAYEN_ERR_UNSUPPORTED, "LMI size %d (padded %d): the register-resident kernels cover r <= 32 (larger: lmi_big = 1)", d->lmi_r, d->lmi_rp);
   if (d->m_pad % 4 || d->m_pad < d->m || d->m_pad < 4 || d->k_pad % 4 || d->k_pad < d->k)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "bad padding m=%d m_pad=%d k=%d k_pad=%d", d->m, d->m_pad, d->k, d->k_pad);
   if (!d->blob || d->blob_words <= 0 || d->blob_words % 4)
@@ -285,12 +403,12 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
     return fail(RAYEN_ERR_BAD_ARGUMENT, "bound section does not fit its slot");
   if (d->lmi_prune && !(d->lmi_bound_margin >= 0.f))
     return fail(RAYEN_ERR_BAD_ARGUMENT, "lmi_bound_margin must be >= 0");
-  if (d->lmi_r > 0 && d->off_lmi + static_cast<int64_t>(d->n) * d->lmi_rp * d->lmi_rp > d->blob_words)
+  if (narrow_r > 0 && d->off_lmi + static_cast<int64_t>(d->n) * d->lmi_rp * d->lmi_rp > d->blob_words)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "LMI section does not fit the block");
   if (d->blob_words > (1ll << 30)) return fail(RAYEN_ERR_UNSUPPORTED, "constant block too large");
   if (d->off_viol < 0 || d->off_viol % 4 || d->off_viol >= d->blob_words || d->off_lmineg < d->off_viol || d->off_lmineg % 4 ||
       d->off_lmineg >= d->blob_words || d->viol_in < 0 || d->viol_eq < 0 ||
-      (d->lmi_r > 0 && d->off_lmineg + static_cast<int64_t>(d->k + 1) * d->lmi_rp * d->lmi_rp > d->blob_words))
+      (narrow_r > 0 && d->off_lmineg + static_cast<int64_t>(d->k + 1) * d->lmi_rp * d->lmi_rp > d->blob_words))
     return fail(RAYEN_ERR_BAD_ARGUMENT, "violation sections do not fit the block");
   if (d->tc_panels < 1 || (d->tc_kp != 8 && d->tc_kp != 16 && d->tc_kp != 32) || d->tc_kp < d->np || d->off_tc % 4 ||
       d->off_tc < d->off_lmi ||
@@ -303,7 +421,7 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
     return fail(RAYEN_ERR_BAD_ARGUMENT, "LMI tensor-core section does not fit the block");
 
   if (d->off_lmiw < 0 || d->off_lmiw % 4 ||
-      (d->lmi_r > 0 && d->off_lmiw > 0 && d->off_lmiw + static_cast<int64_t>(d->n) * kLwMatWords > d->blob_words))
+      (narrow_r > 0 && d->off_lmiw > 0 && d->off_lmiw + static_cast<int64_t>(d->n) * kLwMatWords > d->blob_words))
     return fail(RAYEN_ERR_BAD_ARGUMENT, "LMIW section does not fit the block");
 
   int count = 0;
@@ -347,15 +465,15 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   v.blob = p->d_blob;
   v.n = d->n; v.k = d->k; v.np = d->np; v.k_pad = d->k_pad;
   v.m = d->m; v.m_pad = d->m_pad; v.n_quad = d->n_quad; v.n_soc = d->n_soc;
-  v.lmi_r = d->lmi_r; v.lmi_rp = d->lmi_rp; v.n_is_identity = d->n_is_identity;
+  v.lmi_r = narrow_r; v.lmi_rp = d->lmi_rp; v.n_is_identity = d->n_is_identity;
   v.lin_stride = d->lin_chunk_stride; v.quad_stride = d->quad_stride; v.soc_stride = d->soc_stride;
   v.off_lin = static_cast<int>(d->off_lin); v.off_quad = static_cast<int>(d->off_quad);
   v.off_soc = static_cast<int>(d->off_soc); v.off_nmat = static_cast<int>(d->off_nmat);
   v.off_y0 = static_cast<int>(d->off_y0); v.off_bound = static_cast<int>(d->off_bound);
   v.off_lmi = static_cast<int>(d->off_lmi);
-  v.lmi_prune = (d->lmi_prune && d->lmi_r > 0) ? 1 : 0;
+  v.lmi_prune = (d->lmi_prune && narrow_r > 0) ? 1 : 0;
   v.lqs_words = static_cast<int>(d->off_lmi - d->off_lin);
-  v.lmi_words = d->lmi_r > 0 ? d->n * d->lmi_rp * d->lmi_rp : 0;
+  v.lmi_words = narrow_r > 0 ? d->n * d->lmi_rp * d->lmi_rp : 0;
   v.off_tc = static_cast<int>(d->off_tc); v.tc_panels = d->tc_panels; v.tc_kp = d->tc_kp;
   v.off_viol = static_cast<int>(d->off_viol); v.off_lmineg = static_cast<int>(d->off_lmineg);
   v.viol_in = d->viol_in; v.viol_eq = d->viol_eq;
@@ -443,6 +561,7 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
       if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmi_forward_warp_kernel<true>), p->lmi_warp_smem_bytes);
     }
   }
+  if (rc == 0 && d->lmi_big && d->lmi_r > 0) rc = lmib_setup(p, d);
   // the violation checker keeps one y row per warp in shared memory: large ambient dimensions need the opt-in limit
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(viol_lqs_kernel), p->max_smem_optin);
   cudaSetDevice(prev);
@@ -460,7 +579,8 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
 static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** out) {
   if (d->n <= 32 || d->n > 4096 || d->np < d->n || d->np % 4)
     return fail(RAYEN_ERR_UNSUPPORTED, "wide plan: n=%d (np=%d) outside 33..4096", d->n, d->np);
-  if (d->lmi_r > 0) return fail(RAYEN_ERR_UNSUPPORTED, "an LMI together with n=%d > 32 is not covered", d->n);
+  if (d->lmi_r > 0 && !d->lmi_big)
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "an LMI together with n=%d > 32 needs lmi_big = 1 (section LMIB)", d->n);
   if (d->k_pad % 4 || d->k_pad < d->k) return fail(RAYEN_ERR_BAD_ARGUMENT, "bad padding k=%d k_pad=%d", d->k, d->k_pad);
   if (!d->blob || d->blob_words <= 0 || d->blob_words % 4 || d->blob_words > (1ll << 30))
     return fail(RAYEN_ERR_BAD_ARGUMENT, "bad constant block (%lld words)", static_cast<long long>(d->blob_words));
@@ -552,6 +672,7 @@ static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** o
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_backward_kernel<128>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_backward_kernel<256>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(viol_lqs_kernel), p->max_smem_optin);
+  if (rc == 0 && d->lmi_big && d->lmi_r > 0) rc = lmib_setup(p, d);
   cudaSetDevice(prev);
   if (rc != 0) {
     if (p->d_blob) cudaFree(p->d_blob);
@@ -698,10 +819,12 @@ extern "C" int rayen_plan_set_pruning(rayen_plan_t* p, int enabled) {
 // workspace: [fwd counter, bwd counter, pad to 256 B][forward work list: B ints][backward work list: B ints]
 //            [d kappa/du of the LMI-bound samples: B x n floats, written by forward when want_grad != 0]
 static int64_t ws_list_bytes(int64_t B) { return (B * 4 + 255) / 256 * 256; }
+static int64_t ws_prefix_bytes(int64_t B, int n) { return 256 + 2 * ws_list_bytes(B) + (B * n * 4 + 255) / 256 * 256; }
 extern "C" int64_t rayen_workspace_bytes(const rayen_plan_t* p, int64_t B) {
   if (!p || B < 0) return -1;
+  if (p->lmi_big) return ws_prefix_bytes(B, p->dev.n) + lmib_ws_extra(p, B, p->bdev.p4);
   if (p->dev.lmi_r == 0) return 0;
-  return 256 + 2 * ws_list_bytes(B) + (B * p->dev.n * 4 + 255) / 256 * 256;
+  return ws_prefix_bytes(B, p->dev.n);
 }
 static float* ws_dkappa(void* workspace, int64_t B) {
   return reinterpret_cast<float*>(static_cast<char*>(workspace) + 256 + 2 * ws_list_bytes(B));
@@ -860,10 +983,18 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
   if (has_lmi && (!kappa || !active))
     return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the kappa and active outputs");
   if (has_lmi && !workspace) return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the workspace buffer");
+  if (p->lmi_big && (!kappa || !active || !workspace))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the kappa and active outputs and the workspace buffer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int prev = 0;
   RAYEN_CUDA(cudaGetDevice(&prev));
   if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
+  // big LMI (lmi_big.cuh): behind the other families' kernel, which leaves the prior (kappa, tag, y) of every sample
+  auto run_lmi_big = [&]() -> cudaError_t {
+    return lmib_run(p, p->d_blob + p->bdev.off_lmib, d.n, v, ldv, y, kappa, active,
+                    want_grad ? ws_dkappa(workspace, B) : nullptr, static_cast<char*>(workspace) + ws_prefix_bytes(B, d.n), B,
+                    mode, want_grad ? kLbFlagGrad : 0, stream);
+  };
 
   if (p->wide) {
     if (map) {
@@ -889,6 +1020,7 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
       g_launches.fetch_add(1);
       we = cudaGetLastError();
     }
+    if (we == cudaSuccess && p->lmi_big && (stage_mask & 2)) we = run_lmi_big();
     if (prev != p->device) cudaSetDevice(prev);
     if (we != cudaSuccess) return cuda_fail(we, "forward launch (wide)");
     return RAYEN_OK;
@@ -899,9 +1031,9 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
   const bool use_list = has_lmi && run_lqs && p->prune;
   cudaError_t e = cudaSuccess;
   const bool use_warp = has_lmi && lmi_use_warp(p, run_lqs);
-  // counters: [0] forward work list, [1] backward work list, [2] fail list of the filter kernel (lmi_warp.cuh)
+  // counters: [0] forward work list, [1] backward work list, [2] fail list and [3] chunk dispenser of the filter kernel
   if ((stage_mask & 1) && run_lqs) {
-    if (use_list || use_warp) e = cudaMemsetAsync(counters, 0, 3 * sizeof(int), stream);
+    if (use_list || use_warp) e = cudaMemsetAsync(counters, 0, 4 * sizeof(int), stream);
     if (e == cudaSuccess && p->use_tc) {
       long long grid = (B + 255) / 256;
       if (grid > p->sm_count) grid = p->sm_count;
@@ -933,7 +1065,9 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
       // matrix).  With a cap on the solves per warp (RAYEN_LMI_WARP_SOLVES) the rest goes to a fail list (the region of
       // the backward work list, free until the backward call) and a second launch of the same kernel.
       int* fail_list = reinterpret_cast<int*>(static_cast<char*>(workspace) + 256 + ws_list_bytes(B));
-      if (!behind_lqs) e = cudaMemsetAsync(counters + 2, 0, sizeof(int), stream);  // else zeroed with the other counters
+      // counters [2] fail list, [3] chunk dispenser of the filter kernel: zeroed with the others in front of the
+      // linear/quadratic/SOC kernel, or here when this stage is launched on its own
+      if (!((stage_mask & 1) && run_lqs)) e = cudaMemsetAsync(counters + 2, 0, 2 * sizeof(int), stream);
       // chunks of 4 samples, dealt round-robin to the CTAs (the list length is only known on the device)
       long long blocks = (B + kLwMT - 1) / kLwMT;
       if (blocks > p->sm_count) blocks = p->sm_count;
@@ -954,11 +1088,12 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
       const int filt = p->lmi_warp_filter ? 1 : 0;
       const int budget = p->lmi_warp_solves;
       int* fcnt = counters + 2;
+      int* next = (budget == 0x7fffffff) ? counters + 3 : nullptr;   // dynamic chunks only when there is no second launch
       if (e == cudaSuccess)
         e = grad ? cudaLaunchKernelEx(&cfg, lmi_forward_warp_kernel<true>, d, v, ldv_, y, kappa, active, B_, mode, list, cnt, dk,
-                                      filt, budget, fail_list, fcnt)
+                                      filt, budget, fail_list, fcnt, next)
                  : cudaLaunchKernelEx(&cfg, lmi_forward_warp_kernel<false>, d, v, ldv_, y, kappa, active, B_, mode, list, cnt,
-                                      dk, filt, budget, fail_list, fcnt);
+                                      dk, filt, budget, fail_list, fcnt, next);
       if (e == cudaSuccess && budget != 0x7fffffff) {
         g_launches.fetch_add(1);
         // the same kernel once more on the fail list, filter off, no budget: whoever solves a sample runs the same
@@ -970,9 +1105,9 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
         int* none = nullptr;
         const int all = 0x7fffffff, nofilt = 0;
         e = grad ? cudaLaunchKernelEx(&cfg, lmi_forward_warp_kernel<true>, d, v, ldv_, y, kappa, active, B_, mode, flist, fc, dk,
-                                      nofilt, all, none, none)
+                                      nofilt, all, none, none, none)
                  : cudaLaunchKernelEx(&cfg, lmi_forward_warp_kernel<false>, d, v, ldv_, y, kappa, active, B_, mode, flist, fc,
-                                      dk, nofilt, all, none, none);
+                                      dk, nofilt, all, none, none, none);
       }
     } else if (lmi_use_tc(p, grad, use_list)) {
       // one CTA per SM, persistent over passes of 8 warps x mpw samples; short batches still start one CTA per
@@ -997,6 +1132,7 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
     g_launches.fetch_add(1);
     if (e == cudaSuccess) e = cudaGetLastError();
   }
+  if (e == cudaSuccess && p->lmi_big && (stage_mask & 2)) e = run_lmi_big();
   if (prev != p->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return cuda_fail(e, "forward launch");
   return RAYEN_OK;
@@ -1021,11 +1157,24 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
   if (ldv < need || ldgv < need)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "ldv=%lld / ldgv=%lld < %d", static_cast<long long>(ldv),
                 static_cast<long long>(ldgv), need);
-  if (d.lmi_r > 0 && !workspace) return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the workspace buffer");
+  if ((d.lmi_r > 0 || p->lmi_big) && !workspace)
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "plans with an LMI need the workspace buffer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int prev = 0;
   RAYEN_CUDA(cudaGetDevice(&prev));
   if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
+  // big LMI: d kappa/du of the LMI-bound samples comes from the workspace -- left there by forward (have_dkappa) or
+  // recomputed now by the same two kernels in gradient-only mode (kappa / active / y are inputs only)
+  const float* big_dk = p->lmi_big ? ws_dkappa(workspace, B) : nullptr;
+  if (p->lmi_big && !have_dkappa && (stage_mask & 1)) {
+    cudaError_t ge = lmib_run(p, p->d_blob + p->bdev.off_lmib, d.n, v, ldv, nullptr, const_cast<float*>(kappa),
+                              const_cast<int32_t*>(active), ws_dkappa(workspace, B),
+                              static_cast<char*>(workspace) + ws_prefix_bytes(B, d.n), B, mode, kLbFlagGradOnly, stream);
+    if (ge != cudaSuccess) {
+      if (prev != p->device) cudaSetDevice(prev);
+      return cuda_fail(ge, "backward launch (big LMI gradient)");
+    }
+  }
 
   if (p->wide) {
     cudaError_t we = cudaSuccess;
@@ -1035,10 +1184,10 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
       if (wgrid > wcap) wgrid = wcap;
       if (p->wdev.n < kWideBwdSwitchN)
         wide_backward_kernel<128><<<static_cast<int>(wgrid), 128, p->wide_bwd_smem_bytes, stream>>>(
-            p->wdev, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
+            p->wdev, v, ldv, gy, kappa, active, gv, ldgv, B, mode, big_dk);
       else
         wide_backward_kernel<256><<<static_cast<int>(wgrid), 256, p->wide_bwd_smem_bytes, stream>>>(
-            p->wdev, v, ldv, gy, kappa, active, gv, ldgv, B, mode);
+            p->wdev, v, ldv, gy, kappa, active, gv, ldgv, B, mode, big_dk);
       g_launches.fetch_add(1);
       we = cudaGetLastError();
     }
@@ -1062,7 +1211,8 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
       const size_t tile_bytes = static_cast<size_t>(block / 32) * 2 * 32 * (d.np + 4) * sizeof(float);
       f<<<static_cast<int>(grid), block, tile_bytes, stream>>>(d, v, ldv, gy, kappa, active, gv, ldgv, B, mode, bwd_list,
                                                       has_lmi ? counters + 1 : nullptr,
-                                                      (has_lmi && have_dkappa) ? ws_dkappa(workspace, B) : nullptr);
+                                                      p->lmi_big ? big_dk
+                                                                 : ((has_lmi && have_dkappa) ? ws_dkappa(workspace, B) : nullptr));
       g_launches.fetch_add(1);
       e = cudaGetLastError();
     }
@@ -1114,6 +1264,21 @@ extern "C" int rayen_violation_f32(const rayen_plan_t* p, const float* y, int64_
     g_launches.fetch_add(1);
     e = cudaGetLastError();
   }
+  if (e == cudaSuccess && p->lmi_big) {
+    // lambda_max(-F(y)) = -lambda_min(F(y)): the two kernels of lmi_big.cuh on the ambient matrices (LMINEGB: rows
+    // 0 .. k-1 contract with y, row k is the constant term); the buffer comes from the stream-ordered allocator
+    // (a diagnostic call, not the hot path)
+    const int64_t bytes = lmib_ws_extra(p, B, p->bdev.p4);
+    void* buf = nullptr;
+    e = cudaMallocAsync(&buf, static_cast<size_t>(bytes), stream);
+    if (e == cudaSuccess) {
+      const float* Fn = p->d_blob + p->off_lminegb;
+      e = lmib_run(p, Fn, d.k, y, ldy, nullptr, viol, nullptr, nullptr, buf, B, RAYEN_MODE_RAYEN, kLbFlagLambdaOut, stream,
+                   Fn + static_cast<size_t>(d.k) * p->bdev.p4);
+      cudaError_t fe = cudaFreeAsync(buf, stream);
+      if (e == cudaSuccess) e = fe;
+    }
+  }
   if (prev != p->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return cuda_fail(e, "violation launch");
   return RAYEN_OK;
@@ -1134,7 +1299,7 @@ extern "C" int64_t rayen_host_workspace_bytes(const rayen_plan_t* p, int64_t B) 
   const int64_t n = p->dev.n, k = p->dev.k;
   // v | gy | y | gv | kappa | active, each rounded up to 256 B, then one kernel workspace per chunk
   return round256(B * n * 4) * 2 + round256(B * k * 4) * 2 + round256(B * 4) * 2 + rayen_workspace_bytes(p, B) +
-         kHostMaxChunks * (p->dev.lmi_r > 0 ? 2048 : 0);
+         kHostMaxChunks * ((p->dev.lmi_r > 0 || p->lmi_big) ? 2048 : 0);
 }
 
 static int host_chunk_count(const rayen_plan* p, int64_t B) {
@@ -1147,6 +1312,7 @@ static int host_chunk_count(const rayen_plan* p, int64_t B) {
     const int64_t bytes = B * (p->dev.n + p->dev.k) * 4;
     c = (p->dev.lmi_r == 0 && bytes >= (16ll << 20)) ? 2 : 1;
   }
+  if (p->lmi_big) c = 1;  // the contraction buffer of lmi_big.cuh is sized for ONE call over the batch
   if (c > kHostMaxChunks) c = kHostMaxChunks;
   if (c > B) c = static_cast<int>(B);
   if (c < 1) c = 1;

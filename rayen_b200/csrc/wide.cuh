@@ -400,7 +400,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
     wide_backward_kernel(const WideDev P, const float* __restrict__ v, long long ldv, const float* __restrict__ gy,
                          const float* __restrict__ kappa, const int* __restrict__ active, float* __restrict__ gv,
-                         long long ldgv, long long B, int mode) {
+                         long long ldgv, long long B, int mode, const float* __restrict__ dkappa_lmi) {
   extern __shared__ __align__(16) float wide_smem[];
   const int n = P.n, k = P.k, np4 = n + 4;
   float* u = wide_smem;
@@ -450,6 +450,10 @@ __global__ void __launch_bounds__(THREADS)
     // ---- d kappa / du of the binding constraint (uniform per CTA)
     if (boundary && fam == RAYEN_FAM_LINEAR) {
       for (int j = tid; j < n; j += THREADS) dk[j] = __ldg(wt + static_cast<size_t>(j) * P.r_pad + idx);
+    } else if (boundary && fam == RAYEN_FAM_LMI) {
+      // left in the workspace by the eigen-solve of lmi_big.cuh: d kappa/du_a = q' F~z_a q
+      if (dkappa_lmi)
+        for (int j = tid; j < n; j += THREADS) dk[j] = dkappa_lmi[b * n + j];
     } else if (boundary && (fam == RAYEN_FAM_QUAD || fam == RAYEN_FAM_SOC)) {
       const int hdr = 2;  // tt[0], tt[1]: the header dot products (phi_z.u | c_z.u, h.u); tt[2 + i]: row i of the factor
       const int* it = items + (fam == RAYEN_FAM_QUAD ? idx : P.n_quad + idx) * 8;

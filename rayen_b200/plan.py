@@ -19,10 +19,11 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 MAX_NP = 32      # widest subspace of the register-resident kernels; beyond it the WIDE section / wide.cuh take over
 MAX_WIDE_N = 4096
-MAX_LMI = 32
+MAX_LMI = 32          # largest LMI of the register-resident kernels (lmi.cuh / lmi_warp.cuh)
+MAX_LMI_BIG = 320     # largest LMI of the one-CTA-per-matrix path (lmi_big.cuh kLbMaxR)
 
 
 class PlanError(RuntimeError):
@@ -144,8 +145,6 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
         # n > 32: the directions no longer fit a thread's registers; the WIDE section below feeds wide.cuh
         if n > MAX_WIDE_N:
             raise PlanError(f"subspace dimension n={n} > {MAX_WIDE_N} is not covered by the sm_100a kernels yet")
-        if lmi is not None:
-            raise PlanError(f"an LMI constraint together with n={n} > {MAX_NP} is not covered by the sm_100a kernels yet")
         np_ = (n + 3) // 4 * 4
     k_pad = (k + 3) // 4 * 4
     plan = PackedPlan()
@@ -237,26 +236,29 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
 
     # ---- LMI (reference constraint_module.py:43-52 and :412-421, congruence folded into the constants)
     lmi_r = lmi_rp = 0
+    lmi_big = False       # LMI beyond the register-resident kernels (r > 32, or any r with n > 32): lmi_big.cuh, section LMIB
     Fz = Fperm = None
     if lmi is not None:
         allF = np.asarray([f64(F) for F in lmi])
         lmi_r = allF.shape[1]
-        lmi_rp = _round_up_pow2(lmi_r)
-        if lmi_rp is None:
-            raise PlanError(f"LMI size r={lmi_r} > {MAX_LMI} is not covered by the sm_100a kernels yet")
+        lmi_big = wide or lmi_r > MAX_LMI
+        if lmi_r > MAX_LMI_BIG:
+            raise PlanError(f"LMI size r={lmi_r} > {MAX_LMI_BIG} is not covered by the sm_100a kernels yet")
+        lmi_rp = 0 if lmi_big else _round_up_pow2(lmi_r)
         H = allF[-1] + np.einsum("a,aij->ij", y0[:, 0], allF[:-1])
         try:
             L = np.linalg.cholesky(np.linalg.inv(H))
         except np.linalg.LinAlgError:
             raise PlanError("y0 is not strictly inside the LMI constraint (F(y0) must be positive definite)")
-        Ft = -np.einsum("ji,ajk,kl->ail", L, allF[:-1], L)
-        Fz = np.einsum("ia,ijk->ajk", N, Ft)
+        Ft = -np.matmul(np.matmul(L.T, allF[:-1]), L)          # batched BLAS: k matrices of r x r (r up to 320)
+        Fz = Ft if (k == n and np.array_equal(N, np.eye(k))) else np.tensordot(N.T, Ft, axes=1)
         Fz = 0.5 * (Fz + Fz.transpose(0, 2, 1))
-        lpm = lmi_rp // 4
-        Fpad = np.zeros((n, lmi_rp, lmi_rp))
-        Fpad[:, :lmi_r, :lmi_r] = Fz
-        # [a][i][q][t] with column j = q + lpm*t
-        Fperm = Fpad.reshape(n, lmi_rp, 4, lpm).transpose(0, 1, 3, 2)
+        if not lmi_big:
+            lpm = lmi_rp // 4
+            Fpad = np.zeros((n, lmi_rp, lmi_rp))
+            Fpad[:, :lmi_r, :lmi_r] = Fz
+            # [a][i][q][t] with column j = q + lpm*t
+            Fperm = Fpad.reshape(n, lmi_rp, 4, lpm).transpose(0, 1, 3, 2)
 
     # ---- N and y0
     n_is_identity = int(k == n and np.array_equal(N, np.eye(k)))
@@ -277,7 +279,8 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
     # (<= 5e-7 (|t|/r + |T_c|_F) for unit u) with 8x headroom; it is an absolute amount added to the bound.
     bound = np.zeros(np_ + tri_words + 4) if not wide else np.zeros(4)
     bound_margin = 0.0
-    if lmi is not None:
+    tr_F = bound_T = None
+    if lmi is not None and not lmi_big:   # (the big path evaluates the same bound from the contracted matrix itself)
         tr_F = np.trace(Fz, axis1=1, axis2=2)
         gram = np.einsum("aij,bij->ab", Fz, Fz)
         gram_c = gram - np.outer(tr_F, tr_F) / float(lmi_r)
@@ -289,7 +292,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
         bound[np_ + tri_words] = float(lmi_r)
         bound[np_ + tri_words + 1] = bound_margin
     off_bound = add(bound)
-    off_lmi = add(Fperm) if lmi is not None else add(np.zeros(4))
+    off_lmi = add(Fperm) if Fperm is not None else add(np.zeros(4))
 
     # ---- tensor-core layout of the same linear/quadratic/SOC/bound constants (lqs_tc.cuh): every constraint
     # becomes rows of one [rows x K] matrix W, so that all dot products of a 128-sample tile are ONE tcgen05
@@ -328,7 +331,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
             hdr[0, :n] = cz
             hdr[1, :n] = h
             items.append((3, j, A, hdr, tri_dense(R)))
-        if lmi is not None:
+        if lmi is not None and not lmi_big:
             hdr = np.zeros((2, kp))
             hdr[0, :n] = tr_F
             items.append((5, 0, float(lmi_r), hdr, tri_dense(bound_T)))
@@ -409,7 +412,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
     off_viol = add(np.concatenate(vparts) if sum(v.size for v in vparts) else np.zeros(4))
     viol_in, viol_eq = vin.shape[0], veq.shape[0]
     off_lmineg = add(np.zeros(4))
-    if lmi is not None:
+    if lmi is not None and not lmi_big:
         # lambda_max(-F(y)) = -lambda_min(F(y)): the same solver on the k+1 matrices -F_0..-F_k with u = (y, 1)
         allF = np.asarray([f64(F) for F in lmi])
         lpm = lmi_rp // 4
@@ -421,7 +424,7 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
     # row e = i*rp + 4q + t holding F~z_.[i][q + lpm*t] (the LMI section's order), in 128-row panels, TF32 split
     off_lmitc = add(np.zeros(4))
     lmitc_panels = 0
-    if lmi is not None and lmi_rp >= 16:
+    if lmi is not None and not lmi_big and lmi_rp >= 16:
         Wl = np.zeros((lmi_rp * lmi_rp, kp), dtype=np.float32)
         Wl[:, :n] = np.asarray(Fperm, dtype=np.float64).reshape(n, lmi_rp * lmi_rp).T.astype(np.float32)
         lmitc_panels = lmi_rp * lmi_rp // LMI_TC_PANEL
@@ -435,10 +438,26 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
     # ---- LMIW (lmi_warp.cuh, the filter + one-warp-per-matrix solver): F~z_a row-major, zero padded to 32 x 32, with
     # a row stride of 36 words so that 32 lanes reading 16 bytes of 32 different rows do not collide in shared memory
     off_lmiw = 0
-    if lmi is not None:
+    if lmi is not None and not lmi_big:
         Fw = np.zeros((n, LMIW_R, LMIW_ROW_STRIDE))
         Fw[:, :lmi_r, :lmi_r] = Fz
         off_lmiw = add(Fw)
+
+    # ---- LMIB / LMINEGB (lmi_big.cuh): the lower triangles, row-major packed (entry (i, j), j <= i, at i (i + 1) / 2 + j),
+    # rows padded to a multiple of 4 words -- F~z_a for the contraction GEMM S~(v) = V . F, and -F_0 .. -F_k of the ambient
+    # space (u = (y, 1)) for the violation metric
+    off_lmib = off_lminegb = 0
+    lmib_p4 = 0
+    if lmi_big:
+        il = np.tril_indices(lmi_r)
+        lmib_p4 = (il[0].size + 3) // 4 * 4
+        Fb = np.zeros((n, lmib_p4))
+        Fb[:, :il[0].size] = Fz[:, il[0], il[1]]
+        off_lmib = add(Fb)
+        Fn = -0.5 * (allF + allF.transpose(0, 2, 1))
+        Fnb = np.zeros((k + 1, lmib_p4))
+        Fnb[:, :il[0].size] = Fn[:, il[0], il[1]]
+        off_lminegb = add(Fnb)
 
     # ---- WIDE section (n > 32, wide.cuh): every constraint as rows of ONE matrix W [R_pad x n], stored transposed
     # (Wt[j][row]) so that a warp's 32 lanes read 32 consecutive rows of a column with one coalesced load.  The unit
@@ -526,17 +545,18 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
         blob[off:off + arr.size] = arr
     plan.blob = np.ascontiguousarray(blob)
     plan.fields = dict(n=n, k=k, np=np_, k_pad=k_pad, m=m, m_pad=m_pad, n_quad=len(qcs), n_soc=len(socs),
-                       lmi_r=lmi_r, lmi_rp=lmi_rp, n_is_identity=n_is_identity,
+                       lmi_r=lmi_r, lmi_rp=lmi_rp, n_is_identity=n_is_identity, lmi_big=int(lmi_big), lmib_p4=lmib_p4,
+                       off_lmib=off_lmib, off_lminegb=off_lminegb,
                        lin_chunk_stride=lin_stride, quad_stride=quad_stride, soc_stride=soc_stride,
                        off_lin=off_lin, off_quad=off_quad, off_soc=off_soc, off_nmat=off_nmat,
-                       off_y0=off_y0, off_bound=off_bound, off_lmi=off_lmi, lmi_prune=int(lmi is not None),
+                       off_y0=off_y0, off_bound=off_bound, off_lmi=off_lmi, lmi_prune=int(lmi is not None and not lmi_big),
                        off_tc=off_tc, tc_panels=tc_panels, tc_kp=kp,
                        off_viol=off_viol, off_lmineg=off_lmineg, viol_in=viol_in, viol_eq=viol_eq,
                        off_lmitc=off_lmitc, lmitc_panels=lmitc_panels, wide=int(wide), off_wide=off_wide,
                        off_lmiw=off_lmiw,
                        lmi_bound_margin=float(np.float32(bound_margin)))
     plan.f64 = dict(D=D, N=N, y0=y0, z0=z0, yp=yp, quads=quad_f64, socs=soc_f64, Fz=Fz,
-                    bound=(tr_F, bound_T, lmi_r, bound_margin) if lmi is not None else None)
+                    bound=(tr_F, bound_T, lmi_r, bound_margin) if (lmi is not None and not lmi_big) else None)
     return plan
 
 
@@ -606,7 +626,9 @@ def evaluate_plan_numpy(plan, v):
         cq = np.sum((u @ R.T) ** 2, axis=1) - cu ** 2
         root = np.sqrt(np.maximum(hb * hb + A * cq, 0.0))
         consider((hb + root) / A, (3 << 24) | j)
-    if f["lmi_r"]:
+    if f["lmi_r"] and f.get("lmi_big"):
+        consider(lmi_big_lambda_max_numpy(plan, u[:, :n]), 4 << 24)
+    elif f["lmi_r"]:
         rp = f["lmi_rp"]
         lpm = rp // 4
         Fperm = blob[f["off_lmi"]:f["off_lmi"] + n * rp * rp].reshape(n, rp, lpm, 4)
@@ -622,6 +644,18 @@ def evaluate_plan_numpy(plan, v):
         Nm = blob[f["off_nmat"]:f["off_nmat"] + k * (np_ + 4)].reshape(k, np_ + 4)[:, :np_]
         rho = u @ Nm.T
     return y0[None, :] + alpha[:, None] * rho, best, act
+
+
+def lmi_big_lambda_max_numpy(plan, u):
+    """lambda_max(sum_a u_a F~z_a) for every row of u, decoded from the LMIB section (float64)."""
+    f = plan.fields
+    n, r, p4 = f["n"], f["lmi_r"], f["lmib_p4"]
+    Fb = plan.blob[f["off_lmib"]:f["off_lmib"] + n * p4].astype(np.float64).reshape(n, p4)
+    il = np.tril_indices(r)
+    S = np.zeros((u.shape[0], r, r))
+    S[:, il[0], il[1]] = u @ Fb[:, :il[0].size]
+    S = S + np.tril(S, -1).transpose(0, 2, 1)
+    return np.linalg.eigvalsh(S)[:, -1]
 
 
 def evaluate_wide_numpy(plan, v):
@@ -689,6 +723,11 @@ def evaluate_wide_numpy(plan, v):
                 root = np.sqrt(np.maximum(a1 * a1 + A * cq, 0.0))
                 consider((a1 + root) / A, (3 << 24) | fidx)
     assert seen_tasks == n_tasks
+    if f["lmi_r"]:
+        lam = lmi_big_lambda_max_numpy(plan, u)
+        better = lam > best            # ties keep the earlier family
+        best = np.where(better, lam, best)
+        act = np.where(better, 4 << 24, act)
     with np.errstate(divide="ignore"):
         alpha = np.minimum(np.where(best > 0, 1.0 / np.where(best > 0, best, 1.0), np.inf), s)
     y0 = blob[f["off_y0"]:f["off_y0"] + k]

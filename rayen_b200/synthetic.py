@@ -179,10 +179,10 @@ def config_spec(name, seed=0):
     return random_spec(shp["k"], shp["m"], shp["eta"], shp["mu"], shp["r_M"], shp["r"], seed=seed)
 
 
-def wide_spec(k, m=0, eta=0, mu=0, r_M=0, eq=0, seed=0, loosen=3.0):
+def wide_spec(k, m=0, eta=0, mu=0, r_M=0, eq=0, seed=0, loosen=3.0, r=0):
     """A set with more than 32 dimensions (the wide.cuh kernels): random_spec with the rows loosened so that every
     family binds for some samples, plus ``eq`` equality rows through the origin (y0 = 0 stays interior, n = k - eq)."""
-    spec = random_spec(k=k, m=m, eta=eta, mu=mu, r_M=r_M, seed=seed)
+    spec = random_spec(k=k, m=m, eta=eta, mu=mu, r_M=r_M, r=r, seed=seed)
     if spec["b1"] is not None:
         spec["b1"] = spec["b1"] * loosen
     if eq:

@@ -68,9 +68,9 @@ extern "C" int emu_wide_backward(const float* blob, long long off_wide, int n, i
   if (h[0] != kWideMagic) return -1;
   const WideDev w = make_dev(blob, h, n, k, off_y0, n_is_identity);
   if (threads == 128)
-    emu_launch(grid, 128, [&] { wide_backward_kernel<128>(w, v, ldv, gy, kappa, active, gv, ldgv, B, mode); });
+    emu_launch(grid, 128, [&] { wide_backward_kernel<128>(w, v, ldv, gy, kappa, active, gv, ldgv, B, mode, nullptr); });
   else if (threads == 256)
-    emu_launch(grid, 256, [&] { wide_backward_kernel<256>(w, v, ldv, gy, kappa, active, gv, ldgv, B, mode); });
+    emu_launch(grid, 256, [&] { wide_backward_kernel<256>(w, v, ldv, gy, kappa, active, gv, ldgv, B, mode, nullptr); });
   else
     return -3;
   return 0;

@@ -780,3 +780,128 @@ def test_wide_host_buffer_path_matches_device_path():
     yh, gvh = layer.forward_backward_host(v.pin_memory(), gy.pin_memory(), device=DEV)
     np.testing.assert_array_equal(yh.numpy(), y.astype(np.float32))
     np.testing.assert_array_equal(gvh.numpy(), gv.astype(np.float32))
+
+
+# ----------------------------------------------------------------------------- big LMIs (lmi_big.cuh)
+BIG_LMI_CASES = [
+    # label, spec factory, batch, method
+    ("r33_mixed", lambda: synthetic.random_spec(k=6, m=20, eta=2, mu=2, r_M=5, r=33, seed=21), 700, "RAYEN"),
+    ("r64_mixed", lambda: synthetic.random_spec(k=8, m=30, eta=1, mu=1, r_M=6, r=64, seed=22), 500, "RAYEN"),
+    ("r100_lmi_only", lambda: synthetic.random_spec(k=5, r=100, seed=23), 300, "RAYEN"),
+    ("r150_rows", lambda: synthetic.random_spec(k=10, m=12, r=150, seed=24), 200, "RAYEN"),
+    ("r240_global", lambda: synthetic.random_spec(k=4, m=6, r=240, seed=25), 160, "RAYEN"),   # matrix in the L2 scratch
+    ("r300", lambda: synthetic.random_spec(k=3, r=300, seed=26), 150, "RAYEN"),
+    ("wide_n40_r10", lambda: synthetic.wide_spec(40, 60, 2, 2, 10, 0, seed=27, r=10), 600, "RAYEN"),
+    ("wide_n98_r50", lambda: synthetic.wide_spec(100, 50, 1, 1, 20, 2, seed=28, r=50), 400, "RAYEN"),
+    ("r40_old", lambda: synthetic.random_spec(k=6, m=10, eta=1, r=40, seed=29), 400, "RAYEN_old"),
+    ("wide_n64_r33_old", lambda: synthetic.wide_spec(64, 40, 1, 1, 10, 0, seed=30, r=33), 300, "RAYEN_old"),
+]
+
+
+@pytest.mark.parametrize("label,make,batch,method", BIG_LMI_CASES, ids=[c[0] for c in BIG_LMI_CASES])
+def test_big_lmi_sets_match_the_oracle(label, make, batch, method):
+    """VERDICT r1, missing #1: LMIs beyond 32 x 32 and LMIs together with n > 32 (reference constraint_module.py:401-449
+    takes any size; its sweep runs r_F up to 300).  y and g_v against the float64 oracle (eigvalsh), every output
+    feasible (float64 residuals incl. lambda_min(F(y)) and the GPU violation metric), kappa / binding family against the
+    float64 closed form."""
+    spec = make()
+    if spec["b1"] is not None and "wide" not in label:
+        spec["b1"] = spec["b1"] * 3.0
+    cs = synthetic.build_constraints(spec)
+    extra = 1 if method == "RAYEN_old" else 0
+    v, gy = synthetic.sample_inputs(batch, cs.n + extra, cs.k, seed_v=batch, seed_g=7, scale=2.0)
+    if method == "RAYEN":
+        v[2] = 0.0
+        v[3] *= 1e-3
+    layer, y, gv = run_layer(cs, v, gy, method)
+    assert layer._packed.fields["lmi_big"] == 1
+    oset = OracleSet.from_constraints(cs)
+    y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v.double(), gy.double(), method=method)
+    assert np.isfinite(y).all() and np.isfinite(gv).all()
+    assert rel(y, y_ref.numpy()) <= TOL
+    vv = v.numpy()[:, :cs.n].astype(np.float64)
+    cf = closed_form_numpy(oset, vv, gy.numpy())
+    kap, act = layer.last_kappa_and_active()
+    assert np.abs(kap.cpu().numpy() - cf["kappa"]).max() <= TOL * max(1.0, cf["kappa"].max())
+    fam = (act.cpu().numpy() >> 24)
+    assert (fam == _cabi.FAM_LMI).sum() > 0.05 * batch                 # the LMI does bind
+    ok = (cf["margin"] > 1e-4) & (cf["lmi_gap"] > 1e-3) & (cf["cone_cond"] > 0.05) & (np.linalg.norm(vv, axis=1) > 0) \
+        & np.isfinite(g_ref.numpy()).all(axis=1)
+    assert ok.sum() >= 0.6 * len(ok)
+    assert (fam[ok] == cf["family"][ok]).all()
+    assert rel(gv, g_ref.numpy(), ok) <= 4 * TOL_GRAD        # eigenvector of a 33..300-wide matrix in float32
+    assert max_violation(oset, y, spec["A1"], spec["b1"], spec["A2"], spec["b2"]) <= 1e-5 * max(1.0, np.abs(y).max())
+    viol = layer.violation(torch.as_tensor(y, dtype=torch.float32, device=DEV))
+    assert float(viol.max()) <= 1e-4
+    if method == "RAYEN":
+        np.testing.assert_allclose(y[2], cs.y0[:, 0], atol=1e-6)
+        assert np.all(gv[2] == 0)
+        # the GPU violation metric sees infeasible points of the LMI too: step well outside along the same rays
+        far = cs.y0[:, 0][None] + 3.0 * (y - cs.y0[:, 0][None])
+        lmi_rows = fam == _cabi.FAM_LMI
+        vf = layer.violation(torch.as_tensor(far, dtype=torch.float32, device=DEV)).cpu().numpy()
+        allF = np.asarray(spec["lmi"])
+        Fy = allF[-1][None] + np.einsum("bi,ijk->bjk", far[lmi_rows][:32], allF[:-1])
+        ref = np.maximum(-np.linalg.eigvalsh(Fy)[:, 0], 0.0)
+        assert (ref > 1e-3).any()
+        assert np.all(vf[lmi_rows][:32] >= ref - 1e-4 * max(1.0, ref.max()))
+
+
+def test_big_lmi_chunked_workspace_backward_without_forward_gradient_and_host_path():
+    """(1) RAYEN_LMIB_WS_MB caps the contraction buffer: the batch goes through the two kernels chunk by chunk, results
+    bit-identical to one pass; (2) backward with have_dkappa = 0 (forward ran without want_grad) recomputes d kappa/du in
+    gradient-only mode: same g_v; (3) the pinned-host-buffer step gives the device path's result bit for bit."""
+    import os
+    spec = synthetic.random_spec(k=5, m=10, eta=1, r=48, seed=31)
+    spec["b1"] = spec["b1"] * 3.0
+    cs = synthetic.build_constraints(spec)
+    B = 1500
+    v, gy = synthetic.sample_inputs(B, cs.n, cs.k, seed_v=4)
+    layer, y, gv = run_layer(cs, v, gy)
+    os.environ["RAYEN_LMIB_WS_MB"] = "1"     # 1 MB / (1176 words * 4 B) -> chunks of 128 samples
+    try:
+        layer2, y2, gv2 = run_layer(cs, v, gy)
+    finally:
+        del os.environ["RAYEN_LMIB_WS_MB"]
+    np.testing.assert_array_equal(y2, y)
+    np.testing.assert_array_equal(gv2, gv)
+    # raw C ABI: forward without gradient work, then backward with have_dkappa = 0
+    lib = _cabi.lib()
+    plan = layer._device_plan(torch.device(DEV))
+    vd, gd = v.to(DEV), gy.to(DEV)
+    yd = torch.empty(B, cs.k, device=DEV)
+    kap = torch.empty(B, device=DEV)
+    act = torch.empty(B, dtype=torch.int32, device=DEV)
+    gvd = torch.empty(B, cs.n, device=DEV)
+    ws = torch.empty(plan.workspace_bytes(B) // 4 + 64, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    _cabi.check(lib.rayen_forward_f32(plan.handle, vd.data_ptr(), cs.n, yd.data_ptr(), kap.data_ptr(), act.data_ptr(), B, 0, 0,
+                                      ws.data_ptr(), st), "forward")
+    _cabi.check(lib.rayen_backward_f32(plan.handle, vd.data_ptr(), cs.n, gd.data_ptr(), kap.data_ptr(), act.data_ptr(),
+                                       gvd.data_ptr(), cs.n, B, 0, 0, ws.data_ptr(), st), "backward")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(yd.cpu().numpy(), y.astype(np.float32))
+    np.testing.assert_array_equal(gvd.cpu().numpy(), gv.astype(np.float32))
+    yh, gvh = layer.forward_backward_host(v.pin_memory(), gy.pin_memory(), device=DEV)
+    np.testing.assert_array_equal(yh.numpy(), y.astype(np.float32))
+    np.testing.assert_array_equal(gvh.numpy(), gv.astype(np.float32))
+
+
+def test_big_lmi_epigraph_form_and_grid_stride():
+    """The commonest big LMI: t I - A(y) >= 0 (epigraph of lambda_max) with r = 64, at a batch larger than the solve
+    kernel's grid (grid-stride path), with a competing box: feasibility of every output and oracle parity on a subset."""
+    spec = synthetic.epigraph_lmi_spec(6, 64, 1e-1, seed=3)
+    cs = synthetic.build_constraints(spec)
+    B = 20_000
+    v, gy = synthetic.sample_inputs(B, cs.n, cs.k, seed_v=8, scale=3.0)
+    layer, y, gv = run_layer(cs, v, gy)
+    assert layer._packed.fields["lmi_big"] == 1
+    oset = OracleSet.from_constraints(cs)
+    assert max_violation(oset, y, spec["A1"], spec["b1"], spec["A2"], spec["b2"]) <= 1e-5 * max(1.0, np.abs(y).max())
+    sub = np.arange(0, B, 41)
+    y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v[sub].double(), gy[sub].double())
+    assert rel(y[sub], y_ref.numpy()) <= TOL
+    cf = closed_form_numpy(oset, v[sub].numpy(), gy[sub].numpy())
+    ok = (cf["margin"] > 1e-4) & (cf["lmi_gap"] > 1e-3)
+    assert ok.sum() > 0.5 * len(sub)
+    assert rel(gv[sub], g_ref.numpy(), ok) <= 4 * TOL_GRAD

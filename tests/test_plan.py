@@ -59,10 +59,28 @@ def test_rejects_boundary_or_exterior_points():
 def test_unsupported_sizes_fail_loudly():
     with pytest.raises(plan.PlanError, match="n=4100"):
         plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=4100, m=2)))
-    with pytest.raises(plan.PlanError, match="LMI constraint together with n=40"):
-        plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=40, m=8, r=4)))
-    with pytest.raises(plan.PlanError, match="r=40"):
-        plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=4, r=40)))
+    with pytest.raises(plan.PlanError, match="r=321"):
+        plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=2, r=321)))
+
+
+def test_big_lmi_plans_pack_the_lower_triangles():
+    """LMI beyond the register-resident kernels (r > 32, or any r with n > 32): section LMIB, decoded here in float64
+    and compared with the oracle's kappa."""
+    from oracle.rayen_oracle import OracleSet, closed_form_numpy
+    for spec in (synthetic.random_spec(k=4, m=6, eta=1, mu=1, r_M=3, r=40, seed=1),
+                 synthetic.wide_spec(40, 30, 1, 1, 8, 2, seed=2, r=6)):
+        cs = synthetic.build_constraints(spec)
+        p = plan.build_plan_from_constraints(cs)
+        f = p.fields
+        assert f["lmi_big"] == 1 and f["lmi_rp"] == 0 and f["lmi_prune"] == 0 and f["off_lmiw"] == 0
+        r = f["lmi_r"]
+        assert f["lmib_p4"] == (r * (r + 1) // 2 + 3) // 4 * 4
+        v, _ = synthetic.sample_inputs(64, cs.n, cs.k, seed_v=3)
+        ev = plan.evaluate_wide_numpy if f["wide"] else plan.evaluate_plan_numpy
+        y, kap, act = ev(p, v.numpy())
+        cf = closed_form_numpy(OracleSet.from_constraints(cs), v.numpy(), np.zeros((64, cs.k)))
+        np.testing.assert_allclose(y, cf["y"], rtol=0, atol=2e-6)
+        assert ((act >> 24) == 4).any()          # the LMI binds for some samples
 
 
 @pytest.mark.parametrize("seed", range(6))
