@@ -383,43 +383,61 @@ def run_b200(args, rank, local_rank, world):
         return float(t.item())
 
     # ---- headline: device-resident fwd+bwd through the C ABI (rayen_forward_f32 + rayen_backward_f32), the
-    # boundary the Python drop-in binds; K steps back to back between two CUDA events on the launching stream
+    # boundary the Python drop-in binds.  One step = the forward and the backward call of one buffer set, captured once
+    # per buffer set into a CUDA graph and replayed: K replays back to back between two CUDA events on the launching
+    # stream.  (The kernels take 10-70 us; issued call by call the loop is bound by the host's launch rate on slower
+    # boxes -- `direct_launch` below is that number.)  A capture failure falls back to direct launches, loudly.
     clocks = ClockSampler(local_rank)
     barrier()
     for i in range(warmup):
         bench.step(i)
+    barrier()
+    graphs, launches_per_step = [], None
+    try:
+        side = torch.cuda.Stream(device)
+        with torch.cuda.stream(side):
+            for s in bench.sets:
+                gph = torch.cuda.CUDAGraph()
+                bench.stream = ctypes.c_void_p(side.cuda_stream)
+                l0 = _cabi.launch_count()
+                with torch.cuda.graph(gph, stream=side):
+                    bench.forward(s)
+                    bench.backward(s)
+                launches_per_step = _cabi.launch_count() - l0
+                graphs.append(gph)
+    except Exception as exc:  # noqa: BLE001
+        print(f"bench.py: CUDA-graph capture failed ({exc}); timing direct launches", file=sys.stderr)
+        graphs = []
+    bench.stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    torch.cuda.synchronize(device)
+    step_fn = (lambda i: graphs[i % POOL].replay()) if graphs else bench.step
+    for i in range(warmup):
+        step_fn(i)
     barrier()
     clocks.start()
     launches0 = _cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
+        step_fn(warmup + i)
+    e1.record()
+    barrier()
+    launches = (launches_per_step * steps) if graphs else (_cabi.launch_count() - launches0)
+    headline_ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+    # the same K steps issued call by call (no graph)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
         bench.step(warmup + i)
     e1.record()
     barrier()
-    launches = _cabi.launch_count() - launches0
-    direct_ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+    direct_launch_ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+    direct_ms = headline_ms
+    graph_ms = headline_ms if graphs else None
     # the same through nn.Module.forward + autograd backward (adds PyTorch's eager/autograd overhead per step)
     mod_fn = module_step_fn(layer, bench)
     ms_module = max_over_ranks(bench.time_loop_median(mod_fn, steps, warmup))
-    # ... and replayed from CUDA graphs (one captured fwd+bwd per buffer set): launch overhead removed
-    graph_ms = None
-    try:
-        graphs = []
-        side = torch.cuda.Stream(device)
-        with torch.cuda.stream(side):
-            for s in bench.sets:
-                gph = torch.cuda.CUDAGraph()
-                bench.stream = ctypes.c_void_p(side.cuda_stream)
-                with torch.cuda.graph(gph, stream=side):
-                    bench.forward(s)
-                    bench.backward(s)
-                graphs.append(gph)
-        bench.stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        torch.cuda.synchronize(device)
-        graph_ms = max_over_ranks(bench.time_loop_median(lambda i: graphs[i % POOL].replay(), steps, warmup))
-    except Exception:  # noqa: BLE001 - the graph variant is informational only
-        bench.stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
     # launch floor: a chain of as many empty kernels as one step launches
     per_step_launches = max(1, int(round(launches / max(steps, 1))))
     floor_ms = bench.time_loop_median(lambda i: lib.rayen_launch_empty(per_step_launches, bench.stream), 200, 20, groups=3)
@@ -523,7 +541,8 @@ def run_b200(args, rank, local_rank, world):
                    "l2": f"inputs larger than L2: rotating pool of {POOL} buffer sets, "
                          f"{POOL * batch * 4 * (3 * n + 2 * k) / 1e6:.0f} MB of algorithmic traffic per cycle",
                    "path": "rayen_forward_f32 + rayen_backward_f32 (C ABI; called here through their *_stage_* twins with "
-                           "stage_mask = 3, which launch exactly the same kernels) on device-resident buffers, plain launches"},
+                           "stage_mask = 3, which launch exactly the same kernels) on device-resident buffers; one step = the two "
+                           "calls of one buffer set, captured once into a CUDA graph and replayed (direct_launch: issued call by call)"},
         "clocks": {"sm_mhz": clock_info["sm_mhz"], "sm_max_mhz": clock_info["sm_max_mhz"],
                    "reasons": clock_info["reasons"], "samples": clock_info["samples"]},
         "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "samples/s",
@@ -543,8 +562,10 @@ def run_b200(args, rank, local_rank, world):
         "launch_floor_ms": floor_ms,
         "module_autograd": {"value": world * batch / (ms_module * 1e-3), "ms_per_step": ms_module,
                             "path": "nn.Module forward + autograd backward (PyTorch eager overhead included); median of 5 loops"},
+        "direct_launch": {"value": world * batch / (direct_launch_ms * 1e-3), "ms_per_step": direct_launch_ms,
+                          "path": "the same K steps issued call by call (cudaLaunchKernel per kernel, no graph): host-launch-rate bound on slow hosts"},
         "cuda_graph": ({"value": world * batch / (graph_ms * 1e-3), "ms_per_step": graph_ms,
-                        "path": "the C-ABI fwd+bwd of each buffer set captured once, replayed; median of 5 loops"}
+                        "path": "= the headline: the C-ABI fwd+bwd of each buffer set captured once, replayed"}
                        if graph_ms else None),
     }
     if gather is not None:
@@ -666,7 +687,7 @@ def run_b200(args, rank, local_rank, world):
             fwd_ms = eb_bench.time_loop(lambda i: eb_bench.forward(eb_bench.sets[i % eb_bench.pool]), steps_, 5)
             entry = {"fwd_bwd_samples_per_s": eb / (ms * 1e-3), "ms_per_step": ms, "fwd_ms": fwd_ms,
                      "hbm_frac": per_set / (ms * 1e-3) / 1e9 / peak}
-            if ecs.lmic is not None and (ecs.lc is not None or ecs.qcs or ecs.socs):
+            if ecs.lmic is not None and (ecs.lc is not None or ecs.qcs or ecs.socs) and not elayer._packed.fields.get("lmi_big"):
                 eb_bench.forward(eb_bench.sets[0])
                 torch.cuda.synchronize(device)
                 ll, fl_ = eb_bench.counters(eb_bench.sets[0])
@@ -699,6 +720,20 @@ def run_b200(args, rank, local_rank, world):
                                                     ("wide_n256", (256, 1024, 0, 0, 0, 8192))):
             ecs = synthetic.build_constraints(synthetic.wide_spec(wk, wm, weta, wmu, wrm, 0, seed=1))
             run_extra(f"{wname}_B{wb}", ecs, wb, steps_=20)
+        # LMIs beyond the register-resident kernels (lmi_big.cuh): a 64 x 64 LMI in dim 32 next to 64 rows,
+        # the reference sweep's r_F = 100, k = 100 point (LMI only, 2000 samples), and a wide set (dim 64) with a 33 x 33 LMI
+        bspec = synthetic.random_spec(k=32, m=64, r=64, seed=5)
+        bspec["b1"] = bspec["b1"] * 3.0
+        run_extra("lmi_r64_n32_B8192", synthetic.build_constraints(bspec), 8192, steps_=10)
+        run_extra("lmi_r100_n100_B2000", synthetic.build_constraints(synthetic.random_spec(k=100, r=100, seed=6)), 2000, steps_=10)
+        run_extra("wide_n64_lmi_r33_B8192", synthetic.build_constraints(synthetic.wide_spec(64, 128, 2, 2, 16, 0, seed=7, r=33)),
+                  8192, steps_=10)
+        # the widest linear point of the reference sweep that fits one block of constants: 100 rows in dimension 10000
+        import numpy as _np
+        _rng = _np.random.default_rng(10)
+        wspec = dict(A1=_rng.uniform(-1.0, 1.0, size=(100, 10000)), b1=_rng.uniform(0.1, 1.0, size=(100, 1)), A2=None, b2=None,
+                     qcs=[], socs=[], lmi=None, y0=_np.zeros((10000, 1)))
+        run_extra("wide_n10000_rows100_B2000", synthetic.build_constraints(wspec), 2000, steps_=5)
         line["extra"] = extra
 
     print(json.dumps(line), flush=True)

@@ -29,7 +29,7 @@ extern "C" {
 /* error codes (negative); positive return values are cudaError_t */
 #define RAYEN_OK 0
 #define RAYEN_ERR_BAD_ARGUMENT (-1)
-#define RAYEN_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels cover (n > 4096, LMI size > 320) */
+#define RAYEN_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels cover (n > 12288, LMI size > 320) */
 #define RAYEN_ERR_ABI (-3)
 #define RAYEN_ERR_NO_DEVICE (-4)
 
@@ -82,7 +82,7 @@ extern "C" {
  *   LMIW    (plans with an LMI) F~z_a once more for the filter + one-warp-per-matrix solver of lmi_warp.cuh: n matrices,
  *           zero padded to 32 x 32, row-major with a row stride of 36 words ([a][row][36]); lane j of a warp reads
  *           row j (= column j, the matrices are symmetric) as eight 16-byte loads, conflict-free in shared memory
- *   WIDE    (wide == 1: 32 < n <= 4096, linear + quadratic + SOC; wide.cuh) 16 int32 words {magic 0x57494445, R_pad,
+ *   WIDE    (wide == 1: 32 < n <= 12288, linear + quadratic + SOC (+ an LMI through LMIB); wide.cuh) 16 int32 words {magic 0x57494445, R_pad,
  *           n_tasks, off_tasks, off_wt, off_nt, off_nrow, k32, np, off_items, n_quad, n_soc, n_rounds, off_rounds,
  *           layout version 3, 0} (offsets in words from `blob`), then
  *             Wt      [n][R_pad], Wt[j][row] = W[row][j]; W stacks the rows of D (zero padded to 64), then per round of

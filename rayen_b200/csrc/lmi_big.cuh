@@ -11,14 +11,17 @@
 //      128 x 128 x 8 tiles, 8 x 8 outputs per thread, operands staged through shared memory with a register prefetch.
 //      The result goes to the workspace (L2 / HBM): B_c x P floats; forward_impl cuts the batch into chunks that fit.
 //      (S~ is linear in v: the eigen kernel divides by |v| -- lambda_max(S~(u)) = lambda_max(S~(v)) / |v|.)
-//   2. lmib_solve_kernel<THREADS, GLOBAL_A>: one CTA per sample.
+//   2. lmib_solve_kernel<THREADS>: one CTA per sample.
 //        a. Wolkowicz-Styan bound straight from the packed entries, in the cancellation-free centred form
 //           (mean + sqrt((r-1)/r (sum_i (S_ii - mean)^2 + 2 sum_{i>j} S_ij^2))): below the prior kappa => the LMI cannot
 //           bind, the sample is finished (nothing is written).
-//        b. the matrix is expanded to a full square (odd row stride: a thread per row walks its row conflict-free) in
-//           shared memory (r <= 232) or, beyond that, in an L2-resident scratch of the workspace (GLOBAL_A);
-//        c. Householder tridiagonalisation, thread i = row i: p = tau A v as a row walk, rank-2 update of the trailing
-//           block, the reflector stays in column k (back-transform);
+//        b. the packed lower triangle (row i at word i (i + 1) / 2) is copied to shared memory as it is, scaled by
+//           1 / |v|: r (r + 1) / 2 words, 205 KB at r = 320.  Thread i owns row i.  Entry (i, j), j <= i, of 32
+//           consecutive rows falls into 32 different banks (triangular numbers are a complete residue system modulo a
+//           power of two), entry (j, i), j > i, of 32 consecutive i is 32 consecutive words: both walks are conflict-free;
+//        c. Householder tridiagonalisation: p = tau A v as a walk along row i up to the diagonal and down column i below
+//           it, rank-2 update of the lower triangle of the trailing block, the reflector stays in column k
+//           (back-transform);
 //        d. lambda_max by multisection: every thread probes one shift with the pivot recurrence of T - xI (all pivots
 //           negative <=> x above the spectrum), THREADS sections per round;
 //        e. merge with the prior (ties keep the earlier family, like torch.max), and when the LMI binds: kappa, tag, and
@@ -39,8 +42,7 @@
 
 namespace rayen {
 
-constexpr int kLbMaxR = 320;          // largest LMI of this path (thread per row, <= 320 threads)
-constexpr int kLbSmemMaxR = 232;      // beyond this the square matrix no longer fits 227 KB of shared memory
+constexpr int kLbMaxR = 320;          // largest LMI of this path (thread per row, <= 320 threads; 215 KB of shared memory)
 constexpr int kLbTileM = 128, kLbTileN = 128, kLbTileK = 8, kLbGemmThreads = 256;
 
 struct LmiBigDev {
@@ -51,16 +53,12 @@ struct LmiBigDev {
   int off_y0;
 };
 
-__host__ __device__ inline int lmib_ld(int r) { return r | 1; }  // odd row stride of the square matrix
-// vectors behind the matrix: vv, ww, d, e, tau, dp, dm, q  (r4 each) + 40 words of reduction scratch
+__host__ __device__ inline int lmib_tri(int i) { return i * (i + 1) / 2; }  // first word of packed row i
+// vectors in front of the matrix: vv, ww, d, e, tau, dp, dm, q  (r4 each) + 40 words of reduction scratch
 __host__ __device__ inline size_t lmib_vec_words(int r) { return static_cast<size_t>(8) * ((r + 3) / 4 * 4) + 40; }
-__host__ __device__ inline size_t lmib_square_words(int r) {
-  const size_t sq = static_cast<size_t>(r) * lmib_ld(r);
-  const size_t pk = static_cast<size_t>(r) * (r + 1) / 2 + 4;  // the gradient weights reuse the matrix storage
-  return ((sq > pk ? sq : pk) + 3) / 4 * 4;
-}
-__host__ __device__ inline size_t lmib_smem_bytes(int r, bool global_a) {
-  return (lmib_vec_words(r) + (global_a ? 0 : lmib_square_words(r))) * sizeof(float);
+__host__ __device__ inline size_t lmib_smem_bytes(int r) {
+  const size_t p4 = (static_cast<size_t>(r) * (r + 1) / 2 + 3) / 4 * 4;
+  return (lmib_vec_words(r) + p4) * sizeof(float);
 }
 
 // ----------------------------------------------------------------------------- 1. contraction GEMM
@@ -201,13 +199,13 @@ __device__ __forceinline__ float lb_alpha(float kap, float s, float beta, int mo
   return (mode == RAYEN_MODE_RAYEN_OLD) ? 1.0f / (expf(beta) + kap) : fminf(1.0f / kap, s);
 }
 
-template <int THREADS, bool GLOBAL_A>
+template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
     lmib_solve_kernel(const LmiBigDev P, const float* __restrict__ S, const float* __restrict__ v, long long ldv,
                       float* __restrict__ y, float* __restrict__ kappa_io, int* __restrict__ active_io,
-                      float* __restrict__ dkappa, float* __restrict__ scratch, long long Bc, int mode, int flags) {
+                      float* __restrict__ dkappa, long long Bc, int mode, int flags) {
   extern __shared__ __align__(16) float lmib_smem[];
-  const int r = P.r, ld = lmib_ld(r), r4 = (r + 3) / 4 * 4, n = P.n, k = P.k, p4 = P.p4;
+  const int r = P.r, r4 = (r + 3) / 4 * 4, n = P.n, k = P.k, p4 = P.p4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* vv = lmib_smem;
   float* ww = vv + r4;
@@ -219,15 +217,11 @@ __global__ void __launch_bounds__(THREADS)
   float* sq = dm + r4;
   float* red = sq + r4;           // 16 words
   int* redi = reinterpret_cast<int*>(red + 16);  // 16 words
-  float* bc = red + 32;           // 8 words of broadcast values
-  float* A;
-  if constexpr (GLOBAL_A)
-    A = scratch + static_cast<size_t>(blockIdx.x) * lmib_square_words(r);
-  else
-    A = red + 40;
+  float* A = red + 40;            // packed lower triangle, p4 words (16-byte aligned)
   const bool want_grad = (flags & (kLbFlagGrad | kLbFlagGradOnly)) != 0;
   const bool grad_only = (flags & kLbFlagGradOnly) != 0;
   const bool lambda_out = (flags & kLbFlagLambdaOut) != 0;
+  const int ti = lmib_tri(tid);   // row tid of the packed matrix
 
   for (long long b = blockIdx.x; b < Bc; b += gridDim.x) {
     __syncthreads();  // the previous sample's readers of the shared vectors are done
@@ -251,47 +245,43 @@ __global__ void __launch_bounds__(THREADS)
       if (!need) continue;  // uniform per CTA
     }
 
-    // ---- a. pruning bound from the packed entries (diagonal entry of row i sits at i (i + 1) / 2 + i)
-    float tr = 0.f;
-    for (int i = tid; i < r; i += THREADS) tr += srow[static_cast<size_t>(i) * (i + 1) / 2 + i];
-    const float mean = lb_block_sum<THREADS>(tr, red) / static_cast<float>(r);
-    float dev = 0.f;
-    for (int i = warp; i < r; i += THREADS / 32) {
-      const float* rp = srow + static_cast<size_t>(i) * (i + 1) / 2;
-      for (int j = lane; j < i; j += 32) {
-        const float x = rp[j];
-        dev = fmaf(2.f * x, x, dev);
-      }
-      if (lane == 0) {
-        const float x = rp[i] - mean;
-        dev = fmaf(x, x, dev);
-      }
-    }
-    const float dev2 = lb_block_sum<THREADS>(dev, red);
-    if (!grad_only) {
-      // lambda_max <= mean + sqrt((r - 1) / r dev2); allowance for the float32 sums: 2e-6 of the scale involved
-      const float rad = sqrtf(dev2 * (static_cast<float>(r - 1) / static_cast<float>(r)));
-      const float ub = (mean + rad) * inv + 2e-6f * (fabsf(mean) + rad) * inv;
-      if (ub <= kprior) continue;  // uniform per CTA: the LMI cannot bind (kprior = 0: lambda_max <= 0, kappa_LMI = 0)
-    }
-
-    // ---- b. square matrix, scaled to the unit direction
-    for (int i = warp; i < r; i += THREADS / 32) {
-      const float* rp = srow + static_cast<size_t>(i) * (i + 1) / 2;
-      for (int j = lane; j <= i; j += 32) {
-        const float x = rp[j] * inv;
-        A[i * ld + j] = x;
-        A[j * ld + i] = x;
-      }
+    // ---- b. the packed matrix into shared memory, scaled to the unit direction (16-byte loads: rows of S are 16-byte
+    //         aligned, p4 is a multiple of 4)
+    for (int e = tid; e < p4 / 4; e += THREADS) {
+      float4 x = *reinterpret_cast<const float4*>(srow + 4 * e);
+      x.x *= inv; x.y *= inv; x.z *= inv; x.w *= inv;
+      *reinterpret_cast<float4*>(A + 4 * e) = x;
     }
     __syncthreads();
+    // ---- a. pruning bound (diagonal entry of row i at tri(i) + i): lambda_max <= mean + sqrt((r-1)/r dev2), dev2 the
+    //         squared Frobenius norm of the trace-free part as a sum of squares
+    {
+      const float tr = (tid < r) ? A[ti + tid] : 0.f;
+      const float mean = lb_block_sum<THREADS>(tr, red) / static_cast<float>(r);
+      float dev = 0.f;
+      if (tid < r) {
+        for (int j = 0; j < tid; ++j) {
+          const float x = A[ti + j];
+          dev = fmaf(2.f * x, x, dev);
+        }
+        const float x = A[ti + tid] - mean;
+        dev = fmaf(x, x, dev);
+      }
+      const float dev2 = lb_block_sum<THREADS>(dev, red);
+      if (!grad_only) {
+        // allowance for the float32 sums: 2e-6 of the scale involved
+        const float rad = sqrtf(dev2 * (static_cast<float>(r - 1) / static_cast<float>(r)));
+        const float ub = (mean + rad) + 2e-6f * (fabsf(mean) + rad);
+        if (ub <= kprior) continue;  // uniform per CTA: the LMI cannot bind (kprior = 0: lambda_max <= 0, kappa_LMI = 0)
+      }
+    }
 
     // ---- c. Householder tridiagonalisation (lower form): thread i owns row i
     for (int kk = 0; kk + 2 < r; ++kk) {
       const int i = tid;
-      const float xi = (i > kk && i < r) ? A[i * ld + kk] : 0.f;
+      const float xi = (i > kk && i < r) ? A[ti + kk] : 0.f;
       const float tail2 = lb_block_sum<THREADS>((i > kk + 1) ? xi * xi : 0.f, red);
-      const float x1 = A[(kk + 1) * ld + kk];
+      const float x1 = A[lmib_tri(kk + 1) + kk];
       const bool skip = !(tail2 > 0.f);  // column already tridiagonal
       const float sigma = fmaf(x1, x1, tail2);
       const float rt = sqrtf(sigma);
@@ -300,45 +290,79 @@ __global__ void __launch_bounds__(THREADS)
       const float vi = skip ? 0.f : ((i == kk + 1) ? x1 - alpha : ((i > kk + 1 && i < r) ? xi : 0.f));
       if (i < r) vv[i] = vi;
       if (i == kk) {
-        sd[kk] = A[kk * ld + kk];
+        sd[kk] = A[ti + kk];
         se[kk] = skip ? x1 : alpha;
         stau[kk] = tau;
       }
       __syncthreads();
       if (skip) continue;  // uniform
-      if (i == kk + 1) A[i * ld + kk] = vi;  // the reflector stays in column kk (its other entries are already there)
-      // p = tau A v over the trailing block
+      if (i == kk + 1) A[ti + kk] = vi;  // the reflector stays in column kk (its other entries are already there)
+      // p = tau A v over the trailing block: along row i up to the diagonal, then down column i.  v comes in 16-byte
+      // broadcast loads (one per four entries), the column walk keeps a running offset (row j + 1 starts j + 1 words
+      // behind row j): ~2.3 instructions per entry instead of ~6 -- the walk is issue-bound, not bandwidth-bound
       float pi = 0.f;
       if (i > kk && i < r) {
-        const float* ar = A + i * ld;
+        const float* ar = A + ti;
         float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
         int j = kk + 1;
-        for (; j + 4 <= r; j += 4) {
-          p0 = fmaf(ar[j], vv[j], p0);
-          p1 = fmaf(ar[j + 1], vv[j + 1], p1);
-          p2 = fmaf(ar[j + 2], vv[j + 2], p2);
-          p3 = fmaf(ar[j + 3], vv[j + 3], p3);
+        for (; (j & 3) && j <= i; ++j) p0 = fmaf(ar[j], vv[j], p0);
+        for (; j + 4 <= i + 1; j += 4) {
+          const float4 v4 = *reinterpret_cast<const float4*>(vv + j);
+          p0 = fmaf(ar[j], v4.x, p0);
+          p1 = fmaf(ar[j + 1], v4.y, p1);
+          p2 = fmaf(ar[j + 2], v4.z, p2);
+          p3 = fmaf(ar[j + 3], v4.w, p3);
         }
-        for (; j < r; ++j) p0 = fmaf(ar[j], vv[j], p0);
+        for (; j <= i; ++j) p0 = fmaf(ar[j], vv[j], p0);
+        j = i + 1;
+        int off = lmib_tri(j) + i;
+        for (; (j & 3) && j < r; ++j) {
+          p1 = fmaf(A[off], vv[j], p1);
+          off += j + 1;
+        }
+        for (; j + 4 <= r; j += 4) {
+          const float4 v4 = *reinterpret_cast<const float4*>(vv + j);
+          const int o1 = off + j + 1, o2 = o1 + j + 2, o3 = o2 + j + 3;
+          p0 = fmaf(A[off], v4.x, p0);
+          p1 = fmaf(A[o1], v4.y, p1);
+          p2 = fmaf(A[o2], v4.z, p2);
+          p3 = fmaf(A[o3], v4.w, p3);
+          off = o3 + j + 4;
+        }
+        for (; j < r; ++j) {
+          p2 = fmaf(A[off], vv[j], p2);
+          off += j + 1;
+        }
         pi = tau * ((p0 + p1) + (p2 + p3));
       }
       const float Kc = 0.5f * tau * lb_block_sum<THREADS>(vi * pi, red);
       const float wi = (i > kk && i < r) ? fmaf(-Kc, vi, pi) : 0.f;
       if (i < r) ww[i] = wi;
       __syncthreads();
-      // A <- A - v w' - w v' over the trailing block
+      // A <- A - v w' - w v' over the lower triangle of the trailing block
       if (i > kk && i < r) {
-        float* ar = A + i * ld;
-        for (int j = kk + 1; j < r; ++j) ar[j] = fmaf(-vi, ww[j], fmaf(-wi, vv[j], ar[j]));
+        float* ar = A + ti;
+        int j = kk + 1;
+        for (; (j & 3) && j <= i; ++j) ar[j] = fmaf(-vi, ww[j], fmaf(-wi, vv[j], ar[j]));
+        for (; j + 4 <= i + 1; j += 4) {
+          const float4 v4 = *reinterpret_cast<const float4*>(vv + j);
+          const float4 w4 = *reinterpret_cast<const float4*>(ww + j);
+          const float a0 = ar[j], a1 = ar[j + 1], a2 = ar[j + 2], a3 = ar[j + 3];
+          ar[j] = fmaf(-vi, w4.x, fmaf(-wi, v4.x, a0));
+          ar[j + 1] = fmaf(-vi, w4.y, fmaf(-wi, v4.y, a1));
+          ar[j + 2] = fmaf(-vi, w4.z, fmaf(-wi, v4.z, a2));
+          ar[j + 3] = fmaf(-vi, w4.w, fmaf(-wi, v4.w, a3));
+        }
+        for (; j <= i; ++j) ar[j] = fmaf(-vi, ww[j], fmaf(-wi, vv[j], ar[j]));
       }
       __syncthreads();
     }
     if (tid == 0) {
       if (r >= 2) {
-        sd[r - 2] = A[(r - 2) * ld + (r - 2)];
-        se[r - 2] = A[(r - 1) * ld + (r - 2)];
+        sd[r - 2] = A[lmib_tri(r - 2) + (r - 2)];
+        se[r - 2] = A[lmib_tri(r - 1) + (r - 2)];
       }
-      sd[r - 1] = A[(r - 1) * ld + (r - 1)];
+      sd[r - 1] = A[lmib_tri(r - 1) + (r - 1)];
       se[r - 1] = 0.f;
     }
     __syncthreads();
@@ -481,7 +505,7 @@ __global__ void __launch_bounds__(THREADS)
       for (int kk = r - 3; kk >= 0; --kk) {
         const float tau = stau[kk];
         if (tau == 0.f) continue;  // uniform (shared value)
-        const float vi = (tid > kk && tid < r) ? A[tid * ld + kk] : 0.f;
+        const float vi = (tid > kk && tid < r) ? A[ti + kk] : 0.f;
         const float c = tau * lb_block_sum<THREADS>(vi * qi, red);
         qi = fmaf(-c, vi, qi);
       }
@@ -490,10 +514,11 @@ __global__ void __launch_bounds__(THREADS)
       __syncthreads();
       // gradient weights over the packed order: w_e = (2 - [i = j]) q_i q_j (overwrites the matrix: no longer needed)
       float* wts = A;
-      for (int i = warp; i < r; i += THREADS / 32) {
-        const float qrow = sq[i];
-        float* wp = wts + static_cast<size_t>(i) * (i + 1) / 2;
-        for (int j = lane; j <= i; j += 32) wp[j] = (j == i) ? qrow * qrow : 2.f * qrow * sq[j];
+      if (tid < r) {
+        const float qrow = qi;
+        float* wp = wts + ti;
+        for (int j = 0; j < tid; ++j) wp[j] = 2.f * qrow * sq[j];
+        wp[tid] = qrow * qrow;
       }
       for (int e = r * (r + 1) / 2 + tid; e < p4; e += THREADS) wts[e] = 0.f;
       __syncthreads();

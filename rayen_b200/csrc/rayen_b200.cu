@@ -35,13 +35,12 @@ struct rayen_plan {
   bool viol_lmi_smem;
   bool wide;      // n > 32: the kernels of wide.cuh on the WIDE section (linear + quadratic + SOC, no LMI)
   WideDev wdev;
-  size_t wide_fwd_smem_bytes[2], wide_bwd_smem_bytes;  // forward: tiles of 8 / 16 samples
+  size_t wide_fwd_smem_bytes[3], wide_bwd_smem_bytes;  // forward: tiles of 8 / 16 / 4 samples ([2]: n too wide for 8)
   // LMI beyond the register-resident kernels (lmi_big.cuh): dev.lmi_r stays 0 (the narrow kernels see "no LMI"), the
   // other families' kernel leaves the prior (kappa, tag, y) for every sample and the two kernels of lmi_big.cuh follow
   bool lmi_big;
   LmiBigDev bdev;
   int lmib_threads;        // CTA size of the solve kernel: 64 / 128 / 256 / 320 (>= r)
-  bool lmib_global;        // r > 232: the square matrix lives in the workspace instead of shared memory
   size_t lmib_smem_bytes;
   int lmib_ctas_per_sm;
   int64_t lmib_ws_cap;     // bytes of the contracted-matrix buffer a forward call may use (RAYEN_LMIB_WS_MB, default 512)
@@ -259,14 +258,14 @@ static int allow_smem(const void* fn, size_t bytes) {
 static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** out);
 
 // ----------------------------------------------------------------------------- big LMI (lmi_big.cuh)
-typedef void (*LmibSolveFn)(const LmiBigDev, const float*, const float*, long long, float*, float*, int*, float*, float*,
+typedef void (*LmibSolveFn)(const LmiBigDev, const float*, const float*, long long, float*, float*, int*, float*,
                             long long, int, int);
-static LmibSolveFn lmib_solve_fn(int threads, bool global_a) {
+static LmibSolveFn lmib_solve_fn(int threads) {
   switch (threads) {
-    case 64: return global_a ? lmib_solve_kernel<64, true> : lmib_solve_kernel<64, false>;
-    case 128: return global_a ? lmib_solve_kernel<128, true> : lmib_solve_kernel<128, false>;
-    case 256: return global_a ? lmib_solve_kernel<256, true> : lmib_solve_kernel<256, false>;
-    default: return global_a ? lmib_solve_kernel<320, true> : lmib_solve_kernel<320, false>;
+    case 64: return lmib_solve_kernel<64>;
+    case 128: return lmib_solve_kernel<128>;
+    case 256: return lmib_solve_kernel<256>;
+    default: return lmib_solve_kernel<320>;
   }
 }
 static int allow_smem(const void* fn, size_t bytes);
@@ -290,10 +289,10 @@ static int lmib_setup(rayen_plan* p, const RayenPlanDesc* d) {
   b.off_y0 = static_cast<int>(d->off_y0);
   p->off_lminegb = static_cast<int>(d->off_lminegb);
   p->lmib_threads = b.r <= 64 ? 64 : (b.r <= 128 ? 128 : (b.r <= 256 ? 256 : 320));
-  p->lmib_global = lmib_smem_bytes(b.r, false) > static_cast<size_t>(p->max_smem_optin);
-  if (getenv("RAYEN_LMIB_GLOBAL") && atoi(getenv("RAYEN_LMIB_GLOBAL")) == 1) p->lmib_global = true;
-  p->lmib_smem_bytes = lmib_smem_bytes(b.r, p->lmib_global);
-  int per_sm = p->lmib_global ? 4 : static_cast<int>(static_cast<size_t>(p->max_smem_optin) / (p->lmib_smem_bytes + 1024));
+  p->lmib_smem_bytes = lmib_smem_bytes(b.r);
+  if (p->lmib_smem_bytes > static_cast<size_t>(p->max_smem_optin))
+    return fail(RAYEN_ERR_UNSUPPORTED, "LMI size %d needs %zu bytes of shared memory", b.r, p->lmib_smem_bytes);
+  int per_sm = static_cast<int>(static_cast<size_t>(p->max_smem_optin) / (p->lmib_smem_bytes + 1024));
   const int by_threads = 2048 / p->lmib_threads;
   if (per_sm > by_threads) per_sm = by_threads;
   if (per_sm > 16) per_sm = 16;
@@ -307,8 +306,7 @@ static int lmib_setup(rayen_plan* p, const RayenPlanDesc* d) {
   // the attribute is per function: the device maximum, so that plans of different sizes coexist
   int rc = 0;
   for (int t : {64, 128, 256, 320})
-    for (int g = 0; g < 2 && rc == 0; ++g)
-      rc = allow_smem(reinterpret_cast<const void*>(lmib_solve_fn(t, g != 0)), p->max_smem_optin);
+    if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmib_solve_fn(t)), p->max_smem_optin);
   return rc;
 }
 // samples per chunk of the contraction buffer for a call of B samples (p4 words each)
@@ -322,15 +320,13 @@ static int64_t lmib_solve_grid(const rayen_plan* p, int64_t rows) {
   const int64_t cap = static_cast<int64_t>(p->sm_count) * p->lmib_ctas_per_sm;
   return rows < cap ? (rows < 1 ? 1 : rows) : cap;
 }
-// bytes behind the common workspace prefix: the contraction buffer and, for GLOBAL_A, one square matrix per CTA
+// bytes behind the common workspace prefix: the contraction buffer
 static int64_t lmib_ws_extra(const rayen_plan* p, int64_t B, int p4) {
   const int64_t rows = lmib_chunk_rows(p, B, p4);
-  int64_t bytes = 256 + (rows * p4 * 4 + 255) / 256 * 256;  // 256: the buffer is aligned up inside the caller's workspace
-  if (p->lmib_global) bytes += lmib_solve_grid(p, rows) * static_cast<int64_t>(lmib_square_words(p->bdev.r)) * 4;
-  return bytes;
+  return 256 + (rows * p4 * 4 + 255) / 256 * 256;  // 256: the buffer is aligned up inside the caller's workspace
 }
 // The two kernels of lmi_big.cuh over the batch, chunk by chunk.  F: [nv][p4] packed matrices (LMIB with V = v, or
-// LMINEGB with V = (y, 1)); buf: the contraction buffer (+ the GLOBAL_A scratch behind it).
+// LMINEGB with V = y and its constant row as C0); buf: the contraction buffer.
 static cudaError_t lmib_run(const rayen_plan* p, const float* F, int nv, const float* V, int64_t ldv, float* y, float* kappa,
                             int32_t* active, float* dkappa, void* buf, int64_t B, int mode, int flags, cudaStream_t stream,
                             const float* C0 = nullptr) {
@@ -340,8 +336,7 @@ static cudaError_t lmib_run(const rayen_plan* p, const float* F, int nv, const f
   const int64_t rows = lmib_chunk_rows(p, B, b.p4);
   buf = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(buf) + 255) / 256 * 256);  // 16-byte stores of the GEMM
   float* S = static_cast<float*>(buf);
-  float* scratch = reinterpret_cast<float*>(static_cast<char*>(buf) + (rows * b.p4 * 4 + 255) / 256 * 256);
-  LmibSolveFn sf = lmib_solve_fn(p->lmib_threads, p->lmib_global);
+  LmibSolveFn sf = lmib_solve_fn(p->lmib_threads);
   const int tiles_n = (b.p4 + kLbTileN - 1) / kLbTileN;
   for (int64_t c0 = 0; c0 < B; c0 += rows) {
     const int64_t bc = (B - c0 < rows) ? B - c0 : rows;
@@ -351,7 +346,7 @@ static cudaError_t lmib_run(const rayen_plan* p, const float* F, int nv, const f
     g_launches.fetch_add(1);
     sf<<<static_cast<unsigned>(lmib_solve_grid(p, bc)), p->lmib_threads, p->lmib_smem_bytes, stream>>>(
         b, S, V + c0 * ldv, ldv, y ? y + c0 * b.k : nullptr, kappa + c0, active ? active + c0 : nullptr,
-        dkappa ? dkappa + c0 * nv : nullptr, scratch, bc, mode, flags);
+        dkappa ? dkappa + c0 * nv : nullptr, bc, mode, flags);
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -577,8 +572,8 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
 
 // Wide plan (32 < n <= 4096; linear + quadratic + SOC): only the WIDE, Y0 and VIOL sections are used on the device.
 static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** out) {
-  if (d->n <= 32 || d->n > 4096 || d->np < d->n || d->np % 4)
-    return fail(RAYEN_ERR_UNSUPPORTED, "wide plan: n=%d (np=%d) outside 33..4096", d->n, d->np);
+  if (d->n <= 32 || d->n > kWideMaxN || d->np < d->n || d->np % 4)
+    return fail(RAYEN_ERR_UNSUPPORTED, "wide plan: n=%d (np=%d) outside 33..%d", d->n, d->np, kWideMaxN);
   if (d->lmi_r > 0 && !d->lmi_big)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "an LMI together with n=%d > 32 needs lmi_big = 1 (section LMIB)", d->n);
   if (d->k_pad % 4 || d->k_pad < d->k) return fail(RAYEN_ERR_BAD_ARGUMENT, "bad padding k=%d k_pad=%d", d->k, d->k_pad);
@@ -657,14 +652,18 @@ static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** o
   p->host_graph_on = !(getenv("RAYEN_HOST_GRAPH") && atoi(getenv("RAYEN_HOST_GRAPH")) == 0);
   p->wide_fwd_smem_bytes[0] = wide_fwd_smem_bytes(w.n, 8);
   p->wide_fwd_smem_bytes[1] = wide_fwd_smem_bytes(w.n, 16);
+  p->wide_fwd_smem_bytes[2] = wide_fwd_smem_bytes(w.n, 4);
   p->wide_bwd_smem_bytes = wide_bwd_smem_bytes(w.n);
   cudaError_t e = cudaMalloc(&p->d_blob, d->blob_words * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(p->d_blob, d->blob, d->blob_words * sizeof(float), cudaMemcpyHostToDevice);
   int rc = 0;
   if (e != cudaSuccess) rc = cuda_fail(e, "uploading the constant block");
   // the attribute is per function, not per plan: always the device maximum, so that plans of different n coexist
-  if (rc == 0 && p->wide_fwd_smem_bytes[0] > static_cast<size_t>(p->max_smem_optin))
-    rc = fail(RAYEN_ERR_UNSUPPORTED, "wide plan: n=%d needs %zu bytes of shared memory", w.n, p->wide_fwd_smem_bytes[0]);
+  if (rc == 0 && (p->wide_fwd_smem_bytes[2] > static_cast<size_t>(p->max_smem_optin) ||
+                  p->wide_bwd_smem_bytes > static_cast<size_t>(p->max_smem_optin)))
+    rc = fail(RAYEN_ERR_UNSUPPORTED, "wide plan: n=%d needs %zu bytes of shared memory", w.n, p->wide_fwd_smem_bytes[2]);
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<4, true>), p->max_smem_optin);
+  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<8, true, true>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<8, false>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<16, false>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<8, true>), p->max_smem_optin);
@@ -1008,14 +1007,24 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
       bool ts16 = (B + 15) / 16 >= p->sm_count && p->wide_fwd_smem_bytes[1] <= static_cast<size_t>(p->max_smem_optin) / 2;
       if (force_ts == 8) ts16 = false;
       if (force_ts == 16 && p->wide_fwd_smem_bytes[1] <= static_cast<size_t>(p->max_smem_optin)) ts16 = true;
-      const int ts = ts16 ? 16 : 8;
+      // sets too wide for a tile of 8 directions in shared memory (n > ~6900) take tiles of 4
+      const bool ts4 = p->wide_fwd_smem_bytes[0] > static_cast<size_t>(p->max_smem_optin) || force_ts == 4;
+      const bool cmp = p->wdev.n >= kWideCompensatedN;  // Kahan-compensated block sums (wide.cuh, wide_dot2): 8-sample tiles
+      if (ts4 || cmp) ts16 = false;
+      const int ts = ts4 ? 4 : (ts16 ? 16 : 8);
       long long grid = (B + ts - 1) / ts;
       const long long cap = static_cast<long long>(p->sm_count) * 32;
       if (grid > cap) grid = cap;
       const bool blk = p->wdev.n >= kWideBlockedN;  // blocked accumulation of the long dot products (wide.cuh)
-      const size_t wsm = p->wide_fwd_smem_bytes[ts16 ? 1 : 0];
-      auto wf = ts16 ? (blk ? wide_forward_kernel<16, true> : wide_forward_kernel<16, false>)
-                     : (blk ? wide_forward_kernel<8, true> : wide_forward_kernel<8, false>);
+      const size_t wsm = p->wide_fwd_smem_bytes[ts4 ? 2 : (ts16 ? 1 : 0)];
+      auto wf = ts4 ? wide_forward_kernel<4, true>
+                    : (ts16 ? (blk ? wide_forward_kernel<16, true> : wide_forward_kernel<16, false>)
+                            : (cmp ? wide_forward_kernel<8, true, true>
+                                   : (blk ? wide_forward_kernel<8, true> : wide_forward_kernel<8, false>)));
+      if (ts4 && !blk) {  // (only reachable through RAYEN_WIDE_TS=4 on a narrow set: there is no unblocked 4-tile build)
+        if (prev != p->device) cudaSetDevice(prev);
+        return fail(RAYEN_ERR_UNSUPPORTED, "RAYEN_WIDE_TS=4 needs n >= %d", kWideBlockedN);
+      }
       wf<<<static_cast<int>(grid), kWideThreads, wsm, stream>>>(p->wdev, v, ldv, y, kappa, active, B, mode);
       g_launches.fetch_add(1);
       we = cudaGetLastError();
@@ -1244,15 +1253,18 @@ extern "C" int rayen_violation_f32(const rayen_plan_t* p, const float* y, int64_
   int prev = 0;
   RAYEN_CUDA(cudaGetDevice(&prev));
   if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
-  const int warps = kViolThreads / 32;
+  // one y row per warp in shared memory: as many warps per block (<= 8) as fit
+  const size_t row_bytes = static_cast<size_t>((d.k + 3) / 4 * 4) * sizeof(float);
+  int warps = kViolThreads / 32;
+  while (warps > 1 && warps * row_bytes > static_cast<size_t>(p->max_smem_optin)) --warps;
   long long grid = (B + warps - 1) / warps;
   if (grid > static_cast<long long>(p->sm_count) * 8) grid = static_cast<long long>(p->sm_count) * 8;
-  const size_t smem = static_cast<size_t>(warps) * ((d.k + 3) / 4 * 4) * sizeof(float);
+  const size_t smem = warps * row_bytes;
   if (smem > static_cast<size_t>(p->max_smem_optin)) {
     if (prev != p->device) cudaSetDevice(prev);
     return fail(RAYEN_ERR_UNSUPPORTED, "violation metric: k=%d needs %zu bytes of shared memory", d.k, smem);
   }
-  viol_lqs_kernel<<<static_cast<int>(grid), kViolThreads, smem, stream>>>(d, y, ldy, viol, B);
+  viol_lqs_kernel<<<static_cast<int>(grid), warps * 32, smem, stream>>>(d, y, ldy, viol, B);
   g_launches.fetch_add(1);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && d.lmi_r > 0) {

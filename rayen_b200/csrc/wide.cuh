@@ -16,6 +16,7 @@ constexpr int kWideWarps = kWideThreads / 32;
 // backward: one CTA per sample, 128 threads (n < 512: the per-sample chain is latency-bound, small CTAs keep more samples
 // in flight per SM) or 256 threads (wider sets: more rows of the binding item in flight)
 constexpr int kWideBwdSwitchN = 512;
+constexpr int kWideMaxN = 12288;      // widest subspace: 4-sample tiles of the forward and the backward vectors still fit shared memory
 constexpr int kWideMagic = 0x57494445;
 constexpr int kWideVersion = 3;
 constexpr int kWideGroupRows = 64;   // rows per task: a lane owns two consecutive rows (one 8-byte load per column)
@@ -65,6 +66,7 @@ __device__ __forceinline__ void wide_fma_col(float w, const float4* __restrict__
 // whose rounding is below 1e-6 there anyway.
 constexpr int kWideAccBlock = 128;
 constexpr int kWideBlockedN = 512;
+constexpr int kWideCompensatedN = 2048;  // from here on the block sums are added with a Kahan term (wide_dot2, CMP)
 
 // acc[s] = sum_{j >= j0} Wt[j][row] * us[j][s]: the column walk of one row against the tile's directions; eight
 // column loads in flight per lane
@@ -127,7 +129,7 @@ __device__ __forceinline__ void wide_fma_col2(float2 w, const float4* __restrict
     acc1[4 * q + 3] = fmaf(w.y, a.w, acc1[4 * q + 3]);
   }
 }
-template <int TS, bool BLK>
+template <int TS, bool BLK, bool CMP>
 __device__ __forceinline__ void wide_dot2(const float* __restrict__ wcol2, int r_pad, int j0, int n,
                                           const float4* __restrict__ us4, float (&tot0)[TS], float (&tot1)[TS]) {
   // eight columns in flight per lane (sixteen in the 8-sample kernel measured 2x SLOWER on B200: 26.6 -> 54.7 us at n = 64,
@@ -147,6 +149,42 @@ __device__ __forceinline__ void wide_dot2(const float* __restrict__ wcol2, int r
     for (; j < n; ++j)
       wide_fma_col2<TS>(__ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j) * r_pad)),
                         us4 + static_cast<size_t>(j) * (TS / 4), tot0, tot1);
+  } else if constexpr (CMP) {
+    // CMP (sets with n >= kWideCompensatedN = 2048; always in the 4-sample build): dot products of 10^3..10^4 terms that cancel to
+    // 1 / |v| ~ 1e-2 of their terms' scale.  Plain blocks of 128 leave ~2.5e-5 relative error in kappa for the worst of
+    // 2000 samples (measured: the 1 x 10000 point of the reference's sweep ended 1.09e-5 outside its row); blocks of 16
+    // added to the running total with a Kahan compensation term bring that to the rounding of the inputs (~3e-6).
+    float acc0[TS], acc1[TS], c0[TS], c1[TS];
+#pragma unroll
+    for (int s = 0; s < TS; ++s) tot0[s] = tot1[s] = acc0[s] = acc1[s] = c0[s] = c1[s] = 0.f;
+    auto fold = [&]() {
+#pragma unroll
+      for (int s = 0; s < TS; ++s) {
+        const float y0 = acc0[s] - c0[s], t0 = tot0[s] + y0;
+        c0[s] = (t0 - tot0[s]) - y0;
+        tot0[s] = t0;
+        const float y1 = acc1[s] - c1[s], t1 = tot1[s] + y1;
+        c1[s] = (t1 - tot1[s]) - y1;
+        tot1[s] = t1;
+        acc0[s] = acc1[s] = 0.f;
+      }
+    };
+    int j = j0;
+    while (j + U <= n) {
+      const int stop = (j + 16 < n) ? j + 16 : n;
+      for (; j + U <= stop; j += U) {
+        float2 w[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) w[q] = __ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j + q) * r_pad));
+#pragma unroll
+        for (int q = 0; q < U; ++q) wide_fma_col2<TS>(w[q], us4 + static_cast<size_t>(j + q) * (TS / 4), acc0, acc1);
+      }
+      fold();
+    }
+    for (; j < n; ++j)
+      wide_fma_col2<TS>(__ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j) * r_pad)),
+                        us4 + static_cast<size_t>(j) * (TS / 4), acc0, acc1);
+    fold();
   } else {
     float acc0[TS], acc1[TS];
 #pragma unroll
@@ -199,7 +237,7 @@ __device__ __forceinline__ void wide_take(float c, int ct, float& best, int& tag
 
 // ----------------------------------------------------------------------------- forward
 // grid: one CTA per tile of TS samples (grid-stride); dynamic smem = wide_fwd_smem_bytes(n, TS).
-template <int TS, bool BLK>
+template <int TS, bool BLK, bool CMP = (TS == 4)>
 __global__ void __launch_bounds__(kWideThreads)
     wide_forward_kernel(const WideDev P, const float* __restrict__ v, long long ldv, float* __restrict__ y,
                         float* __restrict__ kappa_out, int* __restrict__ active_out, long long B, int mode) {
@@ -268,7 +306,7 @@ __global__ void __launch_bounds__(kWideThreads)
         const int* tk = tasks + t * 8;
         const int kind = __ldg(tk), row = __ldg(tk + 1), j0 = __ldg(tk + 2), idx = __ldg(tk + 3), slot = __ldg(tk + 5);
         float acc0[TS], acc1[TS];
-        wide_dot2<TS, BLK>(wt + row + 2 * lane, P.r_pad, j0, n, us4, acc0, acc1);
+        wide_dot2<TS, BLK, CMP>(wt + row + 2 * lane, P.r_pad, j0, n, us4, acc0, acc1);
         if (kind == 1) {
           // a lane's rows arrive in ascending order: strict > keeps the lowest
 #pragma unroll

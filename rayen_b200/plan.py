@@ -21,7 +21,7 @@ import numpy as np
 
 ABI_VERSION = 14
 MAX_NP = 32      # widest subspace of the register-resident kernels; beyond it the WIDE section / wide.cuh take over
-MAX_WIDE_N = 4096
+MAX_WIDE_N = 12288   # wide.cuh kWideMaxN
 MAX_LMI = 32          # largest LMI of the register-resident kernels (lmi.cuh / lmi_warp.cuh)
 MAX_LMI_BIG = 320     # largest LMI of the one-CTA-per-matrix path (lmi_big.cuh kLbMaxR)
 

@@ -191,6 +191,22 @@ def wide_spec(k, m=0, eta=0, mu=0, r_M=0, eq=0, seed=0, loosen=3.0, r=0):
     return spec
 
 
+BIG_LMI_GOLDEN = ("big_r40", "big_wide_r12", "big_r96_lmi_only")
+
+
+def big_lmi_spec(name):
+    """The sets behind the golden files tests/golden/big_*.npz (LMIs beyond the register-resident kernels)."""
+    if name == "big_r40":
+        spec = random_spec(k=6, m=20, eta=1, mu=1, r_M=5, r=40, seed=41)
+        spec["b1"] = spec["b1"] * 3.0
+        return spec
+    if name == "big_wide_r12":
+        return wide_spec(40, 60, 1, 1, 10, 0, seed=42, r=12)
+    if name == "big_r96_lmi_only":
+        return random_spec(k=4, r=96, seed=43)
+    raise KeyError(name)
+
+
 def epigraph_lmi_spec(k, r, perturbation, delta=None, seed=0, sign=1.0):
     """The epigraph form ``t I - A(y) >= 0`` (t = y_0), the commonest LMI there is: F_0 = sign * I, F_a = perturbation *
     (a random symmetric matrix) for a >= 1, constant term I, y0 = 0.  S~(u) is then a multiple of the identity plus a

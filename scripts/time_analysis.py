@@ -1,6 +1,7 @@
 """The reference's own timing sweep (examples/scripts/time_analysis.py:57-190: seconds per sample of one forward call on
-2000 samples, per family, over dimension and constraint count) on this library, for the sizes it covers (n <= 4096;
-LMI needs n <= 32 and is not part of this sweep).  Same random generators as the reference script.  Next to each point:
+2000 samples, per family, over dimension and constraint count) on this library, for the sizes it covers (n <= 12288,
+LMI size <= 320: every linear / quadratic / SOC point, and the LMI grid r_F in {10, 100, 200, 300} x k up to 2000).
+Same random generators as the reference script.  Next to each point:
 the oracle port on the host cores (float64 like the reference script) when its cost is small enough, the maximum
 violation of the outputs (GPU metric) and the agreement with the float64 oracle on 16 samples.
 
@@ -49,9 +50,24 @@ def soc_set(r_M, mu, k):
     return constraints.ConvexConstraints(lc=None, qcs=[], socs=socs, lmic=None, y0=np.zeros((k, 1)))
 
 
+def lmi_set(r_F, k):
+    all_F = []
+    for _ in range(k):
+        tmp = rng.uniform(-1.0, 1.0, size=(r_F, r_F))
+        all_F.append((tmp + tmp.T) / 2)
+    tmp = rng.uniform(-1.0, 1.0, size=(r_F, r_F))
+    all_F.append(tmp @ tmp.T + 0.5 * np.eye(r_F))
+    return constraints.ConvexConstraints(lc=None, qcs=[], socs=[], lmic=constraints.LMIConstraint(all_F), y0=np.zeros((k, 1)))
+
+
 points = []
+for r_F in (10, 100, 200, 300):
+    for k in (100, 500, 1000, 2000):
+        if r_F * r_F * k <= 300 * 300 * 1000:       # (host memory of the float64 packing: 300 x 300 x 2000 is left out)
+            points.append(("lmi", dict(r_F=r_F, k=k), lambda r_F=r_F, k=k: lmi_set(r_F, k),
+                           2.0 * k * r_F * r_F + 10.0 * r_F ** 3, 3 * r_F * r_F * k))
 for r in (1, 10, 100, 500, 1000, 2000, 3000):
-    for k in (1, 10, 100, 1000, 2000, 3000, 4000):
+    for k in (1, 10, 100, 1000, 2000, 3000, 4000, 5000, 10000):
         points.append(("linear", dict(r_A1=r, k=k), lambda r=r, k=k: linear_set(r, k), 2.0 * r * k, r * k))
 for eta in (1, 10, 50):
     for k in (1, 10, 100, 300, 500, 1000):
@@ -102,5 +118,6 @@ for fam, params, make, flop_per_sample, _ in points:
     torch.cuda.empty_cache()
 os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
 json.dump(dict(num_samples=NUM, points=out, skipped_for_time=skipped,
-               not_covered="linear k in {5000, 10000} (n > 4096); the LMI sweep (r_F >= 10 with k >= 100: an LMI needs n <= 32 here)"),
+               not_covered="LMI points with k in {5000, 7000, 10000} and (r_F, k) = (300, 2000): the float64 packing of k r_F^2 "
+                           "words on the host; everything else of the reference's grid is covered"),
           open(args.out, "w"), indent=1)

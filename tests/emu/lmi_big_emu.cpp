@@ -30,16 +30,12 @@ extern "C" int emu_lmib_contract(const float* V, long long ldv, const float* F, 
 
 extern "C" int emu_lmib_solve(const float* blob, int n, int k, int r, int p4, int off_lmib, int off_y0, const float* S,
                               const float* v, long long ldv, float* y, float* kappa_io, int* active_io, float* dkappa,
-                              float* scratch, long long Bc, int mode, int flags, int threads, int global_a, int grid) {
+                              long long Bc, int mode, int flags, int threads, int grid) {
   LmiBigDev P{};
   P.blob = blob; P.n = n; P.k = k; P.r = r; P.p4 = p4; P.off_lmib = off_lmib; P.off_y0 = off_y0;
-  if (lmib_smem_bytes(r, global_a != 0) > sizeof(lmib_smem)) return -2;
+  if (lmib_smem_bytes(r) > sizeof(lmib_smem)) return -2;
   if (threads < r) return -4;
-#define LB_RUN(T)                                                                                                          \
-  emu_launch(grid, T, [&] {                                                                                                \
-    if (global_a) lmib_solve_kernel<T, true>(P, S, v, ldv, y, kappa_io, active_io, dkappa, scratch, Bc, mode, flags);       \
-    else lmib_solve_kernel<T, false>(P, S, v, ldv, y, kappa_io, active_io, dkappa, scratch, Bc, mode, flags);               \
-  })
+#define LB_RUN(T) emu_launch(grid, T, [&] { lmib_solve_kernel<T>(P, S, v, ldv, y, kappa_io, active_io, dkappa, Bc, mode, flags); })
   if (threads == 64) LB_RUN(64);
   else if (threads == 128) LB_RUN(128);
   else if (threads == 256) LB_RUN(256);

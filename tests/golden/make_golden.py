@@ -161,5 +161,16 @@ def main():
         make_one(ref, cfg + "_loose", spec, GOLDEN_BATCH[cfg], scale=2.0, store_spec=False)
 
 
+def main_big():
+    """LMIs beyond 32 x 32 and LMIs together with n > 32 (round 2): python tests/golden/make_golden.py big"""
+    warnings.filterwarnings("ignore")
+    ref = load_reference()
+    for name in synthetic.BIG_LMI_GOLDEN:
+        make_one(ref, name, synthetic.big_lmi_spec(name), 64, scale=2.0, store_spec=False)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        main_big()
+    else:
+        main()

@@ -62,6 +62,8 @@ def load_golden(name):
     out["zero_row_ok"] = bool(z["zero_row_ok"])
     if "spec_y0" in z:
         spec = _spec_from_arrays(z)
+    elif name.startswith("big_"):
+        spec = synthetic.big_lmi_spec(name)
     else:  # large specs are regenerated from the seeded generator and checked by digest
         base = name.replace("_loose", "")
         spec = synthetic.config_spec(base)

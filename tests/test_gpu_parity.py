@@ -738,7 +738,8 @@ def test_wide_set_properties_and_violation_metric():
     assert rel(gv[sub], g_ref.numpy(), ok) <= TOL_GRAD
 
 
-@pytest.mark.parametrize("rows,k", [(1, 1000), (1, 2000), (10, 4000), (1, 4000), (100, 2000), (1000, 1000)])
+@pytest.mark.parametrize("rows,k", [(1, 1000), (1, 2000), (10, 4000), (1, 4000), (100, 2000), (1000, 1000),
+                                    (1, 5000), (10, 5000), (1, 10000), (100, 10000)])   # k >= 2048: Kahan block sums; k > ~6900: tiles of 4
 def test_wide_linear_sets_are_feasible_to_1e_5(rows, k):
     """the linear points of the reference's sweep (examples/scripts/time_analysis.py:62-69, 2000
     samples, v ~ U(-1, 1)) at k = 1000 ... 4000.  Every output must satisfy A1 y <= b1 to 1e-5 in float64, and the GPU
@@ -789,7 +790,7 @@ BIG_LMI_CASES = [
     ("r64_mixed", lambda: synthetic.random_spec(k=8, m=30, eta=1, mu=1, r_M=6, r=64, seed=22), 500, "RAYEN"),
     ("r100_lmi_only", lambda: synthetic.random_spec(k=5, r=100, seed=23), 300, "RAYEN"),
     ("r150_rows", lambda: synthetic.random_spec(k=10, m=12, r=150, seed=24), 200, "RAYEN"),
-    ("r240_global", lambda: synthetic.random_spec(k=4, m=6, r=240, seed=25), 160, "RAYEN"),   # matrix in the L2 scratch
+    ("r240", lambda: synthetic.random_spec(k=4, m=6, r=240, seed=25), 160, "RAYEN"),
     ("r300", lambda: synthetic.random_spec(k=3, r=300, seed=26), 150, "RAYEN"),
     ("wide_n40_r10", lambda: synthetic.wide_spec(40, 60, 2, 2, 10, 0, seed=27, r=10), 600, "RAYEN"),
     ("wide_n98_r50", lambda: synthetic.wide_spec(100, 50, 1, 1, 20, 2, seed=28, r=50), 400, "RAYEN"),
@@ -905,3 +906,72 @@ def test_big_lmi_epigraph_form_and_grid_stride():
     ok = (cf["margin"] > 1e-4) & (cf["lmi_gap"] > 1e-3)
     assert ok.sum() > 0.5 * len(sub)
     assert rel(gv[sub], g_ref.numpy(), ok) <= 4 * TOL_GRAD
+
+
+# ----------------------------------------------------------------------------- solver-free preprocessing -> CUDA path
+@pytest.mark.parametrize("which", ["example_2", "example_8", "example_11", "example_13", "cfg3", "cfg5"])
+def test_sets_without_a_given_interior_point_run_through_the_cuda_path(which):
+    """``y0=None, do_preprocessing_linear=True`` (the reference's README default; constraints.py:366-436 there uses cvxpy,
+    here HiGHS + SLSQP): the interior point, the subspace and the reduced polyhedron found on the host feed the packed plan
+    and the sm_100a kernels.  The map differs from the one built around the spec's own y0 (another interior point), so the
+    checks are geometric: every output feasible for the ORIGINAL constraints (float64 residuals and the GPU metric),
+    interior samples map to y0 + N v, boundary samples land on the boundary, and the result matches the float64 oracle
+    evaluated on the SAME preprocessed set."""
+    spec = synthetic.example_spec(int(which.split("_")[1])) if which.startswith("example") else synthetic.config_spec(which)
+    cs = synthetic.build_constraints(spec, y0=None, do_preprocessing_linear=True)
+    B = 3000
+    v, gy = synthetic.sample_inputs(B, cs.n, cs.k, seed_v=11, scale=3.0)
+    v[::5] *= 1e-3
+    layer, y, gv = run_layer(cs, v, gy)
+    oset = OracleSet.from_constraints(cs)
+    scale = max(1.0, np.abs(y).max())
+    assert max_violation(oset, y, spec["A1"], spec["b1"], spec["A2"], spec["b2"]) <= 1e-5 * scale
+    assert float(layer.violation(torch.as_tensor(y, dtype=torch.float32, device=DEV)).max()) <= 1e-4 * scale
+    y_ref, g_ref = TorchOracle(oset, torch.float64).forward_backward(v.double(), gy.double())
+    assert rel(y, y_ref.numpy()) <= TOL
+    cf = closed_form_numpy(oset, v.numpy(), gy.numpy())
+    ok = (cf["margin"] > 1e-4) & (cf["cone_cond"] > 0.05) & (cf["lmi_gap"] > 1e-3) & np.isfinite(g_ref.numpy()).all(axis=1)
+    assert ok.sum() >= 0.6 * B
+    assert rel(gv, g_ref.numpy(), ok) <= 2 * TOL_GRAD
+    inner = np.arange(0, B, 5)
+    inner = inner[cf["kappa"][inner] * np.linalg.norm(v.numpy()[inner], axis=1) < 0.5]
+    assert len(inner) > 0
+    np.testing.assert_allclose(y[inner], cs.y0[:, 0] + v.numpy()[inner].astype(np.float64) @ cs.NA_E.T, atol=1e-5 * scale)
+
+
+def test_whole_training_step_replayed_from_a_cuda_graph():
+    """the layer is capture-safe (launch-only C calls on the current stream), so the reference's training
+    step (examples/main.py:135-171) runs as ONE CUDA graph: same parameters after 5 steps as the eager loop, for a set
+    with every family (cfg5-shaped, dim 32: tcgen05 kernel + filter kernel + backward) behind a trainable mapper."""
+    from rayen_b200.graphed import GraphedStep
+    spec = synthetic.config_spec("cfg5")
+    spec["b1"] = spec["b1"] * 4.0
+    cs = synthetic.build_constraints(spec)
+
+    def make():
+        torch.manual_seed(0)
+        layer = ConstraintModule(cs, input_dim=24, create_map=True).to(DEV)
+        layer.fuse_mapper = False           # same kernels in both runs whatever the batch
+        net = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(24, 24), torch.nn.ReLU(), layer).to(DEV)
+        return net, torch.optim.SGD(net.parameters(), lr=1e-2)
+
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randn(2048, 24, 1, generator=g).to(DEV) for _ in range(5)]
+    ts = [torch.randn(2048, cs.k, 1, generator=g).to(DEV) for _ in range(5)]
+    loss_fn = lambda y, t: torch.nn.functional.mse_loss(y, t)
+    net_e, opt_e = make()
+    eager_losses = []
+    for x, t in zip(xs, ts):
+        opt_e.zero_grad()
+        loss = loss_fn(net_e(x), t)
+        loss.backward()
+        opt_e.step()
+        eager_losses.append(float(loss.detach()))
+    net_g, opt_g = make()
+    state0 = {k_: v_.clone() for k_, v_ in net_g.state_dict().items()}
+    step = GraphedStep(net_g, loss_fn, opt_g, xs[0], ts[0], warmup=2)
+    net_g.load_state_dict(state0)          # the warm-up and the capture took optimizer steps: start over
+    graph_losses = [float(step(x, t)) for x, t in zip(xs, ts)]
+    np.testing.assert_allclose(graph_losses, eager_losses, rtol=1e-5)
+    for (n1, p1), (n2, p2) in zip(net_e.named_parameters(), net_g.named_parameters()):
+        np.testing.assert_allclose(p2.detach().cpu().numpy(), p1.detach().cpu().numpy(), rtol=1e-4, atol=1e-6, err_msg=n1)

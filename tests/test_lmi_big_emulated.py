@@ -31,8 +31,7 @@ def emu(tmp_path_factory):
     lib.emu_lmib_contract.argtypes = [_F, _LL, _F, ctypes.c_int, ctypes.c_int, _F, _LL, _F]
     lib.emu_lmib_solve.restype = ctypes.c_int
     lib.emu_lmib_solve.argtypes = [_F, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F,
-                                   _F, _LL, _F, _F, _I, _F, _F, _LL, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                   ctypes.c_int]
+                                   _F, _LL, _F, _F, _I, _F, _LL, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return lib
 
 
@@ -55,7 +54,7 @@ def _prior(cs, p, v, mode):
     return y.astype(np.float32), kap.astype(np.float32), act.astype(np.int32)
 
 
-def run_emulated(lib, cs, p, v, mode=0, threads=64, global_a=0, grid=3, flags=1):
+def run_emulated(lib, cs, p, v, mode=0, threads=64, grid=3, flags=1):
     f = p.fields
     n, k, r, p4 = f["n"], f["k"], f["lmi_r"], f["lmib_p4"]
     v = np.ascontiguousarray(v, dtype=np.float32)
@@ -66,26 +65,24 @@ def run_emulated(lib, cs, p, v, mode=0, threads=64, global_a=0, grid=3, flags=1)
     Fp = np.ascontiguousarray(blob[f["off_lmib"]:f["off_lmib"] + n * p4])
     assert lib.emu_lmib_contract(_ptr(v), cols, _ptr(Fp), n, p4, _ptr(S), B, None) == 0
     dk = np.full((B, n), np.nan, dtype=np.float32)
-    sq = (max(r * (r | 1), r * (r + 1) // 2 + 4) + 3) // 4 * 4
-    scratch = np.zeros(grid * sq, dtype=np.float32)
     rc = lib.emu_lmib_solve(_ptr(blob), n, k, r, p4, f["off_lmib"], f["off_y0"], _ptr(S), _ptr(v), cols, _ptr(y), _ptr(kap),
-                            _ptr(act, _I), _ptr(dk), _ptr(scratch), B, mode, flags, threads, global_a, grid)
+                            _ptr(act, _I), _ptr(dk), B, mode, flags, threads, grid)
     assert rc == 0
     return y.astype(np.float64), kap, act, dk, S
 
 
 CASES = [
-    # spec, batch, threads, global_a
-    (lambda: synthetic.random_spec(k=5, m=8, eta=1, mu=1, r_M=4, r=33, seed=1), 20, 64, 0),
-    (lambda: synthetic.random_spec(k=3, r=40, seed=2), 12, 64, 1),                 # LMI only; matrix in the global scratch
-    (lambda: synthetic.wide_spec(36, 40, 1, 1, 6, 2, seed=3, r=9), 14, 64, 0),      # wide subspace (n = 34), small LMI
-    (lambda: synthetic.random_spec(k=4, m=4, r=70, seed=4), 6, 128, 0),
+    # spec, batch, threads
+    (lambda: synthetic.random_spec(k=5, m=8, eta=1, mu=1, r_M=4, r=33, seed=1), 20, 64),
+    (lambda: synthetic.random_spec(k=3, r=40, seed=2), 12, 64),                 # LMI only
+    (lambda: synthetic.wide_spec(36, 40, 1, 1, 6, 2, seed=3, r=9), 14, 64),      # wide subspace (n = 34), small LMI
+    (lambda: synthetic.random_spec(k=4, m=4, r=70, seed=4), 6, 128),
 ]
 
 
 @pytest.mark.parametrize("case", range(len(CASES)))
 def test_big_lmi_kernels_match_the_oracle(emu, case):
-    make, B, threads, global_a = CASES[case]
+    make, B, threads = CASES[case]
     spec = make()
     if spec["b1"] is not None and case == 0:
         spec["b1"] = spec["b1"] * 3.0
@@ -95,7 +92,7 @@ def test_big_lmi_kernels_match_the_oracle(emu, case):
     v, gy = synthetic.sample_inputs(B, cs.n, cs.k, seed_v=case + 1)
     v = v.numpy()
     v[1] *= 1e-3                                   # an interior sample
-    y, kap, act, dk, S = run_emulated(emu, cs, p, v, threads=threads, global_a=global_a)
+    y, kap, act, dk, S = run_emulated(emu, cs, p, v, threads=threads)
     oset = OracleSet.from_constraints(cs)
     cf = closed_form_numpy(oset, v, gy.numpy())
     assert np.abs(y - cf["y"]).max() <= 1e-5 * max(1.0, np.abs(cf["y"]).max())
@@ -137,9 +134,8 @@ def test_big_lmi_rayen_old_and_gradient_only_mode(emu):
     v32 = np.ascontiguousarray(v, dtype=np.float32)
     y2, kap2, act2 = y.astype(np.float32), kap.copy(), act.copy()
     dk2 = np.full_like(dk, np.nan)
-    scratch = np.zeros(4, dtype=np.float32)
     rc = emu.emu_lmib_solve(_ptr(p.blob), n, k, r, p4, f["off_lmib"], f["off_y0"], _ptr(S), _ptr(v32), v32.shape[1], _ptr(y2),
-                            _ptr(kap2), _ptr(act2, _I), _ptr(dk2), _ptr(scratch), v32.shape[0], 1, 2, 64, 0, 2)
+                            _ptr(kap2), _ptr(act2, _I), _ptr(dk2), v32.shape[0], 1, 2, 64, 2)
     assert rc == 0
     np.testing.assert_array_equal(kap2, kap)
     np.testing.assert_array_equal(act2, act)
@@ -164,9 +160,8 @@ def test_big_lmi_violation_mode(emu):
     c0 = np.ascontiguousarray(Fn[k * p4:])
     assert emu.emu_lmib_contract(_ptr(y), k, _ptr(Fn), k, p4, _ptr(S), 9, _ptr(c0)) == 0
     viol = np.zeros(9, dtype=np.float32)
-    scratch = np.zeros(4, dtype=np.float32)
     rc = emu.emu_lmib_solve(_ptr(p.blob), k, k, r, p4, f["off_lminegb"], f["off_y0"], _ptr(S), _ptr(y), k, None, _ptr(viol), None,
-                            None, _ptr(scratch), 9, 0, 4, 64, 0, 2)
+                            None, 9, 0, 4, 64, 2)
     assert rc == 0
     allF = np.asarray(spec["lmi"])
     Fy = allF[-1][None] + np.einsum("bi,ijk->bjk", y.astype(np.float64), allF[:-1])

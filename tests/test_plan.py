@@ -57,8 +57,8 @@ def test_rejects_boundary_or_exterior_points():
 
 
 def test_unsupported_sizes_fail_loudly():
-    with pytest.raises(plan.PlanError, match="n=4100"):
-        plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=4100, m=2)))
+    with pytest.raises(plan.PlanError, match="n=12300"):
+        plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=12300, m=2)))
     with pytest.raises(plan.PlanError, match="r=321"):
         plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=2, r=321)))
 

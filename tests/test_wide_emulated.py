@@ -88,9 +88,11 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("ts", [8, 16])
+@pytest.mark.parametrize("ts", [4, 8, 16])
 @pytest.mark.parametrize("k,m,eta,mu,r_M,eq,batch,method", CASES)
 def test_wide_kernels_under_the_emulator_match_the_oracle(emu, k, m, eta, mu, r_M, eq, batch, method, ts):
+    if ts == 4 and k not in (36, 45, 70):
+        pytest.skip("tiles of 4 samples (the build for n > ~6900) are exercised on three of the sets")
     if k == 4096 and ts == 16:
         pytest.skip("tiles of 16 samples of a 4096-dimensional set exceed the shared memory of an SM (the launcher uses 8)")
     spec = synthetic.wide_spec(k, m, eta, mu, r_M, eq, seed=k + batch)
