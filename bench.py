@@ -480,6 +480,35 @@ def run_b200(args, rank, local_rank, world):
                   "step_with_gather_ms": direct_ms + both_ms,
                   "path": "rayen_b200.sharding.all_gather_outputs: dist.all_gather_into_tensor forward, "
                           "dist.reduce_scatter_tensor backward (NCCL)"}
+        # the same exchange through this library's own kernel over peer memory (rayen_gather_push_f32: P2P stores, or one
+        # multimem.st per 16 bytes through the NVSwitch multicast mapping), and fused into the forward kernels' epilogue
+        try:
+            pg = sharding.PeerGather(batch, k, device=device)
+            yl = bench.sets[0]["y"].contiguous()
+            vq = bench.sets[0]["v"]
+            barrier()
+            gather["push_p2p_ms"] = max_over_ranks(bench.time_loop_median(lambda i: pg.all_gather(yl, use_multicast=False), 30, 5))
+            gather["has_multicast"] = bool(pg.has_multicast)
+            if pg.has_multicast:
+                barrier()
+                gather["push_multicast_ms"] = max_over_ranks(bench.time_loop_median(lambda i: pg.all_gather(yl), 30, 5))
+                with torch.no_grad():
+                    barrier()
+                    gather["forward_fused_epilogue_ms"] = max_over_ranks(
+                        bench.time_loop_median(lambda i: sharding.forward_gathered(layer, vq, pg), 30, 5))
+                    barrier()
+                    gather["forward_then_push_multicast_ms"] = max_over_ranks(
+                        bench.time_loop_median(lambda i: pg.all_gather(layer(vq.unsqueeze(2))[:, :, 0]), 30, 5))
+                    barrier()
+                    gather["forward_then_nccl_all_gather_ms"] = max_over_ranks(
+                        bench.time_loop_median(lambda i: sharding.all_gather_outputs(layer(vq.unsqueeze(2))[:, :, 0]), 30, 5))
+            best = min(v_ for k_, v_ in gather.items() if k_.startswith("push_") and k_.endswith("_ms"))
+            gather["push_bus_gbs"] = out_bytes * (world - 1) / world / (best * 1e-3) / 1e9
+            gather["peer_path"] = ("rayen_b200.sharding.PeerGather (torch symmetric memory for the handle exchange and the barrier; "
+                                   "rayen_gather_push_f32 moves the bytes) / sharding.forward_gathered (y stored through the multicast "
+                                   "mapping by the forward kernels themselves)")
+        except Exception as exc:  # noqa: BLE001 - symmetric memory may be unavailable on a box; NCCL numbers stand
+            gather["peer_path_error"] = repr(exc)[:300]
     barrier()
 
     # the link this box gives the step: one 64 MB pinned copy each way, alone (explains e2e, which moves

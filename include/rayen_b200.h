@@ -263,6 +263,20 @@ int rayen_forward_backward_host_wait(const rayen_plan_t* plan, int slot);
 int rayen_violation_f32(const rayen_plan_t* plan, const float* y, int64_t ldy, float* viol, int64_t B,
                         void* cuda_stream);
 
+/*
+ * The optional exchange step of the multi-GPU path (all-gather of y when the downstream loss couples the
+ * batch) as ONE kernel over peer memory instead of a library collective: the `rows` x `k` block `src` of this rank is
+ * stored at row `row_offset` of the gathered [world * rows, k] buffer of every rank.
+ *   multicast_base != NULL: the NVSwitch multicast mapping of that buffer (torch symmetric memory: multicast_ptr) -- one
+ *                           `multimem.st` per 16 bytes, replicated to all ranks by the switch;
+ *   otherwise:              `n_dst` peer-mapped base pointers (host array, the own buffer included), plain stores
+ *                           over NVLink (P2P).
+ * Launch-and-return on `cuda_stream`; the caller orders the consumers behind it with a cross-rank barrier (the symmetric
+ * memory handle's).  Replaces dist.all_gather_into_tensor in rayen_b200/sharding.py::all_gather_outputs.
+ */
+int rayen_gather_push_f32(const float* src, int64_t rows, int32_t k, float* const* dst_bases, int32_t n_dst,
+                          float* multicast_base, int64_t row_offset, void* cuda_stream);
+
 /* Number of kernels this library has launched in the calling process (all plans, all threads). */
 int64_t rayen_launch_count(void);
 /* Launches `count` empty kernels (148 x 128 threads) on the stream: the launch floor a chain of kernels pays on this

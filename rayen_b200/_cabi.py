@@ -68,6 +68,8 @@ SYMBOLS = {
     "rayen_forward_backward_host_submit_f32": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int64, _P, _P, ctypes.c_int]),
     "rayen_forward_backward_host_wait": (ctypes.c_int, [_P, ctypes.c_int]),
     "rayen_violation_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, ctypes.c_int64, _P]),
+    "rayen_gather_push_f32": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(_P), ctypes.c_int32, _P,
+                                             ctypes.c_int64, _P]),
     "rayen_launch_count": (ctypes.c_int64, []),
     "rayen_launch_empty": (ctypes.c_int, [ctypes.c_int, _P]),
     "rayen_plan_kernel_info": (ctypes.c_int, [_P, ctypes.POINTER(RayenKernelInfo)]),

@@ -663,7 +663,6 @@ static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** o
                   p->wide_bwd_smem_bytes > static_cast<size_t>(p->max_smem_optin)))
     rc = fail(RAYEN_ERR_UNSUPPORTED, "wide plan: n=%d needs %zu bytes of shared memory", w.n, p->wide_fwd_smem_bytes[2]);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<4, true>), p->max_smem_optin);
-  if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<8, true, true>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<8, false>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<16, false>), p->max_smem_optin);
   if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(wide_forward_kernel<8, true>), p->max_smem_optin);
@@ -1009,8 +1008,7 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
       if (force_ts == 16 && p->wide_fwd_smem_bytes[1] <= static_cast<size_t>(p->max_smem_optin)) ts16 = true;
       // sets too wide for a tile of 8 directions in shared memory (n > ~6900) take tiles of 4
       const bool ts4 = p->wide_fwd_smem_bytes[0] > static_cast<size_t>(p->max_smem_optin) || force_ts == 4;
-      const bool cmp = p->wdev.n >= kWideCompensatedN;  // Kahan-compensated block sums (wide.cuh, wide_dot2): 8-sample tiles
-      if (ts4 || cmp) ts16 = false;
+      if (ts4) ts16 = false;
       const int ts = ts4 ? 4 : (ts16 ? 16 : 8);
       long long grid = (B + ts - 1) / ts;
       const long long cap = static_cast<long long>(p->sm_count) * 32;
@@ -1019,8 +1017,7 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
       const size_t wsm = p->wide_fwd_smem_bytes[ts4 ? 2 : (ts16 ? 1 : 0)];
       auto wf = ts4 ? wide_forward_kernel<4, true>
                     : (ts16 ? (blk ? wide_forward_kernel<16, true> : wide_forward_kernel<16, false>)
-                            : (cmp ? wide_forward_kernel<8, true, true>
-                                   : (blk ? wide_forward_kernel<8, true> : wide_forward_kernel<8, false>)));
+                            : (blk ? wide_forward_kernel<8, true> : wide_forward_kernel<8, false>));
       if (ts4 && !blk) {  // (only reachable through RAYEN_WIDE_TS=4 on a narrow set: there is no unblocked 4-tile build)
         if (prev != p->device) cudaSetDevice(prev);
         return fail(RAYEN_ERR_UNSUPPORTED, "RAYEN_WIDE_TS=4 needs n >= %d", kWideBlockedN);
@@ -1293,6 +1290,75 @@ extern "C" int rayen_violation_f32(const rayen_plan_t* p, const float* y, int64_
   }
   if (prev != p->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return cuda_fail(e, "violation launch");
+  return RAYEN_OK;
+}
+
+// ----------------------------------------------------------------------------- all-gather of y over peer memory
+struct GatherDst {
+  float* base[16];
+};
+// words: floats to move; each destination receives them at `word_offset`.  VEC: 16-byte accesses (everything aligned).
+template <bool VEC, bool MULTICAST>
+__global__ void __launch_bounds__(256) gather_push_kernel(const float* __restrict__ src, long long words, GatherDst dst,
+                                                          int n_dst, long long word_offset) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  if constexpr (VEC) {
+    const long long n4 = words >> 2;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(src) + i);
+      if constexpr (MULTICAST) {
+        float* p = dst.base[0] + word_offset + 4 * i;
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x.x), "f"(x.y), "f"(x.z),
+                     "f"(x.w)
+                     : "memory");
+      } else {
+        for (int r = 0; r < n_dst; ++r) *(reinterpret_cast<float4*>(dst.base[r] + word_offset) + i) = x;
+      }
+    }
+  } else {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < words; i += stride) {
+      const float x = __ldg(src + i);
+      if constexpr (MULTICAST) {
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst.base[0] + word_offset + i), "f"(x) : "memory");
+      } else {
+        for (int r = 0; r < n_dst; ++r) dst.base[r][word_offset + i] = x;
+      }
+    }
+  }
+}
+
+extern "C" int rayen_gather_push_f32(const float* src, int64_t rows, int32_t k, float* const* dst_bases, int32_t n_dst,
+                                     float* multicast_base, int64_t row_offset, void* stream_) {
+  if (rows < 0 || k < 1 || row_offset < 0) return fail(RAYEN_ERR_BAD_ARGUMENT, "bad gather shape");
+  if (rows == 0) return RAYEN_OK;
+  if (!src || (!multicast_base && (!dst_bases || n_dst < 1 || n_dst > 16)))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "gather: null source, or neither a multicast mapping nor 1..16 peer buffers");
+  GatherDst d{};
+  if (multicast_base) {
+    d.base[0] = multicast_base;
+  } else {
+    for (int r = 0; r < n_dst; ++r) {
+      if (!dst_bases[r]) return fail(RAYEN_ERR_BAD_ARGUMENT, "gather: peer buffer %d is null", r);
+      d.base[r] = dst_bases[r];
+    }
+  }
+  const long long words = rows * static_cast<long long>(k), off = row_offset * static_cast<long long>(k);
+  bool vec = (words % 4 == 0) && (off % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0);
+  for (int r = 0; r < (multicast_base ? 1 : n_dst) && vec; ++r) vec = reinterpret_cast<uintptr_t>(d.base[r]) % 16 == 0;
+  const long long items = vec ? words / 4 : words;
+  long long grid = (items + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (multicast_base) {
+    if (vec) gather_push_kernel<true, true><<<static_cast<int>(grid), 256, 0, stream>>>(src, words, d, 1, off);
+    else gather_push_kernel<false, true><<<static_cast<int>(grid), 256, 0, stream>>>(src, words, d, 1, off);
+  } else {
+    if (vec) gather_push_kernel<true, false><<<static_cast<int>(grid), 256, 0, stream>>>(src, words, d, n_dst, off);
+    else gather_push_kernel<false, false><<<static_cast<int>(grid), 256, 0, stream>>>(src, words, d, n_dst, off);
+  }
+  g_launches.fetch_add(1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "gather launch");
   return RAYEN_OK;
 }
 

@@ -66,7 +66,7 @@ __device__ __forceinline__ void wide_fma_col(float w, const float4* __restrict__
 // whose rounding is below 1e-6 there anyway.
 constexpr int kWideAccBlock = 128;
 constexpr int kWideBlockedN = 512;
-constexpr int kWideCompensatedN = 2048;  // from here on the block sums are added with a Kahan term (wide_dot2, CMP)
+constexpr int kWideCompensatedN = kWideBlockedN;  // the row walk's block sums are added with a Kahan term (wide_dot2, CMP)
 
 // acc[s] = sum_{j >= j0} Wt[j][row] * us[j][s]: the column walk of one row against the tile's directions; eight
 // column loads in flight per lane
@@ -150,7 +150,7 @@ __device__ __forceinline__ void wide_dot2(const float* __restrict__ wcol2, int r
       wide_fma_col2<TS>(__ldg(reinterpret_cast<const float2*>(wcol2 + static_cast<size_t>(j) * r_pad)),
                         us4 + static_cast<size_t>(j) * (TS / 4), tot0, tot1);
   } else if constexpr (CMP) {
-    // CMP (sets with n >= kWideCompensatedN = 2048; always in the 4-sample build): dot products of 10^3..10^4 terms that cancel to
+    // CMP (every blocked build, n >= 512): dot products of 10^3..10^4 terms that cancel to
     // 1 / |v| ~ 1e-2 of their terms' scale.  Plain blocks of 128 leave ~2.5e-5 relative error in kappa for the worst of
     // 2000 samples (measured: the 1 x 10000 point of the reference's sweep ended 1.09e-5 outside its row); blocks of 16
     // added to the running total with a Kahan compensation term bring that to the rounding of the inputs (~3e-6).
@@ -237,7 +237,7 @@ __device__ __forceinline__ void wide_take(float c, int ct, float& best, int& tag
 
 // ----------------------------------------------------------------------------- forward
 // grid: one CTA per tile of TS samples (grid-stride); dynamic smem = wide_fwd_smem_bytes(n, TS).
-template <int TS, bool BLK, bool CMP = (TS == 4)>
+template <int TS, bool BLK, bool CMP = BLK>
 __global__ void __launch_bounds__(kWideThreads)
     wide_forward_kernel(const WideDev P, const float* __restrict__ v, long long ldv, float* __restrict__ y,
                         float* __restrict__ kappa_out, int* __restrict__ active_out, long long B, int mode) {

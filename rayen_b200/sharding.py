@@ -86,3 +86,144 @@ def all_gather_outputs(y_local, batch=None, group=None):
     else:
         sizes = [shard_bounds(batch, r, world)[1] - shard_bounds(batch, r, world)[0] for r in range(world)]
     return _AllGatherRows.apply(y_local, sizes, group)
+
+
+# --------------------------------------------------------------------------- the exchange step over peer memory
+class PeerGather:
+    """All-gather of the layer's output over NVLink / NVSwitch peer memory instead of a library collective.
+
+    Every rank owns a [world * rows, k] float32 buffer in *symmetric memory* (``torch.distributed._symmetric_memory``:
+    the plumbing that exchanges the handles; one allocation per rank, mapped into every peer, plus -- on NVSwitch boxes
+    -- one multicast mapping that a single store reaches all ranks through).  Two ways to fill it:
+
+    * ``all_gather(y_local)``: ONE kernel of this library (``rayen_gather_push_f32``) reads this rank's rows and stores
+      them into every rank's buffer: one ``multimem.st`` per 16 bytes through the multicast mapping (the switch
+      replicates), or plain peer stores when there is no multicast mapping.
+    * ``fused_output()``: the address to hand to the forward kernels as their ``y`` -- this rank's rows *inside the
+      multicast mapping*.  The kernels' ordinary ``y`` stores are then the all-gather: no separate pass over ``y`` at
+      all (the epilogue of the forward kernels writes every rank's copy).  Only for plans whose forward kernels never
+      read ``y`` back (n <= 32 without a big LMI) and only with a multicast mapping.
+
+    Both are followed by ``barrier()`` (the symmetric-memory handle's device-side barrier on the current stream) before
+    anyone reads the gathered rows.  Two buffers alternate, so that a rank may start step t+1 while a peer still reads
+    the rows of step t.  Backward of the exchange: NCCL reduce-scatter of the incoming gradient (``_AllGatherRows``).
+    """
+
+    def __init__(self, rows_local, k, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _cabi
+        self._cabi = _cabi
+        self.group = dist.group.WORLD if group is None else group
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.rows, self.k = int(rows_local), int(k)
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = device
+        self.buffers, self.handles = [], []
+        for _ in range(2):
+            buf = symm_mem.empty((self.world * self.rows, self.k), dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(buf, self.group)
+            self.buffers.append(buf)
+            self.handles.append(hdl)
+        self.turn = 0
+        import ctypes
+        self._ptr_arrays = []
+        for hdl in self.handles:
+            arr = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+            self._ptr_arrays.append(arr)
+        self.multicast = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.handles]
+
+    @property
+    def has_multicast(self):
+        return all(m != 0 for m in self.multicast)
+
+    def _next(self):
+        self.turn ^= 1
+        return self.turn
+
+    def barrier(self, which=None):
+        self.handles[self.turn if which is None else which].barrier(channel=0)
+
+    def all_gather(self, y_local, use_multicast=True):
+        """y_local [rows, k] (float32, contiguous, this device) -> the gathered [world * rows, k] buffer (valid until the
+        call after next).  One kernel + one barrier on the current stream."""
+        assert y_local.shape == (self.rows, self.k) and y_local.dtype == torch.float32 and y_local.is_contiguous()
+        t = self._next()
+        import ctypes
+        mc = self.multicast[t] if (use_multicast and self.multicast[t]) else 0
+        rc = self._cabi.lib().rayen_gather_push_f32(
+            y_local.data_ptr(), self.rows, self.k, ctypes.cast(self._ptr_arrays[t], ctypes.POINTER(ctypes.c_void_p)),
+            self.world, mc or None, self.rank * self.rows, torch.cuda.current_stream(self.device).cuda_stream)
+        self._cabi.check(rc, "rayen_gather_push_f32")
+        self.barrier(t)
+        return self.buffers[t]
+
+    def fused_output(self):
+        """(address for the forward kernels' y, buffer index): this rank's rows inside the multicast mapping."""
+        if not self.has_multicast:
+            raise RuntimeError("PeerGather.fused_output needs an NVSwitch multicast mapping (symmetric memory multicast_ptr)")
+        t = self._next()
+        return self.multicast[t] + 4 * self.rank * self.rows * self.k, t
+
+
+class _GatheredRayShoot(torch.autograd.Function):
+    """q [rows, n] on every rank -> y [world * rows, k] on every rank: the layer's forward kernels store y straight
+    into every rank's gathered buffer through the multicast mapping (PeerGather.fused_output), then one barrier.
+    Backward: reduce-scatter of the incoming gradient (this rank's rows, summed over the ranks), then the layer's
+    closed-form backward."""
+
+    @staticmethod
+    def forward(ctx, q, module, gather):
+        from . import _cabi
+        from .constraint_module import _raw_stream
+        v = q.detach()
+        if v.dtype != torch.float32:
+            v = v.float()
+        if v.stride(1) != 1 or v.stride(0) < v.shape[1]:
+            v = v.contiguous()
+        B, cols = v.shape
+        assert B == gather.rows and module.k == gather.k
+        f = module._packed.fields
+        if f.get("wide") or f.get("lmi_big"):
+            raise RuntimeError("the fused all-gather epilogue needs forward kernels that never read y back "
+                               "(n <= 32, LMI size <= 32); use PeerGather.all_gather for this set")
+        st = module._launch_state(v.device)
+        aux = torch.empty((2 * B + st.ws_words(B),), dtype=torch.float32, device=v.device)
+        base = aux.data_ptr()
+        y_ptr, t = gather.fused_output()
+        want_grad = 1 if ctx.needs_input_grad[0] else 0
+        with torch.cuda.device(v.device):
+            rc = st.forward(st.handle, v.data_ptr(), v.stride(0), y_ptr, base, base + 4 * B, B, module._mode, want_grad,
+                            base + 8 * B, _raw_stream(st.index))
+        if rc != 0:
+            _cabi.check(rc, "rayen_forward_f32")
+        gather.barrier(t)
+        ctx.module, ctx.in_dtype, ctx.aux, ctx.have_dkappa, ctx.state, ctx.gather = module, q.dtype, aux, want_grad, st, gather
+        ctx.save_for_backward(v)
+        module._last_aux = (aux, B)
+        return gather.buffers[t]
+
+    @staticmethod
+    def backward(ctx, g_full):
+        from . import _cabi
+        from .constraint_module import _raw_stream
+        (v,) = ctx.saved_tensors
+        gather, st, module, aux = ctx.gather, ctx.state, ctx.module, ctx.aux
+        B, cols = v.shape
+        gy = g_full.new_empty((B, gather.k))
+        dist.reduce_scatter_tensor(gy, g_full.contiguous().float(), op=dist.ReduceOp.SUM, group=gather.group)
+        gv = torch.empty((B, cols), dtype=torch.float32, device=v.device)
+        base = aux.data_ptr()
+        with torch.cuda.device(v.device):
+            rc = st.backward(st.handle, v.data_ptr(), v.stride(0), gy.data_ptr(), base, base + 4 * B, gv.data_ptr(), cols, B,
+                             module._mode, ctx.have_dkappa, base + 8 * B, _raw_stream(st.index))
+        if rc != 0:
+            _cabi.check(rc, "rayen_backward_f32")
+        return (gv if ctx.in_dtype == torch.float32 else gv.to(ctx.in_dtype)), None, None
+
+
+def forward_gathered(module, q, gather):
+    """``ConstraintModule`` forward on this rank's rows ``q`` [rows, n] with the all-gather fused into the forward
+    kernels' epilogue: returns the gathered output [world * rows, k] (a view of the symmetric buffer, valid until the call
+    after next), differentiable with respect to ``q``."""
+    return _GatheredRayShoot.apply(q, module, gather)

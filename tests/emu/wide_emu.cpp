@@ -55,7 +55,7 @@ extern "C" int emu_wide_forward(const float* blob, long long off_wide, int n, in
   if (ts == 16)
     emu_launch(grid, kWideThreads, [&] { if (n >= kWideBlockedN) wide_forward_kernel<16, true>(w, v, ldv, y, kappa, active, B, mode); else wide_forward_kernel<16, false>(w, v, ldv, y, kappa, active, B, mode); });
   else if (ts == 8)
-    emu_launch(grid, kWideThreads, [&] { if (n >= kWideCompensatedN) wide_forward_kernel<8, true, true>(w, v, ldv, y, kappa, active, B, mode); else if (n >= kWideBlockedN) wide_forward_kernel<8, true>(w, v, ldv, y, kappa, active, B, mode); else wide_forward_kernel<8, false>(w, v, ldv, y, kappa, active, B, mode); });
+    emu_launch(grid, kWideThreads, [&] { if (n >= kWideBlockedN) wide_forward_kernel<8, true>(w, v, ldv, y, kappa, active, B, mode); else wide_forward_kernel<8, false>(w, v, ldv, y, kappa, active, B, mode); });
   else if (ts == 4)
     emu_launch(grid, kWideThreads, [&] { wide_forward_kernel<4, true>(w, v, ldv, y, kappa, active, B, mode); });
   else

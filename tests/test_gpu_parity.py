@@ -975,3 +975,19 @@ def test_whole_training_step_replayed_from_a_cuda_graph():
     np.testing.assert_allclose(graph_losses, eager_losses, rtol=1e-5)
     for (n1, p1), (n2, p2) in zip(net_e.named_parameters(), net_g.named_parameters()):
         np.testing.assert_allclose(p2.detach().cpu().numpy(), p1.detach().cpu().numpy(), rtol=1e-4, atol=1e-6, err_msg=n1)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="the exchange step needs two GPUs on the box")
+def test_peer_memory_all_gather_matches_nccl_on_two_gpus():
+    """the all-gather of y through this library's own kernel over peer memory (P2P stores / NVSwitch
+    multicast) and fused into the forward kernels' epilogue, bit-identical to NCCL's all-gather, gradients included
+    (scripts/gather_check.py under torchrun, world size 2)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "scripts", "gather_check.py"), "--batch", "4096"]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    line = [l for l in proc.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)
+    assert res["ok_all_ranks"] and res["checks_this_rank"]["p2p"]
