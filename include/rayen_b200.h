@@ -162,6 +162,11 @@ int rayen_plan_set_tuning(rayen_plan_t* plan, int samples_per_thread, int lanes_
 int rayen_plan_set_pruning(rayen_plan_t* plan, int enabled);
 /* Linear/quadratic/SOC forward on the tensor cores (tcgen05 3xTF32 GEMM, default) or on the FP32 pipe (0). */
 int rayen_plan_set_tensor_cores(rayen_plan_t* plan, int enabled);
+/* Output rows of the tcgen05 kernel through shared-memory tiles: every store instruction writes whole rows of y (512
+ * contiguous bytes per four rows) instead of 16 bytes per lane a row apart.  Off by default (neutral on local HBM); on
+ * when y is a peer / NVSwitch-multicast mapping (the all-gather fused into the kernel's epilogue, sharding.forward_gathered).
+ * Call it before the plan is used concurrently. */
+int rayen_plan_set_coalesced_output(rayen_plan_t* plan, int enabled);
 /* LMI contraction sum_a u_a F~z_a (reference constraint_module.py:412-421) as a tcgen05 3xTF32 GEMM inside the LMI
  * forward kernel (lmi_tc.cuh; needs lmi_rp >= 16) or on the FP32 pipe out of shared memory (lmi.cuh).
  * mode: 0 never, 1 wherever available, 2 automatic (default): the measured policy -- tensor cores when K = 32 and

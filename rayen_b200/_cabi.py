@@ -50,6 +50,7 @@ SYMBOLS = {
     "rayen_plan_set_tuning": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int]),
     "rayen_plan_set_pruning": (ctypes.c_int, [_P, ctypes.c_int]),
     "rayen_plan_set_tensor_cores": (ctypes.c_int, [_P, ctypes.c_int]),
+    "rayen_plan_set_coalesced_output": (ctypes.c_int, [_P, ctypes.c_int]),
     "rayen_plan_set_lmi_tensor_cores": (ctypes.c_int, [_P, ctypes.c_int]),
     "rayen_plan_set_lmi_filter": (ctypes.c_int, [_P, ctypes.c_int]),
     "rayen_workspace_bytes": (ctypes.c_int64, [_P, ctypes.c_int64]),
@@ -155,6 +156,9 @@ class DevicePlan:
 
     def set_tensor_cores(self, enabled=True):
         check(lib().rayen_plan_set_tensor_cores(self._handle, 1 if enabled else 0), "rayen_plan_set_tensor_cores")
+
+    def set_coalesced_output(self, enabled=True):
+        check(lib().rayen_plan_set_coalesced_output(self._handle, 1 if enabled else 0), "rayen_plan_set_coalesced_output")
 
     def set_lmi_tensor_cores(self, mode):
         """0 / False: never, 1 / True: wherever available, 2 / None: automatic."""

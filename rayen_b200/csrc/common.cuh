@@ -22,6 +22,7 @@ struct PlanDev {
   int off_lmitc, lmitc_panels, lmitc_stages;   // LMI matrices as a tcgen05 B operand (lmi_tc.cuh); ring depth
   float lmi_bound_margin;                      // float32-rounding allowance of the pruning bound (rayen_b200.h, BOUND)
   int off_lmiw;                                // LMI matrices for lmi_warp.cuh (0: none)
+  int tc_y_stage;                              // lqs_tc.cuh: the kernel's shared memory includes the y staging tiles (coalesced stores)
 };
 
 // Fused mapper (reference constraint_module.py:261, :525: q = nn.Linear(input_dim, n)(x)): when x != nullptr the

@@ -133,10 +133,14 @@ __device__ __forceinline__ float soc_kappa_fp32(const float* __restrict__ item, 
   return soc_root(__ldg(item + 2 * KP + TRI), hb, fmaf(-cu, cu, ss), nullptr);
 }
 
+// y staging (coalesced stores): per epilogue warp 16 rows of KP floats, row stride KP + 4 words (16-byte aligned rows; the
+// 8 lanes of a quarter-warp writing 16 bytes of 8 different rows hit 8 different bank groups)
+constexpr int kTcStageRows = 16;
 template <int KP>
-__host__ __device__ constexpr size_t lqs_tc_smem_bytes(int n_panels) {
+__host__ __device__ constexpr size_t lqs_tc_smem_bytes(int n_panels, bool y_stage = false) {
   return 256 + static_cast<size_t>((n_panels * kTcTableWords + 3) / 4 * 4) * 4 + 4 * static_cast<size_t>(KP) * 128 * 4 +
-         static_cast<size_t>(kTcStages) * 2 * KP * kTcPanel * 4;
+         static_cast<size_t>(kTcStages) * 2 * KP * kTcPanel * 4 +
+         (y_stage ? static_cast<size_t>(kTcEpiWarps) * kTcStageRows * (KP + 4) * 4 : 0);
 }
 
 // ----------------------------------------------------------------------------- the kernel
@@ -165,6 +169,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int n_panels = P.tc_panels;
   float* a_tiles = table + (n_panels * kTcTableWords + 3) / 4 * 4;  // [tile 0/1][hi, lo][A_TILE]
   float* w_ring = a_tiles + 4 * A_TILE;                              // [stage][hi, lo][W_TILE]
+  float* y_stage = w_ring + kTcStages * 2 * W_TILE;                  // [epilogue warp][16 rows][KP + 4] (P.tc_y_stage)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* tc_base = P.blob + P.off_tc;
@@ -466,43 +471,81 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           if (enq) work_list[slot0 + __popc(m & ((1u << lane) - 1u))] = static_cast<int>(b);
         }
       }
-      if (!valid) continue;
-      if (kappa_out) kappa_out[b] = best;
-      if (active_out) active_out[b] = tag;
-      if (!finish) continue;
-      float alpha;
-      if (mode == RAYEN_MODE_RAYEN_OLD)
-        alpha = 1.0f / (expf(beta) + best);
-      else
-        alpha = fminf(1.0f / best, s);
-      float* yrow = y + b * k;
-      if (P.n_is_identity) {
+      if (valid) {
+        if (kappa_out) kappa_out[b] = best;
+        if (active_out) active_out[b] = tag;
+      }
+      const bool writes = valid && finish;
+      float alpha = 0.f;
+      if (writes) alpha = (mode == RAYEN_MODE_RAYEN_OLD) ? 1.0f / (expf(beta) + best) : fminf(1.0f / best, s);
+      if (P.n_is_identity && vec_out && P.tc_y_stage) {
+        // Coalesced y: the warp's 32 samples are 32 consecutive rows of y.  Half of them at a time go through a
+        // shared-memory tile, and every store instruction then writes whole rows -- 512 contiguous bytes per four rows --
+        // instead of 16 bytes per lane with a row (128 bytes at k = 32) between lanes.  Same bytes for HBM, but 4x fewer
+        // 32-byte sectors per instruction, and when y is a peer / multicast mapping (sharding.forward_gathered: the
+        // all-gather fused into this epilogue) full-width NVLink writes instead of one small write per lane.
+        const unsigned wmask = __ballot_sync(0xffffffffu, writes);
+        if (wmask != 0u) {
+          constexpr int ST = KP + 4;
+          float* stg = y_stage + warp * (kTcStageRows * ST);
+          const int kc = k >> 2;
+          float* ybase = y + (b - lane) * k;  // row of lane 0
 #pragma unroll
-        for (int kk = 0; kk < KP / 4; ++kk) {
-          if (4 * kk < k) {
-            float4 o;
-            o.x = fmaf(alpha, u[4 * kk + 0], __ldg(y0 + 4 * kk + 0));
-            o.y = fmaf(alpha, u[4 * kk + 1], __ldg(y0 + 4 * kk + 1));
-            o.z = fmaf(alpha, u[4 * kk + 2], __ldg(y0 + 4 * kk + 2));
-            o.w = fmaf(alpha, u[4 * kk + 3], __ldg(y0 + 4 * kk + 3));
-            if (vec_out) {
-              *reinterpret_cast<float4*>(yrow + 4 * kk) = o;
-            } else {
-              if (4 * kk + 0 < k) yrow[4 * kk + 0] = o.x;
-              if (4 * kk + 1 < k) yrow[4 * kk + 1] = o.y;
-              if (4 * kk + 2 < k) yrow[4 * kk + 2] = o.z;
-              if (4 * kk + 3 < k) yrow[4 * kk + 3] = o.w;
+          for (int h = 0; h < 2; ++h) {
+            __syncwarp();
+            if ((lane >> 4) == h && writes) {
+              float* dst = stg + (lane & 15) * ST;
+#pragma unroll
+              for (int kk = 0; kk < KP / 4; ++kk) {
+                if (4 * kk < k) {
+                  float4 o;
+                  o.x = fmaf(alpha, u[4 * kk + 0], __ldg(y0 + 4 * kk + 0));
+                  o.y = fmaf(alpha, u[4 * kk + 1], __ldg(y0 + 4 * kk + 1));
+                  o.z = fmaf(alpha, u[4 * kk + 2], __ldg(y0 + 4 * kk + 2));
+                  o.w = fmaf(alpha, u[4 * kk + 3], __ldg(y0 + 4 * kk + 3));
+                  *reinterpret_cast<float4*>(dst + 4 * kk) = o;
+                }
+              }
+            }
+            __syncwarp();
+            for (int c = lane; c < kTcStageRows * kc; c += 32) {
+              const int r = c / kc, cc = c - r * kc;
+              if ((wmask >> (16 * h + r)) & 1u)
+                *reinterpret_cast<float4*>(ybase + static_cast<long long>(16 * h + r) * k + 4 * cc) =
+                    *reinterpret_cast<const float4*>(stg + r * ST + 4 * cc);
             }
           }
         }
-      } else {
-        for (int i = 0; i < k; ++i) {
-          const float* nrow = nmat + i * (P.np + 4);
-          float acc = 0.f;
+      } else if (writes) {
+        float* yrow = y + b * k;
+        if (P.n_is_identity) {
 #pragma unroll
-          for (int a = 0; a < KP; ++a)
-            if (a < P.np) acc = fmaf(__ldg(nrow + a), u[a], acc);
-          yrow[i] = fmaf(alpha, acc, __ldg(y0 + i));
+          for (int kk = 0; kk < KP / 4; ++kk) {
+            if (4 * kk < k) {
+              float4 o;
+              o.x = fmaf(alpha, u[4 * kk + 0], __ldg(y0 + 4 * kk + 0));
+              o.y = fmaf(alpha, u[4 * kk + 1], __ldg(y0 + 4 * kk + 1));
+              o.z = fmaf(alpha, u[4 * kk + 2], __ldg(y0 + 4 * kk + 2));
+              o.w = fmaf(alpha, u[4 * kk + 3], __ldg(y0 + 4 * kk + 3));
+              if (vec_out) {
+                *reinterpret_cast<float4*>(yrow + 4 * kk) = o;
+              } else {
+                if (4 * kk + 0 < k) yrow[4 * kk + 0] = o.x;
+                if (4 * kk + 1 < k) yrow[4 * kk + 1] = o.y;
+                if (4 * kk + 2 < k) yrow[4 * kk + 2] = o.z;
+                if (4 * kk + 3 < k) yrow[4 * kk + 3] = o.w;
+              }
+            }
+          }
+        } else {
+          for (int i = 0; i < k; ++i) {
+            const float* nrow = nmat + i * (P.np + 4);
+            float acc = 0.f;
+#pragma unroll
+            for (int a = 0; a < KP; ++a)
+              if (a < P.np) acc = fmaf(__ldg(nrow + a), u[a], acc);
+            yrow[i] = fmaf(alpha, acc, __ldg(y0 + i));
+          }
         }
       }
     }

@@ -161,11 +161,11 @@ static LqsTcFn lqs_tc_fn(int kp) {
     default: return lqs_tc_forward_kernel<32>;
   }
 }
-static size_t lqs_tc_smem(int kp, int panels) {
+static size_t lqs_tc_smem(int kp, int panels, bool y_stage = false) {
   switch (kp) {
-    case 8: return lqs_tc_smem_bytes<8>(panels);
-    case 16: return lqs_tc_smem_bytes<16>(panels);
-    default: return lqs_tc_smem_bytes<32>(panels);
+    case 8: return lqs_tc_smem_bytes<8>(panels, y_stage);
+    case 16: return lqs_tc_smem_bytes<16>(panels, y_stage);
+    default: return lqs_tc_smem_bytes<32>(panels, y_stage);
   }
 }
 static LqsBwdFn lqs_bwd_fn(int np) {
@@ -248,6 +248,13 @@ static cudaError_t launch_lmi_forward(LmiFwdFn fn, int blocks, int threads, size
 
 static int allow_smem(const void* fn, size_t bytes) {
   if (bytes > 48 * 1024) {
+    // the attribute belongs to the function, not to the plan: always the device maximum, so that plans of different
+    // sizes coexist in one process (a later, smaller plan must not lower the limit of an earlier one)
+    int dev = 0, optin = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess &&
+        static_cast<size_t>(optin) > bytes)
+      bytes = static_cast<size_t>(optin);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
   }
@@ -487,6 +494,14 @@ extern "C" int rayen_plan_create(const RayenPlanDesc* d, int device, rayen_plan_
   p->lqs_smem = p->lqs_smem_bytes <= static_cast<size_t>(p->max_smem_optin);
   if (!p->lqs_smem) p->lqs_smem_bytes = 64;
   p->tc_smem_bytes = lqs_tc_smem(v.tc_kp, v.tc_panels);
+  // y staging tiles (coalesced stores, rayen_plan_set_coalesced_output): off by default -- measured neutral to slightly
+  // slower on local HBM (cfg5 25.5 vs 25.4 us, cfg3 11.6 vs 11.0 us) -- and what makes y stores through a peer / multicast
+  // mapping efficient (sharding.forward_gathered turns it on: fused all-gather epilogue 124 -> 77 us on 2 GPUs)
+  if (getenv("RAYEN_TC_YSTAGE") && atoi(getenv("RAYEN_TC_YSTAGE")) == 1 &&
+      lqs_tc_smem(v.tc_kp, v.tc_panels, true) <= static_cast<size_t>(p->max_smem_optin)) {
+    p->tc_smem_bytes = lqs_tc_smem(v.tc_kp, v.tc_panels, true);
+    v.tc_y_stage = 1;
+  }
   // measured on B200 (scripts/time_kernels.py): the GEMM formulation wins from K = 16 up; at K = 8 the FP32-pipe
   // kernel is faster (the GEMM is too thin to pay for the TMEM round trip)
   p->use_tc = p->tc_smem_bytes <= static_cast<size_t>(p->max_smem_optin) && v.np >= 16;
@@ -721,6 +736,24 @@ extern "C" int rayen_plan_set_tuning(rayen_plan_t* p, int tm, int lanes) {
     return fail(RAYEN_ERR_BAD_ARGUMENT, "lanes_per_sample must be 0 or a power of two <= 32");
   p->tune_tm = tm;
   p->tune_lanes = lanes;
+  return RAYEN_OK;
+}
+
+extern "C" int rayen_plan_set_coalesced_output(rayen_plan_t* p, int enabled) {
+  if (!p) return fail(RAYEN_ERR_BAD_ARGUMENT, "null plan");
+  if (p->wide || p->dev.tc_kp == 0) return RAYEN_OK;  // only the tcgen05 kernel stages its output
+  const size_t with = lqs_tc_smem(p->dev.tc_kp, p->dev.tc_panels, true), without = lqs_tc_smem(p->dev.tc_kp, p->dev.tc_panels, false);
+  const bool on = enabled && with <= static_cast<size_t>(p->max_smem_optin);
+  if (on) {
+    int prev = 0;
+    RAYEN_CUDA(cudaGetDevice(&prev));
+    if (prev != p->device) RAYEN_CUDA(cudaSetDevice(p->device));
+    const int rc = allow_smem(reinterpret_cast<const void*>(lqs_tc_fn(p->dev.tc_kp)), with);
+    if (prev != p->device) cudaSetDevice(prev);
+    if (rc) return rc;
+  }
+  p->dev.tc_y_stage = on ? 1 : 0;
+  p->tc_smem_bytes = on ? with : without;
   return RAYEN_OK;
 }
 

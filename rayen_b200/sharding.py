@@ -188,6 +188,9 @@ class _GatheredRayShoot(torch.autograd.Function):
             raise RuntimeError("the fused all-gather epilogue needs forward kernels that never read y back "
                                "(n <= 32, LMI size <= 32); use PeerGather.all_gather for this set")
         st = module._launch_state(v.device)
+        if not getattr(st, "_coalesced", False):
+            st.plan.set_coalesced_output(True)   # whole rows per store instruction: full-width NVLink writes
+            st._coalesced = True
         aux = torch.empty((2 * B + st.ws_words(B),), dtype=torch.float32, device=v.device)
         base = aux.data_ptr()
         y_ptr, t = gather.fused_output()
