@@ -134,26 +134,30 @@ __device__ __forceinline__ float lw_sum_chain(float x, float* __restrict__ buf, 
 }
 
 // ----------------------------------------------------------------------------- filter: 4 samples per warp
+template <int MT>
 struct LwFilter {
-  float A[kLwMT][kLwR];  // A[m][i] = entry (i, lane) of sample m's matrix
+  float A[MT][kLwR];  // A[m][i] = entry (i, lane) of sample m's matrix
 
   // S~_m = sum_a u_m[a] F~z_a for the 4 samples of the chunk; us[a * 4 + m] = u_m[a]
   __device__ __forceinline__ void contract(const float* __restrict__ FW, int n, const float* __restrict__ us, int lane) {
 #pragma unroll
-    for (int m = 0; m < kLwMT; ++m)
+    for (int m = 0; m < MT; ++m)
 #pragma unroll
       for (int i = 0; i < kLwR; ++i) A[m][i] = 0.f;
     const float* Fj = FW + lane * kLwRowStride;
 #pragma unroll 2
     for (int a = 0; a < n; ++a) {
       const float4 u4 = lw_ld4(us + 4 * a);
-      const float um[kLwMT] = {u4.x, u4.y, u4.z, u4.w};
+      const float um4[4] = {u4.x, u4.y, u4.z, u4.w};
+      float um[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) um[m] = um4[m];
       const float* Fa = Fj + a * kLwMatWords;
 #pragma unroll
       for (int c = 0; c < kLwR / 4; ++c) {
         const float4 f = lw_ld4(Fa + 4 * c);
 #pragma unroll
-        for (int m = 0; m < kLwMT; ++m) {
+        for (int m = 0; m < MT; ++m) {
           A[m][4 * c + 0] = fmaf(um[m], f.x, A[m][4 * c + 0]);
           A[m][4 * c + 1] = fmaf(um[m], f.y, A[m][4 * c + 1]);
           A[m][4 * c + 2] = fmaf(um[m], f.z, A[m][4 * c + 2]);
@@ -170,18 +174,18 @@ struct LwFilter {
   // it with predicated stores out of the unrolled row loop, and rows >= 8 S are updated whether or not they are still
   // live (rows <= k only collect rounding noise that nothing reads).
   template <int S>
-  __device__ __forceinline__ void ldlt_stage(float* __restrict__ cb, int lane, bool (&ok)[kLwMT]) {
+  __device__ __forceinline__ void ldlt_stage(float* __restrict__ cb, int lane, bool (&ok)[MT]) {
     constexpr int R0 = 8 * S;
 #pragma unroll 1
     for (int k = R0; k < R0 + 8; ++k) {
-      const float* buf = cb + (k & 1) * (kLwMT * kLwR);        // row k of the trailing matrices, spread over the lanes
-      float* nbuf = cb + ((k + 1) & 1) * (kLwMT * kLwR);
+      const float* buf = cb + (k & 1) * (4 * kLwR);        // row k of the trailing matrices, spread over the lanes
+      float* nbuf = cb + ((k + 1) & 1) * (4 * kLwR);
       __syncwarp();
       // all loads of the step first, all stores last: a store to nbuf inside the per-matrix loop would order the next
       // matrix's loads behind it (same base pointer) and serialise the four independent factorisations
-      float my[kLwMT], nxt[kLwMT];
+      float my[MT], nxt[MT];
 #pragma unroll
-      for (int m = 0; m < kLwMT; ++m) {
+      for (int m = 0; m < MT; ++m) {
         const float d = buf[m * kLwR + k];
         ok[m] = ok[m] && (d > 0.f);  // NaN fails
         my[m] = buf[m * kLwR + lane] * lw_rcp(d);  // M[k][lane] / d
@@ -190,7 +194,7 @@ struct LwFilter {
 #pragma unroll
       for (int c = 0; c < (kLwR - R0) / 4; ++c) {
 #pragma unroll
-        for (int m = 0; m < kLwMT; ++m) {
+        for (int m = 0; m < MT; ++m) {
           const float4 x = lw_ld4(buf + m * kLwR + R0 + 4 * c);
           const float cr[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
@@ -205,7 +209,7 @@ struct LwFilter {
         }
       }
 #pragma unroll
-      for (int m = 0; m < kLwMT; ++m) nbuf[m * kLwR + lane] = nxt[m];
+      for (int m = 0; m < MT; ++m) nbuf[m * kLwR + lane] = nxt[m];
     }
   }
 
@@ -214,10 +218,10 @@ struct LwFilter {
   // M + E with |E| <= c r eps |M| (c r eps ~ 2e-6 at r = 32, far less in practice) and |M|_2 <= tau + |S~|_F, so with
   // margin = 1e-5 (kprior + |S~|_F) a pass proves lambda_max(S~_m) < kprior_m; a failure proves nothing and costs a
   // full solve.  Returns the 4-bit pass mask (identical in every lane).  Destroys A.
-  __device__ __forceinline__ unsigned passes(const float (&kprior)[kLwMT], float* __restrict__ cb, int lane) {
-    bool ok[kLwMT];
+  __device__ __forceinline__ unsigned passes(const float (&kprior)[MT], float* __restrict__ cb, int lane) {
+    bool ok[MT];
 #pragma unroll
-    for (int m = 0; m < kLwMT; ++m) {
+    for (int m = 0; m < MT; ++m) {
       float f2 = 0.f;
 #pragma unroll
       for (int i = 0; i < kLwR; ++i) f2 = fmaf(A[m][i], A[m][i], f2);
@@ -234,7 +238,7 @@ struct LwFilter {
     ldlt_stage<3>(cb, lane, ok);
     unsigned mask = 0u;
 #pragma unroll
-    for (int m = 0; m < kLwMT; ++m) mask |= ok[m] ? (1u << m) : 0u;
+    for (int m = 0; m < MT; ++m) mask |= ok[m] ? (1u << m) : 0u;
     return mask;
   }
 };
@@ -550,11 +554,11 @@ struct LwSolver {
 };
 
 // value of x[m] for a runtime m < 4 without dynamic register indexing
-template <class T>
-__device__ __forceinline__ T lw_pick(const T (&x)[kLwMT], int m) {
+template <class T, int MT>
+__device__ __forceinline__ T lw_pick(const T (&x)[MT], int m) {
   T r = x[0];
 #pragma unroll
-  for (int i = 1; i < kLwMT; ++i)
+  for (int i = 1; i < MT; ++i)
     if (m == i) r = x[i];
   return r;
 }
@@ -589,8 +593,8 @@ __device__ __forceinline__ void lw_write_y(const LwCtx& C, float* __restrict__ y
 // need it in backward.
 // `solve_budget` (in/out): how many failing samples this warp may still solve itself; the others are appended to
 // fail_list (fail_count: running counter in global memory) for the launch behind this one.
-template <bool WITH_GRAD>
-__device__ __forceinline__ void lw_process_chunk(const LwCtx& C, const long long (&b)[kLwMT], const bool (&valid)[kLwMT],
+template <bool WITH_GRAD, int MT = kLwMT>
+__device__ __forceinline__ void lw_process_chunk(const LwCtx& C, const long long (&b)[MT], const bool (&valid)[MT],
                                                  const float* __restrict__ v, long long ldv, float* __restrict__ y,
                                                  float* __restrict__ kappa_io, int* __restrict__ active_io,
                                                  float* __restrict__ dkappa, int lane, bool use_filter,
@@ -598,13 +602,13 @@ __device__ __forceinline__ void lw_process_chunk(const LwCtx& C, const long long
                                                  int* __restrict__ fail_count) {
   float* us = C.scr + kLwScrUs;
   const int n = C.n;
-  float kprior[kLwMT], s[kLwMT], beta[kLwMT];
-  int tprior[kLwMT];
+  float kprior[MT], s[MT], beta[MT];
+  int tprior[MT];
   LW_STAMP(0);
   {
-    float x[kLwMT], ss[kLwMT];
+    float x[MT], ss[MT];
 #pragma unroll
-    for (int m = 0; m < kLwMT; ++m) {
+    for (int m = 0; m < MT; ++m) {
       x[m] = (valid[m] && lane < n) ? __ldg(v + b[m] * ldv + lane) : 0.f;
       kprior[m] = valid[m] ? kappa_io[b[m]] : 0.f;
       tprior[m] = valid[m] ? active_io[b[m]] : 0;
@@ -614,11 +618,11 @@ __device__ __forceinline__ void lw_process_chunk(const LwCtx& C, const long long
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1)
 #pragma unroll
-      for (int m = 0; m < kLwMT; ++m) ss[m] += __shfl_xor_sync(0xffffffffu, ss[m], off);
+      for (int m = 0; m < MT; ++m) ss[m] += __shfl_xor_sync(0xffffffffu, ss[m], off);
     float4 u4;
-    float um[kLwMT];
+    float um[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int m = 0; m < kLwMT; ++m) {
+    for (int m = 0; m < MT; ++m) {
       s[m] = sqrtf(ss[m]);
       um[m] = x[m] * (1.0f / fmaxf(s[m], 1e-12f));
     }
@@ -631,7 +635,7 @@ __device__ __forceinline__ void lw_process_chunk(const LwCtx& C, const long long
   LW_STAMP(1);
   unsigned pass = 0u;
   if (use_filter) {
-    LwFilter F;
+    LwFilter<MT> F;
     F.contract(C.FW, n, us, lane);
     LW_STAMP(2);
     pass = F.passes(kprior, C.scr + kLwScrCb, lane);
@@ -639,7 +643,7 @@ __device__ __forceinline__ void lw_process_chunk(const LwCtx& C, const long long
   LW_STAMP(3);
   // ---- samples the filter settled: the prior (kappa, tag) stands; scale step (reference :472-474 / :464-465, :512-514)
 #pragma unroll
-  for (int m = 0; m < kLwMT; ++m) {
+  for (int m = 0; m < MT; ++m) {
     if (valid[m] && ((pass >> m) & 1u)) {
       const float alpha = (C.mode == RAYEN_MODE_RAYEN_OLD) ? 1.0f / (expf(beta[m]) + kprior[m])
                                                           : fminf(1.0f / kprior[m], s[m]);
@@ -651,12 +655,12 @@ __device__ __forceinline__ void lw_process_chunk(const LwCtx& C, const long long
   // low-latency path for the usual case of a rare failure); what is left goes to the fail list
   unsigned todo = 0u;
 #pragma unroll
-  for (int m = 0; m < kLwMT; ++m) todo |= (valid[m] && !((pass >> m) & 1u)) ? (1u << m) : 0u;
+  for (int m = 0; m < MT; ++m) todo |= (valid[m] && !((pass >> m) & 1u)) ? (1u << m) : 0u;
   {
     unsigned hand_over = 0u;
     int keep = solve_budget;
 #pragma unroll
-    for (int m = 0; m < kLwMT; ++m) {
+    for (int m = 0; m < MT; ++m) {
       if ((todo >> m) & 1u) {
         if (keep > 0) --keep;
         else hand_over |= 1u << m;
@@ -667,13 +671,13 @@ __device__ __forceinline__ void lw_process_chunk(const LwCtx& C, const long long
       int slot = 0;
       if (lane == 0) slot = atomicAdd(fail_count, __popc(hand_over));
       slot = __shfl_sync(0xffffffffu, slot, 0);
-      if (lane < kLwMT && ((hand_over >> lane) & 1u))
+      if (lane < MT && ((hand_over >> lane) & 1u))
         fail_list[slot + __popc(hand_over & ((1u << lane) - 1u))] = static_cast<int>(lw_pick(b, lane));
       todo &= ~hand_over;
     }
   }
 #pragma unroll 1
-  for (int m = 0; m < kLwMT; ++m) {
+  for (int m = 0; m < MT; ++m) {
     if (!((todo >> m) & 1u)) continue;  // warp-uniform
     const long long bm = lw_pick(b, m);
     const float k0 = lw_pick(kprior, m), sm = lw_pick(s, m), bt = lw_pick(beta, m);
@@ -720,6 +724,10 @@ __device__ __forceinline__ void lw_process_chunk(const LwCtx& C, const long long
 #ifndef RAYEN_EMU
 // ============================================================================= PTX below: the kernel around the chunks
 constexpr int kLwThreads = 256;
+template <int V>
+struct LwTag {
+  static constexpr int value = V;
+};
 
 __host__ __device__ constexpr size_t lmi_warp_smem_bytes(int n, int threads) {
   return 192 + static_cast<size_t>(n) * kLwMatWords * 4 + static_cast<size_t>(threads / 32) * kLwScratch * 4;
@@ -753,9 +761,13 @@ __global__ void __launch_bounds__(kLwThreads, 1)
   __syncthreads();
   pdl_wait();  // launched behind the linear/quadratic/SOC kernel: its kappa / active / work list must be complete
   const long long total = work_list ? static_cast<long long>(ld_after_wait(work_count)) : B;
-  // with the filter a warp takes 4 samples at a time (register tiling of the contraction); without it the samples are
-  // solved one by one anyway, so one sample per warp spreads a short list over more warps
-  const int per = use_filter ? kLwMT : 1;
+  // with the filter a warp takes 4 samples at a time (register tiling of the contraction: every F~z word feeds 4 FMAs)
+  // -- or 2 when the list is short enough for every warp of the grid to get at most one chunk of 2: a chunk is one
+  // warp's dependent chain, and with one busy warp per scheduler nothing hides its latencies; twice as many warps on
+  // half the work each finish sooner (cfg5: 2115 samples on 1184 warps).  Without the filter the samples are solved one
+  // by one anyway, so one sample per warp spreads a short list over more warps
+  const long long n_warps_total = static_cast<long long>(gridDim.x) * (kLwThreads / 32);
+  const int per = use_filter ? ((total <= 2 * n_warps_total) ? 2 : kLwMT) : 1;
   const long long n_chunks = (total + per - 1) / per;
   const bool cta_has_work = static_cast<long long>(blockIdx.x) < n_chunks;
   if (threadIdx.x == 0 && cta_has_work) stage_bulk(fw, P.blob + P.off_lmiw, fw_words, &bars[0]);
@@ -772,37 +784,41 @@ __global__ void __launch_bounds__(kLwThreads, 1)
   // every warp starts with the chunk of its own number; further chunks are handed out by a counter (next_chunk, zeroed
   // before the launch), so that a warp that had eigen-solves to do takes fewer chunks: with a static stride the kernel
   // waits for the unluckiest warp (cfg5 "loose", 13 % of the samples LMI-bound: 0.48 instead of 0.30 ms)
-  const long long n_warps_total = static_cast<long long>(gridDim.x) * (kLwThreads / 32);
   long long c = static_cast<long long>(warp) * gridDim.x + blockIdx.x;
-  while (c < n_chunks) {
-    long long b[kLwMT];
-    bool valid[kLwMT];
-    {
-      const long long idx = c * per + (lane & 3);
-      const bool ok = (lane & 3) < per && idx < total;
-      const int mine = ok ? (work_list ? work_list[idx] : static_cast<int>(idx)) : 0;
+  auto run = [&](auto mt_tag) {
+    constexpr int MT = decltype(mt_tag)::value;
+    while (c < n_chunks) {
+      long long b[MT];
+      bool valid[MT];
+      {
+        const long long idx = c * per + (lane & 3);
+        const bool ok = (lane & 3) < per && idx < total;
+        const int mine = ok ? (work_list ? work_list[idx] : static_cast<int>(idx)) : 0;
 #pragma unroll
-      for (int m = 0; m < kLwMT; ++m) {
-        b[m] = __shfl_sync(0xffffffffu, mine, m);
-        valid[m] = m < per && c * per + m < total;
+        for (int m = 0; m < MT; ++m) {
+          b[m] = __shfl_sync(0xffffffffu, mine, m);
+          valid[m] = m < per && c * per + m < total;
+        }
+      }
+      LW_STAMP(6);
+      if (!staged) {
+        mbar_wait(&bars[0], 0);
+        staged = true;
+      }
+      LW_STAMP(7);
+      lw_process_chunk<WITH_GRAD, MT>(C, b, valid, v, ldv, y, kappa_io, active_io, dkappa, lane, use_filter != 0, solve_budget,
+                                      fail_list, fail_count);
+      if (next_chunk) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(next_chunk, 1);
+        c = n_warps_total + __shfl_sync(0xffffffffu, t, 0);
+      } else {
+        c += n_warps_total;
       }
     }
-    LW_STAMP(6);
-    if (!staged) {
-      mbar_wait(&bars[0], 0);
-      staged = true;
-    }
-    LW_STAMP(7);
-    lw_process_chunk<WITH_GRAD>(C, b, valid, v, ldv, y, kappa_io, active_io, dkappa, lane, use_filter != 0, solve_budget,
-                                fail_list, fail_count);
-    if (next_chunk) {
-      int t = 0;
-      if (lane == 0) t = atomicAdd(next_chunk, 1);
-      c = n_warps_total + __shfl_sync(0xffffffffu, t, 0);
-    } else {
-      c += n_warps_total;
-    }
-  }
+  };
+  if (per == 2) run(LwTag<2>{});
+  else run(LwTag<kLwMT>{});
   if (!staged && cta_has_work) mbar_wait(&bars[0], 0);  // never exit with a bulk copy in flight
 #if defined(RAYEN_LW_TRACE)
   __syncthreads();

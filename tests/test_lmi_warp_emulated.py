@@ -29,7 +29,7 @@ def emu(tmp_path_factory):
     lib = ctypes.CDLL(lib_path)
     lib.emu_lmi_warp.restype = ctypes.c_int
     lib.emu_lmi_warp.argtypes = [_F, ctypes.c_int, ctypes.c_int, _F, _F, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F, _LL, _F,
-                                 _F, _I, _F, _LL, _I, _LL, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _I, _I]
+                                 _F, _I, _F, _LL, _I, _LL, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _I, _I, ctypes.c_int]
     return lib
 
 
@@ -38,7 +38,7 @@ def _ptr(a, t=_F):
 
 
 def run_warp_path(lib, p, v, kprior, tprior, mode=0, use_filter=True, with_grad=True, work_list=None, warps=3,
-                  solves_per_warp=1 << 20, return_fails=False):
+                  solves_per_warp=1 << 20, return_fails=False, mt=4):
     """kappa_io / active_io start as the prior of the other families; returns y, kappa, active, dkappa (and the list of
     samples handed over to the other kernel when a warp's solve budget is limited)."""
     f = p.fields
@@ -59,7 +59,7 @@ def run_warp_path(lib, p, v, kprior, tprior, mode=0, use_filter=True, with_grad=
     rc = lib.emu_lmi_warp(_ptr(FW), n, k, _ptr(y0), _ptr(nmat), f["np"] + 4, f["n_is_identity"], mode, _ptr(v), cols, _ptr(y),
                           _ptr(kap), _ptr(act, _I), _ptr(dk), B, _ptr(wl, _I) if wl is not None else None,
                           0 if wl is None else len(wl), int(use_filter), int(with_grad), warps, solves_per_warp,
-                          _ptr(fails, _I), _ptr(nfail, _I))
+                          _ptr(fails, _I), _ptr(nfail, _I), mt)
     assert rc == 0
     out = (y.astype(np.float64), kap.astype(np.float64), act, dk.astype(np.float64))
     if return_fails:
@@ -191,3 +191,23 @@ def test_solve_budget_hands_the_rest_to_the_fail_list(emu):
         assert np.array_equal(a[done], b_[done])
     assert np.isnan(y[fails]).all() and np.array_equal(kap[fails], kprior[fails].astype(np.float64))
     assert (act[fails] == tprior[fails]).all()
+
+
+def test_two_sample_chunks_give_the_same_bits_as_four(emu):
+    """Short work lists go through the filter two samples per warp instead of four (lmi_forward_warp_kernel: more warps
+    in flight on half the work each).  A sample's arithmetic does not depend on the chunk it falls into: kappa, tag, y and
+    d kappa/du are bit-identical."""
+    spec = synthetic.random_spec(k=9, r=24, seed=12)
+    cs = synthetic.build_constraints(spec)
+    p = plan.build_plan_from_constraints(cs)
+    B = 23
+    v, _ = synthetic.sample_inputs(B, cs.n, cs.k, seed_v=3, scale=6.0)
+    v = v.numpy()
+    lam, grad, gap, s, u = _lmi_truth(p, v)
+    rng = np.random.default_rng(1)
+    kprior = (np.maximum(lam, 0.0) * rng.choice([3.0, 1.0 + 1e-3, 1.0 - 1e-3, 0.3, 0.0], size=B)).astype(np.float32)
+    tprior = np.where(kprior > 0, (1 << 24) | 2, 0).astype(np.int32)
+    a = run_warp_path(emu, p, v, kprior, tprior, mt=4)
+    b = run_warp_path(emu, p, v, kprior, tprior, mt=2, warps=5)
+    for x, y_ in zip(a, b):
+        np.testing.assert_array_equal(x, y_)
