@@ -13,7 +13,8 @@ def test_packed_plan_reproduces_oracle(name):
     g = load_golden(name)
     cs = synthetic.build_constraints(g["spec"])
     p = plan.build_plan_from_constraints(cs)
-    y, kap, act = plan.evaluate_plan_numpy(p, g["v"])
+    ev = plan.evaluate_wide_numpy if p.fields["wide"] else plan.evaluate_plan_numpy
+    y, kap, act = ev(p, g["v"])
     cf = closed_form_numpy(OracleSet.from_constraints(cs), g["v"])
     scale = np.abs(cf["y"]).max()
     assert np.abs(y - cf["y"]).max() <= 2e-6 * scale      # float32 rounding of the constants only
