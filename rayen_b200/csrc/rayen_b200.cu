@@ -1420,8 +1420,11 @@ static int host_chunk_count(const rayen_plan* p, int64_t B) {
     // each other and the kernels with ONE chunk (gy goes in under the forward kernels, y comes out under the
     // backward kernel).  A second chunk pays only for sets without an LMI once each direction moves >= 8 MB; the
     // eigen-solver's latency-bound kernels take as long on half a batch as on a whole one.
+    // Round 2 (the LMI pass of a mixed set now takes ~33 us instead of ~60): two chunks also pay for sets with an LMI
+    // from 8 MB per direction on -- the copy-out of y_0 starts while chunk 1 is still in its forward kernels
+    // (cfg5 shard, 54 GB/s link: 0.397 -> 0.363 ms per step; four chunks: 0.444, the LMI pass has a fixed latency).
     const int64_t bytes = B * (p->dev.n + p->dev.k) * 4;
-    c = (p->dev.lmi_r == 0 && bytes >= (16ll << 20)) ? 2 : 1;
+    c = (bytes >= ((p->dev.lmi_r == 0) ? (16ll << 20) : (8ll << 20))) ? 2 : 1;
   }
   if (p->lmi_big) c = 1;  // the contraction buffer of lmi_big.cuh is sized for ONE call over the batch
   if (c > kHostMaxChunks) c = kHostMaxChunks;
