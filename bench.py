@@ -287,6 +287,18 @@ def module_step_fn(layer, bench):
     return fn
 
 
+def module_graph_steps(layer, bench):
+    """The same user-facing step (nn.Module forward + autograd backward, input gradient included) captured whole into one
+    CUDA graph per buffer set (rayen_b200.graphed.GraphedStep, loss = <y, g_y>): replay costs the kernels, not the eager
+    dispatch and the autograd engine."""
+    from rayen_b200.graphed import GraphedStep
+    steps = []
+    for s in bench.sets:
+        gy = s["gy"].view(bench.B, bench.k, 1)
+        steps.append(GraphedStep(layer, lambda y, t: (y * t).sum(), None, s["v"].unsqueeze(2), gy, input_grad=True, warmup=2))
+    return steps
+
+
 def e2e_step_fn(layer, bench, device):
     host = []
     for i in range(4):
@@ -438,6 +450,13 @@ def run_b200(args, rank, local_rank, world):
     # the same through nn.Module.forward + autograd backward (adds PyTorch's eager/autograd overhead per step)
     mod_fn = module_step_fn(layer, bench)
     ms_module = max_over_ranks(bench.time_loop_median(mod_fn, steps, warmup))
+    ms_module_graph = None
+    try:
+        gsteps = module_graph_steps(layer, bench)
+        ms_module_graph = max_over_ranks(bench.time_loop_median(lambda i: gsteps[i % POOL].graph.replay(), steps, warmup))
+        del gsteps
+    except Exception as exc:  # noqa: BLE001 - informational
+        print(f"bench.py: GraphedStep capture failed ({exc})", file=sys.stderr)
     # launch floor: a chain of as many empty kernels as one step launches
     per_step_launches = max(1, int(round(launches / max(steps, 1))))
     floor_ms = bench.time_loop_median(lambda i: lib.rayen_launch_empty(per_step_launches, bench.stream), 200, 20, groups=3)
@@ -591,6 +610,9 @@ def run_b200(args, rank, local_rank, world):
         "launch_floor_ms": floor_ms,
         "module_autograd": {"value": world * batch / (ms_module * 1e-3), "ms_per_step": ms_module,
                             "path": "nn.Module forward + autograd backward (PyTorch eager overhead included); median of 5 loops"},
+        "module_cuda_graph": ({"value": world * batch / (ms_module_graph * 1e-3), "ms_per_step": ms_module_graph,
+                               "path": "the same nn.Module forward + autograd backward captured whole into one CUDA graph "
+                                       "(rayen_b200.graphed.GraphedStep) and replayed"} if ms_module_graph else None),
         "direct_launch": {"value": world * batch / (direct_launch_ms * 1e-3), "ms_per_step": direct_launch_ms,
                           "path": "the same K steps issued call by call (cudaLaunchKernel per kernel, no graph): host-launch-rate bound on slow hosts"},
         "cuda_graph": ({"value": world * batch / (graph_ms * 1e-3), "ms_per_step": graph_ms,
