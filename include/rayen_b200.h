@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RAYEN_ABI_VERSION 14
+#define RAYEN_ABI_VERSION 15
 
 /* error codes (negative); positive return values are cudaError_t */
 #define RAYEN_OK 0
@@ -131,6 +131,8 @@ typedef struct RayenPlanDesc {
   int32_t lmi_big;      /* 1: the LMI is served by lmi_big.cuh (lmi_r > 32, or any lmi_r together with n > 32): section LMIB,
                            lmi_rp = 0 and the register-resident LMI sections (LMI, LMIW, LMITC, LMINEG, BOUND) are empty */
   int32_t lmib_p4;      /* words per packed lower triangle: lmi_r (lmi_r + 1) / 2 rounded up to 4 */
+  int32_t lmibt_panels; /* LMIBT: panels of 128 packed entries (0: no tensor-core operand, the FP32 GEMM is used) */
+  int32_t lmibt_slices; /* LMIBT: K slices of 32 subspace coordinates */
   float lmi_bound_margin; /* absolute float32-rounding allowance added to the pruning bound (see BOUND) */
   int64_t off_lin, off_quad, off_soc, off_nmat, off_y0, off_bound, off_lmi, off_tc, off_viol, off_lmineg, off_lmitc;
   int64_t off_wide;     /* WIDE section (0 when wide == 0) */
@@ -138,6 +140,9 @@ typedef struct RayenPlanDesc {
   int64_t off_lmib;     /* LMIB section: F~z_a, a < n, lower triangles row-major packed ((i, j), j <= i, at i (i + 1) / 2 + j),
                            lmib_p4 words each -- the B operand of the contraction GEMM S~(v) = V . F of lmi_big.cuh */
   int64_t off_lminegb;  /* LMINEGB section: -F_0 .. -F_k of the ambient space in the same packing (violation metric) */
+  int64_t off_lmibt;    /* LMIBT section (lmi_big_tc.cuh): F~z' as the B operand of the tcgen05 contraction GEMM -- per (panel of
+                           128 entries, slice of 32 coordinates) a TF32-split pair (hi, lo) of [128 x 32] tiles in the
+                           operand layout [k/4][row/8][row%8][k%4], 8192 words per pair, panel-major */
   int64_t blob_words;
   const float* blob; /* host pointer, blob_words floats */
 } RayenPlanDesc;

@@ -12,13 +12,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # RAYEN_B200_LIB points development scripts at an instrumented build of the same sources (scripts/lmi_trace.py)
 LIB_PATH = os.environ.get("RAYEN_B200_LIB") or os.path.join(CSRC, "librayen_b200.so")
-SOURCES = ["rayen_b200.cu", "lqs.cuh", "lqs_tc.cuh", "lmi.cuh", "lmi_tc.cuh", "lmi_warp.cuh", "lmi_big.cuh", "viol.cuh", "wide.cuh",
+SOURCES = ["rayen_b200.cu", "lqs.cuh", "lqs_tc.cuh", "lmi.cuh", "lmi_tc.cuh", "lmi_warp.cuh", "lmi_big.cuh", "lmi_big_tc.cuh", "viol.cuh", "wide.cuh",
            "common.cuh"]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "rayen_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 MODE_RAYEN, MODE_RAYEN_OLD = 0, 1
 FAM_NONE, FAM_LINEAR, FAM_QUAD, FAM_SOC, FAM_LMI = 0, 1, 2, 3, 4
 
@@ -27,10 +27,10 @@ class RayenPlanDesc(ctypes.Structure):
     _fields_ = [(name, ctypes.c_int32) for name in (
         "abi_version", "n", "k", "np", "k_pad", "m", "m_pad", "n_quad", "n_soc", "lmi_r", "lmi_rp",
         "n_is_identity", "lin_chunk_stride", "quad_stride", "soc_stride", "lmi_prune", "tc_panels", "tc_kp",
-        "viol_in", "viol_eq", "lmitc_panels", "wide", "lmi_big", "lmib_p4")] + [("lmi_bound_margin", ctypes.c_float)] + [
+        "viol_in", "viol_eq", "lmitc_panels", "wide", "lmi_big", "lmib_p4", "lmibt_panels", "lmibt_slices")] + [("lmi_bound_margin", ctypes.c_float)] + [
         (name, ctypes.c_int64) for name in (
             "off_lin", "off_quad", "off_soc", "off_nmat", "off_y0", "off_bound", "off_lmi", "off_tc", "off_viol",
-            "off_lmineg", "off_lmitc", "off_wide", "off_lmiw", "off_lmib", "off_lminegb", "blob_words")] + [
+            "off_lmineg", "off_lmitc", "off_wide", "off_lmiw", "off_lmib", "off_lminegb", "off_lmibt", "blob_words")] + [
         ("blob", ctypes.POINTER(ctypes.c_float))]
 
 

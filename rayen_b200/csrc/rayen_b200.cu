@@ -17,6 +17,7 @@
 #include "viol.cuh"
 #include "wide.cuh"
 #include "lmi_big.cuh"
+#include "lmi_big_tc.cuh"
 
 using namespace rayen;
 
@@ -44,6 +45,9 @@ struct rayen_plan {
   size_t lmib_smem_bytes;
   int lmib_ctas_per_sm;
   int64_t lmib_ws_cap;     // bytes of the contracted-matrix buffer a forward call may use (RAYEN_LMIB_WS_MB, default 512)
+  int64_t off_lmibt;       // LMIBT section: the contraction's tcgen05 B operand (0: FP32 GEMM only)
+  int lmibt_panels, lmibt_slices;
+  bool lmib_tc;            // contraction on the tensor cores (lmi_big_tc.cuh; RAYEN_LMIB_TC=0 keeps the FP32 GEMM)
   int off_lminegb;
   bool has_lqs;   // any non-zero linear row / quadratic / cone: otherwise the LQS forward kernel is skipped
   bool prune;     // LMI pruning enabled (needs has_lqs and a BOUND section)
@@ -284,6 +288,10 @@ static int lmib_validate(const RayenPlanDesc* d) {
       d->off_lmib + static_cast<int64_t>(d->n) * p4 > d->blob_words || d->off_lminegb <= 0 || d->off_lminegb % 4 ||
       d->off_lminegb + static_cast<int64_t>(d->k + 1) * p4 > d->blob_words)
     return fail(RAYEN_ERR_BAD_ARGUMENT, "LMIB / LMINEGB sections do not fit the block");
+  if (d->off_lmibt != 0 &&
+      (d->off_lmibt < 0 || d->off_lmibt % 4 || d->lmibt_panels != (p4 + 127) / 128 || d->lmibt_slices != (d->n + 31) / 32 ||
+       d->off_lmibt + static_cast<int64_t>(d->lmibt_panels) * d->lmibt_slices * 2 * kLbtTile > d->blob_words))
+    return fail(RAYEN_ERR_BAD_ARGUMENT, "LMIBT section does not fit the block");
   return 0;
 }
 // device must be current; p->sm_count / max_smem_optin / d_blob set
@@ -295,6 +303,12 @@ static int lmib_setup(rayen_plan* p, const RayenPlanDesc* d) {
   b.off_lmib = static_cast<int>(d->off_lmib);
   b.off_y0 = static_cast<int>(d->off_y0);
   p->off_lminegb = static_cast<int>(d->off_lminegb);
+  p->off_lmibt = d->off_lmibt;
+  p->lmibt_panels = d->lmibt_panels;
+  p->lmibt_slices = d->lmibt_slices;
+  p->lmib_tc = d->off_lmibt > 0 && d->lmibt_panels > 0 && d->lmibt_slices > 0 &&
+               lmib_tc_smem_bytes() <= static_cast<size_t>(p->max_smem_optin) &&
+               !(getenv("RAYEN_LMIB_TC") && atoi(getenv("RAYEN_LMIB_TC")) == 0);
   p->lmib_threads = b.r <= 64 ? 64 : (b.r <= 128 ? 128 : (b.r <= 256 ? 256 : 320));
   p->lmib_smem_bytes = lmib_smem_bytes(b.r);
   if (p->lmib_smem_bytes > static_cast<size_t>(p->max_smem_optin))
@@ -314,6 +328,7 @@ static int lmib_setup(rayen_plan* p, const RayenPlanDesc* d) {
   int rc = 0;
   for (int t : {64, 128, 256, 320})
     if (rc == 0) rc = allow_smem(reinterpret_cast<const void*>(lmib_solve_fn(t)), p->max_smem_optin);
+  if (rc == 0 && p->lmib_tc) rc = allow_smem(reinterpret_cast<const void*>(lmib_contract_tc_kernel), lmib_tc_smem_bytes());
   return rc;
 }
 // samples per chunk of the contraction buffer for a call of B samples (p4 words each)
@@ -348,8 +363,15 @@ static cudaError_t lmib_run(const rayen_plan* p, const float* F, int nv, const f
   for (int64_t c0 = 0; c0 < B; c0 += rows) {
     const int64_t bc = (B - c0 < rows) ? B - c0 : rows;
     const int64_t tiles_m = (bc + kLbTileM - 1) / kLbTileM;
-    lmib_contract_kernel<<<static_cast<unsigned>(tiles_n * tiles_m), kLbGemmThreads, 0, stream>>>(
-        V + c0 * ldv, ldv, F, nv, b.p4, S, bc, C0);
+    if (p->lmib_tc && C0 == nullptr && F == p->d_blob + p->bdev.off_lmib) {
+      // tensor-core contraction: ceil(bc / 128) x ceil(panels / 4) CTAs
+      const int64_t groups = (p->lmibt_panels + kLbtPanelsPerCta - 1) / kLbtPanelsPerCta;
+      lmib_contract_tc_kernel<<<static_cast<unsigned>(tiles_m * groups), kLbtThreads, lmib_tc_smem_bytes(), stream>>>(
+          V + c0 * ldv, ldv, p->d_blob + p->off_lmibt, nv, b.p4, p->lmibt_panels, p->lmibt_slices, S, bc);
+    } else {
+      lmib_contract_kernel<<<static_cast<unsigned>(tiles_n * tiles_m), kLbGemmThreads, 0, stream>>>(
+          V + c0 * ldv, ldv, F, nv, b.p4, S, bc, C0);
+    }
     g_launches.fetch_add(1);
     sf<<<static_cast<unsigned>(lmib_solve_grid(p, bc)), p->lmib_threads, p->lmib_smem_bytes, stream>>>(
         b, S, V + c0 * ldv, ldv, y ? y + c0 * b.k : nullptr, kappa + c0, active ? active + c0 : nullptr,

@@ -19,11 +19,12 @@ import ctypes
 
 import numpy as np
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 MAX_NP = 32      # widest subspace of the register-resident kernels; beyond it the WIDE section / wide.cuh take over
 MAX_WIDE_N = 12288   # wide.cuh kWideMaxN
 MAX_LMI = 32          # largest LMI of the register-resident kernels (lmi.cuh / lmi_warp.cuh)
 MAX_LMI_BIG = 320     # largest LMI of the one-CTA-per-matrix path (lmi_big.cuh kLbMaxR)
+LMIBT_MIN_N = 64      # from this subspace dimension on the big-LMI contraction also gets its tensor-core operand (LMIBT)
 
 
 class PlanError(RuntimeError):
@@ -458,6 +459,23 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
         Fnb = np.zeros((k + 1, lmib_p4))
         Fnb[:, :il[0].size] = Fn[:, il[0], il[1]]
         off_lminegb = add(Fnb)
+    # ---- LMIBT (lmi_big_tc.cuh): the same F~z as the B operand of the tcgen05 contraction GEMM, for subspaces wide enough
+    # for the GEMM to matter (n >= 64): F' [lmib_p4 -> panels of 128 entries][n -> slices of 32], every [128 x 32] tile
+    # TF32-split (hi, lo) and stored in the K-major no-swizzle operand layout [k/4][row/8][row%8][k%4];
+    # tile pair (panel q, slice s) at off_lmibt + (q * slices + s) * 8192 words
+    off_lmibt = 0
+    lmibt_panels = lmibt_slices = 0
+    if lmi_big and n >= LMIBT_MIN_N:
+        lmibt_panels = -(-lmib_p4 // 128)
+        lmibt_slices = -(-n // 32)
+        Ft32 = np.zeros((lmibt_panels * 128, lmibt_slices * 32), dtype=np.float32)
+        Ft32[:lmib_p4, :n] = Fb.T.astype(np.float32)
+        hi, lo = split_tf32(Ft32)
+
+        def tiles(a):    # [q*128 + rg*8 + r8][s*32 + kc*4 + k4] -> [q][s][kc][rg][r8][k4]
+            return a.reshape(lmibt_panels, 16, 8, lmibt_slices, 8, 4).transpose(0, 3, 4, 1, 2, 5)
+        both = np.stack((tiles(hi), tiles(lo)), axis=2)      # [q][s][hi/lo][kc][rg][r8][k4]
+        off_lmibt = add_f32(np.ascontiguousarray(both).reshape(-1))
 
     # ---- WIDE section (n > 32, wide.cuh): every constraint as rows of ONE matrix W [R_pad x n], stored transposed
     # (Wt[j][row]) so that a warp's 32 lanes read 32 consecutive rows of a column with one coalesced load.  The unit
@@ -546,7 +564,8 @@ def build_plan(A_p, b_p, NA_E, yp, z0, qcs=(), socs=(), lmi=None, lin_rows=None)
     plan.blob = np.ascontiguousarray(blob)
     plan.fields = dict(n=n, k=k, np=np_, k_pad=k_pad, m=m, m_pad=m_pad, n_quad=len(qcs), n_soc=len(socs),
                        lmi_r=lmi_r, lmi_rp=lmi_rp, n_is_identity=n_is_identity, lmi_big=int(lmi_big), lmib_p4=lmib_p4,
-                       off_lmib=off_lmib, off_lminegb=off_lminegb,
+                       off_lmib=off_lmib, off_lminegb=off_lminegb, off_lmibt=off_lmibt, lmibt_panels=lmibt_panels,
+                       lmibt_slices=lmibt_slices,
                        lin_chunk_stride=lin_stride, quad_stride=quad_stride, soc_stride=soc_stride,
                        off_lin=off_lin, off_quad=off_quad, off_soc=off_soc, off_nmat=off_nmat,
                        off_y0=off_y0, off_bound=off_bound, off_lmi=off_lmi, lmi_prune=int(lmi is not None and not lmi_big),

@@ -991,3 +991,33 @@ def test_peer_memory_all_gather_matches_nccl_on_two_gpus():
     line = [l for l in proc.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
     assert res["ok_all_ranks"] and res["checks_this_rank"]["p2p"]
+
+
+def test_big_lmi_tensor_core_contraction_agrees_with_the_fp32_gemm():
+    """lmi_big_tc.cuh (tcgen05 3xTF32 K-loop GEMM, plan section LMIBT, n >= 64) against lmib_contract_kernel (FP32 pipe) on
+    the same set: kappa, y and g_v agree to float32 rounding, the binding families are the same, both match the oracle.
+    Shapes: K not a multiple of 32, entries not a multiple of 128 or of 512 (partial panel groups), batch not a multiple
+    of 128."""
+    import os
+    for (k, r, eq, B) in ((100, 50, 2, 700), (200, 33, 0, 300), (70, 12, 0, 1000)):
+        spec = synthetic.wide_spec(k, 40, 1, 1, 10, eq, seed=k + r, r=r)
+        cs = synthetic.build_constraints(spec)
+        v, gy = synthetic.sample_inputs(B, cs.n, cs.k, seed_v=r)
+        layer_tc, y_tc, gv_tc = run_layer(cs, v, gy)
+        assert layer_tc._packed.fields["lmibt_panels"] > 0
+        os.environ["RAYEN_LMIB_TC"] = "0"
+        try:
+            layer_fp, y_fp, gv_fp = run_layer(cs, v, gy)
+        finally:
+            del os.environ["RAYEN_LMIB_TC"]
+        k_tc, a_tc = layer_tc.last_kappa_and_active()
+        k_fp, a_fp = layer_fp.last_kappa_and_active()
+        assert float((k_tc - k_fp).abs().max()) <= 2e-6 * float(k_fp.abs().max())
+        assert rel(y_tc, y_fp) <= 2e-6
+        oset = OracleSet.from_constraints(cs)
+        cf = closed_form_numpy(oset, v.numpy(), gy.numpy())
+        ok = (cf["margin"] > 1e-4) & (cf["lmi_gap"] > 1e-3) & (cf["cone_cond"] > 0.05)
+        assert ((a_tc.cpu().numpy() >> 24)[ok] == (a_fp.cpu().numpy() >> 24)[ok]).all()
+        assert ((a_tc.cpu().numpy() >> 24) == _cabi.FAM_LMI).sum() > 0.05 * B
+        assert rel(gv_tc, gv_fp, ok) <= 4 * TOL_GRAD
+        assert rel(y_tc, cf["y"]) <= TOL
