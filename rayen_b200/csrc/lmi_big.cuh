@@ -15,6 +15,8 @@
 //        a. Wolkowicz-Styan bound straight from the packed entries, in the cancellation-free centred form
 //           (mean + sqrt((r-1)/r (sum_i (S_ii - mean)^2 + 2 sum_{i>j} S_ij^2))): below the prior kappa => the LMI cannot
 //           bind, the sample is finished (nothing is written).
+//        a'. exact definiteness filter: LDL' of (kprior - margin) I - S~(u) on the packed triangle; all pivots positive
+//           => the LMI cannot bind, the sample is finished after r^3/6 FMAs (a failure falls through to the solve);
 //        b. the packed lower triangle (row i at word i (i + 1) / 2) is copied to shared memory as it is, scaled by
 //           1 / |v|: r (r + 1) / 2 words, 205 KB at r = 320.  Thread i owns row i.  Entry (i, j), j <= i, of 32
 //           consecutive rows falls into 32 different banks (triangular numbers are a complete residue system modulo a
@@ -255,6 +257,7 @@ __global__ void __launch_bounds__(THREADS)
     __syncthreads();
     // ---- a. pruning bound (diagonal entry of row i at tri(i) + i): lambda_max <= mean + sqrt((r-1)/r dev2), dev2 the
     //         squared Frobenius norm of the trace-free part as a sum of squares
+    float fro;
     {
       const float tr = (tid < r) ? A[ti + tid] : 0.f;
       const float mean = lb_block_sum<THREADS>(tr, red) / static_cast<float>(r);
@@ -268,12 +271,64 @@ __global__ void __launch_bounds__(THREADS)
         dev = fmaf(x, x, dev);
       }
       const float dev2 = lb_block_sum<THREADS>(dev, red);
+      fro = sqrtf(fmaf(static_cast<float>(r) * mean, mean, dev2));
       if (!grad_only) {
         // allowance for the float32 sums: 2e-6 of the scale involved
         const float rad = sqrtf(dev2 * (static_cast<float>(r - 1) / static_cast<float>(r)));
         const float ub = (mean + rad) + 2e-6f * (fabsf(mean) + rad);
         if (ub <= kprior) continue;  // uniform per CTA: the LMI cannot bind (kprior = 0: lambda_max <= 0, kappa_LMI = 0)
       }
+    }
+
+    // ---- a'. exact definiteness filter (the idea of lmi_warp.cuh at this size): LDL' of M = tau I - S~(u) on the packed
+    //          triangle, tau = kprior - margin (kprior + |S~|_F).  All pivots positive <=> M positive definite <=>
+    //          lambda_max(S~) < tau: the LMI cannot bind and the sample is finished -- r^3/6 FMAs and two barriers per step
+    //          against ~r^3/2 FMAs, two block reductions and four barriers per Householder step, no multisection.  The
+    //          float32 factorisation is the exact one of M + E, |E| <= c r eps |M|: margin = 3.2e-7 r (1e-5 at r = 32 as
+    //          in lmi_warp.cuh, 1e-4 at r = 320) keeps ~5x headroom over that, so a pass is a proof; a failure proves
+    //          nothing: the matrix is loaded again and solved.
+    if (!grad_only && !lambda_out && kprior > 0.f) {
+      const float tau = kprior - 3.2e-7f * static_cast<float>(r) * (kprior + fro);
+      for (int e = tid; e < p4; e += THREADS) A[e] = -A[e];
+      __syncthreads();
+      if (tid < r) A[ti + tid] += tau;
+      __syncthreads();
+      bool pass = true;
+      for (int kk = 0; kk < r; ++kk) {
+        const float d = A[lmib_tri(kk) + kk];   // the same word for every thread
+        if (!(d > 0.f)) {                       // uniform (NaN fails)
+          pass = false;
+          break;
+        }
+        if (kk == r - 1) break;
+        const bool mine = tid > kk && tid < r;
+        if (mine) vv[tid] = A[ti + kk];
+        __syncthreads();
+        if (mine) {
+          const float l = vv[tid] * (1.0f / d);
+          float* ar = A + ti;
+          int j = kk + 1;
+          for (; (j & 3) && j <= tid; ++j) ar[j] = fmaf(-l, vv[j], ar[j]);
+          for (; j + 4 <= tid + 1; j += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(vv + j);
+            ar[j] = fmaf(-l, v4.x, ar[j]);
+            ar[j + 1] = fmaf(-l, v4.y, ar[j + 1]);
+            ar[j + 2] = fmaf(-l, v4.z, ar[j + 2]);
+            ar[j + 3] = fmaf(-l, v4.w, ar[j + 3]);
+          }
+          for (; j <= tid; ++j) ar[j] = fmaf(-l, vv[j], ar[j]);
+        }
+        __syncthreads();
+      }
+      if (pass) continue;  // uniform per CTA
+      // the factorisation destroyed the matrix: load it again
+      __syncthreads();
+      for (int e = tid; e < p4 / 4; e += THREADS) {
+        float4 x = *reinterpret_cast<const float4*>(srow + 4 * e);
+        x.x *= inv; x.y *= inv; x.z *= inv; x.w *= inv;
+        *reinterpret_cast<float4*>(A + 4 * e) = x;
+      }
+      __syncthreads();
     }
 
     // ---- c. Householder tridiagonalisation (lower form): thread i owns row i

@@ -168,3 +168,45 @@ def test_big_lmi_violation_mode(emu):
     ref = np.maximum(-np.linalg.eigvalsh(Fy)[:, 0], 0.0)
     assert viol[0] == 0.0 and (ref > 0).any()
     assert np.abs(viol - ref).max() <= 1e-5 * max(1.0, ref.max())
+
+
+def test_big_lmi_definiteness_filter_is_exact(emu):
+    """Priors placed around lambda_max (relative offsets 1e-2 ... 2e-5 on both sides): behind the Wolkowicz-Styan bound the
+    LDL' filter may finish a sample only if lambda_max < prior in float64; whatever it decides, the outcome is the exact
+    merge max(lambda_max, prior) with the right tag (a wrong pass would leave kappa = prior < lambda_max)."""
+    spec = synthetic.random_spec(k=5, r=36, seed=21)
+    cs = synthetic.build_constraints(spec)
+    p = plan.build_plan_from_constraints(cs)
+    f = p.fields
+    n, k, r, p4 = f["n"], f["k"], f["lmi_r"], f["lmib_p4"]
+    B = 28
+    v, _ = synthetic.sample_inputs(B, cs.n, cs.k, seed_v=5, scale=4.0)
+    v = np.ascontiguousarray(v.numpy(), dtype=np.float32)
+    s = np.linalg.norm(v.astype(np.float64), axis=1)
+    u = v.astype(np.float64) / s[:, None]
+    lam = np.linalg.eigvalsh(np.einsum("ba,aij->bij", u, p.f64["Fz"]))[:, -1]
+    keep = lam > 0
+    rng = np.random.default_rng(2)
+    rel = rng.choice([1e-2, 1e-3, 2e-4, 2e-5, -2e-5, -2e-4, -1e-3, -1e-2], size=B)
+    kprior = np.where(keep, lam * (1.0 + rel), 0.5).astype(np.float32)
+    kap = kprior.copy()
+    act = np.full(B, (1 << 24) | 3, dtype=np.int32)
+    a_old = np.minimum(1.0 / kprior.astype(np.float64), s)
+    rho = u @ cs.NA_E.T
+    y = (cs.y0[:, 0][None] + a_old[:, None] * rho).astype(np.float32)
+    Fp = np.ascontiguousarray(p.blob[f["off_lmib"]:f["off_lmib"] + n * p4])
+    S = np.full((B, p4), np.nan, dtype=np.float32)
+    assert emu.emu_lmib_contract(_ptr(v), n, _ptr(Fp), n, p4, _ptr(S), B, None) == 0
+    dk = np.full((B, n), np.nan, dtype=np.float32)
+    rc = emu.emu_lmib_solve(_ptr(p.blob), n, k, r, p4, f["off_lmib"], f["off_y0"], _ptr(S), _ptr(v), n, _ptr(y), _ptr(kap),
+                            _ptr(act, _I), _ptr(dk), B, 0, 1, 64, 3)
+    assert rc == 0
+    want = np.maximum(np.maximum(lam, 0.0), kprior.astype(np.float64))
+    assert np.abs(kap - want).max() <= 3e-6 * want.max()
+    clear = np.abs(rel) > 1e-4
+    binds = np.maximum(lam, 0.0) > kprior
+    assert np.array_equal((act >> 24)[clear & keep], np.where(binds, 4, 1)[clear & keep])
+    assert (binds & clear).any() and (~binds & clear).any()
+    a_new = np.minimum(1.0 / want, s)
+    y_want = cs.y0[:, 0][None] + a_new[:, None] * rho
+    assert np.abs(y - y_want).max() <= 5e-6 * np.abs(y_want).max()
