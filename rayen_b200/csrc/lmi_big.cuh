@@ -203,9 +203,10 @@ __device__ __forceinline__ float lb_alpha(float kap, float s, float beta, int mo
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
-    lmib_solve_kernel(const LmiBigDev P, const float* __restrict__ S, const float* __restrict__ v, long long ldv,
+    lmib_solve_kernel(const LmiBigDev P, const float* S, const float* __restrict__ v, long long ldv,
                       float* __restrict__ y, float* __restrict__ kappa_io, int* __restrict__ active_io,
-                      float* __restrict__ dkappa, long long Bc, int mode, int flags) {
+                      float* __restrict__ dkappa, long long Bc, int mode, int flags, float* Sw,  // (Sw may be S itself)
+                      int* __restrict__ grad_list, int* __restrict__ grad_count) {
   extern __shared__ __align__(16) float lmib_smem[];
   const int r = P.r, r4 = (r + 3) / 4 * 4, n = P.n, k = P.k, p4 = P.p4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -577,23 +578,95 @@ __global__ void __launch_bounds__(THREADS)
       }
       for (int e = r * (r + 1) / 2 + tid; e < p4; e += THREADS) wts[e] = 0.f;
       __syncthreads();
-      // d kappa / du_a = <F_a, w>: one warp per a, coalesced 16-byte loads of the packed row
-      const float* F = P.blob + P.off_lmib;
-      for (int a = warp; a < n; a += THREADS / 32) {
-        const float4* fr = reinterpret_cast<const float4*>(F + static_cast<size_t>(a) * p4);
+      if (grad_list != nullptr) {
+        // d kappa / du_a = <F_a, w> for all a is a row of the GEMM  W [samples x P] . F' [P x n]: leave w in this sample's
+        // (now dead) row of the contraction buffer and the sample's number on a list; lmib_grad_gemm_kernel does the rest
+        // for all LMI-bound samples of the chunk at once (streaming F once per 64 samples instead of once per sample)
+        float4* dst = reinterpret_cast<float4*>(Sw + static_cast<size_t>(b) * p4);
         const float4* w4 = reinterpret_cast<const float4*>(wts);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        for (int e = lane; e < p4 / 4; e += 32) {
-          const float4 f = __ldg(fr + e);
-          const float4 w = w4[e];
-          a0 = fmaf(f.x, w.x, a0);
-          a1 = fmaf(f.y, w.y, a1);
-          a2 = fmaf(f.z, w.z, a2);
-          a3 = fmaf(f.w, w.w, a3);
+        for (int e = tid; e < p4 / 4; e += THREADS) dst[e] = w4[e];
+        if (tid == 0) grad_list[atomicAdd(grad_count, 1)] = static_cast<int>(b);
+      } else {
+        // d kappa / du_a = <F_a, w>: one warp per a, coalesced 16-byte loads of the packed row
+        const float* F = P.blob + P.off_lmib;
+        for (int a = warp; a < n; a += THREADS / 32) {
+          const float4* fr = reinterpret_cast<const float4*>(F + static_cast<size_t>(a) * p4);
+          const float4* w4 = reinterpret_cast<const float4*>(wts);
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          for (int e = lane; e < p4 / 4; e += 32) {
+            const float4 f = __ldg(fr + e);
+            const float4 w = w4[e];
+            a0 = fmaf(f.x, w.x, a0);
+            a1 = fmaf(f.y, w.y, a1);
+            a2 = fmaf(f.z, w.z, a2);
+            a3 = fmaf(f.w, w.w, a3);
+          }
+          const float g = lb_warp_sum((a0 + a1) + (a2 + a3));
+          if (lane == 0) dkappa[b * n + a] = g;
         }
-        const float g = lb_warp_sum((a0 + a1) + (a2 + a3));
-        if (lane == 0) dkappa[b * n + a] = g;
       }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- 3. gradient GEMM (NT)
+// dkappa[list[m]][a] = sum_e Sw[list[m]][e] F[a][e]   (m < *count, a < n, e < p4): the rows the solve kernel left behind
+// (w_e = (2 - [i = j]) q_i q_j) against the packed matrices -- both operands K-contiguous.  64 x 64 x 16 tiles, 4 x 4
+// outputs per thread; the grid covers the whole chunk, CTAs beyond the list length leave at once.
+constexpr int kLbGradTile = 64, kLbGradK = 16, kLbGradThreads = 256;
+__global__ void __launch_bounds__(kLbGradThreads)
+    lmib_grad_gemm_kernel(const float* __restrict__ Sw, const int* __restrict__ list, const int* __restrict__ count,
+                          const float* __restrict__ F, int n, int p4, float* __restrict__ dkappa) {
+  LB_STATIC_SHARED __align__(16) float As[kLbGradK][kLbGradTile + 4];
+  LB_STATIC_SHARED __align__(16) float Bs[kLbGradK][kLbGradTile + 4];
+  LB_STATIC_SHARED int rows[kLbGradTile];
+  const int tid = threadIdx.x;
+  const int tiles_n = (n + kLbGradTile - 1) / kLbGradTile;
+  const int m0 = static_cast<int>(blockIdx.x / tiles_n) * kLbGradTile;
+  const int n0 = static_cast<int>(blockIdx.x % tiles_n) * kLbGradTile;
+  const int total = *count;
+  if (m0 >= total) return;  // uniform
+  if (tid < kLbGradTile) rows[tid] = (m0 + tid < total) ? list[m0 + tid] : -1;
+  __syncthreads();
+  const int lr = tid >> 2, lk = (tid & 3) * 4;   // loader: row lr of the tile, k = lk .. lk + 3
+  const int arow = rows[lr];
+  const float* ap = (arow >= 0) ? Sw + static_cast<size_t>(arow) * p4 : nullptr;
+  const float* bp = (n0 + lr < n) ? F + static_cast<size_t>(n0 + lr) * p4 : nullptr;
+  const int ty = tid >> 4, tx = tid & 15;        // outputs: rows ty * 4 .., columns tx * 4 ..
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < p4; k0 += kLbGradK) {
+    float4 a4 = float4{0.f, 0.f, 0.f, 0.f}, b4 = float4{0.f, 0.f, 0.f, 0.f};
+    if (k0 + lk < p4) {   // p4 is a multiple of 4: a 4-group is in or out as a whole
+      if (ap) a4 = *reinterpret_cast<const float4*>(ap + k0 + lk);
+      if (bp) b4 = __ldg(reinterpret_cast<const float4*>(bp + k0 + lk));
+    }
+    __syncthreads();  // the previous tile's readers are done
+    As[lk + 0][lr] = a4.x; As[lk + 1][lr] = a4.y; As[lk + 2][lr] = a4.z; As[lk + 3][lr] = a4.w;
+    Bs[lk + 0][lr] = b4.x; Bs[lk + 1][lr] = b4.y; Bs[lk + 2][lr] = b4.z; Bs[lk + 3][lr] = b4.w;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kLbGradK; ++kk) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r_ = rows[ty * 4 + i];
+    if (r_ < 0) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = n0 + tx * 4 + j;
+      if (a < n) dkappa[static_cast<size_t>(r_) * n + a] = acc[i][j];
     }
   }
 }

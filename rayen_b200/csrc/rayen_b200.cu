@@ -270,7 +270,7 @@ static int create_wide_plan(const RayenPlanDesc* d, int device, rayen_plan_t** o
 
 // ----------------------------------------------------------------------------- big LMI (lmi_big.cuh)
 typedef void (*LmibSolveFn)(const LmiBigDev, const float*, const float*, long long, float*, float*, int*, float*,
-                            long long, int, int);
+                            long long, int, int, float*, int*, int*);
 static LmibSolveFn lmib_solve_fn(int threads) {
   switch (threads) {
     case 64: return lmib_solve_kernel<64>;
@@ -351,7 +351,7 @@ static int64_t lmib_ws_extra(const rayen_plan* p, int64_t B, int p4) {
 // LMINEGB with V = y and its constant row as C0); buf: the contraction buffer.
 static cudaError_t lmib_run(const rayen_plan* p, const float* F, int nv, const float* V, int64_t ldv, float* y, float* kappa,
                             int32_t* active, float* dkappa, void* buf, int64_t B, int mode, int flags, cudaStream_t stream,
-                            const float* C0 = nullptr) {
+                            const float* C0 = nullptr, int* grad_list = nullptr, int* grad_count = nullptr) {
   LmiBigDev b = p->bdev;
   b.n = nv;
   b.off_lmib = static_cast<int>(F - p->d_blob);
@@ -373,10 +373,24 @@ static cudaError_t lmib_run(const rayen_plan* p, const float* F, int nv, const f
           V + c0 * ldv, ldv, F, nv, b.p4, S, bc, C0);
     }
     g_launches.fetch_add(1);
+    // with gradients: the LMI-bound samples leave their weight rows in S and their numbers on a list; one GEMM over the
+    // list turns them into d kappa/du (lmib_grad_gemm_kernel)
+    const bool gemm_grad = dkappa != nullptr && grad_list != nullptr && (flags & (kLbFlagGrad | kLbFlagGradOnly));
+    if (gemm_grad) {
+      cudaError_t me = cudaMemsetAsync(grad_count, 0, sizeof(int), stream);
+      if (me != cudaSuccess) return me;
+    }
     sf<<<static_cast<unsigned>(lmib_solve_grid(p, bc)), p->lmib_threads, p->lmib_smem_bytes, stream>>>(
         b, S, V + c0 * ldv, ldv, y ? y + c0 * b.k : nullptr, kappa + c0, active ? active + c0 : nullptr,
-        dkappa ? dkappa + c0 * nv : nullptr, bc, mode, flags);
+        dkappa ? dkappa + c0 * nv : nullptr, bc, mode, flags, S, gemm_grad ? grad_list : nullptr,
+        gemm_grad ? grad_count : nullptr);
     g_launches.fetch_add(1);
+    if (gemm_grad) {
+      const int64_t gt_n = (nv + kLbGradTile - 1) / kLbGradTile, gt_m = (bc + kLbGradTile - 1) / kLbGradTile;
+      lmib_grad_gemm_kernel<<<static_cast<unsigned>(gt_n * gt_m), kLbGradThreads, 0, stream>>>(
+          S, grad_list, grad_count, F, nv, b.p4, dkappa + c0 * nv);
+      g_launches.fetch_add(1);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -1046,7 +1060,8 @@ static int forward_impl(const rayen_plan_t* p, const float* v, int64_t ldv, floa
   auto run_lmi_big = [&]() -> cudaError_t {
     return lmib_run(p, p->d_blob + p->bdev.off_lmib, d.n, v, ldv, y, kappa, active,
                     want_grad ? ws_dkappa(workspace, B) : nullptr, static_cast<char*>(workspace) + ws_prefix_bytes(B, d.n), B,
-                    mode, want_grad ? kLbFlagGrad : 0, stream);
+                    mode, want_grad ? kLbFlagGrad : 0, stream, nullptr,
+                    reinterpret_cast<int*>(static_cast<char*>(workspace) + 256), static_cast<int*>(workspace) + 8);
   };
 
   if (p->wide) {
@@ -1230,7 +1245,8 @@ extern "C" int rayen_backward_stage_f32(const rayen_plan_t* p, const float* v, i
   if (p->lmi_big && !have_dkappa && (stage_mask & 1)) {
     cudaError_t ge = lmib_run(p, p->d_blob + p->bdev.off_lmib, d.n, v, ldv, nullptr, const_cast<float*>(kappa),
                               const_cast<int32_t*>(active), ws_dkappa(workspace, B),
-                              static_cast<char*>(workspace) + ws_prefix_bytes(B, d.n), B, mode, kLbFlagGradOnly, stream);
+                              static_cast<char*>(workspace) + ws_prefix_bytes(B, d.n), B, mode, kLbFlagGradOnly, stream, nullptr,
+                              reinterpret_cast<int*>(static_cast<char*>(workspace) + 256), static_cast<int*>(workspace) + 8);
     if (ge != cudaSuccess) {
       if (prev != p->device) cudaSetDevice(prev);
       return cuda_fail(ge, "backward launch (big LMI gradient)");

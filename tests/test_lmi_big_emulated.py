@@ -31,7 +31,9 @@ def emu(tmp_path_factory):
     lib.emu_lmib_contract.argtypes = [_F, _LL, _F, ctypes.c_int, ctypes.c_int, _F, _LL, _F]
     lib.emu_lmib_solve.restype = ctypes.c_int
     lib.emu_lmib_solve.argtypes = [_F, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F,
-                                   _F, _LL, _F, _F, _I, _F, _LL, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+                                   _F, _LL, _F, _F, _I, _F, _LL, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F, _I, _I]
+    lib.emu_lmib_grad_gemm.restype = ctypes.c_int
+    lib.emu_lmib_grad_gemm.argtypes = [_F, _I, _I, _F, ctypes.c_int, ctypes.c_int, _F, _LL]
     return lib
 
 
@@ -54,7 +56,7 @@ def _prior(cs, p, v, mode):
     return y.astype(np.float32), kap.astype(np.float32), act.astype(np.int32)
 
 
-def run_emulated(lib, cs, p, v, mode=0, threads=64, grid=3, flags=1):
+def run_emulated(lib, cs, p, v, mode=0, threads=64, grid=3, flags=1, gemm_grad=False):
     f = p.fields
     n, k, r, p4 = f["n"], f["k"], f["lmi_r"], f["lmib_p4"]
     v = np.ascontiguousarray(v, dtype=np.float32)
@@ -65,9 +67,16 @@ def run_emulated(lib, cs, p, v, mode=0, threads=64, grid=3, flags=1):
     Fp = np.ascontiguousarray(blob[f["off_lmib"]:f["off_lmib"] + n * p4])
     assert lib.emu_lmib_contract(_ptr(v), cols, _ptr(Fp), n, p4, _ptr(S), B, None) == 0
     dk = np.full((B, n), np.nan, dtype=np.float32)
+    glist = np.full((B,), -1, dtype=np.int32)
+    gcount = np.zeros((1,), dtype=np.int32)
     rc = lib.emu_lmib_solve(_ptr(blob), n, k, r, p4, f["off_lmib"], f["off_y0"], _ptr(S), _ptr(v), cols, _ptr(y), _ptr(kap),
-                            _ptr(act, _I), _ptr(dk), B, mode, flags, threads, grid)
+                            _ptr(act, _I), _ptr(dk), B, mode, flags, threads, grid, _ptr(S) if gemm_grad else None,
+                            _ptr(glist, _I) if gemm_grad else None, _ptr(gcount, _I) if gemm_grad else None)
     assert rc == 0
+    if gemm_grad:
+        # the LMI-bound samples left their weight rows in S and their numbers on the list: one GEMM over the list
+        assert lib.emu_lmib_grad_gemm(_ptr(S), _ptr(glist, _I), _ptr(gcount, _I), _ptr(Fp), n, p4, _ptr(dk), B) == 0
+        assert sorted(glist[:gcount[0]].tolist()) == sorted(np.nonzero(~np.isnan(dk).any(axis=1))[0].tolist())
     return y.astype(np.float64), kap, act, dk, S
 
 
@@ -93,6 +102,12 @@ def test_big_lmi_kernels_match_the_oracle(emu, case):
     v = v.numpy()
     v[1] *= 1e-3                                   # an interior sample
     y, kap, act, dk, S = run_emulated(emu, cs, p, v, threads=threads)
+    # the gradient through the list GEMM (lmib_grad_gemm_kernel) instead of the per-sample walk: same rows, same values
+    y2, kap2, act2, dk2, _ = run_emulated(emu, cs, p, v, threads=threads, gemm_grad=True)
+    np.testing.assert_array_equal(kap2, kap)
+    np.testing.assert_array_equal(y2, y)
+    assert np.array_equal(np.isnan(dk2), np.isnan(dk))
+    assert np.nanmax(np.abs(dk2 - dk)) <= 2e-6 * np.nanmax(np.abs(dk))
     oset = OracleSet.from_constraints(cs)
     cf = closed_form_numpy(oset, v, gy.numpy())
     assert np.abs(y - cf["y"]).max() <= 1e-5 * max(1.0, np.abs(cf["y"]).max())
@@ -135,7 +150,7 @@ def test_big_lmi_rayen_old_and_gradient_only_mode(emu):
     y2, kap2, act2 = y.astype(np.float32), kap.copy(), act.copy()
     dk2 = np.full_like(dk, np.nan)
     rc = emu.emu_lmib_solve(_ptr(p.blob), n, k, r, p4, f["off_lmib"], f["off_y0"], _ptr(S), _ptr(v32), v32.shape[1], _ptr(y2),
-                            _ptr(kap2), _ptr(act2, _I), _ptr(dk2), v32.shape[0], 1, 2, 64, 2)
+                            _ptr(kap2), _ptr(act2, _I), _ptr(dk2), v32.shape[0], 1, 2, 64, 2, None, None, None)
     assert rc == 0
     np.testing.assert_array_equal(kap2, kap)
     np.testing.assert_array_equal(act2, act)
@@ -161,7 +176,7 @@ def test_big_lmi_violation_mode(emu):
     assert emu.emu_lmib_contract(_ptr(y), k, _ptr(Fn), k, p4, _ptr(S), 9, _ptr(c0)) == 0
     viol = np.zeros(9, dtype=np.float32)
     rc = emu.emu_lmib_solve(_ptr(p.blob), k, k, r, p4, f["off_lminegb"], f["off_y0"], _ptr(S), _ptr(y), k, None, _ptr(viol), None,
-                            None, 9, 0, 4, 64, 2)
+                            None, 9, 0, 4, 64, 2, None, None, None)
     assert rc == 0
     allF = np.asarray(spec["lmi"])
     Fy = allF[-1][None] + np.einsum("bi,ijk->bjk", y.astype(np.float64), allF[:-1])
@@ -199,7 +214,7 @@ def test_big_lmi_definiteness_filter_is_exact(emu):
     assert emu.emu_lmib_contract(_ptr(v), n, _ptr(Fp), n, p4, _ptr(S), B, None) == 0
     dk = np.full((B, n), np.nan, dtype=np.float32)
     rc = emu.emu_lmib_solve(_ptr(p.blob), n, k, r, p4, f["off_lmib"], f["off_y0"], _ptr(S), _ptr(v), n, _ptr(y), _ptr(kap),
-                            _ptr(act, _I), _ptr(dk), B, 0, 1, 64, 3)
+                            _ptr(act, _I), _ptr(dk), B, 0, 1, 64, 3, None, None, None)
     assert rc == 0
     want = np.maximum(np.maximum(lam, 0.0), kprior.astype(np.float64))
     assert np.abs(kap - want).max() <= 3e-6 * want.max()
