@@ -201,8 +201,10 @@ __device__ __forceinline__ float lb_alpha(float kap, float s, float beta, int mo
   return (mode == RAYEN_MODE_RAYEN_OLD) ? 1.0f / (expf(beta) + kap) : fminf(1.0f / kap, s);
 }
 
+// (minimum CTAs per SM: keeps the register count where the shared-memory footprint, not the register file, limits the
+// number of matrices in flight -- 128 registers at 128 threads cost one of five CTAs per SM at r = 100: 1.20 -> 1.41 ms)
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (THREADS <= 64) ? 10 : ((THREADS <= 128) ? 5 : ((THREADS <= 256) ? 2 : 1)))
     lmib_solve_kernel(const LmiBigDev P, const float* S, const float* __restrict__ v, long long ldv,
                       float* __restrict__ y, float* __restrict__ kappa_io, int* __restrict__ active_io,
                       float* __restrict__ dkappa, long long Bc, int mode, int flags, float* Sw,  // (Sw may be S itself)
