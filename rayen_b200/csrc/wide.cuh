@@ -31,10 +31,10 @@ struct WideDev {
 };
 
 // forward smem: us[n][TS] | s_norm, s_beta, s_alpha, sbest [TS each] | stag [TS] | wbest, wtag [warps][TS] |
-//               part_sq [slots][TS] | head [items][2][TS]
+//               part_sq [slots][TS] | head [items][2][TS] | ksplit [warps][64 rows][TS] (column-split partial sums)
 __host__ __device__ inline size_t wide_fwd_smem_bytes(int n, int ts) {
   return (static_cast<size_t>(n) * ts + 5 * ts + 2 * kWideWarps * ts + static_cast<size_t>(kWideSlots) * ts +
-          static_cast<size_t>(kWideRoundItems) * 2 * ts) * sizeof(float);
+          static_cast<size_t>(kWideRoundItems) * 2 * ts + static_cast<size_t>(kWideWarps) * kWideGroupRows * ts) * sizeof(float);
 }
 __host__ __device__ inline size_t wide_bwd_smem_bytes(int n) {
   // u, gz, dk: n each; t: n + 2 (+ pad); 8 words of reduction scratch
@@ -217,6 +217,13 @@ __device__ __forceinline__ void wide_dot2(const float* __restrict__ wcol2, int r
   }
 }
 
+// the same walk as a function call (the column-split branch of the forward kernel)
+template <int TS, bool BLK, bool CMP>
+__device__ __noinline__ void wide_dot2_call(const float* __restrict__ wcol2, int r_pad, int j0, int n,
+                                            const float4* __restrict__ us4, float (&tot0)[TS], float (&tot1)[TS]) {
+  wide_dot2<TS, BLK, CMP>(wcol2, r_pad, j0, n, us4, tot0, tot1);
+}
+
 // value of x[lane] for lane < TS without dynamic register indexing
 template <int TS>
 __device__ __forceinline__ float pick_lane(const float (&x)[TS], int lane) {
@@ -253,6 +260,7 @@ __global__ void __launch_bounds__(kWideThreads)
   int* wtag = reinterpret_cast<int*>(wbest + kWideWarps * TS);
   float* part_sq = wbest + 2 * kWideWarps * TS;      // [kWideSlots][TS]
   float* head = part_sq + kWideSlots * TS;           // [kWideRoundItems][2][TS]
+  float* ksplit = head + kWideRoundItems * 2 * TS;   // [kWideWarps][64][TS]
   const float4* us4 = reinterpret_cast<const float4*>(us);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* blob = P.blob;
@@ -301,12 +309,16 @@ __global__ void __launch_bounds__(kWideThreads)
     for (int rd = 0; rd < P.n_rounds; ++rd) {
       const int t0 = __ldg(rounds + 4 * rd), t1 = __ldg(rounds + 4 * rd + 1), i0 = __ldg(rounds + 4 * rd + 2),
                 i1 = __ldg(rounds + 4 * rd + 3);
-      // ---- tasks of the round: one group of 64 rows each (two per lane), dealt to the warps in order (heaviest first)
-      for (int t = t0 + warp; t < t1; t += kWideWarps) {
-        const int* tk = tasks + t * 8;
-        const int kind = __ldg(tk), row = __ldg(tk + 1), j0 = __ldg(tk + 2), idx = __ldg(tk + 3), slot = __ldg(tk + 5);
-        float acc0[TS], acc1[TS];
-        wide_dot2<TS, BLK, CMP>(wt + row + 2 * lane, P.r_pad, j0, n, us4, acc0, acc1);
+      // ---- tasks of the round: one group of 64 rows each (two per lane), dealt to the warps in order (heaviest first).
+      // A round with fewer tasks than half the warps (few rows in a wide space: 1 ... 100 rows at n = 10^4) splits every
+      // task's COLUMN range over `split` warps -- otherwise one warp walks all n columns with eight loads in flight while
+      // the others wait at the barrier (measured at 100 rows x 10000: barrier stalls 30 per issue, 4.6 ms per 2000
+      // samples) -- and adds the partial sums in a fixed order.  The split depends only on the plan: a sample's arithmetic
+      // does not depend on its tile.
+      const int nt = t1 - t0;
+      const int split = (nt > 0 && 2 * nt <= kWideWarps) ? kWideWarps / nt : 1;
+      // what a warp does with the finished dot products of a task (acc0 / acc1: rows 2 lane, 2 lane + 1 of the group)
+      auto consume = [&](int kind, int idx, int slot, float (&acc0)[TS], float (&acc1)[TS]) {
         if (kind == 1) {
           // a lane's rows arrive in ascending order: strict > keeps the lowest
 #pragma unroll
@@ -336,6 +348,54 @@ __global__ void __launch_bounds__(kWideThreads)
               head[(il * 2 + 1) * TS + s] = acc1[s];
             }
           }
+        }
+      };
+      if (split > 1) {
+        // (the column walk of this branch is a CALL, wide_dot2_call: a second inlined copy of it cost registers in the
+        // common path -- 64 -> 127 at TS = 8 -- and a shared call site de-optimised that path's loop: 3.9 -> 7.3 ms at
+        // 500 x 10000)
+        const int ti = warp / split, q = warp - ti * split;
+        const bool takes = ti < nt;          // (nt * split may be less than the number of warps)
+        int kind = 0, idx = 0, slot = 0;
+        float acc0[TS], acc1[TS];
+        if (takes) {
+          const int* tk = tasks + (t0 + ti) * 8;
+          kind = __ldg(tk);
+          idx = __ldg(tk + 3);
+          slot = __ldg(tk + 5);
+          const int row = __ldg(tk + 1), j0 = __ldg(tk + 2);
+          // slice q of [j0, n), whole blocks of 16 columns (the unit of the compensated sums)
+          const int len = ((n - j0 + split - 1) / split + 15) & ~15;
+          const int jlo = (j0 + q * len < n) ? j0 + q * len : n, jhi = (jlo + len < n) ? jlo + len : n;
+          wide_dot2_call<TS, BLK, CMP>(wt + row + 2 * lane, P.r_pad, jlo, jhi, us4, acc0, acc1);
+          if (q != 0) {
+            float* mine = ksplit + (warp * kWideGroupRows + 2 * lane) * TS;
+#pragma unroll
+            for (int s = 0; s < TS; ++s) {
+              mine[s] = acc0[s];
+              mine[TS + s] = acc1[s];
+            }
+          }
+        }
+        __syncthreads();
+        if (takes && q == 0) {
+          for (int qq = 1; qq < split; ++qq) {
+            const float* other = ksplit + ((warp + qq) * kWideGroupRows + 2 * lane) * TS;
+#pragma unroll
+            for (int s = 0; s < TS; ++s) {
+              acc0[s] += other[s];
+              acc1[s] += other[TS + s];
+            }
+          }
+          consume(kind, idx, slot, acc0, acc1);
+        }
+      } else {
+        for (int t = t0 + warp; t < t1; t += kWideWarps) {
+          const int* tk = tasks + t * 8;
+          const int kind = __ldg(tk), row = __ldg(tk + 1), j0 = __ldg(tk + 2), idx = __ldg(tk + 3), slot = __ldg(tk + 5);
+          float acc0[TS], acc1[TS];
+          wide_dot2<TS, BLK, CMP>(wt + row + 2 * lane, P.r_pad, j0, n, us4, acc0, acc1);
+          consume(kind, idx, slot, acc0, acc1);
         }
       }
       __syncthreads();

@@ -24,6 +24,7 @@ struct float4 { float x, y, z, w; };
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __align__(x) __attribute__((aligned(x)))
 #define __shared__
