@@ -326,3 +326,30 @@ def test_pruning_bound_uncentred_form_would_fail():
         ub = ub + np.float32(1e-4) * np.abs(ub)
         bad += int((ub.astype(np.float64) < lam).sum())
     assert bad > 0
+
+
+def test_big_lmi_tensor_core_operand_decodes_to_the_packed_matrices():
+    """Section LMIBT (the B operand of lmi_big_tc.cuh): per (panel of 128 entries, slice of 32 coordinates) a TF32-split
+    pair of [128 x 32] tiles in the operand layout [k/4][row/8][row%8][k%4].  Decoded here and compared with section LMIB:
+    hi + lo reproduces F~z' to the residual of the split (2^-22 relative), both halves are TF32-representable, and the
+    padding (entries beyond lmib_p4, coordinates beyond n) is zero."""
+    spec = synthetic.wide_spec(70, 30, 1, 0, 0, 3, seed=4, r=20)       # n = 67: three slices, the last one ragged
+    cs = synthetic.build_constraints(spec)
+    p = plan.build_plan_from_constraints(cs)
+    f = p.fields
+    n, p4, NP, KS = f["n"], f["lmib_p4"], f["lmibt_panels"], f["lmibt_slices"]
+    assert NP == -(-p4 // 128) and KS == -(-n // 32) and f["off_lmibt"] > 0
+    Fb = p.blob[f["off_lmib"]:f["off_lmib"] + n * p4].reshape(n, p4)
+    T = p.blob[f["off_lmibt"]:f["off_lmibt"] + NP * KS * 2 * 4096].reshape(NP, KS, 2, 8, 16, 8, 4)   # [q][s][hl][kc][rg][r8][k4]
+    hi = T[:, :, 0].transpose(0, 3, 4, 1, 2, 5).reshape(NP * 128, KS * 32)      # [q, rg, r8][s, kc, k4]
+    lo = T[:, :, 1].transpose(0, 3, 4, 1, 2, 5).reshape(NP * 128, KS * 32)
+    for part in (hi, lo):
+        assert np.all((part.view(np.uint32) & np.uint32(0x1FFF)) == 0)          # 10-bit mantissa: TF32-representable
+    full = np.zeros((NP * 128, KS * 32), dtype=np.float64)
+    full[:p4, :n] = Fb.T
+    err = np.abs(hi.astype(np.float64) + lo.astype(np.float64) - full)
+    assert err.max() <= 2.0 ** -21 * np.abs(full).max()
+    assert not hi[p4:].any() and not lo[p4:].any() and not hi[:, n:].any() and not lo[:, n:].any()
+    # narrow subspaces keep the FP32 GEMM only
+    small = plan.build_plan_from_constraints(synthetic.build_constraints(synthetic.random_spec(k=6, r=40, seed=1)))
+    assert small.fields["lmibt_panels"] == 0 and small.fields["off_lmibt"] == 0
