@@ -118,6 +118,15 @@ __device__ __forceinline__ float lw_sqrt(float x) {
 #ifndef LW_SMEM_REDUCE
 #define LW_SMEM_REDUCE 1
 #endif
+// the read half of lw_sum_chain: the 32 addends are already in `buf` (stored before the last __syncwarp)
+__device__ __forceinline__ float lw_sum_read(const float* __restrict__ buf) {
+  float4 a[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c] = lw_ld4(buf + 4 * c);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c].x = (a[c].x + a[c].y) + (a[c].z + a[c].w);
+  return ((a[0].x + a[1].x) + (a[2].x + a[3].x)) + ((a[4].x + a[5].x) + (a[6].x + a[7].x));
+}
 __device__ __forceinline__ float lw_sum_chain(float x, float* __restrict__ buf, int lane) {
 #if LW_SMEM_REDUCE
   buf[lane] = x;
@@ -301,7 +310,9 @@ struct LwSolver {
       __syncwarp();
       const float xk = rb[lane];  // entry (k, lane) = (lane, k)
       const float xk1 = rb[k + 1];
-      const float tail2 = lw_sum_chain((lane > k + 1) ? xk * xk : 0.f, scr + kLwScrRed, lane);
+      // the squares of this row's tail were stored by whoever wrote the row (the previous step's update, or
+      // tridiagonalize() for row 0): one store + barrier less on the step's dependent chain
+      const float tail2 = lw_sum_read(scr + kLwScrRed);
       const float sigma = fmaf(xk1, xk1, tail2);
       const float rt = lw_sqrt(sigma);
       const float alpha = (xk1 >= 0.f) ? -rt : rt;
@@ -345,7 +356,10 @@ struct LwSolver {
           const int i = R0 + 4 * c + ii;
           const float nv = fmaf(-vr[4 * c + ii], wj, fmaf(-wr[ii], vj, W[i]));
           W[i] = nv;
-          if (i > R0 && i <= R0 + 8 && i == k + 1) nrb[lane] = nv;  // row k + 1 becomes the next pivot row
+          if (i > R0 && i <= R0 + 8 && i == k + 1) {  // row k + 1 becomes the next pivot row
+            nrb[lane] = nv;
+            scr[kLwScrRed + lane] = (lane > k + 2) ? nv * nv : 0.f;  // ... and its tail's squares go with it
+          }
         }
       }
     }
@@ -354,6 +368,7 @@ struct LwSolver {
   // Householder tridiagonalisation: diagonal -> sd, sub-diagonal -> se (se[31] = 0), tau_k = 2 / |v_k|^2 -> stau
   __device__ __forceinline__ void tridiagonalize() {
     scr[kLwScrRb + lane] = W[0];
+    scr[kLwScrRed + lane] = (lane > 1) ? W[0] * W[0] : 0.f;
     householder_stage<0>();
     householder_stage<1>();
     householder_stage<2>();
